@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- TimesBlock forward windows/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload elec] [--impl native|reference]
+
+A "step" is one forward of the TimesBlock stack (n_layers x (period search ->
+fold -> Inception bank -> weighted aggregate + residual + shared LayerNorm)) over
+one batch of synthetic pre-embedded windows that are already resident in HBM.
+`value` = windows/s of that loop (whole job, all ranks).  `e2e` = windows/s of
+the public API call a user makes (TimesNet.forward + NB-NLL) with HOST buffers:
+each step copies x/y from pinned host memory, runs the forward and reads the
+NLL back.  N > 1: one process per GPU (torchrun), weak scaling -- every rank
+holds the full per-GPU batch, the only collective is the all-reduce of the
+batch-summed amplitude spectrum inside the shared period search.
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port:
+same ATen CPU kernels the reference's PyTorch code dispatches to; the reference
+itself is not importable on the GPU box) on the same workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "flow-timesnet_b200"))
+
+import torch  # noqa: E402
+
+import flowtimes_synth as syn  # noqa: E402
+
+METRIC = "timesblock_forward_windows_per_sec"
+UNIT = "windows/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="elec", choices=["elec", "etth1", "traffic", "mid", "toy"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 100 ms through NVML."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, v in names.items():
+                    if bits & v:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def workload_of(args) -> syn.Workload:
+    return syn.WORKLOADS[args.workload]
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- #
+# reference arm / cpu baseline: the oracle port on host cores
+# --------------------------------------------------------------------------- #
+def cpu_forward_factory(wl: syn.Workload, sample_B: int):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import flowtimes_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = model_state(wl, device="cpu")
+    cfg = orc.ModelCfg(wl.T, wl.H, wl.d_model, wl.n_layers, wl.k_periods, wl.mode, "gelu", wl.min_period_threshold)
+    x = syn.planted_series(sample_B, wl.T, wl.N, seed=0)
+    y = syn.poisson_targets(sample_B, wl.H, wl.N, 5.0, seed=2)
+
+    def step():
+        with torch.no_grad():
+            r, d = orc.timesnet_forward(x, w, cfg)
+            return float(orc.nb_nll(y, r, d))
+    return step
+
+
+def model_state(wl: syn.Workload, device):
+    """Seeded TimesNet state dict (keys = reference state_dict keys) for the workload."""
+    shapes = dict(syn.stack_shapes(wl))
+    C, N, L, H = wl.d_model, wl.N, wl.T, wl.H
+    ctx = 32
+    shapes.update({
+        "embedding.gate": (1, 1, C), "embedding.value_embedding.weight": (C, N), "embedding.value_embedding.bias": (C,),
+        "embedding.aux_norm.weight": (C,), "embedding.aux_norm.bias": (C,),
+        "forecast_time_proj.weight": (H, L), "forecast_time_proj.bias": (H,),
+        "mu_head.weight": (N, C), "mu_head.bias": (N,), "sigma_head.weight": (N, C), "sigma_head.bias": (N,),
+        "series_embedding.weight": (N, ctx), "context_norm.weight": (ctx,), "context_norm.bias": (ctx,),
+        "late_bias_norm.weight": (ctx,), "late_bias_norm.bias": (ctx,),
+        "late_bias_head.weight": (H, ctx), "late_bias_head.bias": (H,), "late_bias_gate": (1, H, 1),
+        "pre_embedding_norm.weight": (ctx + 1,), "pre_embedding_norm.bias": (ctx + 1,),
+    })
+    sd = syn.seeded_state(shapes, seed=0)
+    return {k: v.to(device) for k, v in sd.items()}
+
+
+def run_reference(args):
+    """Reference arm: CPU path of the reference algorithm, full TimesNet.forward + NB-NLL."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload_of(args)
+    sample_B = min(wl.B, 16)
+    step = cpu_forward_factory(wl, sample_B)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample_B / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, **wl.as_dict(), "scope": "TimesNet.forward + NB-NLL on host cores",
+                   "sample_windows_per_step": sample_B},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_B} of {wl.B} windows per step, full forward + NLL, fp32, {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+def run_native(args):
+    import torch.distributed as dist
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.losses import negative_binomial_nll
+    from timesnet_forecast.models.timesnet import TimesNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    nv.load()
+    wl = workload_of(args)
+    sdt = syn.torch_dtype(wl.dtype)
+
+    model = TimesNet(input_len=wl.T, pred_len=wl.H, d_model=wl.d_model, n_layers=wl.n_layers, k_periods=wl.k_periods,
+                     kernel_set=[list(k) for k in wl.kernel_set], dropout=0.0, activation="gelu", mode=wl.mode,
+                     d_ff=wl.ff, bottleneck_ratio=wl.bottleneck_ratio, min_period_threshold=wl.min_period_threshold,
+                     use_checkpoint=False, stack_dtype=sdt)
+    x_host = syn.planted_series(wl.B, wl.T, wl.N, seed=rank).pin_memory()
+    y_host = syn.poisson_targets(wl.B, wl.H, wl.N, 5.0, seed=100 + rank).pin_memory()
+    model(x_host[:1].to(dev))                                  # lazy build
+    model.eval()
+    model.load_state_dict(model_state(wl, dev), strict=True)
+    model.check_finite = False                                 # keep the forward free of host syncs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------- resident scope: TimesBlock stack on pre-embedded features ----------
+    n_rot = max(2, int(2 * 126e6 / (wl.B * wl.T * wl.d_model * (2 if sdt == torch.bfloat16 else 4))) + 1)
+    n_rot = min(n_rot, 64)
+    feats = [syn.planted_features(wl.B, wl.T, wl.d_model, seed=1000 * rank + i % 4).to(sdt).to(dev)
+             for i in range(n_rot)]
+
+    def stack_step(i):
+        seq = feats[i % n_rot]
+        for blk in model.blocks:
+            seq = blk.forward_norm(seq, model.layer_norm)
+        return seq
+
+    for i in range(max(3, args.warmup)):
+        stack_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    nv.timing_enable(True)
+    launches0 = nv.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        stack_step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = nv.launch_count() - launches0
+    conv_ms, conv_calls = nv.timing_read(nv.FAM_CONV)
+    spec_ms, spec_calls = nv.timing_read(nv.FAM_SPECTRUM)
+    agg_ms, agg_calls = nv.timing_read(nv.FAM_AGGREGATE)
+    nv.timing_enable(False)
+    clocks = sampler.finish()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = wl.B * world / (ms_step * 1e-3)
+    group_periods = [list(b._last_plan.host().grp_period[: b._last_plan.host().n_groups]) for b in model.blocks]
+
+    # ---------- e2e scope: public API with host buffers ----------
+    e2e = None
+    if not args.no_e2e:
+        xd = torch.empty_like(x_host, device=dev)
+        yd = torch.empty_like(y_host, device=dev)
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            xd.copy_(x_host, non_blocking=True)
+            yd.copy_(y_host, non_blocking=True)
+            rate, disp = model(xd)
+            loss = negative_binomial_nll(yd, rate, disp)
+            loss_host.copy_(loss, non_blocking=True)
+
+        for _ in range(max(3, args.warmup)):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": wl.B * world / (te.item() / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+               "ms_per_step": te.item() / args.steps, "scope": "TimesNet.forward + negative_binomial_nll",
+               "loss": float(loss_host)}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        # dominant kernel: the Inception conv chain (tensor-pipe bound by design)
+        flops_fwd = sum(syn.stack_algorithmic_flops(syn.Workload(**{**wl.__dict__, "n_layers": 1}), gp)
+                        for gp in group_periods)              # as-written conv FLOPs, SURVEY.md 8(d) K3 row
+        flops_per_call = flops_fwd / max(1, len(group_periods))
+        conv_avg_ms = conv_ms / max(1, conv_calls)
+        achieved = flops_per_call / (conv_avg_ms * 1e-3) / 1e12 if conv_avg_ms > 0 else 0.0
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (Inception chain of one TimesBlock)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                    "flops_per_launch_group": flops_per_call, "avg_ms": conv_avg_ms, "calls": conv_calls,
+                    "note": "as-written conv FLOPs of one TimesBlock / CUDA-event time of its conv launches; "
+                            "math runs on fp32 CUDA cores in this round (no tensor pipe yet)",
+                    "share_of_step": {"conv": conv_ms / ms_total, "spectrum": spec_ms / ms_total,
+                                      "aggregate": agg_ms / ms_total}}
+        e_bytes = 2 if sdt == torch.bfloat16 else 4
+        hbm = []
+        for name, ms_f, calls, per_call in (
+                ("spectrum", spec_ms, spec_calls, wl.B * wl.T * wl.d_model * e_bytes + 4 * (wl.T // 2 + 1)),
+                ("aggregate", agg_ms, agg_calls,
+                 wl.B * wl.T * wl.d_model * e_bytes * (statistics.mean(len(g) for g in group_periods) + 2))):
+            if calls:
+                gbs = per_call / (ms_f / calls * 1e-3) / 1e9
+                hbm.append({"kernel": name, "achieved_GBs": gbs, "frac": gbs / float(peaks["hbm_gbs"]),
+                            "avg_ms": ms_f / calls, "algorithmic_bytes": per_call})
+        roofline["hbm_kernels"] = hbm
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample_B = min(wl.B, 8)
+            step = cpu_forward_factory(wl, sample_B)
+            step()
+            t0 = time.perf_counter()
+            n = 0
+            while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+                step()
+                n += 1
+            dt = (time.perf_counter() - t0) / n
+            cores = torch.get_num_threads()
+            cpu_baseline = {"value": sample_B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{n} forwards of {sample_B}/{wl.B} windows, TimesNet.forward + NLL, fp32, "
+                                      f"{cores} threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": {"workload": wl.name, **wl.as_dict(), "global_batch": wl.B * world, "parallelism": f"dp{world}",
+                       "scope": "TimesBlock stack (n_layers x (TimesBlock + shared LayerNorm)), features resident",
+                       "l2": f"inputs rotate over {n_rot} buffers (> 2x L2); fp32 intermediates >> L2",
+                       "selected_periods": group_periods},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,72 @@
+"""Build libflowtimes.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python flow-timesnet_b200/build.py [--force]
+
+No torch, no pybind: the library exposes plain `extern "C"` entry points
+(include/flowtimes.h) and is loaded with ctypes.  nvcc cross-compiles without a
+GPU, so this also is the CPU-side "does it build" check.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "lib" / "libflowtimes.so"
+INCLUDE = HERE.parent / "include"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xptxas", "-v",
+]
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    objs = []
+    procs = []
+    for src in sources():
+        obj = LIB.parent / (src.stem + ".o")
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src.name}\n{out}")
+        if p.returncode != 0:
+            failed = True
+    (LIB.parent / "build.log").write_text("\n".join(log))
+    if failed or verbose:
+        print("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed; see flow-timesnet_b200/lib/build.log")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    subprocess.run(link, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

@@ -1,0 +1,149 @@
+// Shared helpers for libflowtimes (sm_100a).  Error plumbing, dtype access,
+// exact-math activations and the plan geometry helpers used by both the
+// device kernels and the host-side plan builder.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/flowtimes.h"
+
+namespace ftn {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define FTN_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::ftn::set_error(__VA_ARGS__);  \
+      return 1;                       \
+    }                                 \
+  } while (0)
+
+#define FTN_CUDA(call)                                   \
+  do {                                                   \
+    if (::ftn::check_cuda((call), #call)) return 2;      \
+  } while (0)
+
+#define FTN_LAUNCH_CHECK(name)                                     \
+  do {                                                             \
+    ::ftn::count_launch();                                         \
+    if (::ftn::check_cuda(cudaGetLastError(), name)) return 3;     \
+  } while (0)
+
+void count_launch();   // every kernel this library enqueues is counted (bench.py "gpu_launches")
+
+// Optional per-call CUDA-event timing of one kernel family (bench.py roofline leg):
+// TimedScope records an event pair on the launch stream around the enclosed launches.
+struct TimedScope {
+  TimedScope(int family, cudaStream_t st);
+  ~TimedScope();
+  int slot;
+  cudaStream_t st;
+};
+enum { FTN_FAM_SPECTRUM = 0, FTN_FAM_CONV = 1, FTN_FAM_AGGREGATE = 2, FTN_FAM_COUNT = 3 };
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached per process (current device at first call)
+
+// ---- dtype access -------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// round-trip through the activation dtype (models torch's `.to(x.dtype)`)
+template <typename T>
+__device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+// ---- exact-ish activations (fp32 device math, no fast intrinsics) --------------
+__device__ __forceinline__ float gelu_erf(float v) {
+  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  return act == FTN_ACT_RELU ? fmaxf(v, 0.0f) : gelu_erf(v);
+}
+// F.softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplus20(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
+
+// ---- plan geometry (host + device) ---------------------------------------------
+// Default PeriodGrouper semantics (timesnet.py:513-557, log_base/max_unique unset):
+// drop p <= 0, p outside [min_p, max_p], cycles < 2; merge exact duplicates;
+// groups ascend by period; mapping[candidate] = group.
+// `mean_amp[i]` (may be null) picks the canonical member of a duplicate group.
+__host__ __device__ inline void plan_group_default(FtnPeriodPlan* pl, const int64_t* cand, int k,
+                                                   int L, int min_p, int max_p,
+                                                   const float* mean_amp) {
+  pl->seq_len = L;
+  pl->n_groups = 0;
+  int grp_p[FTN_MAX_K];
+  int G = 0;
+  for (int i = 0; i < FTN_MAX_K; ++i) pl->mapping[i] = -1;
+  bool ok[FTN_MAX_K];
+  for (int i = 0; i < k; ++i) {
+    int64_t p = cand[i];
+    bool v = p > 0;
+    if (min_p > 0 && p < min_p) v = false;
+    if (max_p > 0 && p > max_p) v = false;
+    if (v) {
+      int pad = (int)((p - (L % p)) % p);
+      int cyc = (int)((L + pad) / p);
+      if (cyc < 2) v = false;
+    }
+    ok[i] = v;
+    if (!v) continue;
+    bool seen = false;
+    for (int g = 0; g < G; ++g) seen = seen || (grp_p[g] == (int)p);
+    if (!seen) grp_p[G++] = (int)p;
+  }
+  // insertion sort ascending (G <= 16)
+  for (int a = 1; a < G; ++a) {
+    int v = grp_p[a];
+    int b = a - 1;
+    while (b >= 0 && grp_p[b] > v) { grp_p[b + 1] = grp_p[b]; --b; }
+    grp_p[b + 1] = v;
+  }
+  int off = 0;
+  for (int g = 0; g < G; ++g) {
+    int p = grp_p[g];
+    int pad = (p - (L % p)) % p;
+    pl->grp_period[g] = p;
+    pl->grp_pad[g] = pad;
+    pl->grp_cycles[g] = (L + pad) / p;
+    pl->grp_row_off[g] = off;
+    off += L + pad;
+    int canon = -1;
+    float best = 0.f;
+    for (int i = 0; i < k; ++i) {
+      if (!ok[i] || (int)cand[i] != p) continue;
+      pl->mapping[i] = g;
+      float a = mean_amp ? mean_amp[i] : 0.f;
+      if (canon < 0 || a > best) { canon = i; best = a; }
+    }
+    pl->grp_canon[g] = canon;
+  }
+  for (int g = G; g < FTN_MAX_K; ++g) {
+    pl->grp_period[g] = 0; pl->grp_pad[g] = 0; pl->grp_cycles[g] = 0; pl->grp_canon[g] = -1;
+    pl->grp_row_off[g] = off;
+  }
+  pl->grp_row_off[FTN_MAX_K] = off;
+  pl->n_groups = G;
+  pl->total_rows_per_window = off;
+}
+
+}  // namespace ftn

@@ -1,0 +1,317 @@
+// K5 (LowRankTemporalContext add), K6 (Negative-Binomial head + NLL) and the
+// small dense helpers for the callers either side of the TimesBlock stack
+// (Linear layers, DataEmbedding combine).  All fp32 device math: erf GELU is not
+// used here, softplus uses log1pf(expf()) with torch's threshold 20, the NLL uses
+// lgammaf / log1pf (SURVEY.md section 7 "hard parts": no fast approximations).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace ftn {
+
+// ---------------------------------------------------------------------------
+// generic SIMT GEMM:  C[b][m][n] = sum_k A[b][m][k] * Bm[b][k][n] (+ bias)
+//   A: fp32 row-major (lda), Bm: TB (fp32 or bf16), element (k, n) at
+//   TRANS_B ? Bm[n*ldb + k] : Bm[k*ldb + n].  bias_mode 0 none, 1 per-n, 2 per-m.
+// 64x64 tile, 256 threads, 4x4 register tile.
+// ---------------------------------------------------------------------------
+template <typename TB, bool TRANS_B>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, int lda, long long strideA, const TB* __restrict__ Bm, int ldb,
+             long long strideB, float* __restrict__ Cm, int ldc, long long strideC, int M, int N, int K,
+             const float* __restrict__ bias, int bias_mode) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float As[TM][TK + 1];
+  __shared__ __align__(16) float Bs[TK][TN + 4];
+  const int bz = blockIdx.z;
+  A += (size_t)bz * strideA;
+  Bm += (size_t)bz * strideB;
+  Cm += (size_t)bz * strideC;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int i = tid; i < TM * TK; i += 256) {
+      int r = i / TK, k = i - r * TK;
+      float v = 0.f;
+      if (m0 + r < M && k0 + k < K) v = A[(size_t)(m0 + r) * lda + k0 + k];
+      As[r][k] = v;
+    }
+    for (int i = tid; i < TK * TN; i += 256) {
+      int k, n;
+      if (TRANS_B) { n = i / TK; k = i - n * TK; } else { k = i / TN; n = i - k * TN; }
+      float v = 0.f;
+      if (k0 + k < K && n0 + n < N)
+        v = TRANS_B ? to_f32<TB>(Bm[(size_t)(n0 + n) * ldb + k0 + k]) : to_f32<TB>(Bm[(size_t)(k0 + k) * ldb + n0 + n]);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias_mode == 1) v += bias[n];
+      else if (bias_mode == 2) v += bias[m];
+      Cm[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: out = x + scale * (basis . coeff - mean_t(basis . coeff))
+// thread <-> flattened (window, series); basis tile in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+context_add_kernel(const float* __restrict__ x, const float* __restrict__ coeff, const float* __restrict__ basis,
+                   const float* __restrict__ scale, int B, int L, int N, int R, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* bs = sm;                 // [L][R]
+  float* colmean = sm + (size_t)L * R;   // [R]
+  float* cf = colmean + R;        // [128][R+1]
+  for (int i = threadIdx.x; i < L * R; i += blockDim.x) bs[i] = basis[i];
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < L; ++t) s += bs[t * R + r];
+    colmean[r] = s / (float)L;
+  }
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < (long long)B * N;
+  float* my = cf + (size_t)threadIdx.x * (R + 1);
+  if (live)
+    for (int r = 0; r < R; ++r) my[r] = coeff[(size_t)idx * R + r];
+  __syncthreads();
+  if (!live) return;
+  const int b = (int)(idx / N), n = (int)(idx - (long long)b * N);
+  float m = 0.f;
+  for (int r = 0; r < R; ++r) m = fmaf(colmean[r], my[r], m);
+  const float sc = scale[0];
+  for (int t = 0; t < L; ++t) {
+    float v = 0.f;
+    for (int r = 0; r < R; ++r) v = fmaf(bs[t * R + r], my[r], v);
+    size_t o = ((size_t)b * L + t) * N + n;
+    out[o] = x[o] + (v - m) * sc;
+  }
+}
+
+// DataEmbedding combine: out = value + gate[c] * aux[(b,) t, c]
+template <typename TO>
+__global__ void embed_combine_kernel(const float* __restrict__ value, const float* __restrict__ aux,
+                                     const float* __restrict__ gate, int aux_batched, long long total,
+                                     int L, int C, TO* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long bt = i / C;
+  long long ai = aux_batched ? i : ((bt % L) * C + c);
+  out[i] = from_f32<TO>(value[i] + gate[c] * aux[ai]);
+}
+
+// ---------------------------------------------------------------------------
+// K6 epilogue: rate / dispersion from the two head pre-activations
+// ---------------------------------------------------------------------------
+__global__ void nb_epilogue_kernel(float* __restrict__ rate, float* __restrict__ disp,
+                                   const float* __restrict__ hist, const float* __restrict__ late,
+                                   const float* __restrict__ late_gate, const float* __restrict__ floor_n,
+                                   int B, int steps, int N, int32_t* __restrict__ flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * steps * N;
+  int bad = 0;
+  if (i < total) {
+    int n = (int)(i % N);
+    long long bh = i / N;
+    int h = (int)(bh % steps);
+    long long b = bh / steps;
+    float pre = rate[i] + hist[i];                                      // mu_head(h) + history_tail (:2079)
+    if (late) pre += late_gate[h] * late[((size_t)b * N + n) * steps + h];   // gate * bias^T (:2041-2047)
+    float r = softplus20(pre) + 1e-6f;                                  // :2081-2085
+    float d = softplus20(disp[i]) + floor_n[n] + 1e-6f;                 // :2088-2093
+    rate[i] = r;
+    disp[i] = d;
+    if (!isfinite(r) || r <= 0.f) bad |= 1;                             // :2094
+    if (!isfinite(d) || d <= 0.f) bad |= 2;                             // :2096
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------
+// NB NLL: masked mean of -ll  (losses.py:27-58)
+// ---------------------------------------------------------------------------
+constexpr int kNllBlocks = 1024;
+
+__global__ void __launch_bounds__(256)
+nb_nll_partial_kernel(const float* __restrict__ y, const float* __restrict__ rate, const float* __restrict__ disp,
+                      const uint8_t* __restrict__ mask, long long count, float eps, float* __restrict__ partial) {
+  float s = 0.f, wsum = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    float yv = y[i];
+    yv = (yv != yv) ? yv : fmaxf(yv, 0.f);           // torch.clamp propagates NaN
+    float a = disp[i];
+    a = (a != a) ? a : fmaxf(a, eps);
+    float mu = rate[i];
+    mu = (mu != mu) ? mu : fmaxf(mu, eps);
+    float l1p = log1pf(a * mu);
+    float inv = 1.0f / a;
+    float ll = lgammaf(yv + inv) - lgammaf(inv) - lgammaf(yv + 1.0f) + inv * (-l1p)
+               + yv * (logf(a) + logf(mu) - l1p);
+    bool valid = isfinite(yv) && isfinite(mu) && isfinite(a);
+    if (mask) valid = valid && (mask[i] != 0);
+    float w = valid ? 1.f : 0.f;
+    s += ll * w;                                     // NaN * 0 = NaN, like the reference
+    wsum += w;
+  }
+  __shared__ float ss[256], sw[256];
+  ss[threadIdx.x] = s;
+  sw[threadIdx.x] = wsum;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      sw[threadIdx.x] += sw[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = ss[0];
+    partial[2 * blockIdx.x + 1] = sw[0];
+  }
+}
+
+__global__ void __launch_bounds__(256) nb_nll_final_kernel(const float* __restrict__ partial, int nblocks,
+                                                          float* __restrict__ out) {
+  __shared__ double ss[256], sw[256];
+  double s = 0.0, w = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    s += (double)partial[2 * i];
+    w += (double)partial[2 * i + 1];
+  }
+  ss[threadIdx.x] = s;
+  sw[threadIdx.x] = w;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      sw[threadIdx.x] += sw[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(-ss[0] / fmax(sw[0], 1.0));
+}
+
+static int launch_sgemm_f32(const float* A, int lda, long long sA, const float* Bm, int ldb, long long sB,
+                            float* C, int ldc, long long sC, int M, int N, int K, int batch, bool transB,
+                            const float* bias, int bias_mode, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
+  if (transB)
+    sgemm_kernel<float, true><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+  else
+    sgemm_kernel<float, false><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+  FTN_LAUNCH_CHECK("sgemm_kernel");
+  return 0;
+}
+
+}  // namespace ftn
+
+using namespace ftn;
+
+extern "C" int ftn_linear(const float* a, const float* w, const float* bias, int M, int K, int N, float* out,
+                          void* stream) {
+  FTN_REQUIRE(a && w && out, "ftn_linear: null pointer");
+  FTN_REQUIRE(M > 0 && K > 0 && N > 0, "ftn_linear: bad sizes M=%d K=%d N=%d", M, K, N);
+  return launch_sgemm_f32(a, K, 0, w, K, 0, out, N, 0, M, N, K, 1, true, bias, bias ? 1 : 0, as_stream(stream));
+}
+
+extern "C" int ftn_context_add(const float* x, const float* coeff, const float* basis, const float* scale, int B,
+                               int L, int N, int R, float* out, void* stream) {
+  FTN_REQUIRE(x && coeff && basis && scale && out, "ftn_context_add: null pointer");
+  FTN_REQUIRE(B > 0 && L > 0 && N > 0 && R > 0, "ftn_context_add: bad sizes");
+  size_t smem = ((size_t)L * R + R + 128 * (size_t)(R + 1)) * sizeof(float);
+  FTN_REQUIRE(smem <= 200 * 1024, "ftn_context_add: L*R=%d too large for shared memory", L * R);
+  if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(context_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long total = (long long)B * N;
+  context_add_kernel<<<(unsigned)((total + 127) / 128), 128, smem, as_stream(stream)>>>(x, coeff, basis, scale, B, L, N, R, out);
+  FTN_LAUNCH_CHECK("context_add_kernel");
+  return 0;
+}
+
+extern "C" int ftn_embed_combine(const float* value, const float* aux, const float* gate, int aux_batched, int B,
+                                 int L, int C, int dtype_out, void* out, void* stream) {
+  FTN_REQUIRE(value && aux && gate && out, "ftn_embed_combine: null pointer");
+  FTN_REQUIRE(dtype_out == FTN_F32 || dtype_out == FTN_BF16, "ftn_embed_combine: unsupported dtype %d", dtype_out);
+  long long total = (long long)B * L * C;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype_out == FTN_F32)
+    embed_combine_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(value, aux, gate, aux_batched, total, L, C, (float*)out);
+  else
+    embed_combine_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(value, aux, gate, aux_batched, total, L, C,
+                                                                              (__nv_bfloat16*)out);
+  FTN_LAUNCH_CHECK("embed_combine_kernel");
+  return 0;
+}
+
+extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
+                           const float* bt, const float* Wmu, const float* bmu, const float* Wsg, const float* bsg,
+                           const float* hist, const float* late, const float* late_gate, const float* floor_n,
+                           float* rate, float* disp, int32_t* flags, float* workspace, void* stream) {
+  FTN_REQUIRE(seq && Wt && bt && Wmu && bmu && Wsg && bsg && hist && floor_n && rate && disp && flags && workspace,
+              "ftn_nb_head: null pointer");
+  FTN_REQUIRE((late == nullptr) == (late_gate == nullptr), "ftn_nb_head: late and late_gate must come together");
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_nb_head: unsupported dtype %d", dtype);
+  FTN_REQUIRE(B > 0 && L > 0 && C > 0 && steps > 0 && N > 0, "ftn_nb_head: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  // hidden[b] (steps x C) = Wt (steps x L) . seq[b] (L x C) + bt[h]
+  dim3 grid((C + 63) / 64, (steps + 63) / 64, B);
+  if (dtype == FTN_F32)
+    sgemm_kernel<float, false><<<grid, 256, 0, st>>>(Wt, L, 0, (const float*)seq, C, (long long)L * C, workspace, C,
+                                                     (long long)steps * C, steps, C, L, bt, 2);
+  else
+    sgemm_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(Wt, L, 0, (const __nv_bfloat16*)seq, C, (long long)L * C,
+                                                             workspace, C, (long long)steps * C, steps, C, L, bt, 2);
+  FTN_LAUNCH_CHECK("sgemm_kernel(time_proj)");
+  const int M = B * steps;
+  if (int rc = launch_sgemm_f32(workspace, C, 0, Wmu, C, 0, rate, N, 0, M, N, C, 1, true, bmu, 1, st)) return rc;
+  if (int rc = launch_sgemm_f32(workspace, C, 0, Wsg, C, 0, disp, N, 0, M, N, C, 1, true, bsg, 1, st)) return rc;
+  long long total = (long long)M * N;
+  nb_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B, steps, N, flags);
+  FTN_LAUNCH_CHECK("nb_epilogue_kernel");
+  return 0;
+}
+
+extern "C" int ftn_nb_nll(const float* y, const float* rate, const float* disp, const uint8_t* mask, int64_t count,
+                          float eps, float* partial, float* out, void* stream) {
+  FTN_REQUIRE(y && rate && disp && partial && out, "ftn_nb_nll: null pointer");
+  FTN_REQUIRE(count >= 0, "ftn_nb_nll: negative count");
+  cudaStream_t st = as_stream(stream);
+  int blocks = (int)((count + 255) / 256);
+  blocks = blocks < 1 ? 1 : (blocks > kNllBlocks ? kNllBlocks : blocks);
+  nb_nll_partial_kernel<<<blocks, 256, 0, st>>>(y, rate, disp, mask, count, eps, partial);
+  FTN_LAUNCH_CHECK("nb_nll_partial_kernel");
+  nb_nll_final_kernel<<<1, 256, 0, st>>>(partial, blocks, out);
+  FTN_LAUNCH_CHECK("nb_nll_final_kernel");
+  return 0;
+}

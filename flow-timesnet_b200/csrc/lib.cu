@@ -1,0 +1,115 @@
+// Library plumbing: thread-local error text, version, device query.
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ftn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+  return 1;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional event timing ---------------------------------------------------
+constexpr int kMaxTimed = 8192;
+struct TimedRec { cudaEvent_t a, b; int family; };
+static std::mutex g_tmu;
+static std::vector<TimedRec> g_recs;
+static std::atomic<int> g_timing_on{0};
+
+TimedScope::TimedScope(int family, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  if ((int)g_recs.size() >= kMaxTimed) return;
+  TimedRec r{};
+  r.family = family;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+  slot = (int)g_recs.size() - 1;
+}
+TimedScope::~TimedScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  cudaEventRecord(g_recs[slot].b, st);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace ftn
+
+extern "C" int ftn_version(void) { return FTN_ABI_VERSION; }
+
+extern "C" const char* ftn_last_error(void) { return ftn::g_err; }
+
+extern "C" int ftn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  FTN_CUDA(cudaGetDevice(&dev));
+  int n = 0, maj = 0, min = 0;
+  FTN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  FTN_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  FTN_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = n;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  FTN_REQUIRE(maj == 10, "libflowtimes is built for sm_100a only; device reports sm_%d%d", maj, min);
+  return 0;
+}
+
+extern "C" long long ftn_launch_count(void) { return ftn::g_launches.load(); }
+
+extern "C" int ftn_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(ftn::g_tmu);
+  for (auto& r : ftn::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ftn::g_recs.clear();
+  ftn::g_timing_on.store(on ? 1 : 0);
+  return 0;
+}
+
+extern "C" int ftn_timing_read(int family, double* total_ms, int* calls) {
+  FTN_REQUIRE(total_ms && calls, "ftn_timing_read: null pointer");
+  FTN_REQUIRE(family >= 0 && family < ftn::FTN_FAM_COUNT, "ftn_timing_read: unknown family %d", family);
+  std::lock_guard<std::mutex> lk(ftn::g_tmu);
+  double tot = 0.0;
+  int n = 0;
+  for (auto& r : ftn::g_recs) {
+    if (r.family != family) continue;
+    FTN_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    FTN_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *calls = n;
+  return 0;
+}

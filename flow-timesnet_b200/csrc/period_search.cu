@@ -1,0 +1,373 @@
+// K1: shared period search.
+//
+//   spectrum_dft_kernel   |rfft| of every (window, channel) column, fp32
+//   channel_median_kernel lower median over channels per (window, bin)
+//   batch_sum_kernel      deterministic sum over windows  -> amp_sum[F]
+//   select_tail_kernel    DC mask, log penalty, top-k, period math, grouping
+//   finish_kernel         per-window amplitudes at the chosen bins + group weights
+//
+// Reference semantics: FFTPeriodSelector.forward (timesnet.py:64-159) and the
+// default PeriodGrouper (timesnet.py:513-557).  The transform is a direct
+// table-driven DFT (any L, exact twiddles from a per-call cospi/sinpi table),
+// channels on the lane axis so every global and shared access is coalesced /
+// conflict free.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace ftn {
+
+constexpr int kDftChannels = 32;  // channels per CTA = one per lane
+constexpr int kDftWarps = 8;
+constexpr int kDftFreqPerWarp = 4;  // bins accumulated together per pass
+
+template <typename T>
+__global__ void __launch_bounds__(kDftWarps * 32)
+spectrum_dft_kernel(const T* __restrict__ x, int L, int C, int F, float* __restrict__ amp /*[B][F][C]*/) {
+  extern __shared__ float smem[];
+  float* xs = smem;                                  // [L][32]
+  float2* tw = reinterpret_cast<float2*>(smem + (size_t)L * kDftChannels);  // [L]
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kDftChannels;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const T* xb = x + (size_t)b * L * C;
+
+  for (int i = threadIdx.x; i < L * kDftChannels; i += blockDim.x) {
+    int t = i >> 5, c = c0 + (i & 31);
+    xs[i] = c < C ? to_f32<T>(xb[(size_t)t * C + c]) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    double s, co;
+    sincospi(2.0 * (double)i / (double)L, &s, &co);
+    tw[i] = make_float2((float)co, (float)s);
+  }
+  __syncthreads();
+
+  const int c = c0 + lane;
+  for (int fbase = warp * kDftFreqPerWarp; fbase < F; fbase += kDftWarps * kDftFreqPerWarp) {
+    float re[kDftFreqPerWarp], im[kDftFreqPerWarp];
+    int idx[kDftFreqPerWarp], step[kDftFreqPerWarp];
+#pragma unroll
+    for (int j = 0; j < kDftFreqPerWarp; ++j) {
+      re[j] = 0.f; im[j] = 0.f; idx[j] = 0;
+      step[j] = (fbase + j) % L;
+    }
+    for (int t = 0; t < L; ++t) {
+      float xv = xs[t * kDftChannels + lane];
+#pragma unroll
+      for (int j = 0; j < kDftFreqPerWarp; ++j) {
+        float2 w = tw[idx[j]];
+        re[j] = fmaf(xv, w.x, re[j]);
+        im[j] = fmaf(xv, w.y, im[j]);
+        idx[j] += step[j];
+        if (idx[j] >= L) idx[j] -= L;
+      }
+    }
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < kDftFreqPerWarp; ++j) {
+        int f = fbase + j;
+        if (f < F) amp[((size_t)b * F + f) * C + c] = hypotf(re[j], im[j]);
+      }
+    }
+  }
+}
+
+// order-preserving key for float (ascending), NaN sorts last
+__device__ __forceinline__ uint32_t float_key(float v) {
+  uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+constexpr int kMedianWarps = 8;
+
+// one warp per (window, bin): radix-select the (C-1)/2-th smallest of C amplitudes
+__global__ void __launch_bounds__(kMedianWarps * 32)
+channel_median_kernel(const float* __restrict__ amp, int rows /*B*F*/, int C, float* __restrict__ med) {
+  extern __shared__ uint32_t keys_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kMedianWarps + warp;
+  if (row >= rows) return;
+  uint32_t* keys = keys_all + (size_t)warp * C;
+  const float* a = amp + (size_t)row * C;
+  bool has_nan = false;
+  for (int i = lane; i < C; i += 32) {
+    float v = a[i];
+    has_nan = has_nan || (v != v);
+    keys[i] = float_key(v);
+  }
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  __syncwarp();
+  uint32_t prefix = 0, known = 0;
+  int k = (C - 1) >> 1;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t bmask = 1u << bit;
+    int cnt0 = 0;
+    for (int i = lane; i < C; i += 32) {
+      uint32_t key = keys[i];
+      cnt0 += ((key & known) == prefix && !(key & bmask)) ? 1 : 0;
+    }
+    cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+    if (k >= cnt0) { prefix |= bmask; k -= cnt0; }
+    known |= bmask;
+  }
+  if (lane == 0) med[row] = has_nan ? CUDART_NAN_F : key_float(prefix);  // torch.median propagates NaN
+}
+
+// amp_sum[f] = sum_b med[b][f], fixed order: 32 row-lanes then a serial fold
+__global__ void __launch_bounds__(1024) batch_sum_kernel(const float* __restrict__ med, int B, int F,
+                                                        float* __restrict__ amp_sum) {
+  __shared__ float part[32][33];
+  const int fl = threadIdx.x, r = threadIdx.y;
+  const int f = blockIdx.x * 32 + fl;
+  float s = 0.f;
+  if (f < F)
+    for (int b = r; b < B; b += 32) s += med[(size_t)b * F + f];
+  part[r][fl] = s;
+  __syncthreads();
+  if (r == 0 && f < F) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += part[i][fl];
+    amp_sum[f] = t;
+  }
+}
+
+// rank key: larger is better; NaN ranks above everything like torch.topk
+__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {
+  bool na = sa != sa, nb = sb != sb;
+  if (na != nb) return na;
+  if (!na && sa != sb) return sa > sb;
+  return ia < ib;  // tie rule: lower bin first
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+select_tail_kernel(const float* __restrict__ amp_sum, int global_batch, int L, int k, int pmax,
+                   int min_period, FtnPeriodPlan* __restrict__ plan, float* __restrict__ scores_ws) {
+  const int F = L / 2 + 1;
+  __shared__ float s_best[256];
+  __shared__ int s_idx[256];
+  __shared__ int s_top[FTN_MAX_K];
+  const int tid = threadIdx.x;
+  // scores in the activation dtype, exactly as timesnet.py:119-130
+  for (int f = tid; f < F; f += blockDim.x) {
+    float mean = amp_sum[f] / (float)global_batch;
+    float m = round_to<T>(mean);
+    float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
+    float sc = round_to<T>(m - pen);
+    if (f == 0) sc = -CUDART_INF_F;
+    scores_ws[f] = sc;
+  }
+  __syncthreads();
+  int kk = min(k, F - 1);
+  for (int r = 0; r < kk; ++r) {
+    float bs = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int f = tid; f < F; f += blockDim.x) {
+      bool taken = false;
+      for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
+      if (taken) continue;
+      float sc = scores_ws[f];
+      if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
+    }
+    s_best[tid] = bs;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) {
+        int oi = s_idx[tid + off];
+        if (oi != 0x7fffffff && (s_idx[tid] == 0x7fffffff || better(s_best[tid + off], oi, s_best[tid], s_idx[tid]))) {
+          s_best[tid] = s_best[tid + off];
+          s_idx[tid] = oi;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) s_top[r] = s_idx[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    FtnPeriodPlan pl;
+    pl.n_raw = kk;
+    pl.reserved[0] = pl.reserved[1] = pl.reserved[2] = 0;
+    const int upper = min(pmax, max(1, L - 1));
+    const int lower = min_period;
+    int nv = 0;
+    float mean_amp[FTN_MAX_K];
+    for (int i = 0; i < FTN_MAX_K; ++i) { pl.raw_freq[i] = 0; pl.freq[i] = 0; pl.period[i] = 0; }
+    for (int r = 0; r < kk; ++r) {
+      int64_t safe = max(s_top[r], 1);
+      pl.raw_freq[r] = safe;
+      if (upper < lower) continue;
+      int64_t p = (L + safe - 1) / safe;
+      p = p < lower ? lower : (p > upper ? upper : p);
+      int64_t cyc = (L + p - 1) / p;
+      if (cyc < 2) continue;
+      pl.freq[nv] = safe;
+      pl.period[nv] = p;
+      mean_amp[nv] = amp_sum[safe];
+      ++nv;
+    }
+    pl.n_valid = nv;
+    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp);
+    *plan = pl;
+  }
+}
+
+// per window: amplitudes at the chosen bins (dtype) + softmax group weights
+template <typename T>
+__global__ void finish_kernel(const float* __restrict__ amp_median, int B, int F, int k,
+                              const FtnPeriodPlan* __restrict__ plan, T* __restrict__ amps,
+                              float* __restrict__ weights) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nv = plan->n_valid;
+  float a[FTN_MAX_K];
+  for (int j = 0; j < k; ++j) {
+    float v = 0.f;
+    if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + plan->freq[j]]);
+    a[j] = v;
+    amps[(size_t)b * k + j] = from_f32<T>(v);
+  }
+  float mx = -CUDART_INF_F;
+  for (int j = 0; j < nv; ++j)
+    if (plan->mapping[j] >= 0) mx = fmaxf(mx, a[j]);
+  float den = 0.f;
+  for (int j = 0; j < nv; ++j)
+    if (plan->mapping[j] >= 0) den += expf(a[j] - mx);
+  float w[FTN_MAX_K];
+  for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
+  for (int j = 0; j < nv; ++j) {
+    int g = plan->mapping[j];
+    if (g < 0) continue;
+    float sm = round_to<T>(expf(a[j] - mx) / den);      // softmax fp32 -> dtype (timesnet.py:1000)
+    w[g] = round_to<T>(w[g] + sm);                      // scatter_add_ in dtype (:1009)
+  }
+  for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
+}
+
+// same second half for externally supplied amplitudes (custom selector modules)
+template <typename T>
+__global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, int stride,
+                                     const FtnPeriodPlan* __restrict__ plan, float* __restrict__ weights) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float a[FTN_MAX_K];
+  for (int j = 0; j < k; ++j) a[j] = to_f32<T>(amps[(size_t)b * stride + j]);
+  float mx = -CUDART_INF_F;
+  for (int j = 0; j < k; ++j)
+    if (plan->mapping[j] >= 0) mx = fmaxf(mx, a[j]);
+  float den = 0.f;
+  for (int j = 0; j < k; ++j)
+    if (plan->mapping[j] >= 0) den += expf(a[j] - mx);
+  float w[FTN_MAX_K];
+  for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
+  for (int j = 0; j < k; ++j) {
+    int g = plan->mapping[j];
+    if (g < 0) continue;
+    float sm = round_to<T>(expf(a[j] - mx) / den);
+    w[g] = round_to<T>(w[g] + sm);
+  }
+  for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace ftn
+
+using namespace ftn;
+
+extern "C" size_t ftn_spectrum_workspace_bytes(int B, int L, int C) {
+  if (B <= 0 || L <= 0 || C <= 0) return 256;
+  size_t F = (size_t)L / 2 + 1;
+  return align256((size_t)B * F * C * sizeof(float)) + align256(F * sizeof(float)) + 256;
+}
+
+extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
+                            float* amp_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(x && amp_median && amp_sum && workspace, "ftn_spectrum: null pointer");
+  FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_spectrum: need B>0, L>1, C>0 (got %d,%d,%d)", B, L, C);
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_spectrum: unsupported dtype %d", dtype);
+  FTN_REQUIRE(C <= 8192, "ftn_spectrum: C=%d exceeds the per-warp median buffer (8192)", C);
+  FTN_REQUIRE(workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_spectrum: workspace too small");
+  const int F = L / 2 + 1;
+  float* amp = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  TimedScope timed(FTN_FAM_SPECTRUM, st);
+  size_t smem = (size_t)L * kDftChannels * sizeof(float) + (size_t)L * sizeof(float2);
+  FTN_REQUIRE(smem <= 227 * 1024, "ftn_spectrum: L=%d needs %zu B of shared memory (> 227 KB)", L, smem);
+  dim3 grid((C + kDftChannels - 1) / kDftChannels, B);
+  if (dtype == FTN_F32) {
+    FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectrum_dft_kernel<float><<<grid, kDftWarps * 32, smem, st>>>((const float*)x, L, C, F, amp);
+  } else {
+    FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectrum_dft_kernel<__nv_bfloat16><<<grid, kDftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, F, amp);
+  }
+  FTN_LAUNCH_CHECK("spectrum_dft_kernel");
+  const int rows = B * F;
+  size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);
+  FTN_CUDA(cudaFuncSetAttribute(channel_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  channel_median_kernel<<<(rows + kMedianWarps - 1) / kMedianWarps, kMedianWarps * 32, msmem, st>>>(amp, rows, C, amp_median);
+  FTN_LAUNCH_CHECK("channel_median_kernel");
+  batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum);
+  FTN_LAUNCH_CHECK("batch_sum_kernel");
+  return 0;
+}
+
+extern "C" int ftn_select_periods(const float* amp_median, const float* amp_sum, int dtype, int B,
+                                  int global_batch, int L, int k, int pmax, int min_period,
+                                  FtnPeriodPlan* plan, void* amps, float* weights, float* scores_ws,
+                                  void* stream) {
+  FTN_REQUIRE(amp_median && amp_sum && plan && amps && weights && scores_ws, "ftn_select_periods: null pointer");
+  FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_select_periods: k=%d outside [1,%d]", k, FTN_MAX_K);
+  FTN_REQUIRE(B > 0 && global_batch >= B && L > 1, "ftn_select_periods: bad sizes B=%d global=%d L=%d", B, global_batch, L);
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_select_periods: unsupported dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  const int F = L / 2 + 1;
+  if (dtype == FTN_F32) {
+    select_tail_kernel<float><<<1, 256, 0, st>>>(amp_sum, global_batch, L, k, pmax, min_period, plan, scores_ws);
+    FTN_LAUNCH_CHECK("select_tail_kernel");
+    finish_kernel<float><<<(B + 127) / 128, 128, 0, st>>>(amp_median, B, F, k, plan, (float*)amps, weights);
+  } else {
+    select_tail_kernel<__nv_bfloat16><<<1, 256, 0, st>>>(amp_sum, global_batch, L, k, pmax, min_period, plan, scores_ws);
+    FTN_LAUNCH_CHECK("select_tail_kernel");
+    finish_kernel<__nv_bfloat16><<<(B + 127) / 128, 128, 0, st>>>(amp_median, B, F, k, plan, (__nv_bfloat16*)amps, weights);
+  }
+  FTN_LAUNCH_CHECK("finish_kernel");
+  return 0;
+}
+
+extern "C" int ftn_plan_build_host(const int64_t* periods_host, int k, int L, int min_period,
+                                   int max_period, FtnPeriodPlan* plan_host) {
+  FTN_REQUIRE(periods_host && plan_host, "ftn_plan_build_host: null pointer");
+  FTN_REQUIRE(k >= 0 && k <= FTN_MAX_K, "ftn_plan_build_host: k=%d outside [0,%d]", k, FTN_MAX_K);
+  FTN_REQUIRE(L >= 1, "ftn_plan_build_host: L=%d", L);
+  FtnPeriodPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.n_raw = k;
+  pl.n_valid = k;
+  for (int i = 0; i < k; ++i) { pl.period[i] = periods_host[i]; pl.raw_freq[i] = 0; pl.freq[i] = 0; }
+  plan_group_default(&pl, pl.period, k, L, min_period, max_period, nullptr);
+  *plan_host = pl;
+  return 0;
+}
+
+extern "C" int ftn_group_weights(const void* amps, int dtype, int B, int k, int amp_batch_stride,
+                                 const FtnPeriodPlan* plan, float* weights, void* stream) {
+  FTN_REQUIRE(amps && plan && weights, "ftn_group_weights: null pointer");
+  FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_group_weights: k=%d outside [1,%d]", k, FTN_MAX_K);
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_group_weights: unsupported dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == FTN_F32)
+    group_weights_kernel<float><<<(B + 127) / 128, 128, 0, st>>>((const float*)amps, B, k, amp_batch_stride, plan, weights);
+  else
+    group_weights_kernel<__nv_bfloat16><<<(B + 127) / 128, 128, 0, st>>>((const __nv_bfloat16*)amps, B, k, amp_batch_stride, plan, weights);
+  FTN_LAUNCH_CHECK("group_weights_kernel");
+  return 0;
+}

@@ -1,0 +1,315 @@
+"""ctypes binding of libflowtimes.so (the C ABI in include/flowtimes.h).
+
+PyTorch is used for device memory and streams only: every wrapper takes torch
+CUDA tensors, checks layout/dtype, and passes raw device pointers plus the
+current stream to the library.  There is NO fallback: if the shared library is
+missing or a tensor is not a contiguous CUDA tensor the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+FTN_F32, FTN_BF16 = 0, 1
+FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
+FTN_MAX_K = 16
+FTN_MAX_BRANCH = 8
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("FLOWTIMES_LIB", _PKG.parent / "lib" / "libflowtimes.so"))
+
+
+class FtnPeriodPlan(C.Structure):
+    _fields_ = [
+        ("seq_len", C.c_int32),
+        ("n_raw", C.c_int32),
+        ("n_valid", C.c_int32),
+        ("n_groups", C.c_int32),
+        ("total_rows_per_window", C.c_int32),
+        ("reserved", C.c_int32 * 3),
+        ("raw_freq", C.c_int64 * FTN_MAX_K),
+        ("freq", C.c_int64 * FTN_MAX_K),
+        ("period", C.c_int64 * FTN_MAX_K),
+        ("mapping", C.c_int32 * FTN_MAX_K),
+        ("grp_period", C.c_int32 * FTN_MAX_K),
+        ("grp_pad", C.c_int32 * FTN_MAX_K),
+        ("grp_cycles", C.c_int32 * FTN_MAX_K),
+        ("grp_canon", C.c_int32 * FTN_MAX_K),
+        ("grp_row_off", C.c_int32 * (FTN_MAX_K + 1)),
+    ]
+
+
+class FtnInceptionWeights(C.Structure):
+    _fields_ = [
+        ("cin", C.c_int32), ("cout", C.c_int32), ("mid", C.c_int32), ("n_branch", C.c_int32),
+        ("kh", C.c_int32 * FTN_MAX_BRANCH), ("kw", C.c_int32 * FTN_MAX_BRANCH),
+        ("kk_cin", C.c_int32), ("kk_cout", C.c_int32),
+        ("w_in", C.c_void_p), ("b_in", C.c_void_p),
+        ("w_kk", C.c_void_p * FTN_MAX_BRANCH), ("b_kk", C.c_void_p * FTN_MAX_BRANCH),
+        ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+        ("w_res", C.c_void_p), ("b_res", C.c_void_p),
+    ]
+
+
+PLAN_BYTES = C.sizeof(FtnPeriodPlan)
+
+# name -> (restype, argtypes); must list every symbol include/flowtimes.h declares
+_P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+SIGNATURES = {
+    "ftn_version": (_I, []),
+    "ftn_last_error": (C.c_char_p, []),
+    "ftn_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "ftn_launch_count": (C.c_longlong, []),
+    "ftn_timing_enable": (_I, [_I]),
+    "ftn_timing_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_I)]),
+    "ftn_spectrum_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ftn_spectrum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ftn_plan_build_host": (_I, [C.POINTER(_I64), _I, _I, _I, _I, C.POINTER(FtnPeriodPlan)]),
+    "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
+    "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
+                             C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
+    "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
+    "ftn_context_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "ftn_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ftn_layer_norm": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P]),
+    "ftn_embed_combine": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "ftn_nb_head": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ftn_nb_nll": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"libflowtimes.so not found at {LIB_PATH}. Build it with "
+            "`python flow-timesnet_b200/build.py` (nvcc, sm_100a). There is no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI drift, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ftn_version() != 1:
+        raise RuntimeError(f"libflowtimes ABI version {lib.ftn_version()} != 1")
+    _lib = lib
+    return lib
+
+
+class FlowTimesError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ftn_last_error().decode("utf-8", "replace")
+        raise FlowTimesError(f"{what} failed (rc={rc}): {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return FTN_F32
+    if dt == torch.bfloat16:
+        return FTN_BF16
+    raise TypeError(f"flowtimes supports float32 and bfloat16 activations, got {dt} (no fp16 path)")
+
+
+def require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the B200-native TimesBlock path runs on CUDA only (no CPU fallback)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    _check(load().ftn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "ftn_device_info")
+    return sm.value, ma.value, mi.value
+
+
+def launch_count() -> int:
+    return int(load().ftn_launch_count())
+
+
+FAM_SPECTRUM, FAM_CONV, FAM_AGGREGATE = 0, 1, 2
+
+
+def timing_enable(on: bool) -> None:
+    _check(load().ftn_timing_enable(int(on)), "ftn_timing_enable")
+
+
+def timing_read(family: int):
+    ms, n = C.c_double(), C.c_int()
+    _check(load().ftn_timing_read(family, C.byref(ms), C.byref(n)), "ftn_timing_read")
+    return ms.value, n.value
+
+
+# --------------------------------------------------------------------------- #
+# K1
+# --------------------------------------------------------------------------- #
+def spectrum(x: torch.Tensor):
+    """x[B,L,C] -> (amp_median[B,F] fp32, amp_sum[F] fp32)."""
+    lib = load()
+    B, L, Cc = x.shape
+    Fq = L // 2 + 1
+    med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
+    ssum = torch.empty(Fq, dtype=torch.float32, device=x.device)
+    nbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _check(lib.ftn_spectrum(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, med.data_ptr(), ssum.data_ptr(),
+                            ws.data_ptr(), nbytes, _stream()), "ftn_spectrum")
+    return med, ssum
+
+
+def new_plan(device) -> torch.Tensor:
+    return torch.zeros(PLAN_BYTES, dtype=torch.uint8, device=device)
+
+
+def select_periods(med: torch.Tensor, ssum: torch.Tensor, dtype: torch.dtype, global_batch: int, L: int, k: int,
+                   pmax: int, min_period: int):
+    """-> (plan uint8[PLAN_BYTES] device, amps[B,k] dtype, weights[B,FTN_MAX_K] fp32)."""
+    lib = load()
+    B = med.shape[0]
+    plan = new_plan(med.device)
+    amps = torch.empty(B, k, dtype=dtype, device=med.device)
+    weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=med.device)
+    scratch = torch.empty(L // 2 + 1, dtype=torch.float32, device=med.device)
+    _check(lib.ftn_select_periods(med.data_ptr(), ssum.data_ptr(), dtype_code(dtype), B, int(global_batch), L, k,
+                                  pmax, min_period, plan.data_ptr(), amps.data_ptr(), weights.data_ptr(),
+                                  scratch.data_ptr(), _stream()), "ftn_select_periods")
+    return plan, amps, weights
+
+
+def plan_build_host(periods, L: int, min_period: Optional[int], max_period: Optional[int]) -> FtnPeriodPlan:
+    lib = load()
+    k = len(periods)
+    arr = (C.c_int64 * max(k, 1))(*[int(p) for p in periods])
+    plan = FtnPeriodPlan()
+    _check(lib.ftn_plan_build_host(arr, k, int(L), int(min_period or 0), int(max_period or 0), C.byref(plan)),
+           "ftn_plan_build_host")
+    return plan
+
+
+def plan_to_device(plan: FtnPeriodPlan, device) -> torch.Tensor:
+    raw = bytes(memoryview(plan))
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def plan_to_host(plan_dev: torch.Tensor) -> FtnPeriodPlan:
+    raw = plan_dev.cpu().numpy().tobytes()          # one small D2H + sync
+    return FtnPeriodPlan.from_buffer_copy(raw)
+
+
+def group_weights(amps: torch.Tensor, plan_dev: torch.Tensor, B: int) -> torch.Tensor:
+    lib = load()
+    if amps.dim() == 1:
+        amps = amps.view(1, -1)
+    k = amps.shape[1]
+    stride = k if amps.shape[0] == B else 0
+    if amps.shape[0] not in (1, B):
+        raise ValueError("amplitudes must have shape [B, K] or [K]")
+    weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=amps.device)
+    _check(lib.ftn_group_weights(amps.data_ptr(), dtype_code(amps.dtype), B, k, stride, plan_dev.data_ptr(),
+                                 weights.data_ptr(), _stream()), "ftn_group_weights")
+    return weights
+
+
+# --------------------------------------------------------------------------- #
+# K2-K4
+# --------------------------------------------------------------------------- #
+def inception_workspace_bytes(B: int, L: int, max_groups: int, wa: FtnInceptionWeights, wb: FtnInceptionWeights) -> int:
+    return int(load().ftn_inception_workspace_bytes(B, L, max_groups, C.byref(wa), C.byref(wb)))
+
+
+def period_conv(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, wa: FtnInceptionWeights,
+                wb: FtnInceptionWeights, act: int, delta: torch.Tensor, ws: torch.Tensor) -> None:
+    B, L, Cc = x.shape
+    _check(load().ftn_period_conv(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, plan_dev.data_ptr(), max_groups,
+                                  C.byref(wa), C.byref(wb), act, delta.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _stream()), "ftn_period_conv")
+
+
+def aggregate(x: torch.Tensor, delta: torch.Tensor, weights: torch.Tensor, plan_dev: torch.Tensor,
+              ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor], eps: float, out: torch.Tensor) -> None:
+    B, L, Cc = x.shape
+    _check(load().ftn_aggregate(x.data_ptr(), delta.data_ptr(), weights.data_ptr(), plan_dev.data_ptr(),
+                                dtype_code(x.dtype), B, L, Cc, _ptr(ln_w), _ptr(ln_b), float(eps), out.data_ptr(),
+                                _stream()), "ftn_aggregate")
+
+
+# --------------------------------------------------------------------------- #
+# K5, K6, helpers
+# --------------------------------------------------------------------------- #
+def context_add(x, coeff, basis, scale, out) -> None:
+    B, L, N = x.shape
+    R = coeff.shape[-1]
+    _check(load().ftn_context_add(x.data_ptr(), coeff.data_ptr(), basis.data_ptr(), scale.data_ptr(), B, L, N, R,
+                                  out.data_ptr(), _stream()), "ftn_context_add")
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32 Linear on the last dim: a[..., K] x w[N, K]^T + bias."""
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    out = torch.empty(*a.shape[:-1], N, dtype=torch.float32, device=a.device)
+    _check(load().ftn_linear(a.data_ptr(), w.data_ptr(), _ptr(bias), M, K, N, out.data_ptr(), _stream()), "ftn_linear")
+    return out
+
+
+def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty_like(x)
+    _check(load().ftn_layer_norm(x.data_ptr(), dtype_code(x.dtype), rows, Cc, w.data_ptr(), b.data_ptr(), float(eps),
+                                 out.data_ptr(), _stream()), "ftn_layer_norm")
+    return out
+
+
+def embed_combine(value, aux, gate, aux_batched: bool, out_dtype: torch.dtype) -> torch.Tensor:
+    B, L, Cc = value.shape
+    out = torch.empty(B, L, Cc, dtype=out_dtype, device=value.device)
+    _check(load().ftn_embed_combine(value.data_ptr(), aux.data_ptr(), gate.data_ptr(), int(aux_batched), B, L, Cc,
+                                    dtype_code(out_dtype), out.data_ptr(), _stream()), "ftn_embed_combine")
+    return out
+
+
+def nb_head(seq, steps, N, Wt, bt, Wmu, bmu, Wsg, bsg, hist, late, late_gate, floor_n, flags):
+    B, L, Cc = seq.shape
+    rate = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
+    disp = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
+    ws = torch.empty(B * steps * Cc, dtype=torch.float32, device=seq.device)
+    _check(load().ftn_nb_head(seq.data_ptr(), dtype_code(seq.dtype), B, L, Cc, steps, N, Wt.data_ptr(), bt.data_ptr(),
+                              Wmu.data_ptr(), bmu.data_ptr(), Wsg.data_ptr(), bsg.data_ptr(), hist.data_ptr(),
+                              _ptr(late), _ptr(late_gate), floor_n.data_ptr(), rate.data_ptr(), disp.data_ptr(),
+                              flags.data_ptr(), ws.data_ptr(), _stream()), "ftn_nb_head")
+    return rate, disp
+
+
+def nb_nll(y, rate, disp, mask_u8, eps: float) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=y.device)
+    partial = torch.empty(2 * 1024, dtype=torch.float32, device=y.device)
+    _check(load().ftn_nb_nll(y.data_ptr(), rate.data_ptr(), disp.data_ptr(), _ptr(mask_u8), y.numel(), float(eps),
+                             partial.data_ptr(), out.data_ptr(), _stream()), "ftn_nb_nll")
+    return out

@@ -1,0 +1,122 @@
+"""One-time host-side packing of InceptionBlock parameters for libflowtimes.
+
+The reference keeps 3 x (1x1 -> k x k -> 1x1) convs + a 1x1 ``proj`` over their
+concatenation (timesnet.py:586-590, :633, :650-651).  There is no activation
+between a branch's last 1x1 and ``proj``, so they compose exactly:
+
+    proj(cat_j(W3_j h_j + b3_j)) = sum_j (P_j W3_j) h_j + (b_p + sum_j P_j b3_j)
+
+with ``P_j`` the j-th column block of ``proj.weight``.  The packed form therefore
+is: one concatenated input 1x1 (cin -> n_branch*mid), the per-branch k x k convs,
+and ONE folded output 1x1 (n_branch*mid -> cout).  For bottleneck_ratio == 1
+(single k x k conv per branch, timesnet.py:575-580) ``proj`` folds into a single
+conv with the union (largest) window.  Folding is done in float64 and costs
+~1e-6 relative.  Layouts are K-major as
+include/flowtimes.h describes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import torch
+from torch import nn
+
+from . import _native as nv
+
+
+class PackedInception:
+    """Owns the packed device tensors and the C struct that points at them."""
+
+    def __init__(self, struct: nv.FtnInceptionWeights, tensors: List[torch.Tensor], executed_macs: int):
+        self.struct = struct
+        self.tensors = tensors            # keep-alive
+        self.executed_macs_per_pos = executed_macs
+
+
+def _conv_list(branch_seq: nn.Sequential) -> List[nn.Conv2d]:
+    convs = [m for m in branch_seq if isinstance(m, nn.Conv2d)]
+    if len(convs) not in (1, 3):
+        raise ValueError("InceptionBranch must hold 1 (ratio 1) or 3 (bottleneck) Conv2d modules")
+    return convs
+
+
+def pack_inception_block(block: nn.Module, device: torch.device) -> PackedInception:
+    paths = [_conv_list(p.branch) for p in block.paths]
+    n_branch = len(paths)
+    if n_branch > nv.FTN_MAX_BRANCH:
+        raise ValueError(f"kernel_set has {n_branch} entries; libflowtimes supports at most {nv.FTN_MAX_BRANCH}")
+    depth = {len(p) for p in paths}
+    if len(depth) != 1:
+        raise ValueError("all inception branches must share the same bottleneck structure")
+    bottleneck = depth.pop() == 3
+    f64 = torch.float64
+    proj_w = block.proj.weight.detach().to("cpu", f64)[:, :, 0, 0]          # [cout, n_branch*cout]
+    proj_b = block.proj.bias.detach().to("cpu", f64)
+    cout = proj_w.shape[0]
+    cin = paths[0][0].weight.shape[1]
+    st = nv.FtnInceptionWeights()
+    keep: List[torch.Tensor] = []
+
+    def dev(t: torch.Tensor) -> int:
+        d = t.to(torch.float32).contiguous().to(device)
+        keep.append(d)
+        return d.data_ptr()
+
+    st.cin, st.cout, st.n_branch = int(cin), int(cout), n_branch
+    macs = 0
+    if bottleneck:
+        mid = paths[0][0].weight.shape[0]
+        st.mid = int(mid)
+        st.kk_cin = st.kk_cout = int(mid)
+        w_in = torch.cat([p[0].weight.detach().to("cpu", f64)[:, :, 0, 0] for p in paths], dim=0)   # [NB, cin]
+        b_in = torch.cat([p[0].bias.detach().to("cpu", f64) for p in paths], dim=0)
+        st.w_in, st.b_in = dev(w_in.t()), dev(b_in)
+        macs += cin * n_branch * mid
+        w_out_rows = []
+        b_out = proj_b.clone()
+        for j, p in enumerate(paths):
+            wk = p[1].weight.detach().to("cpu", f64)                         # [mid_out, mid_in, kh, kw]
+            kh, kw = int(wk.shape[2]), int(wk.shape[3])
+            st.kh[j], st.kw[j] = kh, kw
+            st.w_kk[j] = dev(wk.permute(2, 3, 1, 0).reshape(kh * kw, mid, mid))
+            st.b_kk[j] = dev(p[1].bias.detach().to("cpu", f64))
+            macs += kh * kw * mid * mid
+            P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
+            W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
+            w_out_rows.append((P @ W3).t())                                  # [mid, cout]
+            b_out = b_out + P @ p[2].bias.detach().to("cpu", f64)
+        st.w_out, st.b_out = dev(torch.cat(w_out_rows, dim=0)), dev(b_out)
+        macs += n_branch * mid * cout
+    else:
+        st.mid = 0
+        st.kk_cin, st.kk_cout = int(cin), int(cout)
+        KH = max(int(p[0].weight.shape[2]) for p in paths)
+        KW = max(int(p[0].weight.shape[3]) for p in paths)
+        wtot = torch.zeros(cout, cin, KH, KW, dtype=f64)
+        btot = proj_b.clone()
+        for j, p in enumerate(paths):
+            w = p[0].weight.detach().to("cpu", f64)                          # [cout, cin, kh, kw]
+            kh, kw = int(w.shape[2]), int(w.shape[3])
+            if (KH - kh) % 2 or (KW - kw) % 2:
+                raise ValueError("kernel_set sizes must share parity to share a centred window")
+            P = proj_w[:, j * cout:(j + 1) * cout]
+            r0, s0 = (KH - kh) // 2, (KW - kw) // 2
+            wtot[:, :, r0:r0 + kh, s0:s0 + kw] += torch.einsum("om,mirs->oirs", P, w)
+            btot = btot + P @ p[0].bias.detach().to("cpu", f64)
+        st.n_branch = 1
+        st.kh[0], st.kw[0] = KH, KW
+        st.w_kk[0] = dev(wtot.permute(2, 3, 1, 0).reshape(KH * KW, cin, cout))
+        st.b_kk[0] = dev(btot)
+        macs += KH * KW * cin * cout
+    if isinstance(block.res_proj, nn.Conv2d):
+        st.w_res = dev(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0].t())   # [cin, cout]
+        st.b_res = dev(block.res_proj.bias.detach().to("cpu", f64))
+        macs += cin * cout
+    else:
+        st.w_res, st.b_res = None, None
+    return PackedInception(st, keep, macs)
+
+
+def params_fingerprint(module: nn.Module) -> Tuple:
+    return tuple((p.data_ptr(), p._version, p.device.type) for p in module.parameters())

@@ -1,0 +1,212 @@
+/*
+ * flowtimes.h -- C ABI of libflowtimes.so, the B200 (sm_100a) implementation of
+ * Flow-TimesNet's TimesBlock forward path.
+ *
+ * The reference has no FFI: its operator boundary is the Python module API of
+ * timesnet_forecast.models.timesnet / timesnet_forecast.losses, and below that
+ * only torch.* library calls.  Each entry point here replaces
+ * one group of those call sites; the "replaces" notes cite
+ * /root/reference/src/timesnet_forecast/<file>:<line>.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it is marked
+ *     "host"; the library never allocates, frees or synchronises
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*)
+ *   - return value 0 = ok, non-zero = error; text via ftn_last_error()
+ *     (thread-local, valid until the next call on the same thread)
+ *   - dtype: FTN_F32 / FTN_BF16 is the ACTIVATION dtype of x / delta / out;
+ *     weights, intermediates and all reductions are fp32
+ *   - tensors are dense row-major; x is [B, L, C] with C contiguous
+ *   - period geometry lives in DEVICE memory (FtnPeriodPlan) so that no call
+ *     needs a host round trip between the period search and the convolutions
+ */
+#ifndef FLOWTIMES_H_
+#define FLOWTIMES_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FTN_API __attribute__((visibility("default")))
+#else
+#define FTN_API
+#endif
+
+#define FTN_F32 0
+#define FTN_BF16 1
+
+#define FTN_ACT_GELU 0 /* exact erf GELU, nn.GELU() default (timesnet.py:643) */
+#define FTN_ACT_RELU 1
+
+#define FTN_MAX_K 16      /* max candidate periods per block (k_periods) */
+#define FTN_MAX_BRANCH 8  /* max kernels in kernel_set */
+
+/* Device-resident result of the period search + PeriodGrouper.
+ * Mirrors FFTPeriodSelector.last_frequency_indices / last_selected_periods
+ * (timesnet.py:156-157) and PeriodGroupResult (timesnet.py:275-283). */
+typedef struct FtnPeriodPlan {
+  int32_t seq_len;               /* L */
+  int32_t n_raw;                 /* k bins ranked by top-k (<= FTN_MAX_K) */
+  int32_t n_valid;               /* K' candidates after the cycles>=2 filter */
+  int32_t n_groups;              /* G after duplicate merging */
+  int32_t total_rows_per_window; /* sum_g (L + pad_g) */
+  int32_t reserved[3];
+  int64_t raw_freq[FTN_MAX_K];   /* top-k bins, descending score, clamped >= 1 */
+  int64_t freq[FTN_MAX_K];       /* bins of the valid candidates */
+  int64_t period[FTN_MAX_K];     /* period of the valid candidates */
+  int32_t mapping[FTN_MAX_K];    /* valid candidate -> group, -1 = dropped */
+  int32_t grp_period[FTN_MAX_K]; /* ascending */
+  int32_t grp_pad[FTN_MAX_K];    /* (-L) mod p */
+  int32_t grp_cycles[FTN_MAX_K]; /* (L + pad) / p */
+  int32_t grp_canon[FTN_MAX_K];  /* canonical candidate index of the group */
+  int32_t grp_row_off[FTN_MAX_K + 1]; /* prefix sum of (L + pad_g): row offset per window */
+} FtnPeriodPlan;
+
+/* One InceptionBlock after host-side packing (all fp32, device pointers).
+ * Replaces the 10 nn.Conv2d modules of InceptionBlock (timesnet.py:596-654).
+ *
+ *   stage "in"  : concatenated 1x1 convs  cin -> n_branch*mid      (absent when mid == 0)
+ *   stage "kk"  : per-branch kh x kw conv  kk_cin -> kk_cout, zero "same" padding
+ *   stage "out" : proj o branch-out folded into ONE 1x1  n_branch*mid -> cout
+ *                 (absent when mid == 0: the fold goes into the single k x k conv)
+ *   residual    : 1x1 cin -> cout, or identity when w_res == NULL
+ *
+ * Weight layouts are K-major ("input channel major"): w[k][n] with n contiguous.
+ * w_kk[j] is [kh*kw][kk_cin][kk_cout]. */
+typedef struct FtnInceptionWeights {
+  int32_t cin, cout, mid, n_branch;
+  int32_t kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
+  int32_t kk_cin, kk_cout; /* channels per branch of the k x k stage */
+  const float* w_in;       /* [cin][n_branch*mid] */
+  const float* b_in;       /* [n_branch*mid] */
+  const float* w_kk[FTN_MAX_BRANCH];
+  const float* b_kk[FTN_MAX_BRANCH];
+  const float* w_out;      /* [n_branch*mid][cout] */
+  const float* b_out;      /* [cout] */
+  const float* w_res;      /* [cin][cout] or NULL */
+  const float* b_res;      /* [cout] or NULL */
+} FtnInceptionWeights;
+
+/* ---- library ---------------------------------------------------------- */
+FTN_API int ftn_version(void);
+FTN_API const char* ftn_last_error(void);
+/* sm count / compute capability of the current device; fails on non-sm_100 */
+FTN_API int ftn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* number of kernels this library has enqueued since load (bench.py "gpu_launches") */
+FTN_API long long ftn_launch_count(void);
+/* Optional CUDA-event timing per kernel family (0 = period-search spectrum,
+ * 1 = Inception conv chain, 2 = aggregate): enable resets the records; read
+ * synchronises the recorded events and returns total ms and number of calls. */
+FTN_API int ftn_timing_enable(int on);
+FTN_API int ftn_timing_read(int family, double* total_ms, int* calls);
+
+/* ---- K1: period search ---------------------------------------------------
+ * replaces torch.fft.rfft + abs + median(dim=2) + mean(dim=0)   timesnet.py:109-112
+ *
+ * ftn_spectrum: amp_median[b][f] = lower median over c of |rfft_t x[b,:,c]|[f],
+ *   amp_sum[f] = sum_b amp_median[b][f]  (deterministic order; the caller
+ *   all-reduces amp_sum across ranks when the batch is sharded).
+ *   F = L/2 + 1.  workspace >= ftn_spectrum_workspace_bytes(). */
+FTN_API size_t ftn_spectrum_workspace_bytes(int B, int L, int C);
+FTN_API int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
+                 float* amp_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces the top-k / period math of FFTPeriodSelector.forward (timesnet.py:115-159)
+ * and PeriodGrouper.group in its default exact-duplicate mode (timesnet.py:513-557).
+ * global_batch = number of windows amp_sum was summed over (all ranks).
+ * Tie rule for equal scores: lower bin index first (torch.topk leaves it unspecified).
+ * amps: [B, k] dtype, columns >= n_valid are zero. */
+FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, int dtype, int B,
+                       int global_batch, int L, int k, int pmax, int min_period,
+                       FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/,
+                       float* scores_ws /*[L/2+1] scratch*/, void* stream);
+
+/* HOST helper (no CUDA): group an externally supplied candidate list (a custom
+ * period_selector module) with the default exact-duplicate rules and fill a
+ * HOST FtnPeriodPlan the caller then copies to the device.  Runs the same
+ * grouping code as the device tail.  replaces PeriodGrouper.group
+ * (timesnet.py:513-557); pass min/max_period <= 0 for "unset". */
+FTN_API int ftn_plan_build_host(const int64_t* periods_host, int k, int L, int min_period,
+                        int max_period, FtnPeriodPlan* plan_host);
+
+/* softmax over the valid candidates (fp32) rounded to dtype, scatter-added into
+ * groups: weights[B][FTN_MAX_K] fp32 holding dtype-rounded values.
+ * amps may be [B,k] (amp_batch_stride = k) or a single row (stride 0).
+ * replaces timesnet.py:992-1009. */
+FTN_API int ftn_group_weights(const void* amps, int dtype, int B, int k, int amp_batch_stride,
+                      const FtnPeriodPlan* plan, float* weights, void* stream);
+
+/* ---- K2+K3: fold + Inception bank + delta --------------------------------
+ * replaces the per-period loop of _period_conv_bucketed_slicing (timesnet.py:1034-1070):
+ * fold (zero-copy index math), InceptionBlock -> act -> InceptionBlock, minus
+ * grid, unfold, cast.  delta: [FTN_MAX_K slots][B][L][C] dtype, slot g < n_groups
+ * written.  max_groups bounds the launch (k_periods).  */
+FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a,
+                                     const FtnInceptionWeights* b);
+FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
+                    int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b,
+                    int act, void* delta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: weighted aggregation + residual (+ shared LayerNorm) ------------
+ * out = x + sum_g w[b][g] * delta_g          replaces timesnet.py:1075-1099, :818
+ * with ln_weight != NULL additionally        replaces timesnet.py:2059-2061
+ *   out = LayerNorm_fp32(x + (out - x)) * ln_weight + ln_bias */
+FTN_API int ftn_aggregate(const void* x, const void* delta, const float* weights, const FtnPeriodPlan* plan,
+                  int dtype, int B, int L, int C, const float* ln_weight, const float* ln_bias,
+                  float ln_eps, void* out, void* stream);
+
+/* ---- K5: LowRankTemporalContext fused into the input add -----------------
+ * out[b,t,n] = x[b,t,n] + scale * (sum_r basis[t][r] coeff[b][n][r] - mean_t(...))
+ * basis: [L][R] fp32 (cached DCT-like basis, timesnet.py:1340-1351)
+ * replaces timesnet.py:1368-1371 and the add at :1981 */
+FTN_API int ftn_context_add(const float* x, const float* coeff, const float* basis, const float* scale,
+                    int B, int L, int N, int R, float* out, void* stream);
+
+/* ---- generic row GEMM used by the callers either side of the path --------
+ * out[m][n] = sum_k a[m][k] * w[n][k] + bias[n]   (torch Linear layout, fp32)
+ * replaces nn.Linear call sites: value_embedding (timesnet.py:1295), context /
+ * late-bias projections (:1899, :1966, :2040). */
+FTN_API int ftn_linear(const float* a, const float* w, const float* bias, int M, int K, int N,
+               float* out, void* stream);
+
+/* LayerNorm over the last dim, fp32 statistics.  replaces _apply_layer_norm
+ * (timesnet.py:1162-1181). */
+FTN_API int ftn_layer_norm(const void* x, int dtype, int rows, int C, const float* w, const float* b,
+                   float eps, void* out, void* stream);
+
+/* DataEmbedding epilogue: out[b,t,c] = value[b,t,c] + gate[c] * aux[t][c]  -> dtype_out
+ * (decoupled norm mode, aux = LayerNorm(PE) precomputed)   replaces timesnet.py:1306-1312 */
+FTN_API int ftn_embed_combine(const float* value, const float* aux, const float* gate, int aux_batched,
+                      int B, int L, int C, int dtype_out, void* out, void* stream);
+
+/* ---- K6: Negative-Binomial head -------------------------------------------
+ * hidden[b,h,c] = sum_t Wt[h][t] seq[b,t,c] + bt[h]              (forecast_time_proj, :2071)
+ * rate  = softplus(hidden . Wmu^T + bmu + hist[b,h,n] + gate[h] late[b,n,h]) + 1e-6   (:2079-2085)
+ * disp  = softplus(hidden . Wsg^T + bsg) + floor[n] + 1e-6       (:2087-2093)
+ * Wt rows are the LAST `steps` rows of forecast_time_proj (caller slices for recursive mode).
+ * late: NULL or late_bias_head output [B][N][steps] with late_gate[steps] (:2028-2048);
+ * floor is [N] (min_sigma broadcast by the caller).
+ * flags[0] |= 1 if any rate is non-finite or <= 0, |= 2 for dispersion      (:2094-2097)
+ * workspace: B*steps*C floats. */
+FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int steps, int N,
+                const float* Wt, const float* bt, const float* Wmu, const float* bmu,
+                const float* Wsg, const float* bsg, const float* hist, const float* late,
+                const float* late_gate, const float* floor_n, float* rate, float* disp,
+                int32_t* flags, float* workspace, void* stream);
+
+/* NB negative log-likelihood, masked mean.  replaces losses.py:27-58.
+ * mask: NULL or uint8 [count]; partial: >= 2*1024 floats scratch; out: 1 float. */
+FTN_API int ftn_nb_nll(const float* y, const float* rate, const float* disp, const uint8_t* mask,
+               int64_t count, float eps, float* partial, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWTIMES_H_ */
