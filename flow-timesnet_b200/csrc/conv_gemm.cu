@@ -17,19 +17,21 @@
 // launches of timesnet.py:1034-1070 / :645-654.  All math fp32 (the reference
 // runs these convs in fp32 even for bf16 activations, timesnet.py:1050-1052).
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace ftn {
 
 constexpr int KC = 16;  // K-chunk (input channels of one tap) per smem stage
 
-enum SrcKind { SRC_SEQ = 0, SRC_POS = 1 };
+enum SrcKind { SRC_SEQ = 0, SRC_POS = 1, SRC_TILED = 2 };
 enum Phase2Kind { P2_NONE = 0, P2_GEMM = 1, P2_IDENTITY = 2 };
-enum OutKind { OUT_POS = 0, OUT_DELTA = 1 };
+enum OutKind { OUT_POS = 0, OUT_DELTA = 1, OUT_TILED = 2 };
 
 struct Src {
   const void* ptr;
   int kind;    // SRC_SEQ: activation-dtype x[B][L][ld], rows t >= L read as zero
                // SRC_POS: fp32 [rows][ld], row = B*off_g + b*Lp_g + t
+               // SRC_TILED: bf16 tile-major [n_tiles*128][ld] of the tensor-core path, row = img_row0 + t
   int ld;
   int ch_off;
 };
@@ -63,7 +65,9 @@ struct ConvGemmParams {
 
 template <typename T>
 __device__ __forceinline__ float load_src(const Src& s, int B, int L, int b, int t, int Lp, int off_g,
-                                          int ch) {
+                                          int ch, size_t img_row0 = 0) {
+  if (s.kind == SRC_TILED)
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.ptr)[(img_row0 + t) * s.ld + s.ch_off + ch]);
   if (s.kind == SRC_SEQ) {
     if (t >= L) return 0.f;
     return to_f32<T>(reinterpret_cast<const T*>(s.ptr)[((size_t)b * L + t) * s.ld + s.ch_off + ch]);
@@ -96,6 +100,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
   if (g >= G) return;
   const int b = tile / tiles_g;
   const int t0 = (tile - b * tiles_g) * TM;
+  const size_t img_row0 = (size_t)(blockIdx.x - (tile - b * tiles_g)) * TM;  // first row of this image, tile-major
   const int per = pl->grp_period[g];
   const int cyc = pl->grp_cycles[g];
   const int Lp = p.L + pl->grp_pad[g];
@@ -159,7 +164,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
         int r2 = row_r[i] + dr, w2 = row_w[i] + dw;
         float v = 0.f;
         if (kc + lk < p.K1 && r2 >= 0 && r2 < cyc && w2 >= 0 && w2 < per)
-          v = load_src<T>(p.a1, p.B, p.L, b, r2 * per + w2, Lp, off_g, br.ci_off + kc + lk);
+          v = load_src<T>(p.a1, p.B, p.L, b, r2 * per + w2, Lp, off_g, br.ci_off + kc + lk, img_row0);
         As[lr0 + i * ROWS_PER_PASS][lk] = v;
       }
       load_w(wtap, p.K1, kc);
@@ -186,7 +191,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
       for (int i = 0; i < A_PASSES; ++i) {
         int t = t0 + lr0 + i * ROWS_PER_PASS;
         float v = 0.f;
-        if (kc + lk < p.K2 && t < Lp) v = load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, kc + lk);
+        if (kc + lk < p.K2 && t < Lp) v = load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, kc + lk, img_row0);
         As[lr0 + i * ROWS_PER_PASS][lk] = v;
       }
       load_w(p.w2, p.K2, kc);
@@ -205,11 +210,13 @@ conv_gemm_kernel(const ConvGemmParams p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       if (p.p2 == P2_GEMM) v += p.b2[n];
-      else if (p.p2 == P2_IDENTITY) v += load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, n);
+      else if (p.p2 == P2_IDENTITY) v += load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, n, img_row0);
       if (p.act2 >= 0) v = apply_act(v, p.act2);
       if (p.out_kind == OUT_POS) {
         size_t row = (size_t)p.B * off_g + (size_t)b * Lp + t;
         reinterpret_cast<float*>(p.out)[row * p.ldo + br.co_off + n] = v;
+      } else if (p.out_kind == OUT_TILED) {
+        reinterpret_cast<__nv_bfloat16*>(p.out)[(img_row0 + t) * p.ldo + br.co_off + n] = __float2bfloat16_rn(v);
       } else if (t < p.L) {
         v -= load_src<T>(p.xsub, p.B, p.L, b, t, Lp, off_g, n);
         reinterpret_cast<T*>(p.out)[(((size_t)g * p.B + b) * p.L + t) * p.N + n] = from_f32<T>(v);
@@ -345,14 +352,36 @@ static int period_conv_impl(const void* x, int B, int L, int C, const FtnPeriodP
   return run_block<T>(b, a2s, base, g1, g2, act, true, delta, 0, xs, max_groups, st);
 }
 
+// k x k stage of the tensor-core path on tile-major bf16 activations (SIMT math for now)
+int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                           __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
+  ConvGemmParams p{};
+  p.plan = plan; p.B = B; p.L = L;
+  p.a1 = Src{in, SRC_TILED, ld, 0}; p.K1 = w->mid; p.N = w->mid;
+  for (int j = 0; j < w->n_branch; ++j)
+    p.br[j] = Branch{w->w_kk[j], w->b_kk[j], w->kh[j], w->kw[j], j * w->mid, j * w->mid};
+  p.act1 = -1; p.p2 = P2_NONE; p.act2 = -1; p.out_kind = OUT_TILED; p.out = out; p.ldo = ld;
+  return launch_conv_gemm<__nv_bfloat16>(p, w->n_branch, max_groups, st);
+}
+
 }  // namespace ftn
 
 using namespace ftn;
 
+namespace ftn {
+bool tc_path_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b);
+size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b);
+int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                   const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
+                   cudaStream_t st);
+}  // namespace ftn
+
 extern "C" size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a,
                                                 const FtnInceptionWeights* b) {
   if (!a || !b || B <= 0 || L <= 0 || max_groups <= 0) return 256;
-  return stack_layout(B, L, max_groups, a, b).total;
+  size_t simt = stack_layout(B, L, max_groups, a, b).total;
+  size_t tcb = (a->mid > 0 && b->mid > 0) ? tc_workspace_bytes(B, L, max_groups, a, b) : 0;
+  return simt > tcb ? simt : tcb;
 }
 
 extern "C" int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
@@ -371,6 +400,8 @@ extern "C" int ftn_period_conv(const void* x, int dtype, int B, int L, int C, co
               "ftn_period_conv: workspace too small");
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_CONV, st);
+  if (tc_path_eligible(dtype, C, a, b))   // bf16 + channel counts the tensor-core tiles accept
+    return period_conv_tc(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
   if (dtype == FTN_F32)
     return period_conv_impl<float>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
   return period_conv_impl<__nv_bfloat16>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);

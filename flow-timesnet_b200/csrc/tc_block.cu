@@ -1,0 +1,89 @@
+// bf16 tensor-core orchestration of one TimesBlock's Inception chain:
+//   S1 h1 = x . W_in                      (tcgen05 GEMM, seq operand through the 3-D TMA map)
+//   S2 h2 = k x k convs of h1             (per-branch implicit GEMM)
+//   S3 a2 = act(act(h2 . W_out) + x . W_res)   (tcgen05, two accumulators, fused double activation)
+//   S4 g1 = a2 . V_in                     (tcgen05)
+//   S5 g2 = k x k convs of g1
+//   S6 delta = act(g2 . V_out) + a2 . V_res - x   (tcgen05, fused "- grid", unfold, crop, cast)
+// Activations between stages are bf16, tile-major (128 rows per tile); accumulation fp32 in TMEM.
+#include "tc_gemm.cuh"
+
+namespace ftn {
+
+static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+bool tc_path_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  if (dtype != FTN_BF16) return false;
+  const FtnInceptionWeights* ws[2] = {a, b};
+  for (const FtnInceptionWeights* w : ws) {
+    if (w->mid <= 0 || w->mid % 16 || w->cin % 16 || w->cout % 16) return false;
+    if (!w->w_in_bf16 || !w->w_out_bf16) return false;
+    if (w->w_res && !w->w_res_bf16) return false;
+  }
+  return C % 16 == 0;
+}
+
+size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  size_t rows = (size_t)tc_worst_case_tiles(B, L, max_groups) * 128;
+  size_t nbA = (size_t)a->n_branch * a->mid, nbB = (size_t)b->n_branch * b->mid;
+  return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)a->cout * 2) + 2 * al256(rows * nbB * 2) + 256;
+}
+
+int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                   const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
+                   cudaStream_t st) {
+  const int tiles = tc_worst_case_tiles(B, L, max_groups);
+  const long long rows = (long long)tiles * 128;
+  const int NBa = a->n_branch * a->mid, NBb = b->n_branch * b->mid, F = a->cout;
+  char* ws = reinterpret_cast<char*>(workspace);
+  size_t o = 0;
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBa * 2);
+  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBa * 2);
+  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * F * 2);
+  __nv_bfloat16* g1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBb * 2);
+  __nv_bfloat16* g2 = reinterpret_cast<__nv_bfloat16*>(ws + o);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+
+  TcGemmArgs base{};
+  base.plan = plan; base.B = B; base.L = L; base.max_groups = max_groups; base.n_tiles = tiles; base.act = act;
+
+  // S1
+  TcGemmArgs s = base;
+  s.a1 = xb; s.a1_seq = 1; s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in; s.K1 = C;
+  s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
+  if (int rc = tc_gemm_launch(s, st)) return rc;
+  // S2
+  if (int rc = simt_conv_tiled_launch(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc;
+  // S3
+  s = base;
+  s.a1 = h2; s.a1_seq = 0; s.a1_ld = NBa; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)a->w_out_bf16;
+  s.bias1 = a->b_out; s.K1 = NBa; s.N = F; s.epi = TC_EPI_BLOCK_A; s.out = a2; s.ldo = F;
+  if (a->w_res) {
+    s.a2 = xb; s.a2_seq = 1; s.a2_ld = C; s.w2 = (const __nv_bfloat16*)a->w_res_bf16; s.bias2 = a->b_res; s.K2 = C;
+    s.res = TC_RES_ACC2;
+  } else {
+    s.res = TC_RES_SEQ; s.res_ptr = xb; s.res_ld = C;
+  }
+  if (int rc = tc_gemm_launch(s, st)) return rc;
+  // S4
+  s = base;
+  s.a1 = a2; s.a1_seq = 0; s.a1_ld = F; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_in_bf16; s.bias1 = b->b_in;
+  s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = NBb;
+  if (int rc = tc_gemm_launch(s, st)) return rc;
+  // S5
+  if (int rc = simt_conv_tiled_launch(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc;
+  // S6
+  s = base;
+  s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;
+  s.bias1 = b->b_out; s.K1 = NBb; s.N = C; s.epi = TC_EPI_DELTA; s.out = (__nv_bfloat16*)delta; s.ldo = C;
+  s.x = xb; s.C = C;
+  if (b->w_res) {
+    s.a2 = a2; s.a2_seq = 0; s.a2_ld = F; s.a2_rows = rows; s.w2 = (const __nv_bfloat16*)b->w_res_bf16;
+    s.bias2 = b->b_res; s.K2 = F; s.res = TC_RES_ACC2;
+  } else {
+    s.res = TC_RES_POS; s.res_ptr = a2; s.res_ld = F;
+  }
+  return tc_gemm_launch(s, st);
+}
+
+}  // namespace ftn

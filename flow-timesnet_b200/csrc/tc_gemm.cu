@@ -1,0 +1,307 @@
+// K3 (bf16 path), 1x1 stages: tcgen05 / TMEM / TMA fused GEMM.
+//
+// One CTA computes a 128 (positions) x 128 (output channels) tile:
+//   warp 0 / lane 0 : TMA producer  -- cp.async.bulk.tensor tiles (128 x 64 bf16, SWIZZLE_128B)
+//                     of the activation and weight operands into a 3-stage ring
+//   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M128 N<=128 K16,
+//                     fp32 accumulators in TMEM (acc1: columns 0..127, acc2: 128..255)
+//   warps 0-3       : epilogue      -- tcgen05.ld (one row per thread), bias / GELU /
+//                     residual / "- grid", bf16 pack, 32-byte row-segment stores
+// Two CTAs fit per SM (96 KB smem, 256 TMEM columns each), so one CTA's SIMT
+// epilogue (GELU-bound) overlaps the other's MMAs.
+//
+// The fold is zero-copy: a tile is 128 consecutive time steps of one (group,
+// window) image.  For x the 3-D tensor map (C, L, B) makes rows t >= L read as
+// zeros (TMA out-of-bounds fill) -- exactly the zero tail F.pad adds in the
+// reference (timesnet.py:1017).  Intermediates live tile-major, 128 rows per
+// tile, so tile id == row block and no store needs masking.
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace ftn {
+
+using namespace tc;
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
+constexpr int TC_STAGE_BYTES = (TC_BM * TC_BK + TC_BN * TC_BK) * 2;  // 32 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcGemmKernelArgs {
+  const FtnPeriodPlan* plan;
+  int B, L, n_tiles;
+  int a1_seq, a2_seq, K1, K2, N, act, epi, res;
+  const float* bias1;
+  const float* bias2;
+  const __nv_bfloat16* res_ptr;
+  int res_ld;
+  __nv_bfloat16* out;
+  int ldo;
+  const __nv_bfloat16* x;
+  int C;
+};
+
+__global__ void __launch_bounds__(128)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
+               const TcGemmKernelArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* done = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile decode (uniform across the CTA) ----
+  int g = 0, b = 0, t0 = 0, Lp = 0;
+  const int tile_id = blockIdx.x;
+  if (p.plan) {
+    const FtnPeriodPlan* pl = p.plan;
+    const int G = pl->n_groups;
+    int tile = tile_id, tiles_g = 1;
+    for (; g < G; ++g) {
+      Lp = p.L + pl->grp_pad[g];
+      tiles_g = (Lp + TC_BM - 1) / TC_BM;
+      int n = tiles_g * p.B;
+      if (tile < n) break;
+      tile -= n;
+    }
+    if (g >= G) return;
+    b = tile / tiles_g;
+    t0 = (tile - b * tiles_g) * TC_BM;
+  } else {
+    if (tile_id >= p.n_tiles) return;
+    Lp = 0x7fffffff;
+  }
+  const int n0 = blockIdx.y * TC_BN;
+  const int n_tile = min(TC_BN, p.N - n0);
+  const int nkb1 = (p.K1 + TC_BK - 1) / TC_BK;
+  const int nkb2 = (p.K2 + TC_BK - 1) / TC_BK;
+  const uint32_t ncols = (p.K2 > 0) ? 256u : 128u;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW1);
+    if (p.K2 > 0) { prefetch_tmap(&tmA2); prefetch_tmap(&tmW2); }
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * TC_STAGE_BYTES;
+        uint8_t* sw = sa + TC_BM * TC_BK * 2;
+        mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+        const bool ph2 = kb >= nkb1;
+        const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
+        const CUtensorMap* ma = ph2 ? &tmA2 : &tmA1;
+        const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
+        if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(sa, ma, &full[s], k0, t0, b);
+        else tma_load_2d(sa, ma, &full[s], k0, tile_id * TC_BM);
+        tma_load_2d(sw, mw, &full[s], k0, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc_bf16(TC_BM, n_tile);
+      for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+        tc_fence_after();
+        const bool ph2 = kb >= nkb1;
+        const int kbl = ph2 ? kb - nkb1 : kb;
+        const int K = ph2 ? p.K2 : p.K1;
+        const int ksteps = min(TC_BK, K - kbl * TC_BK) / 16;
+        const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES);
+        const uint32_t sw = sa + TC_BM * TC_BK * 2;
+        const uint32_t d = tmem_base + (ph2 ? 128u : 0u);
+        for (int k = 0; k < ksteps; ++k)
+          mma_bf16(d, make_desc_sw128(sa + k * 32), make_desc_sw128(sw + k * 32), idesc, (kbl | k) != 0);
+        mma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+      }
+      mma_commit(done);
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: all four warps, one accumulator row per thread =====
+  mbar_wait(done, 0);
+  tc_fence_after();
+  const int r = warp * 32 + lane;
+  const int t = t0 + r;
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const size_t pos_row = (size_t)tile_id * TC_BM + r;
+  const bool row_live = t < Lp;  // rows past the image are never consumed; still written for PLAIN/BLOCK_A
+  for (int c = 0; c < n_tile; c += 16) {
+    float v[16], w[16];
+    tmem_ld16(trow + c, v);
+    if (p.res == TC_RES_ACC2) tmem_ld16(trow + 128 + c, w);
+    const int n = n0 + c;
+    uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (p.res == TC_RES_SEQ) {
+      if (t < p.L) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.res_ptr + ((size_t)b * p.L + t) * p.res_ld + n);
+        rv[0] = src[0]; rv[1] = src[1];
+      }
+    } else if (p.res == TC_RES_POS) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.res_ptr + pos_row * p.res_ld + n);
+      rv[0] = src[0]; rv[1] = src[1];
+    }
+    const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(rv);
+    uint4 xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    const bool delta_row = p.epi == TC_EPI_DELTA && t < p.L && row_live;
+    if (delta_row) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.x + ((size_t)b * p.L + t) * p.C + n);
+      xv[0] = src[0]; xv[1] = src[1];
+    }
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = v[i] + p.bias1[n + i];
+      if (p.epi != TC_EPI_PLAIN) {
+        a = act_fast(a, p.act);
+        float rs = 0.f;
+        if (p.res == TC_RES_ACC2) rs = w[i] + p.bias2[n + i];
+        else if (p.res != TC_RES_NONE) rs = __bfloat162float(rb[i]);
+        a += rs;
+        if (p.epi == TC_EPI_BLOCK_A) a = act_fast(a, p.act);
+        else a -= __bfloat162float(xb[i]);
+      }
+      v[i] = a;
+    }
+    uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+    if (p.epi == TC_EPI_DELTA) {
+      if (delta_row) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)g * p.B + b) * p.L + t) * p.C + n);
+        dst[0] = o0; dst[1] = o1;
+      }
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + pos_row * p.ldo + n);
+      dst[0] = o0; dst[1] = o1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, ncols);
+}
+
+// ---------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no libcuda link dependency)
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows][ld] bf16 row-major viewed as (inner = cols, outer = rows); box 64 x 128, 128-byte swizzle
+static int make_map_2d(CUtensorMap* m, const void* base, long long rows, int cols, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%lld cols=%d ld=%d) failed: %d", rows, cols, ld, (int)rc);
+  return 0;
+}
+
+// x[B][L][C] bf16 viewed as (C, L, B); box 64 x 128 x 1 -> rows t >= L are zero-filled
+static int make_map_seq(CUtensorMap* m, const void* base, int B, int L, int C, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(seq B=%d L=%d C=%d) failed: %d", B, L, C, (int)rc);
+  return 0;
+}
+
+int tc_worst_case_tiles(int B, int L, int max_groups) {
+  return max_groups * B * ((2 * L + TC_BM - 1) / TC_BM);
+}
+
+int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
+  FTN_REQUIRE(a.K1 > 0 && a.K1 % 16 == 0 && a.K2 % 16 == 0 && a.N % 16 == 0,
+              "tc_gemm: K1=%d K2=%d N=%d must be multiples of 16", a.K1, a.K2, a.N);
+  FTN_REQUIRE(a.a1_ld % 8 == 0 && (a.K2 == 0 || a.a2_ld % 8 == 0) && a.ldo % 8 == 0,
+              "tc_gemm: row pitches must be multiples of 8 elements (16 B)");
+  FTN_REQUIRE((a.res == TC_RES_ACC2) == (a.K2 > 0), "tc_gemm: second accumulator and K2 must come together");
+  CUtensorMap mA1, mW1, mA2, mW2;
+  if (a.a1_seq) { if (int rc = make_map_seq(&mA1, a.a1, a.B, a.L, a.K1, a.a1_ld)) return rc; }
+  else if (int rc = make_map_2d(&mA1, a.a1, a.a1_rows, a.K1, a.a1_ld)) return rc;
+  if (int rc = make_map_2d(&mW1, a.w1, a.N, a.K1, a.K1)) return rc;
+  if (a.K2 > 0) {
+    if (a.a2_seq) { if (int rc = make_map_seq(&mA2, a.a2, a.B, a.L, a.K2, a.a2_ld)) return rc; }
+    else if (int rc = make_map_2d(&mA2, a.a2, a.a2_rows, a.K2, a.a2_ld)) return rc;
+    if (int rc = make_map_2d(&mW2, a.w2, a.N, a.K2, a.K2)) return rc;
+  } else {
+    mA2 = mA1;
+    mW2 = mW1;
+  }
+  TcGemmKernelArgs k{};
+  k.plan = a.plan; k.B = a.B; k.L = a.L; k.n_tiles = a.n_tiles;
+  k.a1_seq = a.a1_seq; k.a2_seq = a.a2_seq; k.K1 = a.K1; k.K2 = a.K2; k.N = a.N; k.act = a.act; k.epi = a.epi;
+  k.res = a.res; k.bias1 = a.bias1; k.bias2 = a.bias2; k.res_ptr = a.res_ptr; k.res_ld = a.res_ld;
+  k.out = a.out; k.ldo = a.ldo; k.x = a.x; k.C = a.C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
+  dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
+  tc_gemm_kernel<<<grid, 128, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
+  FTN_LAUNCH_CHECK("tc_gemm_kernel");
+  return 0;
+}
+
+}  // namespace ftn
+
+using namespace ftn;
+
+// Unit-test entry: out[M][N] (bf16) = a[M][K] . w[N][K]^T + bias, M a multiple of 128.
+extern "C" FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
+                                           void* out, void* stream) {
+  FTN_REQUIRE(a && w && bias && out, "ftn_debug_tc_linear: null pointer");
+  FTN_REQUIRE(M > 0 && M % 128 == 0, "ftn_debug_tc_linear: M=%d must be a multiple of 128", M);
+  TcGemmArgs g{};
+  g.plan = nullptr; g.B = 1; g.L = M; g.max_groups = 1; g.n_tiles = M / 128;
+  g.a1 = (const __nv_bfloat16*)a; g.a1_seq = 0; g.a1_ld = K; g.a1_rows = M;
+  g.w1 = (const __nv_bfloat16*)w; g.bias1 = bias; g.K1 = K;
+  g.K2 = 0; g.N = N; g.act = 0; g.epi = TC_EPI_PLAIN; g.res = TC_RES_NONE;
+  g.out = (__nv_bfloat16*)out; g.ldo = N;
+  return tc_gemm_launch(g, as_stream(stream));
+}

@@ -1,0 +1,45 @@
+// Internal interface of the tcgen05 GEMM / conv kernels (bf16 tensor-core path).
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ftn {
+
+enum TcEpi { TC_EPI_PLAIN = 0, TC_EPI_BLOCK_A = 1, TC_EPI_DELTA = 2 };
+enum TcRes { TC_RES_NONE = 0, TC_RES_ACC2 = 1, TC_RES_SEQ = 2, TC_RES_POS = 3 };
+
+// One fused 1x1-conv stage on the tensor cores:
+//   acc1 = A1 . W1^T (K1),  acc2 = A2 . W2^T (K2, optional)
+//   PLAIN  : out = acc1 + bias1
+//   BLOCK_A: out = act(act(acc1 + bias1) + res)              res = acc2 + bias2 | identity
+//   DELTA  : out = act(acc1 + bias1) + res - x[b,t,:]   -> delta[g][b][t][:]  (t < L only)
+// Activations are bf16.  "pos" operands are tile-major [n_tiles * 128][ld] (tile id = CTA id,
+// decoded to (group, window, t0) through the device plan); "seq" operands are x[B][L][C],
+// rows t >= L read as zero through TMA out-of-bounds fill.
+struct TcGemmArgs {
+  const FtnPeriodPlan* plan;  // nullptr: plain GEMM over n_tiles row tiles (unit tests)
+  int B, L, max_groups, n_tiles;
+  // operand 1
+  const __nv_bfloat16* a1; int a1_seq; int a1_ld; long long a1_rows;
+  const __nv_bfloat16* w1;  // [N][K1] bf16
+  const float* bias1; int K1;
+  // operand 2 (optional)
+  const __nv_bfloat16* a2; int a2_seq; int a2_ld; long long a2_rows;
+  const __nv_bfloat16* w2;  // [N][K2]
+  const float* bias2; int K2;
+  int N, act, epi, res;
+  const __nv_bfloat16* res_ptr; int res_ld;   // TC_RES_SEQ: x (ld = C); TC_RES_POS: tile-major tensor
+  __nv_bfloat16* out; int ldo;                // PLAIN / BLOCK_A: tile-major; DELTA: delta base
+  const __nv_bfloat16* x; int C;              // DELTA: grid to subtract
+};
+
+int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st);
+int tc_worst_case_tiles(int B, int L, int max_groups);
+
+// k x k stage on tile-major bf16 activations (SIMT for now; see conv_gemm.cu)
+int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                           __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+
+}  // namespace ftn

@@ -16,6 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
+ABI_VERSION = 2
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -52,6 +53,8 @@ class FtnInceptionWeights(C.Structure):
         ("w_kk", C.c_void_p * FTN_MAX_BRANCH), ("b_kk", C.c_void_p * FTN_MAX_BRANCH),
         ("w_out", C.c_void_p), ("b_out", C.c_void_p),
         ("w_res", C.c_void_p), ("b_res", C.c_void_p),
+        ("w_in_bf16", C.c_void_p), ("w_out_bf16", C.c_void_p), ("w_res_bf16", C.c_void_p),
+        ("w_kk_bf16", C.c_void_p * FTN_MAX_BRANCH),
     ]
 
 
@@ -72,6 +75,7 @@ SIGNATURES = {
     "ftn_plan_build_host": (_I, [C.POINTER(_I64), _I, _I, _I, _I, C.POINTER(FtnPeriodPlan)]),
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
+    "ftn_debug_tc_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
     "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
@@ -101,8 +105,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = ABI drift, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ftn_version() != 1:
-        raise RuntimeError(f"libflowtimes ABI version {lib.ftn_version()} != 1")
+    if lib.ftn_version() != ABI_VERSION:
+        raise RuntimeError(f"libflowtimes ABI version {lib.ftn_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -248,6 +252,15 @@ def period_conv(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, wa: Ft
     _check(load().ftn_period_conv(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, plan_dev.data_ptr(), max_groups,
                                   C.byref(wa), C.byref(wb), act, delta.data_ptr(), ws.data_ptr(), ws.numel(),
                                   _stream()), "ftn_period_conv")
+
+
+def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    _check(load().ftn_debug_tc_linear(a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, K, N, out.data_ptr(), _stream()),
+           "ftn_debug_tc_linear")
+    return out
 
 
 def aggregate(x: torch.Tensor, delta: torch.Tensor, weights: torch.Tensor, plan_dev: torch.Tensor,

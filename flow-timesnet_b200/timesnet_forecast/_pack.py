@@ -63,6 +63,12 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         keep.append(d)
         return d.data_ptr()
 
+    def dev16(t: torch.Tensor) -> int:
+        """bf16 copy in [N][K] (K contiguous) layout for the tcgen05 path."""
+        d = t.to(torch.float32).to(torch.bfloat16).contiguous().to(device)
+        keep.append(d)
+        return d.data_ptr()
+
     st.cin, st.cout, st.n_branch = int(cin), int(cout), n_branch
     macs = 0
     if bottleneck:
@@ -72,6 +78,7 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         w_in = torch.cat([p[0].weight.detach().to("cpu", f64)[:, :, 0, 0] for p in paths], dim=0)   # [NB, cin]
         b_in = torch.cat([p[0].bias.detach().to("cpu", f64) for p in paths], dim=0)
         st.w_in, st.b_in = dev(w_in.t()), dev(b_in)
+        st.w_in_bf16 = dev16(w_in)                                           # [NB][cin]
         macs += cin * n_branch * mid
         w_out_rows = []
         b_out = proj_b.clone()
@@ -80,13 +87,16 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             kh, kw = int(wk.shape[2]), int(wk.shape[3])
             st.kh[j], st.kw[j] = kh, kw
             st.w_kk[j] = dev(wk.permute(2, 3, 1, 0).reshape(kh * kw, mid, mid))
+            st.w_kk_bf16[j] = dev16(wk.permute(2, 3, 0, 1).reshape(kh * kw, mid, mid))   # [tap][out][in]
             st.b_kk[j] = dev(p[1].bias.detach().to("cpu", f64))
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
             w_out_rows.append((P @ W3).t())                                  # [mid, cout]
             b_out = b_out + P @ p[2].bias.detach().to("cpu", f64)
-        st.w_out, st.b_out = dev(torch.cat(w_out_rows, dim=0)), dev(b_out)
+        w_out_kn = torch.cat(w_out_rows, dim=0)                              # [NB][cout]
+        st.w_out, st.b_out = dev(w_out_kn), dev(b_out)
+        st.w_out_bf16 = dev16(w_out_kn.t())                                  # [cout][NB]
         macs += n_branch * mid * cout
     else:
         st.mid = 0
@@ -111,6 +121,7 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         macs += KH * KW * cin * cout
     if isinstance(block.res_proj, nn.Conv2d):
         st.w_res = dev(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0].t())   # [cin, cout]
+        st.w_res_bf16 = dev16(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0])  # [cout][cin]
         st.b_res = dev(block.res_proj.bias.detach().to("cpu", f64))
         macs += cin * cout
     else:

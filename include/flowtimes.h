@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 1
+#define FTN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -91,6 +91,12 @@ typedef struct FtnInceptionWeights {
   const float* b_out;      /* [cout] */
   const float* w_res;      /* [cin][cout] or NULL */
   const float* b_res;      /* [cout] or NULL */
+  /* bf16 copies for the tcgen05 path, output-channel major with K contiguous
+   * ("[N][K]", the K-major B operand of tcgen05.mma); NULL = fp32 kernels only */
+  const void* w_in_bf16;   /* [n_branch*mid][cin] */
+  const void* w_out_bf16;  /* [cout][n_branch*mid] */
+  const void* w_res_bf16;  /* [cout][cin] or NULL */
+  const void* w_kk_bf16[FTN_MAX_BRANCH]; /* [kh*kw][kk_cout][kk_cin] */
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */
@@ -150,6 +156,9 @@ FTN_API int ftn_group_weights(const void* amps, int dtype, int B, int k, int amp
  * written.  max_groups bounds the launch (k_periods).  */
 FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a,
                                      const FtnInceptionWeights* b);
+/* Unit-test hook for the tcgen05 GEMM: out[M][N] bf16 = a[M][K] . w[N][K]^T + bias (M % 128 == 0) */
+FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
+                                void* out, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
                     int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b,
                     int act, void* delta, void* workspace, size_t workspace_bytes, void* stream);
