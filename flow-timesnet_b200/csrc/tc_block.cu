@@ -53,7 +53,8 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
   if (int rc = tc_gemm_launch(s, st)) return rc;
   // S2
-  if (int rc = simt_conv_tiled_launch(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc;
+  if (int rc = (tc_conv_eligible(a) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, h1, h2, NBa, a, st))
+    return rc;
   // S3
   s = base;
   s.a1 = h2; s.a1_seq = 0; s.a1_ld = NBa; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)a->w_out_bf16;
@@ -71,7 +72,8 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = NBb;
   if (int rc = tc_gemm_launch(s, st)) return rc;
   // S5
-  if (int rc = simt_conv_tiled_launch(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc;
+  if (int rc = (tc_conv_eligible(b) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, g1, g2, NBb, b, st))
+    return rc;
   // S6
   s = base;
   s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;

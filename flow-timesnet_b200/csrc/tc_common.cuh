@@ -109,6 +109,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16-byte async copy global -> shared; src_bytes = 0 writes zeros (halo / padding)
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // instruction descriptor: bf16 x bf16 -> fp32, K-major A and B, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(N >> 3) << 17) |
@@ -128,21 +144,35 @@ __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32
 }
 
 // ---- math ------------------------------------------------------------------------
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 1 rcp + 1 ex2 + 6 fma instead of
-// erff()'s branchy ~30 instructions; the GELU epilogues are SIMT-bound, not MMA-bound.
-__device__ __forceinline__ float erf_as(float x) {
-  float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Exact-erf GELU for the bf16 epilogues.  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
+// far below a bf16 ulp): 2 MUFU (rcp, ex2) + 8 FMA-pipe instructions, branch free.  erff() costs
+// ~50 instructions with branches and made the GELU epilogues 10x slower than the MMAs (ncu r1b).
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float u = v * 0.70710678118654752440f;
+  const float ax = fabsf(u);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  float e = exp2f(-1.4426950408889634f * ax * ax);
-  float y = fmaf(-p, e, 1.0f);
-  return copysignf(y, x);
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
+  const float y = fmaf(-p, e, 1.0f);          // erf(|u|)
+  const float hv = 0.5f * v;
+  return fmaf(copysignf(y, u), hv, hv);
 }
-__device__ __forceinline__ float gelu_fast(float v) { return 0.5f * v * (1.0f + erf_as(v * 0.70710678118654752440f)); }
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) { return ACT == 1 ? fmaxf(v, 0.f) : gelu_fast(v); }
 __device__ __forceinline__ float act_fast(float v, int act) { return act == 1 ? fmaxf(v, 0.f) : gelu_fast(v); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -42,4 +42,9 @@ int tc_worst_case_tiles(int B, int L, int max_groups);
 int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                            __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 
+// k x k stage on the tensor cores (tc_conv.cu); eligible for mid in {16, 32} with resident weights
+bool tc_conv_eligible(const FtnInceptionWeights* w);
+int tc_conv_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                   __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+
 }  // namespace ftn

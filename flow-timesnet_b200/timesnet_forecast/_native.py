@@ -76,6 +76,7 @@ SIGNATURES = {
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
     "ftn_debug_tc_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ftn_debug_conv_tiled": (_I, [_P, _P, _I, _P, _I, _I, _I, C.POINTER(FtnInceptionWeights), _I, _P]),
     "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
     "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
@@ -260,6 +261,14 @@ def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> tor
     out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
     _check(load().ftn_debug_tc_linear(a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, K, N, out.data_ptr(), _stream()),
            "ftn_debug_tc_linear")
+    return out
+
+
+def debug_conv_tiled(inp: torch.Tensor, plan_dev: torch.Tensor, B: int, L: int, max_groups: int,
+                     w: FtnInceptionWeights, use_tc: bool) -> torch.Tensor:
+    out = torch.zeros_like(inp)
+    _check(load().ftn_debug_conv_tiled(inp.data_ptr(), out.data_ptr(), inp.shape[1], plan_dev.data_ptr(), B, L,
+                                       max_groups, C.byref(w), int(use_tc), _stream()), "ftn_debug_conv_tiled")
     return out
 
 

@@ -159,6 +159,10 @@ FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const
 /* Unit-test hook for the tcgen05 GEMM: out[M][N] bf16 = a[M][K] . w[N][K]^T + bias (M % 128 == 0) */
 FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
                                 void* out, void* stream);
+/* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
+ * use_tc = 1 tcgen05 kernel, 0 SIMT kernel. */
+FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
+                                 int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
                     int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b,
                     int act, void* delta, void* workspace, size_t workspace_bytes, void* stream);

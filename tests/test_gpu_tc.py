@@ -25,3 +25,43 @@ def test_tc_linear_matches_fp32_matmul(M, K, N):
     out2 = nv.debug_tc_linear(a2.to(torch.bfloat16).cuda(), w.cuda(), torch.zeros(N).cuda())
     ref2 = w.float().t()[torch.arange(M) % K]
     assert torch.equal(out2.float().cpu(), ref2)
+
+
+@pytest.mark.parametrize("mid,L,periods", [(32, 336, [24, 12, 7, 48, 6]), (32, 336, [335, 100, 168]),
+                                            (16, 96, [24, 12, 7, 48, 6, 95]), (32, 28, [27, 14, 7])])
+def test_tc_conv_matches_simt_conv(mid, L, periods):
+    """k x k stage alone: tcgen05 implicit-GEMM kernel vs the fp32-math SIMT kernel on the same
+    tile-major bf16 activations (identical inputs, fp32 accumulation in both -> <= 1 bf16 ulp)."""
+    import flowtimes_synth as syn
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.models.timesnet import InceptionBlock
+    B = 3
+    C = mid * 4
+    torch.manual_seed(0)
+    blk = InceptionBlock(C, C, [(3, 3), (5, 5), (7, 7)], 0.0, "gelu", bottleneck_ratio=4.0).cuda()
+    packed = blk.packed(torch.device("cuda"))
+    assert packed.struct.mid == mid
+    plan_host = nv.plan_build_host(periods, L, None, None)
+    plan = nv.plan_to_device(plan_host, "cuda")
+    G = plan_host.n_groups
+    tiles = len(periods) * B * ((2 * L + 127) // 128)
+    NB = 3 * mid
+    g = torch.Generator().manual_seed(1)
+    inp = torch.randn(tiles * 128, NB, generator=g).to(torch.bfloat16).cuda()
+    ref = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=False)
+    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=True)
+    torch.cuda.synchronize()
+    # compare only rows that belong to an image (pad rows of a tile are never written)
+    row = 0
+    checked = 0
+    for gi in range(G):
+        Lp = L + plan_host.grp_pad[gi]
+        rt = (Lp + 127) // 128
+        for b in range(B):
+            a = ref[row:row + Lp].float()
+            c = got[row:row + Lp].float()
+            err = (a - c).abs().max().item() / max(1e-6, a.abs().max().item())
+            assert err < 1e-2, f"group {gi} (p={plan_host.grp_period[gi]}) window {b}: rel err {err:.3e}"
+            checked += Lp
+            row += rt * 128
+    assert checked > 0
