@@ -6,6 +6,8 @@
 //   S5 g2 = k x k convs of g1
 //   S6 delta = act(g2 . V_out) + a2 . V_res - x   (tcgen05, fused "- grid", unfold, crop, cast)
 // Activations between stages are bf16, tile-major (128 rows per tile); accumulation fp32 in TMEM.
+#include <stdlib.h>
+
 #include "tc_gemm.cuh"
 
 namespace ftn {
@@ -26,7 +28,7 @@ bool tc_path_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnI
 size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
   size_t rows = (size_t)tc_worst_case_tiles(B, L, max_groups) * 128;
   size_t nbA = (size_t)a->n_branch * a->mid, nbB = (size_t)b->n_branch * b->mid;
-  return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)a->cout * 2) + 2 * al256(rows * nbB * 2) + 256;
+  return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)(a->cout > a->cin ? a->cout : a->cin) * 2) + 2 * al256(rows * nbB * 2) + 256;
 }
 
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
@@ -39,7 +41,7 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   size_t o = 0;
   __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBa * 2);
   __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBa * 2);
-  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * F * 2);
+  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * (F > C ? F : C) * 2);
   __nv_bfloat16* g1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * NBb * 2);
   __nv_bfloat16* g2 = reinterpret_cast<__nv_bfloat16*>(ws + o);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -55,22 +57,30 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   // S2
   if (int rc = (tc_conv_eligible(a) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, h1, h2, NBa, a, st))
     return rc;
-  // S3
-  s = base;
-  s.a1 = h2; s.a1_seq = 0; s.a1_ld = NBa; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)a->w_out_bf16;
-  s.bias1 = a->b_out; s.K1 = NBa; s.N = F; s.epi = TC_EPI_BLOCK_A; s.out = a2; s.ldo = F;
-  if (a->w_res) {
-    s.a2 = xb; s.a2_seq = 1; s.a2_ld = C; s.w2 = (const __nv_bfloat16*)a->w_res_bf16; s.bias2 = a->b_res; s.K2 = C;
-    s.res = TC_RES_ACC2;
+  static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
+  const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
+  __nv_bfloat16* q = a2;   // the fused middle never materialises a2: its slot holds q = a2 . V_res + b (C columns)
+  if (fused_mid) {
+    // S3 + S4 + block B's res_proj in one persistent kernel (tc_mid.cu)
+    if (int rc = tc_mid_launch(plan, B, L, max_groups, h2, rows, xb, a, b, act, g1, q, st)) return rc;
   } else {
-    s.res = TC_RES_SEQ; s.res_ptr = xb; s.res_ld = C;
+    // S3
+    s = base;
+    s.a1 = h2; s.a1_seq = 0; s.a1_ld = NBa; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)a->w_out_bf16;
+    s.bias1 = a->b_out; s.K1 = NBa; s.N = F; s.epi = TC_EPI_BLOCK_A; s.out = a2; s.ldo = F;
+    if (a->w_res) {
+      s.a2 = xb; s.a2_seq = 1; s.a2_ld = C; s.w2 = (const __nv_bfloat16*)a->w_res_bf16; s.bias2 = a->b_res; s.K2 = C;
+      s.res = TC_RES_ACC2;
+    } else {
+      s.res = TC_RES_SEQ; s.res_ptr = xb; s.res_ld = C;
+    }
+    if (int rc = tc_gemm_launch(s, st)) return rc;
+    // S4
+    s = base;
+    s.a1 = a2; s.a1_seq = 0; s.a1_ld = F; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_in_bf16; s.bias1 = b->b_in;
+    s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = NBb;
+    if (int rc = tc_gemm_launch(s, st)) return rc;
   }
-  if (int rc = tc_gemm_launch(s, st)) return rc;
-  // S4
-  s = base;
-  s.a1 = a2; s.a1_seq = 0; s.a1_ld = F; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_in_bf16; s.bias1 = b->b_in;
-  s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = NBb;
-  if (int rc = tc_gemm_launch(s, st)) return rc;
   // S5
   if (int rc = (tc_conv_eligible(b) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, g1, g2, NBb, b, st))
     return rc;
@@ -79,7 +89,9 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;
   s.bias1 = b->b_out; s.K1 = NBb; s.N = C; s.epi = TC_EPI_DELTA; s.out = (__nv_bfloat16*)delta; s.ldo = C;
   s.x = xb; s.C = C;
-  if (b->w_res) {
+  if (fused_mid) {
+    s.res = TC_RES_POS; s.res_ptr = q; s.res_ld = C;
+  } else if (b->w_res) {
     s.a2 = a2; s.a2_seq = 0; s.a2_ld = F; s.a2_rows = rows; s.w2 = (const __nv_bfloat16*)b->w_res_bf16;
     s.bias2 = b->b_res; s.K2 = F; s.res = TC_RES_ACC2;
   } else {

@@ -47,4 +47,10 @@ bool tc_conv_eligible(const FtnInceptionWeights* w);
 int tc_conv_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 
+// fused middle of the chain (tc_mid.cu): h2, x -> g1 (block B k x k input) and q (block B residual)
+bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b);
+int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,
+                  const __nv_bfloat16* x, const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
+                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st);
+
 }  // namespace ftn

@@ -1,0 +1,401 @@
+// K3 (bf16 path), fused middle of the Inception chain: everything between the two k x k
+// stages in ONE persistent tcgen05 kernel, so the d_ff-wide activation never leaves the SM.
+//
+//   per 128-row tile, per 64-column chunk c of the d_ff axis
+//     U  = h2 . W_outA[c]^T            (K = n_branch*mid)   \  stage 1, accumulators U/R
+//     R  = x  . W_resA[c]^T            (K = d_model)        /  double-buffered in TMEM
+//     a2 = act(act(U + b_out) + R + b_res)   -> bf16 -> shared memory (128B-swizzled K-major)
+//     G += a2 . W_inB[:, c]^T          (N = n_branch*mid)   \  stage 2, accumulate over chunks
+//     Q += a2 . W_resB[:, c]^T         (N = d_model)        /
+//   after the last chunk:  g1 = G + b_in  (input of block B's k x k stage),  q = Q + b_res
+//   (block B's residual, consumed by the final 1x1 stage).
+//
+// Replaces InceptionBlock A's proj / act / res_proj / "+", the Sequential's middle activation
+// and InceptionBlock B's first 1x1 convs and res_proj (timesnet.py:645-654, :753, :587, :648).
+//
+// Warp roles (384 threads, one CTA per SM, 512 TMEM columns):
+//   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and two weight rings
+//   warp 1 lane 0 : MMA issuer    -- stage 1 of chunk c is issued one chunk ahead of stage 2
+//   warp 2        : TMEM allocator
+//   warps 4..11   : epilogue      -- two warps per TMEM lane quadrant, 32 columns each
+// Every hand-off is an mbarrier; tcgen05.commit releases shared-memory stages and accumulators.
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace ftn {
+
+using namespace tc;
+
+constexpr int MD_THREADS = 384;
+constexpr int MD_BM = 128;   // rows per tile
+constexpr int MD_NC = 64;    // d_ff columns per chunk
+constexpr int MD_BK = 64;    // K elements per 128-byte swizzled row
+constexpr int MD_A_KB_BYTES = MD_BM * MD_BK * 2;   // 16 KB: one K block of an activation tile
+constexpr int MD_W_KB_BYTES = MD_NC * MD_BK * 2;   // 8 KB: one K block of a stage-1 weight chunk
+constexpr int MD_A2_BYTES = MD_BM * MD_NC * 2;     // 16 KB
+
+struct TcMidKernelArgs {
+  const FtnPeriodPlan* plan;
+  int B, L;
+  int K1, K2, F, N3, N4;
+  const float* b_out;   // [F]
+  const float* b_res;   // [F]
+  const float* b_in2;   // [N3]
+  const float* b_res2;  // [N4]
+  __nv_bfloat16* g1; int ld_g1;
+  __nv_bfloat16* q;  int ld_q;
+};
+
+enum {
+  MB_A_FULL = 0, MB_A_EMPTY = 1, MB_R1_FULL = 2, MB_R1_EMPTY = 4, MB_R2_FULL = 6, MB_R2_EMPTY = 8,
+  MB_ACC_FULL = 10, MB_ACC_EMPTY = 12, MB_A2_FULL = 14, MB_A2_EMPTY = 16, MB_GQ_FULL = 18, MB_GQ_EMPTY = 19,
+  MB_COUNT = 20
+};
+
+__device__ __forceinline__ bool mid_decode_tile(const FtnPeriodPlan* pl, int B, int L, int tile, int& b, int& t0) {
+  const int G = pl->n_groups;
+  for (int g = 0; g < G; ++g) {
+    const int Lp = L + pl->grp_pad[g];
+    const int tiles_g = (Lp + MD_BM - 1) / MD_BM;
+    const int n = tiles_g * B;
+    if (tile < n) {
+      b = tile / tiles_g;
+      t0 = (tile - b * tiles_g) * MD_BM;
+      return true;
+    }
+    tile -= n;
+  }
+  return false;
+}
+
+__host__ __device__ inline uint32_t md_align1024(uint32_t v) { return (v + 1023u) & ~1023u; }
+
+template <int ACT>
+__global__ void __launch_bounds__(MD_THREADS, 1)
+tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ CUtensorMap tmX,
+              const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWr,
+              const __grid_constant__ CUtensorMap tmWi2, const __grid_constant__ CUtensorMap tmWr2,
+              const TcMidKernelArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb1 = (p.K1 + MD_BK - 1) / MD_BK, kb2 = (p.K2 + MD_BK - 1) / MD_BK;
+  const int nch = p.F / MD_NC;
+  const uint32_t r1_stage = (uint32_t)(kb1 + kb2) * MD_W_KB_BYTES;
+  const uint32_t wi2_bytes = md_align1024((uint32_t)p.N3 * 128u);
+  const uint32_t wr2_bytes = md_align1024((uint32_t)p.N4 * 128u);
+  const uint32_t r2_stage = wi2_bytes + wr2_bytes;
+
+  uint8_t* sH2 = smem;
+  uint8_t* sX = sH2 + kb1 * MD_A_KB_BYTES;
+  uint8_t* sR1 = sX + kb2 * MD_A_KB_BYTES;
+  uint8_t* sR2 = sR1 + 2 * r1_stage;
+  uint8_t* sA2 = sR2 + 2 * r2_stage;
+  float* sBias = reinterpret_cast<float*>(sA2 + 2 * MD_A2_BYTES);
+  float* sb_out = sBias;
+  float* sb_res = sb_out + p.F;
+  float* sb_in2 = sb_res + p.F;
+  float* sb_res2 = sb_in2 + p.N3;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(sb_res2 + p.N4) + 15) & ~uintptr_t(15));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + MB_COUNT);
+
+  for (int i = threadIdx.x; i < p.F; i += MD_THREADS) { sb_out[i] = p.b_out[i]; sb_res[i] = p.b_res[i]; }
+  for (int i = threadIdx.x; i < p.N3; i += MD_THREADS) sb_in2[i] = p.b_in2[i];
+  for (int i = threadIdx.x; i < p.N4; i += MD_THREADS) sb_res2[i] = p.b_res2[i];
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MB_COUNT; ++i) {
+      const bool epi_arrives = (i >= MB_ACC_EMPTY && i < MB_ACC_EMPTY + 2) || (i >= MB_A2_FULL && i < MB_A2_FULL + 2) ||
+                               i == MB_GQ_EMPTY;
+      mbar_init(&bars[i], epi_arrives ? 8u : 1u);   // 8 epilogue warps arrive, everything else one thread
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmH2); prefetch_tmap(&tmX); prefetch_tmap(&tmWo);
+    prefetch_tmap(&tmWr); prefetch_tmap(&tmWi2); prefetch_tmap(&tmWr2);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: U[s] = s*64, R[s] = 128 + s*64, G = 256, Q = 384
+  const FtnPeriodPlan* pl = p.plan;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t n = 0;
+      int it = 0;
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        int b, t0;
+        if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
+        mbar_wait(&bars[MB_A_EMPTY], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[MB_A_FULL], (uint32_t)(kb1 + kb2) * MD_A_KB_BYTES);
+        for (int kb = 0; kb < kb1; ++kb)
+          tma_load_2d(sH2 + kb * MD_A_KB_BYTES, &tmH2, &bars[MB_A_FULL], kb * MD_BK, tile * MD_BM);
+        for (int kb = 0; kb < kb2; ++kb)
+          tma_load_3d(sX + kb * MD_A_KB_BYTES, &tmX, &bars[MB_A_FULL], kb * MD_BK, t0, b);
+        for (int c = 0; c < nch; ++c, ++n) {
+          const uint32_t s = n & 1, ph = (n >> 1) & 1;
+          mbar_wait(&bars[MB_R1_EMPTY + s], ph ^ 1);
+          mbar_arrive_expect_tx(&bars[MB_R1_FULL + s], r1_stage);
+          uint8_t* d1 = sR1 + s * r1_stage;
+          for (int kb = 0; kb < kb1; ++kb)
+            tma_load_2d(d1 + kb * MD_W_KB_BYTES, &tmWo, &bars[MB_R1_FULL + s], kb * MD_BK, c * MD_NC);
+          for (int kb = 0; kb < kb2; ++kb)
+            tma_load_2d(d1 + (kb1 + kb) * MD_W_KB_BYTES, &tmWr, &bars[MB_R1_FULL + s], kb * MD_BK, c * MD_NC);
+          mbar_wait(&bars[MB_R2_EMPTY + s], ph ^ 1);
+          mbar_arrive_expect_tx(&bars[MB_R2_FULL + s], (uint32_t)(p.N3 + p.N4) * 128u);
+          uint8_t* d2 = sR2 + s * r2_stage;
+          tma_load_2d(d2, &tmWi2, &bars[MB_R2_FULL + s], c * MD_NC, 0);
+          tma_load_2d(d2 + wi2_bytes, &tmWr2, &bars[MB_R2_FULL + s], c * MD_NC, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc1 = make_idesc_bf16(MD_BM, MD_NC);
+      const uint32_t idescG = make_idesc_bf16(MD_BM, p.N3);
+      const uint32_t idescQ = make_idesc_bf16(MD_BM, p.N4);
+      const uint32_t aH2 = smem_u32(sH2), aX = smem_u32(sX), aR1 = smem_u32(sR1), aR2 = smem_u32(sR2),
+                     aA2 = smem_u32(sA2);
+      uint32_t n = 0;
+      int it = 0;
+      auto stage2 = [&](uint32_t m, int cc, int it_) {
+        const uint32_t s = m & 1, ph = (m >> 1) & 1;
+        mbar_wait(&bars[MB_R2_FULL + s], ph);
+        mbar_wait(&bars[MB_A2_FULL + s], ph);
+        if (cc == 0) mbar_wait(&bars[MB_GQ_EMPTY], (it_ & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a = aA2 + s * MD_A2_BYTES;
+        const uint32_t w = aR2 + s * r2_stage;
+#pragma unroll
+        for (int k = 0; k < MD_NC / 16; ++k)
+          mma_bf16(tmem_base + 256, make_desc_sw128(a + k * 32), make_desc_sw128(w + k * 32), idescG, (cc | k) != 0);
+#pragma unroll
+        for (int k = 0; k < MD_NC / 16; ++k)
+          mma_bf16(tmem_base + 384, make_desc_sw128(a + k * 32), make_desc_sw128(w + wi2_bytes + k * 32), idescQ,
+                   (cc | k) != 0);
+        mma_commit(&bars[MB_R2_EMPTY + s]);
+        mma_commit(&bars[MB_A2_EMPTY + s]);
+      };
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        int b, t0;
+        if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
+        mbar_wait(&bars[MB_A_FULL], it & 1);
+        for (int c = 0; c < nch; ++c, ++n) {
+          const uint32_t s = n & 1, ph = (n >> 1) & 1;
+          mbar_wait(&bars[MB_R1_FULL + s], ph);
+          mbar_wait(&bars[MB_ACC_EMPTY + s], ph ^ 1);
+          tc_fence_after();
+          const uint32_t w = aR1 + s * r1_stage;
+          for (int kb = 0; kb < kb1; ++kb) {
+            const int ks = min(MD_BK, p.K1 - kb * MD_BK) / 16;
+            for (int k = 0; k < ks; ++k)
+              mma_bf16(tmem_base + s * MD_NC, make_desc_sw128(aH2 + kb * MD_A_KB_BYTES + k * 32),
+                       make_desc_sw128(w + kb * MD_W_KB_BYTES + k * 32), idesc1, (kb | k) != 0);
+          }
+          for (int kb = 0; kb < kb2; ++kb) {
+            const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
+            for (int k = 0; k < ks; ++k)
+              mma_bf16(tmem_base + 128 + s * MD_NC, make_desc_sw128(aX + kb * MD_A_KB_BYTES + k * 32),
+                       make_desc_sw128(w + (kb1 + kb) * MD_W_KB_BYTES + k * 32), idesc1, (kb | k) != 0);
+          }
+          mma_commit(&bars[MB_R1_EMPTY + s]);
+          mma_commit(&bars[MB_ACC_FULL + s]);
+          if (c == nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
+          if (c >= 1) stage2(n - 1, c - 1, it);
+        }
+        stage2(n - 1, nch - 1, it);
+        mma_commit(&bars[MB_GQ_FULL]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;   // which 32 of the chunk's 64 columns
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t n = 0;
+    int it = 0;
+    for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+      int b, t0;
+      if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
+      for (int c = 0; c < nch; ++c, ++n) {
+        const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        mbar_wait(&bars[MB_ACC_FULL + s], ph);
+        tc_fence_after();
+        uint32_t u[32], r[32];
+        tmem_ld16_nowait(lane_base + s * MD_NC + half * 32, u);
+        tmem_ld16_nowait(lane_base + s * MD_NC + half * 32 + 16, u + 16);
+        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + half * 32, r);
+        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + half * 32 + 16, r + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY + s]);   // accumulators may be overwritten
+        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + half * 32);
+        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + half * 32);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x1 = b1[i], x2 = b2[i];
+          const float v0 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 0]) + x1.x) + __uint_as_float(r[4 * i + 0]) + x2.x);
+          const float v1 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 1]) + x1.y) + __uint_as_float(r[4 * i + 1]) + x2.y);
+          const float v2 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 2]) + x1.z) + __uint_as_float(r[4 * i + 2]) + x2.z);
+          const float v3 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 3]) + x1.w) + __uint_as_float(r[4 * i + 3]) + x2.w);
+          pk[2 * i] = pack_bf16(v0, v1);
+          pk[2 * i + 1] = pack_bf16(v2, v3);
+        }
+        mbar_wait(&bars[MB_A2_EMPTY + s], ph ^ 1);   // stage-2 MMAs of chunk n-2 finished reading this buffer
+        uint8_t* dst = sA2 + s * MD_A2_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + ((((half * 4 + j) ^ (row & 7))) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[MB_A2_FULL + s]);
+      }
+      // ---- tile drain: g1 = G + b_in2, q = Q + b_res2 (bf16, tile-major rows) ----
+      mbar_wait(&bars[MB_GQ_FULL], it & 1);
+      tc_fence_after();
+      const size_t grow = (size_t)tile * MD_BM + row;
+      {
+        const int n16 = p.N3 / 16, lo = half ? (n16 + 1) / 2 : 0, hi = half ? n16 : (n16 + 1) / 2;
+        for (int un = lo; un < hi; ++un) {
+          float v[16];
+          tmem_ld16(lane_base + 256 + un * 16, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += sb_in2[un * 16 + i];
+          uint4* dstg = reinterpret_cast<uint4*>(p.g1 + grow * p.ld_g1 + un * 16);
+          dstg[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          dstg[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        }
+      }
+      {
+        const int n16 = p.N4 / 16, lo = half ? (n16 + 1) / 2 : 0, hi = half ? n16 : (n16 + 1) / 2;
+        for (int un = lo; un < hi; ++un) {
+          float v[16];
+          tmem_ld16(lane_base + 384 + un * 16, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += sb_res2[un * 16 + i];
+          uint4* dstq = reinterpret_cast<uint4*>(p.q + grow * p.ld_q + un * 16);
+          dstq[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          dstq[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[MB_GQ_EMPTY]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn md_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [rows][ld] bf16 row-major, box = 64 columns x box_rows rows, 128-byte swizzle, zero OOB fill
+static int md_map_2d(CUtensorMap* m, const void* base, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = md_encode_fn();
+  FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)MD_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%lld cols=%d ld=%d box_rows=%d) failed: %d", rows,
+              cols, ld, box_rows, (int)rc);
+  return 0;
+}
+
+static int md_map_seq(CUtensorMap* m, const void* base, int B, int L, int C) {
+  EncodeTiledFn fn = md_encode_fn();
+  FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)MD_BK, (cuuint32_t)MD_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(seq B=%d L=%d C=%d) failed: %d", B, L, C, (int)rc);
+  return 0;
+}
+
+static size_t mid_smem_bytes(int K1, int K2, int F, int N3, int N4) {
+  const int kb1 = (K1 + MD_BK - 1) / MD_BK, kb2 = (K2 + MD_BK - 1) / MD_BK;
+  size_t s = (size_t)(kb1 + kb2) * MD_A_KB_BYTES + 2 * (size_t)(kb1 + kb2) * MD_W_KB_BYTES +
+             2 * (size_t)(md_align1024(N3 * 128) + md_align1024(N4 * 128)) + 2 * MD_A2_BYTES;
+  s += (size_t)(2 * F + N3 + N4) * 4 + 16 + MB_COUNT * 8 + 16;
+  return s + 1024;  // alignment slack
+}
+
+bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  if (a->mid <= 0 || b->mid <= 0) return false;
+  if (!a->w_out_bf16 || !a->w_res_bf16 || !b->w_in_bf16 || !b->w_res_bf16) return false;
+  const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
+  if (b->cin != F) return false;
+  if (K1 % 16 || K2 % 16 || F % MD_NC || N3 % 16 || N4 % 16) return false;
+  if (N3 > 128 || N4 > 128 || N3 < 16 || N4 < 16) return false;
+  return mid_smem_bytes(K1, K2, F, N3, N4) <= 227 * 1024;
+}
+
+int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,
+                  const __nv_bfloat16* x, const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
+                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st) {
+  FTN_REQUIRE(tc_mid_eligible(a, b), "tc_mid: unsupported channel configuration");
+  const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
+  CUtensorMap mH2, mX, mWo, mWr, mWi2, mWr2;
+  if (int rc = md_map_2d(&mH2, h2, rows, K1, K1, MD_BM)) return rc;
+  if (int rc = md_map_seq(&mX, x, B, L, K2)) return rc;
+  if (int rc = md_map_2d(&mWo, a->w_out_bf16, F, K1, K1, MD_NC)) return rc;
+  if (int rc = md_map_2d(&mWr, a->w_res_bf16, F, K2, K2, MD_NC)) return rc;
+  if (int rc = md_map_2d(&mWi2, b->w_in_bf16, N3, F, F, N3)) return rc;
+  if (int rc = md_map_2d(&mWr2, b->w_res_bf16, N4, F, F, N4)) return rc;
+  TcMidKernelArgs k{};
+  k.plan = plan; k.B = B; k.L = L; k.K1 = K1; k.K2 = K2; k.F = F; k.N3 = N3; k.N4 = N4;
+  k.b_out = a->b_out; k.b_res = a->b_res; k.b_in2 = b->b_in; k.b_res2 = b->b_res;
+  k.g1 = g1; k.ld_g1 = N3; k.q = q; k.ld_q = N4;
+  const size_t smem = mid_smem_bytes(K1, K2, F, N3, N4);
+  static size_t attr[2] = {0, 0};
+  const int ai = act == FTN_ACT_RELU ? 1 : 0;
+  if (smem > attr[ai]) {
+    if (ai) FTN_CUDA(cudaFuncSetAttribute(tc_mid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else FTN_CUDA(cudaFuncSetAttribute(tc_mid_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[ai] = smem;
+  }
+  const int worst = tc_worst_case_tiles(B, L, max_groups);
+  const int grid = worst < sm_count() ? worst : sm_count();
+  if (ai) tc_mid_kernel<1><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mWo, mWr, mWi2, mWr2, k);
+  else tc_mid_kernel<0><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mWo, mWr, mWi2, mWr2, k);
+  FTN_LAUNCH_CHECK("tc_mid_kernel");
+  return 0;
+}
+
+}  // namespace ftn
