@@ -31,6 +31,14 @@ size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeight
   return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)(a->cout > a->cin ? a->cout : a->cin) * 2) + 2 * al256(rows * nbB * 2) + 256;
 }
 
+int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
+  static const bool force_v1 = getenv("FLOWTIMES_CONV_V1") != nullptr;   // A/B switch for profiling
+  if (!force_v1 && tc_conv2_eligible(w)) return tc_conv2_launch(plan, B, L, max_groups, in, out, ld, w, st);
+  if (tc_conv_eligible(w)) return tc_conv_launch(plan, B, L, max_groups, in, out, ld, w, st);
+  return simt_conv_tiled_launch(plan, B, L, max_groups, in, out, ld, w, st);
+}
+
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
                    cudaStream_t st) {
@@ -55,8 +63,7 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
   if (int rc = tc_gemm_launch(s, st)) return rc;
   // S2
-  if (int rc = (tc_conv_eligible(a) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, h1, h2, NBa, a, st))
-    return rc;
+  if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc;
   static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
   const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
   __nv_bfloat16* q = a2;   // the fused middle never materialises a2: its slot holds q = a2 . V_res + b (C columns)
@@ -82,8 +89,7 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
     if (int rc = tc_gemm_launch(s, st)) return rc;
   }
   // S5
-  if (int rc = (tc_conv_eligible(b) ? tc_conv_launch : simt_conv_tiled_launch)(plan, B, L, max_groups, g1, g2, NBb, b, st))
-    return rc;
+  if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc;
   // S6
   s = base;
   s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;

@@ -286,6 +286,8 @@ using namespace ftn;
 extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                             int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream) {
   FTN_REQUIRE(in && out && plan && w, "ftn_debug_conv_tiled: null pointer");
+  if (use_tc == 2)
+    return tc_conv2_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream));
   if (use_tc)
     return tc_conv_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream));
   return simt_conv_tiled_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w,

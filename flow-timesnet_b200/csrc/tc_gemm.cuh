@@ -47,6 +47,14 @@ bool tc_conv_eligible(const FtnInceptionWeights* w);
 int tc_conv_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 
+// image-resident variant (tc_conv2.cu): the padded grid of one image is staged once per branch
+bool tc_conv2_eligible(const FtnInceptionWeights* w);
+int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+// picks tc_conv2 / tc_conv / SIMT for one k x k stage
+int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+
 // fused middle of the chain (tc_mid.cu): h2, x -> g1 (block B k x k input) and q (block B residual)
 bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b);
 int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,

@@ -27,9 +27,10 @@ def test_tc_linear_matches_fp32_matmul(M, K, N):
     assert torch.equal(out2.float().cpu(), ref2)
 
 
-@pytest.mark.parametrize("mid,L,periods", [(32, 336, [24, 12, 7, 48, 6]), (32, 336, [335, 100, 168]),
+@pytest.mark.parametrize("mid,L,periods", [(32, 336, [24, 12, 7, 48, 6]), (32, 336, [335, 100, 168]), (32, 336, [2, 3, 5]),
                                             (16, 96, [24, 12, 7, 48, 6, 95]), (32, 28, [27, 14, 7])])
-def test_tc_conv_matches_simt_conv(mid, L, periods):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_tc_conv_matches_simt_conv(mid, L, periods, variant):
     """k x k stage alone: tcgen05 implicit-GEMM kernel vs the fp32-math SIMT kernel on the same
     tile-major bf16 activations (identical inputs, fp32 accumulation in both -> <= 1 bf16 ulp)."""
     import flowtimes_synth as syn
@@ -49,7 +50,7 @@ def test_tc_conv_matches_simt_conv(mid, L, periods):
     g = torch.Generator().manual_seed(1)
     inp = torch.randn(tiles * 128, NB, generator=g).to(torch.bfloat16).cuda()
     ref = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=False)
-    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=True)
+    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=variant)
     torch.cuda.synchronize()
     # compare only rows that belong to an image (pad rows of a tile are never written)
     row = 0
