@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
   const FtnPeriodPlan* pl = p.plan;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
       const uint32_t idesc = make_idesc_bf16(C2_BM, mid);
       const uint32_t wbase = smem_u32(s_w);
       C2Unit u;
@@ -174,27 +174,38 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
         mbar_wait(&bars[C2_IMG_FULL + buf], par);
         tc_fence_after();
         const uint32_t abase = smem_u32(buf ? s_buf1 : s_buf0);
+        // Descriptors are advanced incrementally (start-address field, 16-byte units): per MMA the issue
+        // loop is two adds and the instruction itself, so one thread keeps the tensor pipe fed.
+        const uint64_t a_hi = make_desc_interleaved(0, LBO_A) & 0xFFFFFFFF00000000ull;
+        const uint64_t b_hi = make_desc_interleaved(0, LBO_W) & 0xFFFFFFFF00000000ull;
+        const uint32_t a_lo0 = (uint32_t)make_desc_interleaved(abase, LBO_A);
+        const uint32_t b_lo0 = (uint32_t)make_desc_interleaved(wbase, LBO_W);
+        const uint32_t ks_stride = 2 * (LBO_A >> 4);           // two 8-channel chunks per K16 step
+        const uint32_t b_step = 2 * (LBO_W >> 4);              // (tap, kstep) -> next 2 chunks of weights
         for (int m = 0; m < u.tiles; ++m) {
           const uint32_t acc = tmem_base + buf * 256 + m * 32;
-          bool first = true;
+          uint32_t accum = 0;
           for (int dr = 0; dr < kh; ++dr) {
             const int q_lo = u.q0 + m * C2_BM + (dr - hh) * u.PW - hw;
             if (q_lo + C2_BM + 2 * hw <= 0 || q_lo >= u.QT) continue;   // this row of taps only sees zero padding
             const int seg = u.mode_b ? dr * u.seg_rows + m * C2_BM
                                      : u.margin - hw + m * C2_BM + (dr - hh) * u.PW;
+            uint32_t a_lo = a_lo0 + (uint32_t)seg;
+            uint32_t b_lo = b_lo0 + (uint32_t)(dr * kw * ksteps) * b_step;
             for (int dwi = 0; dwi < kw; ++dwi) {
-              const int tap = dr * kw + dwi;
+              uint32_t a_k = a_lo;
               for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t ad = make_desc_interleaved(abase + (2 * ks) * LBO_A + (uint32_t)(seg + dwi) * 16, LBO_A);
-                const uint64_t bd = make_desc_interleaved(wbase + (uint32_t)(tap * nchunk + 2 * ks) * LBO_W, LBO_W);
-                mma_bf16(acc, ad, bd, idesc, !first);
-                first = false;
+                if (elect_one()) mma_bf16_acc(acc, a_hi | a_k, b_hi | b_lo, idesc, accum);
+                accum = 1;
+                a_k += ks_stride;
+                b_lo += b_step;
               }
+              a_lo += 1;
             }
           }
-          mma_commit(&bars[C2_TILE_FULL + buf * C2_MAX_TILES + m]);
+          if (elect_one()) mma_commit(&bars[C2_TILE_FULL + buf * C2_MAX_TILES + m]);
         }
-        mma_commit(&bars[C2_IMG_EMPTY + buf]);   // loaders may overwrite the image buffer
+        if (elect_one()) mma_commit(&bars[C2_IMG_EMPTY + buf]);   // loaders may overwrite the image buffer
       }
     }
     __syncwarp();
