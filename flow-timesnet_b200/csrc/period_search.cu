@@ -278,6 +278,10 @@ __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, i
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// spectrum_fft.cu
+int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, cudaStream_t st);
+int channel_median_reg_launch(const float* amp, int rows, int C, float* med, cudaStream_t st);
+
 }  // namespace ftn
 
 using namespace ftn;
@@ -299,22 +303,30 @@ extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float
   float* amp = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_SPECTRUM, st);
-  size_t smem = (size_t)L * kDftChannels * sizeof(float) + (size_t)L * sizeof(float2);
-  FTN_REQUIRE(smem <= 227 * 1024, "ftn_spectrum: L=%d needs %zu B of shared memory (> 227 KB)", L, smem);
-  dim3 grid((C + kDftChannels - 1) / kDftChannels, B);
-  if (dtype == FTN_F32) {
-    FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spectrum_dft_kernel<float><<<grid, kDftWarps * 32, smem, st>>>((const float*)x, L, C, F, amp);
-  } else {
-    FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spectrum_dft_kernel<__nv_bfloat16><<<grid, kDftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, F, amp);
+  int rc = spectrum_fft_launch(x, dtype, B, L, C, amp, st);   // mixed-radix FFT (even L); -1 = not applicable
+  if (rc > 0) return rc;
+  if (rc < 0) {
+    size_t smem = (size_t)L * kDftChannels * sizeof(float) + (size_t)L * sizeof(float2);
+    FTN_REQUIRE(smem <= 227 * 1024, "ftn_spectrum: L=%d needs %zu B of shared memory (> 227 KB)", L, smem);
+    dim3 grid((C + kDftChannels - 1) / kDftChannels, B);
+    if (dtype == FTN_F32) {
+      FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spectrum_dft_kernel<float><<<grid, kDftWarps * 32, smem, st>>>((const float*)x, L, C, F, amp);
+    } else {
+      FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spectrum_dft_kernel<__nv_bfloat16><<<grid, kDftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, F, amp);
+    }
+    FTN_LAUNCH_CHECK("spectrum_dft_kernel");
   }
-  FTN_LAUNCH_CHECK("spectrum_dft_kernel");
   const int rows = B * F;
-  size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);
-  FTN_CUDA(cudaFuncSetAttribute(channel_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  channel_median_kernel<<<(rows + kMedianWarps - 1) / kMedianWarps, kMedianWarps * 32, msmem, st>>>(amp, rows, C, amp_median);
-  FTN_LAUNCH_CHECK("channel_median_kernel");
+  rc = channel_median_reg_launch(amp, rows, C, amp_median, st);   // keys in registers (C <= 512)
+  if (rc > 0) return rc;
+  if (rc < 0) {
+    size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);
+    FTN_CUDA(cudaFuncSetAttribute(channel_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    channel_median_kernel<<<(rows + kMedianWarps - 1) / kMedianWarps, kMedianWarps * 32, msmem, st>>>(amp, rows, C, amp_median);
+    FTN_LAUNCH_CHECK("channel_median_kernel");
+  }
   batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum);
   FTN_LAUNCH_CHECK("batch_sum_kernel");
   return 0;

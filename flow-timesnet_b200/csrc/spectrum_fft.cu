@@ -1,0 +1,304 @@
+// K1, transform part: batched real FFT + amplitude over the time axis.
+//
+//   |rfft_t x[b, :, c]|[f]  for every window b and channel c   (timesnet.py:109-110)
+//
+// One CTA owns (window, 32-channel slab): lanes are CHANNELS, so every global load is a coalesced
+// row segment of x[b, t, c0:c0+32] and every shared-memory access is conflict free by construction.
+// The real length-L transform (L even) is done as a complex transform of length N = L/2 on
+// z[n] = x[2n] + i x[2n+1] followed by the usual even/odd split, so the working set in shared
+// memory is two ping-pong buffers of N x 32 complex values.
+// The complex transform is a mixed-radix Stockham autosort FFT (no bit reversal): hard-coded
+// radix 4 / 2 / 3 / 5 / 7 butterflies, generic O(r^2) butterfly for any other prime factor, so
+// every even L works (28 = 2.2.7, 96, 336 = 2.(4.2.3.7), 720 ...).  The 8 warps of the CTA split
+// the N/r butterflies of a pass; twiddles come from one exp(-2 pi i k / N) table in shared memory.
+// Odd L (or N too large for shared memory) falls back to the direct DFT kernel in period_search.cu.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace ftn {
+
+constexpr int kFftWarps = 8;
+constexpr int kFftMaxPass = 16;
+
+struct FftPlan {
+  int n_pass;
+  int radix[kFftMaxPass];
+};
+
+struct cplx { float x, y; };
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)}; }
+__device__ __forceinline__ cplx cmul_negi(cplx a) { return {a.y, -a.x}; }   // a * (-i)
+__device__ __forceinline__ cplx cmul_posi(cplx a) { return {-a.y, a.x}; }   // a * (+i)
+
+// odd-radix DFT with the (l, R-l) pairing: R = 3, 5, 7
+template <int R>
+__device__ __forceinline__ void dft_odd(cplx* a) {
+  constexpr int H = (R - 1) / 2;
+  constexpr float kCos[4][3] = {{0, 0, 0}, {-0.5f, 0, 0}, {0.30901699437494745f, -0.8090169943749473f, 0},
+                                {0.6234898018587336f, -0.2225209339563144f, -0.9009688679024191f}};
+  constexpr float kSin[4][3] = {{0, 0, 0}, {0.8660254037844386f, 0, 0}, {0.9510565162951535f, 0.5877852522924732f, 0},
+                                {0.7818314824680298f, 0.9749279121818236f, 0.4338837391175581f}};
+  cplx sp[H], sm[H];
+#pragma unroll
+  for (int l = 1; l <= H; ++l) { sp[l - 1] = cadd(a[l], a[R - l]); sm[l - 1] = csub(a[l], a[R - l]); }
+  cplx o0 = a[0];
+#pragma unroll
+  for (int l = 0; l < H; ++l) o0 = cadd(o0, sp[l]);
+  cplx out[R];
+  out[0] = o0;
+#pragma unroll
+  for (int i = 1; i <= H; ++i) {
+    cplx re = a[0], im = {0.f, 0.f};
+#pragma unroll
+    for (int l = 1; l <= H; ++l) {
+      int m = (i * l) % R;
+      const float sgn = m > H ? -1.f : 1.f;
+      if (m > H) m = R - m;
+      const float c = kCos[H][m - 1], s = sgn * kSin[H][m - 1];
+      re.x = fmaf(sp[l - 1].x, c, re.x); re.y = fmaf(sp[l - 1].y, c, re.y);
+      im.x = fmaf(sm[l - 1].x, s, im.x); im.y = fmaf(sm[l - 1].y, s, im.y);
+    }
+    const cplx t = cmul_negi(im);            // -i * im
+    out[i] = cadd(re, t);
+    out[R - i] = csub(re, t);
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[i] = out[i];
+}
+
+template <int R>
+__device__ __forceinline__ void dft_small(cplx* a) {
+  if constexpr (R == 2) {
+    const cplx t = a[0];
+    a[0] = cadd(t, a[1]);
+    a[1] = csub(t, a[1]);
+  } else if constexpr (R == 4) {
+    const cplx t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = cmul_negi(csub(a[1], a[3]));
+    a[0] = cadd(t0, t2); a[1] = cadd(t1, t3); a[2] = csub(t0, t2); a[3] = csub(t1, t3);
+  } else {
+    dft_odd<R>(a);
+  }
+}
+
+// one Stockham pass of radix R over the butterflies this warp owns
+template <int R>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst,
+                                         const float2* __restrict__ tw, int N, int n_cur, int s, int warp, int lane) {
+  const int m = n_cur / R;
+  const int nb = N / R;
+  for (int j = warp; j < nb; j += kFftWarps) {
+    const int p = j / s, q = j - p * s;
+    cplx a[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float2 v = src[(q + s * (p + i * m)) * 32 + lane];
+      a[i] = {v.x, v.y};
+    }
+    dft_small<R>(a);
+    float2* d = dst + (q + s * R * p) * 32 + lane;
+    d[0] = make_float2(a[0].x, a[0].y);
+#pragma unroll
+    for (int i = 1; i < R; ++i) {
+      const float2 w = tw[p * i * s];
+      const cplx o = cmul(a[i], {w.x, w.y});
+      d[i * s * 32] = make_float2(o.x, o.y);
+    }
+  }
+}
+
+// any radix: O(r^2) with the inputs re-read from shared memory
+__device__ __forceinline__ void fft_pass_generic(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                 const float2* __restrict__ tw, int N, int n_cur, int s, int r,
+                                                 int warp, int lane) {
+  const int m = n_cur / r;
+  const int nb = N / r;
+  const int wr = N / r;   // tw[(k * wr) % N] = exp(-2 pi i k / r)
+  for (int j = warp; j < nb; j += kFftWarps) {
+    const int p = j / s, q = j - p * s;
+    for (int i = 0; i < r; ++i) {
+      cplx acc = {0.f, 0.f};
+      int e = 0;   // (i * l) mod r
+      for (int l = 0; l < r; ++l) {
+        const float2 v = src[(q + s * (p + l * m)) * 32 + lane];
+        const float2 w = tw[e * wr];
+        acc = cadd(acc, cmul({v.x, v.y}, {w.x, w.y}));
+        e += i;
+        if (e >= r) e -= r;
+      }
+      const float2 w = tw[p * i * s];
+      const cplx o = cmul(acc, {w.x, w.y});
+      dst[(q + s * (r * p + i)) * 32 + lane] = make_float2(o.x, o.y);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFftWarps * 32)
+spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ amp /*[B][F][C]*/, const FftPlan plan) {
+  extern __shared__ float2 fsm[];
+  const int N = L >> 1;
+  float2* bufA = fsm;
+  float2* bufB = fsm + (size_t)N * 32;
+  float2* tw = fsm + (size_t)2 * N * 32;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
+  const T* xb = x + (size_t)b * L * C;
+
+  for (int n = warp; n < N; n += kFftWarps) {
+    float re = 0.f, im = 0.f;
+    if (c < C) {
+      re = to_f32<T>(xb[(size_t)(2 * n) * C + c]);
+      im = to_f32<T>(xb[(size_t)(2 * n + 1) * C + c]);
+    }
+    bufA[n * 32 + lane] = make_float2(re, im);
+  }
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float s, co;
+    sincospif(2.0f * (float)k / (float)N, &s, &co);
+    tw[k] = make_float2(co, -s);
+  }
+  __syncthreads();
+
+  float2* src = bufA;
+  float2* dst = bufB;
+  int n_cur = N, s = 1;
+  for (int ps = 0; ps < plan.n_pass; ++ps) {
+    const int r = plan.radix[ps];
+    switch (r) {
+      case 2: fft_pass<2>(src, dst, tw, N, n_cur, s, warp, lane); break;
+      case 3: fft_pass<3>(src, dst, tw, N, n_cur, s, warp, lane); break;
+      case 4: fft_pass<4>(src, dst, tw, N, n_cur, s, warp, lane); break;
+      case 5: fft_pass<5>(src, dst, tw, N, n_cur, s, warp, lane); break;
+      case 7: fft_pass<7>(src, dst, tw, N, n_cur, s, warp, lane); break;
+      default: fft_pass_generic(src, dst, tw, N, n_cur, s, r, warp, lane); break;
+    }
+    n_cur /= r;
+    s *= r;
+    float2* t = src; src = dst; dst = t;
+    __syncthreads();
+  }
+
+  // even/odd split: X[k] = E + exp(-2 pi i k / L) * O,  k = 0 .. N
+  const int F = N + 1;
+  if (c < C) {
+    for (int k = warp; k < F; k += kFftWarps) {
+      const int k0 = k == N ? 0 : k;
+      const int k1 = k == 0 ? 0 : N - k;
+      const float2 zk = src[k0 * 32 + lane];
+      const float2 zc = src[k1 * 32 + lane];   // conj applied below
+      const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
+      const float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);
+      const float orr = di, oi = -dr;          // O = -i * D
+      float sn, cs;
+      sincospif(2.0f * (float)k / (float)L, &sn, &cs);
+      const float xr = er + (cs * orr + sn * oi);      // W = cs - i sn
+      const float xi = ei + (cs * oi - sn * orr);
+      amp[((size_t)b * F + k) * C + c] = sqrtf(fmaf(xr, xr, xi * xi));
+    }
+  }
+}
+
+constexpr int kMedWarps = 8;
+
+__device__ __forceinline__ uint32_t fkey(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// lower median over channels, keys held in registers (C <= 32 * KPL): one warp per (window, bin)
+template <int KPL>
+__global__ void __launch_bounds__(kMedWarps * 32)
+channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float* __restrict__ med) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kMedWarps + warp;
+  if (row >= rows) return;
+  const float* a = amp + (size_t)row * C;
+  uint32_t key[KPL];
+  bool has_nan = false;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < C) {
+      const float v = a[idx];
+      has_nan = has_nan || (v != v);
+      key[i] = fkey(v);
+    } else {
+      key[i] = 0xffffffffu;   // sorts last, never selected because k < C
+    }
+  }
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  uint32_t prefix = 0, known = 0;
+  int k = (C - 1) >> 1;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t bmask = 1u << bit;
+    int cnt0 = 0;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) cnt0 += ((key[i] & known) == prefix && !(key[i] & bmask)) ? 1 : 0;
+    cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+    if (k >= cnt0) { prefix |= bmask; k -= cnt0; }
+    known |= bmask;
+  }
+  if (lane == 0) med[row] = has_nan ? CUDART_NAN_F : fkey_inv(prefix);   // torch.median propagates NaN
+}
+
+static bool fft_factor(int N, FftPlan* plan) {
+  plan->n_pass = 0;
+  auto push = [&](int r) {
+    if (plan->n_pass >= kFftMaxPass) return false;
+    plan->radix[plan->n_pass++] = r;
+    return true;
+  };
+  while (N % 4 == 0) { if (!push(4)) return false; N /= 4; }
+  while (N % 2 == 0) { if (!push(2)) return false; N /= 2; }
+  const int small[3] = {3, 5, 7};
+  for (int f : small)
+    while (N % f == 0) { if (!push(f)) return false; N /= f; }
+  for (int f = 11; N > 1; f += 2)
+    while (N % f == 0) { if (!push(f)) return false; N /= f; }
+  return true;
+}
+
+// returns 0 when the FFT path ran, -1 when the caller must use the direct DFT, > 0 on error
+int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, cudaStream_t st) {
+  if (L & 1) return -1;
+  const int N = L / 2;
+  const size_t smem = ((size_t)2 * N * 32 + N) * sizeof(float2);
+  if (smem > 227 * 1024) return -1;
+  FftPlan plan;
+  if (!fft_factor(N, &plan)) return -1;
+  dim3 grid((C + 31) / 32, B);
+  if (dtype == FTN_F32) {
+    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectrum_fft_kernel<float><<<grid, kFftWarps * 32, smem, st>>>((const float*)x, L, C, amp, plan);
+  } else {
+    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectrum_fft_kernel<__nv_bfloat16><<<grid, kFftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, amp, plan);
+  }
+  FTN_LAUNCH_CHECK("spectrum_fft_kernel");
+  return 0;
+}
+
+// returns 0 when handled, -1 when C is too large for the register variant
+int channel_median_reg_launch(const float* amp, int rows, int C, float* med, cudaStream_t st) {
+  const int grid = (rows + kMedWarps - 1) / kMedWarps;
+  if (C <= 32) channel_median_reg_kernel<1><<<grid, kMedWarps * 32, 0, st>>>(amp, rows, C, med);
+  else if (C <= 64) channel_median_reg_kernel<2><<<grid, kMedWarps * 32, 0, st>>>(amp, rows, C, med);
+  else if (C <= 128) channel_median_reg_kernel<4><<<grid, kMedWarps * 32, 0, st>>>(amp, rows, C, med);
+  else if (C <= 256) channel_median_reg_kernel<8><<<grid, kMedWarps * 32, 0, st>>>(amp, rows, C, med);
+  else if (C <= 512) channel_median_reg_kernel<16><<<grid, kMedWarps * 32, 0, st>>>(amp, rows, C, med);
+  else return -1;
+  FTN_LAUNCH_CHECK("channel_median_reg_kernel");
+  return 0;
+}
+
+}  // namespace ftn
