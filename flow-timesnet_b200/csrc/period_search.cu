@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(1024) batch_sum_kernel(const float* __restrict
     for (int i = 0; i < 32; ++i) t += part[i][fl];
     amp_sum[f] = t;
   }
+  if (blockIdx.x == 0 && r == 0 && fl == 0) amp_sum[F] = (float)B;   // window count rides along (all-reduced with the sums)
 }
 
 // rank key: larger is better; NaN ranks above everything like torch.topk
@@ -156,7 +157,8 @@ select_tail_kernel(const float* __restrict__ amp_sum, int global_batch, int L, i
   const int tid = threadIdx.x;
   // scores in the activation dtype, exactly as timesnet.py:119-130
   for (int f = tid; f < F; f += blockDim.x) {
-    float mean = amp_sum[f] / (float)global_batch;
+    const float gb = global_batch > 0 ? (float)global_batch : amp_sum[F];   // <= 0: count slot written by ftn_spectrum
+    float mean = amp_sum[f] / gb;
     float m = round_to<T>(mean);
     float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
     float sc = round_to<T>(m - pen);
@@ -338,7 +340,7 @@ extern "C" int ftn_select_periods(const float* amp_median, const float* amp_sum,
                                   void* stream) {
   FTN_REQUIRE(amp_median && amp_sum && plan && amps && weights && scores_ws, "ftn_select_periods: null pointer");
   FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_select_periods: k=%d outside [1,%d]", k, FTN_MAX_K);
-  FTN_REQUIRE(B > 0 && global_batch >= B && L > 1, "ftn_select_periods: bad sizes B=%d global=%d L=%d", B, global_batch, L);
+  FTN_REQUIRE(B > 0 && (global_batch <= 0 || global_batch >= B) && L > 1, "ftn_select_periods: bad sizes B=%d global=%d L=%d", B, global_batch, L);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_select_periods: unsupported dtype %d", dtype);
   cudaStream_t st = as_stream(stream);
   const int F = L / 2 + 1;

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -174,12 +174,12 @@ def timing_read(family: int):
 # K1
 # --------------------------------------------------------------------------- #
 def spectrum(x: torch.Tensor):
-    """x[B,L,C] -> (amp_median[B,F] fp32, amp_sum[F] fp32)."""
+    """x[B,L,C] -> (amp_median[B,F] fp32, amp_sum[F+1] fp32; the last slot is the window count B)."""
     lib = load()
     B, L, Cc = x.shape
     Fq = L // 2 + 1
     med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
-    ssum = torch.empty(Fq, dtype=torch.float32, device=x.device)
+    ssum = torch.empty(Fq + 1, dtype=torch.float32, device=x.device)
     nbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     _check(lib.ftn_spectrum(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, med.data_ptr(), ssum.data_ptr(),

@@ -37,6 +37,7 @@ from torch import nn
 
 from .. import _native as nv
 from .._pack import PackedInception, pack_inception_block, params_fingerprint
+from ..parallel import resolve_group
 
 __all__ = [
     "FFTPeriodSelector", "PeriodGroupResult", "PeriodGrouper", "InceptionBranch", "InceptionBlock", "TimesBlock",
@@ -107,11 +108,7 @@ class FFTPeriodSelector(nn.Module):
         return torch.tensor(list(h.period[: h.n_valid]), dtype=torch.long, device=self._last_plan.plan_dev.device)
 
     def _world(self):
-        import torch.distributed as dist
-        if self.process_group is False or not dist.is_available() or not dist.is_initialized():
-            return None, 1
-        group = self.process_group
-        return group, dist.get_world_size(group)
+        return resolve_group(self.process_group)
 
     def search(self, x: torch.Tensor) -> Optional[PeriodPlan]:
         """Sync-free search.  Returns None when the reference would return empty tensors."""
@@ -129,12 +126,14 @@ class FFTPeriodSelector(nn.Module):
         if k > nv.FTN_MAX_K:
             raise ValueError(f"k_periods={self.k} exceeds the supported maximum {nv.FTN_MAX_K}")
         x = nv.require_cuda(x, "x")
-        med, ssum = nv.spectrum(x)
+        med, ssum = nv.spectrum(x)                                     # ssum = [sum_b median spectrum | B]
         group, world = self._world()
         if world > 1:
             import torch.distributed as dist
-            dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=group)   # the only collective of the path
-        plan_dev, amps, weights = nv.select_periods(med, ssum, x.dtype, B * world, L, k, self.pmax,
+            # the only collective of the path: F sums + the window count in one message, so ragged
+            # shards need no host round trip (the select kernel divides by the reduced count)
+            dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=group)
+        plan_dev, amps, weights = nv.select_periods(med, ssum, x.dtype, B if world == 1 else 0, L, k, self.pmax,
                                                     self.min_period_threshold)
         self._last_plan = PeriodPlan(plan_dev, amps, weights, k)
         return self._last_plan

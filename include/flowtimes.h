@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 2
+#define FTN_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -117,16 +117,19 @@ FTN_API int ftn_timing_read(int family, double* total_ms, int* calls);
  * replaces torch.fft.rfft + abs + median(dim=2) + mean(dim=0)   timesnet.py:109-112
  *
  * ftn_spectrum: amp_median[b][f] = lower median over c of |rfft_t x[b,:,c]|[f],
- *   amp_sum[f] = sum_b amp_median[b][f]  (deterministic order; the caller
- *   all-reduces amp_sum across ranks when the batch is sharded).
- *   F = L/2 + 1.  workspace >= ftn_spectrum_workspace_bytes(). */
+ *   amp_sum[f] = sum_b amp_median[b][f]  (deterministic order), f < F = L/2 + 1, and
+ *   amp_sum[F] = B, the number of windows summed.  amp_sum therefore holds F + 1 floats;
+ *   when the batch is sharded the caller all-reduces (SUM) all F + 1 of them, which
+ *   yields the global sums and the global window count in one message.
+ *   workspace >= ftn_spectrum_workspace_bytes(). */
 FTN_API size_t ftn_spectrum_workspace_bytes(int B, int L, int C);
 FTN_API int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
                  float* amp_sum, void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces the top-k / period math of FFTPeriodSelector.forward (timesnet.py:115-159)
  * and PeriodGrouper.group in its default exact-duplicate mode (timesnet.py:513-557).
- * global_batch = number of windows amp_sum was summed over (all ranks).
+ * global_batch = number of windows amp_sum was summed over (all ranks); pass <= 0 to take
+ * it from the count slot amp_sum[F] (no host round trip after an all-reduce).
  * Tie rule for equal scores: lower bin index first (torch.topk leaves it unspecified).
  * amps: [B, k] dtype, columns >= n_valid are zero. */
 FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, int dtype, int B,

@@ -1,0 +1,215 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host-resident integer logic (plan builder, PeriodGrouper, weight packing) agrees with
+the oracle, the product path refuses CPU tensors (no fallback), and the N>1 protocol (shard the
+batch, all-reduce the batch-summed spectrum, select identically on every rank) is exercised with
+two ``gloo`` processes."""
+import os
+import re
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _header_symbols():
+    text = (ROOT / "include" / "flowtimes.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"FTN_API\s+[\w\s\*]+?\b(ftn_\w+)\s*\(", text)))
+
+
+def test_abi_exports_every_declared_symbol():
+    import ctypes
+    from timesnet_forecast import _native as nv
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    lib = ctypes.CDLL(str(nv.LIB_PATH))
+    for s in syms:
+        assert hasattr(lib, s), f"libflowtimes.so does not export {s}"
+    assert set(syms) == set(nv.SIGNATURES), "ctypes signature table and include/flowtimes.h drifted apart"
+    assert nv.load().ftn_version() == nv.ABI_VERSION
+    assert nv.PLAN_BYTES == ctypes.sizeof(nv.FtnPeriodPlan)
+
+
+def test_library_has_sm100a_code_only():
+    import subprocess
+    from timesnet_forecast import _native as nv
+    out = subprocess.run(["cuobjdump", "-lelf", str(nv.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("L,periods", [(336, [24, 12, 7, 48, 6]), (96, [24, 12, 24, 8, 12]), (28, [27, 14, 28, 0]),
+                                        (48, [47, 47, 2, 1, 100])])
+def test_host_plan_builder_matches_oracle_grouping(L, periods):
+    import flowtimes_oracle as orc
+    from timesnet_forecast import _native as nv
+    plan = nv.plan_build_host(periods, L, None, None)
+    amps = torch.ones(2, len(periods))
+    g = orc.group_periods(torch.tensor(periods), amps, L)
+    G = plan.n_groups
+    assert list(plan.grp_period[:G]) == [int(p) for p in g.periods]
+    assert list(plan.grp_pad[:G]) == [int(p) for p in g.pads]
+    assert list(plan.grp_cycles[:G]) == [int(p) for p in g.cycles]
+    assert [m for m in plan.mapping[:len(periods)]] == [int(m) for m in g.mapping]
+    off = 0
+    for i in range(G):
+        assert plan.grp_row_off[i] == off
+        off += L + plan.grp_pad[i]
+    assert plan.total_rows_per_window == off
+
+
+def test_period_grouper_class_matches_oracle():
+    import flowtimes_oracle as orc
+    from timesnet_forecast.models.timesnet import PeriodGrouper
+    torch.manual_seed(0)
+    periods = torch.tensor([8, 4, 4, 3, 3, 50])
+    amps = torch.rand(3, 6) * 4
+    res = PeriodGrouper(periods, amps, 48, min_period=1, max_period=47, block_index=0, freq_indices=None).group()
+    g = orc.group_periods(periods, amps, 48, min_period=1, max_period=47)
+    assert res.periods.tolist() == [int(p) for p in g.periods]
+    assert res.pad_lengths.tolist() == [int(p) for p in g.pads]
+    assert res.cycles.tolist() == [int(p) for p in g.cycles]
+    assert res.mapping.tolist() == [int(m) for m in g.mapping]
+    assert torch.allclose(res.logits, g.logits, atol=1e-6)
+
+
+@pytest.mark.parametrize("ratio,cin,cout", [(4.0, 16, 32), (4.0, 32, 16), (1.0, 8, 8), (2.0, 16, 16)])
+def test_weight_packing_is_exact_refactoring(ratio, cin, cout):
+    """proj o branch-out folding (and the ratio-1 union-window fold) reproduces the unfolded block."""
+    import torch.nn.functional as F
+    import flowtimes_oracle as orc
+    from timesnet_forecast._pack import pack_inception_block
+    from timesnet_forecast.models.timesnet import InceptionBlock
+    import ctypes as C
+    torch.manual_seed(1)
+    blk = InceptionBlock(cin, cout, [(3, 3), (5, 5), (7, 7)], 0.0, "gelu", bottleneck_ratio=ratio)
+    w = {"b." + k: v.detach() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, cin, 6, 9)
+    ref = orc.inception_block(x, w, "b.", "gelu")
+    pk = pack_inception_block(blk, torch.device("cpu"))
+    st = pk.struct
+
+    def arr(ptr, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        buf = (C.c_float * n).from_address(ptr)
+        return torch.frombuffer(buf, dtype=torch.float32).clone().reshape(*shape)
+
+    nb = st.n_branch
+    if st.mid > 0:
+        mid = st.mid
+        h = torch.einsum("bchw,cn->bnhw", x, arr(st.w_in, cin, nb * mid)) + arr(st.b_in, nb * mid).view(1, -1, 1, 1)
+        outs = []
+        for j in range(nb):
+            kh, kw = st.kh[j], st.kw[j]
+            wk = arr(st.w_kk[j], kh * kw, mid, mid).reshape(kh, kw, mid, mid).permute(3, 2, 0, 1)   # OIHW
+            outs.append(F.conv2d(h[:, j * mid:(j + 1) * mid], wk, arr(st.b_kk[j], mid), padding=(kh // 2, kw // 2)))
+        h2 = torch.cat(outs, 1)
+        z = torch.einsum("bchw,cn->bnhw", h2, arr(st.w_out, nb * mid, cout)) + arr(st.b_out, cout).view(1, -1, 1, 1)
+    else:
+        kh, kw = st.kh[0], st.kw[0]
+        wk = arr(st.w_kk[0], kh * kw, cin, cout).reshape(kh, kw, cin, cout).permute(3, 2, 0, 1)
+        z = F.conv2d(x, wk, arr(st.b_kk[0], cout), padding=(kh // 2, kw // 2))
+    z = F.gelu(z)
+    if st.w_res:
+        z = z + torch.einsum("bchw,cn->bnhw", x, arr(st.w_res, cin, cout)) + arr(st.b_res, cout).view(1, -1, 1, 1)
+    else:
+        z = z + x
+    assert torch.allclose(z, ref, rtol=2e-5, atol=2e-5), (z - ref).abs().max()
+
+
+def test_product_path_refuses_cpu_tensors():
+    from timesnet_forecast.losses import negative_binomial_nll
+    from timesnet_forecast.models.timesnet import FFTPeriodSelector, TimesBlock
+    blk = TimesBlock(8, [(3, 3)], 0.0, "gelu")
+    object.__setattr__(blk, "period_selector", FFTPeriodSelector(2, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(torch.randn(2, 16, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FFTPeriodSelector(2, 8)(torch.randn(2, 16, 8))
+    with pytest.raises((RuntimeError, TypeError)):
+        negative_binomial_nll(torch.ones(2, 3, 4), torch.ones(2, 3, 4), torch.ones(2, 3, 4))
+    with pytest.raises(ValueError):
+        blk(torch.randn(16, 8))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = ROOT / "flow-timesnet_b200"
+    for f in pkg.rglob("*.py"):
+        src = f.read_text()
+        assert "flowtimes_oracle" not in src, f"{f} references the oracle"
+        # docstrings cite /root/reference/...:line; nothing may put it on sys.path or open files there
+        assert not re.search(r"(sys\.path|open\(|Path\().*/root/reference", src), f"{f} reads the reference checkout"
+
+
+# --------------------------------------------------------------------------- #
+# N > 1: two gloo processes, batch sharded, spectrum sum all-reduced
+# --------------------------------------------------------------------------- #
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank: int, world: int, port: int, out_dir: str):
+    sys.path.insert(0, str(ROOT / "flow-timesnet_b200"))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import torch.distributed as dist
+    import flowtimes_oracle as orc
+    import flowtimes_synth as syn
+    from timesnet_forecast.parallel import reduce_spectrum_sum, shard_batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, L, C, k = 8, 48, 16, 3
+        x = syn.white_features(B, L, C, seed=5)              # same full batch on both ranks
+        lo, hi = shard_batch(B, rank, world)
+        med_local = orc.channel_median_spectrum(x[lo:hi])    # [B/world, F]
+        ssum = med_local.sum(dim=0)
+        total, global_b = reduce_spectrum_sum(ssum, hi - lo, None)
+        assert global_b == B
+        sel = orc.select_from_spectrum(med_local, total, global_b, L, k, L - 1, 1, x.dtype)
+        torch.save({"periods": sel.periods, "freq": sel.freq_indices, "mean": total / global_b, "lo": lo, "hi": hi},
+                   os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_period_search_selects_identically_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    import flowtimes_oracle as orc
+    import flowtimes_synth as syn
+    world = 2
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    x = syn.white_features(8, 48, 16, seed=5)
+    full = orc.select_periods(x, 3, 47, 1)
+    assert (outs[0]["lo"], outs[0]["hi"], outs[1]["lo"], outs[1]["hi"]) == (0, 4, 4, 8)
+    for o in outs:
+        assert o["periods"].tolist() == full.periods.tolist()
+        assert o["freq"].tolist() == full.freq_indices.tolist()
+        assert torch.allclose(o["mean"], full.amp_mean, rtol=1e-6, atol=1e-6)
+    assert torch.equal(outs[0]["mean"], outs[1]["mean"])     # bit-identical on every rank
+
+
+def test_shard_batch_covers_everything():
+    from timesnet_forecast.parallel import shard_batch
+    for B in (1, 7, 64, 30000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_batch(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
