@@ -63,6 +63,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// wait used by the many-warp consumer roles (epilogue, loaders): back off between polls so the
+// single MMA-issuing warp sharing the scheduler is not starved of issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    __nanosleep(64);
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  __trap();
+}
+
 // ---- TMA -------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

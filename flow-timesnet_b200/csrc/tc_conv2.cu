@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
     for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       const uint32_t par = (uint32_t)(i >> 1) & 1u;
-      mbar_wait(&bars[C2_IMG_EMPTY + buf], par ^ 1u);
+      mbar_wait_relaxed(&bars[C2_IMG_EMPTY + buf], par ^ 1u);
       const uint32_t dst0 = smem_u32(buf ? s_buf1 : s_buf0) + c * LBO_A;
       const __nv_bfloat16* img = p.in + u.img_row0 * p.ld + j * mid + c * 8;
       const int nseg = u.mode_b ? kh : 1;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
       for (int m = 0; m < u.tiles; ++m) {
         if (mid == 16 && (m & 1) != slot) continue;
         const int bi = buf * C2_MAX_TILES + m;
-        mbar_wait(&bars[C2_TILE_FULL + bi], (phase_bits >> bi) & 1u);
+        mbar_wait_relaxed(&bars[C2_TILE_FULL + bi], (phase_bits >> bi) & 1u);
         phase_bits ^= 1u << bi;
         tc_fence_after();
         float v[16];

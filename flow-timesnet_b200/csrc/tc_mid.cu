@@ -13,11 +13,12 @@
 // Replaces InceptionBlock A's proj / act / res_proj / "+", the Sequential's middle activation
 // and InceptionBlock B's first 1x1 convs and res_proj (timesnet.py:645-654, :753, :587, :648).
 //
-// Warp roles (384 threads, one CTA per SM, 512 TMEM columns):
+// Warp roles (640 threads, one CTA per SM, 512 TMEM columns):
 //   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and two weight rings
 //   warp 1 lane 0 : MMA issuer    -- stage 1 of chunk c is issued one chunk ahead of stage 2
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue      -- two warps per TMEM lane quadrant, 32 columns each
+//   warps 4..19   : epilogue      -- four warps per TMEM lane quadrant, 16 columns each (the double
+//                   exact-erf GELU is ~4x the MMA time, so the epilogue gets most of the CTA)
 // Every hand-off is an mbarrier; tcgen05.commit releases shared-memory stages and accumulators.
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
@@ -26,7 +27,8 @@ namespace ftn {
 
 using namespace tc;
 
-constexpr int MD_THREADS = 384;
+constexpr int MD_EPI_WARPS = 16;
+constexpr int MD_THREADS = (4 + MD_EPI_WARPS) * 32;
 constexpr int MD_BM = 128;   // rows per tile
 constexpr int MD_NC = 64;    // d_ff columns per chunk
 constexpr int MD_BK = 64;    // K elements per 128-byte swizzled row
@@ -108,7 +110,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
     for (int i = 0; i < MB_COUNT; ++i) {
       const bool epi_arrives = (i >= MB_ACC_EMPTY && i < MB_ACC_EMPTY + 2) || (i >= MB_A2_FULL && i < MB_A2_FULL + 2) ||
                                i == MB_GQ_EMPTY;
-      mbar_init(&bars[i], epi_arrives ? 8u : 1u);   // 8 epilogue warps arrive, everything else one thread
+      mbar_init(&bars[i], epi_arrives ? (uint32_t)MD_EPI_WARPS : 1u);   // epilogue warps arrive, everything else one thread
     }
     fence_barrier_init();
     prefetch_tmap(&tmH2); prefetch_tmap(&tmX); prefetch_tmap(&tmWo);
@@ -217,7 +219,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    const int half = (warp - 4) >> 2;   // which 32 of the chunk's 64 columns
+    const int colq = (warp - 4) >> 2;   // which 16 of the chunk's 64 columns
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t n = 0;
@@ -229,20 +231,18 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         const uint32_t s = n & 1, ph = (n >> 1) & 1;
         mbar_wait(&bars[MB_ACC_FULL + s], ph);
         tc_fence_after();
-        uint32_t u[32], r[32];
-        tmem_ld16_nowait(lane_base + s * MD_NC + half * 32, u);
-        tmem_ld16_nowait(lane_base + s * MD_NC + half * 32 + 16, u + 16);
-        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + half * 32, r);
-        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + half * 32 + 16, r + 16);
+        uint32_t u[16], r[16];
+        tmem_ld16_nowait(lane_base + s * MD_NC + colq * 16, u);
+        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + colq * 16, r);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY + s]);   // accumulators may be overwritten
-        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + half * 32);
-        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + half * 32);
-        uint32_t pk[16];
+        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + colq * 16);
+        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + colq * 16);
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float4 x1 = b1[i], x2 = b2[i];
           const float v0 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 0]) + x1.x) + __uint_as_float(r[4 * i + 0]) + x2.x);
           const float v1 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 1]) + x1.y) + __uint_as_float(r[4 * i + 1]) + x2.y);
@@ -254,8 +254,8 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         mbar_wait(&bars[MB_A2_EMPTY + s], ph ^ 1);   // stage-2 MMAs of chunk n-2 finished reading this buffer
         uint8_t* dst = sA2 + s * MD_A2_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(dst + ((((half * 4 + j) ^ (row & 7))) << 4)) =
+        for (int j = 0; j < 2; ++j)
+          *reinterpret_cast<uint4*>(dst + ((((colq * 2 + j) ^ (row & 7))) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
@@ -265,29 +265,23 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       mbar_wait(&bars[MB_GQ_FULL], it & 1);
       tc_fence_after();
       const size_t grow = (size_t)tile * MD_BM + row;
-      {
-        const int n16 = p.N3 / 16, lo = half ? (n16 + 1) / 2 : 0, hi = half ? n16 : (n16 + 1) / 2;
-        for (int un = lo; un < hi; ++un) {
-          float v[16];
-          tmem_ld16(lane_base + 256 + un * 16, v);
+      for (int un = colq; un < p.N3 / 16; un += 4) {
+        float v[16];
+        tmem_ld16(lane_base + 256 + un * 16, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += sb_in2[un * 16 + i];
-          uint4* dstg = reinterpret_cast<uint4*>(p.g1 + grow * p.ld_g1 + un * 16);
-          dstg[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          dstg[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-        }
+        for (int i = 0; i < 16; ++i) v[i] += sb_in2[un * 16 + i];
+        uint4* dstg = reinterpret_cast<uint4*>(p.g1 + grow * p.ld_g1 + un * 16);
+        dstg[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        dstg[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
       }
-      {
-        const int n16 = p.N4 / 16, lo = half ? (n16 + 1) / 2 : 0, hi = half ? n16 : (n16 + 1) / 2;
-        for (int un = lo; un < hi; ++un) {
-          float v[16];
-          tmem_ld16(lane_base + 384 + un * 16, v);
+      for (int un = colq; un < p.N4 / 16; un += 4) {
+        float v[16];
+        tmem_ld16(lane_base + 384 + un * 16, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += sb_res2[un * 16 + i];
-          uint4* dstq = reinterpret_cast<uint4*>(p.q + grow * p.ld_q + un * 16);
-          dstq[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          dstq[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-        }
+        for (int i = 0; i < 16; ++i) v[i] += sb_res2[un * 16 + i];
+        uint4* dstq = reinterpret_cast<uint4*>(p.q + grow * p.ld_q + un * 16);
+        dstq[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        dstq[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
       }
       tc_fence_before();
       __syncwarp();

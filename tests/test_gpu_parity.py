@@ -100,7 +100,9 @@ def test_selector_baseline_shapes(golden_dir, wname, kind, dname):
     o = orc.select_periods(x, c["k"], c["L"], c["mpt"])
     # batch-mean spectrum itself: fp32 DFT vs pocketfft, relative to the largest bin
     med, ssum = __import__("timesnet_forecast._native", fromlist=["x"]).spectrum(x.cuda())
-    assert _rel(ssum[1:] / c["B"], o.amp_mean[1:]) < 2e-5
+    Fq = c["L"] // 2 + 1
+    assert ssum.numel() == Fq + 1 and float(ssum[Fq]) == c["B"]      # count slot (all-reduced with the sums)
+    assert _rel(ssum[1:Fq] / c["B"], o.amp_mean[1:]) < 2e-5
     if dname == "bf16" and kind == "white":
         # bf16-rounded scores tie; torch.topk's tie order is unspecified:
         # require the same multiset of scores instead of the same bins
