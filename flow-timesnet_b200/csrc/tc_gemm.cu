@@ -5,8 +5,8 @@
 //                     of the activation and weight operands into a 3-stage ring
 //   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M128 N<=128 K16,
 //                     fp32 accumulators in TMEM (acc1: columns 0..127, acc2: 128..255)
-//   warps 0-3       : epilogue      -- tcgen05.ld (one row per thread), bias / GELU /
-//                     residual / "- grid", bf16 pack, 32-byte row-segment stores
+//   warps 0-7       : epilogue      -- tcgen05.ld (two warps per lane quadrant, one row x 16 columns
+//                     per step), bias / GELU / residual / "- grid", bf16 pack, 32-byte row-segment stores
 // Two CTAs fit per SM (96 KB smem, 256 TMEM columns each), so one CTA's SIMT
 // epilogue (GELU-bound) overlaps the other's MMAs.
 //
@@ -24,7 +24,7 @@ using namespace tc;
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_STAGE_BYTES = (TC_BM * TC_BK + TC_BN * TC_BK) * 2;  // 32 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * TC_BN * 4 /*bias*/;
 
 struct TcGemmKernelArgs {
   const FtnPeriodPlan* plan;
@@ -40,7 +40,7 @@ struct TcGemmKernelArgs {
   int C;
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                const TcGemmKernelArgs p) {
@@ -51,6 +51,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t* empty = bars + TC_STAGES;
   uint64_t* done = bars + 2 * TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+  float* s_bias1 = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + 256);
+  float* s_bias2 = s_bias1 + TC_BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -81,6 +83,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int nkb2 = (p.K2 + TC_BK - 1) / TC_BK;
   const uint32_t ncols = (p.K2 > 0) ? 256u : 128u;
 
+  if ((int)threadIdx.x < n_tile) {
+    s_bias1[threadIdx.x] = p.bias1[n0 + threadIdx.x];
+    s_bias2[threadIdx.x] = p.K2 > 0 ? p.bias2[n0 + threadIdx.x] : 0.f;
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
@@ -138,18 +144,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncwarp();
   }
 
-  // ===== epilogue: all four warps, one accumulator row per thread =====
+  // ===== epilogue: eight warps, two per TMEM lane quadrant (each takes every other 16-column group) =====
   mbar_wait(done, 0);
   tc_fence_after();
-  const int r = warp * 32 + lane;
+  const int quad = warp & 3, half = warp >> 2;
+  const int r = quad * 32 + lane;
   const int t = t0 + r;
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
   const size_t pos_row = (size_t)tile_id * TC_BM + r;
   const bool row_live = t < Lp;  // rows past the image are never consumed; still written for PLAIN/BLOCK_A
-  for (int c = 0; c < n_tile; c += 16) {
-    float v[16], w[16];
-    tmem_ld16(trow + c, v);
-    if (p.res == TC_RES_ACC2) tmem_ld16(trow + 128 + c, w);
+  const bool delta_row = p.epi == TC_EPI_DELTA && t < p.L && row_live;
+  for (int c = half * 16; c < n_tile; c += 32) {
+    uint32_t vr[16], wr[16];
+    tmem_ld16_nowait(trow + c, vr);
+    if (p.res == TC_RES_ACC2) tmem_ld16_nowait(trow + 128 + c, wr);
     const int n = n0 + c;
     uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (p.res == TC_RES_SEQ) {
@@ -163,19 +171,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(rv);
     uint4 xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    const bool delta_row = p.epi == TC_EPI_DELTA && t < p.L && row_live;
     if (delta_row) {
       const uint4* src = reinterpret_cast<const uint4*>(p.x + ((size_t)b * p.L + t) * p.C + n);
       xv[0] = src[0]; xv[1] = src[1];
     }
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
+    tmem_ld_wait();
+    float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      float a = v[i] + p.bias1[n + i];
+      float a = __uint_as_float(vr[i]) + s_bias1[c + i];
       if (p.epi != TC_EPI_PLAIN) {
         a = act_fast(a, p.act);
         float rs = 0.f;
-        if (p.res == TC_RES_ACC2) rs = w[i] + p.bias2[n + i];
+        if (p.res == TC_RES_ACC2) rs = __uint_as_float(wr[i]) + s_bias2[c + i];
         else if (p.res != TC_RES_NONE) rs = __bfloat162float(rb[i]);
         a += rs;
         if (p.epi == TC_EPI_BLOCK_A) a = act_fast(a, p.act);
@@ -283,7 +292,7 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   }
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
-  tc_gemm_kernel<<<grid, 128, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
+  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
   FTN_LAUNCH_CHECK("tc_gemm_kernel");
   return 0;
 }
