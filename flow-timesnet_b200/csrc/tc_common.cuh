@@ -123,6 +123,28 @@ __device__ __forceinline__ void mma_bf16_acc(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Descriptors as (lo, hi) 32-bit halves: hi is a per-layout constant, lo = start address (16-byte units)
+// plus layout bits, so stepping through K blocks / row shifts is a 32-bit add and the issue loop stays
+// ~6 instructions per MMA (a lone issuing warp that rebuilds 64-bit descriptors per MMA is slower than
+// the tensor pipe -- measured: 27-33 instructions per MMA starved both tc_conv2 and tc_mid).
+constexpr uint32_t kDescSw128Hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_sw128_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// dynamic shared memory base rounded up WITHOUT losing the shared address space (a cast through
+// uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
+__device__ __forceinline__ uint8_t* align_smem(uint8_t* raw, uint32_t align) {
+  return raw + ((align - (smem_u32(raw) & (align - 1))) & (align - 1));
+}
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

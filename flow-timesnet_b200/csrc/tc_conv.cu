@@ -81,7 +81,7 @@ __device__ __forceinline__ int fast_div(int q, int d, float inv) {
 
 __global__ void __launch_bounds__(CV_THREADS, 1) tc_conv_kernel(const TcConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = align_smem(smem_raw, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- which branch does this CTA serve ----

@@ -112,7 +112,7 @@ enum { C2_IMG_FULL = 0, C2_IMG_EMPTY = 2, C2_ACC_EMPTY = 4, C2_TILE_FULL = 6, C2
 
 __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Args p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = align_smem(smem_raw, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int j = 0;

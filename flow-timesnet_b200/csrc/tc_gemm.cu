@@ -45,7 +45,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                const TcGemmKernelArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem(smem_raw, 1024);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + TC_STAGES;
@@ -121,8 +121,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
       const uint32_t idesc = make_idesc_bf16(TC_BM, n_tile);
       for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
         const int s = kb % TC_STAGES;
@@ -132,14 +132,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int kbl = ph2 ? kb - nkb1 : kb;
         const int K = ph2 ? p.K2 : p.K1;
         const int ksteps = min(TC_BK, K - kbl * TC_BK) / 16;
-        const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES);
-        const uint32_t sw = sa + TC_BM * TC_BK * 2;
+        const uint32_t sa = desc_sw128_lo(smem_u32(smem + s * TC_STAGE_BYTES));
+        const uint32_t sw = sa + ((TC_BM * TC_BK * 2) >> 4);
         const uint32_t d = tmem_base + (ph2 ? 128u : 0u);
         for (int k = 0; k < ksteps; ++k)
-          mma_bf16(d, make_desc_sw128(sa + k * 32), make_desc_sw128(sw + k * 32), idesc, (kbl | k) != 0);
-        mma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          if (elect_one())
+            mma_bf16_lohi(d, sa + k * 2, kDescSw128Hi, sw + k * 2, kDescSw128Hi, idesc, (kbl | k) != 0 ? 1u : 0u);
+        if (elect_one()) mma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        __syncwarp();
       }
-      mma_commit(done);
+      if (elect_one()) mma_commit(done);
     }
     __syncwarp();
   }

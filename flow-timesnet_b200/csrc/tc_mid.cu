@@ -14,12 +14,16 @@
 // and InceptionBlock B's first 1x1 convs and res_proj (timesnet.py:645-654, :753, :587, :648).
 //
 // Warp roles (640 threads, one CTA per SM, 512 TMEM columns):
-//   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and two weight rings
-//   warp 1 lane 0 : MMA issuer    -- stage 1 of chunk c is issued one chunk ahead of stage 2
+//   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and the stage-1 weight ring
+//   warp 3 lane 0 : TMA producer  -- stage-2 weight ring
+//   warp 1 lane 0 : MMA issuer    -- stage 1 of chunk n is issued two chunks ahead of stage 2
 //   warp 2        : TMEM allocator
 //   warps 4..19   : epilogue      -- four warps per TMEM lane quadrant, 16 columns each (the double
 //                   exact-erf GELU is ~4x the MMA time, so the epilogue gets most of the CTA)
 // Every hand-off is an mbarrier; tcgen05.commit releases shared-memory stages and accumulators.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -46,6 +50,7 @@ struct TcMidKernelArgs {
   const float* b_res2;  // [N4]
   __nv_bfloat16* g1; int ld_g1;
   __nv_bfloat16* q;  int ld_q;
+  long long* trace;   // debug (FLOWTIMES_MID_TRACE): CTA 0 records (event, chunk, clock) triples
 };
 
 enum {
@@ -70,23 +75,26 @@ __device__ __forceinline__ bool mid_decode_tile(const FtnPeriodPlan* pl, int B, 
   return false;
 }
 
+#define MD_TRACE(ev, n)                                                                        \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && (n) < 256) p.trace[(ev) * 256 + (n)] = clock64();       \
+  } while (0)
+
 __host__ __device__ inline uint32_t md_align1024(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 template <int ACT>
 __global__ void __launch_bounds__(MD_THREADS, 1)
 tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ CUtensorMap tmX,
-              const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWr,
-              const __grid_constant__ CUtensorMap tmWi2, const __grid_constant__ CUtensorMap tmWr2,
+              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
               const TcMidKernelArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem(smem_raw, 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb1 = (p.K1 + MD_BK - 1) / MD_BK, kb2 = (p.K2 + MD_BK - 1) / MD_BK;
   const int nch = p.F / MD_NC;
   const uint32_t r1_stage = (uint32_t)(kb1 + kb2) * MD_W_KB_BYTES;
-  const uint32_t wi2_bytes = md_align1024((uint32_t)p.N3 * 128u);
-  const uint32_t wr2_bytes = md_align1024((uint32_t)p.N4 * 128u);
-  const uint32_t r2_stage = wi2_bytes + wr2_bytes;
+  const uint32_t wi2_bytes = (uint32_t)p.N3 * 128u;          // N3 % 8 == 0 keeps the second operand 1024-byte aligned
+  const uint32_t r2_stage = md_align1024((uint32_t)(p.N3 + p.N4) * 128u);
 
   uint8_t* sH2 = smem;
   uint8_t* sX = sH2 + kb1 * MD_A_KB_BYTES;
@@ -98,8 +106,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   float* sb_res = sb_out + p.F;
   float* sb_in2 = sb_res + p.F;
   float* sb_res2 = sb_in2 + p.N3;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      (reinterpret_cast<uintptr_t>(sb_res2 + p.N4) + 15) & ~uintptr_t(15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(sb_res2 + p.N4), 16));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + MB_COUNT);
 
   for (int i = threadIdx.x; i < p.F; i += MD_THREADS) { sb_out[i] = p.b_out[i]; sb_res[i] = p.b_res[i]; }
@@ -113,8 +120,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       mbar_init(&bars[i], epi_arrives ? (uint32_t)MD_EPI_WARPS : 1u);   // epilogue warps arrive, everything else one thread
     }
     fence_barrier_init();
-    prefetch_tmap(&tmH2); prefetch_tmap(&tmX); prefetch_tmap(&tmWo);
-    prefetch_tmap(&tmWr); prefetch_tmap(&tmWi2); prefetch_tmap(&tmWr2);
+    prefetch_tmap(&tmH2); prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -124,14 +130,22 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   // TMEM columns: U[s] = s*64, R[s] = 128 + s*64, G = 256, Q = 384
   const FtnPeriodPlan* pl = p.plan;
 
+  // tiles this CTA owns (static round-robin), used to run the chunk stream across tile boundaries
+  int my_tiles = 0;
+  {
+    int b_, t_;
+    for (int tile = blockIdx.x; mid_decode_tile(pl, p.B, p.L, tile, b_, t_); tile += gridDim.x) ++my_tiles;
+  }
+  const uint32_t n_total = (uint32_t)my_tiles * (uint32_t)nch;
+
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer 1: activation tiles + stage-1 weight ring =====================
       uint32_t n = 0;
       int it = 0;
-      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; it < my_tiles; tile += gridDim.x, ++it) {
         int b, t0;
-        if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
+        mid_decode_tile(pl, p.B, p.L, tile, b, t0);
         mbar_wait(&bars[MB_A_EMPTY], (it & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[MB_A_FULL], (uint32_t)(kb1 + kb2) * MD_A_KB_BYTES);
         for (int kb = 0; kb < kb1; ++kb)
@@ -142,77 +156,116 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
           const uint32_t s = n & 1, ph = (n >> 1) & 1;
           mbar_wait(&bars[MB_R1_EMPTY + s], ph ^ 1);
           mbar_arrive_expect_tx(&bars[MB_R1_FULL + s], r1_stage);
-          uint8_t* d1 = sR1 + s * r1_stage;
-          for (int kb = 0; kb < kb1; ++kb)
-            tma_load_2d(d1 + kb * MD_W_KB_BYTES, &tmWo, &bars[MB_R1_FULL + s], kb * MD_BK, c * MD_NC);
-          for (int kb = 0; kb < kb2; ++kb)
-            tma_load_2d(d1 + (kb1 + kb) * MD_W_KB_BYTES, &tmWr, &bars[MB_R1_FULL + s], kb * MD_BK, c * MD_NC);
-          mbar_wait(&bars[MB_R2_EMPTY + s], ph ^ 1);
-          mbar_arrive_expect_tx(&bars[MB_R2_FULL + s], (uint32_t)(p.N3 + p.N4) * 128u);
-          uint8_t* d2 = sR2 + s * r2_stage;
-          tma_load_2d(d2, &tmWi2, &bars[MB_R2_FULL + s], c * MD_NC, 0);
-          tma_load_2d(d2 + wi2_bytes, &tmWr2, &bars[MB_R2_FULL + s], c * MD_NC, 0);
+          // one box = the whole stage image of chunk c (a TMA issue costs ~400 cycles whatever its size)
+          tma_load_2d(sR1 + s * r1_stage, &tmW1, &bars[MB_R1_FULL + s], 0, c * (kb1 + kb2) * MD_NC);
+          MD_TRACE(1, n);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 3) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
+      // ===================== TMA producer 2: stage-2 weight ring (independent of producer 1, so a
+      // stage-1 prefetch never queues behind a stage-2 slot that is still being read) ==============
+      for (uint32_t n = 0; n < n_total; ++n) {
+        const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        const int c = (int)(n % (uint32_t)nch);
+        mbar_wait(&bars[MB_R2_EMPTY + s], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[MB_R2_FULL + s], (uint32_t)(p.N3 + p.N4) * 128u);
+        tma_load_2d(sR2 + s * r2_stage, &tmW2, &bars[MB_R2_FULL + s], 0, c * (p.N3 + p.N4));
+        MD_TRACE(2, n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    {
+      // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
+      // Chunk stream n = tile_iteration * nch + c.  Stage 1 runs TWO chunks ahead of stage 2:
+      //   S1(n) needs only the accumulator pair n&1 to be drained (early in epilogue n-2), so by the
+      //   time the epilogue warps finish chunk n-1 the accumulators of chunk n are already complete
+      //   and the epilogue never waits on the tensor pipe.
       const uint32_t idesc1 = make_idesc_bf16(MD_BM, MD_NC);
       const uint32_t idescG = make_idesc_bf16(MD_BM, p.N3);
       const uint32_t idescQ = make_idesc_bf16(MD_BM, p.N4);
-      const uint32_t aH2 = smem_u32(sH2), aX = smem_u32(sX), aR1 = smem_u32(sR1), aR2 = smem_u32(sR2),
-                     aA2 = smem_u32(sA2);
-      uint32_t n = 0;
-      int it = 0;
-      auto stage2 = [&](uint32_t m, int cc, int it_) {
-        const uint32_t s = m & 1, ph = (m >> 1) & 1;
-        mbar_wait(&bars[MB_R2_FULL + s], ph);
-        mbar_wait(&bars[MB_A2_FULL + s], ph);
-        if (cc == 0) mbar_wait(&bars[MB_GQ_EMPTY], (it_ & 1) ^ 1);
+      const uint32_t loH2 = desc_sw128_lo(smem_u32(sH2)), loX = desc_sw128_lo(smem_u32(sX)),
+                     loR1 = desc_sw128_lo(smem_u32(sR1)), loR2 = desc_sw128_lo(smem_u32(sR2)),
+                     loA2 = desc_sw128_lo(smem_u32(sA2));
+      constexpr uint32_t A_KB = MD_A_KB_BYTES >> 4, W_KB = MD_W_KB_BYTES >> 4, KSTEP = 32 >> 4;
+      auto stage1 = [&](uint32_t n) {
+        const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        const uint32_t it = n / (uint32_t)nch, c = n - it * (uint32_t)nch;
+        if (c == 0) mbar_wait(&bars[MB_A_FULL], it & 1);
+        if (lane == 0) MD_TRACE(10, n);
+        mbar_wait(&bars[MB_R1_FULL + s], ph);
+        if (lane == 0) MD_TRACE(11, n);
+        mbar_wait(&bars[MB_ACC_EMPTY + s], ph ^ 1);
+        if (lane == 0) MD_TRACE(12, n);
         tc_fence_after();
-        const uint32_t a = aA2 + s * MD_A2_BYTES;
-        const uint32_t w = aR2 + s * r2_stage;
-#pragma unroll
-        for (int k = 0; k < MD_NC / 16; ++k)
-          mma_bf16(tmem_base + 256, make_desc_sw128(a + k * 32), make_desc_sw128(w + k * 32), idescG, (cc | k) != 0);
-#pragma unroll
-        for (int k = 0; k < MD_NC / 16; ++k)
-          mma_bf16(tmem_base + 384, make_desc_sw128(a + k * 32), make_desc_sw128(w + wi2_bytes + k * 32), idescQ,
-                   (cc | k) != 0);
-        mma_commit(&bars[MB_R2_EMPTY + s]);
-        mma_commit(&bars[MB_A2_EMPTY + s]);
-      };
-      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
-        int b, t0;
-        if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
-        mbar_wait(&bars[MB_A_FULL], it & 1);
-        for (int c = 0; c < nch; ++c, ++n) {
-          const uint32_t s = n & 1, ph = (n >> 1) & 1;
-          mbar_wait(&bars[MB_R1_FULL + s], ph);
-          mbar_wait(&bars[MB_ACC_EMPTY + s], ph ^ 1);
-          tc_fence_after();
-          const uint32_t w = aR1 + s * r1_stage;
-          for (int kb = 0; kb < kb1; ++kb) {
-            const int ks = min(MD_BK, p.K1 - kb * MD_BK) / 16;
-            for (int k = 0; k < ks; ++k)
-              mma_bf16(tmem_base + s * MD_NC, make_desc_sw128(aH2 + kb * MD_A_KB_BYTES + k * 32),
-                       make_desc_sw128(w + kb * MD_W_KB_BYTES + k * 32), idesc1, (kb | k) != 0);
+        const uint32_t w = loR1 + s * (r1_stage >> 4);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < kb1; ++kb) {
+          const int ks = min(MD_BK, p.K1 - kb * MD_BK) / 16;
+          for (int k = 0; k < ks; ++k) {
+            if (elect_one())
+              mma_bf16_lohi(tmem_base + s * MD_NC, loH2 + kb * A_KB + k * KSTEP, kDescSw128Hi,
+                            w + kb * W_KB + k * KSTEP, kDescSw128Hi, idesc1, acc);
+            acc = 1;
           }
-          for (int kb = 0; kb < kb2; ++kb) {
-            const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
-            for (int k = 0; k < ks; ++k)
-              mma_bf16(tmem_base + 128 + s * MD_NC, make_desc_sw128(aX + kb * MD_A_KB_BYTES + k * 32),
-                       make_desc_sw128(w + (kb1 + kb) * MD_W_KB_BYTES + k * 32), idesc1, (kb | k) != 0);
+        }
+        acc = 0;
+        for (int kb = 0; kb < kb2; ++kb) {
+          const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
+          for (int k = 0; k < ks; ++k) {
+            if (elect_one())
+              mma_bf16_lohi(tmem_base + 128 + s * MD_NC, loX + kb * A_KB + k * KSTEP, kDescSw128Hi,
+                            w + (kb1 + kb) * W_KB + k * KSTEP, kDescSw128Hi, idesc1, acc);
+            acc = 1;
           }
+        }
+        if (elect_one()) {
           mma_commit(&bars[MB_R1_EMPTY + s]);
           mma_commit(&bars[MB_ACC_FULL + s]);
-          if (c == nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
-          if (c >= 1) stage2(n - 1, c - 1, it);
+          if (c == (uint32_t)nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
         }
-        stage2(n - 1, nch - 1, it);
-        mma_commit(&bars[MB_GQ_FULL]);
+        __syncwarp();
+        if (lane == 0) MD_TRACE(13, n);
+      };
+      auto stage2 = [&](uint32_t m) {
+        const uint32_t s = m & 1, ph = (m >> 1) & 1;
+        const uint32_t it = m / (uint32_t)nch, cc = m - it * (uint32_t)nch;
+        if (lane == 0) MD_TRACE(20, m);
+        mbar_wait(&bars[MB_R2_FULL + s], ph);
+        if (lane == 0) MD_TRACE(21, m);
+        mbar_wait(&bars[MB_A2_FULL + s], ph);
+        if (cc == 0) mbar_wait(&bars[MB_GQ_EMPTY], (it & 1) ^ 1);
+        if (lane == 0) MD_TRACE(22, m);
+        tc_fence_after();
+        const uint32_t a = loA2 + s * (MD_A2_BYTES >> 4);
+        const uint32_t w = loR2 + s * (r2_stage >> 4);
+#pragma unroll
+        for (int k = 0; k < MD_NC / 16; ++k)
+          if (elect_one())
+            mma_bf16_lohi(tmem_base + 256, a + k * KSTEP, kDescSw128Hi, w + k * KSTEP, kDescSw128Hi, idescG,
+                          (cc | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < MD_NC / 16; ++k)
+          if (elect_one())
+            mma_bf16_lohi(tmem_base + 384, a + k * KSTEP, kDescSw128Hi, w + (wi2_bytes >> 4) + k * KSTEP, kDescSw128Hi,
+                          idescQ, (cc | k) != 0 ? 1u : 0u);
+        if (elect_one()) {
+          mma_commit(&bars[MB_R2_EMPTY + s]);
+          mma_commit(&bars[MB_A2_EMPTY + s]);
+          if (cc == (uint32_t)nch - 1) mma_commit(&bars[MB_GQ_FULL]);
+        }
+        __syncwarp();
+        if (lane == 0) MD_TRACE(23, m);
+      };
+      for (uint32_t n = 0; n < n_total + 2; ++n) {
+        // a tile's first stage 1 waits for its activation TMA: let the previous tile's stage 2 go first
+        const bool tile_start = n >= 2 && n < n_total && n % (uint32_t)nch == 0;
+        if (tile_start) stage2(n - 2);
+        if (n < n_total) stage1(n);
+        if (n >= 2 && !tile_start) stage2(n - 2);
       }
     }
     __syncwarp();
@@ -229,7 +282,9 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
       for (int c = 0; c < nch; ++c, ++n) {
         const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(30 + (warp == 19) * 10, n);
         mbar_wait(&bars[MB_ACC_FULL + s], ph);
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(31 + (warp == 19) * 10, n);
         tc_fence_after();
         uint32_t u[16], r[16];
         tmem_ld16_nowait(lane_base + s * MD_NC + colq * 16, u);
@@ -238,6 +293,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY + s]);   // accumulators may be overwritten
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(32 + (warp == 19) * 10, n);
         const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + colq * 16);
         const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + colq * 16);
         uint32_t pk[8];
@@ -251,7 +307,9 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
           pk[2 * i] = pack_bf16(v0, v1);
           pk[2 * i + 1] = pack_bf16(v2, v3);
         }
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(33 + (warp == 19) * 10, n);
         mbar_wait(&bars[MB_A2_EMPTY + s], ph ^ 1);   // stage-2 MMAs of chunk n-2 finished reading this buffer
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(34 + (warp == 19) * 10, n);
         uint8_t* dst = sA2 + s * MD_A2_BYTES + row * 128;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -260,6 +318,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[MB_A2_FULL + s]);
+        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(35 + (warp == 19) * 10, n);
       }
       // ---- tile drain: g1 = G + b_in2, q = Q + b_res2 (bf16, tile-major rows) ----
       mbar_wait(&bars[MB_GQ_FULL], it & 1);
@@ -345,18 +404,19 @@ static int md_map_seq(CUtensorMap* m, const void* base, int B, int L, int C) {
 static size_t mid_smem_bytes(int K1, int K2, int F, int N3, int N4) {
   const int kb1 = (K1 + MD_BK - 1) / MD_BK, kb2 = (K2 + MD_BK - 1) / MD_BK;
   size_t s = (size_t)(kb1 + kb2) * MD_A_KB_BYTES + 2 * (size_t)(kb1 + kb2) * MD_W_KB_BYTES +
-             2 * (size_t)(md_align1024(N3 * 128) + md_align1024(N4 * 128)) + 2 * MD_A2_BYTES;
+             2 * (size_t)md_align1024((N3 + N4) * 128) + 2 * MD_A2_BYTES;
   s += (size_t)(2 * F + N3 + N4) * 4 + 16 + MB_COUNT * 8 + 16;
   return s + 1024;  // alignment slack
 }
 
 bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
   if (a->mid <= 0 || b->mid <= 0) return false;
-  if (!a->w_out_bf16 || !a->w_res_bf16 || !b->w_in_bf16 || !b->w_res_bf16) return false;
+  if (!a->w_mid_first || !b->w_mid_second) return false;
   const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
   if (b->cin != F) return false;
   if (K1 % 16 || K2 % 16 || F % MD_NC || N3 % 16 || N4 % 16) return false;
   if (N3 > 128 || N4 > 128 || N3 < 16 || N4 < 16) return false;
+  if (((K1 + 63) / 64 + (K2 + 63) / 64) * MD_NC > 256 || N3 + N4 > 256) return false;   // one TMA box per stage
   return mid_smem_bytes(K1, K2, F, N3, N4) <= 227 * 1024;
 }
 
@@ -365,17 +425,21 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
                   __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st) {
   FTN_REQUIRE(tc_mid_eligible(a, b), "tc_mid: unsupported channel configuration");
   const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
-  CUtensorMap mH2, mX, mWo, mWr, mWi2, mWr2;
+  CUtensorMap mH2, mX, mW1, mW2;
+  const int kbs = (K1 + 63) / 64 + (K2 + 63) / 64;
   if (int rc = md_map_2d(&mH2, h2, rows, K1, K1, MD_BM)) return rc;
   if (int rc = md_map_seq(&mX, x, B, L, K2)) return rc;
-  if (int rc = md_map_2d(&mWo, a->w_out_bf16, F, K1, K1, MD_NC)) return rc;
-  if (int rc = md_map_2d(&mWr, a->w_res_bf16, F, K2, K2, MD_NC)) return rc;
-  if (int rc = md_map_2d(&mWi2, b->w_in_bf16, N3, F, F, N3)) return rc;
-  if (int rc = md_map_2d(&mWr2, b->w_res_bf16, N4, F, F, N4)) return rc;
+  // packed stage images: [F/64 chunks][rows per chunk][64] bf16, one box per chunk
+  if (int rc = md_map_2d(&mW1, a->w_mid_first, (long long)(F / MD_NC) * kbs * MD_NC, MD_BK, MD_BK, kbs * MD_NC)) return rc;
+  if (int rc = md_map_2d(&mW2, b->w_mid_second, (long long)(F / MD_NC) * (N3 + N4), MD_BK, MD_BK, N3 + N4)) return rc;
   TcMidKernelArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K1 = K1; k.K2 = K2; k.F = F; k.N3 = N3; k.N4 = N4;
   k.b_out = a->b_out; k.b_res = a->b_res; k.b_in2 = b->b_in; k.b_res2 = b->b_res;
   k.g1 = g1; k.ld_g1 = N3; k.q = q; k.ld_q = N4;
+  static const char* trace_path = getenv("FLOWTIMES_MID_TRACE");
+  static long long* trace_dev = nullptr;
+  if (trace_path && !trace_dev) { cudaMalloc(&trace_dev, (64 * 256) * sizeof(long long)); }
+  if (trace_dev) { cudaMemsetAsync(trace_dev, 0, (64 * 256) * sizeof(long long), st); k.trace = trace_dev; }
   const size_t smem = mid_smem_bytes(K1, K2, F, N3, N4);
   static size_t attr[2] = {0, 0};
   const int ai = act == FTN_ACT_RELU ? 1 : 0;
@@ -386,9 +450,20 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   }
   const int worst = tc_worst_case_tiles(B, L, max_groups);
   const int grid = worst < sm_count() ? worst : sm_count();
-  if (ai) tc_mid_kernel<1><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mWo, mWr, mWi2, mWr2, k);
-  else tc_mid_kernel<0><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mWo, mWr, mWi2, mWr2, k);
+  if (ai) tc_mid_kernel<1><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mW1, mW2, k);
+  else tc_mid_kernel<0><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mW1, mW2, k);
   FTN_LAUNCH_CHECK("tc_mid_kernel");
+  if (trace_dev) {   // debug only: dump the timeline of CTA 0 (synchronises!)
+    cudaStreamSynchronize(st);
+    static long long host[64 * 256];
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int ev = 0; ev < 64; ++ev)
+        for (int n = 0; n < 256; ++n)
+          if (host[ev * 256 + n]) fprintf(f, "%d %d %lld\n", ev, n, host[ev * 256 + n]);
+      fclose(f);
+    }
+  }
   return 0;
 }
 

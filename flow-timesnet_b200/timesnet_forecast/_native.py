@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -55,6 +55,7 @@ class FtnInceptionWeights(C.Structure):
         ("w_res", C.c_void_p), ("b_res", C.c_void_p),
         ("w_in_bf16", C.c_void_p), ("w_out_bf16", C.c_void_p), ("w_res_bf16", C.c_void_p),
         ("w_kk_bf16", C.c_void_p * FTN_MAX_BRANCH),
+        ("w_mid_first", C.c_void_p), ("w_mid_second", C.c_void_p),
     ]
 
 

@@ -126,6 +126,28 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         macs += cin * cout
     else:
         st.w_res, st.b_res = None, None
+    st.w_mid_first, st.w_mid_second = None, None
+    if bottleneck and isinstance(block.res_proj, nn.Conv2d):
+        # stage images of the fused middle kernel (tc_mid.cu), see include/flowtimes.h
+        NB = n_branch * int(st.mid)
+        w_res_nk = block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0]          # [cout][cin]
+        w_out_nk = w_out_kn.t()                                                        # [cout][NB]
+
+        def kblocks(w_nk: torch.Tensor) -> torch.Tensor:                               # [N][K] -> [N/64][kb][64][64]
+            N_, K_ = w_nk.shape
+            kb = (K_ + 63) // 64
+            padded = torch.zeros(N_, kb * 64, dtype=f64)
+            padded[:, :K_] = w_nk
+            return padded.reshape(N_ // 64, 64, kb, 64).permute(0, 2, 1, 3)
+
+        if cout % 64 == 0:
+            first = torch.cat([kblocks(w_out_nk), kblocks(w_res_nk)], dim=1)           # [cout/64][kb1+kb2][64][64]
+            st.w_mid_first = dev16(first)
+        if cin % 64 == 0:
+            w_in_nk = w_in                                                             # [NB][cin]
+            both = torch.cat([w_in_nk, w_res_nk], dim=0)                               # [NB+cout][cin]
+            second = both.reshape(NB + cout, cin // 64, 64).permute(1, 0, 2)           # [cin/64][NB+cout][64]
+            st.w_mid_second = dev16(second)
     return PackedInception(st, keep, macs)
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 3
+#define FTN_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -97,6 +97,16 @@ typedef struct FtnInceptionWeights {
   const void* w_out_bf16;  /* [cout][n_branch*mid] */
   const void* w_res_bf16;  /* [cout][cin] or NULL */
   const void* w_kk_bf16[FTN_MAX_BRANCH]; /* [kh*kw][kk_cout][kk_cin] */
+  /* Shared-memory stage images for the fused middle kernel (one TMA box per 64-column chunk of
+   * d_ff; a TMA issue costs ~400 cycles whatever its size, so chunks are streamed as single boxes).
+   * Only used when this block is the FIRST (w_mid_first) / SECOND (w_mid_second) of the pair:
+   *   w_mid_first : [cout/64][kb1+kb2][64][64], blocks kb < kb1: w_out[c*64+n][kb*64+k], then
+   *                 kb2 blocks of w_res[c*64+n][kb*64+k]; K zero-padded to multiples of 64
+   *   w_mid_second: [cin/64][n_branch*mid + cout][64]: rows n < n_branch*mid: w_in[n][c*64+k],
+   *                 then rows of w_res[n][c*64+k]
+   * NULL = the fused middle kernel is not used with this block. */
+  const void* w_mid_first;
+  const void* w_mid_second;
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */
