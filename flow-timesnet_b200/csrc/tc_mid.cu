@@ -1,25 +1,33 @@
 // K3 (bf16 path), fused middle of the Inception chain: everything between the two k x k
 // stages in ONE persistent tcgen05 kernel, so the d_ff-wide activation never leaves the SM.
 //
-//   per 128-row tile, per 64-column chunk c of the d_ff axis
-//     U  = h2 . W_outA[c]^T            (K = n_branch*mid)   \  stage 1, accumulators U/R
-//     R  = x  . W_resA[c]^T            (K = d_model)        /  double-buffered in TMEM
+//   per 128-row tile, per 128-column chunk c of the d_ff axis
+//     U  = h2 . W_outA[c]^T            (K = n_branch*mid, N = 128)   \  stage 1
+//     R  = x  . W_resA[c]^T            (K = d_model,      N = 128)   /
 //     a2 = act(act(U + b_out) + R + b_res)   -> bf16 -> shared memory (128B-swizzled K-major)
-//     G += a2 . W_inB[:, c]^T          (N = n_branch*mid)   \  stage 2, accumulate over chunks
-//     Q += a2 . W_resB[:, c]^T         (N = d_model)        /
+//     [G | Q] += a2 . [W_inB ; W_resB][:, c]^T      (one MMA stream, N = n_branch*mid + d_model)
 //   after the last chunk:  g1 = G + b_in  (input of block B's k x k stage),  q = Q + b_res
 //   (block B's residual, consumed by the final 1x1 stage).
 //
 // Replaces InceptionBlock A's proj / act / res_proj / "+", the Sequential's middle activation
 // and InceptionBlock B's first 1x1 convs and res_proj (timesnet.py:645-654, :753, :587, :648).
 //
-// Warp roles (640 threads, one CTA per SM, 512 TMEM columns):
-//   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and the stage-1 weight ring
-//   warp 3 lane 0 : TMA producer  -- stage-2 weight ring
-//   warp 1 lane 0 : MMA issuer    -- stage 1 of chunk n is issued two chunks ahead of stage 2
+// Shape of the pipeline (all measured on B200):
+//   * a tcgen05.mma with A and B in shared memory costs ~64 cycles for ANY N <= 128, so stage 1 uses
+//     N = 128 and stage 2 concatenates G and Q into one N = 224 stream -- 30 MMAs per 128 columns
+//     instead of 44, all at full tensor rate;
+//   * a TMA issue costs ~400 cycles whatever the box size, so each weight stage is two boxes of a
+//     pre-packed stage image (FtnInceptionWeights::w_mid_first / w_mid_second);
+//   * the double GELU epilogue is ~2x the MMA time, so every buffer is single-buffered (the MMAs of
+//     chunk c+1 / c hide completely under the epilogue of chunk c / c+1) and 16 of the 20 warps are
+//     epilogue warps.
+//
+// Warp roles (640 threads, one CTA per SM, 512 TMEM columns: U 0..127, R 128..255, G|Q 256..):
+//   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and the stage-1 weight stage
+//   warp 3 lane 0 : TMA producer  -- stage-2 weight stage
+//   warp 1        : MMA issuer    -- warp-uniform loop, one elected lane issues
 //   warp 2        : TMEM allocator
-//   warps 4..19   : epilogue      -- four warps per TMEM lane quadrant, 16 columns each (the double
-//                   exact-erf GELU is ~4x the MMA time, so the epilogue gets most of the CTA)
+//   warps 4..19   : epilogue      -- four warps per TMEM lane quadrant, 32 columns each
 // Every hand-off is an mbarrier; tcgen05.commit releases shared-memory stages and accumulators.
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,11 +42,11 @@ using namespace tc;
 constexpr int MD_EPI_WARPS = 16;
 constexpr int MD_THREADS = (4 + MD_EPI_WARPS) * 32;
 constexpr int MD_BM = 128;   // rows per tile
-constexpr int MD_NC = 64;    // d_ff columns per chunk
+constexpr int MD_NC = 128;   // d_ff columns per chunk
 constexpr int MD_BK = 64;    // K elements per 128-byte swizzled row
 constexpr int MD_A_KB_BYTES = MD_BM * MD_BK * 2;   // 16 KB: one K block of an activation tile
-constexpr int MD_W_KB_BYTES = MD_NC * MD_BK * 2;   // 8 KB: one K block of a stage-1 weight chunk
-constexpr int MD_A2_BYTES = MD_BM * MD_NC * 2;     // 16 KB
+constexpr int MD_W_KB_BYTES = MD_NC * MD_BK * 2;   // 16 KB: one K block of a stage-1 weight chunk
+constexpr int MD_A2_BYTES = MD_BM * MD_NC * 2;     // 32 KB: a2 chunk, two K blocks
 
 struct TcMidKernelArgs {
   const FtnPeriodPlan* plan;
@@ -50,14 +58,18 @@ struct TcMidKernelArgs {
   const float* b_res2;  // [N4]
   __nv_bfloat16* g1; int ld_g1;
   __nv_bfloat16* q;  int ld_q;
-  long long* trace;   // debug (FLOWTIMES_MID_TRACE): CTA 0 records (event, chunk, clock) triples
+  long long* trace;     // debug (FLOWTIMES_MID_TRACE): CTA 0 records clock64() per (event, chunk)
 };
 
 enum {
-  MB_A_FULL = 0, MB_A_EMPTY = 1, MB_R1_FULL = 2, MB_R1_EMPTY = 4, MB_R2_FULL = 6, MB_R2_EMPTY = 8,
-  MB_ACC_FULL = 10, MB_ACC_EMPTY = 12, MB_A2_FULL = 14, MB_A2_EMPTY = 16, MB_GQ_FULL = 18, MB_GQ_EMPTY = 19,
-  MB_COUNT = 20
+  MB_A_FULL = 0, MB_A_EMPTY, MB_R1_FULL, MB_R1_EMPTY, MB_R2_FULL, MB_R2_EMPTY,
+  MB_ACC_FULL, MB_ACC_EMPTY, MB_A2_FULL, MB_A2_EMPTY, MB_GQ_FULL, MB_GQ_EMPTY, MB_COUNT
 };
+
+#define MD_TRACE(ev, n)                                                                        \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && (n) < 256) p.trace[(ev) * 256 + (n)] = clock64();       \
+  } while (0)
 
 __device__ __forceinline__ bool mid_decode_tile(const FtnPeriodPlan* pl, int B, int L, int tile, int& b, int& t0) {
   const int G = pl->n_groups;
@@ -75,11 +87,6 @@ __device__ __forceinline__ bool mid_decode_tile(const FtnPeriodPlan* pl, int B, 
   return false;
 }
 
-#define MD_TRACE(ev, n)                                                                        \
-  do {                                                                                        \
-    if (p.trace && blockIdx.x == 0 && (n) < 256) p.trace[(ev) * 256 + (n)] = clock64();       \
-  } while (0)
-
 __host__ __device__ inline uint32_t md_align1024(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 template <int ACT>
@@ -92,17 +99,16 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb1 = (p.K1 + MD_BK - 1) / MD_BK, kb2 = (p.K2 + MD_BK - 1) / MD_BK;
   const int nch = p.F / MD_NC;
-  const uint32_t r1_stage = (uint32_t)(kb1 + kb2) * MD_W_KB_BYTES;
-  const uint32_t wi2_bytes = (uint32_t)p.N3 * 128u;          // N3 % 8 == 0 keeps the second operand 1024-byte aligned
-  const uint32_t r2_stage = md_align1024((uint32_t)(p.N3 + p.N4) * 128u);
+  const int N34 = p.N3 + p.N4;
+  const uint32_t r1_bytes = (uint32_t)(kb1 + kb2) * MD_W_KB_BYTES;
+  const uint32_t w2_kb_bytes = md_align1024((uint32_t)N34 * 128u);   // one K block of the stage-2 image
 
   uint8_t* sH2 = smem;
   uint8_t* sX = sH2 + kb1 * MD_A_KB_BYTES;
   uint8_t* sR1 = sX + kb2 * MD_A_KB_BYTES;
-  uint8_t* sR2 = sR1 + 2 * r1_stage;
-  uint8_t* sA2 = sR2 + 2 * r2_stage;
-  float* sBias = reinterpret_cast<float*>(sA2 + 2 * MD_A2_BYTES);
-  float* sb_out = sBias;
+  uint8_t* sR2 = sR1 + r1_bytes;
+  uint8_t* sA2 = sR2 + 2 * w2_kb_bytes;
+  float* sb_out = reinterpret_cast<float*>(sA2 + MD_A2_BYTES);
   float* sb_res = sb_out + p.F;
   float* sb_in2 = sb_res + p.F;
   float* sb_res2 = sb_in2 + p.N3;
@@ -115,8 +121,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < MB_COUNT; ++i) {
-      const bool epi_arrives = (i >= MB_ACC_EMPTY && i < MB_ACC_EMPTY + 2) || (i >= MB_A2_FULL && i < MB_A2_FULL + 2) ||
-                               i == MB_GQ_EMPTY;
+      const bool epi_arrives = i == MB_ACC_EMPTY || i == MB_A2_FULL || i == MB_GQ_EMPTY;
       mbar_init(&bars[i], epi_arrives ? (uint32_t)MD_EPI_WARPS : 1u);   // epilogue warps arrive, everything else one thread
     }
     fence_barrier_init();
@@ -127,10 +132,10 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: U[s] = s*64, R[s] = 128 + s*64, G = 256, Q = 384
   const FtnPeriodPlan* pl = p.plan;
 
-  // tiles this CTA owns (static round-robin), used to run the chunk stream across tile boundaries
+  // tiles this CTA owns (static round-robin); the chunk stream n = tile_iteration * nch + c runs
+  // across tile boundaries
   int my_tiles = 0;
   {
     int b_, t_;
@@ -140,7 +145,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer 1: activation tiles + stage-1 weight ring =====================
+      // ===================== TMA producer 1: activation tiles + stage-1 weights =====================
       uint32_t n = 0;
       int it = 0;
       for (int tile = blockIdx.x; it < my_tiles; tile += gridDim.x, ++it) {
@@ -153,11 +158,11 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         for (int kb = 0; kb < kb2; ++kb)
           tma_load_3d(sX + kb * MD_A_KB_BYTES, &tmX, &bars[MB_A_FULL], kb * MD_BK, t0, b);
         for (int c = 0; c < nch; ++c, ++n) {
-          const uint32_t s = n & 1, ph = (n >> 1) & 1;
-          mbar_wait(&bars[MB_R1_EMPTY + s], ph ^ 1);
-          mbar_arrive_expect_tx(&bars[MB_R1_FULL + s], r1_stage);
-          // one box = the whole stage image of chunk c (a TMA issue costs ~400 cycles whatever its size)
-          tma_load_2d(sR1 + s * r1_stage, &tmW1, &bars[MB_R1_FULL + s], 0, c * (kb1 + kb2) * MD_NC);
+          mbar_wait(&bars[MB_R1_EMPTY], (n & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[MB_R1_FULL], r1_bytes);
+          // the stage image of chunk c is (kb1+kb2) x 128 rows of 128 B, streamed as 256-row boxes
+          for (int kb = 0; kb < kb1 + kb2; kb += 2)
+            tma_load_2d(sR1 + kb * MD_W_KB_BYTES, &tmW1, &bars[MB_R1_FULL], 0, (c * (kb1 + kb2) + kb) * MD_NC);
           MD_TRACE(1, n);
         }
       }
@@ -165,160 +170,146 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 3) {
     if (lane == 0) {
-      // ===================== TMA producer 2: stage-2 weight ring (independent of producer 1, so a
-      // stage-1 prefetch never queues behind a stage-2 slot that is still being read) ==============
+      // ===================== TMA producer 2: stage-2 weights =====================
       for (uint32_t n = 0; n < n_total; ++n) {
-        const uint32_t s = n & 1, ph = (n >> 1) & 1;
         const int c = (int)(n % (uint32_t)nch);
-        mbar_wait(&bars[MB_R2_EMPTY + s], ph ^ 1);
-        mbar_arrive_expect_tx(&bars[MB_R2_FULL + s], (uint32_t)(p.N3 + p.N4) * 128u);
-        tma_load_2d(sR2 + s * r2_stage, &tmW2, &bars[MB_R2_FULL + s], 0, c * (p.N3 + p.N4));
+        mbar_wait(&bars[MB_R2_EMPTY], (n & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[MB_R2_FULL], 2u * (uint32_t)N34 * 128u);
+        tma_load_2d(sR2, &tmW2, &bars[MB_R2_FULL], 0, (c * 2 + 0) * N34);
+        tma_load_2d(sR2 + w2_kb_bytes, &tmW2, &bars[MB_R2_FULL], 0, (c * 2 + 1) * N34);
         MD_TRACE(2, n);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    {
-      // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
-      // Chunk stream n = tile_iteration * nch + c.  Stage 1 runs TWO chunks ahead of stage 2:
-      //   S1(n) needs only the accumulator pair n&1 to be drained (early in epilogue n-2), so by the
-      //   time the epilogue warps finish chunk n-1 the accumulators of chunk n are already complete
-      //   and the epilogue never waits on the tensor pipe.
-      const uint32_t idesc1 = make_idesc_bf16(MD_BM, MD_NC);
-      const uint32_t idescG = make_idesc_bf16(MD_BM, p.N3);
-      const uint32_t idescQ = make_idesc_bf16(MD_BM, p.N4);
-      const uint32_t loH2 = desc_sw128_lo(smem_u32(sH2)), loX = desc_sw128_lo(smem_u32(sX)),
-                     loR1 = desc_sw128_lo(smem_u32(sR1)), loR2 = desc_sw128_lo(smem_u32(sR2)),
-                     loA2 = desc_sw128_lo(smem_u32(sA2));
-      constexpr uint32_t A_KB = MD_A_KB_BYTES >> 4, W_KB = MD_W_KB_BYTES >> 4, KSTEP = 32 >> 4;
-      auto stage1 = [&](uint32_t n) {
-        const uint32_t s = n & 1, ph = (n >> 1) & 1;
-        const uint32_t it = n / (uint32_t)nch, c = n - it * (uint32_t)nch;
-        if (c == 0) mbar_wait(&bars[MB_A_FULL], it & 1);
-        if (lane == 0) MD_TRACE(10, n);
-        mbar_wait(&bars[MB_R1_FULL + s], ph);
-        if (lane == 0) MD_TRACE(11, n);
-        mbar_wait(&bars[MB_ACC_EMPTY + s], ph ^ 1);
-        if (lane == 0) MD_TRACE(12, n);
-        tc_fence_after();
-        const uint32_t w = loR1 + s * (r1_stage >> 4);
-        uint32_t acc = 0;
-        for (int kb = 0; kb < kb1; ++kb) {
-          const int ks = min(MD_BK, p.K1 - kb * MD_BK) / 16;
-          for (int k = 0; k < ks; ++k) {
-            if (elect_one())
-              mma_bf16_lohi(tmem_base + s * MD_NC, loH2 + kb * A_KB + k * KSTEP, kDescSw128Hi,
-                            w + kb * W_KB + k * KSTEP, kDescSw128Hi, idesc1, acc);
-            acc = 1;
-          }
-        }
-        acc = 0;
-        for (int kb = 0; kb < kb2; ++kb) {
-          const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
-          for (int k = 0; k < ks; ++k) {
-            if (elect_one())
-              mma_bf16_lohi(tmem_base + 128 + s * MD_NC, loX + kb * A_KB + k * KSTEP, kDescSw128Hi,
-                            w + (kb1 + kb) * W_KB + k * KSTEP, kDescSw128Hi, idesc1, acc);
-            acc = 1;
-          }
-        }
-        if (elect_one()) {
-          mma_commit(&bars[MB_R1_EMPTY + s]);
-          mma_commit(&bars[MB_ACC_FULL + s]);
-          if (c == (uint32_t)nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
-        }
-        __syncwarp();
-        if (lane == 0) MD_TRACE(13, n);
-      };
-      auto stage2 = [&](uint32_t m) {
-        const uint32_t s = m & 1, ph = (m >> 1) & 1;
-        const uint32_t it = m / (uint32_t)nch, cc = m - it * (uint32_t)nch;
-        if (lane == 0) MD_TRACE(20, m);
-        mbar_wait(&bars[MB_R2_FULL + s], ph);
-        if (lane == 0) MD_TRACE(21, m);
-        mbar_wait(&bars[MB_A2_FULL + s], ph);
-        if (cc == 0) mbar_wait(&bars[MB_GQ_EMPTY], (it & 1) ^ 1);
-        if (lane == 0) MD_TRACE(22, m);
-        tc_fence_after();
-        const uint32_t a = loA2 + s * (MD_A2_BYTES >> 4);
-        const uint32_t w = loR2 + s * (r2_stage >> 4);
-#pragma unroll
-        for (int k = 0; k < MD_NC / 16; ++k)
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
+    const uint32_t idesc1 = make_idesc_bf16(MD_BM, MD_NC);
+    const uint32_t idesc2 = make_idesc_bf16(MD_BM, N34);
+    const uint32_t loH2 = desc_sw128_lo(smem_u32(sH2)), loX = desc_sw128_lo(smem_u32(sX)),
+                   loR1 = desc_sw128_lo(smem_u32(sR1)), loR2 = desc_sw128_lo(smem_u32(sR2)),
+                   loA2 = desc_sw128_lo(smem_u32(sA2));
+    constexpr uint32_t A_KB = MD_A_KB_BYTES >> 4, W_KB = MD_W_KB_BYTES >> 4, KSTEP = 32 >> 4;
+    auto stage1 = [&](uint32_t n) {
+      const uint32_t it = n / (uint32_t)nch, c = n - it * (uint32_t)nch;
+      if (c == 0) mbar_wait(&bars[MB_A_FULL], it & 1);
+      mbar_wait(&bars[MB_R1_FULL], n & 1);
+      mbar_wait(&bars[MB_ACC_EMPTY], (n & 1) ^ 1);
+      if (lane == 0) MD_TRACE(12, n);
+      tc_fence_after();
+      uint32_t acc = 0;
+      for (int kb = 0; kb < kb1; ++kb) {
+        const int ks = min(MD_BK, p.K1 - kb * MD_BK) / 16;
+        for (int k = 0; k < ks; ++k) {
           if (elect_one())
-            mma_bf16_lohi(tmem_base + 256, a + k * KSTEP, kDescSw128Hi, w + k * KSTEP, kDescSw128Hi, idescG,
-                          (cc | k) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < MD_NC / 16; ++k)
-          if (elect_one())
-            mma_bf16_lohi(tmem_base + 384, a + k * KSTEP, kDescSw128Hi, w + (wi2_bytes >> 4) + k * KSTEP, kDescSw128Hi,
-                          idescQ, (cc | k) != 0 ? 1u : 0u);
-        if (elect_one()) {
-          mma_commit(&bars[MB_R2_EMPTY + s]);
-          mma_commit(&bars[MB_A2_EMPTY + s]);
-          if (cc == (uint32_t)nch - 1) mma_commit(&bars[MB_GQ_FULL]);
+            mma_bf16_lohi(tmem_base, loH2 + kb * A_KB + k * KSTEP, kDescSw128Hi, loR1 + kb * W_KB + k * KSTEP,
+                          kDescSw128Hi, idesc1, acc);
+          acc = 1;
         }
-        __syncwarp();
-        if (lane == 0) MD_TRACE(23, m);
-      };
-      for (uint32_t n = 0; n < n_total + 2; ++n) {
-        // a tile's first stage 1 waits for its activation TMA: let the previous tile's stage 2 go first
-        const bool tile_start = n >= 2 && n < n_total && n % (uint32_t)nch == 0;
-        if (tile_start) stage2(n - 2);
-        if (n < n_total) stage1(n);
-        if (n >= 2 && !tile_start) stage2(n - 2);
       }
+      acc = 0;
+      for (int kb = 0; kb < kb2; ++kb) {
+        const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
+        for (int k = 0; k < ks; ++k) {
+          if (elect_one())
+            mma_bf16_lohi(tmem_base + 128, loX + kb * A_KB + k * KSTEP, kDescSw128Hi,
+                          loR1 + (kb1 + kb) * W_KB + k * KSTEP, kDescSw128Hi, idesc1, acc);
+          acc = 1;
+        }
+      }
+      if (elect_one()) {
+        mma_commit(&bars[MB_R1_EMPTY]);
+        mma_commit(&bars[MB_ACC_FULL]);
+        if (c == (uint32_t)nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
+      }
+      __syncwarp();
+      if (lane == 0) MD_TRACE(13, n);
+    };
+    auto stage2 = [&](uint32_t m) {
+      const uint32_t it = m / (uint32_t)nch, cc = m - it * (uint32_t)nch;
+      mbar_wait(&bars[MB_R2_FULL], m & 1);
+      mbar_wait(&bars[MB_A2_FULL], m & 1);
+      if (cc == 0) mbar_wait(&bars[MB_GQ_EMPTY], (it & 1) ^ 1);
+      if (lane == 0) MD_TRACE(22, m);
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < MD_BK / 16; ++k)
+          if (elect_one())
+            mma_bf16_lohi(tmem_base + 256, loA2 + kb * A_KB + k * KSTEP, kDescSw128Hi,
+                          loR2 + kb * (w2_kb_bytes >> 4) + k * KSTEP, kDescSw128Hi, idesc2,
+                          (cc | (uint32_t)kb | (uint32_t)k) != 0 ? 1u : 0u);
+      if (elect_one()) {
+        mma_commit(&bars[MB_R2_EMPTY]);
+        mma_commit(&bars[MB_A2_EMPTY]);
+        if (cc == (uint32_t)nch - 1) mma_commit(&bars[MB_GQ_FULL]);
+      }
+      __syncwarp();
+      if (lane == 0) MD_TRACE(23, m);
+    };
+    // S1(n+1) only needs the epilogue of chunk n to have LOADED its accumulators, S2(n) needs it finished
+    if (n_total > 0) stage1(0);
+    for (uint32_t n = 0; n < n_total; ++n) {
+      if (n + 1 < n_total) stage1(n + 1);
+      stage2(n);
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    const int colq = (warp - 4) >> 2;   // which 16 of the chunk's 64 columns
+    const int colq = (warp - 4) >> 2;   // which 32 of the chunk's 128 columns
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool tr = lane == 0 && warp == 4;
     uint32_t n = 0;
     int it = 0;
     for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
       int b, t0;
       if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
       for (int c = 0; c < nch; ++c, ++n) {
-        const uint32_t s = n & 1, ph = (n >> 1) & 1;
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(30 + (warp == 19) * 10, n);
-        mbar_wait(&bars[MB_ACC_FULL + s], ph);
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(31 + (warp == 19) * 10, n);
+        if (tr) MD_TRACE(30, n);
+        mbar_wait(&bars[MB_ACC_FULL], n & 1);
+        if (tr) MD_TRACE(31, n);
         tc_fence_after();
-        uint32_t u[16], r[16];
-        tmem_ld16_nowait(lane_base + s * MD_NC + colq * 16, u);
-        tmem_ld16_nowait(lane_base + 128 + s * MD_NC + colq * 16, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY + s]);   // accumulators may be overwritten
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(32 + (warp == 19) * 10, n);
-        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + colq * 16);
-        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + colq * 16);
-        uint32_t pk[8];
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x1 = b1[i], x2 = b2[i];
-          const float v0 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 0]) + x1.x) + __uint_as_float(r[4 * i + 0]) + x2.x);
-          const float v1 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 1]) + x1.y) + __uint_as_float(r[4 * i + 1]) + x2.y);
-          const float v2 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 2]) + x1.z) + __uint_as_float(r[4 * i + 2]) + x2.z);
-          const float v3 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 3]) + x1.w) + __uint_as_float(r[4 * i + 3]) + x2.w);
-          pk[2 * i] = pack_bf16(v0, v1);
-          pk[2 * i + 1] = pack_bf16(v2, v3);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t u[16], r[16];
+          const int col = colq * 32 + h * 16;
+          tmem_ld16_nowait(lane_base + col, u);
+          tmem_ld16_nowait(lane_base + 128 + col, r);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY]);   // U / R may be overwritten by chunk n+1
+            if (tr) MD_TRACE(32, n);
+          }
+          const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + col);
+          const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 x1 = b1[i], x2 = b2[i];
+            const float v0 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 0]) + x1.x) + __uint_as_float(r[4 * i + 0]) + x2.x);
+            const float v1 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 1]) + x1.y) + __uint_as_float(r[4 * i + 1]) + x2.y);
+            const float v2 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 2]) + x1.z) + __uint_as_float(r[4 * i + 2]) + x2.z);
+            const float v3 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 3]) + x1.w) + __uint_as_float(r[4 * i + 3]) + x2.w);
+            pk[h * 8 + 2 * i] = pack_bf16(v0, v1);
+            pk[h * 8 + 2 * i + 1] = pack_bf16(v2, v3);
+          }
         }
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(33 + (warp == 19) * 10, n);
-        mbar_wait(&bars[MB_A2_EMPTY + s], ph ^ 1);   // stage-2 MMAs of chunk n-2 finished reading this buffer
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(34 + (warp == 19) * 10, n);
-        uint8_t* dst = sA2 + s * MD_A2_BYTES + row * 128;
+        if (tr) MD_TRACE(33, n);
+        mbar_wait(&bars[MB_A2_EMPTY], (n & 1) ^ 1);   // stage-2 MMAs of chunk n-1 finished reading the a2 buffer
+        if (tr) MD_TRACE(34, n);
+        // a2[row][colq*32 .. +32): K block colq>>1, 16-byte chunks (colq&1)*4 .. +4, 128B swizzle
+        uint8_t* dst = sA2 + (colq >> 1) * MD_A_KB_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          *reinterpret_cast<uint4*>(dst + ((((colq * 2 + j) ^ (row & 7))) << 4)) =
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + (((((colq & 1) * 4 + j)) ^ (row & 7)) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[MB_A2_FULL + s]);
-        if (lane == 0 && (warp == 4 || warp == 19)) MD_TRACE(35 + (warp == 19) * 10, n);
+        if (lane == 0) mbar_arrive(&bars[MB_A2_FULL]);
+        if (tr) MD_TRACE(35, n);
       }
       // ---- tile drain: g1 = G + b_in2, q = Q + b_res2 (bf16, tile-major rows) ----
       mbar_wait(&bars[MB_GQ_FULL], it & 1);
@@ -335,7 +326,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       }
       for (int un = colq; un < p.N4 / 16; un += 4) {
         float v[16];
-        tmem_ld16(lane_base + 384 + un * 16, v);
+        tmem_ld16(lane_base + 256 + p.N3 + un * 16, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += sb_res2[un * 16 + i];
         uint4* dstq = reinterpret_cast<uint4*>(p.q + grow * p.ld_q + un * 16);
@@ -403,8 +394,8 @@ static int md_map_seq(CUtensorMap* m, const void* base, int B, int L, int C) {
 
 static size_t mid_smem_bytes(int K1, int K2, int F, int N3, int N4) {
   const int kb1 = (K1 + MD_BK - 1) / MD_BK, kb2 = (K2 + MD_BK - 1) / MD_BK;
-  size_t s = (size_t)(kb1 + kb2) * MD_A_KB_BYTES + 2 * (size_t)(kb1 + kb2) * MD_W_KB_BYTES +
-             2 * (size_t)md_align1024((N3 + N4) * 128) + 2 * MD_A2_BYTES;
+  size_t s = (size_t)(kb1 + kb2) * MD_A_KB_BYTES + (size_t)(kb1 + kb2) * MD_W_KB_BYTES +
+             2 * (size_t)md_align1024((N3 + N4) * 128) + MD_A2_BYTES;
   s += (size_t)(2 * F + N3 + N4) * 4 + 16 + MB_COUNT * 8 + 16;
   return s + 1024;  // alignment slack
 }
@@ -415,8 +406,8 @@ bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b)
   const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
   if (b->cin != F) return false;
   if (K1 % 16 || K2 % 16 || F % MD_NC || N3 % 16 || N4 % 16) return false;
-  if (N3 > 128 || N4 > 128 || N3 < 16 || N4 < 16) return false;
-  if (((K1 + 63) / 64 + (K2 + 63) / 64) * MD_NC > 256 || N3 + N4 > 256) return false;   // one TMA box per stage
+  if (N3 < 16 || N4 < 16 || N3 + N4 > 256) return false;             // one MMA stream, one TMEM accumulator
+  if (((K1 + 63) / 64 + (K2 + 63) / 64) % 2) return false;           // stage-1 image is streamed as 256-row boxes
   return mid_smem_bytes(K1, K2, F, N3, N4) <= 227 * 1024;
 }
 
@@ -429,16 +420,16 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   const int kbs = (K1 + 63) / 64 + (K2 + 63) / 64;
   if (int rc = md_map_2d(&mH2, h2, rows, K1, K1, MD_BM)) return rc;
   if (int rc = md_map_seq(&mX, x, B, L, K2)) return rc;
-  // packed stage images: [F/64 chunks][rows per chunk][64] bf16, one box per chunk
-  if (int rc = md_map_2d(&mW1, a->w_mid_first, (long long)(F / MD_NC) * kbs * MD_NC, MD_BK, MD_BK, kbs * MD_NC)) return rc;
-  if (int rc = md_map_2d(&mW2, b->w_mid_second, (long long)(F / MD_NC) * (N3 + N4), MD_BK, MD_BK, N3 + N4)) return rc;
+  // packed stage images: [F/128 chunks][K blocks][rows][64] bf16
+  if (int rc = md_map_2d(&mW1, a->w_mid_first, (long long)(F / MD_NC) * kbs * MD_NC, MD_BK, MD_BK, 2 * MD_NC)) return rc;
+  if (int rc = md_map_2d(&mW2, b->w_mid_second, (long long)(F / MD_NC) * 2 * (N3 + N4), MD_BK, MD_BK, N3 + N4)) return rc;
   TcMidKernelArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K1 = K1; k.K2 = K2; k.F = F; k.N3 = N3; k.N4 = N4;
   k.b_out = a->b_out; k.b_res = a->b_res; k.b_in2 = b->b_in; k.b_res2 = b->b_res;
   k.g1 = g1; k.ld_g1 = N3; k.q = q; k.ld_q = N4;
   static const char* trace_path = getenv("FLOWTIMES_MID_TRACE");
   static long long* trace_dev = nullptr;
-  if (trace_path && !trace_dev) { cudaMalloc(&trace_dev, (64 * 256) * sizeof(long long)); }
+  if (trace_path && !trace_dev) cudaMalloc(&trace_dev, (64 * 256) * sizeof(long long));
   if (trace_dev) { cudaMemsetAsync(trace_dev, 0, (64 * 256) * sizeof(long long), st); k.trace = trace_dev; }
   const size_t smem = mid_smem_bytes(K1, K2, F, N3, N4);
   static size_t attr[2] = {0, 0};

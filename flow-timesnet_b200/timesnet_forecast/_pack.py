@@ -133,21 +133,20 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         w_res_nk = block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0]          # [cout][cin]
         w_out_nk = w_out_kn.t()                                                        # [cout][NB]
 
-        def kblocks(w_nk: torch.Tensor) -> torch.Tensor:                               # [N][K] -> [N/64][kb][64][64]
+        def kblocks(w_nk: torch.Tensor) -> torch.Tensor:                               # [N][K] -> [N/128][kb][128][64]
             N_, K_ = w_nk.shape
             kb = (K_ + 63) // 64
             padded = torch.zeros(N_, kb * 64, dtype=f64)
             padded[:, :K_] = w_nk
-            return padded.reshape(N_ // 64, 64, kb, 64).permute(0, 2, 1, 3)
+            return padded.reshape(N_ // 128, 128, kb, 64).permute(0, 2, 1, 3)
 
-        if cout % 64 == 0:
-            first = torch.cat([kblocks(w_out_nk), kblocks(w_res_nk)], dim=1)           # [cout/64][kb1+kb2][64][64]
+        if cout % 128 == 0:
+            first = torch.cat([kblocks(w_out_nk), kblocks(w_res_nk)], dim=1)           # [cout/128][kb1+kb2][128][64]
             st.w_mid_first = dev16(first)
-        if cin % 64 == 0:
-            w_in_nk = w_in                                                             # [NB][cin]
-            both = torch.cat([w_in_nk, w_res_nk], dim=0)                               # [NB+cout][cin]
+        if cin % 128 == 0:
+            both = torch.cat([w_in, w_res_nk], dim=0)                                  # [NB+cout][cin]
             second = both.reshape(NB + cout, cin // 64, 64).permute(1, 0, 2)           # [cin/64][NB+cout][64]
-            st.w_mid_second = dev16(second)
+            st.w_mid_second = dev16(second)                                            # == [cin/128][2][NB+cout][64]
     return PackedInception(st, keep, macs)
 
 

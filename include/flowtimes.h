@@ -97,13 +97,15 @@ typedef struct FtnInceptionWeights {
   const void* w_out_bf16;  /* [cout][n_branch*mid] */
   const void* w_res_bf16;  /* [cout][cin] or NULL */
   const void* w_kk_bf16[FTN_MAX_BRANCH]; /* [kh*kw][kk_cout][kk_cin] */
-  /* Shared-memory stage images for the fused middle kernel (one TMA box per 64-column chunk of
-   * d_ff; a TMA issue costs ~400 cycles whatever its size, so chunks are streamed as single boxes).
-   * Only used when this block is the FIRST (w_mid_first) / SECOND (w_mid_second) of the pair:
-   *   w_mid_first : [cout/64][kb1+kb2][64][64], blocks kb < kb1: w_out[c*64+n][kb*64+k], then
-   *                 kb2 blocks of w_res[c*64+n][kb*64+k]; K zero-padded to multiples of 64
-   *   w_mid_second: [cin/64][n_branch*mid + cout][64]: rows n < n_branch*mid: w_in[n][c*64+k],
-   *                 then rows of w_res[n][c*64+k]
+  /* Shared-memory stage images for the fused middle kernel (tc_mid.cu), which walks d_ff in
+   * chunks of 128 columns and streams each weight stage as two TMA boxes (a TMA issue costs
+   * ~400 cycles whatever its size).  Only used when this block is the FIRST (w_mid_first) /
+   * SECOND (w_mid_second) of the pair:
+   *   w_mid_first : [cout/128][kb1+kb2][128][64] bf16; K blocks kb < kb1 hold
+   *                 w_out[c*128+n][kb*64+k], the next kb2 blocks w_res[c*128+n][kb*64+k];
+   *                 K zero-padded to multiples of 64
+   *   w_mid_second: [cin/128][2][n_branch*mid + cout][64] bf16; rows n < n_branch*mid hold
+   *                 w_in[n][c*128+kb*64+k], the remaining rows w_res[n][c*128+kb*64+k]
    * NULL = the fused middle kernel is not used with this block. */
   const void* w_mid_first;
   const void* w_mid_second;
