@@ -248,6 +248,75 @@ __device__ __forceinline__ float gelu_tanh3(float v) {
 }
 template <int ACT>
 __device__ __forceinline__ float act_fast(float v) { return ACT == 1 ? fmaxf(v, 0.f) : gelu_tanh3(v); }
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2, sm_100): two lanes of fp32 math per issued instruction.
+// The SIMT epilogues are bound by FP32 issue slots (measured: 3-register FFMA/FMUL/FADD retire one warp
+// instruction per 2 cycles per scheduler), so the GELU epilogues run on pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_tanh3 on a pair: 6 packed FMA-pipe instructions + 2 MUFU.TANH
+__device__ __forceinline__ f32x2 gelu_tanh3_x2(f32x2 v) {
+  const f32x2 c2 = pack2(-0.0003515167886192015f, -0.0003515167886192015f);
+  const f32x2 c1 = pack2(0.03700564602269518f, 0.03700564602269518f);
+  const f32x2 c0 = pack2(0.7975078842851249f, 0.7975078842851249f);
+  const f32x2 half = pack2(0.5f, 0.5f);
+  const f32x2 v2 = mul2(v, v);
+  f32x2 p = fma2(v2, c2, c1);
+  p = fma2(p, v2, c0);
+  float t0, t1;
+  unpack2(mul2(p, v), t0, t1);
+  const f32x2 th = pack2(tanh_approx(t0), tanh_approx(t1));
+  const f32x2 hv = mul2(v, half);
+  return fma2(th, hv, hv);
+}
+template <int ACT>
+__device__ __forceinline__ f32x2 act_fast_x2(f32x2 v) {
+  if (ACT == 1) {
+    float a, b;
+    unpack2(v, a, b);
+    return pack2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+  }
+  return gelu_tanh3_x2(v);
+}
+__device__ __forceinline__ f32x2 act_fast_x2(f32x2 v, int act) { return act == 1 ? act_fast_x2<1>(v) : act_fast_x2<0>(v); }
+__device__ __forceinline__ uint32_t pack_bf16_x2(f32x2 v) {
+  float a, b;
+  unpack2(v, a, b);
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float act_fast(float v, int act) { return act == 1 ? fmaxf(v, 0.f) : gelu_tanh3(v); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

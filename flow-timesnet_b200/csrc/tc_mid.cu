@@ -25,8 +25,8 @@
 // Warp roles (640 threads, one CTA per SM, 512 TMEM columns: U 0..127, R 128..255, G|Q 256..):
 //   warp 0 lane 0 : TMA producer  -- activation tiles (once per tile) and the stage-1 weight stage
 //   warp 3 lane 0 : TMA producer  -- stage-2 weight stage
-//   warp 1        : MMA issuer    -- warp-uniform loop, one elected lane issues
-//   warp 2        : TMEM allocator
+//   warp 1        : MMA issuer, stage 1  -- warp-uniform loop, one elected lane issues
+//   warp 2        : MMA issuer, stage 2  (also allocates / frees TMEM)
 //   warps 4..19   : epilogue      -- four warps per TMEM lane quadrant, 32 columns each
 // Every hand-off is an mbarrier; tcgen05.commit releases shared-memory stages and accumulators.
 #include <stdio.h>
@@ -181,8 +181,9 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) ==========
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 = stage 1, warp 2 = stage 2 (warp-uniform loops, one
+    // elected lane issues) ==========
     const uint32_t idesc1 = make_idesc_bf16(MD_BM, MD_NC);
     const uint32_t idesc2 = make_idesc_bf16(MD_BM, N34);
     const uint32_t loH2 = desc_sw128_lo(smem_u32(sH2)), loX = desc_sw128_lo(smem_u32(sX)),
@@ -247,11 +248,13 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) MD_TRACE(23, m);
     };
-    // S1(n+1) only needs the epilogue of chunk n to have LOADED its accumulators, S2(n) needs it finished
-    if (n_total > 0) stage1(0);
-    for (uint32_t n = 0; n < n_total; ++n) {
-      if (n + 1 < n_total) stage1(n + 1);
-      stage2(n);
+    // Two issuing warps: the sync-unit round trips of one stream (each mbarrier wait / commit costs
+    // 100+ cycles even when satisfied) overlap with the other stream's MMAs.  S1(n+1) only needs the
+    // epilogue of chunk n to have LOADED its accumulators, S2(n) needs it finished.
+    if (warp == 1) {
+      for (uint32_t n = 0; n < n_total; ++n) stage1(n);
+    } else {
+      for (uint32_t n = 0; n < n_total; ++n) stage2(n);
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
@@ -289,12 +292,13 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 x1 = b1[i], x2 = b2[i];
-            const float v0 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 0]) + x1.x) + __uint_as_float(r[4 * i + 0]) + x2.x);
-            const float v1 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 1]) + x1.y) + __uint_as_float(r[4 * i + 1]) + x2.y);
-            const float v2 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 2]) + x1.z) + __uint_as_float(r[4 * i + 2]) + x2.z);
-            const float v3 = act_fast<ACT>(act_fast<ACT>(__uint_as_float(u[4 * i + 3]) + x1.w) + __uint_as_float(r[4 * i + 3]) + x2.w);
-            pk[h * 8 + 2 * i] = pack_bf16(v0, v1);
-            pk[h * 8 + 2 * i + 1] = pack_bf16(v2, v3);
+            // a2 = act(act(U + b_out) + (R + b_res)) on fp32 pairs
+            const f32x2 lo = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 0], u[4 * i + 1]), pack2(x1.x, x1.y))),
+                                                   add2(pack2u(r[4 * i + 0], r[4 * i + 1]), pack2(x2.x, x2.y))));
+            const f32x2 hi = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 2], u[4 * i + 3]), pack2(x1.z, x1.w))),
+                                                   add2(pack2u(r[4 * i + 2], r[4 * i + 3]), pack2(x2.z, x2.w))));
+            pk[h * 8 + 2 * i] = pack_bf16_x2(lo);
+            pk[h * 8 + 2 * i + 1] = pack_bf16_x2(hi);
           }
         }
         if (tr) MD_TRACE(33, n);
