@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -224,16 +225,14 @@ def run_native(args):
              for i in range(n_rot)]
 
     def stack_step(i):
-        seq = feats[i % n_rot]
-        for blk in model.blocks:
-            seq = blk.forward_norm(seq, model.layer_norm)
-        return seq
+        return model.stack_forward(feats[i % n_rot])
 
     for i in range(max(3, args.warmup)):
         stack_step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    # ---- pass A: eager launches with per-family CUDA-event timing inside the library ----
     nv.timing_enable(True)
     launches0 = nv.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -243,17 +242,33 @@ def run_native(args):
         stack_step(i)
     ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    eager_ms_total = ev0.elapsed_time(ev1)
     launches = nv.launch_count() - launches0
     conv_ms, conv_calls = nv.timing_read(nv.FAM_CONV)
     spec_ms, spec_calls = nv.timing_read(nv.FAM_SPECTRUM)
     agg_ms, agg_calls = nv.timing_read(nv.FAM_AGGREGATE)
     nv.timing_enable(False)
+    ms_total = eager_ms_total
+    # ---- pass B: the same step replayed from a CUDA graph (no host round trip exists on the path) ----
+    graphed = None
+    if not args.no_graph:
+        from timesnet_forecast.cuda_graphs import GraphedCallable
+        graphed = GraphedCallable(model.stack_forward, [feats[0]])
+        for i in range(max(3, args.warmup)):
+            graphed(feats[i % n_rot])
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            graphed(feats[i % n_rot])            # device copy of the step's input into the graph's buffer + replay
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.finish()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, eager_ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
+    ms_step = t[0].item() / args.steps
+    eager_ms_step = t[1].item() / args.steps
     value = wl.B * world / (ms_step * 1e-3)
     group_periods = [list(b._last_plan.host().grp_period[: b._last_plan.host().n_groups]) for b in model.blocks]
 
@@ -264,12 +279,23 @@ def run_native(args):
         yd = torch.empty_like(y_host, device=dev)
         loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            xd.copy_(x_host, non_blocking=True)
-            yd.copy_(y_host, non_blocking=True)
-            rate, disp = model(xd)
-            loss = negative_binomial_nll(yd, rate, disp)
-            loss_host.copy_(loss, non_blocking=True)
+        def fwd_loss(xx, yy):
+            rate, disp = model(xx)
+            return negative_binomial_nll(yy, rate, disp)
+
+        if args.no_graph:
+            def e2e_step():
+                xd.copy_(x_host, non_blocking=True)
+                yd.copy_(y_host, non_blocking=True)
+                loss_host.copy_(fwd_loss(xd, yd), non_blocking=True)
+        else:
+            from timesnet_forecast.cuda_graphs import GraphedCallable
+            g2 = GraphedCallable(fwd_loss, [xd, yd])
+
+            def e2e_step():
+                g2.inputs[0].copy_(x_host, non_blocking=True)     # pinned host -> device, every step
+                g2.inputs[1].copy_(y_host, non_blocking=True)
+                loss_host.copy_(g2.replay(), non_blocking=True)   # device -> pinned host, every step
 
         for _ in range(max(3, args.warmup)):
             e2e_step()
@@ -297,14 +323,15 @@ def run_native(args):
         conv_avg_ms = conv_ms / max(1, conv_calls)
         achieved = flops_per_call / (conv_avg_ms * 1e-3) / 1e12 if conv_avg_ms > 0 else 0.0
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (Inception chain of one TimesBlock)",
+        roofline = {"bound": "tensor", "kernel": "Inception chain of one TimesBlock (tc_gemm, tc_conv2, tc_mid, tc_conv2, tc_gemm)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": None, "peak_source": peak_src + ", sustained bf16",
                     "flops_per_launch_group": flops_per_call, "avg_ms": conv_avg_ms, "calls": conv_calls,
-                    "note": "as-written conv FLOPs of one TimesBlock / CUDA-event time of its conv launches; "
-                            "math runs on fp32 CUDA cores in this round (no tensor pipe yet)",
-                    "share_of_step": {"conv": conv_ms / ms_total, "spectrum": spec_ms / ms_total,
-                                      "aggregate": agg_ms / ms_total}}
+                    "note": "as-written conv FLOPs of one TimesBlock (SURVEY 8d) / CUDA-event time of its Inception-chain "
+                            "launches; proj o branch-out folding makes executed FLOPs 2.97x lower (elec), see profiles/",
+                    "share_of_step": {"conv": conv_ms / eager_ms_total, "spectrum": spec_ms / eager_ms_total,
+                                      "aggregate": agg_ms / eager_ms_total,
+                                      "note": "shares of the eager pass (library CUDA events)"}}
         e_bytes = 2 if sdt == torch.bfloat16 else 4
         hbm = []
         for name, ms_f, calls, per_call in (
@@ -336,10 +363,12 @@ def run_native(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
             "config": {"workload": wl.name, **wl.as_dict(), "global_batch": wl.B * world, "parallelism": f"dp{world}",
-                       "scope": "TimesBlock stack (n_layers x (TimesBlock + shared LayerNorm)), features resident",
+                       "scope": "TimesBlock stack (n_layers x (TimesBlock + shared LayerNorm)), features resident"
+                                + ("" if args.no_graph else "; step = copy into the graph input + CUDA-graph replay"),
                        "l2": f"inputs rotate over {n_rot} buffers (> 2x L2); fp32 intermediates >> L2",
                        "selected_periods": group_periods},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launch_mode": "eager" if args.no_graph else "cuda_graph",
+            "eager_ms_per_step": eager_ms_step, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

@@ -277,11 +277,18 @@ int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* am
   FftPlan plan;
   if (!fft_factor(N, &plan)) return -1;
   dim3 grid((C + 31) / 32, B);
+  static size_t attr[2] = {0, 0};   // raise the dynamic shared memory limit once per size (not a stream operation)
   if (dtype == FTN_F32) {
-    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > attr[0]) {
+      FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[0] = smem;
+    }
     spectrum_fft_kernel<float><<<grid, kFftWarps * 32, smem, st>>>((const float*)x, L, C, amp, plan);
   } else {
-    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > attr[1]) {
+      FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[1] = smem;
+    }
     spectrum_fft_kernel<__nv_bfloat16><<<grid, kFftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, amp, plan);
   }
   FTN_LAUNCH_CHECK("spectrum_fft_kernel");

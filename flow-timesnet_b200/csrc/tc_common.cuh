@@ -238,8 +238,10 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // rounding (2^-9 relative) applied to every value this function produces.  6 FMA-pipe + 1 MUFU
 // instructions instead of ~20 for an erf-accurate evaluation; the GELU epilogues are what bounds the
 // fused 1x1 stages, so this is where the time goes.
+// The polynomial is only used for v^2 <= 64: beyond |v| = 8 the tanh argument is > 13 and the result is
+// exactly v or -0, while the unclamped quartic would turn negative near |v| = 11.5 and flip the sign.
 __device__ __forceinline__ float gelu_tanh3(float v) {
-  const float v2 = v * v;
+  const float v2 = fminf(v * v, 64.0f);
   float p = fmaf(v2, -0.0003515167886192015f, 0.03700564602269518f);
   p = fmaf(p, v2, 0.7975078842851249f);
   const float th = tanh_approx(p * v);
@@ -292,7 +294,9 @@ __device__ __forceinline__ f32x2 gelu_tanh3_x2(f32x2 v) {
   const f32x2 c1 = pack2(0.03700564602269518f, 0.03700564602269518f);
   const f32x2 c0 = pack2(0.7975078842851249f, 0.7975078842851249f);
   const f32x2 half = pack2(0.5f, 0.5f);
-  const f32x2 v2 = mul2(v, v);
+  float q0, q1;
+  unpack2(mul2(v, v), q0, q1);
+  const f32x2 v2 = pack2(fminf(q0, 64.0f), fminf(q1, 64.0f));   // see gelu_tanh3: keeps the quartic monotone
   f32x2 p = fma2(v2, c2, c1);
   p = fma2(p, v2, c0);
   float t0, t1;

@@ -1167,6 +1167,32 @@ class TimesNet(nn.Module):
                                 self.context_norm.eps)
         return ctx
 
+    def stack_forward(self, seq: torch.Tensor) -> torch.Tensor:
+        """TimesBlock stack on pre-embedded features ``[B, L, d_model]``: ``n_layers x (TimesBlock + residual +
+        shared LayerNorm)`` (timesnet.py:2050-2061).  Sync-free, so it can be captured in a CUDA graph."""
+        for block in self.blocks:
+            object.__setattr__(block, "period_selector", self.period_selector)
+            seq = block.forward_norm(seq, self.layer_norm)
+        return seq
+
+    def graphed(self, x: torch.Tensor, x_mark: Optional[torch.Tensor] = None,
+                series_static: Optional[torch.Tensor] = None, series_ids: Optional[torch.Tensor] = None):
+        """CUDA-graph replay of ``forward`` for inputs shaped like the given examples.  Returns a callable
+        taking the same tensors (positionally, ``None`` entries dropped).  Turns ``check_finite`` off:
+        the two host-syncing sanity checks of timesnet.py:2094-2097 cannot live inside a graph."""
+        from ..cuda_graphs import GraphedCallable
+        self.check_finite = False
+        names = ["x", "x_mark", "series_static", "series_ids"]
+        given = [x, x_mark, series_static, series_ids]
+        idx = [i for i, t in enumerate(given) if t is not None]
+
+        def run(*tensors):
+            kw = {names[i]: t for i, t in zip(idx, tensors)}
+            return self.forward(**kw)
+
+        run(*[given[i] for i in idx])                       # lazy build outside of any capture
+        return GraphedCallable(run, [given[i] for i in idx])
+
     def forward(self, x: torch.Tensor, x_mark: Optional[torch.Tensor] = None,
                 series_static: Optional[torch.Tensor] = None,
                 series_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -1201,9 +1227,7 @@ class TimesNet(nn.Module):
             seq = self.embedding(feat_in, mark, out_dtype=sdt)               # timesnet.py:1996
             if seq.size(1) != L or seq.size(-1) != self.d_model:
                 raise RuntimeError("Embedding output must have shape [B, input_len, d_model]")
-            for block in self.blocks:                                        # timesnet.py:2050-2061
-                object.__setattr__(block, "period_selector", self.period_selector)
-                seq = block.forward_norm(seq, self.layer_norm)
+            seq = self.stack_forward(seq)                                    # timesnet.py:2050-2061
             # ---- head (timesnet.py:2008-2014, 2063-2093) ----
             hist_steps = min(steps, L)
             hist = xv[:, -hist_steps:, :]
