@@ -278,6 +278,151 @@ __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, i
   for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
 }
 
+// ---- fused tail: batch sum (optional) + scores + top-k + plan + per-window amplitudes / weights ----
+// One CTA of 1024 threads.  Replaces batch_sum_kernel + select_tail_kernel + finish_kernel (three
+// launches, ~32 us at the elec shape, all latency) when no all-reduce has to happen in between; with
+// a sharded batch the caller runs batch_sum_kernel, all-reduces, and calls this with do_sum = 0.
+// Summation order, score rounding, tie rule and grouping are the ones of the separate kernels.
+__device__ __forceinline__ void argbest_warp(float& s, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float so = __shfl_xor_sync(0xffffffffu, s, o);
+    const int io = __shfl_xor_sync(0xffffffffu, i, o);
+    if (io != 0x7fffffff && (i == 0x7fffffff || better(so, io, s, i))) { s = so; i = io; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ amp_sum, int do_sum, int B,
+                    int global_batch, int L, int k, int pmax, int min_period, FtnPeriodPlan* __restrict__ plan,
+                    T* __restrict__ amps, float* __restrict__ weights) {
+  extern __shared__ float sf[];
+  const int F = L / 2 + 1;
+  float* s_sum = sf;            // [F + 1]
+  float* s_score = sf + F + 1;  // [F]
+  __shared__ float part[32][33];
+  __shared__ float w_best[32];
+  __shared__ int w_idx[32];
+  __shared__ int s_top[FTN_MAX_K];
+  __shared__ FtnPeriodPlan s_plan;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (do_sum) {
+    // same order as batch_sum_kernel: 32 row-lanes, each serial over b = r, r+32, ..., then a serial fold
+    const int fl = lane, r = warp;
+    for (int f0 = 0; f0 < F; f0 += 32) {
+      const int f = f0 + fl;
+      float acc = 0.f;
+      if (f < F)
+        for (int b = r; b < B; b += 32) acc += amp_median[(size_t)b * F + f];
+      part[r][fl] = acc;
+      __syncthreads();
+      if (r == 0 && f < F) {
+        float t = 0.f;
+        for (int i = 0; i < 32; ++i) t += part[i][fl];
+        s_sum[f] = t;
+        amp_sum[f] = t;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { s_sum[F] = (float)B; amp_sum[F] = (float)B; }
+  } else {
+    for (int f = tid; f <= F; f += blockDim.x) s_sum[f] = amp_sum[f];
+  }
+  __syncthreads();
+
+  // scores in the activation dtype, exactly as timesnet.py:119-130
+  const float gb = global_batch > 0 ? (float)global_batch : s_sum[F];
+  for (int f = tid; f < F; f += blockDim.x) {
+    const float m = round_to<T>(s_sum[f] / gb);
+    const float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
+    float sc = round_to<T>(m - pen);
+    if (f == 0) sc = -CUDART_INF_F;
+    s_score[f] = sc;
+  }
+  __syncthreads();
+  const int kk = min(k, F - 1);
+  for (int r = 0; r < kk; ++r) {
+    float bs = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int f = tid; f < F; f += blockDim.x) {
+      bool taken = false;
+      for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
+      if (taken) continue;
+      const float sc = s_score[f];
+      if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
+    }
+    argbest_warp(bs, bi);
+    if (lane == 0) { w_best[warp] = bs; w_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bs = w_best[lane];
+      bi = w_idx[lane];
+      argbest_warp(bs, bi);
+      if (lane == 0) s_top[r] = bi;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    FtnPeriodPlan& pl = s_plan;
+    pl.n_raw = kk;
+    pl.reserved[0] = pl.reserved[1] = pl.reserved[2] = 0;
+    const int upper = min(pmax, max(1, L - 1));
+    const int lower = min_period;
+    int nv = 0;
+    float mean_amp[FTN_MAX_K];
+    for (int i = 0; i < FTN_MAX_K; ++i) { pl.raw_freq[i] = 0; pl.freq[i] = 0; pl.period[i] = 0; }
+    for (int r = 0; r < kk; ++r) {
+      const int64_t safe = max(s_top[r], 1);
+      pl.raw_freq[r] = safe;
+      if (upper < lower) continue;
+      int64_t p = (L + safe - 1) / safe;
+      p = p < lower ? lower : (p > upper ? upper : p);
+      const int64_t cyc = (L + p - 1) / p;
+      if (cyc < 2) continue;
+      pl.freq[nv] = safe;
+      pl.period[nv] = p;
+      mean_amp[nv] = s_sum[safe];
+      ++nv;
+    }
+    pl.n_valid = nv;
+    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp);
+  }
+  __syncthreads();
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
+    for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel)
+  const int nv = s_plan.n_valid;
+  for (int b = tid; b < B; b += blockDim.x) {
+    float a[FTN_MAX_K];
+    for (int j = 0; j < k; ++j) {
+      float v = 0.f;
+      if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + s_plan.freq[j]]);
+      a[j] = v;
+      amps[(size_t)b * k + j] = from_f32<T>(v);
+    }
+    float mx = -CUDART_INF_F;
+    for (int j = 0; j < nv; ++j)
+      if (s_plan.mapping[j] >= 0) mx = fmaxf(mx, a[j]);
+    float den = 0.f;
+    for (int j = 0; j < nv; ++j)
+      if (s_plan.mapping[j] >= 0) den += expf(a[j] - mx);
+    float w[FTN_MAX_K];
+    for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
+    for (int j = 0; j < nv; ++j) {
+      const int g = s_plan.mapping[j];
+      if (g < 0) continue;
+      const float sm = round_to<T>(expf(a[j] - mx) / den);      // softmax fp32 -> dtype (timesnet.py:1000)
+      w[g] = round_to<T>(w[g] + sm);                            // scatter_add_ in dtype (:1009)
+    }
+    for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
+  }
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // spectrum_fft.cu
@@ -294,8 +439,55 @@ extern "C" size_t ftn_spectrum_workspace_bytes(int B, int L, int C) {
   return align256((size_t)B * F * C * sizeof(float)) + align256(F * sizeof(float)) + 256;
 }
 
+static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum);
+
 extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
                             float* amp_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  TimedScope timed(FTN_FAM_SPECTRUM, st);
+  return spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, true);
+}
+
+static int launch_select_fused(const float* amp_median, float* amp_sum, int do_sum, int dtype, int B, int global_batch,
+                               int L, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
+                               cudaStream_t st) {
+  const int F = L / 2 + 1;
+  const size_t smem = (size_t)(2 * F + 1) * sizeof(float);
+  FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
+  static size_t attr[2] = {0, 0};
+  if (dtype == FTN_F32) {
+    if (smem > 40 * 1024 && smem > attr[0]) {
+      FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[0] = smem;
+    }
+    select_fused_kernel<float><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax, min_period,
+                                                      plan, (float*)amps, weights);
+  } else {
+    if (smem > 40 * 1024 && smem > attr[1]) {
+      FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[1] = smem;
+    }
+    select_fused_kernel<__nv_bfloat16><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax,
+                                                              min_period, plan, (__nv_bfloat16*)amps, weights);
+  }
+  FTN_LAUNCH_CHECK("select_fused_kernel");
+  return 0;
+}
+
+extern "C" int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
+                                 float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(plan && amps && weights, "ftn_period_search: null pointer");
+  FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_period_search: k=%d outside [1,%d]", k, FTN_MAX_K);
+  cudaStream_t st = as_stream(stream);
+  TimedScope timed(FTN_FAM_SPECTRUM, st);
+  if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false)) return rc;
+  return launch_select_fused(amp_median, amp_sum, 1, dtype, B, B, L, k, pmax, min_period, plan, amps, weights, st);
+}
+
+static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum) {
   FTN_REQUIRE(x && amp_median && amp_sum && workspace, "ftn_spectrum: null pointer");
   FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_spectrum: need B>0, L>1, C>0 (got %d,%d,%d)", B, L, C);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_spectrum: unsupported dtype %d", dtype);
@@ -303,8 +495,6 @@ extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float
   FTN_REQUIRE(workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_spectrum: workspace too small");
   const int F = L / 2 + 1;
   float* amp = reinterpret_cast<float*>(workspace);
-  cudaStream_t st = as_stream(stream);
-  TimedScope timed(FTN_FAM_SPECTRUM, st);
   int rc = spectrum_fft_launch(x, dtype, B, L, C, amp, st);   // mixed-radix FFT (even L); -1 = not applicable
   if (rc > 0) return rc;
   if (rc < 0) {
@@ -329,8 +519,10 @@ extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float
     channel_median_kernel<<<(rows + kMedianWarps - 1) / kMedianWarps, kMedianWarps * 32, msmem, st>>>(amp, rows, C, amp_median);
     FTN_LAUNCH_CHECK("channel_median_kernel");
   }
-  batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum);
-  FTN_LAUNCH_CHECK("batch_sum_kernel");
+  if (with_batch_sum) {
+    batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum);
+    FTN_LAUNCH_CHECK("batch_sum_kernel");
+  }
   return 0;
 }
 
@@ -342,19 +534,9 @@ extern "C" int ftn_select_periods(const float* amp_median, const float* amp_sum,
   FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_select_periods: k=%d outside [1,%d]", k, FTN_MAX_K);
   FTN_REQUIRE(B > 0 && (global_batch <= 0 || global_batch >= B) && L > 1, "ftn_select_periods: bad sizes B=%d global=%d L=%d", B, global_batch, L);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_select_periods: unsupported dtype %d", dtype);
-  cudaStream_t st = as_stream(stream);
-  const int F = L / 2 + 1;
-  if (dtype == FTN_F32) {
-    select_tail_kernel<float><<<1, 256, 0, st>>>(amp_sum, global_batch, L, k, pmax, min_period, plan, scores_ws);
-    FTN_LAUNCH_CHECK("select_tail_kernel");
-    finish_kernel<float><<<(B + 127) / 128, 128, 0, st>>>(amp_median, B, F, k, plan, (float*)amps, weights);
-  } else {
-    select_tail_kernel<__nv_bfloat16><<<1, 256, 0, st>>>(amp_sum, global_batch, L, k, pmax, min_period, plan, scores_ws);
-    FTN_LAUNCH_CHECK("select_tail_kernel");
-    finish_kernel<__nv_bfloat16><<<(B + 127) / 128, 128, 0, st>>>(amp_median, B, F, k, plan, (__nv_bfloat16*)amps, weights);
-  }
-  FTN_LAUNCH_CHECK("finish_kernel");
-  return 0;
+  (void)scores_ws;   // kept in the signature for ABI stability; the fused tail keeps scores in shared memory
+  return launch_select_fused(amp_median, const_cast<float*>(amp_sum), 0, dtype, B, global_batch, L, k, pmax, min_period,
+                             plan, amps, weights, as_stream(stream));
 }
 
 extern "C" int ftn_plan_build_host(const int64_t* periods_host, int k, int L, int min_period,

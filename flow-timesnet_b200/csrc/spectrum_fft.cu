@@ -241,10 +241,10 @@ channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float*
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t bmask = 1u << bit;
-    int cnt0 = 0;
+    int cnt0 = 0;   // ballots + popc: warp-uniform counting without a REDUX round trip per bit
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) cnt0 += ((key[i] & known) == prefix && !(key[i] & bmask)) ? 1 : 0;
-    cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+    for (int i = 0; i < KPL; ++i)
+      cnt0 += __popc(__ballot_sync(0xffffffffu, (key[i] & known) == prefix && !(key[i] & bmask)));
     if (k >= cnt0) { prefix |= bmask; k -= cnt0; }
     known |= bmask;
   }

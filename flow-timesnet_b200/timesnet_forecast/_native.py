@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "ftn_spectrum_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ftn_spectrum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ftn_plan_build_host": (_I, [C.POINTER(_I64), _I, _I, _I, _I, C.POINTER(FtnPeriodPlan)]),
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
@@ -186,6 +187,24 @@ def spectrum(x: torch.Tensor):
     _check(lib.ftn_spectrum(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, med.data_ptr(), ssum.data_ptr(),
                             ws.data_ptr(), nbytes, _stream()), "ftn_spectrum")
     return med, ssum
+
+
+def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int):
+    """Single-rank fused search: x[B,L,C] -> (plan, amps[B,k], weights[B,16], amp_median[B,F], amp_sum[F+1])."""
+    lib = load()
+    B, L, Cc = x.shape
+    Fq = L // 2 + 1
+    med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
+    ssum = torch.empty(Fq + 1, dtype=torch.float32, device=x.device)
+    plan = new_plan(x.device)
+    amps = torch.empty(B, k, dtype=x.dtype, device=x.device)
+    weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=x.device)
+    nbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _check(lib.ftn_period_search(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
+                                 ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), ws.data_ptr(),
+                                 nbytes, _stream()), "ftn_period_search")
+    return plan, amps, weights, med, ssum
 
 
 def new_plan(device) -> torch.Tensor:

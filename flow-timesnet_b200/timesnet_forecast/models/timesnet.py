@@ -126,8 +126,12 @@ class FFTPeriodSelector(nn.Module):
         if k > nv.FTN_MAX_K:
             raise ValueError(f"k_periods={self.k} exceeds the supported maximum {nv.FTN_MAX_K}")
         x = nv.require_cuda(x, "x")
-        med, ssum = nv.spectrum(x)                                     # ssum = [sum_b median spectrum | B]
         group, world = self._world()
+        if world == 1:                                                 # nothing to reduce: fused 3-launch search
+            plan_dev, amps, weights, _, _ = nv.period_search(x, k, self.pmax, self.min_period_threshold)
+            self._last_plan = PeriodPlan(plan_dev, amps, weights, k)
+            return self._last_plan
+        med, ssum = nv.spectrum(x)                                     # ssum = [sum_b median spectrum | B]
         if world > 1:
             import torch.distributed as dist
             # the only collective of the path: F sums + the window count in one message, so ragged

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 4
+#define FTN_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -148,6 +148,13 @@ FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, in
                        int global_batch, int L, int k, int pmax, int min_period,
                        FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/,
                        float* scores_ws /*[L/2+1] scratch*/, void* stream);
+
+/* Single-rank fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the
+ * selection kernel (3 launches instead of 5; nothing to all-reduce).  Same outputs as the pair:
+ * amp_median [B][F], amp_sum [F+1], plan, amps [B][k], weights [B][FTN_MAX_K]. */
+FTN_API int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
+                      float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* HOST helper (no CUDA): group an externally supplied candidate list (a custom
  * period_selector module) with the default exact-duplicate rules and fill a
