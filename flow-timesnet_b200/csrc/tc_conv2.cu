@@ -43,6 +43,7 @@ struct TcConv2Args {
   int mid;       // channels per branch (K and N of the MMAs): 16 or 32
   int n_branch;
   int cap_rows;  // rows one image buffer can hold
+  int v3_cap[FTN_MAX_BRANCH];   // > 0: skip the groups tc_conv3 handles (c3_group_fits with this capacity)
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
   int cta_begin[FTN_MAX_BRANCH + 1];       // CTA ranges per branch
   const __nv_bfloat16* w[FTN_MAX_BRANCH];  // [tap][n][k] bf16
@@ -60,8 +61,8 @@ struct C2Unit {
 };
 
 // unit index (within one branch's enumeration) -> image, band and buffer geometry
-__device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L, int kh, int hw, int cap, int unit,
-                                          C2Unit& u) {
+__device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L, int kh, int hw, int cap, int v3cap,
+                                          int unit, C2Unit& u) {
   const int G = pl->n_groups;
   const int hh = kh / 2;
   int row_tiles_before = 0;
@@ -87,7 +88,7 @@ __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L,
       const long long cost_a = (long long)bands_a * (ta * C2_BM + 2 * margin);
       if (cost_a <= cost_b) { mode_b = 0; T = ta; bands = bands_a; }
     }
-    const int n = bands * B;
+    const int n = (v3cap > 0 && c3_group_fits(per, kh, 2 * hw + 1, v3cap)) ? 0 : bands * B;   // tc_conv3 owns this group
     const int rt = (Lp + 127) / 128;
     if (unit < n) {
       u.g = g;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
       const uint32_t wbase = smem_u32(s_w);
       C2Unit u;
       int i = 0;
-      for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, unit, u); unit += ctas_of_branch, ++i) {
+      for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
         const int buf = i & 1;
         const uint32_t par = (uint32_t)(i >> 1) & 1u;
         mbar_wait(&bars[C2_ACC_EMPTY + buf], par ^ 1u);   // epilogue drained the unit that used these columns
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
     const int r_step = C2_LOADERS / nchunk;
     C2Unit u;
     int i = 0;
-    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       const uint32_t par = (uint32_t)(i >> 1) & 1u;
       mbar_wait_relaxed(&bars[C2_IMG_EMPTY + buf], par ^ 1u);
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
     uint32_t phase_bits = 0;                 // one parity bit per (buffer, tile) barrier
     C2Unit u;
     int i = 0;
-    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       const float inv = 1.0f / (float)u.PW;
       for (int m = 0; m < u.tiles; ++m) {
@@ -332,9 +333,15 @@ bool tc_conv2_eligible(const FtnInceptionWeights* w) {
 
 int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
+  return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, nullptr, st);
+}
+
+int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st) {
   FTN_REQUIRE(tc_conv2_eligible(w), "tc_conv2: unsupported branch shape (mid=%d)", w->mid);
   (void)max_groups;
   TcConv2Args a{};
+  for (int j = 0; j < w->n_branch; ++j) a.v3_cap[j] = v3_caps ? v3_caps[j] : 0;
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.mid = w->mid; a.n_branch = w->n_branch;
   a.cap_rows = conv2_cap_rows(w);
   int cost_total = 0;

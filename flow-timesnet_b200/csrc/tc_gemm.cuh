@@ -51,7 +51,22 @@ int tc_conv_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
 bool tc_conv2_eligible(const FtnInceptionWeights* w);
 int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
-// picks tc_conv2 / tc_conv / SIMT for one k x k stage
+// "positions on N" variant (tc_conv3.cu): full-rate N = 256 MMAs, 4 taps x 32 channels on M; periods too long
+// for its shared-memory layouts are left to tc_conv2 (same launch sequence, disjoint groups)
+bool tc_conv3_eligible(const FtnInceptionWeights* w);
+void tc_conv3_caps(const FtnInceptionWeights* w, int* caps);
+int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st);
+// does tc_conv3 take a group of period `per` for a kh x kw branch whose image buffer holds `cap` rows?
+__host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) {
+  const int hw = kw / 2, hh = kh / 2, PW = per + 2 * hw;
+  const int tail = 256 + ((kw + 3) / 4 - 1) * 4;
+  return cap >= tail + 2 * hh * PW || cap / kh >= tail;
+}
+
+// picks tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 

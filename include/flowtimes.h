@@ -182,7 +182,8 @@ FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const
 FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
                                 void* out, void* stream);
 /* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
- * use_tc = 2 image-resident tcgen05 kernel, 1 tile-patch tcgen05 kernel, 0 SIMT kernel. */
+ * use_tc = 3 positions-on-N tcgen05 kernel (+ tc_conv2 for long periods), 2 image-resident tcgen05 kernel,
+ * 1 tile-patch tcgen05 kernel, 0 SIMT kernel. */
 FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                  int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
