@@ -134,6 +134,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_buf1 + ((BUF_BYTES + 127) & ~127u));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C2_BARS);
 
+  {
+    // nothing to do for this CTA (e.g. tc_conv3 owns every group): leave before touching TMEM / weights
+    C2Unit probe;
+    if (!c2_decode(p.plan, p.B, p.L, kh, hw, cap, p.v3_cap[j], cta_in_branch, probe)) return;
+  }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[C2_IMG_FULL + i], C2_LOADERS / 32);

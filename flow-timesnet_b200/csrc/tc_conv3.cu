@@ -16,13 +16,17 @@
 // per 253 positions instead of 2 * 98 slow ones per 2 * 128.
 //
 // The epilogue is where the four shifted partial rows meet: TMEM lane quadrant q holds tap tl = q, so
-// each of the four warps of a half-block loads its rows at column offset +tl (warp-uniform), stores
-// them to a small fp32 staging tile, and after a 128-thread named barrier every thread sums four
-// values for 4 channels of one position, adds the bias and writes 8 bytes of the bf16 output row.
+// each of the four warps of a 64-column quarter loads its rows at column offset +tl (warp-uniform),
+// stores 8 positions to a double-buffered fp32 staging tile, and after ONE 128-thread named barrier
+// every thread sums four values for 2 channels of one position, adds the bias and writes 4 bytes of
+// the bf16 output row.
 //
 // Staging of the zero-padded image (cp.async with zero fill, interleaved K-major layout, row shifts =
 // +16 B on the descriptor), the band / segment fallback for long periods, persistent CTAs partitioned
 // over branches and the double-buffered load / MMA / drain pipeline are those of tc_conv2.cu.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -30,7 +34,8 @@ namespace ftn {
 
 using namespace tc;
 
-constexpr int C3_THREADS = 416;   // warp 0: MMA issuer + TMEM owner, warps 1-3: loaders, warps 4-11: epilogue, warp 12: loader
+constexpr int C3_EPI_WARPS = 16;
+constexpr int C3_THREADS = (5 + C3_EPI_WARPS) * 32;   // warp 0: MMA issuer + TMEM owner, warps 1-3 + 20: loaders, warps 4-19: epilogue
 constexpr int C3_LOADERS = 128;
 constexpr int C3_MID = 32;        // channels per branch this kernel is written for
 constexpr int C3_TL = 4;          // taps per M group (128 / mid)
@@ -40,7 +45,10 @@ constexpr int C3_MAX_BLOCKS = 8;  // blocks per unit
 constexpr int C3_NCHUNK = C3_MID / 8;
 constexpr uint32_t C3_W_LBO = 128 * 16;                 // weight tile: chunk stride
 constexpr uint32_t C3_W_GROUP = C3_NCHUNK * C3_W_LBO;   // 8 KB per (dr, dq) group
-constexpr int C3_STAGE_BYTES = 2 * 4 * 16 * C3_MID * 4;  // [half][tl][16 pos][32 n] fp32 = 16 KB
+constexpr int C3_EPI_COST = 4000;   // measured cycles the drain of one block takes (bounds the small kernels)
+constexpr int C3_CHUNK = 8;       // positions per epilogue chunk
+constexpr int C3_STAGE_FLOATS = 4 * C3_CHUNK * C3_MID;          // one staging tile: [tl][8 pos][32 n] fp32 = 4 KB
+constexpr int C3_STAGE_BYTES = 4 * 2 * C3_STAGE_FLOATS * 4;      // [column quarter][double buffer] = 32 KB
 
 struct TcConv3Args {
   const FtnPeriodPlan* plan;
@@ -54,6 +62,7 @@ struct TcConv3Args {
   int cta_begin[FTN_MAX_BRANCH + 1];
   const __nv_bfloat16* w[FTN_MAX_BRANCH];  // [tap][n][k] bf16
   const float* bias[FTN_MAX_BRANCH];       // [mid]
+  long long* trace;   // debug (FLOWTIMES_CONV_TRACE): the last CTA records clock64() per (event, index)
 };
 
 struct C3Unit {
@@ -112,6 +121,11 @@ __device__ __forceinline__ bool c3_decode(const FtnPeriodPlan* pl, int B, int L,
   return false;
 }
 
+#define C3_TRACE(ev, n)                                                                                  \
+  do {                                                                                                  \
+    if (p.trace && blockIdx.x == gridDim.x - 1 && (n) < 256) p.trace[(ev) * 256 + (n)] = clock64();      \
+  } while (0)
+
 enum { C3_IMG_FULL = 0, C3_IMG_EMPTY = 2, C3_ACC_FULL = 4, C3_ACC_EMPTY = 6, C3_BARS = 8 };
 
 __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Args p) {
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
       mbar_init(&bars[C3_IMG_FULL + i], C3_LOADERS / 32);
       mbar_init(&bars[C3_IMG_EMPTY + i], 1);
       mbar_init(&bars[C3_ACC_FULL + i], 1);
-      mbar_init(&bars[C3_ACC_EMPTY + i], 8);
+      mbar_init(&bars[C3_ACC_EMPTY + i], C3_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -182,10 +196,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
     for (int unit = cta_in_branch; c3_decode(pl, p.B, p.L, kh, hw, dq_n, cap, unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       mbar_wait(&bars[C3_IMG_FULL + buf], (uint32_t)(i >> 1) & 1u);
+      if (lane == 0) C3_TRACE(1, i);
       const uint32_t b_lo0 = (uint32_t)make_desc_interleaved(smem_u32(buf ? s_buf1 : s_buf0), LBO_B);
       for (int t = 0; t < u.blocks; ++t, ++blk_count) {
         const uint32_t acc_i = blk_count & 1;
         mbar_wait(&bars[C3_ACC_EMPTY + acc_i], ((blk_count >> 1) & 1u) ^ 1u);
+        if (lane == 0) C3_TRACE(2, blk_count);
         tc_fence_after();
         const uint32_t acc = tmem_base + acc_i * C3_NB;
         uint32_t accum = 0;
@@ -206,13 +222,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
         }
         if (elect_one()) mma_commit(&bars[C3_ACC_FULL + acc_i]);
         __syncwarp();
+        if (lane == 0) C3_TRACE(3, blk_count);
       }
       if (elect_one()) mma_commit(&bars[C3_IMG_EMPTY + buf]);   // loaders may overwrite the image buffer
       __syncwarp();
     }
-  } else if (warp <= 3 || warp == 12) {
+  } else if (warp <= 3 || warp == 4 + C3_EPI_WARPS) {
     // ===================== loaders =====================
-    const int lt = warp == 12 ? 96 + lane : tid - 32;   // 0..127
+    const int lt = warp > 3 ? 96 + lane : tid - 32;   // 0..127
     const int c = lt % C3_NCHUNK;
     const int r_first = lt / C3_NCHUNK;
     const int r_step = C3_LOADERS / C3_NCHUNK;
@@ -220,7 +237,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
     int i = 0;
     for (int unit = cta_in_branch; c3_decode(pl, p.B, p.L, kh, hw, dq_n, cap, unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
+      if (lt == 0) C3_TRACE(4, i);
       mbar_wait_relaxed(&bars[C3_IMG_EMPTY + buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      if (lt == 0) C3_TRACE(5, i);
       const uint32_t dst0 = smem_u32(buf ? s_buf1 : s_buf0) + c * LBO_B;
       const __nv_bfloat16* img = p.in + u.img_row0 * p.ld + j * C3_MID + c * 8;
       const int nseg = u.mode_b ? kh : 1;
@@ -247,67 +266,80 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[C3_IMG_FULL + buf]);
+      if (lt == 0) C3_TRACE(6, i);
     }
   } else {
-    // ===================== epilogue: warps 4..11 =====================
+    // ===================== epilogue: warps 4..19 =====================
     const int e = warp - 4;
     const int tl = e & 3;                // == TMEM lane quadrant of this warp == tap within the group
-    const int half = e >> 2;             // which 128 columns of the block
-    const int t128 = tl * 32 + lane;     // thread index inside the half's 128-thread group
-    float* stage = reinterpret_cast<float*>(s_stage) + half * (4 * 16 * C3_MID);
-    const int r_pos = t128 >> 3, r_n4 = (t128 & 7) * 4;     // reduce step: one position x 4 channels per thread
-    const float4 bias4 = *reinterpret_cast<const float4*>(p.bias[j] + r_n4);
+    const int qr = e >> 2;               // which 64 columns of the block
+    const int t128 = tl * 32 + lane;     // thread index inside the quarter's 128-thread group
+    float* stage0 = reinterpret_cast<float*>(s_stage) + qr * (2 * C3_STAGE_FLOATS);
+    const int r_pos = t128 >> 4, r_n2 = (t128 & 15) * 2;    // reduce step: one position x 2 channels per thread
+    const float2 bias2 = *reinterpret_cast<const float2*>(p.bias[j] + r_n2);
     C3Unit u;
     int i = 0;
-    uint32_t blk_count = 0;
+    uint32_t blk_count = 0, chunk_count = 0;
     for (int unit = cta_in_branch; c3_decode(pl, p.B, p.L, kh, hw, dq_n, cap, unit, u); unit += ctas_of_branch, ++i) {
       const float inv = 1.0f / (float)u.PW;
+      const int step_r = C3_CHUNK / u.PW, step_w = C3_CHUNK - step_r * u.PW;
       for (int t = 0; t < u.blocks; ++t, ++blk_count) {
         const uint32_t acc_i = blk_count & 1;
+        if (e == 0 && lane == 0) C3_TRACE(7, blk_count);
         mbar_wait_relaxed(&bars[C3_ACC_FULL + acc_i], (blk_count >> 1) & 1u);
+        if (e == 0 && lane == 0) C3_TRACE(8, blk_count);
         tc_fence_after();
         const uint32_t lane_base = tmem_base + acc_i * C3_NB + ((uint32_t)(tl * 32) << 16);
         const int P0 = u.p0 + t * C3_UB;
+        // padded-grid coordinates of this thread's position in the first chunk; advanced incrementally
+        int rr, wq;
+        {
+          const int q = P0 + qr * 64 + r_pos;
+          rr = __float2int_rd(__int2float_rn(q) * inv);
+          if (rr * u.PW > q) --rr;
+          if ((rr + 1) * u.PW <= q) ++rr;
+          wq = q - rr * u.PW;
+        }
+        // software pipeline: the TMEM load of chunk jc+1 is in flight while chunk jc goes through the
+        // staging tile, the barrier and the reduction
+        uint32_t vn[C3_CHUNK];
+        tmem_ld8_nowait(lane_base + (uint32_t)(min(qr * 64, C3_NB - C3_TL - (C3_CHUNK - 1)) + tl), vn);
 #pragma unroll 1
-        for (int jc = 0; jc < 8; ++jc) {
-          // 16 finished positions starting at block column c0 (the last chunk overlaps its predecessor so that
-          // c0 + tl + 15 stays inside the 256-column accumulator)
-          const int c0 = min(half * 128 + jc * 16, C3_NB - C3_TL - 15);
-          float v[16];
-          tmem_ld16(lane_base + (uint32_t)(c0 + tl), v);
-          float* st = stage + (tl * 16) * C3_MID + lane;
+        for (int jc = 0; jc < 64 / C3_CHUNK; ++jc, ++chunk_count) {
+          // 8 finished positions starting at block column c0 (the very last chunk overlaps its predecessor so
+          // that c0 + tl + 7 stays inside the 256-column accumulator)
+          const int c0 = min(qr * 64 + jc * C3_CHUNK, C3_NB - C3_TL - (C3_CHUNK - 1));
+          float* stage = stage0 + (chunk_count & 1) * C3_STAGE_FLOATS;   // double buffered: one barrier per chunk
+          tmem_ld_wait();
+          float* st = stage + (tl * C3_CHUNK) * C3_MID + lane;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) st[k * C3_MID] = v[k];
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-          {
-            const float* sp = stage + r_pos * C3_MID + r_n4;
-            float4 a0 = *reinterpret_cast<const float4*>(sp);
-            const float4 a1 = *reinterpret_cast<const float4*>(sp + 16 * C3_MID);
-            const float4 a2 = *reinterpret_cast<const float4*>(sp + 32 * C3_MID);
-            const float4 a3 = *reinterpret_cast<const float4*>(sp + 48 * C3_MID);
-            a0.x = ((a0.x + a1.x) + (a2.x + a3.x)) + bias4.x;
-            a0.y = ((a0.y + a1.y) + (a2.y + a3.y)) + bias4.y;
-            a0.z = ((a0.z + a1.z) + (a2.z + a3.z)) + bias4.z;
-            a0.w = ((a0.w + a1.w) + (a2.w + a3.w)) + bias4.w;
-            const int q = P0 + c0 + r_pos;
-            if (q < u.QT) {
-              int rr = __float2int_rd(__int2float_rn(q) * inv);
-              if (rr * u.PW > q) --rr;
-              if ((rr + 1) * u.PW <= q) ++rr;
-              const int w = q - rr * u.PW - hw;
-              if (w >= 0 && w < u.per) {
-                uint2 o;
-                o.x = pack_bf16(a0.x, a0.y);
-                o.y = pack_bf16(a0.z, a0.w);
-                *reinterpret_cast<uint2*>(p.out + (u.img_row0 + (size_t)(rr * u.per + w)) * p.ld + j * C3_MID + r_n4) = o;
-              }
-            }
+          for (int k = 0; k < C3_CHUNK; ++k) st[k * C3_MID] = __uint_as_float(vn[k]);
+          if (jc + 1 < 64 / C3_CHUNK)
+            tmem_ld8_nowait(lane_base + (uint32_t)(min(qr * 64 + (jc + 1) * C3_CHUNK, C3_NB - C3_TL - (C3_CHUNK - 1)) + tl), vn);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + qr) : "memory");
+          const float* sp = stage + r_pos * C3_MID + r_n2;
+          const float2 a0 = *reinterpret_cast<const float2*>(sp);
+          const float2 a1 = *reinterpret_cast<const float2*>(sp + C3_CHUNK * C3_MID);
+          const float2 a2 = *reinterpret_cast<const float2*>(sp + 2 * C3_CHUNK * C3_MID);
+          const float2 a3 = *reinterpret_cast<const float2*>(sp + 3 * C3_CHUNK * C3_MID);
+          const float ox = ((a0.x + a1.x) + (a2.x + a3.x)) + bias2.x;
+          const float oy = ((a0.y + a1.y) + (a2.y + a3.y)) + bias2.y;
+          int rr_c = rr, wq_c = wq;
+          if (c0 != qr * 64 + jc * C3_CHUNK) {           // the clamped last chunk: 3 positions back
+            wq_c -= (qr * 64 + jc * C3_CHUNK) - c0;
+            while (wq_c < 0) { wq_c += u.PW; --rr_c; }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          if (rr_c < u.cyc && wq_c >= hw && wq_c < hw + u.per)
+            *reinterpret_cast<uint32_t*>(p.out + (u.img_row0 + (size_t)(rr_c * u.per + wq_c - hw)) * p.ld + j * C3_MID + r_n2) =
+                pack_bf16(ox, oy);
+          rr += step_r;                                  // next chunk: 8 positions further along the padded grid
+          wq += step_w;
+          if (wq >= u.PW) { wq -= u.PW; ++rr; }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[C3_ACC_EMPTY + acc_i]);
+        if (e == 0 && lane == 0) C3_TRACE(9, blk_count);
       }
     }
   }
@@ -359,7 +391,7 @@ int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
     a.w[j] = (const __nv_bfloat16*)w->w_kk_bf16[j];
     a.bias[j] = w->b_kk[j];
     const int mma = w->kh[j] * ((w->kw[j] + C3_TL - 1) / C3_TL) * (C3_MID / 16) * 128;
-    cost[j] = mma > 2400 ? mma : 2400;
+    cost[j] = mma > C3_EPI_COST ? mma : C3_EPI_COST;
     cost_total += cost[j];
   }
   const size_t smem = 227 * 1024;
@@ -379,8 +411,23 @@ int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
     FTN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
+  static const char* trace_path = getenv("FLOWTIMES_CONV_TRACE");
+  static long long* trace_dev = nullptr;
+  if (trace_path && !trace_dev) cudaMalloc(&trace_dev, 16 * 256 * sizeof(long long));
+  if (trace_dev) { cudaMemsetAsync(trace_dev, 0, 16 * 256 * sizeof(long long), st); a.trace = trace_dev; }
   tc_conv3_kernel<<<ctas, C3_THREADS, smem, st>>>(a);
   FTN_LAUNCH_CHECK("tc_conv3_kernel");
+  if (trace_dev) {   // debug only (synchronises)
+    cudaStreamSynchronize(st);
+    static long long host[16 * 256];
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int ev = 0; ev < 16; ++ev)
+        for (int n = 0; n < 256; ++n)
+          if (host[ev * 256 + n]) fprintf(f, "%d %d %lld\n", ev, n, host[ev * 256 + n]);
+      fclose(f);
+    }
+  }
   return 0;
 }
 
