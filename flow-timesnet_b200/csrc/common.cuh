@@ -86,30 +86,41 @@ __device__ __forceinline__ float softplus20(float v) { return v > 20.0f ? v : lo
 // drop p <= 0, p outside [min_p, max_p], cycles < 2; merge exact duplicates;
 // groups ascend by period; mapping[candidate] = group.
 // `mean_amp[i]` (may be null) picks the canonical member of a duplicate group.
+// Scratch for plan_group_default.  On the device it must live in SHARED memory: dynamically indexed
+// thread-local arrays go to local memory, and the ~100 dependent L2-latency accesses of this routine were
+// most of the 30 us the selection kernel took.
+struct PlanScratch {
+  int grp_p[FTN_MAX_K];
+  int ok[FTN_MAX_K];
+};
+
 __host__ __device__ inline void plan_group_default(FtnPeriodPlan* pl, const int64_t* cand, int k,
                                                    int L, int min_p, int max_p,
-                                                   const float* mean_amp) {
+                                                   const float* mean_amp, PlanScratch* scratch) {
   pl->seq_len = L;
   pl->n_groups = 0;
-  int grp_p[FTN_MAX_K];
+  int* grp_p = scratch->grp_p;
   int G = 0;
   for (int i = 0; i < FTN_MAX_K; ++i) pl->mapping[i] = -1;
-  bool ok[FTN_MAX_K];
+  int* ok = scratch->ok;
   for (int i = 0; i < k; ++i) {
-    int64_t p = cand[i];
+    // periods are <= L, so 32-bit arithmetic is exact (64-bit division is ~10x the instructions on the device,
+    // and this runs in one thread on the critical path of every block)
+    const int64_t p64 = cand[i];
+    const int p = p64 > 0x7fffffff ? 0x7fffffff : (p64 < 0 ? 0 : (int)p64);
     bool v = p > 0;
     if (min_p > 0 && p < min_p) v = false;
     if (max_p > 0 && p > max_p) v = false;
     if (v) {
-      int pad = (int)((p - (L % p)) % p);
-      int cyc = (int)((L + pad) / p);
+      int pad = (p - (L % p)) % p;
+      int cyc = (L + pad) / p;
       if (cyc < 2) v = false;
     }
-    ok[i] = v;
+    ok[i] = v ? 1 : 0;
     if (!v) continue;
     bool seen = false;
-    for (int g = 0; g < G; ++g) seen = seen || (grp_p[g] == (int)p);
-    if (!seen) grp_p[G++] = (int)p;
+    for (int g = 0; g < G; ++g) seen = seen || (grp_p[g] == p);
+    if (!seen) grp_p[G++] = p;
   }
   // insertion sort ascending (G <= 16)
   for (int a = 1; a < G; ++a) {

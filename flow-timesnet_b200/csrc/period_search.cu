@@ -216,7 +216,8 @@ select_tail_kernel(const float* __restrict__ amp_sum, int global_batch, int L, i
       ++nv;
     }
     pl.n_valid = nv;
-    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp);
+    PlanScratch scr;
+    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp, &scr);
     *plan = pl;
   }
 }
@@ -306,6 +307,8 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   __shared__ int w_idx[32];
   __shared__ int s_top[FTN_MAX_K];
   __shared__ FtnPeriodPlan s_plan;
+  __shared__ PlanScratch s_scratch;
+  __shared__ float s_mean_amp[FTN_MAX_K];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (do_sum) {
@@ -371,15 +374,15 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
     const int upper = min(pmax, max(1, L - 1));
     const int lower = min_period;
     int nv = 0;
-    float mean_amp[FTN_MAX_K];
+    float* mean_amp = s_mean_amp;
     for (int i = 0; i < FTN_MAX_K; ++i) { pl.raw_freq[i] = 0; pl.freq[i] = 0; pl.period[i] = 0; }
     for (int r = 0; r < kk; ++r) {
-      const int64_t safe = max(s_top[r], 1);
+      const int safe = max(s_top[r], 1);
       pl.raw_freq[r] = safe;
       if (upper < lower) continue;
-      int64_t p = (L + safe - 1) / safe;
+      int p = (L + safe - 1) / safe;                 // 32-bit: everything here is <= L
       p = p < lower ? lower : (p > upper ? upper : p);
-      const int64_t cyc = (L + p - 1) / p;
+      const int cyc = (L + p - 1) / p;
       if (cyc < 2) continue;
       pl.freq[nv] = safe;
       pl.period[nv] = p;
@@ -387,7 +390,7 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
       ++nv;
     }
     pl.n_valid = nv;
-    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp);
+    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp, &s_scratch);
   }
   __syncthreads();
   {
@@ -395,30 +398,35 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
     uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
     for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
   }
-  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel)
+  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel).
+  // Fixed-trip, fully unrolled loops keep a[] / w[] in registers (dynamic indexing would spill them to local memory).
   const int nv = s_plan.n_valid;
   for (int b = tid; b < B; b += blockDim.x) {
-    float a[FTN_MAX_K];
-    for (int j = 0; j < k; ++j) {
+    float a[FTN_MAX_K], w[FTN_MAX_K];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < FTN_MAX_K; ++j) {
       float v = 0.f;
       if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + s_plan.freq[j]]);
       a[j] = v;
-      amps[(size_t)b * k + j] = from_f32<T>(v);
+      if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
+      if (j < nv && s_plan.mapping[j] >= 0) mx = fmaxf(mx, v);
+      w[j] = 0.f;
     }
-    float mx = -CUDART_INF_F;
-    for (int j = 0; j < nv; ++j)
-      if (s_plan.mapping[j] >= 0) mx = fmaxf(mx, a[j]);
     float den = 0.f;
-    for (int j = 0; j < nv; ++j)
-      if (s_plan.mapping[j] >= 0) den += expf(a[j] - mx);
-    float w[FTN_MAX_K];
-    for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
-    for (int j = 0; j < nv; ++j) {
-      const int g = s_plan.mapping[j];
+#pragma unroll
+    for (int j = 0; j < FTN_MAX_K; ++j)
+      if (j < nv && s_plan.mapping[j] >= 0) den += expf(a[j] - mx);
+#pragma unroll
+    for (int j = 0; j < FTN_MAX_K; ++j) {
+      const int g = (j < nv) ? s_plan.mapping[j] : -1;
       if (g < 0) continue;
       const float sm = round_to<T>(expf(a[j] - mx) / den);      // softmax fp32 -> dtype (timesnet.py:1000)
-      w[g] = round_to<T>(w[g] + sm);                            // scatter_add_ in dtype (:1009)
+#pragma unroll
+      for (int gg = 0; gg < FTN_MAX_K; ++gg)
+        if (gg == g) w[gg] = round_to<T>(w[gg] + sm);           // scatter_add_ in dtype (:1009)
     }
+#pragma unroll
     for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
   }
 }
@@ -549,7 +557,8 @@ extern "C" int ftn_plan_build_host(const int64_t* periods_host, int k, int L, in
   pl.n_raw = k;
   pl.n_valid = k;
   for (int i = 0; i < k; ++i) { pl.period[i] = periods_host[i]; pl.raw_freq[i] = 0; pl.freq[i] = 0; }
-  plan_group_default(&pl, pl.period, k, L, min_period, max_period, nullptr);
+  PlanScratch scr;
+  plan_group_default(&pl, pl.period, k, L, min_period, max_period, nullptr, &scr);
   *plan_host = pl;
   return 0;
 }

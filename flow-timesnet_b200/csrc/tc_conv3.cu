@@ -45,7 +45,7 @@ constexpr int C3_MAX_BLOCKS = 8;  // blocks per unit
 constexpr int C3_NCHUNK = C3_MID / 8;
 constexpr uint32_t C3_W_LBO = 128 * 16;                 // weight tile: chunk stride
 constexpr uint32_t C3_W_GROUP = C3_NCHUNK * C3_W_LBO;   // 8 KB per (dr, dq) group
-constexpr int C3_EPI_COST = 4000;   // measured cycles the drain of one block takes (bounds the small kernels)
+constexpr int C3_EPI_COST = 2400;   // floor of the per-block cost used to split the CTAs over branches
 constexpr int C3_CHUNK = 8;       // positions per epilogue chunk
 constexpr int C3_STAGE_FLOATS = 4 * C3_CHUNK * C3_MID;          // one staging tile: [tl][8 pos][32 n] fp32 = 4 KB
 constexpr int C3_STAGE_BYTES = 4 * 2 * C3_STAGE_FLOATS * 4;      // [column quarter][double buffer] = 32 KB
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_start = clock64();
 
   int j = 0;
   while (j + 1 < p.n_branch && (int)blockIdx.x >= p.cta_begin[j + 1]) ++j;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
       if (elect_one()) mma_commit(&bars[C3_IMG_EMPTY + buf]);   // loaders may overwrite the image buffer
       __syncwarp();
     }
+    if (p.trace && lane == 0 && blockIdx.x < 256) { p.trace[13 * 256 + blockIdx.x] = i + 1; p.trace[14 * 256 + blockIdx.x] = blk_count + 1; }
   } else if (warp <= 3 || warp == 4 + C3_EPI_WARPS) {
     // ===================== loaders =====================
     const int lt = warp > 3 ? 96 + lane : tid - 32;   // 0..127
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) tc_conv3_kernel(const TcConv3Ar
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && tid == 0 && blockIdx.x < 256) p.trace[15 * 256 + blockIdx.x] = clock64() - t_start;
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -391,6 +394,8 @@ int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
     a.w[j] = (const __nv_bfloat16*)w->w_kk_bf16[j];
     a.bias[j] = w->b_kk[j];
     const int mma = w->kh[j] * ((w->kw[j] + C3_TL - 1) / C3_TL) * (C3_MID / 16) * 128;
+    // a block is bound by shared-memory wavefronts: 96 per N = 256 MMA (A 4 KB + B 8 KB) plus ~2048 for the
+    // staging tile of the shifted-sum epilogue (measured: 4.9k cycles per 7x7 block)
     cost[j] = mma > C3_EPI_COST ? mma : C3_EPI_COST;
     cost_total += cost[j];
   }
