@@ -61,3 +61,51 @@ class GraphedCallable:
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
         return self._static_out
+
+
+class PipelinedRunner:
+    """Host-fed streaming of ``fn``: the host->device copy of batch ``i+1`` overlaps the graph replay of
+    batch ``i``.
+
+    Two captured graphs with their own static input buffers alternate; a dedicated copy stream fills
+    the idle one from (pinned) host memory while the compute stream replays the other.  ``submit``
+    enqueues copy + replay + device->host read-back of the result and returns immediately;
+    ``results`` are pinned host tensors, valid after ``synchronize()`` (or after the matching
+    event).  This is the serving loop a caller with host-resident windows uses
+    (reference: predict.py:930-950 moves each batch to the device inside its forecast loop).
+    """
+
+    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], depth: int = 2):
+        dev = example_inputs[0].device
+        self._graphs = [GraphedCallable(fn, example_inputs) for _ in range(depth)]
+        self._copy = torch.cuda.Stream(device=dev)
+        self._filled = [torch.cuda.Event() for _ in range(depth)]      # inputs of slot s are on the device
+        self._consumed = [torch.cuda.Event() for _ in range(depth)]    # slot s's replay has read its inputs
+        out = self._graphs[0]._static_out
+        if not isinstance(out, torch.Tensor):
+            raise TypeError("PipelinedRunner expects fn to return one tensor (e.g. the loss)")
+        self.results = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(depth)]
+        self._i = 0
+        cur = torch.cuda.current_stream(dev)
+        for e in self._consumed:
+            e.record(cur)
+
+    def submit(self, *host_inputs: torch.Tensor) -> int:
+        """Enqueue one batch (host tensors, ideally pinned).  Returns the slot whose ``results`` entry it fills."""
+        s = self._i % len(self._graphs)
+        self._i += 1
+        g = self._graphs[s]
+        cur = torch.cuda.current_stream()
+        self._copy.wait_event(self._consumed[s])            # the previous replay of this slot is done with the buffers
+        with torch.cuda.stream(self._copy):
+            for dst, src in zip(g.inputs, host_inputs):
+                dst.copy_(src, non_blocking=True)
+            self._filled[s].record(self._copy)
+        cur.wait_event(self._filled[s])
+        out = g.replay()
+        self._consumed[s].record(cur)
+        self.results[s].copy_(out, non_blocking=True)
+        return s
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream().synchronize()
