@@ -376,7 +376,13 @@ def run_native(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: communicator destruction with captured graphs that still hold
+        # NCCL nodes can block forever (seen on the 2-GPU box).  Everything is flushed and synchronised here.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
