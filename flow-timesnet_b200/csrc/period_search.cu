@@ -293,6 +293,78 @@ __device__ __forceinline__ void argbest_warp(float& s, int& i) {
   }
 }
 
+// Warp-cooperative equivalent of plan_group_default (common.cuh): lane i owns candidate i.  Same semantics
+// (default exact-duplicate grouping, groups ascending by period, canonical member = largest mean amplitude,
+// lowest index on ties), ~200 instructions per lane instead of ~2000 dependent ones in a single thread.
+__device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
+                                                float my_amp, int nv, int L, int min_p, int max_p) {
+  bool v = lane < nv && my_p > 0;
+  if (min_p > 0 && my_p < min_p) v = false;
+  if (max_p > 0 && my_p > max_p) v = false;
+  int pad = 0, cyc = 0;
+  if (v) {
+    pad = (my_p - (L % my_p)) % my_p;
+    cyc = (L + pad) / my_p;
+    if (cyc < 2) v = false;
+  }
+  const int p = v ? my_p : 0;
+  // first = lowest valid lane holding this period
+  bool first = v;
+  int rank = 0, off = 0, canon = lane;
+  float best = my_amp;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {
+    const int pj = __shfl_sync(0xffffffffu, p, j);
+    const float aj = __shfl_sync(0xffffffffu, my_amp, j);
+    if (pj > 0 && pj == p && j < lane) first = false;
+  }
+  const int padv = pad;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {
+    const int pj = __shfl_sync(0xffffffffu, p, j);
+    const int firstj = __shfl_sync(0xffffffffu, (int)first, j);
+    const int padj = __shfl_sync(0xffffffffu, padv, j);
+    const float aj = __shfl_sync(0xffffffffu, my_amp, j);
+    if (firstj && pj > 0 && pj < p) { ++rank; off += L + padj; }           // groups ascend by period
+    if (pj > 0 && pj == p && j != lane) {
+      // canonical member: strictly larger amplitude wins, scanning candidates in index order
+      if (j < canon ? !(best > aj) : aj > best) { canon = j; best = aj; }
+    }
+  }
+  const unsigned firsts = __ballot_sync(0xffffffffu, first && v);
+  const int G = __popc(firsts);
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {
+    const int firstj = __shfl_sync(0xffffffffu, (int)(first && v), j);
+    const int padj = __shfl_sync(0xffffffffu, padv, j);
+    if (firstj) total += L + padj;
+  }
+  if (lane < FTN_MAX_K) {
+    pl->mapping[lane] = v ? rank : -1;
+    // unused group slots
+    if (lane >= G) {
+      pl->grp_period[lane] = 0; pl->grp_pad[lane] = 0; pl->grp_cycles[lane] = 0; pl->grp_canon[lane] = -1;
+      pl->grp_row_off[lane] = total;
+    }
+  }
+  if (first && v) {
+    pl->grp_period[rank] = p;
+    pl->grp_pad[rank] = pad;
+    pl->grp_cycles[rank] = cyc;
+    pl->grp_row_off[rank] = off;
+    pl->grp_canon[rank] = canon;
+  }
+  if (lane == 0) {
+    pl->seq_len = L;
+    pl->n_groups = G;
+    pl->total_rows_per_window = total;
+    pl->grp_row_off[FTN_MAX_K] = total;
+  }
+}
+
+constexpr int kSelFinishThreads = 256;
+
 template <typename T>
 __global__ void __launch_bounds__(1024)
 select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ amp_sum, int do_sum, int B,
@@ -300,34 +372,27 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
                     T* __restrict__ amps, float* __restrict__ weights) {
   extern __shared__ float sf[];
   const int F = L / 2 + 1;
-  float* s_sum = sf;            // [F + 1]
-  float* s_score = sf + F + 1;  // [F]
-  __shared__ float part[32][33];
-  __shared__ float w_best[32];
-  __shared__ int w_idx[32];
+  float* s_sum = sf;              // [F + 1]
+  float* s_score = sf + F + 1;    // [F]
+  float* s_part = s_score + F;    // [32][F]   (do_sum only)
   __shared__ int s_top[FTN_MAX_K];
   __shared__ FtnPeriodPlan s_plan;
-  __shared__ PlanScratch s_scratch;
-  __shared__ float s_mean_amp[FTN_MAX_K];
+  __shared__ float s_e[FTN_MAX_K][kSelFinishThreads];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (do_sum) {
-    // same order as batch_sum_kernel: 32 row-lanes, each serial over b = r, r+32, ..., then a serial fold
-    const int fl = lane, r = warp;
-    for (int f0 = 0; f0 < F; f0 += 32) {
-      const int f = f0 + fl;
+    // same order as batch_sum_kernel: row-lane r sums b = r, r+32, ... serially, then a serial fold over r
+    for (int f = lane; f < F; f += 32) {
       float acc = 0.f;
-      if (f < F)
-        for (int b = r; b < B; b += 32) acc += amp_median[(size_t)b * F + f];
-      part[r][fl] = acc;
-      __syncthreads();
-      if (r == 0 && f < F) {
-        float t = 0.f;
-        for (int i = 0; i < 32; ++i) t += part[i][fl];
-        s_sum[f] = t;
-        amp_sum[f] = t;
-      }
-      __syncthreads();
+      for (int b = warp; b < B; b += 32) acc += amp_median[(size_t)b * F + f];
+      s_part[warp * F + f] = acc;
+    }
+    __syncthreads();
+    for (int f = tid; f < F; f += blockDim.x) {
+      float t = 0.f;
+      for (int i = 0; i < 32; ++i) t += s_part[i * F + f];
+      s_sum[f] = t;
+      amp_sum[f] = t;
     }
     if (tid == 0) { s_sum[F] = (float)B; amp_sum[F] = (float)B; }
   } else {
@@ -346,51 +411,52 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   }
   __syncthreads();
   const int kk = min(k, F - 1);
-  for (int r = 0; r < kk; ++r) {
-    float bs = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int f = tid; f < F; f += blockDim.x) {
-      bool taken = false;
-      for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
-      if (taken) continue;
-      const float sc = s_score[f];
-      if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
-    }
-    argbest_warp(bs, bi);
-    if (lane == 0) { w_best[warp] = bs; w_idx[warp] = bi; }
-    __syncthreads();
-    if (warp == 0) {
-      bs = w_best[lane];
-      bi = w_idx[lane];
+  if (warp == 0) {
+    // top-k by one warp: kk rounds of (lane-local scan, shuffle arg-best), no block barriers
+    for (int r = 0; r < kk; ++r) {
+      float bs = -CUDART_INF_F;
+      int bi = 0x7fffffff;
+      for (int f = lane; f < F; f += 32) {
+        bool taken = false;
+        for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
+        if (taken) continue;
+        const float sc = s_score[f];
+        if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
+      }
       argbest_warp(bs, bi);
       if (lane == 0) s_top[r] = bi;
+      __syncwarp();
     }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    FtnPeriodPlan& pl = s_plan;
-    pl.n_raw = kk;
-    pl.reserved[0] = pl.reserved[1] = pl.reserved[2] = 0;
+    // period math for candidate `lane` (timesnet.py:137-154), then the cooperative grouping
     const int upper = min(pmax, max(1, L - 1));
     const int lower = min_period;
-    int nv = 0;
-    float* mean_amp = s_mean_amp;
-    for (int i = 0; i < FTN_MAX_K; ++i) { pl.raw_freq[i] = 0; pl.freq[i] = 0; pl.period[i] = 0; }
-    for (int r = 0; r < kk; ++r) {
-      const int safe = max(s_top[r], 1);
-      pl.raw_freq[r] = safe;
-      if (upper < lower) continue;
-      int p = (L + safe - 1) / safe;                 // 32-bit: everything here is <= L
-      p = p < lower ? lower : (p > upper ? upper : p);
-      const int cyc = (L + p - 1) / p;
-      if (cyc < 2) continue;
-      pl.freq[nv] = safe;
-      pl.period[nv] = p;
-      mean_amp[nv] = s_sum[safe];
-      ++nv;
+    int safe = 0, per = 0;
+    bool keep = false;
+    if (lane < kk) {
+      safe = max(s_top[lane], 1);
+      if (upper >= lower) {
+        int p = (L + safe - 1) / safe;
+        p = p < lower ? lower : (p > upper ? upper : p);
+        if ((L + p - 1) / p >= 2) { keep = true; per = p; }
+      }
     }
-    pl.n_valid = nv;
-    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp, &s_scratch);
+    // compact the kept candidates in rank order: position = number of kept lanes below
+    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    const int nv = __popc(kept);
+    const int pos = __popc(kept & ((1u << lane) - 1u));
+    if (lane < FTN_MAX_K) {
+      s_plan.raw_freq[lane] = lane < kk ? safe : 0;
+      s_plan.freq[lane] = 0;
+      s_plan.period[lane] = 0;
+    }
+    if (lane < 3) s_plan.reserved[lane] = 0;
+    __syncwarp();
+    if (keep) { s_plan.freq[pos] = safe; s_plan.period[pos] = per; }
+    if (lane == 0) { s_plan.n_raw = kk; s_plan.n_valid = nv; }
+    __syncwarp();
+    const int my_p = lane < nv ? (int)s_plan.period[lane] : 0;
+    const float my_amp = lane < nv ? s_sum[(int)s_plan.freq[lane]] : 0.f;
+    plan_group_warp(&s_plan, lane, my_p, my_amp, nv, L, min_period, pmax);
   }
   __syncthreads();
   {
@@ -398,36 +464,32 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
     uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
     for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
   }
-  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel).
-  // Fixed-trip, fully unrolled loops keep a[] / w[] in registers (dynamic indexing would spill them to local memory).
+  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel)
   const int nv = s_plan.n_valid;
-  for (int b = tid; b < B; b += blockDim.x) {
-    float a[FTN_MAX_K], w[FTN_MAX_K];
-    float mx = -CUDART_INF_F;
-#pragma unroll
-    for (int j = 0; j < FTN_MAX_K; ++j) {
-      float v = 0.f;
-      if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + s_plan.freq[j]]);
-      a[j] = v;
-      if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
-      if (j < nv && s_plan.mapping[j] >= 0) mx = fmaxf(mx, v);
-      w[j] = 0.f;
+  if (tid < kSelFinishThreads) {
+    for (int b = tid; b < B; b += kSelFinishThreads) {
+      float mx = -CUDART_INF_F;
+      for (int j = 0; j < k; ++j) {
+        float v = 0.f;
+        if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + (int)s_plan.freq[j]]);
+        amps[(size_t)b * k + j] = from_f32<T>(v);
+        if (j < nv) {
+          s_e[j][tid] = v;
+          if (s_plan.mapping[j] >= 0) mx = fmaxf(mx, v);
+        }
+      }
+      float den = 0.f;
+      for (int j = 0; j < nv; ++j)
+        if (s_plan.mapping[j] >= 0) den += expf(s_e[j][tid] - mx);
+      for (int j = 0; j < nv; ++j)
+        s_e[j][tid] = round_to<T>(expf(s_e[j][tid] - mx) / den);     // softmax fp32 -> dtype (timesnet.py:1000)
+      for (int g = 0; g < FTN_MAX_K; ++g) {
+        float acc = 0.f;
+        for (int j = 0; j < nv; ++j)
+          if (s_plan.mapping[j] == g) acc = round_to<T>(acc + s_e[j][tid]);   // scatter_add_ in dtype (:1009)
+        weights[(size_t)b * FTN_MAX_K + g] = acc;
+      }
     }
-    float den = 0.f;
-#pragma unroll
-    for (int j = 0; j < FTN_MAX_K; ++j)
-      if (j < nv && s_plan.mapping[j] >= 0) den += expf(a[j] - mx);
-#pragma unroll
-    for (int j = 0; j < FTN_MAX_K; ++j) {
-      const int g = (j < nv) ? s_plan.mapping[j] : -1;
-      if (g < 0) continue;
-      const float sm = round_to<T>(expf(a[j] - mx) / den);      // softmax fp32 -> dtype (timesnet.py:1000)
-#pragma unroll
-      for (int gg = 0; gg < FTN_MAX_K; ++gg)
-        if (gg == g) w[gg] = round_to<T>(w[gg] + sm);           // scatter_add_ in dtype (:1009)
-    }
-#pragma unroll
-    for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
   }
 }
 
@@ -461,18 +523,18 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
                                int L, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
                                cudaStream_t st) {
   const int F = L / 2 + 1;
-  const size_t smem = (size_t)(2 * F + 1) * sizeof(float);
+  const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : 0)) * sizeof(float);
   FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
   static size_t attr[2] = {0, 0};
   if (dtype == FTN_F32) {
-    if (smem > 40 * 1024 && smem > attr[0]) {
+    if (smem > 24 * 1024 && smem > attr[0]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[0] = smem;
     }
     select_fused_kernel<float><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax, min_period,
                                                       plan, (float*)amps, weights);
   } else {
-    if (smem > 40 * 1024 && smem > attr[1]) {
+    if (smem > 24 * 1024 && smem > attr[1]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[1] = smem;
     }
