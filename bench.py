@@ -35,6 +35,11 @@ import torch  # noqa: E402
 
 import flowtimes_synth as syn  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels, per launch, from the ncu --set full
+# captures summarised under profiles/ (r1t); algorithmic bytes are in DESIGN.md section 4
+NCU_TRAFFIC = {"elec": {"tc_conv3_kernel": 23.0e6, "tc_mid_kernel": 36.3e6, "unit": "bytes per launch",
+                        "source": "profiles/r1t_ncu_full.csv"}}
+
 METRIC = "timesblock_forward_windows_per_sec"
 UNIT = "windows/s"
 
@@ -247,6 +252,8 @@ def run_native(args):
     conv_ms, conv_calls = nv.timing_read(nv.FAM_CONV)
     spec_ms, spec_calls = nv.timing_read(nv.FAM_SPECTRUM)
     agg_ms, agg_calls = nv.timing_read(nv.FAM_AGGREGATE)
+    chain = {name: nv.timing_read(fam) for name, fam in (
+        ("s1_gemm", nv.FAM_S1), ("kk_a", nv.FAM_KK_A), ("mid", nv.FAM_MID), ("kk_b", nv.FAM_KK_B), ("s6_gemm", nv.FAM_S6))}
     nv.timing_enable(False)
     ms_total = eager_ms_total
     # ---- pass B: the same step replayed from a CUDA graph (no host round trip exists on the path) ----
@@ -335,6 +342,25 @@ def run_native(args):
                     "share_of_step": {"conv": conv_ms / eager_ms_total, "spectrum": spec_ms / eager_ms_total,
                                       "aggregate": agg_ms / eager_ms_total,
                                       "note": "shares of the eager pass (library CUDA events)"}}
+        # single kernels of the bf16 chain: executed (post weight-folding) FLOPs per call / measured time
+        C_, F_, nb_ = wl.d_model, wl.ff, len(wl.kernel_set)
+        mid_ = syn._mid(C_, F_, wl.bottleneck_ratio)
+        taps_ = sum(kh * kw for kh, kw in wl.kernel_set)
+        pos_per_call = wl.B * statistics.mean(sum(wl.T + ((-wl.T) % p) for p in gp) for gp in group_periods)
+        mac_per_pos = {"s1_gemm": C_ * nb_ * mid_, "kk_a": taps_ * mid_ * mid_,
+                       "mid": nb_ * mid_ * F_ + C_ * F_ + F_ * nb_ * mid_ + F_ * C_,
+                       "kk_b": taps_ * mid_ * mid_, "s6_gemm": nb_ * mid_ * C_}
+        kernels = []
+        for name, (ms_f, calls) in chain.items():
+            if calls:
+                avg = ms_f / calls
+                tf = 2.0 * mac_per_pos[name] * pos_per_call / (avg * 1e-3) / 1e12
+                kernels.append({"kernel": name, "avg_ms": avg, "executed_TFLOPs": tf, "frac_of_peak": tf / peak_tf,
+                                "executed_mac_per_position": mac_per_pos[name]})
+        roofline["chain_kernels"] = kernels
+        roofline["executed_flops_per_launch_group"] = 2.0 * sum(mac_per_pos.values()) * pos_per_call
+        # dram bytes of one tc_mid / tc_conv3 launch from the committed ncu --set full captures (profiles/)
+        roofline["traffic"] = NCU_TRAFFIC.get(wl.name)
         e_bytes = 2 if sdt == torch.bfloat16 else 4
         hbm = []
         for name, ms_f, calls, per_call in (

@@ -46,7 +46,9 @@ struct TimedScope {
   int slot;
   cudaStream_t st;
 };
-enum { FTN_FAM_SPECTRUM = 0, FTN_FAM_CONV = 1, FTN_FAM_AGGREGATE = 2, FTN_FAM_COUNT = 3 };
+enum { FTN_FAM_SPECTRUM = 0, FTN_FAM_CONV = 1, FTN_FAM_AGGREGATE = 2,
+       // single kernels of the bf16 Inception chain (nested inside FTN_FAM_CONV)
+       FTN_FAM_S1 = 3, FTN_FAM_KK_A = 4, FTN_FAM_MID = 5, FTN_FAM_KK_B = 6, FTN_FAM_S6 = 7, FTN_FAM_COUNT = 8 };
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

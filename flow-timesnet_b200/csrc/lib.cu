@@ -29,7 +29,7 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- optional event timing ---------------------------------------------------
-constexpr int kMaxTimed = 8192;
+constexpr int kMaxTimed = 32768;
 struct TimedRec { cudaEvent_t a, b; int family; };
 static std::mutex g_tmu;
 static std::vector<TimedRec> g_recs;

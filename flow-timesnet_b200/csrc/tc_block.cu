@@ -31,6 +31,12 @@ size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeight
   return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)(a->cout > a->cin ? a->cout : a->cin) * 2) + 2 * al256(rows * nbB * 2) + 256;
 }
 
+int tc_stage_launch(const TcGemmArgs& a, cudaStream_t st) {
+  static const bool force_v1 = getenv("FLOWTIMES_GEMM_V1") != nullptr;   // A/B switch for profiling
+  if (!force_v1 && tc_gemm2_eligible(a)) return tc_gemm2_launch(a, st);
+  return tc_gemm_launch(a, st);
+}
+
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
   static const bool force_v1 = getenv("FLOWTIMES_CONV_V1") != nullptr;   // A/B switches for profiling
@@ -70,14 +76,15 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   TcGemmArgs s = base;
   s.a1 = xb; s.a1_seq = 1; s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in; s.K1 = C;
   s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
-  if (int rc = tc_gemm_launch(s, st)) return rc;
+  { TimedScope t1(FTN_FAM_S1, st); if (int rc = tc_stage_launch(s, st)) return rc; }
   // S2
-  if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc;
+  { TimedScope t2(FTN_FAM_KK_A, st); if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc; }
   static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
   const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
   __nv_bfloat16* q = a2;   // the fused middle never materialises a2: its slot holds q = a2 . V_res + b (C columns)
   if (fused_mid) {
     // S3 + S4 + block B's res_proj in one persistent kernel (tc_mid.cu)
+    TimedScope t3(FTN_FAM_MID, st);
     if (int rc = tc_mid_launch(plan, B, L, max_groups, h2, rows, xb, a, b, act, g1, q, st)) return rc;
   } else {
     // S3
@@ -98,7 +105,7 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
     if (int rc = tc_gemm_launch(s, st)) return rc;
   }
   // S5
-  if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc;
+  { TimedScope t4(FTN_FAM_KK_B, st); if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc; }
   // S6
   s = base;
   s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;
@@ -112,7 +119,8 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   } else {
     s.res = TC_RES_POS; s.res_ptr = a2; s.res_ld = F;
   }
-  return tc_gemm_launch(s, st);
+  TimedScope t5(FTN_FAM_S6, st);
+  return tc_stage_launch(s, st);
 }
 
 }  // namespace ftn

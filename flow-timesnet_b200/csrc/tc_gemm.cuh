@@ -36,6 +36,10 @@ struct TcGemmArgs {
 };
 
 int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st);
+// persistent variant for the K <= 128, N <= 128 single-operand stages (tc_gemm2.cu); tc_stage_launch picks
+bool tc_gemm2_eligible(const TcGemmArgs& a);
+int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st);
+int tc_stage_launch(const TcGemmArgs& a, cudaStream_t st);
 int tc_worst_case_tiles(int B, int L, int max_groups);
 
 // k x k stage on tile-major bf16 activations (SIMT for now; see conv_gemm.cu)

@@ -160,6 +160,7 @@ def launch_count() -> int:
 
 
 FAM_SPECTRUM, FAM_CONV, FAM_AGGREGATE = 0, 1, 2
+FAM_S1, FAM_KK_A, FAM_MID, FAM_KK_B, FAM_S6 = 3, 4, 5, 6, 7     # single kernels of the bf16 chain
 
 
 def timing_enable(on: bool) -> None:
