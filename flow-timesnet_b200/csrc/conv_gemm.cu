@@ -63,10 +63,10 @@ struct ConvGemmParams {
   Src xsub;    // OUT_DELTA: grid to subtract (SEQ x)
 };
 
-template <typename T>
+template <typename T, bool TILED = false>
 __device__ __forceinline__ float load_src(const Src& s, int B, int L, int b, int t, int Lp, int off_g,
                                           int ch, size_t img_row0 = 0) {
-  if (s.kind == SRC_TILED)
+  if (TILED)   // compile-time: the fp32 chain never pays for the tile-major addressing of the bf16 fallback
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.ptr)[(img_row0 + t) * s.ld + s.ch_off + ch]);
   if (s.kind == SRC_SEQ) {
     if (t >= L) return 0.f;
@@ -76,7 +76,7 @@ __device__ __forceinline__ float load_src(const Src& s, int B, int L, int b, int
   return reinterpret_cast<const float*>(s.ptr)[row * s.ld + s.ch_off + ch];
 }
 
-template <typename T, int TM, int TN, int RM, int RN>
+template <typename T, int TM, int TN, int RM, int RN, bool TILED>
 __global__ void __launch_bounds__((TM / RM) * (TN / RN))
 conv_gemm_kernel(const ConvGemmParams p) {
   constexpr int NT = (TM / RM) * (TN / RN);
@@ -164,7 +164,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
         int r2 = row_r[i] + dr, w2 = row_w[i] + dw;
         float v = 0.f;
         if (kc + lk < p.K1 && r2 >= 0 && r2 < cyc && w2 >= 0 && w2 < per)
-          v = load_src<T>(p.a1, p.B, p.L, b, r2 * per + w2, Lp, off_g, br.ci_off + kc + lk, img_row0);
+          v = load_src<T, TILED>(p.a1, p.B, p.L, b, r2 * per + w2, Lp, off_g, br.ci_off + kc + lk, img_row0);
         As[lr0 + i * ROWS_PER_PASS][lk] = v;
       }
       load_w(wtap, p.K1, kc);
@@ -191,7 +191,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
       for (int i = 0; i < A_PASSES; ++i) {
         int t = t0 + lr0 + i * ROWS_PER_PASS;
         float v = 0.f;
-        if (kc + lk < p.K2 && t < Lp) v = load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, kc + lk, img_row0);
+        if (kc + lk < p.K2 && t < Lp) v = load_src<T, false>(p.a2, p.B, p.L, b, t, Lp, off_g, kc + lk);
         As[lr0 + i * ROWS_PER_PASS][lk] = v;
       }
       load_w(p.w2, p.K2, kc);
@@ -210,13 +210,13 @@ conv_gemm_kernel(const ConvGemmParams p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       if (p.p2 == P2_GEMM) v += p.b2[n];
-      else if (p.p2 == P2_IDENTITY) v += load_src<T>(p.a2, p.B, p.L, b, t, Lp, off_g, n, img_row0);
+      else if (p.p2 == P2_IDENTITY) v += load_src<T, false>(p.a2, p.B, p.L, b, t, Lp, off_g, n);
       if (p.act2 >= 0) v = apply_act(v, p.act2);
-      if (p.out_kind == OUT_POS) {
+      if (TILED) {
+        reinterpret_cast<__nv_bfloat16*>(p.out)[(img_row0 + t) * p.ldo + br.co_off + n] = __float2bfloat16_rn(v);
+      } else if (p.out_kind == OUT_POS) {
         size_t row = (size_t)p.B * off_g + (size_t)b * Lp + t;
         reinterpret_cast<float*>(p.out)[row * p.ldo + br.co_off + n] = v;
-      } else if (p.out_kind == OUT_TILED) {
-        reinterpret_cast<__nv_bfloat16*>(p.out)[(img_row0 + t) * p.ldo + br.co_off + n] = __float2bfloat16_rn(v);
       } else if (t < p.L) {
         v -= load_src<T>(p.xsub, p.B, p.L, b, t, Lp, off_g, n);
         reinterpret_cast<T*>(p.out)[(((size_t)g * p.B + b) * p.L + t) * p.N + n] = from_f32<T>(v);
@@ -225,17 +225,17 @@ conv_gemm_kernel(const ConvGemmParams p) {
   }
 }
 
-template <typename T>
+template <typename T, bool TILED = false>
 static int launch_conv_gemm(const ConvGemmParams& p, int n_branch, int max_groups, cudaStream_t st) {
   const int Lp_max = 2 * p.L;
   if (p.N > 32) {
     constexpr int TM = 128, TN = 64;
     dim3 grid(max_groups * p.B * ((Lp_max + TM - 1) / TM), (p.N + TN - 1) / TN, n_branch);
-    conv_gemm_kernel<T, TM, TN, 8, 4><<<grid, 256, 0, st>>>(p);
+    conv_gemm_kernel<T, TM, TN, 8, 4, TILED><<<grid, 256, 0, st>>>(p);
   } else {
     constexpr int TM = 128, TN = 32;
     dim3 grid(max_groups * p.B * ((Lp_max + TM - 1) / TM), (p.N + TN - 1) / TN, n_branch);
-    conv_gemm_kernel<T, TM, TN, 8, 4><<<grid, 128, 0, st>>>(p);
+    conv_gemm_kernel<T, TM, TN, 8, 4, TILED><<<grid, 128, 0, st>>>(p);
   }
   FTN_LAUNCH_CHECK("conv_gemm_kernel");
   return 0;
@@ -361,7 +361,7 @@ int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_grou
   for (int j = 0; j < w->n_branch; ++j)
     p.br[j] = Branch{w->w_kk[j], w->b_kk[j], w->kh[j], w->kw[j], j * w->mid, j * w->mid};
   p.act1 = -1; p.p2 = P2_NONE; p.act2 = -1; p.out_kind = OUT_TILED; p.out = out; p.ldo = ld;
-  return launch_conv_gemm<__nv_bfloat16>(p, w->n_branch, max_groups, st);
+  return launch_conv_gemm<__nv_bfloat16, true>(p, w->n_branch, max_groups, st);
 }
 
 }  // namespace ftn

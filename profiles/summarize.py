@@ -15,7 +15,10 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum"]
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
 
 
 def launches(path: Path, out: Path):
@@ -53,7 +56,7 @@ def full(rep: Path, out: Path):
 if __name__ == "__main__":
     tag = sys.argv[1]
     here = Path(__file__).resolve().parent
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and sys.argv[2] not in ("", "-"):
         launches(Path(sys.argv[2]), here / f"{tag}_launches.txt")
     if len(sys.argv) > 3:
         full(Path(sys.argv[3]), here / f"{tag}_ncu_full.csv")
