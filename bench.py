@@ -254,6 +254,8 @@ def run_native(args):
     agg_ms, agg_calls = nv.timing_read(nv.FAM_AGGREGATE)
     chain = {name: nv.timing_read(fam) for name, fam in (
         ("s1_gemm", nv.FAM_S1), ("kk_a", nv.FAM_KK_A), ("mid", nv.FAM_MID), ("kk_b", nv.FAM_KK_B), ("s6_gemm", nv.FAM_S6))}
+    search = {name: nv.timing_read(fam) for name, fam in (
+        ("fft", nv.FAM_FFT), ("median", nv.FAM_MEDIAN), ("select", nv.FAM_SELECT))}
     nv.timing_enable(False)
     ms_total = eager_ms_total
     # ---- pass B: the same step replayed from a CUDA graph (no host round trip exists on the path) ----
@@ -372,6 +374,7 @@ def run_native(args):
                 hbm.append({"kernel": name, "achieved_GBs": gbs, "frac": gbs / float(peaks["hbm_gbs"]),
                             "avg_ms": ms_f / calls, "algorithmic_bytes": per_call})
         roofline["hbm_kernels"] = hbm
+        roofline["search_kernels"] = [{"kernel": n, "avg_ms": ms_f / calls} for n, (ms_f, calls) in search.items() if calls]
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             sample_B = min(wl.B, 8)

@@ -48,7 +48,9 @@ struct TimedScope {
 };
 enum { FTN_FAM_SPECTRUM = 0, FTN_FAM_CONV = 1, FTN_FAM_AGGREGATE = 2,
        // single kernels of the bf16 Inception chain (nested inside FTN_FAM_CONV)
-       FTN_FAM_S1 = 3, FTN_FAM_KK_A = 4, FTN_FAM_MID = 5, FTN_FAM_KK_B = 6, FTN_FAM_S6 = 7, FTN_FAM_COUNT = 8 };
+       FTN_FAM_S1 = 3, FTN_FAM_KK_A = 4, FTN_FAM_MID = 5, FTN_FAM_KK_B = 6, FTN_FAM_S6 = 7,
+       // single kernels of the period search (nested inside FTN_FAM_SPECTRUM)
+       FTN_FAM_FFT = 8, FTN_FAM_MEDIAN = 9, FTN_FAM_SELECT = 10, FTN_FAM_COUNT = 11 };
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -285,7 +285,7 @@ __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, i
 // a sharded batch the caller runs batch_sum_kernel, all-reduces, and calls this with do_sum = 0.
 // Summation order, score rounding, tie rule and grouping are the ones of the separate kernels.
 __device__ __forceinline__ void argbest_warp(float& s, int& i) {
-#pragma unroll
+  #pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
     const float so = __shfl_xor_sync(0xffffffffu, s, o);
     const int io = __shfl_xor_sync(0xffffffffu, i, o);
@@ -296,7 +296,7 @@ __device__ __forceinline__ void argbest_warp(float& s, int& i) {
 // Warp-cooperative equivalent of plan_group_default (common.cuh): lane i owns candidate i.  Same semantics
 // (default exact-duplicate grouping, groups ascending by period, canonical member = largest mean amplitude,
 // lowest index on ties), ~200 instructions per lane instead of ~2000 dependent ones in a single thread.
-__device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
+__device__ __noinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
                                                 float my_amp, int nv, int L, int min_p, int max_p) {
   bool v = lane < nv && my_p > 0;
   if (min_p > 0 && my_p < min_p) v = false;
@@ -312,14 +312,14 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   bool first = v;
   int rank = 0, off = 0, canon = lane;
   float best = my_amp;
-#pragma unroll
+  #pragma unroll 1
   for (int j = 0; j < FTN_MAX_K; ++j) {
     const int pj = __shfl_sync(0xffffffffu, p, j);
     const float aj = __shfl_sync(0xffffffffu, my_amp, j);
     if (pj > 0 && pj == p && j < lane) first = false;
   }
   const int padv = pad;
-#pragma unroll
+  #pragma unroll 1
   for (int j = 0; j < FTN_MAX_K; ++j) {
     const int pj = __shfl_sync(0xffffffffu, p, j);
     const int firstj = __shfl_sync(0xffffffffu, (int)first, j);
@@ -334,7 +334,7 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   const unsigned firsts = __ballot_sync(0xffffffffu, first && v);
   const int G = __popc(firsts);
   int total = 0;
-#pragma unroll
+  #pragma unroll 1
   for (int j = 0; j < FTN_MAX_K; ++j) {
     const int firstj = __shfl_sync(0xffffffffu, (int)(first && v), j);
     const int padj = __shfl_sync(0xffffffffu, padv, j);
@@ -363,7 +363,7 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   }
 }
 
-constexpr int kSelFinishThreads = 256;
+constexpr int kSelFinishThreads = 128;   // 2 x 8 KB of per-thread slots; static + dynamic shared memory must stay < 48 KB by default
 
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -378,30 +378,62 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   __shared__ int s_top[FTN_MAX_K];
   __shared__ FtnPeriodPlan s_plan;
   __shared__ float s_e[FTN_MAX_K][kSelFinishThreads];
+  __shared__ float s_w[FTN_MAX_K][kSelFinishThreads];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (do_sum) {
-    // same order as batch_sum_kernel: row-lane r sums b = r, r+32, ... serially, then a serial fold over r
-    for (int f = lane; f < F; f += 32) {
-      float acc = 0.f;
-      for (int b = warp; b < B; b += 32) acc += amp_median[(size_t)b * F + f];
-      s_part[warp * F + f] = acc;
+    // same order as batch_sum_kernel: row-lane r sums b = r, r+32, ... serially, then a serial fold over r.
+    // Loads are issued four at a time before they are consumed: this kernel is one CTA, so dependent L2 round
+    // trips (~700 cycles each on B200), not instructions, are what it spends its time on.
+#pragma unroll 1
+    for (int f0 = lane; f0 < F; f0 += 128) {       // 4 bins x 2 rows = 8 independent loads in flight per thread
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      int b = warp;
+#pragma unroll 1
+      for (; b + 32 < B; b += 64) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int f = f0 + 32 * q;
+          v[q] = f < F ? amp_median[(size_t)b * F + f] : 0.f;
+          v[4 + q] = f < F ? amp_median[(size_t)(b + 32) * F + f] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[q] += v[q]; acc[q] += v[4 + q]; }   // same order as the serial loop
+      }
+#pragma unroll 1
+      for (; b < B; b += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int f = f0 + 32 * q;
+          if (f < F) acc[q] += amp_median[(size_t)b * F + f];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int f = f0 + 32 * q;
+        if (f < F) s_part[warp * F + f] = acc[q];
+      }
     }
     __syncthreads();
+#pragma unroll 1
     for (int f = tid; f < F; f += blockDim.x) {
       float t = 0.f;
+#pragma unroll 8
       for (int i = 0; i < 32; ++i) t += s_part[i * F + f];
       s_sum[f] = t;
       amp_sum[f] = t;
     }
     if (tid == 0) { s_sum[F] = (float)B; amp_sum[F] = (float)B; }
   } else {
+#pragma unroll 1
     for (int f = tid; f <= F; f += blockDim.x) s_sum[f] = amp_sum[f];
   }
   __syncthreads();
 
   // scores in the activation dtype, exactly as timesnet.py:119-130
   const float gb = global_batch > 0 ? (float)global_batch : s_sum[F];
+  #pragma unroll 1
   for (int f = tid; f < F; f += blockDim.x) {
     const float m = round_to<T>(s_sum[f] / gb);
     const float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
@@ -411,22 +443,32 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   }
   __syncthreads();
   const int kk = min(k, F - 1);
+  // top-k by rank counting: candidate f's rank = number of candidates that beat it (the ordering `better` is
+  // total: score, then lower bin), so all kk winners are found in one parallel pass instead of kk dependent
+  // arg-max rounds
+  // (s_part is free again after the batch sum and doubles as the integer rank counters)
+  int* s_rank = reinterpret_cast<int*>(s_sum + 2 * F + 1);
+  const int nseg = max(1, (int)blockDim.x / F);            // threads per candidate
+  const int seg_len = (F + nseg - 1) / nseg;
+#pragma unroll 1
+  for (int f = tid; f < F; f += blockDim.x) s_rank[f] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int item = tid; item < nseg * F; item += blockDim.x) {
+    const int f = item % F, sg = item / F;
+    const float sc = s_score[f];
+    const int o_end = min(F, (sg + 1) * seg_len);
+    int part = 0;
+#pragma unroll 4
+    for (int o = sg * seg_len; o < o_end; ++o) part += (o != f && better(s_score[o], o, sc, f)) ? 1 : 0;
+    if (part) atomicAdd(&s_rank[f], part);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int f = tid; f < F; f += blockDim.x)
+    if (s_rank[f] < kk) s_top[s_rank[f]] = f;
+  __syncthreads();
   if (warp == 0) {
-    // top-k by one warp: kk rounds of (lane-local scan, shuffle arg-best), no block barriers
-    for (int r = 0; r < kk; ++r) {
-      float bs = -CUDART_INF_F;
-      int bi = 0x7fffffff;
-      for (int f = lane; f < F; f += 32) {
-        bool taken = false;
-        for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
-        if (taken) continue;
-        const float sc = s_score[f];
-        if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
-      }
-      argbest_warp(bs, bi);
-      if (lane == 0) s_top[r] = bi;
-      __syncwarp();
-    }
     // period math for candidate `lane` (timesnet.py:137-154), then the cooperative grouping
     const int upper = min(pmax, max(1, L - 1));
     const int lower = min_period;
@@ -462,33 +504,44 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_plan);
     uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
+    #pragma unroll 1
     for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
   }
   // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel)
   const int nv = s_plan.n_valid;
   if (tid < kSelFinishThreads) {
+    #pragma unroll 1
     for (int b = tid; b < B; b += kSelFinishThreads) {
       float mx = -CUDART_INF_F;
-      for (int j = 0; j < k; ++j) {
-        float v = 0.f;
-        if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + (int)s_plan.freq[j]]);
-        amps[(size_t)b * k + j] = from_f32<T>(v);
+      float raw[FTN_MAX_K];
+#pragma unroll
+      for (int j = 0; j < FTN_MAX_K; ++j)                    // all loads in flight together (one L2 round trip)
+        raw[j] = j < nv ? amp_median[(size_t)b * F + (int)s_plan.freq[j]] : 0.f;
+#pragma unroll
+      for (int j = 0; j < FTN_MAX_K; ++j) {
+        const float v = j < nv ? round_to<T>(raw[j]) : 0.f;
+        if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
         if (j < nv) {
           s_e[j][tid] = v;
           if (s_plan.mapping[j] >= 0) mx = fmaxf(mx, v);
         }
       }
       float den = 0.f;
+      #pragma unroll 1
       for (int j = 0; j < nv; ++j)
         if (s_plan.mapping[j] >= 0) den += expf(s_e[j][tid] - mx);
+      #pragma unroll 1
       for (int j = 0; j < nv; ++j)
         s_e[j][tid] = round_to<T>(expf(s_e[j][tid] - mx) / den);     // softmax fp32 -> dtype (timesnet.py:1000)
-      for (int g = 0; g < FTN_MAX_K; ++g) {
-        float acc = 0.f;
-        for (int j = 0; j < nv; ++j)
-          if (s_plan.mapping[j] == g) acc = round_to<T>(acc + s_e[j][tid]);   // scatter_add_ in dtype (:1009)
-        weights[(size_t)b * FTN_MAX_K + g] = acc;
+      #pragma unroll
+      for (int g = 0; g < FTN_MAX_K; ++g) s_w[g][tid] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < nv; ++j) {                        // candidates in index order, exactly like scatter_add_
+        const int g = s_plan.mapping[j];
+        if (g >= 0) s_w[g][tid] = round_to<T>(s_w[g][tid] + s_e[j][tid]);   // scatter_add_ in dtype (:1009)
       }
+#pragma unroll
+      for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = s_w[g][tid];
     }
   }
 }
@@ -523,18 +576,19 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
                                int L, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
                                cudaStream_t st) {
   const int F = L / 2 + 1;
-  const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : 0)) * sizeof(float);
+  TimedScope ts(FTN_FAM_SELECT, st);
+  const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : F)) * sizeof(float);
   FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
   static size_t attr[2] = {0, 0};
   if (dtype == FTN_F32) {
-    if (smem > 24 * 1024 && smem > attr[0]) {
+    if (smem > 16 * 1024 && smem > attr[0]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[0] = smem;
     }
     select_fused_kernel<float><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax, min_period,
                                                       plan, (float*)amps, weights);
   } else {
-    if (smem > 24 * 1024 && smem > attr[1]) {
+    if (smem > 16 * 1024 && smem > attr[1]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[1] = smem;
     }
@@ -565,7 +619,8 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
   FTN_REQUIRE(workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_spectrum: workspace too small");
   const int F = L / 2 + 1;
   float* amp = reinterpret_cast<float*>(workspace);
-  int rc = spectrum_fft_launch(x, dtype, B, L, C, amp, st);   // mixed-radix FFT (even L); -1 = not applicable
+  int rc;
+  { TimedScope tf(FTN_FAM_FFT, st); rc = spectrum_fft_launch(x, dtype, B, L, C, amp, st); }   // mixed-radix FFT (even L); -1 = n/a
   if (rc > 0) return rc;
   if (rc < 0) {
     size_t smem = (size_t)L * kDftChannels * sizeof(float) + (size_t)L * sizeof(float2);
@@ -581,7 +636,7 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
     FTN_LAUNCH_CHECK("spectrum_dft_kernel");
   }
   const int rows = B * F;
-  rc = channel_median_reg_launch(amp, rows, C, amp_median, st);   // keys in registers (C <= 512)
+  { TimedScope tm(FTN_FAM_MEDIAN, st); rc = channel_median_reg_launch(amp, rows, C, amp_median, st); }   // registers (C <= 512)
   if (rc > 0) return rc;
   if (rc < 0) {
     size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);

@@ -143,13 +143,15 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
   float2* bufA = fsm;
   float2* bufB = fsm + (size_t)N * 32;
   float2* tw = fsm + (size_t)2 * N * 32;
+  float2* tw2 = tw + N;                      // exp(-2 pi i k / L), k = 0 .. N (even/odd split)
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = c0 + lane;
   const T* xb = x + (size_t)b * L * C;
 
-  for (int n = warp; n < N; n += kFftWarps) {
+#pragma unroll 4
+  for (int n = warp; n < N; n += kFftWarps) {   // unrolled: several independent global loads in flight per thread
     float re = 0.f, im = 0.f;
     if (c < C) {
       re = to_f32<T>(xb[(size_t)(2 * n) * C + c]);
@@ -161,6 +163,11 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
     float s, co;
     sincospif(2.0f * (float)k / (float)N, &s, &co);
     tw[k] = make_float2(co, -s);
+  }
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) {   // one sincospif per bin per CTA instead of one per (bin, channel)
+    float s, co;
+    sincospif(2.0f * (float)k / (float)L, &s, &co);
+    tw2[k] = make_float2(co, s);
   }
   __syncthreads();
 
@@ -194,8 +201,7 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
       const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
       const float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);
       const float orr = di, oi = -dr;          // O = -i * D
-      float sn, cs;
-      sincospif(2.0f * (float)k / (float)L, &sn, &cs);
+      const float cs = tw2[k].x, sn = tw2[k].y;
       const float xr = er + (cs * orr + sn * oi);      // W = cs - i sn
       const float xi = ei + (cs * oi - sn * orr);
       amp[((size_t)b * F + k) * C + c] = sqrtf(fmaf(xr, xr, xi * xi));
@@ -295,7 +301,7 @@ static bool fft_factor(int N, FftPlan* plan) {
 int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, cudaStream_t st) {
   if (L & 1) return -1;
   const int N = L / 2;
-  const size_t smem = ((size_t)2 * N * 32 + N) * sizeof(float2);
+  const size_t smem = ((size_t)2 * N * 32 + N + N + 1) * sizeof(float2);
   if (smem > 227 * 1024) return -1;
   FftPlan plan;
   if (!fft_factor(N, &plan)) return -1;

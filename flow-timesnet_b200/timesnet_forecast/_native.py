@@ -161,6 +161,7 @@ def launch_count() -> int:
 
 FAM_SPECTRUM, FAM_CONV, FAM_AGGREGATE = 0, 1, 2
 FAM_S1, FAM_KK_A, FAM_MID, FAM_KK_B, FAM_S6 = 3, 4, 5, 6, 7     # single kernels of the bf16 chain
+FAM_FFT, FAM_MEDIAN, FAM_SELECT = 8, 9, 10                     # single kernels of the period search
 
 
 def timing_enable(on: bool) -> None:

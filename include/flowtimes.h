@@ -121,7 +121,8 @@ FTN_API int ftn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 FTN_API long long ftn_launch_count(void);
 /* Optional CUDA-event timing per kernel family (0 = period search, 1 = Inception conv chain,
  * 2 = aggregate; 3..7 = the single kernels of the bf16 chain: first 1x1, k x k of block A, fused
- * middle, k x k of block B, last 1x1): enable resets the records; read
+ * middle, k x k of block B, last 1x1; 8..10 = FFT, channel median, selection tail): enable resets the
+ * records; read
  * synchronises the recorded events and returns total ms and number of calls. */
 FTN_API int ftn_timing_enable(int on);
 FTN_API int ftn_timing_read(int family, double* total_ms, int* calls);
