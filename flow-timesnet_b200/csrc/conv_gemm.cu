@@ -374,6 +374,10 @@ size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeight
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
                    cudaStream_t st);
+bool tc_block_fused_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b);
+int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
+                    const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st);
 }  // namespace ftn
 
 extern "C" size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a,
@@ -405,4 +409,28 @@ extern "C" int ftn_period_conv(const void* x, int dtype, int B, int L, int C, co
   if (dtype == FTN_F32)
     return period_conv_impl<float>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
   return period_conv_impl<__nv_bfloat16>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
+}
+
+// Whole TimesBlock after the period search: out = [LayerNorm](x + sum_g w[b][g] * delta_g).
+// Returns 0 when the fused tensor-core route ran, -1 (no error text) when the configuration is not
+// eligible and the caller must run ftn_period_conv + ftn_aggregate, > 0 on error.
+extern "C" int ftn_timesblock_fused(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
+                                    const float* weights, const float* ln_weight, const float* ln_bias, float ln_eps,
+                                    void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(x && plan && out && workspace && weights, "ftn_timesblock_fused: null pointer");
+  FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_timesblock_fused: bad sizes B=%d L=%d C=%d", B, L, C);
+  FTN_REQUIRE(max_groups >= 1 && max_groups <= FTN_MAX_K, "ftn_timesblock_fused: max_groups=%d", max_groups);
+  FTN_REQUIRE(act == FTN_ACT_GELU || act == FTN_ACT_RELU, "ftn_timesblock_fused: unknown activation %d", act);
+  FTN_REQUIRE((ln_weight == nullptr) == (ln_bias == nullptr), "ftn_timesblock_fused: ln_weight/ln_bias must come together");
+  if (int rc = check_weights(a, "block A")) return rc;
+  if (int rc = check_weights(b, "block B")) return rc;
+  FTN_REQUIRE(a->cin == C && b->cout == C && a->cout == b->cin,
+              "ftn_timesblock_fused: channel chain %d->%d->%d->%d does not match C=%d", a->cin, a->cout, b->cin, b->cout, C);
+  if (!tc_block_fused_eligible(dtype, C, a, b)) return -1;
+  FTN_REQUIRE(workspace_bytes >= ftn_inception_workspace_bytes(B, L, max_groups, a, b),
+              "ftn_timesblock_fused: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  TimedScope timed(FTN_FAM_CONV, st);
+  return period_block_tc(x, B, L, C, plan, max_groups, a, b, act, weights, ln_weight, ln_bias, ln_eps, out, workspace, st);
 }

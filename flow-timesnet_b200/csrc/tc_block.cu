@@ -54,9 +54,41 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
   return simt_conv_tiled_launch(plan, B, L, max_groups, in, out, ld, w, st);
 }
 
+struct TcTailSpec {          // non-null: finish the block in the fused tail kernel instead of writing deltas
+  const float* weights;
+  const float* ln_w;
+  const float* ln_b;
+  float eps;
+  void* out;
+};
+
+static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                               const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
+                               void* workspace, const TcTailSpec* tail, cudaStream_t st);
+
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
                    cudaStream_t st) {
+  return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, nullptr, st);
+}
+
+// whole TimesBlock after the period search on the bf16 tensor-core path; false = caller must use the unfused pair
+bool tc_block_fused_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  static const bool off = getenv("FLOWTIMES_NO_FUSED_TAIL") != nullptr;   // A/B switch for profiling
+  if (off || !tc_path_eligible(dtype, C, a, b) || !tc_mid_eligible(a, b)) return false;
+  return tc_tail_eligible(b->n_branch * b->mid, C);
+}
+
+int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
+                    const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st) {
+  TcTailSpec tail{weights, ln_w, ln_b, eps, out};
+  return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, nullptr, workspace, &tail, st);
+}
+
+static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                               const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
+                               void* workspace, const TcTailSpec* tail, cudaStream_t st) {
   const int tiles = tc_worst_case_tiles(B, L, max_groups);
   const long long rows = (long long)tiles * 128;
   const int NBa = a->n_branch * a->mid, NBb = b->n_branch * b->mid, F = a->cout;
@@ -106,6 +138,12 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
   }
   // S5
   { TimedScope t4(FTN_FAM_KK_B, st); if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc; }
+  if (tail) {
+    // S6 + aggregation + residual + LayerNorm in one kernel: the deltas never reach HBM
+    TimedScope t5(FTN_FAM_S6, st);
+    return tc_tail_launch(plan, B, L, max_groups, g2, rows, NBb, (const __nv_bfloat16*)b->w_out_bf16, b->b_out, q, C, xb,
+                          tail->weights, tail->ln_w, tail->ln_b, tail->eps, act, (__nv_bfloat16*)tail->out, st);
+  }
   // S6
   s = base;
   s.a1 = g2; s.a1_seq = 0; s.a1_ld = NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_bf16;

@@ -74,6 +74,13 @@ __host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) 
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 
+// fused tail (tc_tail.cu): last 1x1 stage + weighted aggregation + residual + LayerNorm
+bool tc_tail_eligible(int K, int C);
+int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* g2, long long rows, int K,
+                   const __nv_bfloat16* w_out, const float* bias, const __nv_bfloat16* q, int C, const __nv_bfloat16* x,
+                   const float* weights, const float* ln_w, const float* ln_b, float eps, int act, __nv_bfloat16* out,
+                   cudaStream_t st);
+
 // fused middle of the chain (tc_mid.cu): h2, x -> g1 (block B k x k input) and q (block B residual)
 bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b);
 int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,

@@ -1,0 +1,332 @@
+// K3 + K4 (bf16 path), fused tail of a TimesBlock: the last 1x1 stage of the Inception chain together with
+// the softmax-weighted aggregation over period groups, the residual add and the shared LayerNorm.
+//
+//   for every window b and 128-step time tile, for every period group g
+//     delta_g = act(g2_g . V_out^T + b) + q_g - x                  (timesnet.py:645-654, :1063-1069)
+//   out = LayerNorm( x + sum_g w[b, g] * delta_g )                  (timesnet.py:1075-1099, :818, :2059-2061)
+//
+// The unfused pair (tc_gemm2 S6 + aggregate) writes G deltas (L*C*e bytes each per window) and reads
+// them back; here a delta lives in registers for the few instructions between the TMEM load and the
+// weighted accumulation, so the tail's HBM traffic is g2 + q in, x in, out out.  Rounding points are
+// those of the unfused kernels (delta, the weighted product, the sums and the residual are rounded to
+// the activation dtype exactly where aggregate.cu rounds them), so both routes give the same bits.
+//
+// Persistent, one CTA per SM; work item = (window, time tile), inner loop over the G groups:
+//   warp 0 lane 0 : TMA producer   -- g2 tiles of (group, window, tile) into a 2-deep ring, weights once
+//   warp 1        : MMA issuer     -- 6 MMAs per sub-tile, accumulators double-buffered in TMEM
+//   warp 2        : TMEM allocator
+//   warps 4..11   : epilogue       -- two warps per lane quadrant (64 columns each); the two halves of a
+//                   row meet through shared memory for the LayerNorm statistics
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace ftn {
+
+using namespace tc;
+
+constexpr int TL_THREADS = 384;
+constexpr int TL_BM = 128, TL_BK = 64;
+constexpr int TL_A_KB = TL_BM * TL_BK * 2;
+constexpr int TL_STAGES = 2;
+
+struct TcTailArgs {
+  const FtnPeriodPlan* plan;
+  int B, L, K, C, act;
+  const float* bias;              // [C]
+  const __nv_bfloat16* q; int ld_q;     // tile-major residual of block B
+  const __nv_bfloat16* x;         // [B][L][C]
+  const float* weights;           // [B][FTN_MAX_K] group weights (dtype-rounded values in fp32)
+  const float* ln_w;              // [C] or nullptr: plain TimesBlock output
+  const float* ln_b;
+  float eps;
+  __nv_bfloat16* out;             // [B][L][C]
+};
+
+enum { TL_W_FULL = 0, TL_A_FULL = 1, TL_A_EMPTY = 3, TL_ACC_FULL = 5, TL_ACC_EMPTY = 7, TL_BARS = 9 };
+
+// tile-major index of (group g, window b, time tile tt): tiles are enumerated group-major, then window, then tile
+__device__ __forceinline__ int tl_tile_index(const FtnPeriodPlan* pl, int B, int L, int g, int b, int tt) {
+  int base = 0;
+  for (int h = 0; h < g; ++h) base += ((L + pl->grp_pad[h] + TL_BM - 1) / TL_BM) * B;
+  return base + b * ((L + pl->grp_pad[g] + TL_BM - 1) / TL_BM) + tt;
+}
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <int ACT>
+__global__ void __launch_bounds__(TL_THREADS, 1)
+tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcTailArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + TL_BK - 1) / TL_BK;
+  const uint32_t w_kb = (uint32_t)((p.C * 128 + 1023) & ~1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + nkb * w_kb;
+  float* s_bias = reinterpret_cast<float*>(sA + TL_STAGES * nkb * TL_A_KB);
+  float* s_lnw = s_bias + 128;
+  float* s_lnb = s_lnw + 128;
+  float* s_red = s_lnb + 128;                         // [2 halves][128 rows][2] LayerNorm partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(s_red + 512), 16));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TL_BARS);
+
+  if ((int)threadIdx.x < p.C) {
+    s_bias[threadIdx.x] = p.bias[threadIdx.x];
+    s_lnw[threadIdx.x] = p.ln_w ? p.ln_w[threadIdx.x] : 1.f;
+    s_lnb[threadIdx.x] = p.ln_b ? p.ln_b[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    mbar_init(&bars[TL_W_FULL], 1);
+    for (int s = 0; s < TL_STAGES; ++s) {
+      mbar_init(&bars[TL_A_FULL + s], 1);
+      mbar_init(&bars[TL_A_EMPTY + s], 1);
+      mbar_init(&bars[TL_ACC_FULL + s], 1);
+      mbar_init(&bars[TL_ACC_EMPTY + s], 8);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const FtnPeriodPlan* pl = p.plan;
+  const int G = pl->n_groups;
+  const int tiles_x = (p.L + TL_BM - 1) / TL_BM;
+  const int n_items = p.B * tiles_x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_arrive_expect_tx(&bars[TL_W_FULL], (uint32_t)nkb * (uint32_t)p.C * 128u);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sW + kb * w_kb, &tmW, &bars[TL_W_FULL], kb * TL_BK, 0);
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / tiles_x, tt = item - b * tiles_x;
+        for (int g = 0; g < G; ++g, ++n) {
+          const uint32_t s = n & 1;
+          mbar_wait(&bars[TL_A_EMPTY + s], ((n >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
+          const int tile = tl_tile_index(pl, p.B, p.L, g, b, tt);
+          for (int kb = 0; kb < nkb; ++kb)
+            tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, tile * TL_BM);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(TL_BM, p.C);
+    const uint32_t loW = desc_sw128_lo(smem_u32(sW)), loA = desc_sw128_lo(smem_u32(sA));
+    mbar_wait(&bars[TL_W_FULL], 0);
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int g = 0; g < G; ++g, ++n) {
+        const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        mbar_wait(&bars[TL_A_FULL + s], ph);
+        mbar_wait(&bars[TL_ACC_EMPTY + s], ph ^ 1);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int ks = min(TL_BK, p.K - kb * TL_BK) / 16;
+          for (int k = 0; k < ks; ++k) {
+            if (elect_one())
+              mma_bf16_lohi(tmem_base + s * 128, loA + (uint32_t)((s * nkb + kb) * (TL_A_KB >> 4)) + k * 2, kDescSw128Hi,
+                            loW + (uint32_t)kb * (w_kb >> 4) + k * 2, kDescSw128Hi, idesc, acc);
+            acc = 1;
+          }
+        }
+        if (elect_one()) {
+          mma_commit(&bars[TL_A_EMPTY + s]);
+          mma_commit(&bars[TL_ACC_FULL + s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int cpt = p.C / 2;                 // columns per thread (<= 64)
+    const int c_lo = half * cpt;
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / tiles_x, tt = item - b * tiles_x;
+      const int t = tt * TL_BM + r;
+      const bool live = t < p.L;
+      const __nv_bfloat16* xrow = p.x + ((size_t)b * p.L + (live ? t : 0)) * p.C + c_lo;
+      float comb[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) comb[i] = 0.f;
+      for (int g = 0; g < G; ++g, ++n) {
+        const uint32_t s = n & 1;
+        const float wg = p.weights[(size_t)b * FTN_MAX_K + g];
+        const size_t pos_row = (size_t)tl_tile_index(pl, p.B, p.L, g, b, tt) * TL_BM + r;
+        mbar_wait_relaxed(&bars[TL_ACC_FULL + s], (n >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u * 16 < cpt) {
+            const int c = c_lo + u * 16;
+            uint32_t vr[16];
+            tmem_ld16_nowait(lane_base + s * 128 + c, vr);
+            uint4 qv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (live) {
+              const uint4* qs = reinterpret_cast<const uint4*>(p.q + pos_row * p.ld_q + c);
+              qv[0] = qs[0]; qv[1] = qs[1];
+              const uint4* xs = reinterpret_cast<const uint4*>(xrow + u * 16);
+              xv[0] = xs[0]; xv[1] = xs[1];
+            }
+            tmem_ld_wait();
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(qv);
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f32x2 v = add2(pack2u(vr[2 * i], vr[2 * i + 1]), pack2(s_bias[c + 2 * i], s_bias[c + 2 * i + 1]));
+              v = act_fast_x2<ACT>(v);
+              const f32x2 qq = pack2(__uint_as_float(qw[i] << 16), __uint_as_float(qw[i] & 0xffff0000u));
+              const f32x2 xx = pack2(__uint_as_float(xw[i] << 16), __uint_as_float(xw[i] & 0xffff0000u));
+              v = sub2(add2(v, qq), xx);
+              float d0, d1;
+              unpack2(v, d0, d1);
+              // delta rounded to the activation dtype, weighted, rounded again, accumulated in fp32 (aggregate.cu)
+              comb[u * 16 + 2 * i] += bf16_round(bf16_round(d0) * wg);
+              comb[u * 16 + 2 * i + 1] += bf16_round(bf16_round(d1) * wg);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[TL_ACC_EMPTY + s]);
+      }
+      // ---- residual (+ inter-block residual) and LayerNorm over the full row ----
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u * 16 < cpt) {
+          uint4 xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (live) {
+            const uint4* xs = reinterpret_cast<const uint4*>(xrow + u * 16);
+            xv[0] = xs[0]; xv[1] = xs[1];
+          }
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float xf = __uint_as_float((i & 1) ? (xw[i >> 1] & 0xffff0000u) : (xw[i >> 1] << 16));
+            float v = G > 0 ? bf16_round(xf + bf16_round(comb[u * 16 + i])) : xf;
+            if (p.ln_w) {
+              const float d2 = bf16_round(v - xf);     // updated - seq      (:2059)
+              v = bf16_round(xf + d2);                 // seq + delta        (:2060)
+            }
+            comb[u * 16 + i] = v;
+            sum += v;
+          }
+        }
+      }
+      if (p.ln_w) {
+        // the two halves of a row live in two warps: exchange partial sums through shared memory
+        s_red[(half * 128 + r) * 2] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = (s_red[r * 2] + s_red[(128 + r) * 2]) / (float)p.C;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < cpt) { const float d = comb[i] - mean; var += d * d; }
+        s_red[(half * 128 + r) * 2 + 1] = var;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rstd = rsqrtf((s_red[r * 2 + 1] + s_red[(128 + r) * 2 + 1]) / (float)p.C + p.eps);
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < cpt) comb[i] = (comb[i] - mean) * rstd * s_lnw[c_lo + i] + s_lnb[c_lo + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // s_red is reused by the next item
+      }
+      if (live) {
+        __nv_bfloat16* orow = p.out + ((size_t)b * p.L + t) * p.C + c_lo;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u * 16 < cpt) {
+            uint4 o0, o1;
+            o0.x = pack_bf16(comb[u * 16 + 0], comb[u * 16 + 1]);  o0.y = pack_bf16(comb[u * 16 + 2], comb[u * 16 + 3]);
+            o0.z = pack_bf16(comb[u * 16 + 4], comb[u * 16 + 5]);  o0.w = pack_bf16(comb[u * 16 + 6], comb[u * 16 + 7]);
+            o1.x = pack_bf16(comb[u * 16 + 8], comb[u * 16 + 9]);  o1.y = pack_bf16(comb[u * 16 + 10], comb[u * 16 + 11]);
+            o1.z = pack_bf16(comb[u * 16 + 12], comb[u * 16 + 13]); o1.w = pack_bf16(comb[u * 16 + 14], comb[u * 16 + 15]);
+            uint4* dst = reinterpret_cast<uint4*>(orow + u * 16);
+            dst[0] = o0;
+            dst[1] = o1;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tl_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int tl_map_2d(CUtensorMap* m, const void* base, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = tl_encode_fn();
+  FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TL_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tail rows=%lld cols=%d) failed: %d", rows, cols, (int)rc);
+  return 0;
+}
+
+bool tc_tail_eligible(int K, int C) { return K % 16 == 0 && K <= 128 && C % 32 == 0 && C <= 128 && C >= 32; }
+
+int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* g2, long long rows, int K,
+                   const __nv_bfloat16* w_out, const float* bias, const __nv_bfloat16* q, int C, const __nv_bfloat16* x,
+                   const float* weights, const float* ln_w, const float* ln_b, float eps, int act, __nv_bfloat16* out,
+                   cudaStream_t st) {
+  FTN_REQUIRE(tc_tail_eligible(K, C), "tc_tail: unsupported K=%d C=%d", K, C);
+  (void)max_groups;
+  CUtensorMap mA, mW;
+  if (int rc = tl_map_2d(&mA, g2, rows, K, K, TL_BM)) return rc;
+  if (int rc = tl_map_2d(&mW, w_out, C, K, K, C)) return rc;
+  TcTailArgs k{};
+  k.plan = plan; k.B = B; k.L = L; k.K = K; k.C = C; k.act = act; k.bias = bias; k.q = q; k.ld_q = C; k.x = x;
+  k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out;
+  const int nkb = (K + TL_BK - 1) / TL_BK;
+  const size_t smem = 1024 + (size_t)nkb * ((C * 128 + 1023) & ~1023) + (size_t)TL_STAGES * nkb * TL_A_KB +
+                      (3 * 128 + 512) * 4 + 16 + TL_BARS * 8 + 16;
+  static size_t attr[2] = {0, 0};
+  const int ai = act == FTN_ACT_RELU ? 1 : 0;
+  if (smem > attr[ai]) {
+    if (ai) FTN_CUDA(cudaFuncSetAttribute(tc_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else FTN_CUDA(cudaFuncSetAttribute(tc_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[ai] = smem;
+  }
+  const int items = B * ((L + TL_BM - 1) / TL_BM);
+  const int grid = items < sm_count() ? items : sm_count();
+  if (ai) tc_tail_kernel<1><<<grid, TL_THREADS, smem, st>>>(mA, mW, k);
+  else tc_tail_kernel<0><<<grid, TL_THREADS, smem, st>>>(mA, mW, k);
+  FTN_LAUNCH_CHECK("tc_tail_kernel");
+  return 0;
+}
+
+}  // namespace ftn

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -81,6 +81,8 @@ SIGNATURES = {
     "ftn_debug_conv_tiled": (_I, [_P, _P, _I, _P, _I, _I, _I, C.POINTER(FtnInceptionWeights), _I, _P]),
     "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
+    "ftn_timesblock_fused": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
+                                  C.POINTER(FtnInceptionWeights), _I, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ftn_context_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ftn_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -275,6 +277,20 @@ def period_conv(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, wa: Ft
     _check(load().ftn_period_conv(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, plan_dev.data_ptr(), max_groups,
                                   C.byref(wa), C.byref(wb), act, delta.data_ptr(), ws.data_ptr(), ws.numel(),
                                   _stream()), "ftn_period_conv")
+
+
+def timesblock_fused(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, wa: FtnInceptionWeights,
+                     wb: FtnInceptionWeights, act: int, weights: torch.Tensor, ln_w: Optional[torch.Tensor],
+                     ln_b: Optional[torch.Tensor], eps: float, out: torch.Tensor, ws: torch.Tensor) -> bool:
+    """Fused K2+K3+K4.  Returns False when the configuration is not eligible (caller runs the unfused pair)."""
+    B, L, Cc = x.shape
+    rc = load().ftn_timesblock_fused(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, plan_dev.data_ptr(), max_groups,
+                                     C.byref(wa), C.byref(wb), act, weights.data_ptr(), _ptr(ln_w), _ptr(ln_b),
+                                     float(eps), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    if rc == -1:
+        return False
+    _check(rc, "ftn_timesblock_fused")
+    return True
 
 
 def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

@@ -632,6 +632,10 @@ class TimesBlock(nn.Module):
                 max_groups = max(1, min(plan.k, nv.FTN_MAX_K))
                 nbytes = nv.inception_workspace_bytes(B, L, max_groups, pa.struct, pb.struct)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                out = torch.empty_like(x)
+                if nv.timesblock_fused(x, plan.plan_dev, max_groups, pa.struct, pb.struct,
+                                       _act_code(self._activation_name), plan.weights, ln_w, ln_b, eps, out, ws):
+                    return out                                  # chain + aggregation + LayerNorm, no deltas in HBM
                 delta = torch.empty(max_groups, B, L, C, dtype=x.dtype, device=x.device)
                 nv.period_conv(x, plan.plan_dev, max_groups, pa.struct, pb.struct, _act_code(self._activation_name),
                                delta, ws)

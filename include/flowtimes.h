@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 5
+#define FTN_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -191,6 +191,17 @@ FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPer
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
                     int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b,
                     int act, void* delta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2+K3+K4 in one call (bf16 tensor-core route) ------------------------
+ * out = [LayerNorm](x + sum_g w[b][g] * delta_g) with the last 1x1 stage, the weighted aggregation, the
+ * residual and the LayerNorm fused in one kernel, so no delta is written to HBM.
+ * replaces timesnet.py:1034-1099, :818 and (ln_weight != NULL) :2059-2061.
+ * Returns 0 = done, -1 = configuration not eligible for the fused route (caller runs ftn_period_conv +
+ * ftn_aggregate instead; no error text is set), > 0 = error.  Workspace as for ftn_period_conv. */
+FTN_API int ftn_timesblock_fused(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                         const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
+                         const float* ln_weight, const float* ln_bias, float ln_eps, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- K4: weighted aggregation + residual (+ shared LayerNorm) ------------
  * out = x + sum_g w[b][g] * delta_g          replaces timesnet.py:1075-1099, :818
