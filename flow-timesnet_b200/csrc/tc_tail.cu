@@ -12,10 +12,11 @@
 // the activation dtype exactly where aggregate.cu rounds them), so both routes give the same bits.
 //
 // Persistent, one CTA per SM; work item = (window, time tile), inner loop over the G groups:
-//   warp 0 lane 0 : TMA producer   -- g2 tiles of (group, window, tile) into a 2-deep ring, weights once
+//   warp 0 lane 0 : TMA producer   -- g2 and q tiles of (group, window, tile) into 2-deep rings, the item's x tile,
+//                   weights once: the epilogue never issues a global load
 //   warp 1        : MMA issuer     -- 6 MMAs per sub-tile, accumulators double-buffered in TMEM
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue       -- two warps per lane quadrant (64 columns each); the two halves of a
+//   warps 4..19   : epilogue       -- four warps per lane quadrant (32 columns each); the four quarters of a
 //                   row meet through shared memory for the LayerNorm statistics
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
@@ -24,7 +25,8 @@ namespace ftn {
 
 using namespace tc;
 
-constexpr int TL_THREADS = 384;
+constexpr int TL_EPI_WARPS = 16;
+constexpr int TL_THREADS = (4 + TL_EPI_WARPS) * 32;
 constexpr int TL_BM = 128, TL_BK = 64;
 constexpr int TL_A_KB = TL_BM * TL_BK * 2;
 constexpr int TL_STAGES = 2;
@@ -42,7 +44,8 @@ struct TcTailArgs {
   __nv_bfloat16* out;             // [B][L][C]
 };
 
-enum { TL_W_FULL = 0, TL_A_FULL = 1, TL_A_EMPTY = 3, TL_ACC_FULL = 5, TL_ACC_EMPTY = 7, TL_BARS = 9 };
+enum { TL_W_FULL = 0, TL_A_FULL = 1, TL_A_EMPTY = 3, TL_ACC_FULL = 5, TL_ACC_EMPTY = 7, TL_Q_FULL = 9, TL_Q_EMPTY = 11,
+       TL_X_FULL = 13, TL_X_EMPTY = 14, TL_BARS = 15 };
 
 // tile-major index of (group g, window b, time tile tt): tiles are enumerated group-major, then window, then tile
 __device__ __forceinline__ int tl_tile_index(const FtnPeriodPlan* pl, int B, int L, int g, int b, int tt) {
@@ -55,7 +58,8 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 
 template <int ACT>
 __global__ void __launch_bounds__(TL_THREADS, 1)
-tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcTailArgs p) {
+tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const TcTailArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,11 +67,14 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t w_kb = (uint32_t)((p.C * 128 + 1023) & ~1023);
   uint8_t* sW = smem;
   uint8_t* sA = sW + nkb * w_kb;
-  float* s_bias = reinterpret_cast<float*>(sA + TL_STAGES * nkb * TL_A_KB);
+  const int nq = (p.C + TL_BK - 1) / TL_BK;                       // K blocks of a q / x tile (C columns)
+  uint8_t* sQ = sA + TL_STAGES * nkb * TL_A_KB;                   // [stage][nq] 16 KB each: residual tiles via TMA
+  uint8_t* sX = sQ + TL_STAGES * nq * TL_A_KB;                    // [nq] 16 KB: the item's x tile (rows t >= L zero-filled)
+  float* s_bias = reinterpret_cast<float*>(sX + nq * TL_A_KB);
   float* s_lnw = s_bias + 128;
   float* s_lnb = s_lnw + 128;
-  float* s_red = s_lnb + 128;                         // [2 halves][128 rows][2] LayerNorm partials
-  uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(s_red + 512), 16));
+  float* s_red = s_lnb + 128;                         // [4 quarters][128 rows][2] LayerNorm partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(s_red + 1024), 16));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TL_BARS);
 
   if ((int)threadIdx.x < p.C) {
@@ -81,11 +88,17 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&bars[TL_A_FULL + s], 1);
       mbar_init(&bars[TL_A_EMPTY + s], 1);
       mbar_init(&bars[TL_ACC_FULL + s], 1);
-      mbar_init(&bars[TL_ACC_EMPTY + s], 8);
+      mbar_init(&bars[TL_ACC_EMPTY + s], TL_EPI_WARPS);
+      mbar_init(&bars[TL_Q_FULL + s], 1);
+      mbar_init(&bars[TL_Q_EMPTY + s], TL_EPI_WARPS);
     }
+    mbar_init(&bars[TL_X_FULL], 1);
+    mbar_init(&bars[TL_X_EMPTY], TL_EPI_WARPS);
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmX);
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -103,15 +116,23 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_arrive_expect_tx(&bars[TL_W_FULL], (uint32_t)nkb * (uint32_t)p.C * 128u);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sW + kb * w_kb, &tmW, &bars[TL_W_FULL], kb * TL_BK, 0);
       uint32_t n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int b = item / tiles_x, tt = item - b * tiles_x;
+        mbar_wait(&bars[TL_X_EMPTY], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[TL_X_FULL], (uint32_t)nq * TL_A_KB);
+        for (int kb = 0; kb < nq; ++kb) tma_load_3d(sX + kb * TL_A_KB, &tmX, &bars[TL_X_FULL], kb * TL_BK, tt * TL_BM, b);
         for (int g = 0; g < G; ++g, ++n) {
-          const uint32_t s = n & 1;
-          mbar_wait(&bars[TL_A_EMPTY + s], ((n >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
+          const uint32_t s = n & 1, ph = (n >> 1) & 1;
           const int tile = tl_tile_index(pl, p.B, p.L, g, b, tt);
+          mbar_wait(&bars[TL_A_EMPTY + s], ph ^ 1);
+          mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
           for (int kb = 0; kb < nkb; ++kb)
             tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, tile * TL_BM);
+          mbar_wait(&bars[TL_Q_EMPTY + s], ph ^ 1);
+          mbar_arrive_expect_tx(&bars[TL_Q_FULL + s], (uint32_t)nq * TL_A_KB);
+          for (int kb = 0; kb < nq; ++kb)
+            tma_load_2d(sQ + (s * nq + kb) * TL_A_KB, &tmQ, &bars[TL_Q_FULL + s], kb * TL_BK, tile * TL_BM);
         }
       }
     }
@@ -147,39 +168,42 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int quad = warp & 3, half = (warp - 4) >> 2;     // `half` = column quarter 0..3
     const int r = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int cpt = p.C / 2;                 // columns per thread (<= 64)
+    const int cpt = p.C / 4;                 // columns per thread (<= 32)
     const int c_lo = half * cpt;
     uint32_t n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int it = 0;
+    // 16-byte chunk `ch` (8 bf16 columns) of row r inside a 128B-swizzled [rows][64] K block
+    auto sw_chunk = [&](const uint8_t* base, int col) -> const uint4* {
+      const int kb = col >> 6, ch = (col & 63) >> 3;
+      return reinterpret_cast<const uint4*>(base + kb * TL_A_KB + r * 128 + ((ch ^ (r & 7)) << 4));
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / tiles_x, tt = item - b * tiles_x;
       const int t = tt * TL_BM + r;
       const bool live = t < p.L;
-      const __nv_bfloat16* xrow = p.x + ((size_t)b * p.L + (live ? t : 0)) * p.C + c_lo;
-      float comb[64];
+      float comb[32];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) comb[i] = 0.f;
+      for (int i = 0; i < 32; ++i) comb[i] = 0.f;
+      mbar_wait_relaxed(&bars[TL_X_FULL], it & 1);
       for (int g = 0; g < G; ++g, ++n) {
         const uint32_t s = n & 1;
         const float wg = p.weights[(size_t)b * FTN_MAX_K + g];
-        const size_t pos_row = (size_t)tl_tile_index(pl, p.B, p.L, g, b, tt) * TL_BM + r;
         mbar_wait_relaxed(&bars[TL_ACC_FULL + s], (n >> 1) & 1);
+        mbar_wait_relaxed(&bars[TL_Q_FULL + s], (n >> 1) & 1);
         tc_fence_after();
+        const uint8_t* qbase = sQ + s * nq * TL_A_KB;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           if (u * 16 < cpt) {
             const int c = c_lo + u * 16;
             uint32_t vr[16];
             tmem_ld16_nowait(lane_base + s * 128 + c, vr);
-            uint4 qv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (live) {
-              const uint4* qs = reinterpret_cast<const uint4*>(p.q + pos_row * p.ld_q + c);
-              qv[0] = qs[0]; qv[1] = qs[1];
-              const uint4* xs = reinterpret_cast<const uint4*>(xrow + u * 16);
-              xv[0] = xs[0]; xv[1] = xs[1];
-            }
+            uint4 qv[2], xv[2];
+            qv[0] = *sw_chunk(qbase, c); qv[1] = *sw_chunk(qbase, c + 8);
+            xv[0] = *sw_chunk(sX, c);    xv[1] = *sw_chunk(sX, c + 8);
             tmem_ld_wait();
             const uint32_t* qw = reinterpret_cast<const uint32_t*>(qv);
             const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
@@ -200,18 +224,15 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[TL_ACC_EMPTY + s]);
+        if (lane == 0) { mbar_arrive(&bars[TL_ACC_EMPTY + s]); mbar_arrive(&bars[TL_Q_EMPTY + s]); }
       }
       // ---- residual (+ inter-block residual) and LayerNorm over the full row ----
       float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         if (u * 16 < cpt) {
-          uint4 xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (live) {
-            const uint4* xs = reinterpret_cast<const uint4*>(xrow + u * 16);
-            xv[0] = xs[0]; xv[1] = xs[1];
-          }
+          uint4 xv[2];
+          xv[0] = *sw_chunk(sX, c_lo + u * 16); xv[1] = *sw_chunk(sX, c_lo + u * 16 + 8);
           const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -226,27 +247,30 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[TL_X_EMPTY]);       // the x tile may be overwritten by the next item
       if (p.ln_w) {
         // the two halves of a row live in two warps: exchange partial sums through shared memory
         s_red[(half * 128 + r) * 2] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mean = (s_red[r * 2] + s_red[(128 + r) * 2]) / (float)p.C;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float mean = ((s_red[r * 2] + s_red[(128 + r) * 2]) + (s_red[(256 + r) * 2] + s_red[(384 + r) * 2])) / (float)p.C;
         float var = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < 32; ++i)
           if (i < cpt) { const float d = comb[i] - mean; var += d * d; }
         s_red[(half * 128 + r) * 2 + 1] = var;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float rstd = rsqrtf((s_red[r * 2 + 1] + s_red[(128 + r) * 2 + 1]) / (float)p.C + p.eps);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float rstd = rsqrtf(((s_red[r * 2 + 1] + s_red[(128 + r) * 2 + 1]) +
+                                   (s_red[(256 + r) * 2 + 1] + s_red[(384 + r) * 2 + 1])) / (float)p.C + p.eps);
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < 32; ++i)
           if (i < cpt) comb[i] = (comb[i] - mean) * rstd * s_lnw[c_lo + i] + s_lnb[c_lo + i];
-        asm volatile("bar.sync 1, 256;" ::: "memory");    // s_red is reused by the next item
+        asm volatile("bar.sync 1, 512;" ::: "memory");    // s_red is reused by the next item
       }
       if (live) {
         __nv_bfloat16* orow = p.out + ((size_t)b * p.L + t) * p.C + c_lo;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           if (u * 16 < cpt) {
             uint4 o0, o1;
             o0.x = pack_bf16(comb[u * 16 + 0], comb[u * 16 + 1]);  o0.y = pack_bf16(comb[u * 16 + 2], comb[u * 16 + 3]);
@@ -297,7 +321,7 @@ static int tl_map_2d(CUtensorMap* m, const void* base, long long rows, int cols,
   return 0;
 }
 
-bool tc_tail_eligible(int K, int C) { return K % 16 == 0 && K <= 128 && C % 32 == 0 && C <= 128 && C >= 32; }
+bool tc_tail_eligible(int K, int C) { return K % 16 == 0 && K <= 128 && C % 64 == 0 && C <= 128; }   // smem <= 200 KB
 
 int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* g2, long long rows, int K,
                    const __nv_bfloat16* w_out, const float* bias, const __nv_bfloat16* q, int C, const __nv_bfloat16* x,
@@ -308,12 +332,26 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   CUtensorMap mA, mW;
   if (int rc = tl_map_2d(&mA, g2, rows, K, K, TL_BM)) return rc;
   if (int rc = tl_map_2d(&mW, w_out, C, K, K, C)) return rc;
+  CUtensorMap mQ, mX;
+  if (int rc = tl_map_2d(&mQ, q, rows, C, C, TL_BM)) return rc;
+  {
+    EncodeTiledFn fn = tl_encode_fn();
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
+    cuuint32_t box[3] = {TL_BK, TL_BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(&mX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FTN_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tail x B=%d L=%d C=%d) failed: %d", B, L, C, (int)rc);
+  }
   TcTailArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K = K; k.C = C; k.act = act; k.bias = bias; k.q = q; k.ld_q = C; k.x = x;
   k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out;
   const int nkb = (K + TL_BK - 1) / TL_BK;
+  const int nq = (C + TL_BK - 1) / TL_BK;
   const size_t smem = 1024 + (size_t)nkb * ((C * 128 + 1023) & ~1023) + (size_t)TL_STAGES * nkb * TL_A_KB +
-                      (3 * 128 + 512) * 4 + 16 + TL_BARS * 8 + 16;
+                      (size_t)(TL_STAGES + 1) * nq * TL_A_KB + (3 * 128 + 1024) * 4 + 16 + TL_BARS * 8 + 16;
   static size_t attr[2] = {0, 0};
   const int ai = act == FTN_ACT_RELU ? 1 : 0;
   if (smem > attr[ai]) {
@@ -323,8 +361,8 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   }
   const int items = B * ((L + TL_BM - 1) / TL_BM);
   const int grid = items < sm_count() ? items : sm_count();
-  if (ai) tc_tail_kernel<1><<<grid, TL_THREADS, smem, st>>>(mA, mW, k);
-  else tc_tail_kernel<0><<<grid, TL_THREADS, smem, st>>>(mA, mW, k);
+  if (ai) tc_tail_kernel<1><<<grid, TL_THREADS, smem, st>>>(mA, mW, mQ, mX, k);
+  else tc_tail_kernel<0><<<grid, TL_THREADS, smem, st>>>(mA, mW, mQ, mX, k);
   FTN_LAUNCH_CHECK("tc_tail_kernel");
   return 0;
 }
