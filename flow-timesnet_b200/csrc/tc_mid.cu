@@ -263,84 +263,108 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool tr = lane == 0 && warp == 4;
+    // one 128-column chunk: U, R -> a2 (bf16, swizzled) -> a2_full
+    auto do_chunk = [&](uint32_t n, int c) {
+      if (tr) MD_TRACE(30, n);
+      mbar_wait(&bars[MB_ACC_FULL], n & 1);
+      if (tr) MD_TRACE(31, n);
+      tc_fence_after();
+      uint32_t pk[16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t u[16], r[16];
+        const int col = colq * 32 + h * 16;
+        tmem_ld16_nowait(lane_base + col, u);
+        tmem_ld16_nowait(lane_base + 128 + col, r);
+        tmem_ld_wait();
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY]);   // U / R may be overwritten by chunk n+1
+          if (tr) MD_TRACE(32, n);
+        }
+        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + col);
+        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x1 = b1[i], x2 = b2[i];
+          // a2 = act(act(U + b_out) + (R + b_res)) on fp32 pairs
+          const f32x2 lo = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 0], u[4 * i + 1]), pack2(x1.x, x1.y))),
+                                                 add2(pack2u(r[4 * i + 0], r[4 * i + 1]), pack2(x2.x, x2.y))));
+          const f32x2 hi = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 2], u[4 * i + 3]), pack2(x1.z, x1.w))),
+                                                 add2(pack2u(r[4 * i + 2], r[4 * i + 3]), pack2(x2.z, x2.w))));
+          pk[h * 8 + 2 * i] = pack_bf16_x2(lo);
+          pk[h * 8 + 2 * i + 1] = pack_bf16_x2(hi);
+        }
+      }
+      if (tr) MD_TRACE(33, n);
+      mbar_wait(&bars[MB_A2_EMPTY], (n & 1) ^ 1);   // stage-2 MMAs of chunk n-1 finished reading the a2 buffer
+      if (tr) MD_TRACE(34, n);
+      // a2[row][colq*32 .. +32): K block colq>>1, 16-byte chunks (colq&1)*4 .. +4, 128B swizzle
+      uint8_t* dst = sA2 + (colq >> 1) * MD_A_KB_BYTES + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + (((((colq & 1) * 4 + j)) ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[MB_A2_FULL]);
+      if (tr) MD_TRACE(35, n);
+    };
+    // tile drain: g1 = G + b_in2, q = Q + b_res2 (bf16, tile-major rows).  The accumulator columns of this warp
+    // (every 4th group of 16) are loaded with ONE wait and released before the conversion / stores.
+    auto do_drain = [&](int tile, int it) {
+      if (tr) MD_TRACE(36, it);
+      mbar_wait(&bars[MB_GQ_FULL], it & 1);
+      tc_fence_after();
+      const int n16 = N34 / 16;                 // G columns then Q columns, contiguous in TMEM
+      const size_t grow = (size_t)tile * MD_BM + row;
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {       // two rounds of two 16-column groups: one TMEM wait per round
+        uint32_t v[2][16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (colq + 4 * (2 * rnd + k) < n16) tmem_ld16_nowait(lane_base + 256 + (colq + 4 * (2 * rnd + k)) * 16, v[k]);
+        tmem_ld_wait();
+        if (rnd == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[MB_GQ_EMPTY]);    // stage 2 of the next tile may overwrite G | Q
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int un = colq + 4 * (2 * rnd + k);
+          if (un < n16) {
+            const int col = un * 16;                          // column in [G | Q]
+            const bool is_g = col < p.N3;
+            const float* bias = is_g ? sb_in2 + col : sb_res2 + (col - p.N3);
+            __nv_bfloat16* drow = is_g ? p.g1 + grow * p.ld_g1 + col : p.q + grow * p.ld_q + (col - p.N3);
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = pack_bf16(__uint_as_float(v[k][2 * i]) + bias[2 * i], __uint_as_float(v[k][2 * i + 1]) + bias[2 * i + 1]);
+            uint4* d4 = reinterpret_cast<uint4*>(drow);
+            d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      if (tr) MD_TRACE(37, it);
+    };
+    // Chunk stream across tiles; the drain of tile `it` is deferred until the first chunk of tile `it+1` is done, so
+    // the last stage-2 MMAs of a tile (and their barrier hops) hide under useful epilogue work instead of idling 16 warps.
     uint32_t n = 0;
-    int it = 0;
+    int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
       int b, t0;
       if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
       for (int c = 0; c < nch; ++c, ++n) {
-        if (tr) MD_TRACE(30, n);
-        mbar_wait(&bars[MB_ACC_FULL], n & 1);
-        if (tr) MD_TRACE(31, n);
-        tc_fence_after();
-        uint32_t pk[16];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t u[16], r[16];
-          const int col = colq * 32 + h * 16;
-          tmem_ld16_nowait(lane_base + col, u);
-          tmem_ld16_nowait(lane_base + 128 + col, r);
-          tmem_ld_wait();
-          if (h == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY]);   // U / R may be overwritten by chunk n+1
-            if (tr) MD_TRACE(32, n);
-          }
-          const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + col);
-          const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 x1 = b1[i], x2 = b2[i];
-            // a2 = act(act(U + b_out) + (R + b_res)) on fp32 pairs
-            const f32x2 lo = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 0], u[4 * i + 1]), pack2(x1.x, x1.y))),
-                                                   add2(pack2u(r[4 * i + 0], r[4 * i + 1]), pack2(x2.x, x2.y))));
-            const f32x2 hi = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 2], u[4 * i + 3]), pack2(x1.z, x1.w))),
-                                                   add2(pack2u(r[4 * i + 2], r[4 * i + 3]), pack2(x2.z, x2.w))));
-            pk[h * 8 + 2 * i] = pack_bf16_x2(lo);
-            pk[h * 8 + 2 * i + 1] = pack_bf16_x2(hi);
-          }
-        }
-        if (tr) MD_TRACE(33, n);
-        mbar_wait(&bars[MB_A2_EMPTY], (n & 1) ^ 1);   // stage-2 MMAs of chunk n-1 finished reading the a2 buffer
-        if (tr) MD_TRACE(34, n);
-        // a2[row][colq*32 .. +32): K block colq>>1, 16-byte chunks (colq&1)*4 .. +4, 128B swizzle
-        uint8_t* dst = sA2 + (colq >> 1) * MD_A_KB_BYTES + row * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(dst + (((((colq & 1) * 4 + j)) ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[MB_A2_FULL]);
-        if (tr) MD_TRACE(35, n);
+        do_chunk(n, c);
+        if (c == 0 && prev_tile >= 0) do_drain(prev_tile, it - 1);
       }
-      // ---- tile drain: g1 = G + b_in2, q = Q + b_res2 (bf16, tile-major rows) ----
-      mbar_wait(&bars[MB_GQ_FULL], it & 1);
-      tc_fence_after();
-      const size_t grow = (size_t)tile * MD_BM + row;
-      for (int un = colq; un < p.N3 / 16; un += 4) {
-        float v[16];
-        tmem_ld16(lane_base + 256 + un * 16, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += sb_in2[un * 16 + i];
-        uint4* dstg = reinterpret_cast<uint4*>(p.g1 + grow * p.ld_g1 + un * 16);
-        dstg[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        dstg[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-      }
-      for (int un = colq; un < p.N4 / 16; un += 4) {
-        float v[16];
-        tmem_ld16(lane_base + 256 + p.N3 + un * 16, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += sb_res2[un * 16 + i];
-        uint4* dstq = reinterpret_cast<uint4*>(p.q + grow * p.ld_q + un * 16);
-        dstq[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        dstq[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[MB_GQ_EMPTY]);
+      prev_tile = tile;
     }
+    if (prev_tile >= 0) do_drain(prev_tile, it - 1);
   }
   tc_fence_before();
   __syncthreads();
