@@ -380,3 +380,41 @@ def test_graph_replay_and_pipelined_runner_match_eager():
     s1 = runner.submit(xs[2].pin_memory(), ys[2].pin_memory())
     runner.synchronize()
     assert float(runner.results[s0]) == eager[1] and float(runner.results[s1]) == eager[2]
+
+
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_fused_block_route_equals_unfused_route(with_ln):
+    """ftn_timesblock_fused (chain + aggregation + LayerNorm in the tail kernel, no deltas in HBM) returns the
+    same bits as ftn_period_conv + ftn_aggregate: the rounding points are identical by construction."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.models.timesnet import FFTPeriodSelector, TimesBlock
+    wl = syn.WORKLOADS["elec"]
+    B = 3
+    torch.manual_seed(0)
+    blk = TimesBlock(wl.d_model, [list(k) for k in wl.kernel_set], 0.0, "gelu", d_ff=wl.ff,
+                     bottleneck_ratio=wl.bottleneck_ratio).cuda()
+    x = syn.white_features(B, wl.T, wl.d_model, seed=3).to(torch.bfloat16).cuda()
+    sel = FFTPeriodSelector(wl.k_periods, wl.T, 1)
+    plan = sel.search(x)
+    pa, pb = blk.inception[0].packed(x.device), blk.inception[2].packed(x.device)
+    k = plan.k
+    ws = torch.empty(nv.inception_workspace_bytes(B, wl.T, k, pa.struct, pb.struct), dtype=torch.uint8, device="cuda")
+    ln_w = (1.0 + 0.1 * torch.randn(wl.d_model)).cuda() if with_ln else None
+    ln_b = (0.1 * torch.randn(wl.d_model)).cuda() if with_ln else None
+    fused = torch.empty_like(x)
+    assert nv.timesblock_fused(x, plan.plan_dev, k, pa.struct, pb.struct, nv.FTN_ACT_GELU, plan.weights, ln_w, ln_b,
+                               1e-5, fused, ws), "elec shape must be eligible for the fused route"
+    delta = torch.empty(k, B, wl.T, wl.d_model, dtype=x.dtype, device="cuda")
+    nv.period_conv(x, plan.plan_dev, k, pa.struct, pb.struct, nv.FTN_ACT_GELU, delta, ws)
+    unfused = torch.empty_like(x)
+    nv.aggregate(x, delta, plan.weights, plan.plan_dev, ln_w, ln_b, 1e-5, unfused)
+    torch.cuda.synchronize()
+    assert plan.host().n_groups >= 2
+    if not with_ln:
+        assert torch.equal(fused, unfused), (fused.float() - unfused.float()).abs().max()
+    else:
+        # the LayerNorm statistics are summed in a different order (4 column quarters vs a shuffle tree), which can
+        # move a value across a bf16 rounding boundary: allow one bf16 ulp on a vanishing fraction of the elements
+        f, u = fused.float(), unfused.float()
+        assert torch.allclose(f, u, rtol=2 ** -7, atol=1e-6)
+        assert (f != u).float().mean().item() < 1e-3
