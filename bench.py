@@ -36,9 +36,9 @@ import torch  # noqa: E402
 import flowtimes_synth as syn  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels, per launch, from the ncu --set full
-# captures summarised under profiles/ (r1t); algorithmic bytes are in DESIGN.md section 4
-NCU_TRAFFIC = {"elec": {"tc_conv3_kernel": 23.0e6, "tc_mid_kernel": 36.3e6, "unit": "bytes per launch",
-                        "source": "profiles/r1t_ncu_full.csv"}}
+# capture summarised under profiles/ (r1z); algorithmic bytes are in DESIGN.md section 4
+NCU_TRAFFIC = {"elec": {"tc_conv3_kernel": 20.9e6, "tc_mid_kernel": 35.4e6, "tc_tail_kernel": 61.5e6,
+                        "tc_gemm2_kernel": 5.6e6, "unit": "bytes per launch", "source": "profiles/r1z_ncu_full.csv"}}
 
 METRIC = "timesblock_forward_windows_per_sec"
 UNIT = "windows/s"
@@ -335,7 +335,7 @@ def run_native(args):
         conv_avg_ms = conv_ms / max(1, conv_calls)
         achieved = flops_per_call / (conv_avg_ms * 1e-3) / 1e12 if conv_avg_ms > 0 else 0.0
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        roofline = {"bound": "tensor", "kernel": "Inception chain of one TimesBlock (tc_gemm, tc_conv2, tc_mid, tc_conv2, tc_gemm)",
+        roofline = {"bound": "tensor", "kernel": "Inception chain of one TimesBlock (tc_gemm2, tc_conv3, tc_mid, tc_conv3, tc_tail)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": None, "peak_source": peak_src + ", sustained bf16",
                     "flops_per_launch_group": flops_per_call, "avg_ms": conv_avg_ms, "calls": conv_calls,
@@ -343,7 +343,8 @@ def run_native(args):
                             "launches; proj o branch-out folding makes executed FLOPs 2.97x lower (elec), see profiles/",
                     "share_of_step": {"conv": conv_ms / eager_ms_total, "spectrum": spec_ms / eager_ms_total,
                                       "aggregate": agg_ms / eager_ms_total,
-                                      "note": "shares of the eager pass (library CUDA events)"}}
+                                      "note": "shares of the eager pass (library CUDA events); aggregate is 0 when the "
+                                              "fused tail (last 1x1 + aggregation + LayerNorm) runs inside the chain"}}
         # single kernels of the bf16 chain: executed (post weight-folding) FLOPs per call / measured time
         C_, F_, nb_ = wl.d_model, wl.ff, len(wl.kernel_set)
         mid_ = syn._mid(C_, F_, wl.bottleneck_ratio)
@@ -356,9 +357,11 @@ def run_native(args):
         for name, (ms_f, calls) in chain.items():
             if calls:
                 avg = ms_f / calls
-                tf = 2.0 * mac_per_pos[name] * pos_per_call / (avg * 1e-3) / 1e12
-                kernels.append({"kernel": name, "avg_ms": avg, "executed_TFLOPs": tf, "frac_of_peak": tf / peak_tf,
-                                "executed_mac_per_position": mac_per_pos[name]})
+                mac = mac_per_pos[name]
+                tf = 2.0 * mac * pos_per_call / (avg * 1e-3) / 1e12
+                label = "tail (last 1x1 + aggregate + LayerNorm)" if name == "s6_gemm" and not agg_calls else name
+                kernels.append({"kernel": label, "avg_ms": avg, "executed_TFLOPs": tf, "frac_of_peak": tf / peak_tf,
+                                "executed_mac_per_position": mac})
         roofline["chain_kernels"] = kernels
         roofline["executed_flops_per_launch_group"] = 2.0 * sum(mac_per_pos.values()) * pos_per_call
         # dram bytes of one tc_mid / tc_conv3 launch from the committed ncu --set full captures (profiles/)
@@ -366,7 +369,9 @@ def run_native(args):
         e_bytes = 2 if sdt == torch.bfloat16 else 4
         hbm = []
         for name, ms_f, calls, per_call in (
-                ("spectrum", spec_ms, spec_calls, wl.B * wl.T * wl.d_model * e_bytes + 4 * (wl.T // 2 + 1)),
+                ("spectrum_fft" if search["fft"][1] else "period_search (all kernels)",
+                 *(search["fft"] if search["fft"][1] else (spec_ms, spec_calls)),
+                 wl.B * wl.T * wl.d_model * e_bytes + 4 * wl.B * (wl.T // 2 + 1) * wl.d_model),
                 ("aggregate", agg_ms, agg_calls,
                  wl.B * wl.T * wl.d_model * e_bytes * (statistics.mean(len(g) for g in group_periods) + 2))):
             if calls:
