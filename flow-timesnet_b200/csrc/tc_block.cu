@@ -41,6 +41,14 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
   static const bool force_v1 = getenv("FLOWTIMES_CONV_V1") != nullptr;   // A/B switches for profiling
   static const bool force_v2 = getenv("FLOWTIMES_CONV_V2") != nullptr;
+  static const bool force_v3 = getenv("FLOWTIMES_CONV_V3") != nullptr;
+  if (!force_v1 && !force_v2 && !force_v3 && tc_conv4_eligible(w)) {
+    // phases-on-M kernel for every group whose padded image fits shared memory, tc_conv2 for the rest
+    int caps[FTN_MAX_BRANCH];
+    tc_conv4_caps(w, caps);
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st)) return rc;
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st);
+  }
   if (!force_v1 && !force_v2 && tc_conv3_eligible(w)) {
     // full-rate kernel for every period whose padded grid fits its shared-memory layouts, tile-patch kernel for the
     // rest; both read the same device plan and apply the same predicate, so the two launches cover disjoint groups

@@ -286,6 +286,15 @@ using namespace ftn;
 extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                             int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream) {
   FTN_REQUIRE(in && out && plan && w, "ftn_debug_conv_tiled: null pointer");
+  if (use_tc == 4) {
+    int caps[FTN_MAX_BRANCH];
+    FTN_REQUIRE(tc_conv4_eligible(w), "ftn_debug_conv_tiled: tc_conv4 not eligible for this block");
+    tc_conv4_caps(w, caps);
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream)))
+      return rc;
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, caps,
+                                    as_stream(stream));
+  }
   if (use_tc == 3) {
     int caps[FTN_MAX_BRANCH];
     FTN_REQUIRE(tc_conv3_eligible(w), "ftn_debug_conv_tiled: tc_conv3 not eligible for this block");

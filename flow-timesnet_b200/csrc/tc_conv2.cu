@@ -43,7 +43,7 @@ struct TcConv2Args {
   int mid;       // channels per branch (K and N of the MMAs): 16 or 32
   int n_branch;
   int cap_rows;  // rows one image buffer can hold
-  int v3_cap[FTN_MAX_BRANCH];   // > 0: skip the groups tc_conv3 handles (c3_group_fits with this capacity)
+  int v3_cap[FTN_MAX_BRANCH];   // > 0: skip the groups tc_conv3 handles (c3_group_fits with this capacity); < 0: tc_conv4's
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
   int cta_begin[FTN_MAX_BRANCH + 1];       // CTA ranges per branch
   const __nv_bfloat16* w[FTN_MAX_BRANCH];  // [tap][n][k] bf16
@@ -88,7 +88,9 @@ __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L,
       const long long cost_a = (long long)bands_a * (ta * C2_BM + 2 * margin);
       if (cost_a <= cost_b) { mode_b = 0; T = ta; bands = bands_a; }
     }
-    const int n = (v3cap > 0 && c3_group_fits(per, kh, 2 * hw + 1, v3cap)) ? 0 : bands * B;   // tc_conv3 owns this group
+    const bool taken = (v3cap > 0 && c3_group_fits(per, kh, 2 * hw + 1, v3cap)) ||
+                       (v3cap < 0 && c4_group_fits(per, cyc, kh, 2 * hw + 1, -v3cap));
+    const int n = taken ? 0 : bands * B;   // tc_conv3 / tc_conv4 owns this group
     const int rt = (Lp + 127) / 128;
     if (unit < n) {
       u.g = g;

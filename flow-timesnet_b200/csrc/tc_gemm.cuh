@@ -70,7 +70,31 @@ __host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) 
   return cap >= tail + 2 * hh * PW || cap / kh >= tail;
 }
 
-// picks tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
+// "output phases on M" variant (tc_conv4.cu): 4 phases x 32 channels on M, no cross-quadrant reduction in the
+// drain; whole images only, groups whose padded image does not fit go to tc_conv2
+struct C4Geom { int PW, QT, blocks, NB, O4, rows; };
+__host__ __device__ inline C4Geom c4_geometry(int per, int cyc, int kh, int kw) {
+  C4Geom g;
+  const int hw = kw / 2, hh = kh / 2;
+  g.PW = per + 2 * hw;
+  g.QT = cyc * g.PW;
+  const int nc = (g.QT + 3) / 4;                       // accumulator columns: 4 positions each
+  g.blocks = (nc + 255) / 256;
+  g.NB = (((nc + g.blocks - 1) / g.blocks) + 15) & ~15;
+  g.O4 = (hh * g.PW + hw + 3) / 4;                     // plane rows in front of the image origin
+  const int max_beta = 4 * (g.blocks * g.NB - 1) + (kw + 2) + hh * g.PW - hw + 4 * g.O4;
+  g.rows = (max_beta >> 2) + 1;                        // rows per phase plane the MMAs may touch
+  return g;
+}
+__host__ __device__ inline bool c4_group_fits(int per, int cyc, int kh, int kw, int cap) {
+  return c4_geometry(per, cyc, kh, kw).rows <= cap;
+}
+bool tc_conv4_eligible(const FtnInceptionWeights* w);
+void tc_conv4_caps(const FtnInceptionWeights* w, int* caps);   // negated capacities for tc_conv2_launch_filtered
+int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+
+// picks tc_conv4 / tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -56,6 +56,7 @@ class FtnInceptionWeights(C.Structure):
         ("w_in_bf16", C.c_void_p), ("w_out_bf16", C.c_void_p), ("w_res_bf16", C.c_void_p),
         ("w_kk_bf16", C.c_void_p * FTN_MAX_BRANCH),
         ("w_mid_first", C.c_void_p), ("w_mid_second", C.c_void_p),
+        ("w_kk_phase", C.c_void_p * FTN_MAX_BRANCH),
     ]
 
 

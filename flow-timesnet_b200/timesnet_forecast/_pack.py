@@ -89,6 +89,8 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             st.w_kk[j] = dev(wk.permute(2, 3, 1, 0).reshape(kh * kw, mid, mid))
             st.w_kk_bf16[j] = dev16(wk.permute(2, 3, 0, 1).reshape(kh * kw, mid, mid))   # [tap][out][in]
             st.b_kk[j] = dev(p[1].bias.detach().to("cpu", f64))
+            if mid == 32 and kh % 2 == 1 and kw % 2 == 1:
+                st.w_kk_phase[j] = dev16(_phase_stage_images(wk))
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
@@ -148,6 +150,22 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             second = both.reshape(NB + cout, cin // 64, 64).permute(1, 0, 2)           # [cin/64][NB+cout][64]
             st.w_mid_second = dev16(second)                                            # == [cin/128][2][NB+cout][64]
     return PackedInception(st, keep, macs)
+
+
+def _phase_stage_images(wk: torch.Tensor) -> torch.Tensor:
+    """Stage images of the phases-on-M k x k kernel (tc_conv4.cu; layout in include/flowtimes.h).
+
+    wk: [32 out, 32 in, kh, kw].  Per tap row: four 8-input-channel planes of (kw + 3) * 32 rows, each
+    starting with 3 zero blocks of 32 rows, plus 3 closing zero blocks -- any 128-row window of a plane
+    is the Toeplitz operand of one (tap row, position shift) pair.
+    """
+    n_out, n_in, kh, kw = (int(v) for v in wk.shape)
+    plane = (kw + 3) * 32
+    img = torch.zeros(kh, (n_in // 8) * plane + 96, 8, dtype=wk.dtype)
+    blk = wk.permute(2, 1, 3, 0).reshape(kh, n_in // 8, 8, kw, n_out).permute(0, 1, 3, 4, 2)   # [kh][c][dx][n][8]
+    for c in range(n_in // 8):
+        img[:, c * plane + 96:c * plane + 96 + kw * 32] = blk[:, c].reshape(kh, kw * n_out, 8)
+    return img
 
 
 def params_fingerprint(module: nn.Module) -> Tuple:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 6
+#define FTN_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -109,6 +109,11 @@ typedef struct FtnInceptionWeights {
    * NULL = the fused middle kernel is not used with this block. */
   const void* w_mid_first;
   const void* w_mid_second;
+  /* Stage images of the "output phases on M" k x k kernel (tc_conv4.cu, mid = 32): per branch kh
+   * tap rows of 128 (kw + 3) + 96 sixteen-byte rows.  Row c * (kw + 3) * 32 + 96 + dx * 32 + n of tap
+   * row dr holds w_kk[dr][dx][n][c * 8 .. c * 8 + 8) (output channel n, 8 input channels, bf16); all
+   * other rows are zero.  NULL = that kernel is not used for this block. */
+  const void* w_kk_phase[FTN_MAX_BRANCH];
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */
@@ -184,7 +189,8 @@ FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const
 FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
                                 void* out, void* stream);
 /* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
- * use_tc = 3 positions-on-N tcgen05 kernel (+ tc_conv2 for long periods), 2 image-resident tcgen05 kernel,
+ * use_tc = 4 phases-on-M tcgen05 kernel, 3 positions-on-N tcgen05 kernel (both + tc_conv2 for long periods),
+ * 2 image-resident tcgen05 kernel,
  * 1 tile-patch tcgen05 kernel, 0 SIMT kernel. */
 FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                  int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
