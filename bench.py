@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of CUDA-graph replay")
+    ap.add_argument("--activation", default="gelu", choices=["gelu", "relu"],
+                    help="diagnostic only: relu removes the GELU cost from the epilogues (the metric is quoted on gelu)")
     return ap.parse_args()
 
 
@@ -177,7 +179,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.name, **wl.as_dict(), "scope": "TimesNet.forward + NB-NLL on host cores",
+        "config": {"workload": wl.name, **wl.as_dict(), **({"activation": args.activation} if args.activation != "gelu" else {}), "scope": "TimesNet.forward + NB-NLL on host cores",
                    "sample_windows_per_step": sample_B},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample_B} of {wl.B} windows per step, full forward + NLL, fp32, {cores} threads"},
@@ -208,7 +210,7 @@ def run_native(args):
     sdt = syn.torch_dtype(wl.dtype)
 
     model = TimesNet(input_len=wl.T, pred_len=wl.H, d_model=wl.d_model, n_layers=wl.n_layers, k_periods=wl.k_periods,
-                     kernel_set=[list(k) for k in wl.kernel_set], dropout=0.0, activation="gelu", mode=wl.mode,
+                     kernel_set=[list(k) for k in wl.kernel_set], dropout=0.0, activation=args.activation, mode=wl.mode,
                      d_ff=wl.ff, bottleneck_ratio=wl.bottleneck_ratio, min_period_threshold=wl.min_period_threshold,
                      use_checkpoint=False, stack_dtype=sdt)
     x_host = syn.planted_series(wl.B, wl.T, wl.N, seed=rank).pin_memory()

@@ -37,17 +37,46 @@ int tc_stage_launch(const TcGemmArgs& a, cudaStream_t st) {
   return tc_gemm_launch(a, st);
 }
 
+static bool kk_force(int v) {   // A/B switches for profiling
+  static const bool f1 = getenv("FLOWTIMES_CONV_V1") != nullptr, f2 = getenv("FLOWTIMES_CONV_V2") != nullptr,
+                    f3 = getenv("FLOWTIMES_CONV_V3") != nullptr;
+  return v == 1 ? f1 : (v == 2 ? f2 : f3);
+}
+
+bool tc_kk_uses_conv4(const FtnInceptionWeights* w) {
+  return !kk_force(1) && !kk_force(2) && !kk_force(3) && tc_conv4_eligible(w);
+}
+
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
-  static const bool force_v1 = getenv("FLOWTIMES_CONV_V1") != nullptr;   // A/B switches for profiling
-  static const bool force_v2 = getenv("FLOWTIMES_CONV_V2") != nullptr;
-  static const bool force_v3 = getenv("FLOWTIMES_CONV_V3") != nullptr;
-  if (!force_v1 && !force_v2 && !force_v3 && tc_conv4_eligible(w)) {
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row) {
+  const bool force_v1 = kk_force(1), force_v2 = kk_force(2);
+  FTN_REQUIRE(shared_bias_row < 0 || tc_kk_uses_conv4(w), "tc_kk_stage: the shared input layout needs the tc_conv4 route");
+  if (tc_kk_uses_conv4(w)) {
     // phases-on-M kernel for every group whose padded image fits shared memory, tc_conv2 for the rest
+    // The two launches cover disjoint groups and only read `in`, so the (normally empty, ~5 us) tc_conv2 launch
+    // runs on a side stream forked from and joined back into `st`: in a captured graph the two kernels become
+    // parallel nodes, and the fallback's launch latency hides under tc_conv4.
     int caps[FTN_MAX_BRANCH];
     tc_conv4_caps(w, caps);
-    if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st)) return rc;
-    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st);
+    static const bool serial = getenv("FLOWTIMES_NO_SIDE_STREAM") != nullptr;
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!serial && !side) {
+      FTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    if (serial) {
+      if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
+      return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row);
+    }
+    FTN_CUDA(cudaEventRecord(ev_fork, st));
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
+    FTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    if (int rc = tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, side, shared_bias_row)) return rc;
+    FTN_CUDA(cudaEventRecord(ev_join, side));
+    FTN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    return 0;
   }
   if (!force_v1 && !force_v2 && tc_conv3_eligible(w)) {
     // full-rate kernel for every period whose padded grid fits its shared-memory layouts, tile-patch kernel for the
@@ -112,13 +141,26 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
   TcGemmArgs base{};
   base.plan = plan; base.B = B; base.L = L; base.max_groups = max_groups; base.n_tiles = tiles; base.act = act;
 
-  // S1
+  // S1.  The first 1x1 stage does not depend on the period: on the tc_conv4 route it runs ONCE over x[B*L][C] (plus
+  // one tile of out-of-bounds = zero rows, whose output is the row every padded step t >= L stands for) instead of
+  // once per group over the tile-major grid; the k x k loaders then index h1 by (window, t).
   TcGemmArgs s = base;
-  s.a1 = xb; s.a1_seq = 1; s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in; s.K1 = C;
+  s.a1 = xb; s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in; s.K1 = C;
   s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
+  long long shared_bias_row = -1;
+  const long long seq_tiles = ((long long)B * L + 127) / 128 + 1;
+  if (tc_kk_uses_conv4(a) && seq_tiles <= tiles) {
+    s.plan = nullptr; s.a1_seq = 0; s.a1_rows = (long long)B * L; s.n_tiles = (int)seq_tiles;
+    shared_bias_row = seq_tiles * 128 - 1;
+  } else {
+    s.a1_seq = 1;
+  }
   { TimedScope t1(FTN_FAM_S1, st); if (int rc = tc_stage_launch(s, st)) return rc; }
   // S2
-  { TimedScope t2(FTN_FAM_KK_A, st); if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st)) return rc; }
+  {
+    TimedScope t2(FTN_FAM_KK_A, st);
+    if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st, shared_bias_row)) return rc;
+  }
   static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
   const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
   __nv_bfloat16* q = a2;   // the fused middle never materialises a2: its slot holds q = a2 . V_res + b (C columns)

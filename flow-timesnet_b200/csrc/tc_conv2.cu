@@ -40,6 +40,7 @@ struct TcConv2Args {
   const __nv_bfloat16* in;
   __nv_bfloat16* out;
   int ld;        // row pitch of in / out (elements)
+  long long shared_bias_row;   // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L (tc_gemm.cuh)
   int mid;       // channels per branch (K and N of the MMAs): 16 or 32
   int n_branch;
   int cap_rows;  // rows one image buffer can hold
@@ -230,7 +231,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
       const uint32_t par = (uint32_t)(i >> 1) & 1u;
       mbar_wait_relaxed(&bars[C2_IMG_EMPTY + buf], par ^ 1u);
       const uint32_t dst0 = smem_u32(buf ? s_buf1 : s_buf0) + c * LBO_A;
-      const __nv_bfloat16* img = p.in + u.img_row0 * p.ld + j * mid + c * 8;
+      const bool shared = p.shared_bias_row >= 0;
+      const __nv_bfloat16* img = p.in + (shared ? (size_t)u.b * p.L : u.img_row0) * p.ld + j * mid + c * 8;
+      const __nv_bfloat16* pad_row = p.in + (size_t)(shared ? p.shared_bias_row : 0) * p.ld + j * mid + c * 8;
+      const int t_lim = shared ? p.L : 0x7fffffff;
       const int nseg = u.mode_b ? kh : 1;
       const int rows = u.mode_b ? u.seg_rows : u.tiles * C2_BM + 2 * u.margin;
       const int step_r = r_step / u.PW, step_w = r_step - step_r * u.PW;
@@ -243,7 +247,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
         uint32_t dst = dst0 + (uint32_t)(sg * rows + r_first) * 16;
         for (int r = r_first; r < rows; r += r_step) {
           const bool ok = rr >= 0 && rr < u.cyc && wq >= hw && wq < hw + u.per;
-          const __nv_bfloat16* src = ok ? img + (size_t)(rr * u.per + wq - hw) * p.ld : img;
+          const int tt = rr * u.per + wq - hw;
+          const __nv_bfloat16* src = ok ? (tt < t_lim ? img + (size_t)tt * p.ld : pad_row) : img;
           cp_async16(dst, src, ok ? 16u : 0u);
           dst += r_step * 16;
           rr += step_r;
@@ -344,12 +349,14 @@ int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
 }
 
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st) {
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
+                             long long shared_bias_row) {
   FTN_REQUIRE(tc_conv2_eligible(w), "tc_conv2: unsupported branch shape (mid=%d)", w->mid);
   (void)max_groups;
   TcConv2Args a{};
   for (int j = 0; j < w->n_branch; ++j) a.v3_cap[j] = v3_caps ? v3_caps[j] : 0;
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.mid = w->mid; a.n_branch = w->n_branch;
+  a.shared_bias_row = shared_bias_row;
   a.cap_rows = conv2_cap_rows(w);
   int cost_total = 0;
   for (int j = 0; j < w->n_branch; ++j) {

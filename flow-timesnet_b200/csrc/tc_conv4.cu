@@ -56,6 +56,7 @@ struct TcConv4Args {
   const __nv_bfloat16* in;
   __nv_bfloat16* out;
   int ld;
+  long long shared_bias_row;      // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L
   int n_branch;
   int cap_rows[FTN_MAX_BRANCH];   // rows one phase plane of an image buffer can hold
   int wstages[FTN_MAX_BRANCH];    // weight stages in shared memory; >= kh: resident, loaded once
@@ -74,7 +75,7 @@ struct TcConv4Args {
   } while (0)
 
 struct C4Unit {
-  int per, cyc, PW, NB, blocks, O4, rows;
+  int per, cyc, PW, NB, blocks, O4, rows, b;
   size_t img_row0;
 };
 
@@ -90,6 +91,7 @@ __device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int unit, C
     if (unit < q.n_units) {
       u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
       u.img_row0 = (size_t)(q.tile0 + unit * q.rt) * 128;
+      u.b = unit;
       return true;
     }
     unit -= q.n_units;
@@ -280,7 +282,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
       mbar_wait_relaxed(&bars[C4_IMG_EMPTY + buf], (((uint32_t)i / NBUF) & 1u) ^ 1u);
       if (lt == 0) C4_TRACE(5, i);
       uint32_t dst = smem_u32(s_buf0 + buf * BUF_BYTES) + c * LBO_B + (uint32_t)(r_first & 3) * PH + (uint32_t)(r_first >> 2) * 16;
-      const __nv_bfloat16* img = p.in + u.img_row0 * p.ld + j * C4_MID + c * 8;
+      const bool shared = p.shared_bias_row >= 0;
+      const __nv_bfloat16* img = p.in + (shared ? (size_t)u.b * p.L : u.img_row0) * p.ld + j * C4_MID + c * 8;
+      const __nv_bfloat16* pad_row = p.in + (size_t)(shared ? p.shared_bias_row : 0) * p.ld + j * C4_MID + c * 8;
+      const int t_lim = shared ? p.L : 0x7fffffff;
       const int K = hh + 4;                           // shift that keeps the dividend non-negative
       const int qs = r_first - 4 * u.O4 + K * u.PW;
       int rr = qs / u.PW;
@@ -292,7 +297,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
       // LSU walking ~12 partially used lines per warp instruction -- 64 B of every 192 B row -- not by latency)
       for (int beta = r_first; beta < n_beta; beta += C4_LSTEP) {
         const bool ok = rr >= 0 && rr < u.cyc && wq >= hw && wq < hw + u.per;
-        const __nv_bfloat16* src = ok ? img + (size_t)(rr * u.per + wq - hw) * p.ld : img;
+        const int tt = rr * u.per + wq - hw;
+        const __nv_bfloat16* src = ok ? (tt < t_lim ? img + (size_t)tt * p.ld : pad_row) : img;
         cp_async16(dst, src, ok ? 16u : 0u);
         dst += C4_LSTEP * 4;
         rr += step_r;
@@ -408,10 +414,11 @@ void tc_conv4_caps(const FtnInceptionWeights* w, int* caps) {
 }
 
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st) {
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row) {
   FTN_REQUIRE(tc_conv4_eligible(w), "tc_conv4: unsupported branch shape (mid=%d)", w->mid);
   TcConv4Args a{};
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.n_branch = w->n_branch;
+  a.shared_bias_row = shared_bias_row;
   // cycles per image: MMAs at ~94 cycles (N ~ 170 columns, barrier hops included) plus the fixed cost of the unit
   // hand-over; a branch with few MMAs is bound by its image loader instead (measured, FLOWTIMES_CONV_TRACE)
   long long cost[FTN_MAX_BRANCH];

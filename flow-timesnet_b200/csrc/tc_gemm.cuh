@@ -62,7 +62,8 @@ void tc_conv3_caps(const FtnInceptionWeights* w, int* caps);
 int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st);
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
+                             long long shared_bias_row = -1);
 // does tc_conv3 take a group of period `per` for a kh x kw branch whose image buffer holds `cap` rows?
 __host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) {
   const int hw = kw / 2, hh = kh / 2, PW = per + 2 * hw;
@@ -92,11 +93,15 @@ __host__ __device__ inline bool c4_group_fits(int per, int cyc, int kh, int kw, 
 bool tc_conv4_eligible(const FtnInceptionWeights* w);
 void tc_conv4_caps(const FtnInceptionWeights* w, int* caps);   // negated capacities for tc_conv2_launch_filtered
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1);
 
 // picks tc_conv4 / tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
+// shared_bias_row >= 0: `in` is NOT tile-major but one copy per window, row b * L + t for t < L, and row
+// `shared_bias_row` stands for every padded step t >= L (the first 1x1 stage does not depend on the period, so
+// block A's k x k input is computed once instead of once per group); only the tc_conv4 route takes it
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1);
+bool tc_kk_uses_conv4(const FtnInceptionWeights* w);
 
 // fused tail (tc_tail.cu): last 1x1 stage + weighted aggregation + residual + LayerNorm
 bool tc_tail_eligible(int K, int C);

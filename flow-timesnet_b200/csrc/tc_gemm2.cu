@@ -26,7 +26,8 @@ constexpr int G2_A_KB = G2_BM * G2_BK * 2;   // 16 KB per K block of an activati
 constexpr int G2_STAGES = 2;
 
 struct TcGemm2Args {
-  const FtnPeriodPlan* plan;
+  const FtnPeriodPlan* plan;   // nullptr: plain GEMM over n_plain row tiles (a_seq = 0, PLAIN epilogue)
+  int n_plain;
   int B, L;
   int a_seq;            // 1: A is x[B][L][K] through the 3-D map, 0: tile-major [tiles*128][K]
   int K, N, act, epi;   // epi: TC_EPI_PLAIN | TC_EPI_DELTA
@@ -38,7 +39,12 @@ struct TcGemm2Args {
 
 enum { G2_W_FULL = 0, G2_A_FULL = 1, G2_A_EMPTY = 3, G2_ACC_FULL = 5, G2_ACC_EMPTY = 7, G2_BARS = 9 };
 
-__device__ __forceinline__ bool g2_decode(const FtnPeriodPlan* pl, int B, int L, int tile, int& g, int& b, int& t0, int& Lp) {
+__device__ __forceinline__ bool g2_decode(const FtnPeriodPlan* pl, int n_plain, int B, int L, int tile, int& g, int& b, int& t0,
+                                          int& Lp) {
+  if (!pl) {   // plain GEMM over n_plain row tiles of a 2-D operand (PLAIN epilogue only)
+    g = 0; b = 0; t0 = 0; Lp = 0;
+    return tile < n_plain;
+  }
   const int G = pl->n_groups;
   for (g = 0; g < G; ++g) {
     Lp = L + pl->grp_pad[g];
@@ -96,7 +102,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int it = 0;
       for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
         int g, b, t0, Lp;
-        if (!g2_decode(pl, p.B, p.L, tile, g, b, t0, Lp)) break;
+        if (!g2_decode(pl, p.n_plain, p.B, p.L, tile, g, b, t0, Lp)) break;
         const int s = it & 1;
         mbar_wait(&bars[G2_A_EMPTY + s], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[G2_A_FULL + s], (uint32_t)nkb * G2_A_KB);
@@ -116,7 +122,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int it = 0;
     for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
       int g, b, t0, Lp;
-      if (!g2_decode(pl, p.B, p.L, tile, g, b, t0, Lp)) break;
+      if (!g2_decode(pl, p.n_plain, p.B, p.L, tile, g, b, t0, Lp)) break;
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&bars[G2_A_FULL + s], ph);
@@ -147,7 +153,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int it = 0;
     for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
       int g, b, t0, Lp;
-      if (!g2_decode(pl, p.B, p.L, tile, g, b, t0, Lp)) break;
+      if (!g2_decode(pl, p.n_plain, p.B, p.L, tile, g, b, t0, Lp)) break;
       const int s = it & 1;
       mbar_wait_relaxed(&bars[G2_ACC_FULL + s], (it >> 1) & 1);
       tc_fence_after();
@@ -233,7 +239,8 @@ static int g2_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 }
 
 bool tc_gemm2_eligible(const TcGemmArgs& a) {
-  if (!a.plan || a.K2 > 0) return false;
+  if (a.K2 > 0) return false;
+  if (!a.plan && (a.a1_seq || a.epi != TC_EPI_PLAIN)) return false;
   if (a.K1 % 16 || a.K1 > 128 || a.N % 16 || a.N > 128 || a.N < 16) return false;
   if (a.epi == TC_EPI_PLAIN) return a.res == TC_RES_NONE;
   if (a.epi == TC_EPI_DELTA) return a.res == TC_RES_POS && a.C == a.N && a.res_ld % 8 == 0;
@@ -261,7 +268,7 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
     if (int rc = g2_map(&mW, a.w1, 2, dims, strides, box)) return rc;
   }
   TcGemm2Args k{};
-  k.plan = a.plan; k.B = a.B; k.L = a.L; k.a_seq = a.a1_seq; k.K = a.K1; k.N = a.N; k.act = a.act; k.epi = a.epi;
+  k.plan = a.plan; k.n_plain = a.n_tiles; k.B = a.B; k.L = a.L; k.a_seq = a.a1_seq; k.K = a.K1; k.N = a.N; k.act = a.act; k.epi = a.epi;
   k.bias = a.bias1; k.q = a.res_ptr; k.ld_q = a.res_ld; k.x = a.x; k.C = a.C; k.out = a.out; k.ldo = a.ldo;
   const int nkb = (a.K1 + G2_BK - 1) / G2_BK;
   const size_t smem = 1024 + (size_t)nkb * ((a.N * 128 + 1023) & ~1023) + (size_t)G2_STAGES * nkb * G2_A_KB + 128 * 4 + 16 +
@@ -273,7 +280,7 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
     else FTN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[ai] = smem;
   }
-  const int worst = tc_worst_case_tiles(a.B, a.L, a.max_groups);
+  const int worst = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   const int grid = worst < sm_count() ? worst : sm_count();
   if (ai) tc_gemm2_kernel<1><<<grid, G2_THREADS, smem, st>>>(mA, mW, k);
   else tc_gemm2_kernel<0><<<grid, G2_THREADS, smem, st>>>(mA, mW, k);

@@ -244,6 +244,23 @@ def test_full_size_elec_windows_match_oracle():
     assert _rel(out[-1:], tr.out) < REL_BF16
 
 
+def test_elec_block_with_long_periods_matches_oracle():
+    """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
+    inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""
+    wl = syn.WORKLOADS["elec"]
+    w = syn.stack_weights(wl, seed=0)
+    B = 5
+    x = syn.white_features(B, wl.T, wl.d_model, seed=5).to(torch.bfloat16)
+    periods = [24, 100, 7, 168, 6]
+    g = torch.Generator().manual_seed(4)
+    amps = torch.randn(B, 5, generator=g)
+    blk = _make_block(wl, w)
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    tr = orc.timesblock_from_periods(x, periods, amps.to(torch.bfloat16), w, "blocks.0.inception.")
+    assert _rel(out, tr.out) < REL_BF16
+
+
 def test_block_identity_and_errors():
     from timesnet_forecast.models.timesnet import TimesBlock
     blk = TimesBlock(d_model=2, kernel_set=[(3, 3)], dropout=0.0, activation="gelu").cuda()
