@@ -189,14 +189,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.epi == TC_EPI_DELTA) {
           if (delta_row) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)g * p.B + b) * p.L + t) * p.C + c);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            st_global_256(p.out + (((size_t)g * p.B + b) * p.L + t) * p.C + c, o);
           }
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + pos_row * p.ldo + c);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          st_global_256(p.out + pos_row * p.ldo + c, o);
         }
       }
       tc_fence_before();

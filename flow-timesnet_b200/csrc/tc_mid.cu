@@ -63,7 +63,9 @@ struct TcMidKernelArgs {
 
 enum {
   MB_A_FULL = 0, MB_A_EMPTY, MB_R1_FULL, MB_R1_EMPTY, MB_R2_FULL, MB_R2_EMPTY,
-  MB_ACC_FULL, MB_ACC_EMPTY, MB_A2_FULL, MB_A2_EMPTY, MB_GQ_FULL, MB_GQ_EMPTY, MB_COUNT
+  MB_ACC_FULL, MB_ACC_EMPTY /* U */, MB_A2_FULL, MB_A2_EMPTY, MB_GQ_FULL, MB_GQ_EMPTY, MB_R_EMPTY,
+  MB_R1B_FULL, MB_R1B_EMPTY,   // stage-1 weights of the R (res_proj) half; MB_R1_* is the U (branch-out) half
+  MB_COUNT
 };
 
 #define MD_TRACE(ev, n)                                                                        \
@@ -121,7 +123,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < MB_COUNT; ++i) {
-      const bool epi_arrives = i == MB_ACC_EMPTY || i == MB_A2_FULL || i == MB_GQ_EMPTY;
+      const bool epi_arrives = i == MB_ACC_EMPTY || i == MB_R_EMPTY || i == MB_A2_FULL || i == MB_GQ_EMPTY;
       mbar_init(&bars[i], epi_arrives ? (uint32_t)MD_EPI_WARPS : 1u);   // epilogue warps arrive, everything else one thread
     }
     fence_barrier_init();
@@ -158,12 +160,20 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         for (int kb = 0; kb < kb2; ++kb)
           tma_load_3d(sX + kb * MD_A_KB_BYTES, &tmX, &bars[MB_A_FULL], kb * MD_BK, t0, b);
         for (int c = 0; c < nch; ++c, ++n) {
+          // the stage image of chunk c is (kb1+kb2) x 128 rows of 128 B, streamed as 256-row boxes.  Its U and R
+          // halves have their own barriers: the buffer is single (64 KB do not fit twice), so each half is refilled
+          // as soon as ITS MMAs of the previous chunk are done and the U weights of chunk n+1 land while the R MMAs of
+          // chunk n still run (FLOWTIMES_MID_TRACE: one barrier pair made the ~2 k cycle refill + the ~1.5 k cycle
+          // MMA stream a serial loop that set the chunk cadence)
           mbar_wait(&bars[MB_R1_EMPTY], (n & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[MB_R1_FULL], r1_bytes);
-          // the stage image of chunk c is (kb1+kb2) x 128 rows of 128 B, streamed as 256-row boxes
-          for (int kb = 0; kb < kb1 + kb2; kb += 2)
+          mbar_arrive_expect_tx(&bars[MB_R1_FULL], (uint32_t)kb1 * MD_W_KB_BYTES);
+          for (int kb = 0; kb < kb1; kb += 2)
             tma_load_2d(sR1 + kb * MD_W_KB_BYTES, &tmW1, &bars[MB_R1_FULL], 0, (c * (kb1 + kb2) + kb) * MD_NC);
           MD_TRACE(1, n);
+          mbar_wait(&bars[MB_R1B_EMPTY], (n & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[MB_R1B_FULL], (uint32_t)kb2 * MD_W_KB_BYTES);
+          for (int kb = kb1; kb < kb1 + kb2; kb += 2)
+            tma_load_2d(sR1 + kb * MD_W_KB_BYTES, &tmW1, &bars[MB_R1B_FULL], 0, (c * (kb1 + kb2) + kb) * MD_NC);
         }
       }
     }
@@ -207,6 +217,13 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
           acc = 1;
         }
       }
+      // U and R are released separately: the epilogue hands U back as soon as its 32 U values are in registers and R
+      // one half-chunk of math later, so the U MMAs of chunk n+1 no longer wait for that math
+      if (elect_one()) mma_commit(&bars[MB_R1_EMPTY]);    // U weights may be refilled
+      __syncwarp();
+      mbar_wait(&bars[MB_R1B_FULL], n & 1);
+      mbar_wait(&bars[MB_R_EMPTY], (n & 1) ^ 1);
+      tc_fence_after();
       acc = 0;
       for (int kb = 0; kb < kb2; ++kb) {
         const int ks = min(MD_BK, p.K2 - kb * MD_BK) / 16;
@@ -218,7 +235,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
         }
       }
       if (elect_one()) {
-        mma_commit(&bars[MB_R1_EMPTY]);
+        mma_commit(&bars[MB_R1B_EMPTY]);
         mma_commit(&bars[MB_ACC_FULL]);
         if (c == (uint32_t)nch - 1) mma_commit(&bars[MB_A_EMPTY]);   // activation tile may be overwritten
       }
@@ -269,43 +286,54 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
       mbar_wait(&bars[MB_ACC_FULL], n & 1);
       if (tr) MD_TRACE(31, n);
       tc_fence_after();
-      uint32_t pk[16];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t u[16], r[16];
-        const int col = colq * 32 + h * 16;
-        tmem_ld16_nowait(lane_base + col, u);
-        tmem_ld16_nowait(lane_base + 128 + col, r);
-        tmem_ld_wait();
-        if (h == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY]);   // U / R may be overwritten by chunk n+1
-          if (tr) MD_TRACE(32, n);
-        }
-        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + col);
-        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x1 = b1[i], x2 = b2[i];
-          // a2 = act(act(U + b_out) + (R + b_res)) on fp32 pairs
-          const f32x2 lo = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 0], u[4 * i + 1]), pack2(x1.x, x1.y))),
-                                                 add2(pack2u(r[4 * i + 0], r[4 * i + 1]), pack2(x2.x, x2.y))));
-          const f32x2 hi = act_fast_x2<ACT>(add2(act_fast_x2<ACT>(add2(pack2u(u[4 * i + 2], u[4 * i + 3]), pack2(x1.z, x1.w))),
-                                                 add2(pack2u(r[4 * i + 2], r[4 * i + 3]), pack2(x2.z, x2.w))));
-          pk[h * 8 + 2 * i] = pack_bf16_x2(lo);
-          pk[h * 8 + 2 * i + 1] = pack_bf16_x2(hi);
-        }
-      }
-      if (tr) MD_TRACE(33, n);
-      mbar_wait(&bars[MB_A2_EMPTY], (n & 1) ^ 1);   // stage-2 MMAs of chunk n-1 finished reading the a2 buffer
-      if (tr) MD_TRACE(34, n);
+      uint32_t u[2][16], r[16];
+      tmem_ld16_nowait(lane_base + colq * 32, u[0]);
+      tmem_ld16_nowait(lane_base + 128 + colq * 32, r);
+      tmem_ld16_nowait(lane_base + colq * 32 + 16, u[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[MB_ACC_EMPTY]);   // U may be overwritten by chunk n+1
       // a2[row][colq*32 .. +32): K block colq>>1, 16-byte chunks (colq&1)*4 .. +4, 128B swizzle
       uint8_t* dst = sA2 + (colq >> 1) * MD_A_KB_BYTES + row * 128;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(dst + (((((colq & 1) * 4 + j)) ^ (row & 7)) << 4)) =
-            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      for (int h = 0; h < 2; ++h) {
+        const int col = colq * 32 + h * 16;
+        const float4* b1 = reinterpret_cast<const float4*>(sb_out + c * MD_NC + col);
+        const float4* b2 = reinterpret_cast<const float4*>(sb_res + c * MD_NC + col);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x1 = b1[i], x2 = b2[i];
+          // 2 * a2 = 2 * act(act(U + b_out) + (R + b_res)) on fp32 pairs: both activations are evaluated as 2 * act
+          // (one FMA-pipe instruction less each); the first factor goes into the FMA that adds R, the second into the
+          // stage-2 weights (w_mid_second holds V / 2), so the results are bit-identical to the unscaled form
+          const f32x2 half2 = pack2(0.5f, 0.5f);
+          const f32x2 lo = act2x_fast_x2<ACT>(fma2(act2x_fast_x2<ACT>(add2(pack2u(u[h][4 * i + 0], u[h][4 * i + 1]), pack2(x1.x, x1.y))),
+                                                   half2, add2(pack2u(r[4 * i + 0], r[4 * i + 1]), pack2(x2.x, x2.y))));
+          const f32x2 hi = act2x_fast_x2<ACT>(fma2(act2x_fast_x2<ACT>(add2(pack2u(u[h][4 * i + 2], u[h][4 * i + 3]), pack2(x1.z, x1.w))),
+                                                   half2, add2(pack2u(r[4 * i + 2], r[4 * i + 3]), pack2(x2.z, x2.w))));
+          pk[2 * i] = pack_bf16_x2(lo);
+          pk[2 * i + 1] = pack_bf16_x2(hi);
+        }
+        if (h == 0) {
+          tmem_ld16_nowait(lane_base + 128 + colq * 32 + 16, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[MB_R_EMPTY]);   // R may be overwritten by chunk n+1
+          if (tr) MD_TRACE(32, n);
+          if (tr) MD_TRACE(33, n);
+          mbar_wait(&bars[MB_A2_EMPTY], (n & 1) ^ 1);   // stage-2 MMAs of chunk n-1 finished reading the a2 buffer
+          if (tr) MD_TRACE(34, n);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = h * 2 + jj;
+          *reinterpret_cast<uint4*>(dst + (((((colq & 1) * 4 + j)) ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        }
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[MB_A2_FULL]);
@@ -343,9 +371,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               o[i] = pack_bf16(__uint_as_float(v[k][2 * i]) + bias[2 * i], __uint_as_float(v[k][2 * i + 1]) + bias[2 * i + 1]);
-            uint4* d4 = reinterpret_cast<uint4*>(drow);
-            d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            st_global_256(drow, o);   // one 256-bit store per (row, 16 columns)
           }
         }
       }
@@ -435,7 +461,7 @@ bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b)
   if (b->cin != F) return false;
   if (K1 % 16 || K2 % 16 || F % MD_NC || N3 % 16 || N4 % 16) return false;
   if (N3 < 16 || N4 < 16 || N3 + N4 > 256) return false;             // one MMA stream, one TMEM accumulator
-  if (((K1 + 63) / 64 + (K2 + 63) / 64) % 2) return false;           // stage-1 image is streamed as 256-row boxes
+  if (((K1 + 63) / 64) % 2 || ((K2 + 63) / 64) % 2) return false;    // each half of the stage-1 image is streamed as 256-row boxes
   return mid_smem_bytes(K1, K2, F, N3, N4) <= 227 * 1024;
 }
 

@@ -272,14 +272,10 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (u * 16 < cpt) {
-            uint4 o0, o1;
-            o0.x = pack_bf16(comb[u * 16 + 0], comb[u * 16 + 1]);  o0.y = pack_bf16(comb[u * 16 + 2], comb[u * 16 + 3]);
-            o0.z = pack_bf16(comb[u * 16 + 4], comb[u * 16 + 5]);  o0.w = pack_bf16(comb[u * 16 + 6], comb[u * 16 + 7]);
-            o1.x = pack_bf16(comb[u * 16 + 8], comb[u * 16 + 9]);  o1.y = pack_bf16(comb[u * 16 + 10], comb[u * 16 + 11]);
-            o1.z = pack_bf16(comb[u * 16 + 12], comb[u * 16 + 13]); o1.w = pack_bf16(comb[u * 16 + 14], comb[u * 16 + 15]);
-            uint4* dst = reinterpret_cast<uint4*>(orow + u * 16);
-            dst[0] = o0;
-            dst[1] = o1;
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16(comb[u * 16 + 2 * i], comb[u * 16 + 2 * i + 1]);
+            st_global_256(orow + u * 16, o);
           }
         }
       }

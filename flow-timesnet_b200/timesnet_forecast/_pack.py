@@ -146,7 +146,9 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             first = torch.cat([kblocks(w_out_nk), kblocks(w_res_nk)], dim=1)           # [cout/128][kb1+kb2][128][64]
             st.w_mid_first = dev16(first)
         if cin % 128 == 0:
-            both = torch.cat([w_in, w_res_nk], dim=0)                                  # [NB+cout][cin]
+            # halved: tc_mid feeds this stage 2 * a2 (its second activation is evaluated as 2 * act, one instruction
+            # less); a power of two, so the products are bit-identical to a2 . w
+            both = 0.5 * torch.cat([w_in, w_res_nk], dim=0)                            # [NB+cout][cin]
             second = both.reshape(NB + cout, cin // 64, 64).permute(1, 0, 2)           # [cin/64][NB+cout][64]
             st.w_mid_second = dev16(second)                                            # == [cin/128][2][NB+cout][64]
     return PackedInception(st, keep, macs)

@@ -105,7 +105,8 @@ typedef struct FtnInceptionWeights {
    *                 w_out[c*128+n][kb*64+k], the next kb2 blocks w_res[c*128+n][kb*64+k];
    *                 K zero-padded to multiples of 64
    *   w_mid_second: [cin/128][2][n_branch*mid + cout][64] bf16; rows n < n_branch*mid hold
-   *                 w_in[n][c*128+kb*64+k], the remaining rows w_res[n][c*128+kb*64+k]
+   *                 w_in[n][c*128+kb*64+k] / 2, the remaining rows w_res[n][c*128+kb*64+k] / 2
+   *                 (the kernel feeds this stage 2 * activation; halving is exact in bf16)
    * NULL = the fused middle kernel is not used with this block. */
   const void* w_mid_first;
   const void* w_mid_second;
