@@ -549,7 +549,8 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // spectrum_fft.cu
-int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, cudaStream_t st);
+int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, float* med, bool* fused_median,
+                        cudaStream_t st);
 int channel_median_reg_launch(const float* amp, int rows, int C, float* med, cudaStream_t st);
 
 }  // namespace ftn
@@ -620,7 +621,8 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
   const int F = L / 2 + 1;
   float* amp = reinterpret_cast<float*>(workspace);
   int rc;
-  { TimedScope tf(FTN_FAM_FFT, st); rc = spectrum_fft_launch(x, dtype, B, L, C, amp, st); }   // mixed-radix FFT (even L); -1 = n/a
+  bool fused_median = false;   // C <= 256: the FFT kernel's clusters also reduce over channels
+  { TimedScope tf(FTN_FAM_FFT, st); rc = spectrum_fft_launch(x, dtype, B, L, C, amp, amp_median, &fused_median, st); }   // mixed-radix FFT (even L); -1 = n/a
   if (rc > 0) return rc;
   if (rc < 0) {
     size_t smem = (size_t)L * kDftChannels * sizeof(float) + (size_t)L * sizeof(float2);
@@ -636,7 +638,8 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
     FTN_LAUNCH_CHECK("spectrum_dft_kernel");
   }
   const int rows = B * F;
-  { TimedScope tm(FTN_FAM_MEDIAN, st); rc = channel_median_reg_launch(amp, rows, C, amp_median, st); }   // registers (C <= 512)
+  rc = 0;
+  if (!fused_median) { TimedScope tm(FTN_FAM_MEDIAN, st); rc = channel_median_reg_launch(amp, rows, C, amp_median, st); }   // registers (C <= 512)
   if (rc > 0) return rc;
   if (rc < 0) {
     size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);

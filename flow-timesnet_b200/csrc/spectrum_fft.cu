@@ -12,6 +12,9 @@
 // every even L works (28 = 2.2.7, 96, 336 = 2.(4.2.3.7), 720 ...).  The 8 warps of the CTA split
 // the N/r butterflies of a pass; twiddles come from one exp(-2 pi i k / N) table in shared memory.
 // Odd L (or N too large for shared memory) falls back to the direct DFT kernel in period_search.cu.
+#include <stdlib.h>
+
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -135,9 +138,18 @@ __device__ __forceinline__ void fft_pass_generic(const float2* __restrict__ src,
   }
 }
 
-template <typename T>
+template <int KPL>
+__device__ __forceinline__ float warp_lower_median(float (&v)[KPL], int C, int lane);
+
+// KPL > 0: the CTAs of one window (32 channels each) form a thread-block cluster; the amplitudes stay in shared
+// memory, and after a cluster barrier every CTA takes the bins k = rank, rank + slabs, ... and computes their
+// lower median over all C channels from its peers' shared memory (DSMEM), KPL = values per lane of the sorting
+// network (slabs rounded up to a power of two).  amp[B][F][C] never goes to global memory and the separate median
+// kernel (14.7 us at the elec shape, 11 MB of L2 traffic) disappears.
+template <typename T, int KPL>
 __global__ void __launch_bounds__(kFftWarps * 32)
-spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ amp /*[B][F][C]*/, const FftPlan plan) {
+spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ amp /*[B][F][C]*/,
+                    float* __restrict__ med /*[B][F], KPL > 0*/, const FftPlan plan) {
   extern __shared__ float2 fsm[];
   const int N = L >> 1;
   float2* bufA = fsm;
@@ -204,8 +216,37 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
       const float cs = tw2[k].x, sn = tw2[k].y;
       const float xr = er + (cs * orr + sn * oi);      // W = cs - i sn
       const float xi = ei + (cs * oi - sn * orr);
-      amp[((size_t)b * F + k) * C + c] = sqrtf(fmaf(xr, xr, xi * xi));
+      const float a = sqrtf(fmaf(xr, xr, xi * xi));
+      if (KPL > 0) reinterpret_cast<float*>(dst)[k * 32 + lane] = a;   // dst is the idle ping-pong buffer
+      else amp[((size_t)b * F + k) * C + c] = a;
     }
+  }
+  if constexpr (KPL > 0) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                    // every slab's amplitudes are in place
+    const int slabs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const float* peer[KPL];
+#pragma unroll
+    for (int sl = 0; sl < KPL; ++sl)
+      peer[sl] = sl < slabs ? cluster.map_shared_rank(reinterpret_cast<float*>(dst), sl) : nullptr;
+    for (int k = rank + slabs * warp; k < F; k += slabs * kFftWarps) {
+      float v[KPL];
+      bool has_nan = false;
+#pragma unroll
+      for (int sl = 0; sl < KPL; ++sl) {
+        float a = CUDART_INF_F;                        // padding sorts last; never selected because (C-1)/2 < C
+        if (sl < slabs && sl * 32 + lane < C) {
+          a = peer[sl][k * 32 + lane];
+          has_nan = has_nan || (a != a);
+        }
+        v[sl] = a;
+      }
+      has_nan = __any_sync(0xffffffffu, has_nan);
+      const float pick = warp_lower_median<KPL>(v, C, lane);
+      if (lane == 0) med[(size_t)b * F + k] = has_nan ? CUDART_NAN_F : pick;   // torch.median propagates NaN
+    }
+    cluster.sync();                                    // peers may still be reading this CTA's amplitudes
   }
 }
 
@@ -220,31 +261,12 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
   return __uint_as_float(u);
 }
 
-// lower median over channels: one warp per (window, bin), the C amplitudes sorted by a register-resident
-// bitonic network (KPL values per lane, element e = lane * KPL + i; strides < KPL are register-to-register
-// compare-exchanges, larger strides one SHFL each).  ~250 instructions per row instead of the ~640 of a
-// bit-serial radix select.  Amplitudes are compared as floats; NaN is handled separately because
-// torch.median propagates it.
+// lower median of the C values a warp holds KPL per lane (element e = lane * KPL + i; slots >= C hold +inf):
+// register-resident bitonic network, strides < KPL are register-to-register compare-exchanges, larger strides one
+// SHFL each.  ~250 instructions per row instead of the ~640 of a bit-serial radix select.  Amplitudes are compared
+// as floats; NaN is handled by the callers because torch.median propagates it.
 template <int KPL>
-__global__ void __launch_bounds__(kMedWarps * 32)
-channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float* __restrict__ med) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kMedWarps + warp;
-  if (row >= rows) return;
-  const float* a = amp + (size_t)row * C;
-  float v[KPL];
-  bool has_nan = false;
-#pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    const int idx = lane * KPL + i;
-    float x = CUDART_INF_F;          // padding sorts last; never selected because k < C
-    if (idx < C) {
-      x = a[idx];
-      has_nan = has_nan || (x != x);
-    }
-    v[i] = x;
-  }
-  has_nan = __any_sync(0xffffffffu, has_nan);
+__device__ __forceinline__ float warp_lower_median(float (&v)[KPL], int C, int lane) {
 #pragma unroll
   for (int size = 2; size <= 32 * KPL; size <<= 1) {
 #pragma unroll
@@ -276,7 +298,31 @@ channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float*
   float pick = v[0];
 #pragma unroll
   for (int i = 1; i < KPL; ++i) pick = (k % KPL == i) ? v[i] : pick;
-  pick = __shfl_sync(0xffffffffu, pick, k / KPL);
+  return __shfl_sync(0xffffffffu, pick, k / KPL);
+}
+
+// lower median over channels: one warp per (window, bin)
+template <int KPL>
+__global__ void __launch_bounds__(kMedWarps * 32)
+channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float* __restrict__ med) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kMedWarps + warp;
+  if (row >= rows) return;
+  const float* a = amp + (size_t)row * C;
+  float v[KPL];
+  bool has_nan = false;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int idx = lane * KPL + i;
+    float x = CUDART_INF_F;          // padding sorts last; never selected because k < C
+    if (idx < C) {
+      x = a[idx];
+      has_nan = has_nan || (x != x);
+    }
+    v[i] = x;
+  }
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  const float pick = warp_lower_median<KPL>(v, C, lane);
   if (lane == 0) med[row] = has_nan ? CUDART_NAN_F : pick;   // torch.median propagates NaN
 }
 
@@ -297,30 +343,63 @@ static bool fft_factor(int N, FftPlan* plan) {
   return true;
 }
 
-// returns 0 when the FFT path ran, -1 when the caller must use the direct DFT, > 0 on error
-int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, cudaStream_t st) {
+template <typename T, int KPL>
+static int fft_launch_one(const T* x, int B, int L, int C, float* amp, float* med, const FftPlan& plan, size_t smem,
+                          cudaStream_t st) {
+  static size_t attr = 0;   // raise the dynamic shared memory limit once per size (not a stream operation)
+  if (smem > attr) {
+    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<T, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int slabs = (C + 31) / 32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(slabs, B);
+  cfg.blockDim = dim3(kFftWarps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (KPL > 0) {   // the slabs of one window are one cluster
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = slabs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  FTN_CUDA(cudaLaunchKernelEx(&cfg, spectrum_fft_kernel<T, KPL>, x, L, C, amp, med, plan));
+  FTN_LAUNCH_CHECK("spectrum_fft_kernel");
+  return 0;
+}
+
+template <typename T>
+static int fft_launch_dtype(const T* x, int B, int L, int C, float* amp, float* med, const FftPlan& plan, size_t smem,
+                            bool fused, cudaStream_t st) {
+  if (!fused) return fft_launch_one<T, 0>(x, B, L, C, amp, med, plan, smem, st);
+  const int slabs = (C + 31) / 32;
+  if (slabs <= 1) return fft_launch_one<T, 1>(x, B, L, C, amp, med, plan, smem, st);
+  if (slabs <= 2) return fft_launch_one<T, 2>(x, B, L, C, amp, med, plan, smem, st);
+  if (slabs <= 4) return fft_launch_one<T, 4>(x, B, L, C, amp, med, plan, smem, st);
+  return fft_launch_one<T, 8>(x, B, L, C, amp, med, plan, smem, st);
+}
+
+// returns 0 when the FFT path ran, -1 when the caller must use the direct DFT, > 0 on error.  *fused_median is set
+// when the kernel also produced med[B][F] (C <= 256: the <= 8 channel slabs of a window fit one portable cluster).
+int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, float* med, bool* fused_median,
+                        cudaStream_t st) {
+  *fused_median = false;
   if (L & 1) return -1;
   const int N = L / 2;
   const size_t smem = ((size_t)2 * N * 32 + N + N + 1) * sizeof(float2);
   if (smem > 227 * 1024) return -1;
   FftPlan plan;
   if (!fft_factor(N, &plan)) return -1;
-  dim3 grid((C + 31) / 32, B);
-  static size_t attr[2] = {0, 0};   // raise the dynamic shared memory limit once per size (not a stream operation)
-  if (dtype == FTN_F32) {
-    if (smem > attr[0]) {
-      FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[0] = smem;
-    }
-    spectrum_fft_kernel<float><<<grid, kFftWarps * 32, smem, st>>>((const float*)x, L, C, amp, plan);
-  } else {
-    if (smem > attr[1]) {
-      FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[1] = smem;
-    }
-    spectrum_fft_kernel<__nv_bfloat16><<<grid, kFftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, amp, plan);
-  }
-  FTN_LAUNCH_CHECK("spectrum_fft_kernel");
+  static const bool no_fuse = getenv("FLOWTIMES_NO_FUSED_MEDIAN") != nullptr;   // A/B switch for profiling
+  const bool fused = !no_fuse && med != nullptr && (C + 31) / 32 <= 8;
+  int rc;
+  if (dtype == FTN_F32) rc = fft_launch_dtype<float>((const float*)x, B, L, C, amp, med, plan, smem, fused, st);
+  else rc = fft_launch_dtype<__nv_bfloat16>((const __nv_bfloat16*)x, B, L, C, amp, med, plan, smem, fused, st);
+  if (rc) return rc;
+  *fused_median = fused;
   return 0;
 }
 

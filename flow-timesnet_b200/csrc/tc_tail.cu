@@ -54,7 +54,14 @@ __device__ __forceinline__ int tl_tile_index(const FtnPeriodPlan* pl, int B, int
   return base + b * ((L + pl->grp_pad[g] + TL_BM - 1) / TL_BM) + tt;
 }
 
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// Round a PAIR to bf16 and widen it again.  A scalar __float2bfloat16_rn is F2F.BF16.F32 on the XU pipe (8 cycles per
+// warp instruction, like MUFU): with two roundings per value and group this kernel was XU-bound (ncu: 54 % XU).
+// The packed F2FP.BF16.F32.PACK_AB runs on the ALU side at ~2 cycles for two values; the results are identical.
+__device__ __forceinline__ void bf16_round2(float a, float b, float& ra, float& rb) {
+  const uint32_t pk = pack_bf16(a, b);
+  ra = __uint_as_float(pk << 16);
+  rb = __uint_as_float(pk & 0xffff0000u);
+}
 
 template <int ACT>
 __global__ void __launch_bounds__(TL_THREADS, 1)
@@ -217,8 +224,10 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float d0, d1;
               unpack2(v, d0, d1);
               // delta rounded to the activation dtype, weighted, rounded again, accumulated in fp32 (aggregate.cu)
-              comb[u * 16 + 2 * i] += bf16_round(bf16_round(d0) * wg);
-              comb[u * 16 + 2 * i + 1] += bf16_round(bf16_round(d1) * wg);
+              bf16_round2(d0, d1, d0, d1);
+              bf16_round2(d0 * wg, d1 * wg, d0, d1);
+              comb[u * 16 + 2 * i] += d0;
+              comb[u * 16 + 2 * i + 1] += d1;
             }
           }
         }
@@ -235,15 +244,22 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           xv[0] = *sw_chunk(sX, c_lo + u * 16); xv[1] = *sw_chunk(sX, c_lo + u * 16 + 8);
           const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float xf = __uint_as_float((i & 1) ? (xw[i >> 1] & 0xffff0000u) : (xw[i >> 1] << 16));
-            float v = G > 0 ? bf16_round(xf + bf16_round(comb[u * 16 + i])) : xf;
-            if (p.ln_w) {
-              const float d2 = bf16_round(v - xf);     // updated - seq      (:2059)
-              v = bf16_round(xf + d2);                 // seq + delta        (:2060)
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = __uint_as_float(xw[i] << 16), x1 = __uint_as_float(xw[i] & 0xffff0000u);
+            float v0 = x0, v1 = x1;
+            if (G > 0) {
+              bf16_round2(comb[u * 16 + 2 * i], comb[u * 16 + 2 * i + 1], v0, v1);
+              bf16_round2(x0 + v0, x1 + v1, v0, v1);
             }
-            comb[u * 16 + i] = v;
-            sum += v;
+            if (p.ln_w) {
+              float e0, e1;
+              bf16_round2(v0 - x0, v1 - x1, e0, e1);   // updated - seq      (:2059)
+              bf16_round2(x0 + e0, x1 + e1, v0, v1);   // seq + delta        (:2060)
+            }
+            comb[u * 16 + 2 * i] = v0;
+            comb[u * 16 + 2 * i + 1] = v1;
+            sum += v0;
+            sum += v1;
           }
         }
       }
