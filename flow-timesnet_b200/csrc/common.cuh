@@ -54,6 +54,31 @@ enum { FTN_FAM_SPECTRUM = 0, FTN_FAM_CONV = 1, FTN_FAM_AGGREGATE = 2,
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch --------------------------------------------
+// Every kernel of the TimesBlock chain is launched with the programmatic-stream-serialization attribute, calls
+// pdl_trigger() first thing and pdl_wait() after its input-independent prologue (shared-memory carve-up, mbarrier
+// init, TMEM allocation, bias staging, twiddle tables) and before it touches anything a predecessor wrote.  Its CTAs
+// are then placed as soon as the predecessor's CTAs leave their SMs, so launch latency and prologue hide under the
+// predecessor's tail.  pdl_wait() returns when the preceding grid has completed and flushed, so nothing after it needs
+// care; nothing before it may read activations / the plan or write global memory.
+bool pdl_enabled();   // FLOWTIMES_NO_PDL switches it off (A/B)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 int sm_count();  // cached per process (current device at first call)
 
 // ---- dtype access -------------------------------------------------------------

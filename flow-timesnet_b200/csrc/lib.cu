@@ -6,6 +6,8 @@
 #include <vector>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ftn {
@@ -66,6 +68,11 @@ int sm_count() {
 }
 
 }  // namespace ftn
+
+bool ftn::pdl_enabled() {
+  static const bool on = getenv("FLOWTIMES_NO_PDL") == nullptr;
+  return on;
+}
 
 extern "C" int ftn_version(void) { return FTN_ABI_VERSION; }
 

@@ -380,6 +380,8 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   __shared__ float s_e[FTN_MAX_K][kSelFinishThreads];
   __shared__ float s_w[FTN_MAX_K][kSelFinishThreads];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();   // reads the medians and rewrites the plan / weights earlier kernels of the stream were reading
 
   if (do_sum) {
     // same order as batch_sum_kernel: row-lane r sums b = r, r+32, ... serially, then a serial fold over r.
@@ -586,15 +588,15 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[0] = smem;
     }
-    select_fused_kernel<float><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax, min_period,
-                                                      plan, (float*)amps, weights);
+    FTN_CUDA(launch_pdl(select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B, global_batch, L,
+                        k, pmax, min_period, plan, (float*)amps, weights));
   } else {
     if (smem > 16 * 1024 && smem > attr[1]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[1] = smem;
     }
-    select_fused_kernel<__nv_bfloat16><<<1, 1024, smem, st>>>(amp_median, amp_sum, do_sum, B, global_batch, L, k, pmax,
-                                                              min_period, plan, (__nv_bfloat16*)amps, weights);
+    FTN_CUDA(launch_pdl(select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B,
+                        global_batch, L, k, pmax, min_period, plan, (__nv_bfloat16*)amps, weights));
   }
   FTN_LAUNCH_CHECK("select_fused_kernel");
   return 0;

@@ -162,15 +162,7 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
   const int c = c0 + lane;
   const T* xb = x + (size_t)b * L * C;
 
-#pragma unroll 4
-  for (int n = warp; n < N; n += kFftWarps) {   // unrolled: several independent global loads in flight per thread
-    float re = 0.f, im = 0.f;
-    if (c < C) {
-      re = to_f32<T>(xb[(size_t)(2 * n) * C + c]);
-      im = to_f32<T>(xb[(size_t)(2 * n + 1) * C + c]);
-    }
-    bufA[n * 32 + lane] = make_float2(re, im);
-  }
+  pdl_trigger();
   for (int k = threadIdx.x; k < N; k += blockDim.x) {
     float s, co;
     sincospif(2.0f * (float)k / (float)N, &s, &co);
@@ -180,6 +172,16 @@ spectrum_fft_kernel(const T* __restrict__ x, int L, int C, float* __restrict__ a
     float s, co;
     sincospif(2.0f * (float)k / (float)L, &s, &co);
     tw2[k] = make_float2(co, s);
+  }
+  pdl_wait();   // x is a predecessor's output; the twiddle tables above are not
+#pragma unroll 4
+  for (int n = warp; n < N; n += kFftWarps) {   // unrolled: several independent global loads in flight per thread
+    float re = 0.f, im = 0.f;
+    if (c < C) {
+      re = to_f32<T>(xb[(size_t)(2 * n) * C + c]);
+      im = to_f32<T>(xb[(size_t)(2 * n + 1) * C + c]);
+    }
+    bufA[n * 32 + lane] = make_float2(re, im);
   }
   __syncthreads();
 
@@ -357,15 +359,22 @@ static int fft_launch_one(const T* x, int B, int L, int C, float* amp, float* me
   cfg.blockDim = dim3(kFftWarps * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
+  int na = 0;
   if (KPL > 0) {   // the slabs of one window are one cluster
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = slabs;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = slabs;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
   FTN_CUDA(cudaLaunchKernelEx(&cfg, spectrum_fft_kernel<T, KPL>, x, L, C, amp, med, plan));
   FTN_LAUNCH_CHECK("spectrum_fft_kernel");
   return 0;

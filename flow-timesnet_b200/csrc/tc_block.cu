@@ -53,12 +53,14 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
   FTN_REQUIRE(shared_bias_row < 0 || tc_kk_uses_conv4(w), "tc_kk_stage: the shared input layout needs the tc_conv4 route");
   if (tc_kk_uses_conv4(w)) {
     // phases-on-M kernel for every group whose padded image fits shared memory, tc_conv2 for the rest
-    // The two launches cover disjoint groups and only read `in`, so the (normally empty, ~5 us) tc_conv2 launch
-    // runs on a side stream forked from and joined back into `st`: in a captured graph the two kernels become
-    // parallel nodes, and the fallback's launch latency hides under tc_conv4.
+    // The two launches cover disjoint groups and only read `in`.  With programmatic dependent launch (the default)
+    // they stay in stream order: the (normally empty) tc_conv2 grid is placed while tc_conv4 drains.  The side-stream
+    // fork / join variant (FLOWTIMES_SIDE_STREAM) makes them parallel graph nodes instead, but its event records sit
+    // between kernels and would turn the programmatic edges back into full serialisation.
     int caps[FTN_MAX_BRANCH];
     tc_conv4_caps(w, caps);
-    static const bool serial = getenv("FLOWTIMES_NO_SIDE_STREAM") != nullptr;
+    static const bool serial = getenv("FLOWTIMES_NO_SIDE_STREAM") != nullptr ||
+                               (pdl_enabled() && getenv("FLOWTIMES_SIDE_STREAM") == nullptr);
     static cudaStream_t side = nullptr;
     static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     if (!serial && !side) {

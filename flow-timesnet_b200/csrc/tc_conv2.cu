@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_buf1 + ((BUF_BYTES + 127) & ~127u));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C2_BARS);
 
+  pdl_trigger();
+  pdl_wait();   // the plan and the input image are a predecessor's output
   {
     // nothing to do for this CTA (e.g. tc_conv3 owns every group): leave before touching TMEM / weights
     C2Unit probe;
@@ -383,7 +385,7 @@ int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_gr
     FTN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  tc_conv2_kernel<<<ctas, C2_THREADS, smem, st>>>(a);
+  FTN_CUDA(launch_pdl(tc_conv2_kernel, dim3(ctas), dim3(C2_THREADS), smem, st, a));
   FTN_LAUNCH_CHECK("tc_conv2_kernel");
   return 0;
 }

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
   uint8_t* smem = align_smem(smem_raw, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long t_start = clock64();
+  pdl_trigger();
 
   int j = 0;
   while (j + 1 < p.n_branch && (int)blockIdx.x >= p.cta_begin[j + 1]) ++j;
@@ -138,7 +139,6 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C4_BARS);
   C4Group* s_grp = reinterpret_cast<C4Group*>(tmem_slot + 2);
   const FtnPeriodPlan* pl = p.plan;
-  const int G = pl->n_groups;
 
   if (tid == 0) {
     for (int i = 0; i < C4_NBUF_MAX; ++i) {
@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  pdl_wait();   // the plan and the input image are a predecessor's output
+  const int G = pl->n_groups;
   if (tid >= 32 && tid < 32 + G) {
     const int g = tid - 32;
     C4Group q;
@@ -460,7 +462,7 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   constexpr int kTraceWords = 2 * 16 * 256 + 256;
   if (trace_path && !trace_dev) cudaMalloc(&trace_dev, kTraceWords * sizeof(long long));
   if (trace_dev) { cudaMemsetAsync(trace_dev, 0, kTraceWords * sizeof(long long), st); a.trace = trace_dev; }
-  tc_conv4_kernel<<<ctas, C4_THREADS, smem, st>>>(a);
+  FTN_CUDA(launch_pdl(tc_conv4_kernel, dim3(ctas), dim3(C4_THREADS), smem, st, a));
   FTN_LAUNCH_CHECK("tc_conv4_kernel");
   if (trace_dev) {   // debug only (synchronises): "cta event index clock"
     cudaStreamSynchronize(st);

@@ -66,6 +66,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int nkb = (p.K + G2_BK - 1) / G2_BK;
   const uint32_t w_kb = (uint32_t)((p.N * 128 + 1023) & ~1023);     // one K block of the weights: N rows x 128 B
   uint8_t* sW = smem;
@@ -92,6 +93,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the activations (and the plan) are predecessors' outputs
   const FtnPeriodPlan* pl = p.plan;
 
   if (warp == 0) {
@@ -278,8 +280,8 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   }
   const int worst = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   const int grid = worst < sm_count() ? worst : sm_count();
-  if (ai) tc_gemm2_kernel<1><<<grid, G2_THREADS, smem, st>>>(mA, mW, k);
-  else tc_gemm2_kernel<0><<<grid, G2_THREADS, smem, st>>>(mA, mW, k);
+  if (ai) FTN_CUDA(launch_pdl(tc_gemm2_kernel<1>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
+  else FTN_CUDA(launch_pdl(tc_gemm2_kernel<0>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
   FTN_LAUNCH_CHECK("tc_gemm2_kernel");
   return 0;
 }

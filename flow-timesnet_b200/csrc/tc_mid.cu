@@ -99,6 +99,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int kb1 = (p.K1 + MD_BK - 1) / MD_BK, kb2 = (p.K2 + MD_BK - 1) / MD_BK;
   const int nch = p.F / MD_NC;
   const int N34 = p.N3 + p.N4;
@@ -134,6 +135,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the plan, h2 and x are predecessors' outputs
   const FtnPeriodPlan* pl = p.plan;
 
   // tiles this CTA owns (static round-robin); the chunk stream n = tile_iteration * nch + c runs
@@ -495,8 +497,8 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   }
   const int worst = tc_worst_case_tiles(B, L, max_groups);
   const int grid = worst < sm_count() ? worst : sm_count();
-  if (ai) tc_mid_kernel<1><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mW1, mW2, k);
-  else tc_mid_kernel<0><<<grid, MD_THREADS, smem, st>>>(mH2, mX, mW1, mW2, k);
+  if (ai) FTN_CUDA(launch_pdl(tc_mid_kernel<1>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
+  else FTN_CUDA(launch_pdl(tc_mid_kernel<0>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
   FTN_LAUNCH_CHECK("tc_mid_kernel");
   if (trace_dev) {   // debug only: dump the timeline of CTA 0 (synchronises!)
     cudaStreamSynchronize(st);

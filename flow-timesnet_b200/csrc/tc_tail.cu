@@ -70,6 +70,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int nkb = (p.K + TL_BK - 1) / TL_BK;
   const uint32_t w_kb = (uint32_t)((p.C * 128 + 1023) & ~1023);
   uint8_t* sW = smem;
@@ -112,6 +113,7 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the plan, g2, q, x and the group weights are predecessors' outputs
   const FtnPeriodPlan* pl = p.plan;
   const int G = pl->n_groups;
   const int tiles_x = (p.L + TL_BM - 1) / TL_BM;
@@ -373,8 +375,8 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   }
   const int items = B * ((L + TL_BM - 1) / TL_BM);
   const int grid = items < sm_count() ? items : sm_count();
-  if (ai) tc_tail_kernel<1><<<grid, TL_THREADS, smem, st>>>(mA, mW, mQ, mX, k);
-  else tc_tail_kernel<0><<<grid, TL_THREADS, smem, st>>>(mA, mW, mQ, mX, k);
+  if (ai) FTN_CUDA(launch_pdl(tc_tail_kernel<1>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
+  else FTN_CUDA(launch_pdl(tc_tail_kernel<0>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
   FTN_LAUNCH_CHECK("tc_tail_kernel");
   return 0;
 }
