@@ -36,9 +36,11 @@ import torch  # noqa: E402
 import flowtimes_synth as syn  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels, per launch, from the ncu --set full
-# capture summarised under profiles/ (r1z); algorithmic bytes are in DESIGN.md section 4
-NCU_TRAFFIC = {"elec": {"tc_conv3_kernel": 20.9e6, "tc_mid_kernel": 35.4e6, "tc_tail_kernel": 61.5e6,
-                        "tc_gemm2_kernel": 5.6e6, "unit": "bytes per launch", "source": "profiles/r1z_ncu_full.csv"}}
+# capture summarised under profiles/ (r1C); algorithmic bytes are in DESIGN.md section 4
+NCU_TRAFFIC = {"elec": {"tc_conv4_kernel (block A, input computed once per window)": 4.5e6,
+                        "tc_conv4_kernel (block B)": 21.0e6, "tc_mid_kernel": 37.9e6, "tc_tail_kernel": 61.7e6,
+                        "tc_gemm2_kernel": 5.6e6, "spectrum_fft_kernel": 5.6e6, "unit": "bytes per launch",
+                        "source": "profiles/r1C_ncu_full.csv"}}
 
 METRIC = "timesblock_forward_windows_per_sec"
 UNIT = "windows/s"
@@ -337,7 +339,7 @@ def run_native(args):
         conv_avg_ms = conv_ms / max(1, conv_calls)
         achieved = flops_per_call / (conv_avg_ms * 1e-3) / 1e12 if conv_avg_ms > 0 else 0.0
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        roofline = {"bound": "tensor", "kernel": "Inception chain of one TimesBlock (tc_gemm2, tc_conv3, tc_mid, tc_conv3, tc_tail)",
+        roofline = {"bound": "tensor", "kernel": "Inception chain of one TimesBlock (tc_gemm2, tc_conv4, tc_mid, tc_conv4, tc_tail)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": None, "peak_source": peak_src + ", sustained bf16",
                     "flops_per_launch_group": flops_per_call, "avg_ms": conv_avg_ms, "calls": conv_calls,
@@ -360,7 +362,9 @@ def run_native(args):
             if calls:
                 avg = ms_f / calls
                 mac = mac_per_pos[name]
-                tf = 2.0 * mac * pos_per_call / (avg * 1e-3) / 1e12
+                # on the tc_conv4 route (mid = 32) the first 1x1 stage runs once per window, not once per period group
+                units = wl.B * wl.T if (name == "s1_gemm" and mid_ == 32) else pos_per_call
+                tf = 2.0 * mac * units / (avg * 1e-3) / 1e12
                 label = "tail (last 1x1 + aggregate + LayerNorm)" if name == "s6_gemm" and not agg_calls else name
                 kernels.append({"kernel": label, "avg_ms": avg, "executed_TFLOPs": tf, "frac_of_peak": tf / peak_tf,
                                 "executed_mac_per_position": mac})

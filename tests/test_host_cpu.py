@@ -213,3 +213,26 @@ def test_shard_batch_covers_everything():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_phase_stage_images_are_toeplitz_windows():
+    """w_kk_phase (tc_conv4.cu): rows [32 s, 32 s + 128) of a plane are the operand of position shift s, i.e. row
+    (3 - phi) * 32 + n holds W[n, :, dr, s - phi] when 0 <= s - phi < kw and zeros otherwise."""
+    import torch
+    from timesnet_forecast._pack import _phase_stage_images
+    g = torch.Generator().manual_seed(0)
+    for kh, kw in ((3, 3), (5, 5), (7, 7)):
+        wk = torch.randn(32, 32, kh, kw, generator=g, dtype=torch.float64)
+        img = _phase_stage_images(wk)
+        plane = (kw + 3) * 32
+        assert img.shape == (kh, 4 * plane + 96, 8)
+        assert img.numel() * 2 == kh * (2048 * (kw + 3) + 1536)          # bf16 bytes == c4_stage_bytes(kw) per tap row
+        for dr in range(kh):
+            for c in range(4):
+                for s in range(kw + 3):
+                    win = img[dr, c * plane + 32 * s: c * plane + 32 * s + 128]
+                    for phi in range(4):
+                        blk = win[(3 - phi) * 32:(4 - phi) * 32]
+                        dx = s - phi
+                        want = wk[:, c * 8:(c + 1) * 8, dr, dx] if 0 <= dx < kw else torch.zeros(32, 8, dtype=torch.float64)
+                        assert torch.equal(blk, want), (kh, dr, c, s, phi)
