@@ -323,9 +323,21 @@ def run_native(args):
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # the same host->device copies alone (nothing else on the GPU): the floor the host link puts under a step
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(5):
+            xd.copy_(x_host, non_blocking=True)
+            yd.copy_(y_host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_ms = c0.elapsed_time(c1) / 5
+        h2d_bytes = int(x_host.numel() * 4 + y_host.numel() * 4)
         e2e = {"value": wl.B * world / (te.item() / args.steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": te.item() / args.steps,
+               "h2d_alone_ms_per_step": h2d_ms, "h2d_alone_GBs": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
                "scope": "TimesNet.forward + negative_binomial_nll" + ("" if args.no_graph else
                         " through PipelinedRunner (H2D of the next step overlaps the replay of the current one)"),
                "loss": float(loss_host)}

@@ -380,6 +380,12 @@ int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
                    cudaStream_t st);
 bool tc_block_fused_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b);
+bool tc_block_search_overlap_eligible(int dtype, int B, int L, int C, int max_groups, const FtnInceptionWeights* a,
+                                      const FtnInceptionWeights* b);
+int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
+                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
+                                const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
+                                int (*search)(void*, cudaStream_t), void* search_ctx);
 int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                     const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                     const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st);
@@ -438,4 +444,44 @@ extern "C" int ftn_timesblock_fused(const void* x, int dtype, int B, int L, int 
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_CONV, st);
   return period_block_tc(x, B, L, C, plan, max_groups, a, b, act, weights, ln_weight, ln_bias, ln_eps, out, workspace, st);
+}
+
+// ftn_period_search + ftn_timesblock_fused in one call (single rank).  The first 1x1 stage of block A depends on x only,
+// so it is enqueued on a low-priority side stream before the search and joined before the k x k stage: the selection
+// kernel of the search is one CTA, and the 1x1 GEMM tiles run on the SMs it leaves idle.  Returns -1 (nothing
+// enqueued) when the configuration is not eligible; the caller then issues the two calls itself.
+namespace {
+struct SearchCtx {
+  const void* x; int dtype, B, L, C, k, pmax, min_period;
+  float* amp_median; float* amp_sum; FtnPeriodPlan* plan; void* amps; float* weights; void* ws; size_t ws_bytes;
+};
+int run_search(void* c, cudaStream_t st) {
+  const SearchCtx* s = static_cast<const SearchCtx*>(c);
+  return ftn_period_search(s->x, s->dtype, s->B, s->L, s->C, s->k, s->pmax, s->min_period, s->amp_median, s->amp_sum, s->plan,
+                           s->amps, s->weights, s->ws, s->ws_bytes, st);
+}
+}  // namespace
+
+extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
+                                      float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
+                                      void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
+                                      const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
+                                      float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(x && plan && out && workspace && weights && amps && amp_median && amp_sum && search_workspace,
+              "ftn_timesblock_forward: null pointer");
+  FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_timesblock_forward: bad sizes B=%d L=%d C=%d", B, L, C);
+  FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_timesblock_forward: k=%d outside [1,%d]", k, FTN_MAX_K);
+  FTN_REQUIRE(act == FTN_ACT_GELU || act == FTN_ACT_RELU, "ftn_timesblock_forward: unknown activation %d", act);
+  FTN_REQUIRE((ln_weight == nullptr) == (ln_bias == nullptr), "ftn_timesblock_forward: ln_weight/ln_bias must come together");
+  if (int rc = check_weights(a, "block A")) return rc;
+  if (int rc = check_weights(b, "block B")) return rc;
+  FTN_REQUIRE(a->cin == C && b->cout == C && a->cout == b->cin,
+              "ftn_timesblock_forward: channel chain %d->%d->%d->%d does not match C=%d", a->cin, a->cout, b->cin, b->cout, C);
+  if (!tc_block_search_overlap_eligible(dtype, B, L, C, k, a, b)) return -1;
+  FTN_REQUIRE(workspace_bytes >= ftn_inception_workspace_bytes(B, L, k, a, b), "ftn_timesblock_forward: workspace too small");
+  FTN_REQUIRE(search_workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_timesblock_forward: search workspace too small");
+  SearchCtx ctx{x, dtype, B, L, C, k, pmax, min_period, amp_median, amp_sum, plan, amps, weights, search_workspace,
+                search_workspace_bytes};
+  return period_block_tc_with_search(x, B, L, C, plan, k, a, b, act, weights, ln_weight, ln_bias, ln_eps, out, workspace,
+                                     as_stream(stream), run_search, &ctx);
 }

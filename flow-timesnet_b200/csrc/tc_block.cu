@@ -101,9 +101,13 @@ struct TcTailSpec {          // non-null: finish the block in the fused tail ker
   void* out;
 };
 
+// s1 != nullptr: the first 1x1 stage was already enqueued elsewhere (period_block_tc_s1) with this result
+struct TcS1Done { long long shared_bias_row; };
 static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
-                               void* workspace, const TcTailSpec* tail, cudaStream_t st);
+                               void* workspace, const TcTailSpec* tail, cudaStream_t st, const TcS1Done* s1 = nullptr);
+static int launch_block_s1(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row);
 
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
@@ -118,6 +122,15 @@ bool tc_block_fused_eligible(int dtype, int C, const FtnInceptionWeights* a, con
   return tc_tail_eligible(b->n_branch * b->mid, C);
 }
 
+// ftn_timesblock_forward: the fused route must apply and the first stage must be the once-per-window form (it is
+// enqueued before the plan exists)
+bool tc_block_search_overlap_eligible(int dtype, int B, int L, int C, int max_groups, const FtnInceptionWeights* a,
+                                      const FtnInceptionWeights* b) {
+  static const bool off = getenv("FLOWTIMES_NO_SEARCH_OVERLAP") != nullptr;   // A/B switch for profiling
+  if (off || !tc_block_fused_eligible(dtype, C, a, b) || !tc_kk_uses_conv4(a)) return false;
+  return ((long long)B * L + 127) / 128 + 1 <= tc_worst_case_tiles(B, L, max_groups);
+}
+
 int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                     const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                     const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st) {
@@ -125,9 +138,62 @@ int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* pla
   return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, nullptr, workspace, &tail, st);
 }
 
+// Whole block with the period search in the middle (ftn_timesblock_forward): the first 1x1 stage needs only x, so it is
+// forked onto a low-priority side stream before the search is enqueued and joined before the k x k stage.  The
+// selection kernel of the search is a single CTA; the 169 GEMM tiles fill the 147 SMs it leaves idle.
+int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
+                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
+                                const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
+                                int (*search)(void*, cudaStream_t), void* search_ctx) {
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    int least = 0, greatest = 0;
+    FTN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    FTN_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least));
+    FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  TcS1Done s1{-1};
+  FTN_CUDA(cudaEventRecord(ev_fork, st));
+  FTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  if (int rc = launch_block_s1(x, B, L, C, nullptr, max_groups, a, act, workspace, side, &s1.shared_bias_row)) return rc;
+  FTN_CUDA(cudaEventRecord(ev_join, side));
+  int rc = search(search_ctx, st);
+  FTN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));      // join even when the search failed: the side stream must not dangle
+  if (rc) return rc;
+  TcTailSpec tail{weights, ln_w, ln_b, eps, out};
+  TimedScope timed(FTN_FAM_CONV, st);
+  return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, nullptr, workspace, &tail, st, &s1);
+}
+
+// first 1x1 stage of block A.  It does not depend on the period: on the tc_conv4 route it runs ONCE over x[B*L][C]
+// (plus one tile of out-of-bounds = zero rows, whose output is the row every padded step t >= L stands for) instead
+// of once per group over the tile-major grid; the k x k loaders then index h1 by (window, t).
+static int launch_block_s1(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
+                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row) {
+  const int tiles = tc_worst_case_tiles(B, L, max_groups);
+  const int NBa = a->n_branch * a->mid;
+  TcGemmArgs s{};
+  s.plan = plan; s.B = B; s.L = L; s.max_groups = max_groups; s.n_tiles = tiles; s.act = act;
+  s.a1 = reinterpret_cast<const __nv_bfloat16*>(x); s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in;
+  s.K1 = C; s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = reinterpret_cast<__nv_bfloat16*>(workspace); s.ldo = NBa;
+  *shared_bias_row = -1;
+  const long long seq_tiles = ((long long)B * L + 127) / 128 + 1;
+  if (tc_kk_uses_conv4(a) && seq_tiles <= tiles) {
+    s.plan = nullptr; s.a1_seq = 0; s.a1_rows = (long long)B * L; s.n_tiles = (int)seq_tiles;
+    *shared_bias_row = seq_tiles * 128 - 1;
+  } else {
+    FTN_REQUIRE(plan != nullptr, "tc block: the tile-major first stage needs the plan");
+    s.a1_seq = 1;
+  }
+  TimedScope t1(FTN_FAM_S1, st);
+  return tc_stage_launch(s, st);
+}
+
 static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
-                               void* workspace, const TcTailSpec* tail, cudaStream_t st) {
+                               void* workspace, const TcTailSpec* tail, cudaStream_t st, const TcS1Done* s1) {
   const int tiles = tc_worst_case_tiles(B, L, max_groups);
   const long long rows = (long long)tiles * 128;
   const int NBa = a->n_branch * a->mid, NBb = b->n_branch * b->mid, F = a->cout;
@@ -143,21 +209,11 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
   TcGemmArgs base{};
   base.plan = plan; base.B = B; base.L = L; base.max_groups = max_groups; base.n_tiles = tiles; base.act = act;
 
-  // S1.  The first 1x1 stage does not depend on the period: on the tc_conv4 route it runs ONCE over x[B*L][C] (plus
-  // one tile of out-of-bounds = zero rows, whose output is the row every padded step t >= L stands for) instead of
-  // once per group over the tile-major grid; the k x k loaders then index h1 by (window, t).
+  // S1 (h1 is the first buffer of the workspace)
   TcGemmArgs s = base;
-  s.a1 = xb; s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in; s.K1 = C;
-  s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = NBa;
   long long shared_bias_row = -1;
-  const long long seq_tiles = ((long long)B * L + 127) / 128 + 1;
-  if (tc_kk_uses_conv4(a) && seq_tiles <= tiles) {
-    s.plan = nullptr; s.a1_seq = 0; s.a1_rows = (long long)B * L; s.n_tiles = (int)seq_tiles;
-    shared_bias_row = seq_tiles * 128 - 1;
-  } else {
-    s.a1_seq = 1;
-  }
-  { TimedScope t1(FTN_FAM_S1, st); if (int rc = tc_stage_launch(s, st)) return rc; }
+  if (s1) shared_bias_row = s1->shared_bias_row;
+  else if (int rc = launch_block_s1(x, B, L, C, plan, max_groups, a, act, workspace, st, &shared_bias_row)) return rc;
   // S2
   {
     TimedScope t2(FTN_FAM_KK_A, st);

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -84,6 +84,9 @@ SIGNATURES = {
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
     "ftn_timesblock_fused": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                                   C.POINTER(FtnInceptionWeights), _I, _P, _P, _P, _F, _P, _P, _SZ, _P]),
+    "ftn_timesblock_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ,
+                                    C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights), _I, _P, _P, _F, _P, _P,
+                                    _SZ, _P]),
     "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ftn_context_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ftn_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -292,6 +295,36 @@ def timesblock_fused(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, w
         return False
     _check(rc, "ftn_timesblock_fused")
     return True
+
+
+def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: FtnInceptionWeights,
+                       wb: FtnInceptionWeights, act: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
+                       eps: float):
+    """Period search + fused TimesBlock in one call (the first 1x1 stage overlaps the search).
+
+    Returns None when the configuration is not eligible (nothing was enqueued), else
+    (out, plan, amps[B,k], weights[B,16])."""
+    lib = load()
+    B, L, Cc = x.shape
+    Fq = L // 2 + 1
+    med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
+    ssum = torch.empty(Fq + 1, dtype=torch.float32, device=x.device)
+    plan = new_plan(x.device)
+    amps = torch.empty(B, k, dtype=x.dtype, device=x.device)
+    weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=x.device)
+    sbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)
+    sws = torch.empty(sbytes, dtype=torch.uint8, device=x.device)
+    nbytes = lib.ftn_inception_workspace_bytes(B, L, k, C.byref(wa), C.byref(wb))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty_like(x)
+    rc = lib.ftn_timesblock_forward(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
+                                    ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), sws.data_ptr(),
+                                    sbytes, C.byref(wa), C.byref(wb), act, _ptr(ln_w), _ptr(ln_b), float(eps),
+                                    out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    if rc == -1:
+        return None
+    _check(rc, "ftn_timesblock_forward")
+    return out, plan, amps, weights
 
 
 def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

@@ -601,6 +601,39 @@ class TimesBlock(nn.Module):
             delta[g] = d.permute(0, 2, 1).to(x.dtype)
         return delta
 
+    def _forward_with_search(self, x: torch.Tensor, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
+                             eps: float) -> Optional[torch.Tensor]:
+        """Single-rank fast path: period search and block in one library call (``ftn_timesblock_forward``), so the
+        period-independent first 1x1 stage runs beside the one-CTA selection kernel.  None = not applicable; the
+        caller then runs the selector and the block separately (identical results)."""
+        sel = self.period_selector
+        if not isinstance(sel, FFTPeriodSelector) or not self._is_native_bank():
+            return None
+        if os.getenv("TIMES_PERIOD_MAX_UNIQ") or os.getenv("TIMES_PERIOD_BINNING"):
+            return None
+        B, L, C = x.shape
+        if sel.k <= 0 or L <= 1 or x.dtype != torch.bfloat16:
+            return None
+        k = min(sel.k, L // 2)                                       # timesnet.py:122-126 (nbins - 1)
+        if k <= 0 or k > nv.FTN_MAX_K or sel._world()[1] != 1:
+            return None
+        if self.inception[0].proj.weight.device != x.device:
+            self.inception = self.inception.to(x.device)
+        pa = self.inception[0].packed(x.device)
+        pb = self.inception[2].packed(x.device)
+        res = nv.timesblock_forward(x, k, sel.pmax, sel.min_period_threshold, pa.struct, pb.struct,
+                                    _act_code(self._activation_name), ln_w, ln_b, eps)
+        if res is None:
+            return None
+        out, plan_dev, amps, weights = res
+        plan = PeriodPlan(plan_dev, amps, weights, k)
+        sel._last_plan = plan
+        sel._empty_device = x.device
+        self._last_plan = plan
+        self._last_raw = -1
+        self._vec_calls += 1
+        return out
+
     def _run(self, x: torch.Tensor, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
              eps: float) -> torch.Tensor:
         if x.ndim != 3:
@@ -618,6 +651,9 @@ class TimesBlock(nn.Module):
             raise ValueError("Number of channels changed between calls")
         B, L, C = x.shape
         with torch.no_grad():
+            fused = self._forward_with_search(x, ln_w, ln_b, eps)
+            if fused is not None:
+                return fused
             plan = self._plan_for(x)
             if plan is None:
                 if ln_w is None:

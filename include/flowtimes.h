@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 7
+#define FTN_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -210,6 +210,17 @@ FTN_API int ftn_timesblock_fused(const void* x, int dtype, int B, int L, int C, 
                          const float* ln_weight, const float* ln_bias, float ln_eps, void* out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ftn_period_search followed by ftn_timesblock_fused in ONE call (single rank; replaces TimesBlock.forward
+ * timesnet.py:767-818 incl. the selector call :791).  The first 1x1 stage of block A depends on x only: it is forked
+ * onto a low-priority side stream before the search is enqueued and joined before the k x k stage, so its GEMM tiles
+ * run on the SMs the one-CTA selection kernel leaves idle.  Outputs of the search (plan, amps, weights, amp_median,
+ * amp_sum) are written as by ftn_period_search.  Returns -1 with nothing enqueued when not eligible (the caller
+ * issues the two calls itself), 0 on success. */
+FTN_API int ftn_timesblock_forward(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
+                                   float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
+                                   void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
+                                   const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
+                                   float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* stream);
 /* ---- K4: weighted aggregation + residual (+ shared LayerNorm) ------------
  * out = x + sum_g w[b][g] * delta_g          replaces timesnet.py:1075-1099, :818
  * with ln_weight != NULL additionally        replaces timesnet.py:2059-2061
