@@ -334,10 +334,21 @@ def run_native(args):
         torch.cuda.synchronize()
         h2d_ms = c0.elapsed_time(c1) / 5
         h2d_bytes = int(x_host.numel() * 4 + y_host.numel() * 4)
+        # ... and the same forward + loss alone (inputs already on the device)
+        fwd_alone_ms = None
+        if not args.no_graph:
+            torch.cuda.synchronize()
+            c0.record()
+            for _ in range(5):
+                runner._graphs[0].replay()
+            c1.record()
+            torch.cuda.synchronize()
+            fwd_alone_ms = c0.elapsed_time(c1) / 5
         e2e = {"value": wl.B * world / (te.item() / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": te.item() / args.steps,
                "h2d_alone_ms_per_step": h2d_ms, "h2d_alone_GBs": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+               "forward_alone_ms_per_step": fwd_alone_ms,
                "scope": "TimesNet.forward + negative_binomial_nll" + ("" if args.no_graph else
                         " through PipelinedRunner (H2D of the next step overlaps the replay of the current one)"),
                "loss": float(loss_host)}

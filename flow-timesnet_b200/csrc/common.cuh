@@ -61,11 +61,15 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // are then placed as soon as the predecessor's CTAs leave their SMs, so launch latency and prologue hide under the
 // predecessor's tail.  pdl_wait() returns when the preceding grid has completed and flushed, so nothing after it needs
 // care; nothing before it may read activations / the plan or write global memory.
+// The attribute is only set when the predecessor in the stream is known to be one of these kernels (`dependent`):
+// the FIRST kernel of every API call is launched plainly, because what precedes it is the caller's business -- a
+// host-to-device copy of x, for one, must have landed before the kernel starts.
 bool pdl_enabled();   // FLOWTIMES_NO_PDL switches it off (A/B)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(bool dependent, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -75,7 +79,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = dependent && pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -385,7 +385,7 @@ bool tc_block_search_overlap_eligible(int dtype, int B, int L, int C, int max_gr
 int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
                                 const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                                 const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
-                                int (*search)(void*, cudaStream_t), void* search_ctx);
+                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi);
 int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                     const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                     const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st);
@@ -482,6 +482,11 @@ extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, in
   FTN_REQUIRE(search_workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_timesblock_forward: search workspace too small");
   SearchCtx ctx{x, dtype, B, L, C, k, pmax, min_period, amp_median, amp_sum, plan, amps, weights, search_workspace,
                 search_workspace_bytes};
+  // periods the selection kernel can emit: ceil(L / bin) with bin in [1, L/2], clamped to [min_period, pmax], and at
+  // least two cycles (period_search.cu); the k x k stages skip their long-period fallback launch when none can need it
+  const int hi_raw = pmax > 0 && pmax < L - 1 ? pmax : L - 1;
+  const int lo = hi_raw >= 2 ? (min_period > 2 ? min_period : 2) : 1;
+  const int hi = hi_raw > lo ? hi_raw : lo;
   return period_block_tc_with_search(x, B, L, C, plan, k, a, b, act, weights, ln_weight, ln_bias, ln_eps, out, workspace,
-                                     as_stream(stream), run_search, &ctx);
+                                     as_stream(stream), run_search, &ctx, lo, hi);
 }

@@ -10,73 +10,132 @@
 namespace ftn {
 
 // ---------------------------------------------------------------------------
-// generic SIMT GEMM:  C[b][m][n] = sum_k A[b][m][k] * Bm[b][k][n] (+ bias)
+// fp32 SIMT GEMM for the dense layers either side of the TimesBlock stack (value embedding, time
+// projection, mu / sigma heads):  C[b][m][n] = sum_k A[b][m][k] * Bm[b][k][n] (+ bias)
 //   A: fp32 row-major (lda), Bm: TB (fp32 or bf16), element (k, n) at
 //   TRANS_B ? Bm[n*ldb + k] : Bm[k*ldb + n].  bias_mode 0 none, 1 per-n, 2 per-m.
-// 64x64 tile, 256 threads, 4x4 register tile.
+// These stay in fp32 FMA arithmetic (1e-4 parity bound); what the first version lacked was
+// register blocking: 64x64 tiles with 4x4 outputs per thread issue one shared-memory load per two FMAs
+// and ran at ~8 TFLOP/s, so the three layers cost more than the whole TimesBlock stack (0.67 ms of a
+// 1.18 ms forward at the elec shape).  Here: TM x 128 tiles (TM = 128 or 64), 256 threads,
+// (TM/16) x 8 outputs per thread, K-major shared tiles read as 128-bit vectors (4 loads per 64 FMAs at
+// TM = 128), next K tile prefetched into registers while the current one is multiplied.
+// A thread owns rows {ty*RH + i, TM/2 + ty*RH + i} and columns {tx*4 + j, 64 + tx*4 + j}: every vector
+// load of a half-warp is one contiguous 256-byte run (conflict free).
 // ---------------------------------------------------------------------------
-template <typename TB, bool TRANS_B>
+template <typename TB, bool TRANS_B, int TM>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, int lda, long long strideA, const TB* __restrict__ Bm, int ldb,
              long long strideB, float* __restrict__ Cm, int ldc, long long strideC, int M, int N, int K,
              const float* __restrict__ bias, int bias_mode) {
-  constexpr int TM = 64, TN = 64, TK = 16;
-  __shared__ float As[TM][TK + 1];
-  __shared__ __align__(16) float Bs[TK][TN + 4];
+  constexpr int TN = 128, TK = 16, RH = TM / 32;          // RH rows per thread and half tile (4 or 2)
+  constexpr int PA = TM + 4, PB = TN + 4;                 // row pitches: 16-byte aligned, de-phased banks
+  __shared__ __align__(16) float As[2][TK][PA];
+  __shared__ __align__(16) float Bs[2][TK][PB];
   const int bz = blockIdx.z;
   A += (size_t)bz * strideA;
   Bm += (size_t)bz * strideB;
   Cm += (size_t)bz * strideC;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  constexpr int NA = TM * TK / 256, NBV = TN * TK / 256;  // elements of A / B a thread moves per K tile
+  float ra[NA], rb[NBV];
+  auto load_tile = [&](int k0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += TK) {
-    for (int i = tid; i < TM * TK; i += 256) {
-      int r = i / TK, k = i - r * TK;
-      float v = 0.f;
-      if (m0 + r < M && k0 + k < K) v = A[(size_t)(m0 + r) * lda + k0 + k];
-      As[r][k] = v;
+    for (int i = 0; i < NA; ++i) {                        // A tile: lanes run along k (64-byte runs)
+      const int e = tid + i * 256, r = e / TK, k = e - r * TK;
+      ra[i] = (m0 + r < M && k0 + k < K) ? A[(size_t)(m0 + r) * lda + k0 + k] : 0.f;
     }
-    for (int i = tid; i < TK * TN; i += 256) {
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int e = tid + i * 256;
       int k, n;
-      if (TRANS_B) { n = i / TK; k = i - n * TK; } else { k = i / TN; n = i - k * TN; }
+      if (TRANS_B) { n = e / TK; k = e - n * TK; } else { k = e / TN; n = e - k * TN; }
       float v = 0.f;
       if (k0 + k < K && n0 + n < N)
         v = TRANS_B ? to_f32<TB>(Bm[(size_t)(n0 + n) * ldb + k0 + k]) : to_f32<TB>(Bm[(size_t)(k0 + k) * ldb + n0 + n]);
-      Bs[k][n] = v;
+      rb[i] = v;
     }
-    __syncthreads();
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int e = tid + i * 256, r = e / TK, k = e - r * TK;
+      As[buf][k][r] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int e = tid + i * 256;
+      int k, n;
+      if (TRANS_B) { n = e / TK; k = e - n * TK; } else { k = e / TN; n = e - k * TN; }
+      Bs[buf][k][n] = rb[i];
+    }
+  };
+  float acc[2 * RH][8];
+#pragma unroll
+  for (int i = 0; i < 2 * RH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  const int nk = (K + TK - 1) / TK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tile((kt + 1) * TK);            // global loads in flight under the FMAs below
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      float a[4], w[4];
+      float a[2 * RH], w[8];
+      if (RH == 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][TM / 2 + ty * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        a[RH + 0] = a1.x; a[RH + 1] = a1.y; a[RH + 2] = a1.z; a[RH + 3] = a1.w;
+      } else {
+        const float2 a0 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+        const float2 a1 = *reinterpret_cast<const float2*>(&As[buf][k][TM / 2 + ty * 2]);
+        a[0] = a0.x; a[1] = a0.y;
+        a[RH + 0] = a1.x; a[RH + 1] = a1.y;
+      }
+      const float4 w0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+      w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][k];
+      for (int i = 0; i < 2 * RH; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
     }
+    if (kt + 1 < nk) store_tile(buf ^ 1);                 // the other buffer: its readers passed the barrier below one tile ago
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 2 * RH; ++i) {
+    const int m = m0 + (i < RH ? ty * RH + i : TM / 2 + ty * RH + (i - RH));
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int n = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias_mode == 1) v += bias[n];
       else if (bias_mode == 2) v += bias[m];
       Cm[(size_t)m * ldc + n] = v;
     }
+  }
+}
+
+// TM = 64 when 128-row tiles would leave SMs idle (few rows per batch entry)
+template <typename TB, bool TRANS_B>
+static void sgemm_launch(const float* A, int lda, long long sA, const TB* Bm, int ldb, long long sB, float* C, int ldc,
+                         long long sC, int M, int N, int K, int batch, const float* bias, int bias_mode, cudaStream_t st) {
+  const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * batch;
+  if (tiles128 >= sm_count() && M >= 96) {
+    dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
+    sgemm_kernel<TB, TRANS_B, 128><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+  } else {
+    dim3 grid((N + 127) / 128, (M + 63) / 64, batch);
+    sgemm_kernel<TB, TRANS_B, 64><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
   }
 }
 
@@ -226,11 +285,8 @@ __global__ void __launch_bounds__(256) nb_nll_final_kernel(const float* __restri
 static int launch_sgemm_f32(const float* A, int lda, long long sA, const float* Bm, int ldb, long long sB,
                             float* C, int ldc, long long sC, int M, int N, int K, int batch, bool transB,
                             const float* bias, int bias_mode, cudaStream_t st) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
-  if (transB)
-    sgemm_kernel<float, true><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
-  else
-    sgemm_kernel<float, false><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+  if (transB) sgemm_launch<float, true>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, batch, bias, bias_mode, st);
+  else sgemm_launch<float, false>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, batch, bias, bias_mode, st);
   FTN_LAUNCH_CHECK("sgemm_kernel");
   return 0;
 }
@@ -285,13 +341,12 @@ extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int 
   FTN_REQUIRE(B > 0 && L > 0 && C > 0 && steps > 0 && N > 0, "ftn_nb_head: bad sizes");
   cudaStream_t st = as_stream(stream);
   // hidden[b] (steps x C) = Wt (steps x L) . seq[b] (L x C) + bt[h]
-  dim3 grid((C + 63) / 64, (steps + 63) / 64, B);
   if (dtype == FTN_F32)
-    sgemm_kernel<float, false><<<grid, 256, 0, st>>>(Wt, L, 0, (const float*)seq, C, (long long)L * C, workspace, C,
-                                                     (long long)steps * C, steps, C, L, bt, 2);
+    sgemm_launch<float, false>(Wt, L, 0, (const float*)seq, C, (long long)L * C, workspace, C, (long long)steps * C, steps, C,
+                               L, B, bt, 2, st);
   else
-    sgemm_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(Wt, L, 0, (const __nv_bfloat16*)seq, C, (long long)L * C,
-                                                             workspace, C, (long long)steps * C, steps, C, L, bt, 2);
+    sgemm_launch<__nv_bfloat16, false>(Wt, L, 0, (const __nv_bfloat16*)seq, C, (long long)L * C, workspace, C,
+                                       (long long)steps * C, steps, C, L, B, bt, 2, st);
   FTN_LAUNCH_CHECK("sgemm_kernel(time_proj)");
   const int M = B * steps;
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wmu, C, 0, rate, N, 0, M, N, C, 1, true, bmu, 1, st)) return rc;

@@ -577,7 +577,7 @@ extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float
 
 static int launch_select_fused(const float* amp_median, float* amp_sum, int do_sum, int dtype, int B, int global_batch,
                                int L, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool after_fft) {
   const int F = L / 2 + 1;
   TimedScope ts(FTN_FAM_SELECT, st);
   const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : F)) * sizeof(float);
@@ -588,14 +588,14 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[0] = smem;
     }
-    FTN_CUDA(launch_pdl(select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B, global_batch, L,
+    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B, global_batch, L,
                         k, pmax, min_period, plan, (float*)amps, weights));
   } else {
     if (smem > 16 * 1024 && smem > attr[1]) {
       FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[1] = smem;
     }
-    FTN_CUDA(launch_pdl(select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B,
+    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B,
                         global_batch, L, k, pmax, min_period, plan, (__nv_bfloat16*)amps, weights));
   }
   FTN_LAUNCH_CHECK("select_fused_kernel");
@@ -610,7 +610,7 @@ extern "C" int ftn_period_search(const void* x, int dtype, int B, int L, int C, 
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_SPECTRUM, st);
   if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false)) return rc;
-  return launch_select_fused(amp_median, amp_sum, 1, dtype, B, B, L, k, pmax, min_period, plan, amps, weights, st);
+  return launch_select_fused(amp_median, amp_sum, 1, dtype, B, B, L, k, pmax, min_period, plan, amps, weights, st, true);
 }
 
 static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
@@ -666,7 +666,7 @@ extern "C" int ftn_select_periods(const float* amp_median, const float* amp_sum,
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_select_periods: unsupported dtype %d", dtype);
   (void)scores_ws;   // kept in the signature for ABI stability; the fused tail keeps scores in shared memory
   return launch_select_fused(amp_median, const_cast<float*>(amp_sum), 0, dtype, B, global_batch, L, k, pmax, min_period,
-                             plan, amps, weights, as_stream(stream));
+                             plan, amps, weights, as_stream(stream), false);
 }
 
 extern "C" int ftn_plan_build_host(const int64_t* periods_host, int k, int L, int min_period,

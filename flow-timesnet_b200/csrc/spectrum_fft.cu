@@ -368,11 +368,8 @@ static int fft_launch_one(const T* x, int B, int L, int C, float* amp, float* me
     at[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {
-    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
+  // no programmatic-launch attribute here: this is the first kernel of a search and whatever precedes it in the
+  // stream (a host-to-device copy of x, the caller's kernels) must have completed before it starts
   cfg.attrs = at;
   cfg.numAttrs = na;
   FTN_CUDA(cudaLaunchKernelEx(&cfg, spectrum_fft_kernel<T, KPL>, x, L, C, amp, med, plan));

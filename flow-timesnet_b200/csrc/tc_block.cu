@@ -48,7 +48,8 @@ bool tc_kk_uses_conv4(const FtnInceptionWeights* w) {
 }
 
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row) {
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
+                int period_lo, int period_hi) {
   const bool force_v1 = kk_force(1), force_v2 = kk_force(2);
   FTN_REQUIRE(shared_bias_row < 0 || tc_kk_uses_conv4(w), "tc_kk_stage: the shared input layout needs the tc_conv4 route");
   if (tc_kk_uses_conv4(w)) {
@@ -68,6 +69,8 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
       FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
+    if (period_lo > 0 && tc_conv4_covers(w, L, period_lo, period_hi))   // nothing can be left for the fallback
+      return tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row);
     if (serial) {
       if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
       return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row);
@@ -102,7 +105,7 @@ struct TcTailSpec {          // non-null: finish the block in the fused tail ker
 };
 
 // s1 != nullptr: the first 1x1 stage was already enqueued elsewhere (period_block_tc_s1) with this result
-struct TcS1Done { long long shared_bias_row; };
+struct TcS1Done { long long shared_bias_row; int period_lo, period_hi; };
 static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
                                void* workspace, const TcTailSpec* tail, cudaStream_t st, const TcS1Done* s1 = nullptr);
@@ -144,7 +147,7 @@ int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* pla
 int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
                                 const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                                 const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
-                                int (*search)(void*, cudaStream_t), void* search_ctx) {
+                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi) {
   static cudaStream_t side = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   if (!side) {
@@ -154,7 +157,7 @@ int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPla
     FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
-  TcS1Done s1{-1};
+  TcS1Done s1{-1, period_lo, period_hi};
   FTN_CUDA(cudaEventRecord(ev_fork, st));
   FTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   if (int rc = launch_block_s1(x, B, L, C, nullptr, max_groups, a, act, workspace, side, &s1.shared_bias_row)) return rc;
@@ -178,6 +181,7 @@ static int launch_block_s1(const void* x, int B, int L, int C, const FtnPeriodPl
   s.plan = plan; s.B = B; s.L = L; s.max_groups = max_groups; s.n_tiles = tiles; s.act = act;
   s.a1 = reinterpret_cast<const __nv_bfloat16*>(x); s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in;
   s.K1 = C; s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = reinterpret_cast<__nv_bfloat16*>(workspace); s.ldo = NBa;
+  s.first_in_call = true;
   *shared_bias_row = -1;
   const long long seq_tiles = ((long long)B * L + 127) / 128 + 1;
   if (tc_kk_uses_conv4(a) && seq_tiles <= tiles) {
@@ -217,7 +221,9 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
   // S2
   {
     TimedScope t2(FTN_FAM_KK_A, st);
-    if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st, shared_bias_row)) return rc;
+    if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st, shared_bias_row, s1 ? s1->period_lo : 0,
+                             s1 ? s1->period_hi : 0))
+      return rc;
   }
   static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
   const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
@@ -245,7 +251,11 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
     if (int rc = tc_gemm_launch(s, st)) return rc;
   }
   // S5
-  { TimedScope t4(FTN_FAM_KK_B, st); if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st)) return rc; }
+  {
+    TimedScope t4(FTN_FAM_KK_B, st);
+    if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st, -1, s1 ? s1->period_lo : 0, s1 ? s1->period_hi : 0))
+      return rc;
+  }
   if (tail) {
     // S6 + aggregation + residual + LayerNorm in one kernel: the deltas never reach HBM
     TimedScope t5(FTN_FAM_S6, st);

@@ -290,7 +290,8 @@ extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, c
     int caps[FTN_MAX_BRANCH];
     FTN_REQUIRE(tc_conv4_eligible(w), "ftn_debug_conv_tiled: tc_conv4 not eligible for this block");
     tc_conv4_caps(w, caps);
-    if (int rc = tc_conv4_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream)))
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream),
+                                 -1, false))
       return rc;
     return tc_conv2_launch_filtered(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, caps,
                                     as_stream(stream));
@@ -305,7 +306,8 @@ extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, c
                                     as_stream(stream));
   }
   if (use_tc == 2)
-    return tc_conv2_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream));
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, nullptr,
+                                    as_stream(stream), -1, false);
   if (use_tc)
     return tc_conv_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w, as_stream(stream));
   return simt_conv_tiled_launch(plan, B, L, max_groups, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ld, w,

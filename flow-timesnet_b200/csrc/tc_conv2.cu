@@ -352,7 +352,7 @@ int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
 
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                              __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
-                             long long shared_bias_row) {
+                             long long shared_bias_row, bool dependent) {
   FTN_REQUIRE(tc_conv2_eligible(w), "tc_conv2: unsupported branch shape (mid=%d)", w->mid);
   (void)max_groups;
   TcConv2Args a{};
@@ -385,7 +385,7 @@ int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_gr
     FTN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  FTN_CUDA(launch_pdl(tc_conv2_kernel, dim3(ctas), dim3(C2_THREADS), smem, st, a));
+  FTN_CUDA(launch_pdl(dependent, tc_conv2_kernel, dim3(ctas), dim3(C2_THREADS), smem, st, a));
   FTN_LAUNCH_CHECK("tc_conv2_kernel");
   return 0;
 }

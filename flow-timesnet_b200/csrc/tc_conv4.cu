@@ -59,6 +59,7 @@ struct TcConv4Args {
   long long shared_bias_row;      // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L
   int n_branch;
   int cap_rows[FTN_MAX_BRANCH];   // rows one phase plane of an image buffer can hold
+  int cap_min[FTN_MAX_BRANCH];    // groups needing <= this many rows belong to the previous pass (0: first pass)
   int wstages[FTN_MAX_BRANCH];    // weight stages in shared memory; >= kh: resident, loaded once
   int nbuf[FTN_MAX_BRANCH];       // image buffers (2..C4_NBUF_MAX): a third one takes the loader off the MMA's heels
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
@@ -75,13 +76,13 @@ struct TcConv4Args {
   } while (0)
 
 struct C4Unit {
-  int per, cyc, PW, NB, blocks, O4, rows, b;
+  int per, cyc, PW, NB, blocks, O4, rows, b, hh_eff;
   size_t img_row0;
 };
 
 // per-group geometry, computed once per CTA: the device plan lives in global memory and a decode that re-reads
 // it per image costs ~700 cycles per group visited (L2 latency) in every role of the pipeline
-struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, tile0, rt; };
+struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, tile0, rt, hh_eff; };
 
 __host__ __device__ inline int c4_stage_bytes(int kw) { return 2048 * (kw + 3) + 1536; }
 
@@ -92,6 +93,7 @@ __device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int unit, C
       u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
       u.img_row0 = (size_t)(q.tile0 + unit * q.rt) * 128;
       u.b = unit;
+      u.hh_eff = q.hh_eff;
       return true;
     }
     unit -= q.n_units;
@@ -155,16 +157,25 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
   pdl_wait();   // the plan and the input image are a predecessor's output
   const int G = pl->n_groups;
+  {
+    // nothing for this pass (the usual case for the single-buffer pass): leave before touching TMEM
+    bool any = false;
+    for (int g = 0; g < G; ++g) {
+      const int rows = c4_geometry(pl->grp_period[g], pl->grp_cycles[g], kh, kw).rows;
+      any = any || (rows <= cap && rows > p.cap_min[j]);
+    }
+    if (!any) return;
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid >= 32 && tid < 32 + G) {
     const int g = tid - 32;
     C4Group q;
     q.per = pl->grp_period[g]; q.cyc = pl->grp_cycles[g];
     const C4Geom gm = c4_geometry(q.per, q.cyc, kh, kw);
-    q.PW = gm.PW; q.NB = gm.NB; q.blocks = gm.blocks; q.O4 = gm.O4; q.rows = gm.rows;
-    q.n_units = gm.rows <= cap ? p.B : 0;     // the rest is tc_conv2's
+    q.PW = gm.PW; q.NB = gm.NB; q.blocks = gm.blocks; q.O4 = gm.O4; q.rows = gm.rows; q.hh_eff = gm.hh_eff;
+    q.n_units = (gm.rows <= cap && gm.rows > p.cap_min[j]) ? p.B : 0;     // the rest is another pass's or tc_conv2's
     q.rt = (p.L + pl->grp_pad[g] + 127) / 128;
     int tiles = 0;
     for (int h = 0; h < g; ++h) tiles += (p.L + pl->grp_pad[h] + 127) / 128;
@@ -182,7 +193,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     // shared-memory round trips queue behind the operand fetch of the running MMAs) costs ~1.5 k cycles during which
     // a single issuer leaves the tensor pipe empty (FLOWTIMES_CONV_TRACE: 4.8 k cycles per 3 x 3 image, 3.0 k of MMA).
     const int mw = warp == 0 ? 0 : 1;
-    bool first = true;
+    // one image buffer (second pass): a single issuer.  With two, issuer 0 would wait for image 2 on the barrier
+    // image 1 has not completed yet, and an mbarrier parity cannot tell phase 2 from phase 0.
+    const bool two_issuers = NBUF > 1;
+    uint32_t seen = 0;
     const bool tr = lane == 0 && warp == 0;
     const uint32_t d_hi = (uint32_t)(make_desc_interleaved(0, 0) >> 32);
     const uint32_t a_lo0 = (uint32_t)make_desc_interleaved(smem_u32(s_wring), LBO_W);
@@ -191,7 +205,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     int i = 0;
     uint32_t blk_count = 0, wc = 0;
     for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, u); unit += ctas_of_branch, ++i) {
-      if ((i & 1) != mw) {   // the other issuer's image
+      if (two_issuers ? (i & 1) != mw : mw != 0) {   // the other issuer's image
         blk_count += (uint32_t)u.blocks;
         continue;
       }
@@ -208,11 +222,12 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
         tc_fence_after();
         const uint32_t acc = tmem_base + acc_i * 256;
         uint32_t accum = 0;
-        for (int dr = 0; dr < kh; ++dr, ++wc) {
+        for (int dr = 0; dr < kh; ++dr) {
+          if (dr < hh - u.hh_eff || dr > hh + u.hh_eff) continue;   // only zero padding under this tap row
           // streamed tap rows: this issuer's own ring of S / 2 stages, wc counts its own stages only
           const uint32_t ws = resident ? (uint32_t)dr : (uint32_t)mw * RING + wc % RING;
           if (!resident) mbar_wait(&bars[C4_W_FULL + ws], (wc / RING) & 1u);
-          else if (first) mbar_wait(&bars[C4_W_FULL + ws], 0);
+          else if (!((seen >> dr) & 1u)) { mbar_wait(&bars[C4_W_FULL + ws], 0); seen |= 1u << dr; }   // resident: once per stage
           if (tr) C4_TRACE(3, wc);
           const uint32_t a_lo_s = a_lo0 + ws * (SBA >> 4);
           const int sig0 = (dr - hh) * u.PW - hw + 4 * u.O4;   // >= 0
@@ -231,8 +246,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
             __syncwarp();
           }
           if (tr) C4_TRACE(4, wc);
+          ++wc;
         }
-        first = false;
         if (elect_one()) mma_commit(&bars[C4_ACC_FULL + acc_i]);
         __syncwarp();
         if (tr) C4_TRACE(12, blk_count);
@@ -254,13 +269,16 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
         // is refilled when ITS issuer's MMAs on it have completed (neither issuer ever waits for the other)
         C4Unit ua, ub;
         uint32_t wl[2] = {0, 0};
-        for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, ua); unit += 2 * ctas_of_branch) {
-          const bool vb = c4_decode(s_grp, G, unit + ctas_of_branch, ub);
+        const bool two_issuers = NBUF > 1;       // one image buffer: one issuer, every image on ring 0
+        for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, ua); unit += (two_issuers ? 2 : 1) * ctas_of_branch) {
+          const bool vb = two_issuers && c4_decode(s_grp, G, unit + ctas_of_branch, ub);
           const int na = ua.blocks * kh, nb = vb ? ub.blocks * kh : 0;
           for (int k = 0; k < (na > nb ? na : nb); ++k) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               if (k >= (r ? nb : na)) continue;
+              const int he = r ? ub.hh_eff : ua.hh_eff, dr = k % kh;
+              if (dr < hh - he || dr > hh + he) continue;     // the issuer skips this tap row too
               const uint32_t ws = (uint32_t)r * RING + wl[r] % RING;
               mbar_wait_relaxed(&bars[C4_W_EMPTY + ws], ((wl[r] / RING) & 1u) ^ 1u);
               if (r == 0) C4_TRACE(9, wl[0]);
@@ -395,8 +413,11 @@ static int conv4_nbuf(const FtnInceptionWeights* w, int j) {
   return conv4_img_budget(w, j) / 3 / (C4_NCHUNK * 4 * 16) >= 200 ? 3 : 2;
 }
 
-static int conv4_cap_rows(const FtnInceptionWeights* w, int j) {
-  long long rows = conv4_img_budget(w, j) / conv4_nbuf(w, j) / (C4_NCHUNK * 4 * 16);
+// pass 0: 2-3 image buffers (loads overlap the MMAs); pass 1: ONE buffer of the whole image area for the groups whose
+// padded image is too long for pass 0 (few-cycle periods: p = L - 1 has a 2 x (L - 1) grid) -- no overlap, but the
+// alternative is tc_conv2 at a fraction of the MMA rate (190 us for one such group at the elec shape)
+static int conv4_cap_rows(const FtnInceptionWeights* w, int j, int pass = 0) {
+  long long rows = conv4_img_budget(w, j) / (pass ? 1 : conv4_nbuf(w, j)) / (C4_NCHUNK * 4 * 16);
   if (rows > 4000) rows = 4000;      // LBO field of the descriptor: 64 * rows < 256 KB
   return rows < 0 ? 0 : (int)rows;
 }
@@ -406,17 +427,44 @@ bool tc_conv4_eligible(const FtnInceptionWeights* w) {
   if (!tc_conv2_eligible(w)) return false;   // groups that do not fit are delegated to tc_conv2
   for (int j = 0; j < w->n_branch; ++j) {
     if (!w->w_kk_phase[j] || !(w->kh[j] & 1) || !(w->kw[j] & 1)) return false;
-    if (!c4_group_fits(1, 64, w->kh[j], w->kw[j], conv4_cap_rows(w, j))) return false;   // pointless otherwise
+    if (!c4_group_fits(8, 8, w->kh[j], w->kw[j], conv4_cap_rows(w, j))) return false;   // pointless otherwise
   }
   return true;
 }
 
-void tc_conv4_caps(const FtnInceptionWeights* w, int* caps) {
-  for (int j = 0; j < w->n_branch; ++j) caps[j] = -conv4_cap_rows(w, j);   // negative: tc_conv2 applies c4_group_fits
+// does tc_conv4 (either pass) take every period in [lo, hi] at sequence length L?  (cached: called per launch)
+bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int lo, int hi) {
+  static int c_L = -1, c_lo = -1, c_hi = -1, c_sig = -1, c_ans = 0;
+  int sig = w->n_branch;
+  for (int j = 0; j < w->n_branch; ++j) sig = sig * 131 + w->kh[j] * 16 + w->kw[j];
+  if (L == c_L && lo == c_lo && hi == c_hi && sig == c_sig) return c_ans != 0;
+  bool ok = lo >= 1 && hi >= lo;
+  for (int j = 0; ok && j < w->n_branch; ++j) {
+    const int cap = conv4_cap_rows(w, j, 1);
+    for (int p = lo; ok && p <= hi; ++p) ok = c4_group_fits(p, (L + p - 1) / p, w->kh[j], w->kw[j], cap);
+  }
+  c_L = L; c_lo = lo; c_hi = hi; c_sig = sig; c_ans = ok;
+  return ok;
 }
 
+void tc_conv4_caps(const FtnInceptionWeights* w, int* caps) {
+  for (int j = 0; j < w->n_branch; ++j) caps[j] = -conv4_cap_rows(w, j, 1);   // negative: tc_conv2 applies c4_group_fits
+}
+
+static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st,
+                             long long shared_bias_row, bool dependent, int pass);
+
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row) {
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
+                    bool dependent) {
+  if (int rc = conv4_launch_pass(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, dependent, 0)) return rc;
+  return conv4_launch_pass(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, true, 1);
+}
+
+static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
+                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st,
+                             long long shared_bias_row, bool dependent, int pass) {
   FTN_REQUIRE(tc_conv4_eligible(w), "tc_conv4: unsupported branch shape (mid=%d)", w->mid);
   TcConv4Args a{};
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.n_branch = w->n_branch;
@@ -425,9 +473,10 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   // hand-over; a branch with few MMAs is bound by its image loader instead (measured, FLOWTIMES_CONV_TRACE)
   long long cost[FTN_MAX_BRANCH];
   for (int j = 0; j < w->n_branch; ++j) {
-    a.cap_rows[j] = conv4_cap_rows(w, j);
+    a.cap_rows[j] = conv4_cap_rows(w, j, pass);
+    a.cap_min[j] = pass ? conv4_cap_rows(w, j, 0) : 0;
     a.wstages[j] = conv4_wstages(w, j);
-    a.nbuf[j] = conv4_nbuf(w, j);
+    a.nbuf[j] = pass ? 1 : conv4_nbuf(w, j);
     a.kh[j] = w->kh[j]; a.kw[j] = w->kw[j];
     a.w[j] = (const uint8_t*)w->w_kk_phase[j];
     a.bias[j] = w->b_kk[j];
@@ -462,7 +511,7 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   constexpr int kTraceWords = 2 * 16 * 256 + 256;
   if (trace_path && !trace_dev) cudaMalloc(&trace_dev, kTraceWords * sizeof(long long));
   if (trace_dev) { cudaMemsetAsync(trace_dev, 0, kTraceWords * sizeof(long long), st); a.trace = trace_dev; }
-  FTN_CUDA(launch_pdl(tc_conv4_kernel, dim3(ctas), dim3(C4_THREADS), smem, st, a));
+  FTN_CUDA(launch_pdl(dependent, tc_conv4_kernel, dim3(ctas), dim3(C4_THREADS), smem, st, a));
   FTN_LAUNCH_CHECK("tc_conv4_kernel");
   if (trace_dev) {   // debug only (synchronises): "cta event index clock"
     cudaStreamSynchronize(st);

@@ -33,6 +33,7 @@ struct TcGemmArgs {
   const __nv_bfloat16* res_ptr; int res_ld;   // TC_RES_SEQ: x (ld = C); TC_RES_POS: tile-major tensor
   __nv_bfloat16* out; int ldo;                // PLAIN / BLOCK_A: tile-major; DELTA: delta base
   const __nv_bfloat16* x; int C;              // DELTA: grid to subtract
+  bool first_in_call;                         // first kernel of an API call: plain launch, no programmatic dependency
 };
 
 int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st);
@@ -63,7 +64,7 @@ int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                              __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
-                             long long shared_bias_row = -1);
+                             long long shared_bias_row = -1, bool dependent = true);
 // does tc_conv3 take a group of period `per` for a kh x kw branch whose image buffer holds `cap` rows?
 __host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) {
   const int hw = kw / 2, hh = kh / 2, PW = per + 2 * hw;
@@ -73,7 +74,7 @@ __host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) 
 
 // "output phases on M" variant (tc_conv4.cu): 4 phases x 32 channels on M, no cross-quadrant reduction in the
 // drain; whole images only, groups whose padded image does not fit go to tc_conv2
-struct C4Geom { int PW, QT, blocks, NB, O4, rows; };
+struct C4Geom { int PW, QT, blocks, NB, O4, rows, hh_eff; };
 __host__ __device__ inline C4Geom c4_geometry(int per, int cyc, int kh, int kw) {
   C4Geom g;
   const int hw = kw / 2, hh = kh / 2;
@@ -82,8 +83,11 @@ __host__ __device__ inline C4Geom c4_geometry(int per, int cyc, int kh, int kw) 
   const int nc = (g.QT + 3) / 4;                       // accumulator columns: 4 positions each
   g.blocks = (nc + 255) / 256;
   g.NB = (((nc + g.blocks - 1) / g.blocks) + 15) & ~15;
-  g.O4 = (hh * g.PW + hw + 3) / 4;                     // plane rows in front of the image origin
-  const int max_beta = 4 * (g.blocks * g.NB - 1) + (kw + 2) + hh * g.PW - hw + 4 * g.O4;
+  // tap rows further than cycles - 1 from the centre only ever see zero padding: they are skipped, and the halo
+  // the image buffer has to hold shrinks with them (long periods have few cycles: p = 168 at L = 336 has 2)
+  g.hh_eff = hh < cyc - 1 ? hh : (cyc > 1 ? cyc - 1 : 0);
+  g.O4 = (g.hh_eff * g.PW + hw + 3) / 4;               // plane rows in front of the image origin
+  const int max_beta = 4 * (g.blocks * g.NB - 1) + (kw + 2) + g.hh_eff * g.PW - hw + 4 * g.O4;
   g.rows = (max_beta >> 2) + 1;                        // rows per phase plane the MMAs may touch
   return g;
 }
@@ -93,14 +97,19 @@ __host__ __device__ inline bool c4_group_fits(int per, int cyc, int kh, int kw, 
 bool tc_conv4_eligible(const FtnInceptionWeights* w);
 void tc_conv4_caps(const FtnInceptionWeights* w, int* caps);   // negated capacities for tc_conv2_launch_filtered
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1);
+                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1,
+                    bool dependent = true);   // dependent: the previous kernel in the stream is one of this library's
 
 // picks tc_conv4 / tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
 // shared_bias_row >= 0: `in` is NOT tile-major but one copy per window, row b * L + t for t < L, and row
 // `shared_bias_row` stands for every padded step t >= L (the first 1x1 stage does not depend on the period, so
 // block A's k x k input is computed once instead of once per group); only the tc_conv4 route takes it
+// period_lo / period_hi (> 0): the plan comes from this library's own search, whose periods lie in that range; if
+// tc_conv4 takes every one of them the tc_conv2 fallback is not launched at all
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1);
+                __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1,
+                int period_lo = 0, int period_hi = 0);
+bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int period_lo, int period_hi);
 bool tc_kk_uses_conv4(const FtnInceptionWeights* w);
 
 // fused tail (tc_tail.cu): last 1x1 stage + weighted aggregation + residual + LayerNorm

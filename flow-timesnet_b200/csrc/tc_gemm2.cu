@@ -280,8 +280,8 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   }
   const int worst = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   const int grid = worst < sm_count() ? worst : sm_count();
-  if (ai) FTN_CUDA(launch_pdl(tc_gemm2_kernel<1>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
-  else FTN_CUDA(launch_pdl(tc_gemm2_kernel<0>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
+  if (ai) FTN_CUDA(launch_pdl(!a.first_in_call, tc_gemm2_kernel<1>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
+  else FTN_CUDA(launch_pdl(!a.first_in_call, tc_gemm2_kernel<0>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
   FTN_LAUNCH_CHECK("tc_gemm2_kernel");
   return 0;
 }

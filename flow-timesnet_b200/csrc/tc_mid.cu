@@ -497,8 +497,8 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   }
   const int worst = tc_worst_case_tiles(B, L, max_groups);
   const int grid = worst < sm_count() ? worst : sm_count();
-  if (ai) FTN_CUDA(launch_pdl(tc_mid_kernel<1>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
-  else FTN_CUDA(launch_pdl(tc_mid_kernel<0>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
+  if (ai) FTN_CUDA(launch_pdl(true, tc_mid_kernel<1>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
+  else FTN_CUDA(launch_pdl(true, tc_mid_kernel<0>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));
   FTN_LAUNCH_CHECK("tc_mid_kernel");
   if (trace_dev) {   // debug only: dump the timeline of CTA 0 (synchronises!)
     cudaStreamSynchronize(st);

@@ -375,8 +375,8 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   }
   const int items = B * ((L + TL_BM - 1) / TL_BM);
   const int grid = items < sm_count() ? items : sm_count();
-  if (ai) FTN_CUDA(launch_pdl(tc_tail_kernel<1>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
-  else FTN_CUDA(launch_pdl(tc_tail_kernel<0>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
+  if (ai) FTN_CUDA(launch_pdl(true, tc_tail_kernel<1>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
+  else FTN_CUDA(launch_pdl(true, tc_tail_kernel<0>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
   FTN_LAUNCH_CHECK("tc_tail_kernel");
   return 0;
 }
