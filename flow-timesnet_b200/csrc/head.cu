@@ -91,6 +91,12 @@ sgemm_kernel(const float* __restrict__ A, int lda, long long strideA, const TB* 
         const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][TM / 2 + ty * 4]);
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
         a[RH + 0] = a1.x; a[RH + 1] = a1.y; a[RH + 2] = a1.z; a[RH + 3] = a1.w;
+      } else if (RH != 2) {                               // odd row counts (TM = 160): scalar loads, all broadcasts
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+          a[i] = As[buf][k][ty * RH + i];
+          a[RH + i] = As[buf][k][TM / 2 + ty * RH + i];
+        }
       } else {
         const float2 a0 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
         const float2 a1 = *reinterpret_cast<const float2*>(&As[buf][k][TM / 2 + ty * 2]);
@@ -125,12 +131,23 @@ sgemm_kernel(const float* __restrict__ A, int lda, long long strideA, const TB* 
   }
 }
 
-// TM = 64 when 128-row tiles would leave SMs idle (few rows per batch entry)
+// Tile height by wave efficiency: the number of tiles against the CTA slots of the last wave decides more than the
+// per-tile efficiency (embedding at the elec shape: 168 tiles of 128 rows are 2 waves on 148 SMs, 135 tiles of 160
+// rows are one).  TM = 64 runs two CTAs per SM.
 template <typename TB, bool TRANS_B>
 static void sgemm_launch(const float* A, int lda, long long sA, const TB* Bm, int ldb, long long sB, float* C, int ldc,
                          long long sC, int M, int N, int K, int batch, const float* bias, int bias_mode, cudaStream_t st) {
-  const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * batch;
-  if (tiles128 >= sm_count() && M >= 96) {
+  const long long sms = sm_count(), nt = (long long)((N + 127) / 128) * batch;
+  auto eff = [&](int tm, int per_sm, double w) {
+    const long long tiles = (long long)((M + tm - 1) / tm) * nt, slots = sms * per_sm;
+    const double useful = (double)M / ((double)((M + tm - 1) / tm) * tm);          // padding rows of the last tile
+    return w * useful * (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
+  };
+  const double e64 = eff(64, 2, 0.85), e128 = eff(128, 1, 1.0), e160 = eff(160, 1, 1.0);
+  if (e160 > e128 && e160 > e64) {
+    dim3 grid((N + 127) / 128, (M + 159) / 160, batch);
+    sgemm_kernel<TB, TRANS_B, 160><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+  } else if (e128 >= e64) {
     dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
     sgemm_kernel<TB, TRANS_B, 128><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
   } else {
@@ -196,14 +213,15 @@ __global__ void nb_epilogue_kernel(float* __restrict__ rate, float* __restrict__
                                    const float* __restrict__ hist, const float* __restrict__ late,
                                    const float* __restrict__ late_gate, const float* __restrict__ floor_n,
                                    int B, int steps, int N, int32_t* __restrict__ flags) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * steps * N;
+  // blockIdx.y = (window, step), threads along the series axis: no per-element 64-bit division (the flat-index form
+  // spent most of its 22 us in two emulated long-long divides per element)
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   int bad = 0;
-  if (i < total) {
-    int n = (int)(i % N);
-    long long bh = i / N;
-    int h = (int)(bh % steps);
-    long long b = bh / steps;
+  for (long long bh = blockIdx.y; bh < (long long)B * steps; bh += gridDim.y) {
+    if (n >= N) break;
+    const int h = (int)(bh % steps);
+    const long long b = bh / steps;
+    const long long i = bh * N + n;
     float pre = rate[i] + hist[i];                                      // mu_head(h) + history_tail (:2079)
     if (late) pre += late_gate[h] * late[((size_t)b * N + n) * steps + h];   // gate * bias^T (:2041-2047)
     float r = softplus20(pre) + 1e-6f;                                  // :2081-2085
@@ -351,8 +369,9 @@ extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int 
   const int M = B * steps;
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wmu, C, 0, rate, N, 0, M, N, C, 1, true, bmu, 1, st)) return rc;
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wsg, C, 0, disp, N, 0, M, N, C, 1, true, bsg, 1, st)) return rc;
-  long long total = (long long)M * N;
-  nb_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B, steps, N, flags);
+  const long long rows = (long long)M;
+  dim3 egrid((N + 255) / 256, (unsigned)(rows < 65535 ? rows : 65535));
+  nb_epilogue_kernel<<<egrid, 256, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B, steps, N, flags);
   FTN_LAUNCH_CHECK("nb_epilogue_kernel");
   return 0;
 }

@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     const int r_first = lt >> 2;                      // first beta of this thread; the step keeps its phase plane
     C4Unit u;
     int i = 0;
+    uint4 padv = make_uint4(0, 0, 0, 0);     // this thread's 16 bytes of the row that stands for every padded step
+    if (p.shared_bias_row >= 0)
+      padv = *reinterpret_cast<const uint4*>(p.in + (size_t)p.shared_bias_row * p.ld + j * C4_MID + c * 8);
     for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, u); unit += ctas_of_branch, ++i) {
       const uint32_t buf = (uint32_t)i % NBUF;
       mbar_wait_relaxed(&bars[C4_IMG_EMPTY + buf], (((uint32_t)i / NBUF) & 1u) ^ 1u);
@@ -304,7 +307,6 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
       uint32_t dst = smem_u32(s_buf0 + buf * BUF_BYTES) + c * LBO_B + (uint32_t)(r_first & 3) * PH + (uint32_t)(r_first >> 2) * 16;
       const bool shared = p.shared_bias_row >= 0;
       const __nv_bfloat16* img = p.in + (shared ? (size_t)u.b * p.L : u.img_row0) * p.ld + j * C4_MID + c * 8;
-      const __nv_bfloat16* pad_row = p.in + (size_t)(shared ? p.shared_bias_row : 0) * p.ld + j * C4_MID + c * 8;
       const int t_lim = shared ? p.L : 0x7fffffff;
       const int K = hh + 4;                           // shift that keeps the dividend non-negative
       const int qs = r_first - 4 * u.O4 + K * u.PW;
@@ -318,8 +320,14 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
       for (int beta = r_first; beta < n_beta; beta += C4_LSTEP) {
         const bool ok = rr >= 0 && rr < u.cyc && wq >= hw && wq < hw + u.per;
         const int tt = rr * u.per + wq - hw;
-        const __nv_bfloat16* src = ok ? (tt < t_lim ? img + (size_t)tt * p.ld : pad_row) : img;
-        cp_async16(dst, src, ok ? 16u : 0u);
+        if (ok && tt >= t_lim) {
+          // padded step of the once-per-window input: every such position holds the same row.  Reading it from
+          // global memory makes all SMs hammer one L2 line (a p = L - 1 group is half padding: 86 us instead of 26)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(padv.x), "r"(padv.y), "r"(padv.z), "r"(padv.w)
+                       : "memory");
+        } else {
+          cp_async16(dst, ok ? img + (size_t)tt * p.ld : img, ok ? 16u : 0u);
+        }
         dst += C4_LSTEP * 4;
         rr += step_r;
         wq += step_w;
