@@ -143,7 +143,8 @@ static void sgemm_launch(const float* A, int lda, long long sA, const TB* Bm, in
     const double useful = (double)M / ((double)((M + tm - 1) / tm) * tm);          // padding rows of the last tile
     return w * useful * (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
   };
-  const double e64 = eff(64, 2, 0.85), e128 = eff(128, 1, 1.0), e160 = eff(160, 1, 1.0);
+  double e64 = eff(64, 2, 0.85), e128 = eff(128, 1, 1.0), e160 = eff(160, 1, 1.0);
+  if ((long long)((M + 127) / 128) * nt < sms) e64 = 2.0;   // fewer big tiles than SMs: latency-bound, take the most CTAs
   if (e160 > e128 && e160 > e64) {
     dim3 grid((N + 127) / 128, (M + 159) / 160, batch);
     sgemm_kernel<TB, TRANS_B, 160><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
@@ -213,23 +214,23 @@ __global__ void nb_epilogue_kernel(float* __restrict__ rate, float* __restrict__
                                    const float* __restrict__ hist, const float* __restrict__ late,
                                    const float* __restrict__ late_gate, const float* __restrict__ floor_n,
                                    int B, int steps, int N, int32_t* __restrict__ flags) {
-  // blockIdx.y = (window, step), threads along the series axis: no per-element 64-bit division (the flat-index form
-  // spent most of its 22 us in two emulated long-long divides per element)
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  // one (window, step) row per block, threads stride over the series axis: no per-element 64-bit division, and
+  // N = 321 fills 128-thread blocks to 84 % (the flat-index form spent its time in two long-long divides per element)
   int bad = 0;
-  for (long long bh = blockIdx.y; bh < (long long)B * steps; bh += gridDim.y) {
-    if (n >= N) break;
+  for (long long bh = blockIdx.x; bh < (long long)B * steps; bh += gridDim.x) {
     const int h = (int)(bh % steps);
     const long long b = bh / steps;
-    const long long i = bh * N + n;
-    float pre = rate[i] + hist[i];                                      // mu_head(h) + history_tail (:2079)
-    if (late) pre += late_gate[h] * late[((size_t)b * N + n) * steps + h];   // gate * bias^T (:2041-2047)
-    float r = softplus20(pre) + 1e-6f;                                  // :2081-2085
-    float d = softplus20(disp[i]) + floor_n[n] + 1e-6f;                 // :2088-2093
-    rate[i] = r;
-    disp[i] = d;
-    if (!isfinite(r) || r <= 0.f) bad |= 1;                             // :2094
-    if (!isfinite(d) || d <= 0.f) bad |= 2;                             // :2096
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const long long i = bh * N + n;
+      float pre = rate[i] + hist[i];                                      // mu_head(h) + history_tail (:2079)
+      if (late) pre += late_gate[h] * late[((size_t)b * N + n) * steps + h];   // gate * bias^T (:2041-2047)
+      float r = softplus20(pre) + 1e-6f;                                  // :2081-2085
+      float d = softplus20(disp[i]) + floor_n[n] + 1e-6f;                 // :2088-2093
+      rate[i] = r;
+      disp[i] = d;
+      if (!isfinite(r) || r <= 0.f) bad |= 1;                             // :2094
+      if (!isfinite(d) || d <= 0.f) bad |= 2;                             // :2096
+    }
   }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
@@ -370,8 +371,8 @@ extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int 
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wmu, C, 0, rate, N, 0, M, N, C, 1, true, bmu, 1, st)) return rc;
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wsg, C, 0, disp, N, 0, M, N, C, 1, true, bsg, 1, st)) return rc;
   const long long rows = (long long)M;
-  dim3 egrid((N + 255) / 256, (unsigned)(rows < 65535 ? rows : 65535));
-  nb_epilogue_kernel<<<egrid, 256, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B, steps, N, flags);
+  nb_epilogue_kernel<<<(unsigned)(rows < (1 << 20) ? rows : (1 << 20)), 128, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B,
+                                                                                    steps, N, flags);
   FTN_LAUNCH_CHECK("nb_epilogue_kernel");
   return 0;
 }
