@@ -59,7 +59,9 @@ struct TcConv4Args {
   long long shared_bias_row;      // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L
   int n_branch;
   int cap_rows[FTN_MAX_BRANCH];   // rows one phase plane of an image buffer can hold
-  int cap_min[FTN_MAX_BRANCH];    // groups needing <= this many rows belong to the previous pass (0: first pass)
+  int cap_rows1[FTN_MAX_BRANCH];  // the same for the single-buffer CTAs (second half of the grid)
+  int n_ctas0;                    // CTAs [0, n_ctas0): 2-3 image buffers; [n_ctas0, 2 n_ctas0): ONE buffer for the groups
+                                  // whose padded image is too long for those (usually none: these CTAs leave at once)
   int wstages[FTN_MAX_BRANCH];    // weight stages in shared memory; >= kh: resident, loaded once
   int nbuf[FTN_MAX_BRANCH];       // image buffers (2..C4_NBUF_MAX): a third one takes the loader off the MMA's heels
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
@@ -71,7 +73,7 @@ struct TcConv4Args {
 
 #define C4_TRACE(ev, n)                                                                                          \
   do {                                                                                                          \
-    if (p.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (n) < 256)                                \
+    if (p.trace && (blockIdx.x == 0 || (int)blockIdx.x == p.n_ctas0 - 1) && (n) < 256)                           \
       p.trace[(blockIdx.x ? 16 * 256 : 0) + (ev) * 256 + (n)] = clock64();                                       \
   } while (0)
 
@@ -117,14 +119,17 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
   const long long t_start = clock64();
   pdl_trigger();
 
+  const int pass = (int)blockIdx.x >= p.n_ctas0 ? 1 : 0;
+  const int bx = (int)blockIdx.x - pass * p.n_ctas0;
   int j = 0;
-  while (j + 1 < p.n_branch && (int)blockIdx.x >= p.cta_begin[j + 1]) ++j;
-  const int cta_in_branch = blockIdx.x - p.cta_begin[j];
+  while (j + 1 < p.n_branch && bx >= p.cta_begin[j + 1]) ++j;
+  const int cta_in_branch = bx - p.cta_begin[j];
   const int ctas_of_branch = p.cta_begin[j + 1] - p.cta_begin[j];
   const int kh = p.kh[j], kw = p.kw[j], hw = kw / 2, hh = kh / 2;
-  const int cap = p.cap_rows[j];
+  const int cap = pass ? p.cap_rows1[j] : p.cap_rows[j];
+  const int cap_min = pass ? p.cap_rows[j] : 0;     // groups needing <= this many rows belong to the first pass
   const int S = p.wstages[j];
-  const uint32_t NBUF = (uint32_t)p.nbuf[j];
+  const uint32_t NBUF = pass ? 1u : (uint32_t)p.nbuf[j];
   const uint32_t RING = (uint32_t)S / 2;           // streamed branches: stages per MMA issuer
   const bool resident = S >= kh;
   const uint32_t SB = (uint32_t)c4_stage_bytes(kw);
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     bool any = false;
     for (int g = 0; g < G; ++g) {
       const int rows = c4_geometry(pl->grp_period[g], pl->grp_cycles[g], kh, kw).rows;
-      any = any || (rows <= cap && rows > p.cap_min[j]);
+      any = any || (rows <= cap && rows > cap_min);
     }
     if (!any) return;
   }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     q.per = pl->grp_period[g]; q.cyc = pl->grp_cycles[g];
     const C4Geom gm = c4_geometry(q.per, q.cyc, kh, kw);
     q.PW = gm.PW; q.NB = gm.NB; q.blocks = gm.blocks; q.O4 = gm.O4; q.rows = gm.rows; q.hh_eff = gm.hh_eff;
-    q.n_units = (gm.rows <= cap && gm.rows > p.cap_min[j]) ? p.B : 0;     // the rest is another pass's or tc_conv2's
+    q.n_units = (gm.rows <= cap && gm.rows > cap_min) ? p.B : 0;     // the rest is another pass's or tc_conv2's
     q.rt = (p.L + pl->grp_pad[g] + 127) / 128;
     int tiles = 0;
     for (int h = 0; h < g; ++h) tiles += (p.L + pl->grp_pad[h] + 127) / 128;
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace && tid == 0 && blockIdx.x < 256) p.trace[2 * 16 * 256 + blockIdx.x] = ((long long)j << 32) | (clock64() - t_start);
+  if (p.trace && tid == 0 && !pass && blockIdx.x < 256) p.trace[2 * 16 * 256 + blockIdx.x] = ((long long)j << 32) | (clock64() - t_start);
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -459,20 +464,9 @@ void tc_conv4_caps(const FtnInceptionWeights* w, int* caps) {
   for (int j = 0; j < w->n_branch; ++j) caps[j] = -conv4_cap_rows(w, j, 1);   // negative: tc_conv2 applies c4_group_fits
 }
 
-static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st,
-                             long long shared_bias_row, bool dependent, int pass);
-
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
                     bool dependent) {
-  if (int rc = conv4_launch_pass(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, dependent, 0)) return rc;
-  return conv4_launch_pass(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, true, 1);
-}
-
-static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                             __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st,
-                             long long shared_bias_row, bool dependent, int pass) {
   FTN_REQUIRE(tc_conv4_eligible(w), "tc_conv4: unsupported branch shape (mid=%d)", w->mid);
   TcConv4Args a{};
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.n_branch = w->n_branch;
@@ -481,10 +475,10 @@ static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_gr
   // hand-over; a branch with few MMAs is bound by its image loader instead (measured, FLOWTIMES_CONV_TRACE)
   long long cost[FTN_MAX_BRANCH];
   for (int j = 0; j < w->n_branch; ++j) {
-    a.cap_rows[j] = conv4_cap_rows(w, j, pass);
-    a.cap_min[j] = pass ? conv4_cap_rows(w, j, 0) : 0;
+    a.cap_rows[j] = conv4_cap_rows(w, j, 0);
+    a.cap_rows1[j] = conv4_cap_rows(w, j, 1);
     a.wstages[j] = conv4_wstages(w, j);
-    a.nbuf[j] = pass ? 1 : conv4_nbuf(w, j);
+    a.nbuf[j] = conv4_nbuf(w, j);
     a.kh[j] = w->kh[j]; a.kw[j] = w->kw[j];
     a.w[j] = (const uint8_t*)w->w_kk_phase[j];
     a.bias[j] = w->b_kk[j];
@@ -508,7 +502,10 @@ static int conv4_launch_pass(const FtnPeriodPlan* plan, int B, int L, int max_gr
   }
   a.cta_begin[0] = 0;
   for (int j = 0; j < w->n_branch; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + n_cta[j];
-  const int ctas = a.cta_begin[w->n_branch];
+  a.n_ctas0 = a.cta_begin[w->n_branch];
+  // second half of the grid: the same branch split with ONE image buffer per CTA.  Those CTAs are placed as the
+  // first half leaves, find (almost always) nothing to do and return; a separate launch for them cost ~3 us
+  const int ctas = 2 * a.n_ctas0;
   static size_t attr = 0;
   if (smem > attr) {
     FTN_CUDA(cudaFuncSetAttribute(tc_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
