@@ -435,3 +435,42 @@ def test_fused_block_route_equals_unfused_route(with_ln):
         f, u = fused.float(), unfused.float()
         assert torch.allclose(f, u, rtol=2 ** -7, atol=1e-6)
         assert (f != u).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["white", "planted"])
+def test_timesblock_forward_equals_search_plus_fused(kind):
+    """ftn_timesblock_forward (search + block in one call, first 1x1 stage forked beside the selection kernel) returns
+    the bits of ftn_period_search followed by ftn_timesblock_fused, and the same plan.  The planted input selects
+    p = L - 1 (two cycles), which takes tc_conv4's single-buffer CTAs."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.models.timesnet import TimesBlock
+    wl = syn.WORKLOADS["elec"]
+    B = 6
+    torch.manual_seed(0)
+    blk = TimesBlock(wl.d_model, [list(k) for k in wl.kernel_set], 0.0, "gelu", d_ff=wl.ff,
+                     bottleneck_ratio=wl.bottleneck_ratio).cuda()
+    feats = syn.white_features if kind == "white" else syn.planted_features
+    x = feats(B, wl.T, wl.d_model, seed=7).to(torch.bfloat16).cuda()
+    if kind == "planted":
+        x = x + torch.linspace(0.0, 4.0, wl.T, device="cuda").view(1, -1, 1).to(torch.bfloat16)   # a trend: bin 1
+    from timesnet_forecast.models.timesnet import FFTPeriodSelector
+    object.__setattr__(blk, "period_selector", FFTPeriodSelector(wl.k_periods, wl.T, 1))
+    blk(x)                                                       # lazy build
+    pa, pb = blk.inception[0].packed(x.device), blk.inception[2].packed(x.device)
+    k = wl.k_periods
+    ln_w = (1.0 + 0.1 * torch.randn(wl.d_model)).cuda()
+    ln_b = (0.1 * torch.randn(wl.d_model)).cuda()
+    res = nv.timesblock_forward(x, k, wl.T, 1, pa.struct, pb.struct, nv.FTN_ACT_GELU, ln_w, ln_b, 1e-5)
+    assert res is not None, "elec shape must be eligible for the combined call"
+    out, plan, amps, weights = res
+    plan2, amps2, weights2, _, _ = nv.period_search(x, k, wl.T, 1)
+    ws = torch.empty(nv.inception_workspace_bytes(B, wl.T, k, pa.struct, pb.struct), dtype=torch.uint8, device="cuda")
+    out2 = torch.empty_like(x)
+    assert nv.timesblock_fused(x, plan2, k, pa.struct, pb.struct, nv.FTN_ACT_GELU, weights2, ln_w, ln_b, 1e-5, out2, ws)
+    torch.cuda.synchronize()
+    # (the last 4 of the 808 plan bytes are struct padding)
+    assert torch.equal(plan[:804], plan2[:804]) and torch.equal(amps, amps2) and torch.equal(weights, weights2)
+    assert torch.equal(out, out2)
+    host = nv.plan_to_host(plan)
+    if kind == "planted":
+        assert max(host.grp_period[: host.n_groups]) >= wl.T // 2, list(host.grp_period[: host.n_groups])
