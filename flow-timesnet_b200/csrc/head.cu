@@ -91,7 +91,7 @@ sgemm_kernel(const float* __restrict__ A, int lda, long long strideA, const TB* 
         const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][TM / 2 + ty * 4]);
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
         a[RH + 0] = a1.x; a[RH + 1] = a1.y; a[RH + 2] = a1.z; a[RH + 3] = a1.w;
-      } else if (RH != 2) {                               // odd row counts (TM = 160): scalar loads, all broadcasts
+      } else if (RH != 2) {                               // other row counts (TM = 160, 32): scalar loads, all broadcasts
 #pragma unroll
         for (int i = 0; i < RH; ++i) {
           a[i] = As[buf][k][ty * RH + i];
@@ -144,7 +144,14 @@ static void sgemm_launch(const float* A, int lda, long long sA, const TB* Bm, in
     return w * useful * (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
   };
   double e64 = eff(64, 2, 0.85), e128 = eff(128, 1, 1.0), e160 = eff(160, 1, 1.0);
-  if ((long long)((M + 127) / 128) * nt < sms) e64 = 2.0;   // fewer big tiles than SMs: latency-bound, take the most CTAs
+  if ((long long)((M + 127) / 128) * nt < sms) {            // fewer big tiles than SMs: latency-bound, take the most CTAs
+    e64 = 2.0;
+    if ((long long)((M + 63) / 64) * nt < sms) {            // still under one CTA per SM (time projection: 96 x 128 per window)
+      dim3 grid((N + 127) / 128, (M + 31) / 32, batch);
+      sgemm_kernel<TB, TRANS_B, 32><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
+      return;
+    }
+  }
   if (e160 > e128 && e160 > e64) {
     dim3 grid((N + 127) / 128, (M + 159) / 160, batch);
     sgemm_kernel<TB, TRANS_B, 160><<<grid, 256, 0, st>>>(A, lda, sA, Bm, ldb, sB, C, ldc, sC, M, N, K, bias, bias_mode);
