@@ -474,3 +474,20 @@ def test_timesblock_forward_equals_search_plus_fused(kind):
     host = nv.plan_to_host(plan)
     if kind == "planted":
         assert max(host.grp_period[: host.n_groups]) >= wl.T // 2, list(host.grp_period[: host.n_groups])
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (33, 17, 64), (97, 128, 129), (200, 321, 128), (1000, 96, 321), (6144, 128, 321),
+                                   (21504, 321, 128), (150, 7, 300)])
+def test_linear_matches_fp32_matmul(M, K, N):
+    """ftn_linear (the register-blocked fp32 SIMT GEMM of the embedding / head layers; every tile height and the
+    ragged edges) against torch's fp32 matmul."""
+    from timesnet_forecast import _native as nv
+    g = torch.Generator().manual_seed(M * 7 + K * 3 + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / max(1.0, K ** 0.5)
+    b = torch.randn(N, generator=g)
+    out = nv.linear(a.cuda(), w.cuda(), b.cuda())
+    ref = (a.double() @ w.double().t() + b.double()).float()
+    assert _rel(out, ref) < 2e-6
+    out = nv.linear(a.cuda(), w.cuda(), None)
+    assert _rel(out, (a.double() @ w.double().t()).float()) < 2e-6
