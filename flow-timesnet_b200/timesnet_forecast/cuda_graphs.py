@@ -79,15 +79,18 @@ class PipelinedRunner:
         dev = example_inputs[0].device
         self._graphs = [GraphedCallable(fn, example_inputs) for _ in range(depth)]
         self._copy = torch.cuda.Stream(device=dev)
+        self._back = torch.cuda.Stream(device=dev)                     # result read-back: off the compute stream, so the
+                                                                       # next replay does not queue behind a DMA round trip
         self._filled = [torch.cuda.Event() for _ in range(depth)]      # inputs of slot s are on the device
         self._consumed = [torch.cuda.Event() for _ in range(depth)]    # slot s's replay has read its inputs
+        self._read = [torch.cuda.Event() for _ in range(depth)]        # slot s's result is in its host buffer
         out = self._graphs[0]._static_out
         if not isinstance(out, torch.Tensor):
             raise TypeError("PipelinedRunner expects fn to return one tensor (e.g. the loss)")
         self.results = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(depth)]
         self._i = 0
         cur = torch.cuda.current_stream(dev)
-        for e in self._consumed:
+        for e in self._consumed + self._read:
             e.record(cur)
 
     def submit(self, *host_inputs: torch.Tensor) -> int:
@@ -102,10 +105,15 @@ class PipelinedRunner:
                 dst.copy_(src, non_blocking=True)
             self._filled[s].record(self._copy)
         cur.wait_event(self._filled[s])
+        cur.wait_event(self._read[s])                       # the slot's previous result has left its (static) output tensor
         out = g.replay()
         self._consumed[s].record(cur)
-        self.results[s].copy_(out, non_blocking=True)
+        self._back.wait_event(self._consumed[s])
+        with torch.cuda.stream(self._back):
+            self.results[s].copy_(out, non_blocking=True)
+            self._read[s].record(self._back)
         return s
 
     def synchronize(self) -> None:
         torch.cuda.current_stream().synchronize()
+        self._back.synchronize()
