@@ -36,11 +36,11 @@ import torch  # noqa: E402
 import flowtimes_synth as syn  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels, per launch, from the ncu --set full
-# capture summarised under profiles/ (r1F); algorithmic bytes are in DESIGN.md section 4
+# capture summarised under profiles/ (r1G); algorithmic bytes are in DESIGN.md section 4
 NCU_TRAFFIC = {"elec": {"tc_conv4_kernel (block A, input computed once per window)": 4.5e6,
                         "tc_conv4_kernel (block B)": 21.0e6, "tc_mid_kernel": 37.9e6, "tc_tail_kernel": 61.7e6,
                         "tc_gemm2_kernel": 5.6e6, "spectrum_fft_kernel": 5.6e6, "unit": "bytes per launch",
-                        "source": "profiles/r1F_ncu_full.csv"}}
+                        "source": "profiles/r1G_ncu_full.csv"}}
 
 METRIC = "timesblock_forward_windows_per_sec"
 UNIT = "windows/s"
