@@ -63,7 +63,7 @@ def parse_args():
 
 # --------------------------------------------------------------------------- #
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU every 100 ms through NVML."""
+    """Samples SM clock / throttle reasons of one GPU every 10 ms through NVML (the timed regions are tens of milliseconds long)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.01)
 
     def finish(self):
         self._halt.set()
