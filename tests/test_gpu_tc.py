@@ -28,7 +28,8 @@ def test_tc_linear_matches_fp32_matmul(M, K, N):
 
 
 @pytest.mark.parametrize("mid,L,periods", [(32, 336, [24, 12, 7, 48, 6]), (32, 336, [335, 100, 168]), (32, 336, [2, 3, 5]),
-                                            (16, 96, [24, 12, 7, 48, 6, 95]), (32, 28, [27, 14, 7]), (32, 96, [1, 2, 48])])
+                                            (16, 96, [24, 12, 7, 48, 6, 95]), (32, 28, [27, 14, 7]), (32, 96, [1, 2, 48]),
+                                            (32, 720, [6, 24, 359])])
 @pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_tc_conv_matches_simt_conv(mid, L, periods, variant):
     if variant >= 3 and mid != 32:
