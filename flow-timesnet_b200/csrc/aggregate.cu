@@ -173,7 +173,8 @@ aggregate_vec4_kernel(const T* __restrict__ x, const T* __restrict__ delta, cons
   }
 }
 
-template <typename T>
+// RMS = true: RMSNorm (timesnet.py:1132-1159): x * rsqrt(mean(x^2) + eps) * w + b, no centring
+template <typename T, bool RMS = false>
 __global__ void __launch_bounds__(kAggWarps * 32)
 layer_norm_kernel(const T* __restrict__ x, long long rows, int C, const float* __restrict__ w,
                   const float* __restrict__ bsh, float eps, T* __restrict__ out) {
@@ -189,7 +190,7 @@ layer_norm_kernel(const T* __restrict__ x, long long rows, int C, const float* _
     rowbuf[c] = v;
     s += v;
   }
-  const float mean = warp_sum(s) / (float)C;
+  const float mean = RMS ? 0.f : warp_sum(s) / (float)C;
   __syncwarp();
   float v = 0.f;
   for (int c = lane; c < C; c += 32) {
@@ -236,11 +237,11 @@ extern "C" int ftn_aggregate(const void* x, const void* delta, const float* weig
     return 0;
   }
   if (dtype == FTN_F32) {
-    if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(aggregate_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FTN_DYN_SMEM(aggregate_kernel<float>, smem);
     aggregate_kernel<float><<<grid, kAggWarps * 32, smem, st>>>((const float*)x, (const float*)delta, weights, plan, B, L, C,
                                                                 ln_weight, ln_bias, ln_eps, (float*)out);
   } else {
-    if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(aggregate_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FTN_DYN_SMEM(aggregate_kernel<__nv_bfloat16>, smem);
     aggregate_kernel<__nv_bfloat16><<<grid, kAggWarps * 32, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, weights,
                                                                         plan, B, L, C, ln_weight, ln_bias, ln_eps,
                                                                         (__nv_bfloat16*)out);
@@ -259,12 +260,32 @@ extern "C" int ftn_layer_norm(const void* x, int dtype, int rows, int C, const f
   const unsigned grid = (unsigned)(((long long)rows + kAggWarps - 1) / kAggWarps);
   cudaStream_t st = as_stream(stream);
   if (dtype == FTN_F32) {
-    if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(layer_norm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FTN_DYN_SMEM(layer_norm_kernel<float>, smem);
     layer_norm_kernel<float><<<grid, kAggWarps * 32, smem, st>>>((const float*)x, rows, C, w, b, eps, (float*)out);
   } else {
-    if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(layer_norm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FTN_DYN_SMEM(layer_norm_kernel<__nv_bfloat16>, smem);
     layer_norm_kernel<__nv_bfloat16><<<grid, kAggWarps * 32, smem, st>>>((const __nv_bfloat16*)x, rows, C, w, b, eps, (__nv_bfloat16*)out);
   }
   FTN_LAUNCH_CHECK("layer_norm_kernel");
+  return 0;
+}
+
+extern "C" int ftn_rms_norm(const void* x, int dtype, int rows, int C, const float* w, const float* b,
+                              float eps, void* out, void* stream) {
+  FTN_REQUIRE(x && w && b && out, "ftn_rms_norm: null pointer");
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_rms_norm: unsupported dtype %d", dtype);
+  FTN_REQUIRE(rows > 0 && C > 0, "ftn_rms_norm: bad sizes");
+  const size_t smem = (size_t)kAggWarps * C * sizeof(float);
+  FTN_REQUIRE(smem <= 200 * 1024, "ftn_rms_norm: C=%d too large", C);
+  const unsigned grid = (unsigned)(((long long)rows + kAggWarps - 1) / kAggWarps);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == FTN_F32) {
+    FTN_DYN_SMEM((layer_norm_kernel<float, true>), smem);
+    (layer_norm_kernel<float, true>)<<<grid, kAggWarps * 32, smem, st>>>((const float*)x, rows, C, w, b, eps, (float*)out);
+  } else {
+    FTN_DYN_SMEM((layer_norm_kernel<__nv_bfloat16, true>), smem);
+    (layer_norm_kernel<__nv_bfloat16, true>)<<<grid, kAggWarps * 32, smem, st>>>((const __nv_bfloat16*)x, rows, C, w, b, eps, (__nv_bfloat16*)out);
+  }
+  FTN_LAUNCH_CHECK("rms_norm_kernel");
   return 0;
 }

@@ -83,7 +83,15 @@ inline cudaError_t launch_pdl(bool dependent, void (*kernel)(KArgs...), dim3 gri
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-int sm_count();  // cached per process (current device at first call)
+// Per-device context (lib.cu): everything the library caches is keyed by the device current at the call.
+int sm_count();                                           // SMs of the current device
+int ensure_dyn_smem(const void* func, size_t bytes);      // opt-in dynamic shared memory of `func` on the current device
+int ctx_side_stream(cudaStream_t* side);                  // low-priority non-blocking side stream of the current device
+int ctx_event_pair(cudaEvent_t* a, cudaEvent_t* b);       // a fresh fork / join event pair from the device's ring
+#define FTN_DYN_SMEM(kernel, bytes)                                                   \
+  do {                                                                                \
+    if (int rc_ = ::ftn::ensure_dyn_smem((const void*)(kernel), (size_t)(bytes))) return rc_; \
+  } while (0)
 
 // ---- dtype access -------------------------------------------------------------
 template <typename T>

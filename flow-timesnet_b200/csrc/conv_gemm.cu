@@ -294,7 +294,7 @@ static int check_weights(const FtnInceptionWeights* w, const char* which) {
 template <typename T>
 static int run_block(const FtnInceptionWeights* w, const Src& in, const ConvGemmParams& base,
                      float* h1, float* h2, int act, bool is_last, void* out, int ldo, const Src& xsub,
-                     int max_groups, cudaStream_t st) {
+                     int max_groups, cudaStream_t st, bool trailing_act = true) {
   ConvGemmParams p = base;
   Src kk_in = in;
   if (w->mid > 0) {
@@ -329,7 +329,7 @@ static int run_block(const FtnInceptionWeights* w, const Src& in, const ConvGemm
   if (w->w_res) { p.p2 = P2_GEMM; p.w2 = w->w_res; p.b2 = w->b_res; p.K2 = w->cin; }   // :648
   else p.p2 = P2_IDENTITY;
   if (!is_last) {
-    p.act2 = act;                                 // Sequential's middle activation (:753)
+    p.act2 = trailing_act ? act : -1;             // Sequential's middle activation (:753)
     p.out_kind = OUT_POS; p.out = out; p.ldo = ldo;
   } else {
     p.act2 = -1;
@@ -420,6 +420,59 @@ extern "C" int ftn_period_conv(const void* x, int dtype, int B, int L, int C, co
   if (dtype == FTN_F32)
     return period_conv_impl<float>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
   return period_conv_impl<__nv_bfloat16>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
+}
+
+// One InceptionBlock on its own (InceptionBlock.forward on an NCHW grid = one period group with period W, H cycles
+// and no padding; timesnet.py:645-654): out[b][t][:] = act(proj(cat branches))(t) + res_proj(x)(t), optionally
+// followed by the Sequential's middle activation.  fp32 SIMT chain; out is fp32 [B][L][cout] for a one-group plan
+// (row = B * row_off_g + b * (L + pad_g) + t in general).
+extern "C" size_t ftn_inception_block_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* w) {
+  if (!w || B <= 0 || L <= 0 || max_groups <= 0) return 256;
+  const size_t rows = (size_t)max_groups * B * (size_t)(2 * L);
+  const size_t nb = (size_t)w->n_branch * (w->mid > 0 ? w->mid : 0);
+  return 2 * align256(rows * nb * sizeof(float)) + 256;
+}
+
+extern "C" int ftn_inception_block(const void* x, int dtype, int B, int L, const FtnPeriodPlan* plan, int max_groups,
+                                   const FtnInceptionWeights* w, int act, int trailing_act, float* out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(x && plan && out && workspace, "ftn_inception_block: null pointer");
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_inception_block: unsupported dtype %d", dtype);
+  FTN_REQUIRE(B > 0 && L >= 1, "ftn_inception_block: bad sizes B=%d L=%d", B, L);
+  FTN_REQUIRE(max_groups >= 1 && max_groups <= FTN_MAX_K, "ftn_inception_block: max_groups=%d", max_groups);
+  FTN_REQUIRE(act == FTN_ACT_GELU || act == FTN_ACT_RELU, "ftn_inception_block: unknown activation %d", act);
+  if (int rc = check_weights(w, "block")) return rc;
+  FTN_REQUIRE(workspace_bytes >= ftn_inception_block_workspace_bytes(B, L, max_groups, w),
+              "ftn_inception_block: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const size_t rows = (size_t)max_groups * B * (size_t)(2 * L);
+  const size_t nb = (size_t)w->n_branch * (w->mid > 0 ? w->mid : 0);
+  float* h1 = reinterpret_cast<float*>(workspace);
+  float* h2 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256(rows * nb * sizeof(float)));
+  ConvGemmParams base{};
+  base.plan = plan; base.B = B; base.L = L;
+  Src xs{x, SRC_SEQ, w->cin, 0};
+  // is_last = false: POS output; the second activation of run_block is the Sequential's, so it is optional here
+  const int rc = dtype == FTN_F32
+      ? run_block<float>(w, xs, base, h1, h2, act, false, out, w->cout, xs, max_groups, st, trailing_act != 0)
+      : run_block<__nv_bfloat16>(w, xs, base, h1, h2, act, false, out, w->cout, xs, max_groups, st, trailing_act != 0);
+  return rc;
+}
+
+// One Conv2d (bias, zero "same" padding, odd kernel) on the folded grids of a plan: the building block of
+// InceptionBranch.forward (timesnet.py:592-593).  x: fp32 [B][L][cin]; w: [kh*kw][cin][cout]; out: fp32 POS rows.
+extern "C" int ftn_conv2d_grid(const float* x, int B, int L, int cin, int cout, int kh, int kw, const FtnPeriodPlan* plan,
+                               int max_groups, const float* w, const float* bias, float* out, void* stream) {
+  FTN_REQUIRE(x && plan && w && bias && out, "ftn_conv2d_grid: null pointer");
+  FTN_REQUIRE(B > 0 && L >= 1 && cin > 0 && cout > 0, "ftn_conv2d_grid: bad sizes");
+  FTN_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "ftn_conv2d_grid: kernel %dx%d must be odd", kh, kw);
+  FTN_REQUIRE(max_groups >= 1 && max_groups <= FTN_MAX_K, "ftn_conv2d_grid: max_groups=%d", max_groups);
+  ConvGemmParams p{};
+  p.plan = plan; p.B = B; p.L = L;
+  p.a1 = Src{x, SRC_SEQ, cin, 0}; p.K1 = cin; p.N = cout;
+  p.br[0] = Branch{w, bias, kh, kw, 0, 0};
+  p.act1 = -1; p.p2 = P2_NONE; p.act2 = -1; p.out_kind = OUT_POS; p.out = out; p.ldo = cout;
+  return launch_conv_gemm<float>(p, 1, max_groups, as_stream(stream));
 }
 
 // Whole TimesBlock after the period search: out = [LayerNorm](x + sum_g w[b][g] * delta_g).

@@ -308,6 +308,43 @@ __global__ void __launch_bounds__(256) nb_nll_final_kernel(const float* __restri
   if (threadIdx.x == 0) out[0] = (float)(-ss[0] / fmax(sw[0], 1.0));
 }
 
+// ---------------------------------------------------------------------------
+// Rolling one-step forecast, device-resident (predict.py:333-341): after a forward produced (rate, disp)[B][1][N],
+//   rates[b][s][n] = rate, disps[b][s][n] = disp, window = cat(window[:, 1:], rate), marks likewise with y_mark[:, s]
+// with s = *step_counter, which the kernel then increments -- the host replays ONE captured graph H times and never
+// looks at the step index.  A thread owns one (window, series) column and shifts it in place (reads t + 1 before it
+// writes t), so no second buffer is needed.
+// ---------------------------------------------------------------------------
+__global__ void recursive_advance_kernel(float* __restrict__ window, const float* __restrict__ rate,
+                                         const float* __restrict__ disp, int B, int L, int N, int H,
+                                         float* __restrict__ rates, float* __restrict__ disps,
+                                         float* __restrict__ mark, const float* __restrict__ y_mark, int Tm,
+                                         int* __restrict__ step_counter) {
+  const int s = *step_counter;
+  const long long total = (long long)B * N, totm = (long long)B * Tm;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    const float r = rate[i], d = disp[i];
+    if (s < H) {
+      rates[(b * H + s) * N + n] = r;
+      disps[(b * H + s) * N + n] = d;
+    }
+    float* col = window + b * (long long)L * N + n;
+    for (int t = 0; t + 1 < L; ++t) col[(long long)t * N] = col[(long long)(t + 1) * N];
+    col[(long long)(L - 1) * N] = r;
+  } else if (mark && i - total < totm) {
+    const long long j = i - total, b = j / Tm;
+    const int f = (int)(j - b * Tm);
+    float* col = mark + b * (long long)L * Tm + f;
+    for (int t = 0; t + 1 < L; ++t) col[(long long)t * Tm] = col[(long long)(t + 1) * Tm];
+    col[(long long)(L - 1) * Tm] = s < H ? y_mark[(b * H + s) * Tm + f] : 0.f;
+  }
+}
+// the counter is bumped by a second one-thread kernel: every thread of the first must have read the old value
+__global__ void recursive_bump_kernel(int* __restrict__ step_counter) { *step_counter += 1; }
+
 static int launch_sgemm_f32(const float* A, int lda, long long sA, const float* Bm, int ldb, long long sB,
                             float* C, int ldc, long long sC, int M, int N, int K, int batch, bool transB,
                             const float* bias, int bias_mode, cudaStream_t st) {
@@ -334,7 +371,7 @@ extern "C" int ftn_context_add(const float* x, const float* coeff, const float* 
   FTN_REQUIRE(B > 0 && L > 0 && N > 0 && R > 0, "ftn_context_add: bad sizes");
   size_t smem = ((size_t)L * R + R + 128 * (size_t)(R + 1)) * sizeof(float);
   FTN_REQUIRE(smem <= 200 * 1024, "ftn_context_add: L*R=%d too large for shared memory", L * R);
-  if (smem > 48 * 1024) FTN_CUDA(cudaFuncSetAttribute(context_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FTN_DYN_SMEM(context_add_kernel, smem);
   long long total = (long long)B * N;
   context_add_kernel<<<(unsigned)((total + 127) / 128), 128, smem, as_stream(stream)>>>(x, coeff, basis, scale, B, L, N, R, out);
   FTN_LAUNCH_CHECK("context_add_kernel");
@@ -395,5 +432,22 @@ extern "C" int ftn_nb_nll(const float* y, const float* rate, const float* disp, 
   FTN_LAUNCH_CHECK("nb_nll_partial_kernel");
   nb_nll_final_kernel<<<1, 256, 0, st>>>(partial, blocks, out);
   FTN_LAUNCH_CHECK("nb_nll_final_kernel");
+  return 0;
+}
+
+extern "C" int ftn_recursive_advance(float* window, const float* rate, const float* disp, int B, int L, int N, int H,
+                                     float* rates, float* disps, float* mark, const float* y_mark, int mark_features,
+                                     int* step_counter, void* stream) {
+  FTN_REQUIRE(window && rate && disp && rates && disps && step_counter, "ftn_recursive_advance: null pointer");
+  FTN_REQUIRE(B > 0 && L > 0 && N > 0 && H > 0, "ftn_recursive_advance: bad sizes");
+  FTN_REQUIRE((mark == nullptr) == (y_mark == nullptr), "ftn_recursive_advance: mark and y_mark must come together");
+  FTN_REQUIRE(!mark || mark_features > 0, "ftn_recursive_advance: mark_features=%d", mark_features);
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)B * N + (mark ? (long long)B * mark_features : 0);
+  recursive_advance_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(window, rate, disp, B, L, N, H, rates, disps, mark,
+                                                                          y_mark, mark ? mark_features : 0, step_counter);
+  FTN_LAUNCH_CHECK("recursive_advance_kernel");
+  recursive_bump_kernel<<<1, 1, 0, st>>>(step_counter);
+  FTN_LAUNCH_CHECK("recursive_bump_kernel");
   return 0;
 }

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <vector>
 #include <string.h>
@@ -54,17 +55,83 @@ TimedScope::~TimedScope() {
   cudaEventRecord(g_recs[slot].b, st);
 }
 
-int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
+// ---- per-device context --------------------------------------------------------
+// Everything the library keeps between calls is keyed by the CUDA device that is current when the call is made:
+// SM count, the per-kernel dynamic-shared-memory attribute (function attributes are per device), the low-priority
+// side stream of ftn_timesblock_forward and a ring of fork / join events.  One host thread may drive several GPUs
+// and several host threads may drive one: the table is guarded by a mutex and every call takes its own event pair
+// from the ring, so two concurrent calls never record the same event.
+constexpr int kMaxDevices = 64;
+constexpr int kEventRing = 256;
+struct DeviceCtx {
+  bool init = false;
+  int sms = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t events[kEventRing] = {};
+  int next_event = 0;
+  std::map<const void*, size_t> dyn_smem;
+};
+static std::mutex g_ctx_mu;
+static DeviceCtx g_ctx[kMaxDevices];
+
+// caller holds g_ctx_mu
+static DeviceCtx* ctx_locked() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  DeviceCtx* c = &g_ctx[dev];
+  if (!c->init) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    c->sms = n;
+    c->init = true;
   }
-  return cached;
+  return c;
+}
+
+int sm_count() {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx* c = ctx_locked();
+  return c ? c->sms : 148;
+}
+
+int ensure_dyn_smem(const void* func, size_t bytes) {
+  if (bytes == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx* c = ctx_locked();
+  FTN_REQUIRE(c, "no current CUDA device");
+  size_t& have = c->dyn_smem[func];
+  if (bytes > have) {
+    FTN_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
+
+int ctx_side_stream(cudaStream_t* side) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx* c = ctx_locked();
+  FTN_REQUIRE(c, "no current CUDA device");
+  if (!c->side) {
+    int least = 0, greatest = 0;
+    FTN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    FTN_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, least));
+  }
+  *side = c->side;
+  return 0;
+}
+
+int ctx_event_pair(cudaEvent_t* a, cudaEvent_t* b) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx* c = ctx_locked();
+  FTN_REQUIRE(c, "no current CUDA device");
+  cudaEvent_t* out[2] = {a, b};
+  for (int i = 0; i < 2; ++i) {
+    cudaEvent_t& e = c->events[c->next_event];
+    c->next_event = (c->next_event + 1) % kEventRing;
+    if (!e) FTN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out[i] = e;
+  }
+  return 0;
 }
 
 }  // namespace ftn

@@ -3,8 +3,8 @@
 //   spectrum_dft_kernel   |rfft| of every (window, channel) column, fp32
 //   channel_median_kernel lower median over channels per (window, bin)
 //   batch_sum_kernel      deterministic sum over windows  -> amp_sum[F]
-//   select_tail_kernel    DC mask, log penalty, top-k, period math, grouping
-//   finish_kernel         per-window amplitudes at the chosen bins + group weights
+//   select_fused_kernel   (batch sum,) DC mask, log penalty, top-k, period math, grouping, per-window
+//                         amplitudes at the chosen bins + softmax group weights
 //
 // Reference semantics: FFTPeriodSelector.forward (timesnet.py:64-159) and the
 // default PeriodGrouper (timesnet.py:513-557).  The transform is a direct
@@ -146,114 +146,6 @@ __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {
   return ia < ib;  // tie rule: lower bin first
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-select_tail_kernel(const float* __restrict__ amp_sum, int global_batch, int L, int k, int pmax,
-                   int min_period, FtnPeriodPlan* __restrict__ plan, float* __restrict__ scores_ws) {
-  const int F = L / 2 + 1;
-  __shared__ float s_best[256];
-  __shared__ int s_idx[256];
-  __shared__ int s_top[FTN_MAX_K];
-  const int tid = threadIdx.x;
-  // scores in the activation dtype, exactly as timesnet.py:119-130
-  for (int f = tid; f < F; f += blockDim.x) {
-    const float gb = global_batch > 0 ? (float)global_batch : amp_sum[F];   // <= 0: count slot written by ftn_spectrum
-    float mean = amp_sum[f] / gb;
-    float m = round_to<T>(mean);
-    float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
-    float sc = round_to<T>(m - pen);
-    if (f == 0) sc = -CUDART_INF_F;
-    scores_ws[f] = sc;
-  }
-  __syncthreads();
-  int kk = min(k, F - 1);
-  for (int r = 0; r < kk; ++r) {
-    float bs = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int f = tid; f < F; f += blockDim.x) {
-      bool taken = false;
-      for (int j = 0; j < r; ++j) taken = taken || (s_top[j] == f);
-      if (taken) continue;
-      float sc = scores_ws[f];
-      if (bi == 0x7fffffff || better(sc, f, bs, bi)) { bs = sc; bi = f; }
-    }
-    s_best[tid] = bs;
-    s_idx[tid] = bi;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-      if (tid < off) {
-        int oi = s_idx[tid + off];
-        if (oi != 0x7fffffff && (s_idx[tid] == 0x7fffffff || better(s_best[tid + off], oi, s_best[tid], s_idx[tid]))) {
-          s_best[tid] = s_best[tid + off];
-          s_idx[tid] = oi;
-        }
-      }
-      __syncthreads();
-    }
-    if (tid == 0) s_top[r] = s_idx[0];
-    __syncthreads();
-  }
-  if (tid == 0) {
-    FtnPeriodPlan pl;
-    pl.n_raw = kk;
-    pl.reserved[0] = pl.reserved[1] = pl.reserved[2] = 0;
-    const int upper = min(pmax, max(1, L - 1));
-    const int lower = min_period;
-    int nv = 0;
-    float mean_amp[FTN_MAX_K];
-    for (int i = 0; i < FTN_MAX_K; ++i) { pl.raw_freq[i] = 0; pl.freq[i] = 0; pl.period[i] = 0; }
-    for (int r = 0; r < kk; ++r) {
-      int64_t safe = max(s_top[r], 1);
-      pl.raw_freq[r] = safe;
-      if (upper < lower) continue;
-      int64_t p = (L + safe - 1) / safe;
-      p = p < lower ? lower : (p > upper ? upper : p);
-      int64_t cyc = (L + p - 1) / p;
-      if (cyc < 2) continue;
-      pl.freq[nv] = safe;
-      pl.period[nv] = p;
-      mean_amp[nv] = amp_sum[safe];
-      ++nv;
-    }
-    pl.n_valid = nv;
-    PlanScratch scr;
-    plan_group_default(&pl, pl.period, nv, L, min_period, pmax, mean_amp, &scr);
-    *plan = pl;
-  }
-}
-
-// per window: amplitudes at the chosen bins (dtype) + softmax group weights
-template <typename T>
-__global__ void finish_kernel(const float* __restrict__ amp_median, int B, int F, int k,
-                              const FtnPeriodPlan* __restrict__ plan, T* __restrict__ amps,
-                              float* __restrict__ weights) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int nv = plan->n_valid;
-  float a[FTN_MAX_K];
-  for (int j = 0; j < k; ++j) {
-    float v = 0.f;
-    if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + plan->freq[j]]);
-    a[j] = v;
-    amps[(size_t)b * k + j] = from_f32<T>(v);
-  }
-  float mx = -CUDART_INF_F;
-  for (int j = 0; j < nv; ++j)
-    if (plan->mapping[j] >= 0) mx = fmaxf(mx, a[j]);
-  float den = 0.f;
-  for (int j = 0; j < nv; ++j)
-    if (plan->mapping[j] >= 0) den += expf(a[j] - mx);
-  float w[FTN_MAX_K];
-  for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
-  for (int j = 0; j < nv; ++j) {
-    int g = plan->mapping[j];
-    if (g < 0) continue;
-    float sm = round_to<T>(expf(a[j] - mx) / den);      // softmax fp32 -> dtype (timesnet.py:1000)
-    w[g] = round_to<T>(w[g] + sm);                      // scatter_add_ in dtype (:1009)
-  }
-  for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
-}
-
 // same second half for externally supplied amplitudes (custom selector modules)
 template <typename T>
 __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, int stride,
@@ -280,8 +172,7 @@ __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, i
 }
 
 // ---- fused tail: batch sum (optional) + scores + top-k + plan + per-window amplitudes / weights ----
-// One CTA of 1024 threads.  Replaces batch_sum_kernel + select_tail_kernel + finish_kernel (three
-// launches, ~32 us at the elec shape, all latency) when no all-reduce has to happen in between; with
+// One CTA of 1024 threads (three separate launches cost ~32 us at the elec shape, all latency); with
 // a sharded batch the caller runs batch_sum_kernel, all-reduces, and calls this with do_sum = 0.
 // Summation order, score rounding, tie rule and grouping are the ones of the separate kernels.
 __device__ __forceinline__ void argbest_warp(float& s, int& i) {
@@ -509,7 +400,7 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
     #pragma unroll 1
     for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
   }
-  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  (= finish_kernel)
+  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  
   const int nv = s_plan.n_valid;
   if (tid < kSelFinishThreads) {
     #pragma unroll 1
@@ -582,19 +473,12 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
   TimedScope ts(FTN_FAM_SELECT, st);
   const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : F)) * sizeof(float);
   FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
-  static size_t attr[2] = {0, 0};
   if (dtype == FTN_F32) {
-    if (smem > 16 * 1024 && smem > attr[0]) {
-      FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[0] = smem;
-    }
+    FTN_DYN_SMEM(select_fused_kernel<float>, smem);
     FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B, global_batch, L,
                         k, pmax, min_period, plan, (float*)amps, weights));
   } else {
-    if (smem > 16 * 1024 && smem > attr[1]) {
-      FTN_CUDA(cudaFuncSetAttribute(select_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[1] = smem;
-    }
+    FTN_DYN_SMEM(select_fused_kernel<__nv_bfloat16>, smem);
     FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B,
                         global_batch, L, k, pmax, min_period, plan, (__nv_bfloat16*)amps, weights));
   }
@@ -631,10 +515,10 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
     FTN_REQUIRE(smem <= 227 * 1024, "ftn_spectrum: L=%d needs %zu B of shared memory (> 227 KB)", L, smem);
     dim3 grid((C + kDftChannels - 1) / kDftChannels, B);
     if (dtype == FTN_F32) {
-      FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FTN_DYN_SMEM(spectrum_dft_kernel<float>, smem);
       spectrum_dft_kernel<float><<<grid, kDftWarps * 32, smem, st>>>((const float*)x, L, C, F, amp);
     } else {
-      FTN_CUDA(cudaFuncSetAttribute(spectrum_dft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FTN_DYN_SMEM(spectrum_dft_kernel<__nv_bfloat16>, smem);
       spectrum_dft_kernel<__nv_bfloat16><<<grid, kDftWarps * 32, smem, st>>>((const __nv_bfloat16*)x, L, C, F, amp);
     }
     FTN_LAUNCH_CHECK("spectrum_dft_kernel");
@@ -645,7 +529,7 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
   if (rc > 0) return rc;
   if (rc < 0) {
     size_t msmem = (size_t)kMedianWarps * C * sizeof(uint32_t);
-    FTN_CUDA(cudaFuncSetAttribute(channel_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    FTN_DYN_SMEM(channel_median_kernel, msmem);
     channel_median_kernel<<<(rows + kMedianWarps - 1) / kMedianWarps, kMedianWarps * 32, msmem, st>>>(amp, rows, C, amp_median);
     FTN_LAUNCH_CHECK("channel_median_kernel");
   }
@@ -658,13 +542,11 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
 
 extern "C" int ftn_select_periods(const float* amp_median, const float* amp_sum, int dtype, int B,
                                   int global_batch, int L, int k, int pmax, int min_period,
-                                  FtnPeriodPlan* plan, void* amps, float* weights, float* scores_ws,
-                                  void* stream) {
-  FTN_REQUIRE(amp_median && amp_sum && plan && amps && weights && scores_ws, "ftn_select_periods: null pointer");
+                                  FtnPeriodPlan* plan, void* amps, float* weights, void* stream) {
+  FTN_REQUIRE(amp_median && amp_sum && plan && amps && weights, "ftn_select_periods: null pointer");
   FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_select_periods: k=%d outside [1,%d]", k, FTN_MAX_K);
   FTN_REQUIRE(B > 0 && (global_batch <= 0 || global_batch >= B) && L > 1, "ftn_select_periods: bad sizes B=%d global=%d L=%d", B, global_batch, L);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_select_periods: unsupported dtype %d", dtype);
-  (void)scores_ws;   // kept in the signature for ABI stability; the fused tail keeps scores in shared memory
   return launch_select_fused(amp_median, const_cast<float*>(amp_sum), 0, dtype, B, global_batch, L, k, pmax, min_period,
                              plan, amps, weights, as_stream(stream), false);
 }

@@ -348,11 +348,7 @@ static bool fft_factor(int N, FftPlan* plan) {
 template <typename T, int KPL>
 static int fft_launch_one(const T* x, int B, int L, int C, float* amp, float* med, const FftPlan& plan, size_t smem,
                           cudaStream_t st) {
-  static size_t attr = 0;   // raise the dynamic shared memory limit once per size (not a stream operation)
-  if (smem > attr) {
-    FTN_CUDA(cudaFuncSetAttribute(spectrum_fft_kernel<T, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  FTN_DYN_SMEM((spectrum_fft_kernel<T, KPL>), smem);   // per device, once per size (not a stream operation)
   const int slabs = (C + 31) / 32;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(slabs, B);

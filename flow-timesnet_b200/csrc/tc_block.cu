@@ -37,62 +37,32 @@ int tc_stage_launch(const TcGemmArgs& a, cudaStream_t st) {
   return tc_gemm_launch(a, st);
 }
 
-static bool kk_force(int v) {   // A/B switches for profiling
-  static const bool f1 = getenv("FLOWTIMES_CONV_V1") != nullptr, f2 = getenv("FLOWTIMES_CONV_V2") != nullptr,
-                    f3 = getenv("FLOWTIMES_CONV_V3") != nullptr;
-  return v == 1 ? f1 : (v == 2 ? f2 : f3);
+static bool kk_force(int v) {   // A/B switches for profiling: FLOWTIMES_CONV_V2 = image-resident kernel only, _V0 = SIMT
+  static const bool f0 = getenv("FLOWTIMES_CONV_V0") != nullptr, f2 = getenv("FLOWTIMES_CONV_V2") != nullptr;
+  return v == 0 ? f0 : f2;
 }
 
 bool tc_kk_uses_conv4(const FtnInceptionWeights* w) {
-  return !kk_force(1) && !kk_force(2) && !kk_force(3) && tc_conv4_eligible(w);
+  return !kk_force(0) && !kk_force(2) && tc_conv4_eligible(w);
 }
 
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
                 int period_lo, int period_hi) {
-  const bool force_v1 = kk_force(1), force_v2 = kk_force(2);
+  const bool force_v2 = kk_force(0);   // SIMT only
   FTN_REQUIRE(shared_bias_row < 0 || tc_kk_uses_conv4(w), "tc_kk_stage: the shared input layout needs the tc_conv4 route");
   if (tc_kk_uses_conv4(w)) {
     // phases-on-M kernel for every group whose padded image fits shared memory, tc_conv2 for the rest
-    // The two launches cover disjoint groups and only read `in`.  With programmatic dependent launch (the default)
-    // they stay in stream order: the (normally empty) tc_conv2 grid is placed while tc_conv4 drains.  The side-stream
-    // fork / join variant (FLOWTIMES_SIDE_STREAM) makes them parallel graph nodes instead, but its event records sit
-    // between kernels and would turn the programmatic edges back into full serialisation.
+    // The two launches cover disjoint groups and only read `in`; they stay in stream order (programmatic dependent
+    // launch places the normally empty tc_conv2 grid while tc_conv4 drains).
     int caps[FTN_MAX_BRANCH];
     tc_conv4_caps(w, caps);
-    static const bool serial = getenv("FLOWTIMES_NO_SIDE_STREAM") != nullptr ||
-                               (pdl_enabled() && getenv("FLOWTIMES_SIDE_STREAM") == nullptr);
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (!serial && !side) {
-      FTN_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-      FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
     if (period_lo > 0 && tc_conv4_covers(w, L, period_lo, period_hi))   // nothing can be left for the fallback
       return tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row);
-    if (serial) {
-      if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
-      return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row);
-    }
-    FTN_CUDA(cudaEventRecord(ev_fork, st));
     if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
-    FTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (int rc = tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, side, shared_bias_row)) return rc;
-    FTN_CUDA(cudaEventRecord(ev_join, side));
-    FTN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-    return 0;
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row);
   }
-  if (!force_v1 && !force_v2 && tc_conv3_eligible(w)) {
-    // full-rate kernel for every period whose padded grid fits its shared-memory layouts, tile-patch kernel for the
-    // rest; both read the same device plan and apply the same predicate, so the two launches cover disjoint groups
-    int caps[FTN_MAX_BRANCH];
-    tc_conv3_caps(w, caps);
-    if (int rc = tc_conv3_launch(plan, B, L, max_groups, in, out, ld, w, st)) return rc;
-    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st);
-  }
-  if (!force_v1 && tc_conv2_eligible(w)) return tc_conv2_launch(plan, B, L, max_groups, in, out, ld, w, st);
-  if (tc_conv_eligible(w)) return tc_conv_launch(plan, B, L, max_groups, in, out, ld, w, st);
+  if (!force_v2 && tc_conv2_eligible(w)) return tc_conv2_launch(plan, B, L, max_groups, in, out, ld, w, st);
   return simt_conv_tiled_launch(plan, B, L, max_groups, in, out, ld, w, st);
 }
 
@@ -148,23 +118,23 @@ int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPla
                                 const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                                 const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
                                 int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi) {
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (!side) {
-    int least = 0, greatest = 0;
-    FTN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    FTN_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least));
-    FTN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    FTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  }
+  // per-device side stream, per-call event pair (lib.cu): re-entrant across devices and host threads
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (int rc = ctx_side_stream(&side)) return rc;
+  if (int rc = ctx_event_pair(&ev_fork, &ev_join)) return rc;
   TcS1Done s1{-1, period_lo, period_hi};
   FTN_CUDA(cudaEventRecord(ev_fork, st));
   FTN_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-  if (int rc = launch_block_s1(x, B, L, C, nullptr, max_groups, a, act, workspace, side, &s1.shared_bias_row)) return rc;
-  FTN_CUDA(cudaEventRecord(ev_join, side));
-  int rc = search(search_ctx, st);
-  FTN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));      // join even when the search failed: the side stream must not dangle
+  // from here on the side stream is forked: whatever happens, it is joined back into `st` before returning (a
+  // dangling fork would invalidate a stream capture in progress)
+  const int rc_s1 = launch_block_s1(x, B, L, C, nullptr, max_groups, a, act, workspace, side, &s1.shared_bias_row);
+  const cudaError_t e_rec = cudaEventRecord(ev_join, side);
+  const int rc = rc_s1 ? 0 : search(search_ctx, st);
+  const cudaError_t e_join = e_rec == cudaSuccess ? cudaStreamWaitEvent(st, ev_join, 0) : e_rec;
+  if (rc_s1) return rc_s1;
   if (rc) return rc;
+  FTN_CUDA(e_join);
   TcTailSpec tail{weights, ln_w, ln_b, eps, out};
   TimedScope timed(FTN_FAM_CONV, st);
   return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, nullptr, workspace, &tail, st, &s1);
@@ -280,3 +250,25 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
 }
 
 }  // namespace ftn
+
+using namespace ftn;
+
+// Unit-test hook: run only the k x k stage on tile-major bf16 activations.
+// use_tc = 4: phases-on-M tcgen05 kernel (+ tc_conv2 for the groups it leaves), 2: image-resident tcgen05 kernel, 0: SIMT.
+extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
+                                            int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream) {
+  FTN_REQUIRE(in && out && plan && w, "ftn_debug_conv_tiled: null pointer");
+  const __nv_bfloat16* src = (const __nv_bfloat16*)in;
+  __nv_bfloat16* dst = (__nv_bfloat16*)out;
+  cudaStream_t st = as_stream(stream);
+  if (use_tc == 4) {
+    int caps[FTN_MAX_BRANCH];
+    FTN_REQUIRE(tc_conv4_eligible(w), "ftn_debug_conv_tiled: tc_conv4 not eligible for this block");
+    tc_conv4_caps(w, caps);
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, src, dst, ld, w, st, -1, false)) return rc;
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, src, dst, ld, w, caps, st);
+  }
+  if (use_tc == 2) return tc_conv2_launch_filtered(plan, B, L, max_groups, src, dst, ld, w, nullptr, st, -1, false);
+  FTN_REQUIRE(use_tc == 0, "ftn_debug_conv_tiled: unknown variant %d", use_tc);
+  return simt_conv_tiled_launch(plan, B, L, max_groups, src, dst, ld, w, st);
+}

@@ -44,7 +44,7 @@ struct TcConv2Args {
   int mid;       // channels per branch (K and N of the MMAs): 16 or 32
   int n_branch;
   int cap_rows;  // rows one image buffer can hold
-  int v3_cap[FTN_MAX_BRANCH];   // > 0: skip the groups tc_conv3 handles (c3_group_fits with this capacity); < 0: tc_conv4's
+  int v3_cap[FTN_MAX_BRANCH];   // < 0: skip the groups tc_conv4 takes (c4_group_fits with capacity -v3_cap); 0: take all
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH];
   int cta_begin[FTN_MAX_BRANCH + 1];       // CTA ranges per branch
   const __nv_bfloat16* w[FTN_MAX_BRANCH];  // [tap][n][k] bf16
@@ -89,9 +89,8 @@ __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L,
       const long long cost_a = (long long)bands_a * (ta * C2_BM + 2 * margin);
       if (cost_a <= cost_b) { mode_b = 0; T = ta; bands = bands_a; }
     }
-    const bool taken = (v3cap > 0 && c3_group_fits(per, kh, 2 * hw + 1, v3cap)) ||
-                       (v3cap < 0 && c4_group_fits(per, cyc, kh, 2 * hw + 1, -v3cap));
-    const int n = taken ? 0 : bands * B;   // tc_conv3 / tc_conv4 owns this group
+    const bool taken = v3cap < 0 && c4_group_fits(per, cyc, kh, 2 * hw + 1, -v3cap);
+    const int n = taken ? 0 : bands * B;   // tc_conv4 owns this group
     const int rt = (Lp + 127) / 128;
     if (unit < n) {
       u.g = g;
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
   pdl_trigger();
   pdl_wait();   // the plan and the input image are a predecessor's output
   {
-    // nothing to do for this CTA (e.g. tc_conv3 owns every group): leave before touching TMEM / weights
+    // nothing to do for this CTA (e.g. tc_conv4 owns every group): leave before touching TMEM / weights
     C2Unit probe;
     if (!c2_decode(p.plan, p.B, p.L, kh, hw, cap, p.v3_cap[j], cta_in_branch, probe)) return;
   }
@@ -380,11 +379,7 @@ int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_gr
     a.cta_begin[j + 1] = end;
   }
   ctas = a.cta_begin[w->n_branch];
-  static size_t attr = 0;
-  if (smem > attr) {
-    FTN_CUDA(cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  FTN_DYN_SMEM(tc_conv2_kernel, smem);
   FTN_CUDA(launch_pdl(dependent, tc_conv2_kernel, dim3(ctas), dim3(C2_THREADS), smem, st, a));
   FTN_LAUNCH_CHECK("tc_conv2_kernel");
   return 0;

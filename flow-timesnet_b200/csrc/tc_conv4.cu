@@ -447,7 +447,7 @@ bool tc_conv4_eligible(const FtnInceptionWeights* w) {
 
 // does tc_conv4 (either pass) take every period in [lo, hi] at sequence length L?  (cached: called per launch)
 bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int lo, int hi) {
-  static int c_L = -1, c_lo = -1, c_hi = -1, c_sig = -1, c_ans = 0;
+  static thread_local int c_L = -1, c_lo = -1, c_hi = -1, c_sig = -1, c_ans = 0;   // pure function of the arguments
   int sig = w->n_branch;
   for (int j = 0; j < w->n_branch; ++j) sig = sig * 131 + w->kh[j] * 16 + w->kw[j];
   if (L == c_L && lo == c_lo && hi == c_hi && sig == c_sig) return c_ans != 0;
@@ -506,11 +506,7 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   // second half of the grid: the same branch split with ONE image buffer per CTA.  Those CTAs are placed as the
   // first half leaves, find (almost always) nothing to do and return; a separate launch for them cost ~3 us
   const int ctas = 2 * a.n_ctas0;
-  static size_t attr = 0;
-  if (smem > attr) {
-    FTN_CUDA(cudaFuncSetAttribute(tc_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  FTN_DYN_SMEM(tc_conv4_kernel, smem);
   static const char* trace_path = getenv("FLOWTIMES_CONV_TRACE");
   static long long* trace_dev = nullptr;
   constexpr int kTraceWords = 2 * 16 * 256 + 256;

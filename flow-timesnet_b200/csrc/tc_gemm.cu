@@ -287,11 +287,7 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.a1_seq = a.a1_seq; k.a2_seq = a.a2_seq; k.K1 = a.K1; k.K2 = a.K2; k.N = a.N; k.act = a.act; k.epi = a.epi;
   k.res = a.res; k.bias1 = a.bias1; k.bias2 = a.bias2; k.res_ptr = a.res_ptr; k.res_ld = a.res_ld;
   k.out = a.out; k.ldo = a.ldo; k.x = a.x; k.C = a.C;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  FTN_DYN_SMEM(tc_gemm_kernel, TC_SMEM_BYTES);
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
   tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);

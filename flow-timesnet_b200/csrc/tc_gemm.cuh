@@ -47,31 +47,13 @@ int tc_worst_case_tiles(int B, int L, int max_groups);
 int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                            __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 
-// k x k stage on the tensor cores (tc_conv.cu); eligible for mid in {16, 32} with resident weights
-bool tc_conv_eligible(const FtnInceptionWeights* w);
-int tc_conv_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                   __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
-
 // image-resident variant (tc_conv2.cu): the padded grid of one image is staged once per branch
 bool tc_conv2_eligible(const FtnInceptionWeights* w);
 int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
-// "positions on N" variant (tc_conv3.cu): full-rate N = 256 MMAs, 4 taps x 32 channels on M; periods too long
-// for its shared-memory layouts are left to tc_conv2 (same launch sequence, disjoint groups)
-bool tc_conv3_eligible(const FtnInceptionWeights* w);
-void tc_conv3_caps(const FtnInceptionWeights* w, int* caps);
-int tc_conv3_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
-                    __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                              __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
                              long long shared_bias_row = -1, bool dependent = true);
-// does tc_conv3 take a group of period `per` for a kh x kw branch whose image buffer holds `cap` rows?
-__host__ __device__ inline bool c3_group_fits(int per, int kh, int kw, int cap) {
-  const int hw = kw / 2, hh = kh / 2, PW = per + 2 * hw;
-  const int tail = 256 + ((kw + 3) / 4 - 1) * 4;
-  return cap >= tail + 2 * hh * PW || cap / kh >= tail;
-}
-
 // "output phases on M" variant (tc_conv4.cu): 4 phases x 32 channels on M, no cross-quadrant reduction in the
 // drain; whole images only, groups whose padded image does not fit go to tc_conv2
 struct C4Geom { int PW, QT, blocks, NB, O4, rows, hh_eff; };
@@ -100,7 +82,7 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1,
                     bool dependent = true);   // dependent: the previous kernel in the stream is one of this library's
 
-// picks tc_conv4 / tc_conv3 / tc_conv2 / tc_conv / SIMT for one k x k stage
+// picks tc_conv4 (+ tc_conv2 for the groups it leaves) / tc_conv2 / SIMT for one k x k stage
 // shared_bias_row >= 0: `in` is NOT tile-major but one copy per window, row b * L + t for t < L, and row
 // `shared_bias_row` stands for every padded step t >= L (the first 1x1 stage does not depend on the period, so
 // block A's k x k input is computed once instead of once per group); only the tc_conv4 route takes it

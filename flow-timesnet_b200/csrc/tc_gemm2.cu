@@ -271,13 +271,9 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   const int nkb = (a.K1 + G2_BK - 1) / G2_BK;
   const size_t smem = 1024 + (size_t)nkb * ((a.N * 128 + 1023) & ~1023) + (size_t)G2_STAGES * nkb * G2_A_KB + 128 * 4 + 16 +
                       G2_BARS * 8 + 16;
-  static size_t attr[2] = {0, 0};
   const int ai = a.act == FTN_ACT_RELU ? 1 : 0;
-  if (smem > attr[ai]) {
-    if (ai) FTN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else FTN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[ai] = smem;
-  }
+  if (ai) FTN_DYN_SMEM(tc_gemm2_kernel<1>, smem);
+  else FTN_DYN_SMEM(tc_gemm2_kernel<0>, smem);
   const int worst = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   const int grid = worst < sm_count() ? worst : sm_count();
   if (ai) FTN_CUDA(launch_pdl(!a.first_in_call, tc_gemm2_kernel<1>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));

@@ -488,13 +488,9 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   if (trace_path && !trace_dev) cudaMalloc(&trace_dev, (64 * 256) * sizeof(long long));
   if (trace_dev) { cudaMemsetAsync(trace_dev, 0, (64 * 256) * sizeof(long long), st); k.trace = trace_dev; }
   const size_t smem = mid_smem_bytes(K1, K2, F, N3, N4);
-  static size_t attr[2] = {0, 0};
   const int ai = act == FTN_ACT_RELU ? 1 : 0;
-  if (smem > attr[ai]) {
-    if (ai) FTN_CUDA(cudaFuncSetAttribute(tc_mid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else FTN_CUDA(cudaFuncSetAttribute(tc_mid_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[ai] = smem;
-  }
+  if (ai) FTN_DYN_SMEM(tc_mid_kernel<1>, smem);
+  else FTN_DYN_SMEM(tc_mid_kernel<0>, smem);
   const int worst = tc_worst_case_tiles(B, L, max_groups);
   const int grid = worst < sm_count() ? worst : sm_count();
   if (ai) FTN_CUDA(launch_pdl(true, tc_mid_kernel<1>, dim3(grid), dim3(MD_THREADS), smem, st, mH2, mX, mW1, mW2, k));

@@ -366,13 +366,9 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   const int nq = (C + TL_BK - 1) / TL_BK;
   const size_t smem = 1024 + (size_t)nkb * ((C * 128 + 1023) & ~1023) + (size_t)TL_STAGES * nkb * TL_A_KB +
                       (size_t)(TL_STAGES + 1) * nq * TL_A_KB + (3 * 128 + 1024) * 4 + 16 + TL_BARS * 8 + 16;
-  static size_t attr[2] = {0, 0};
   const int ai = act == FTN_ACT_RELU ? 1 : 0;
-  if (smem > attr[ai]) {
-    if (ai) FTN_CUDA(cudaFuncSetAttribute(tc_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else FTN_CUDA(cudaFuncSetAttribute(tc_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[ai] = smem;
-  }
+  if (ai) FTN_DYN_SMEM(tc_tail_kernel<1>, smem);
+  else FTN_DYN_SMEM(tc_tail_kernel<0>, smem);
   const int items = B * ((L + TL_BM - 1) / TL_BM);
   const int grid = items < sm_count() ? items : sm_count();
   if (ai) FTN_CUDA(launch_pdl(true, tc_tail_kernel<1>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -73,7 +73,7 @@ SIGNATURES = {
     "ftn_timing_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_I)]),
     "ftn_spectrum_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ftn_spectrum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
-    "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ftn_plan_build_host": (_I, [C.POINTER(_I64), _I, _I, _I, _I, C.POINTER(FtnPeriodPlan)]),
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
@@ -87,6 +87,11 @@ SIGNATURES = {
     "ftn_timesblock_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ,
                                     C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights), _I, _P, _P, _F, _P, _P,
                                     _SZ, _P]),
+    "ftn_inception_block_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights)]),
+    "ftn_inception_block": (_I, [_P, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights), _I, _I, _P, _P, _SZ, _P]),
+    "ftn_conv2d_grid": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "ftn_rms_norm": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P]),
+    "ftn_recursive_advance": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "ftn_aggregate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ftn_context_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ftn_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -227,10 +232,9 @@ def select_periods(med: torch.Tensor, ssum: torch.Tensor, dtype: torch.dtype, gl
     plan = new_plan(med.device)
     amps = torch.empty(B, k, dtype=dtype, device=med.device)
     weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=med.device)
-    scratch = torch.empty(L // 2 + 1, dtype=torch.float32, device=med.device)
     _check(lib.ftn_select_periods(med.data_ptr(), ssum.data_ptr(), dtype_code(dtype), B, int(global_batch), L, k,
                                   pmax, min_period, plan.data_ptr(), amps.data_ptr(), weights.data_ptr(),
-                                  scratch.data_ptr(), _stream()), "ftn_select_periods")
+                                  _stream()), "ftn_select_periods")
     return plan, amps, weights
 
 
@@ -327,6 +331,47 @@ def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: 
     return out, plan, amps, weights
 
 
+def single_group_plan(period: int, cycles: int, device) -> torch.Tensor:
+    """Device plan holding ONE group (period, cycles, no padding): the fold of an NCHW grid [B, C, cycles, period]."""
+    pl = FtnPeriodPlan()
+    L = int(period) * int(cycles)
+    pl.seq_len, pl.n_raw, pl.n_valid, pl.n_groups, pl.total_rows_per_window = L, 1, 1, 1, L
+    for i in range(FTN_MAX_K):
+        pl.mapping[i] = -1
+        pl.grp_canon[i] = -1
+        pl.grp_row_off[i] = L
+    pl.mapping[0] = 0
+    pl.period[0] = int(period)
+    pl.grp_period[0], pl.grp_pad[0], pl.grp_cycles[0], pl.grp_canon[0], pl.grp_row_off[0] = int(period), 0, int(cycles), 0, 0
+    pl.grp_row_off[FTN_MAX_K] = L
+    return plan_to_device(pl, device)
+
+
+def inception_block(x: torch.Tensor, plan_dev: torch.Tensor, w: FtnInceptionWeights, act: int,
+                    trailing_act: bool) -> torch.Tensor:
+    """One packed InceptionBlock on x[B, L, cin] folded by a ONE-group plan -> fp32 [B, L, cout]."""
+    lib = load()
+    B, L, _ = x.shape
+    out = torch.empty(B, L, int(w.cout), dtype=torch.float32, device=x.device)
+    nbytes = lib.ftn_inception_block_workspace_bytes(B, L, 1, C.byref(w))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _check(lib.ftn_inception_block(x.data_ptr(), dtype_code(x.dtype), B, L, plan_dev.data_ptr(), 1, C.byref(w), act,
+                                   int(trailing_act), out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+           "ftn_inception_block")
+    return out
+
+
+def conv2d_grid(x: torch.Tensor, plan_dev: torch.Tensor, w_taps: torch.Tensor, bias: torch.Tensor, kh: int,
+                kw: int) -> torch.Tensor:
+    """conv2d with zero "same" padding on x[B, L, cin] (fp32) folded by a ONE-group plan; w_taps [kh*kw, cin, cout]."""
+    B, L, cin = x.shape
+    cout = w_taps.shape[-1]
+    out = torch.empty(B, L, cout, dtype=torch.float32, device=x.device)
+    _check(load().ftn_conv2d_grid(x.data_ptr(), B, L, cin, cout, kh, kw, plan_dev.data_ptr(), 1, w_taps.data_ptr(),
+                                  bias.data_ptr(), out.data_ptr(), _stream()), "ftn_conv2d_grid")
+    return out
+
+
 def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     M, K = a.shape
     N = w.shape[0]
@@ -379,6 +424,24 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) ->
     _check(load().ftn_layer_norm(x.data_ptr(), dtype_code(x.dtype), rows, Cc, w.data_ptr(), b.data_ptr(), float(eps),
                                  out.data_ptr(), _stream()), "ftn_layer_norm")
     return out
+
+
+def rms_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty_like(x)
+    _check(load().ftn_rms_norm(x.data_ptr(), dtype_code(x.dtype), rows, Cc, w.data_ptr(), b.data_ptr(), float(eps),
+                               out.data_ptr(), _stream()), "ftn_rms_norm")
+    return out
+
+
+def recursive_advance(window, rate, disp, rates, disps, mark, y_mark, step_counter) -> None:
+    B, L, N = window.shape
+    H = rates.shape[1]
+    Tm = 0 if mark is None else mark.shape[-1]
+    _check(load().ftn_recursive_advance(window.data_ptr(), rate.data_ptr(), disp.data_ptr(), B, L, N, H, rates.data_ptr(),
+                                        disps.data_ptr(), _ptr(mark), _ptr(y_mark), Tm, step_counter.data_ptr(), _stream()),
+           "ftn_recursive_advance")
 
 
 def embed_combine(value, aux, gate, aux_batched: bool, out_dtype: torch.dtype) -> torch.Tensor:

@@ -23,13 +23,31 @@ class GraphedCallable:
     (everything in ``timesnet_forecast`` does when ``check_finite`` is off).  Inputs are copied into
     static buffers before each replay; outputs are the static tensors of the capture (clone them if
     they have to survive the next call).
+
+    The capture bakes in the device pointers of the PACKED weight copies (``_pack.PackedInception``), not the
+    ``nn.Parameter`` storage.  Pass the owning module as ``params_of``: every call then compares the parameters'
+    (pointer, version) fingerprint with the one taken at capture time and re-captures after ``load_state_dict`` or an
+    in-place update instead of silently replaying stale weights.
     """
 
-    def __init__(self, fn: Callable[..., TensorOrTuple], example_inputs: Sequence[torch.Tensor], warmup: int = 2):
+    def __init__(self, fn: Callable[..., TensorOrTuple], example_inputs: Sequence[torch.Tensor], warmup: int = 2,
+                 params_of: Optional[torch.nn.Module] = None):
         if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedCallable needs CUDA tensors as example inputs (no CPU fallback)")
         self._fn = fn
         self._static_in = [t.detach().clone() for t in example_inputs]
+        self._params_of = params_of
+        self._warmup = warmup
+        self.captures = 0
+        self._capture()
+
+    def _fingerprint(self):
+        if self._params_of is None:
+            return None
+        return tuple((p.data_ptr(), p._version) for p in self._params_of.parameters())
+
+    def _capture(self) -> None:
+        fn, warmup = self._fn, self._warmup
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # warm-up: lazy builds, weight packing, smem attributes
@@ -40,6 +58,13 @@ class GraphedCallable:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_out = fn(*self._static_in)
+        self._captured_fp = self._fingerprint()
+        self.captures += 1
+
+    def _refresh(self) -> None:
+        if self._params_of is not None and self._fingerprint() != self._captured_fp:
+            torch.cuda.synchronize()
+            self._capture()                                 # parameters changed: re-pack and re-capture
 
     @property
     def inputs(self):
@@ -47,6 +72,7 @@ class GraphedCallable:
         return self._static_in
 
     def replay(self) -> TensorOrTuple:
+        self._refresh()
         self._graph.replay()
         return self._static_out
 
@@ -59,6 +85,7 @@ class GraphedCallable:
                                  f"{tuple(dst.shape)}/{dst.dtype}, got {tuple(src.shape)}/{src.dtype}")
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        self._refresh()
         self._graph.replay()
         return self._static_out
 
@@ -75,9 +102,10 @@ class PipelinedRunner:
     (reference: predict.py:930-950 moves each batch to the device inside its forecast loop).
     """
 
-    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], depth: int = 2):
+    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], depth: int = 2,
+                 params_of: Optional[torch.nn.Module] = None):
         dev = example_inputs[0].device
-        self._graphs = [GraphedCallable(fn, example_inputs) for _ in range(depth)]
+        self._graphs = [GraphedCallable(fn, example_inputs, params_of=params_of) for _ in range(depth)]
         self._copy = torch.cuda.Stream(device=dev)
         self._back = torch.cuda.Stream(device=dev)                     # result read-back: off the compute stream, so the
                                                                        # next replay does not queue behind a DMA round trip

@@ -11,7 +11,11 @@ Differences a caller can observe, all deliberate:
   * CUDA only, float32 / bfloat16 activations only -- CPU tensors and fp16 raise
     (BASELINE.json north_star: "no CPU fallback").
   * forward-only: outputs carry no autograd graph, dropout is the identity
-    (inference semantics; the reference's eval mode).
+    (inference semantics; the reference's eval mode).  A module left in train
+    mode with dropout > 0 warns once; an input that requires grad raises.
+  * multi-rank period search is OPT-IN: like the reference under DDP every rank
+    selects periods from its local batch unless
+    ``timesnet_forecast.parallel.share_period_search(model)`` was called.
   * periods stay on the device: ``TimesBlock`` no longer does the reference's
     ~20 ``.item()`` syncs per call.  The diagnostic attributes
     (``last_selected_periods``, ``_last_group_count`` ...) read the plan back
@@ -29,6 +33,7 @@ from __future__ import annotations
 
 import math
 import os
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -37,7 +42,7 @@ from torch import nn
 
 from .. import _native as nv
 from .._pack import PackedInception, pack_inception_block, params_fingerprint
-from ..parallel import resolve_group
+from ..parallel import reduce_spectrum_sum, resolve_group
 
 __all__ = [
     "FFTPeriodSelector", "PeriodGroupResult", "PeriodGrouper", "InceptionBranch", "InceptionBlock", "TimesBlock",
@@ -47,6 +52,22 @@ __all__ = [
 
 def _act_code(name: str) -> int:
     return nv.FTN_ACT_RELU if name == "relu" else nv.FTN_ACT_GELU
+
+
+_warned_train = set()
+
+
+def _forward_only_guard(module: nn.Module, x: torch.Tensor, dropout: float) -> None:
+    """The build is forward-only: say so instead of silently returning grad-less, dropout-free outputs."""
+    if torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.requires_grad:
+        raise RuntimeError(
+            f"{type(module).__name__}: input requires grad, but the B200 build is forward-only (its outputs carry no "
+            "autograd graph); detach the input or wrap the call in torch.no_grad()")
+    if module.training and dropout > 0.0 and id(module) not in _warned_train:
+        _warned_train.add(id(module))
+        warnings.warn(
+            f"{type(module).__name__} is in train mode with dropout={dropout}: the B200 build is forward-only and runs "
+            "the eval-mode path (dropout = identity); call .eval()", RuntimeWarning, stacklevel=3)
 
 
 # --------------------------------------------------------------------------- #
@@ -77,10 +98,14 @@ class FFTPeriodSelector(nn.Module):
 
     ``forward`` keeps the reference contract ``x[B,L,C] -> (periods[K] long,
     amplitudes[B,K] x.dtype)``.  ``search`` is the sync-free entry TimesBlock
-    uses.  When ``torch.distributed`` is initialised and the batch is sharded
-    over ranks, the batch-summed spectrum is all-reduced (one message of
-    L/2+1 floats) so every rank selects the same periods (SURVEY.md section 8e);
-    set ``process_group = False`` to keep the search rank-local.
+    uses.  Like the reference under DDP, every rank selects periods from its
+    LOCAL batch by default (``process_group = False``).  Opt in to the shared
+    search of SURVEY.md section 8e with ``parallel.share_period_search(model, group)``
+    (sets ``process_group`` to a group, or ``None`` for the default group): the
+    batch-summed spectrum (L/2+1 floats + the window count) is then all-reduced
+    so every rank selects the same periods.  Every rank must call ``forward``
+    the same number of times; a rank holding zero windows still enters the
+    collective.
     """
 
     def __init__(self, k_periods: int, pmax: int, min_period_threshold: int = 1) -> None:
@@ -88,7 +113,7 @@ class FFTPeriodSelector(nn.Module):
         self.k = int(max(0, k_periods))
         self.pmax = int(max(1, pmax))
         self.min_period_threshold = int(min(self.pmax, int(max(1, min_period_threshold))))
-        self.process_group = None          # None = default group when initialised, False = never reduce
+        self.process_group = False         # False = rank-local (reference behaviour); None / a group = shared search
         self._last_plan: Optional[PeriodPlan] = None
         self._empty_device = torch.device("cpu")
 
@@ -117,28 +142,29 @@ class FFTPeriodSelector(nn.Module):
         B, L, C = x.shape
         self._last_plan = None
         self._empty_device = x.device
-        if self.k <= 0 or L <= 1 or C <= 0 or B <= 0:
-            return None                                              # timesnet.py:89-90
+        if self.k <= 0 or L <= 1 or C <= 0:
+            return None                                              # timesnet.py:89-90 (same on every rank)
         nbins = L // 2 + 1
         k = min(self.k, nbins - 1)                                   # timesnet.py:122-126
         if k <= 0:
             return None
         if k > nv.FTN_MAX_K:
             raise ValueError(f"k_periods={self.k} exceeds the supported maximum {nv.FTN_MAX_K}")
-        x = nv.require_cuda(x, "x")
         group, world = self._world()
+        if B <= 0:
+            if world > 1:                                            # an empty shard still enters the collective
+                reduce_spectrum_sum(torch.zeros(nbins + 1, dtype=torch.float32, device=x.device), self.process_group)
+            return None                                              # timesnet.py:89-90
+        x = nv.require_cuda(x, "x")
         if world == 1:                                                 # nothing to reduce: fused 3-launch search
             plan_dev, amps, weights, _, _ = nv.period_search(x, k, self.pmax, self.min_period_threshold)
             self._last_plan = PeriodPlan(plan_dev, amps, weights, k)
             return self._last_plan
         med, ssum = nv.spectrum(x)                                     # ssum = [sum_b median spectrum | B]
-        if world > 1:
-            import torch.distributed as dist
-            # the only collective of the path: F sums + the window count in one message, so ragged
-            # shards need no host round trip (the select kernel divides by the reduced count)
-            dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=group)
-        plan_dev, amps, weights = nv.select_periods(med, ssum, x.dtype, B if world == 1 else 0, L, k, self.pmax,
-                                                    self.min_period_threshold)
+        # the only collective of the path: F sums + the window count in one message, so ragged
+        # shards need no host round trip (the select kernel divides by the reduced count)
+        reduce_spectrum_sum(ssum, self.process_group)
+        plan_dev, amps, weights = nv.select_periods(med, ssum, x.dtype, 0, L, k, self.pmax, self.min_period_threshold)
         self._last_plan = PeriodPlan(plan_dev, amps, weights, k)
         return self._last_plan
 
@@ -409,9 +435,25 @@ class InceptionBranch(nn.Module):
         self.branch = nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise RuntimeError(
-            "InceptionBranch is a parameter container in the B200 build: the bank runs fused inside "
-            "TimesBlock / InceptionBlock.forward (libflowtimes), not branch by branch")
+        """``branch(x)`` on an NCHW grid (timesnet.py:592-593): each Conv2d runs as an implicit GEMM on the
+        zero-copy fold of the grid (``ftn_conv2d_grid``; one group, period = W, H cycles)."""
+        if x.ndim != 4:
+            raise ValueError("InceptionBranch expects an NCHW grid [B, C, H, W]")
+        x = nv.require_cuda(x, "x")
+        B, _, H, W = x.shape
+        dt = x.dtype
+        with torch.no_grad():
+            seq = x.permute(0, 2, 3, 1).reshape(B, H * W, -1).to(torch.float32).contiguous()
+            plan = nv.single_group_plan(W, H, x.device)
+            for conv in self.branch:
+                kh, kw = conv.kernel_size
+                if kh % 2 == 0 or kw % 2 == 0:
+                    raise ValueError("libflowtimes convolutions need odd kernel sizes (\"same\" padding k // 2)")
+                w = conv.weight.detach().to(device=x.device, dtype=torch.float32)
+                taps = w.permute(2, 3, 1, 0).reshape(kh * kw, w.shape[1], w.shape[0]).contiguous()
+                seq = nv.conv2d_grid(seq, plan, taps, conv.bias.detach().to(device=x.device, dtype=torch.float32).contiguous(),
+                                     kh, kw)
+            return seq.reshape(B, H, W, -1).permute(0, 3, 1, 2).to(dt)
 
 
 def _parse_kernel_set(kernel_set) -> List[Tuple[int, int]]:
@@ -461,9 +503,21 @@ class InceptionBlock(nn.Module):
         return self._packed
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise RuntimeError(
-            "InceptionBlock.forward on a bare NCHW grid is not part of the B200 hot path; call it through "
-            "TimesBlock (which fuses fold -> bank -> delta on the device)")
+        """``act(proj(cat_j paths_j(x))) + res_proj(x)`` on an NCHW grid (timesnet.py:645-654) through the packed
+        block (``ftn_inception_block``): the grid is one period group of the zero-copy fold (period W, H cycles)."""
+        if x.ndim != 4:
+            raise ValueError("InceptionBlock expects an NCHW grid [B, C, H, W]")
+        x = nv.require_cuda(x, "x")
+        _forward_only_guard(self, x, float(self.dropout.p))
+        B, _, H, W = x.shape
+        dt = x.dtype
+        if self.proj.weight.device != x.device:
+            self.to(x.device)
+        with torch.no_grad():
+            seq = x.permute(0, 2, 3, 1).reshape(B, H * W, -1).to(torch.float32).contiguous()
+            act = nv.FTN_ACT_RELU if isinstance(self.act, nn.ReLU) else nv.FTN_ACT_GELU
+            out = nv.inception_block(seq, nv.single_group_plan(W, H, x.device), self.packed(x.device).struct, act, False)
+            return out.reshape(B, H, W, -1).permute(0, 3, 1, 2).to(dt)
 
 
 # --------------------------------------------------------------------------- #
@@ -591,7 +645,7 @@ class TimesBlock(nn.Module):
         views, call the module, subtract the grid.  The module is the compute here."""
         B, L, C = x.shape
         h = plan.host()
-        delta = torch.zeros(nv.FTN_MAX_K, B, L, C, dtype=x.dtype, device=x.device)
+        delta = torch.empty(max(1, h.n_groups), B, L, C, dtype=x.dtype, device=x.device)
         xp = x.permute(0, 2, 1)
         for g in range(h.n_groups):
             p, pad, cyc = h.grp_period[g], h.grp_pad[g], h.grp_cycles[g]
@@ -642,6 +696,7 @@ class TimesBlock(nn.Module):
             raise RuntimeError("TimesBlock.period_selector has not been set")
         x = nv.require_cuda(x, "x")
         nv.dtype_code(x.dtype)
+        _forward_only_guard(self, x, self._dropout)
         self._period_calls = getattr(self, "_period_calls", 0) + 1
         if self.inception is None:
             if self._configured_d_model is not None and x.size(-1) != self._configured_d_model:
@@ -719,7 +774,7 @@ class PositionalEmbedding(nn.Module):
 
 
 class RMSNorm(nn.Module):
-    """Parameter container for the optional ``rms`` embedding norm (timesnet.py:1132-1159)."""
+    """Root-mean-square normalisation with affine parameters (timesnet.py:1132-1159); ``ftn_rms_norm``."""
 
     def __init__(self, d_model: int, eps: float = 1e-5) -> None:
         super().__init__()
@@ -730,7 +785,13 @@ class RMSNorm(nn.Module):
         self.bias = nn.Parameter(torch.zeros(int(d_model)))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("embed_norm_mode='rms' is outside the B200 hot path (SURVEY.md section 8)")
+        if x.size(-1) != self.weight.numel():
+            raise ValueError("RMSNorm dimension mismatch")
+        x = nv.require_cuda(x, "x")
+        nv.dtype_code(x.dtype)
+        with torch.no_grad():
+            return nv.rms_norm(x, self.weight.detach().to(device=x.device, dtype=torch.float32).contiguous(),
+                               self.bias.detach().to(device=x.device, dtype=torch.float32).contiguous(), self.eps)
 
 
 class DataEmbedding(nn.Module):
@@ -791,8 +852,6 @@ class DataEmbedding(nn.Module):
                 out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         if x.ndim not in (3, 4):
             raise ValueError("DataEmbedding expects input shaped [B, L, C] or [B, L, N, C]")
-        if self.embed_norm_mode == "rms":
-            raise NotImplementedError("embed_norm_mode='rms' is outside the B200 hot path")
         shape4 = None
         if x.ndim == 4:
             B4, L4, N4, C4 = x.shape
@@ -832,10 +891,11 @@ class DataEmbedding(nn.Module):
                 gate = self.gate.detach().float().reshape(-1).contiguous()
             else:
                 gate = torch.ones(d_model, dtype=torch.float32, device=dev)
-            if self.embed_norm_mode == "layer":
+            if self.embed_norm_mode in ("layer", "rms"):                       # timesnet.py:1313-1316
                 out = nv.embed_combine(value, aux, gate, batched, torch.float32)
-                out = nv.layer_norm(out, self.norm.weight.detach().float().contiguous(),
-                                    self.norm.bias.detach().float().contiguous(), self.norm.eps).to(out_dtype)
+                norm_fn = nv.layer_norm if self.embed_norm_mode == "layer" else nv.rms_norm
+                out = norm_fn(out, self.norm.weight.detach().float().contiguous(),
+                              self.norm.bias.detach().float().contiguous(), self.norm.eps).to(out_dtype)
             else:
                 out = nv.embed_combine(value, aux, gate, batched, out_dtype)
         if shape4 is not None:
@@ -1225,17 +1285,21 @@ class TimesNet(nn.Module):
         taking the same tensors (positionally, ``None`` entries dropped).  Turns ``check_finite`` off:
         the two host-syncing sanity checks of timesnet.py:2094-2097 cannot live inside a graph."""
         from ..cuda_graphs import GraphedCallable
-        self.check_finite = False
         names = ["x", "x_mark", "series_static", "series_ids"]
         given = [x, x_mark, series_static, series_ids]
         idx = [i for i, t in enumerate(given) if t is not None]
 
         def run(*tensors):
             kw = {names[i]: t for i, t in zip(idx, tensors)}
-            return self.forward(**kw)
+            keep = self.check_finite
+            self.check_finite = False                       # scoped to the graphed callable (capture and warm-up)
+            try:
+                return self.forward(**kw)
+            finally:
+                self.check_finite = keep
 
         run(*[given[i] for i in idx])                       # lazy build outside of any capture
-        return GraphedCallable(run, [given[i] for i in idx])
+        return GraphedCallable(run, [given[i] for i in idx], params_of=self)
 
     def forward(self, x: torch.Tensor, x_mark: Optional[torch.Tensor] = None,
                 series_static: Optional[torch.Tensor] = None,
@@ -1251,6 +1315,7 @@ class TimesNet(nn.Module):
         if x.dtype != torch.float32:
             raise TypeError("TimesNet.forward takes float32 input (the reference rejects half inputs too); "
                             "use stack_dtype=torch.bfloat16 for the bf16 TimesBlock stack")
+        _forward_only_guard(self, x, self.dropout)
         L = self.input_len
         dev = x.device
         with torch.no_grad():

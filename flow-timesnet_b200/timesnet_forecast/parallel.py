@@ -25,26 +25,44 @@ def shard_batch(batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def resolve_group(process_group) -> Tuple[Optional[object], int]:
-    """``process_group`` semantics of ``FFTPeriodSelector``: ``None`` = default group when
-    torch.distributed is initialised, ``False`` = never reduce.  Returns ``(group, world_size)``."""
+    """``process_group`` semantics of ``FFTPeriodSelector``: ``False`` (the default) = never
+    reduce, ``None`` = default group when torch.distributed is initialised, else the given group.  Returns ``(group, world_size)``."""
     import torch.distributed as dist
     if process_group is False or not dist.is_available() or not dist.is_initialized():
         return None, 1
     return process_group, dist.get_world_size(process_group)
 
 
-def reduce_spectrum_sum(amp_sum: torch.Tensor, local_batch: int, process_group=None) -> Tuple[torch.Tensor, int]:
-    """All-reduce (SUM) the batch-summed spectrum in place and return it with the global window count.
+def share_period_search(model_or_selector, process_group=None):
+    """Opt in to the SHARED period search of SURVEY.md section 8e: the batch-summed amplitude spectrum is all-reduced
+    over ``process_group`` (``None`` = the default group) so that every rank folds with the same periods -- the
+    periods the single-process reference would pick on the concatenated batch.  Without this call every rank selects
+    from its local batch, which is what a reference checkout running DDP does.
 
-    Ranks may hold different numbers of windows (ragged last shard), so the count is reduced too --
-    it rides in the same message as one extra float-exact integer slot (counts < 2**24)."""
+    Accepts a ``TimesNet`` (its ``period_selector``), a ``TimesBlock`` or an ``FFTPeriodSelector``.  Every rank of the
+    group must then call ``forward`` the same number of times (the search contains a collective)."""
+    sel = getattr(model_or_selector, "period_selector", model_or_selector)
+    if not hasattr(sel, "process_group"):
+        raise TypeError("share_period_search expects a TimesNet, a TimesBlock or an FFTPeriodSelector")
+    sel.process_group = process_group
+    return sel
+
+
+def local_period_search(model_or_selector):
+    """Undo ``share_period_search``: rank-local period selection (the default)."""
+    sel = getattr(model_or_selector, "period_selector", model_or_selector)
+    sel.process_group = False
+    return sel
+
+
+def reduce_spectrum_sum(msg: torch.Tensor, process_group=None) -> torch.Tensor:
+    """The one collective of the path: all-reduce (SUM), in place, the ``[F + 1]`` fp32 message ``ftn_spectrum``
+    writes -- ``F`` batch-summed channel-median amplitudes followed by the number of windows summed.  Ranks may hold
+    different numbers of windows (ragged last shard, even zero); the count rides in the same message as one
+    float-exact integer slot (counts < 2**24), so the selection tail divides by the GLOBAL batch without a host
+    round trip.  Called by ``FFTPeriodSelector.search`` (NCCL on the B200 box) and by the CPU tests (gloo)."""
     import torch.distributed as dist
     group, world = resolve_group(process_group)
-    if world == 1:
-        return amp_sum, int(local_batch)
-    msg = torch.empty(amp_sum.numel() + 1, dtype=torch.float32, device=amp_sum.device)
-    msg[:-1] = amp_sum.reshape(-1).to(torch.float32)
-    msg[-1] = float(local_batch)
-    dist.all_reduce(msg, op=dist.ReduceOp.SUM, group=group)
-    amp_sum.copy_(msg[:-1].reshape(amp_sum.shape))
-    return amp_sum, int(round(float(msg[-1].item())))
+    if world > 1:
+        dist.all_reduce(msg, op=dist.ReduceOp.SUM, group=group)
+    return msg

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 8
+#define FTN_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -154,8 +154,7 @@ FTN_API int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* a
  * amps: [B, k] dtype, columns >= n_valid are zero. */
 FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, int dtype, int B,
                        int global_batch, int L, int k, int pmax, int min_period,
-                       FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/,
-                       float* scores_ws /*[L/2+1] scratch*/, void* stream);
+                       FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/, void* stream);
 
 /* Single-rank fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the
  * selection kernel (3 launches instead of 5; nothing to all-reduce).  Same outputs as the pair:
@@ -190,14 +189,29 @@ FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const
 FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
                                 void* out, void* stream);
 /* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
- * use_tc = 4 phases-on-M tcgen05 kernel, 3 positions-on-N tcgen05 kernel (both + tc_conv2 for long periods),
- * 2 image-resident tcgen05 kernel,
- * 1 tile-patch tcgen05 kernel, 0 SIMT kernel. */
+ * use_tc = 4 phases-on-M tcgen05 kernel (+ the image-resident kernel for long periods),
+ * 2 image-resident tcgen05 kernel, 0 SIMT kernel. */
 FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                  int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,
                     int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b,
                     int act, void* delta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- one InceptionBlock / one Conv2d on a folded grid ----------------------
+ * The reference's InceptionBlock.forward / InceptionBranch.forward take an NCHW grid [B, C, H, W]
+ * (timesnet.py:645-654, :592-593; pinned by tests/test_inception_block.py).  In the zero-copy fold that grid is
+ * x[B][L = H*W][C] with ONE period group (period W, H cycles, pad 0), so both run as a one-group plan through the
+ * same implicit-GEMM stages as the TimesBlock chain (fp32 math).
+ *   ftn_inception_block: out = act(proj(cat_j branch_j(x))) + res_proj(x)   [then act again if trailing_act]
+ *   ftn_conv2d_grid    : out = conv2d(x, w, bias), odd kernel, zero "same" padding
+ * out is fp32, row = B * grp_row_off[g] + b * (L + pad_g) + t, i.e. [B][L][cout] for a one-group plan.
+ * w of ftn_conv2d_grid: [kh*kw][cin][cout] fp32. */
+FTN_API size_t ftn_inception_block_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* w);
+FTN_API int ftn_inception_block(const void* x, int dtype, int B, int L, const FtnPeriodPlan* plan, int max_groups,
+                                const FtnInceptionWeights* w, int act, int trailing_act, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+FTN_API int ftn_conv2d_grid(const float* x, int B, int L, int cin, int cout, int kh, int kw, const FtnPeriodPlan* plan,
+                            int max_groups, const float* w, const float* bias, float* out, void* stream);
 
 /* ---- K2+K3+K4 in one call (bf16 tensor-core route) ------------------------
  * out = [LayerNorm](x + sum_g w[b][g] * delta_g) with the last 1x1 stage, the weighted aggregation, the
@@ -248,6 +262,11 @@ FTN_API int ftn_linear(const float* a, const float* w, const float* bias, int M,
 FTN_API int ftn_layer_norm(const void* x, int dtype, int rows, int C, const float* w, const float* b,
                    float eps, void* out, void* stream);
 
+/* RMSNorm over the last dim: x * rsqrt(mean(x^2) + eps) * w + b, fp32 statistics.
+ * replaces RMSNorm.forward (timesnet.py:1132-1159). */
+FTN_API int ftn_rms_norm(const void* x, int dtype, int rows, int C, const float* w, const float* b,
+                 float eps, void* out, void* stream);
+
 /* DataEmbedding epilogue: out[b,t,c] = value[b,t,c] + gate[c] * aux[t][c]  -> dtype_out
  * (decoupled norm mode, aux = LayerNorm(PE) precomputed)   replaces timesnet.py:1306-1312 */
 FTN_API int ftn_embed_combine(const float* value, const float* aux, const float* gate, int aux_batched,
@@ -272,6 +291,18 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
  * mask: NULL or uint8 [count]; partial: >= 2*1024 floats scratch; out: 1 float. */
 FTN_API int ftn_nb_nll(const float* y, const float* rate, const float* disp, const uint8_t* mask,
                int64_t count, float eps, float* partial, float* out, void* stream);
+
+/* ---- rolling one-step forecast, device resident ----------------------------
+ * replaces the tail of the loop body of forecast_recursive_batch (predict.py:333-341):
+ *   s = *step_counter;  rates[b][s][n] = rate[b][0][n];  disps[b][s][n] = disp[b][0][n];
+ *   window = cat(window[:, 1:], rate)            (in place, [B][L][N] fp32)
+ *   mark   = cat(mark[:, 1:], y_mark[:, s])      (in place, [B][L][mark_features]; NULL = no time marks)
+ *   *step_counter = s + 1
+ * The step index lives on the device, so ONE captured CUDA graph of (forward + this call) is replayed H times
+ * without the host ever looking at it.  rates / disps: [B][H][N]; y_mark: [B][H][mark_features]. */
+FTN_API int ftn_recursive_advance(float* window, const float* rate, const float* disp, int B, int L, int N, int H,
+                                  float* rates, float* disps, float* mark, const float* y_mark, int mark_features,
+                                  int* step_counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -438,9 +438,21 @@ def data_embedding(x: Tensor, w: Weights, x_mark: Optional[Tensor] = None, mode:
     if mode == "decoupled":
         auxn = layer_norm_fp32(aux, w["embedding.aux_norm.weight"], w["embedding.aux_norm.bias"])   # :1308
         return value + w["embedding.gate"].to(value.dtype) * auxn          # :1312
+    out = value + aux                                                      # :1314
+    if mode == "layer":
+        return layer_norm_fp32(out, w["embedding.norm.weight"], w["embedding.norm.bias"])   # :1315-1317
+    if mode == "rms":
+        return rms_norm(out, w["embedding.norm.weight"], w["embedding.norm.bias"])          # :1318-1320
     if mode == "none":
-        return value + aux
+        return out
     raise NotImplementedError(mode)
+
+
+def rms_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> Tensor:
+    """RMSNorm.forward (timesnet.py:1132-1159)."""
+    xc = x.to(torch.float32) if x.dtype in (torch.float16, torch.bfloat16) else x
+    scale = torch.rsqrt(xc.pow(2).mean(dim=-1, keepdim=True) + eps)
+    return (xc * scale * weight.to(xc.dtype) + bias.to(xc.dtype)).to(x.dtype)
 
 
 # --------------------------------------------------------------------------- #

@@ -30,10 +30,10 @@ def test_tc_linear_matches_fp32_matmul(M, K, N):
 @pytest.mark.parametrize("mid,L,periods", [(32, 336, [24, 12, 7, 48, 6]), (32, 336, [335, 100, 168]), (32, 336, [2, 3, 5]),
                                             (16, 96, [24, 12, 7, 48, 6, 95]), (32, 28, [27, 14, 7]), (32, 96, [1, 2, 48]),
                                             (32, 720, [6, 24, 359])])
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [2, 4])
 def test_tc_conv_matches_simt_conv(mid, L, periods, variant):
-    if variant >= 3 and mid != 32:
-        pytest.skip("tc_conv3 / tc_conv4 are written for mid = 32")
+    if variant == 4 and mid != 32:
+        pytest.skip("tc_conv4 is written for mid = 32")
     """k x k stage alone: tcgen05 implicit-GEMM kernel vs the fp32-math SIMT kernel on the same
     tile-major bf16 activations (identical inputs, fp32 accumulation in both -> <= 1 bf16 ulp)."""
     import flowtimes_synth as syn

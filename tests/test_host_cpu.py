@@ -175,8 +175,9 @@ def _gloo_worker(rank: int, world: int, port: int, out_dir: str):
         x = syn.white_features(B, L, C, seed=5)              # same full batch on both ranks
         lo, hi = shard_batch(B, rank, world)
         med_local = orc.channel_median_spectrum(x[lo:hi])    # [B/world, F]
-        ssum = med_local.sum(dim=0)
-        total, global_b = reduce_spectrum_sum(ssum, hi - lo, None)
+        msg = torch.cat([med_local.sum(dim=0), torch.tensor([float(hi - lo)])])   # the layout ftn_spectrum writes
+        reduce_spectrum_sum(msg, None)
+        total, global_b = msg[:-1], int(msg[-1].item())
         assert global_b == B
         sel = orc.select_from_spectrum(med_local, total, global_b, L, k, L - 1, 1, x.dtype)
         torch.save({"periods": sel.periods, "freq": sel.freq_indices, "mean": total / global_b, "lo": lo, "hi": hi},

@@ -138,3 +138,87 @@ def test_model_toy(golden_dir):
     assert torch.isnan(orc.nb_nll(c["y"], c["rate"], c["disp"], c["mask"]))      # NaN target poisons the masked sum
     assert _rel(orc.nb_nll(c["y_finite"], c["rate"], c["disp"], c["mask"]), c["nll"]) < 1e-6
     assert _rel(orc.nb_nll(c["y_finite"], c["rate"], c["disp"]), c["nll_nomask"]) < 1e-6
+
+
+# --------------------------------------------------------------------------- #
+# round 2 fixtures (oracle/make_golden_r2.py)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("key", ["traffic.planted.f32", "traffic.white.bf16"])
+def test_r2_traffic_stack(golden_dir, key):
+    c = torch.load(golden_dir / "r2_stack_traffic.pt")[key]
+    d = dict(c["workload"])
+    d["kernel_set"] = tuple(tuple(k) for k in d["kernel_set"])
+    wl = syn.Workload(**d)
+    dname = key.split(".")[2]
+    w = syn.stack_weights(wl, seed=c["weight_seed"])
+    x = (syn.planted_features(wl.B, wl.T, wl.d_model, 0) if c["input"] == "planted"
+         else syn.white_features(wl.B, wl.T, wl.d_model, 1)).to(syn.torch_dtype(dname))
+    trace = []
+    y = orc.stack_forward(x, w, wl.n_layers, wl.k_periods, wl.T, wl.min_period_threshold, trace=trace)
+    assert [t.selection.periods.tolist() for t in trace] == c["periods"]
+    assert _rel(_sub(y), c["out_sub"]) < (1e-5 if dname == "f32" else 1.6e-2)
+
+
+def test_r2_recursive5_forward(golden_dir):
+    c = torch.load(golden_dir / "r2_recursive5.pt")
+    d = dict(c["workload"])
+    d["kernel_set"] = tuple(tuple(k) for k in d["kernel_set"])
+    wl = syn.Workload(**d)
+    g = torch.Generator().manual_seed(c["x_seed"])
+    x = torch.poisson(torch.full((wl.B, wl.T, wl.N), 4.0), generator=g)
+    static = torch.randn(wl.B, wl.N, wl.static_features, generator=g)
+    sd = syn.seeded_state(c["state_keys"], seed=c["state_seed"])
+    cfg = orc.ModelCfg(wl.T, wl.H, wl.d_model, wl.n_layers, wl.k_periods, wl.mode, "gelu", wl.min_period_threshold, 1e-3,
+                       True, wl.context_rank)
+    n = 64                                              # period selection is shared: keep the whole batch for it
+    r, dd = orc.timesnet_forward(x, sd, cfg, series_static=static, series_ids=torch.arange(wl.N))
+    assert _rel(r, c["rate"]) < 1e-5 and _rel(dd, c["disp"]) < 1e-5
+    assert _rel(r[:n], c["rec_rate"][:n, :1]) < 1e-5
+
+
+def test_r2_embedding_with_marks(golden_dir):
+    g = torch.load(golden_dir / "r2_embed_mark.pt")
+    for mode in ("decoupled", "none", "layer", "rms"):
+        c = g[f"embed.{mode}"]
+        w = {"embedding." + k: v for k, v in c["state"].items()}
+        assert _rel(orc.data_embedding(c["x"], w, c["mark"], mode), c["out"]) < 1e-6, mode
+        assert _rel(orc.data_embedding(c["x"], w, None, mode), c["out_nomark"]) < 1e-6, mode
+    for name in ("mark_direct", "mark_recursive"):
+        c = g[name]
+        d = dict(c["workload"])
+        d["kernel_set"] = tuple(tuple(k) for k in d["kernel_set"])
+        wl = syn.Workload(**d)
+        cfg = orc.ModelCfg(wl.T, wl.H, wl.d_model, wl.n_layers, wl.k_periods, wl.mode, "gelu", wl.min_period_threshold,
+                           1e-3, wl.context_rank > 0, wl.context_rank)
+        x = syn.planted_series(wl.B, c["T_in"], wl.N, seed=c["x_seed"])
+        r, dd = orc.timesnet_forward(x, c["state"], cfg, x_mark=c["x_mark"], series_ids=torch.arange(wl.N))
+        assert _rel(r, c["rate"]) < 1e-5 and _rel(dd, c["disp"]) < 1e-5, name
+
+
+def test_r2_block_env_modes(golden_dir):
+    g = torch.load(golden_dir / "r2_block_env.pt")
+    for name, c in g.items():
+        d = dict(c["workload"])
+        d["kernel_set"] = tuple(tuple(k) for k in d["kernel_set"])
+        wl = syn.Workload(**d)
+        w = syn.stack_weights(wl, seed=c["weight_seed"])
+        for depth, r in c["by_depth"].items():
+            base = 2.0 if "TIMES_PERIOD_BINNING" in c["env"] else None
+            mu = None
+            if "TIMES_PERIOD_MAX_UNIQ" in c["env"]:
+                raw = c["env"]["TIMES_PERIOD_MAX_UNIQ"]
+                mu = int(raw) if raw.isdigit() else {0: 3, 1: 1}[depth]
+            tr = orc.timesblock_from_periods(c["x"], c["periods"], c["amps"], w, "blocks.0.inception.", "gelu",
+                                             log_base=base, max_unique=mu)
+            assert len(tr.groups.periods) == r["groups"], (name, depth)
+            assert _rel(tr.out, r["fixed_out"]) < 1e-5, (name, depth)
+
+
+def test_r2_inception_nchw(golden_dir):
+    g = torch.load(golden_dir / "r2_inception_nchw.pt")
+    for name, c in g.items():
+        if c["kind"] == "block":
+            y = orc.inception_block(c["x"], c["state"], "", c["act"])
+            assert _rel(y, c["out"]) < 1e-5, name
+        elif c["kind"] == "rms":
+            assert _rel(orc.rms_norm(c["x"], c["state"]["weight"], c["state"]["bias"]), c["out"]) < 1e-6
