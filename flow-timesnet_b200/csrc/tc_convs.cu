@@ -1,0 +1,463 @@
+// K3, k x k stage, general streaming variant: implicit-GEMM convolution on tcgen05 tensor cores for ANY branch width
+// mid (a multiple of 16, up to 128) in both activation formats of the tensor-core chain:
+//   NS = 1  bf16 activations [rows][NB]                     (one MMA per tap and K16 step)
+//   NS = 3  fp32 activations as three bf16 planes [rows][3 NB]   (tc_gemm.cu: six MMAs per tap and K16 step,
+//           fp32 accumulate in TMEM -- the fp32 configurations keep the 1e-4 bound on the tensor cores)
+//
+//   out[pos][n] = bias[n] + sum_{dr,dw} sum_c in[pos shifted by (dr,dw)][c] * W[dr][dw][n][c]
+// on the folded [cycles, period] grid with zero "same" padding (timesnet.py:588, :1044-1057).
+//
+// tc_conv4 (mid = 32, bf16) keeps whole images and Toeplitz weight windows resident; tc_conv2 keeps the weights of a
+// branch resident.  Neither scales: at mid = 64 one 7 x 7 branch is 401 KB of bf16 weights (1.2 MB as three planes).
+// Here NOTHING is resident.  A unit is one 128-position tile of one (group, window, branch) image in the padded-width
+// flattening (row pitch PW = p + 2 hw, so a tap (dr, dw) is a pure row shift of dr PW + dw); per unit
+//   * the zero-padded input rows stream through a ring of SEGMENT buffers in the un-swizzled interleaved K-major
+//     layout [16-byte channel chunk][row][8 ch] (a row shift = +16 bytes on the descriptor start address): either ONE
+//     band holding the halo of all tap rows (short periods, "mode A") or one 128 + 2 hw row segment per tap row
+//     ("mode B", long periods) -- loader warps, cp.async with zero fill;
+//   * the weights stream through a ring of slots, one tap row (or one tap when a row does not fit) per slot, each a
+//     single cp.async.bulk of a host-packed image [tap][plane][chunk][n][8] -- one producer thread;
+//   * one warp issues the MMAs (M128, N = mid, K16) into a double-buffered TMEM accumulator, eight warps drain it
+//     (+bias, bf16 or three-plane split, store) while the next unit's MMAs run.
+// With N = mid <= 64 an MMA costs what an N = 128 one does (the 4 KB A fetch bounds it), so the kernel is bound by its
+// MMA issue rate; at mid = 64 that is half of the tensor peak, which tc_conv4's phases-on-M trick would double for
+// mid = 32 only.
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace ftn {
+
+using namespace tc;
+
+constexpr int CS_THREADS = 14 * 32;   // warp 0 MMA issuer + TMEM owner, warp 1 weight producer, 2-5 loaders, 6-13 epilogue
+constexpr int CS_LOADERS = 128;
+constexpr int CS_BM = 128;
+constexpr int CS_NSEG = 2;
+constexpr int CS_WSLOTS_MAX = 8;
+
+struct TcConvsArgs {
+  const FtnPeriodPlan* plan;
+  int B, L;
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;
+  int ld;          // row pitch of in / out in elements (all planes)
+  int NB;          // n_branch * mid = width of one plane
+  int mid, n_branch, ns;
+  int seg_cap;     // rows one segment buffer holds
+  int w_slots, w_slot_bytes;
+  int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH], ut[FTN_MAX_BRANCH];   // ut: taps per weight slot (kw or 1)
+  const uint8_t* w[FTN_MAX_BRANCH];    // [tap][plane][chunk][n][8] bf16
+  const float* bias[FTN_MAX_BRANCH];
+};
+
+struct CsGroup {
+  int per, cyc, row_tiles_before, rt, S, unit0;
+  int tiles[FTN_MAX_BRANCH];
+};
+
+struct CsUnit {
+  int g, b, j, per, cyc, PW, QT, q0, hw, hh, kh, kw, mode_a, margin, rows;
+  size_t img_row0;
+};
+
+__device__ __forceinline__ bool cs_decode(const CsGroup* grp, int G, int n_branch, const TcConvsArgs& p, int unit, CsUnit& u) {
+  int g = 0;
+  while (g < G && unit >= grp[g].unit0 + p.B * grp[g].S) ++g;
+  if (g >= G) return false;
+  const CsGroup& gr = grp[g];
+  int r = unit - gr.unit0;
+  const int b = r / gr.S;
+  r -= b * gr.S;
+  int j = 0;
+  while (j + 1 < n_branch && r >= gr.tiles[j]) { r -= gr.tiles[j]; ++j; }
+  u.g = g; u.b = b; u.j = j; u.per = gr.per; u.cyc = gr.cyc;
+  u.kh = p.kh[j]; u.kw = p.kw[j]; u.hw = u.kw / 2; u.hh = u.kh / 2;
+  u.PW = gr.per + 2 * u.hw;
+  u.QT = gr.cyc * u.PW;
+  u.q0 = r * CS_BM;
+  u.margin = u.hh * u.PW + u.hw;
+  u.mode_a = (CS_BM + 2 * u.margin <= p.seg_cap) ? 1 : 0;
+  u.rows = u.mode_a ? CS_BM + 2 * u.margin : CS_BM + 2 * u.hw;
+  u.img_row0 = (size_t)(gr.row_tiles_before + b * gr.rt) * 128;
+  return true;
+}
+// tap row dr of this unit only ever sees zero padding
+__device__ __forceinline__ bool cs_row_dead(const CsUnit& u, int dr) {
+  const int q_lo = u.q0 + (dr - u.hh) * u.PW - u.hw;
+  return q_lo + CS_BM + 2 * u.hw <= 0 || q_lo >= u.QT;
+}
+
+__device__ __forceinline__ void cs_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+enum { CS_SEG_FULL = 0, CS_SEG_EMPTY = CS_NSEG, CS_ACC_FULL = 2 * CS_NSEG, CS_ACC_EMPTY = 2 * CS_NSEG + 2,
+       CS_W_FULL = 2 * CS_NSEG + 4, CS_W_EMPTY = CS_W_FULL + CS_WSLOTS_MAX, CS_BARS = CS_W_EMPTY + CS_WSLOTS_MAX };
+
+template <int NS>
+__global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mid = p.mid, nchunk = mid / 8, nck = NS * nchunk, ksteps = mid / 16;
+  const uint32_t LBO_A = (uint32_t)(p.seg_cap + 2) * 16;      // chunk stride; +2 rows de-phases the banks of the chunks
+  const uint32_t SEG_BYTES = ((uint32_t)nck * LBO_A + 127) & ~127u;
+  const uint32_t LBO_W = (uint32_t)mid * 16;
+  const uint32_t PLANE_W = (uint32_t)mid * mid * 2;           // one weight plane of one tap
+  const uint32_t TAP_BYTES = NS * PLANE_W;
+
+  uint8_t* s_w = smem;
+  uint8_t* s_seg = smem + (size_t)p.w_slots * p.w_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_seg + (size_t)CS_NSEG * SEG_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + CS_BARS);
+  CsGroup* s_grp = reinterpret_cast<CsGroup*>(tmem_slot + 4);
+  int* s_G = reinterpret_cast<int*>(s_grp + FTN_MAX_K);
+
+  pdl_trigger();
+  if (tid == 0) {
+    for (int i = 0; i < CS_NSEG; ++i) {
+      mbar_init(&bars[CS_SEG_FULL + i], CS_LOADERS / 32);
+      mbar_init(&bars[CS_SEG_EMPTY + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[CS_ACC_FULL + i], 1);
+      mbar_init(&bars[CS_ACC_EMPTY + i], 8);
+    }
+    for (int i = 0; i < CS_WSLOTS_MAX; ++i) {
+      mbar_init(&bars[CS_W_FULL + i], 1);
+      mbar_init(&bars[CS_W_EMPTY + i], 1);
+    }
+    fence_barrier_init();
+  }
+  const uint32_t tmem_cols = 2 * mid <= 32 ? 32u : (2 * mid <= 64 ? 64u : (2 * mid <= 128 ? 128u : 256u));
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  pdl_wait();   // the plan and the input are a predecessor's output
+  if (tid == 0) {
+    const FtnPeriodPlan* pl = p.plan;
+    const int G = pl->n_groups;
+    int rtb = 0, unit0 = 0;
+    for (int g = 0; g < G && g < FTN_MAX_K; ++g) {
+      CsGroup gr;
+      gr.per = pl->grp_period[g];
+      gr.cyc = pl->grp_cycles[g];
+      gr.rt = (p.L + pl->grp_pad[g] + 127) / 128;
+      gr.row_tiles_before = rtb;
+      gr.S = 0;
+      for (int j = 0; j < p.n_branch; ++j) {
+        const int QT = gr.cyc * (gr.per + 2 * (p.kw[j] / 2));
+        gr.tiles[j] = (QT + CS_BM - 1) / CS_BM;
+        gr.S += gr.tiles[j];
+      }
+      gr.unit0 = unit0;
+      unit0 += p.B * gr.S;
+      rtb += gr.rt * p.B;
+      s_grp[g] = gr;
+    }
+    *s_G = G < FTN_MAX_K ? G : FTN_MAX_K;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int G = *s_G;
+  const int stride = gridDim.x;
+
+  if (warp == 0) {
+    // ===================== MMA issuer: ONE lane runs the whole loop =====================
+    // The stream is thousands of small MMAs (N = mid <= 64, ~80 cycles each on the tensor pipe), so the issuing
+    // thread must spend only a handful of instructions per MMA: 32-bit descriptor low words advanced by adds, the
+    // high words and every plane offset hoisted out of the loops (measured on the first version, which rebuilt 64-bit
+    // descriptors under elect.sync for each MMA: 230 cycles per MMA at mid = 16, tensor pipe 4 % active).
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(CS_BM, mid);
+      const uint32_t a_hi = (uint32_t)(make_desc_interleaved(0, LBO_A) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_desc_interleaved(0, LBO_W) >> 32);
+      const uint32_t a_lbo = (uint32_t)make_desc_interleaved(0, LBO_A);      // LBO field of the low word
+      const uint32_t b_lbo = (uint32_t)make_desc_interleaved(0, LBO_W);
+      const uint32_t ks_a = 2 * (LBO_A >> 4), ks_w = 2 * (LBO_W >> 4);
+      const uint32_t a_pl = (uint32_t)nchunk * (LBO_A >> 4);                 // activation plane stride (16-byte units)
+      const uint32_t w_pl = PLANE_W >> 4, w_tap = TAP_BYTES >> 4;
+      uint32_t seg_base[CS_NSEG];
+#pragma unroll
+      for (int i = 0; i < CS_NSEG; ++i) seg_base[i] = ((smem_u32(s_seg + (size_t)i * SEG_BYTES) & 0x3FFFFu) >> 4) | a_lbo;
+      const uint32_t w_base0 = ((smem_u32(s_w) & 0x3FFFFu) >> 4) | b_lbo;
+      const uint32_t w_slot16 = (uint32_t)p.w_slot_bytes >> 4;
+      const uint32_t n_wslots = (uint32_t)p.w_slots;
+      CsUnit u;
+      uint32_t seg_it = 0, w_slot = 0, w_par = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bars[CS_ACC_EMPTY + buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * mid;
+        uint32_t accum = 0;
+        const int ut = p.ut[u.j];
+        uint32_t seg_lo = 0;
+        if (u.mode_a) {
+          const uint32_t ss = seg_it % CS_NSEG;
+          mbar_wait(&bars[CS_SEG_FULL + ss], (seg_it / CS_NSEG) & 1u);
+          tc_fence_after();
+          seg_lo = seg_base[ss] + (uint32_t)(u.margin - u.hw - u.hh * u.PW);
+        }
+        for (int dr = 0; dr < u.kh; ++dr) {
+          if (cs_row_dead(u, dr)) continue;
+          uint32_t row_lo;
+          if (u.mode_a) {
+            row_lo = seg_lo + (uint32_t)(dr * u.PW);
+          } else {
+            const uint32_t ss = seg_it % CS_NSEG;
+            mbar_wait(&bars[CS_SEG_FULL + ss], (seg_it / CS_NSEG) & 1u);
+            tc_fence_after();
+            row_lo = seg_base[ss];
+          }
+          for (int dw0 = 0; dw0 < u.kw; dw0 += ut) {
+            mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
+            tc_fence_after();
+            uint32_t tap_lo = w_base0 + w_slot * w_slot16;
+            const int dw1 = min(u.kw, dw0 + ut);
+            uint32_t a_tap = row_lo + (uint32_t)dw0;
+            for (int dw = dw0; dw < dw1; ++dw, ++a_tap, tap_lo += w_tap) {
+              if (NS == 3) {
+                // (activation plane, weight plane) with i + j <= 2, smallest products first; hi = 0, mid = 1, lo = 2
+                const uint32_t a0 = a_tap, a1 = a_tap + a_pl, a2 = a_tap + 2 * a_pl;
+                const uint32_t w0 = tap_lo, w1 = tap_lo + w_pl, w2 = tap_lo + 2 * w_pl;
+                uint32_t ko_a = 0, ko_w = 0;
+                for (int ks = 0; ks < ksteps; ++ks, ko_a += ks_a, ko_w += ks_w) {
+                  mma_bf16_lohi(acc, a2 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, accum);
+                  mma_bf16_lohi(acc, a1 + ko_a, a_hi, w1 + ko_w, b_hi, idesc, 1u);
+                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w2 + ko_w, b_hi, idesc, 1u);
+                  mma_bf16_lohi(acc, a1 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, 1u);
+                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w1 + ko_w, b_hi, idesc, 1u);
+                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, 1u);
+                  accum = 1;
+                }
+              } else {
+                uint32_t a_k = a_tap, b_k = tap_lo;
+                for (int ks = 0; ks < ksteps; ++ks, a_k += ks_a, b_k += ks_w) {
+                  mma_bf16_lohi(acc, a_k, a_hi, b_k, b_hi, idesc, accum);
+                  accum = 1;
+                }
+              }
+            }
+            mma_commit(&bars[CS_W_EMPTY + w_slot]);
+            if (++w_slot == n_wslots) { w_slot = 0; w_par ^= 1u; }
+          }
+          if (!u.mode_a) {
+            mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
+            ++seg_it;
+          }
+        }
+        if (u.mode_a) {
+          mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
+          ++seg_it;
+        }
+        mma_commit(&bars[CS_ACC_FULL + buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== weight producer: one bulk copy per ring slot =====================
+    if (lane == 0) {
+      CsUnit u;
+      uint32_t w_it = 0;
+      for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride) {
+        const int ut = p.ut[u.j];
+        for (int dr = 0; dr < u.kh; ++dr) {
+          if (cs_row_dead(u, dr)) continue;
+          for (int dw0 = 0; dw0 < u.kw; dw0 += ut) {
+            const uint32_t ws = w_it % (uint32_t)p.w_slots;
+            mbar_wait(&bars[CS_W_EMPTY + ws], ((w_it / (uint32_t)p.w_slots) & 1u) ^ 1u);
+            const uint32_t bytes = (uint32_t)(min(u.kw, dw0 + ut) - dw0) * TAP_BYTES;
+            mbar_arrive_expect_tx(&bars[CS_W_FULL + ws], bytes);
+            cs_bulk_load(s_w + (size_t)ws * p.w_slot_bytes, p.w[u.j] + (size_t)(dr * u.kw + dw0) * TAP_BYTES, bytes,
+                         &bars[CS_W_FULL + ws]);
+            ++w_it;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 5) {
+    // ===================== segment loaders =====================
+    const int lt = tid - 64;                 // 0..127
+    const int d_row = CS_LOADERS / nck, d_cc = CS_LOADERS - d_row * nck;
+    CsUnit u;
+    uint32_t seg_it = 0;
+    for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride) {
+      const float inv = 1.0f / (float)u.PW;
+      const __nv_bfloat16* img = p.in + u.img_row0 * p.ld + u.j * mid;
+      const int nseg = u.mode_a ? 1 : u.kh;
+      for (int sg = 0; sg < nseg; ++sg) {
+        if (!u.mode_a && cs_row_dead(u, sg)) continue;
+        const uint32_t ss = seg_it % CS_NSEG;
+        mbar_wait_relaxed(&bars[CS_SEG_EMPTY + ss], ((seg_it / CS_NSEG) & 1u) ^ 1u);
+        const uint32_t dst0 = smem_u32(s_seg + (size_t)ss * SEG_BYTES);
+        // padded position of buffer row 0
+        const int qs = u.mode_a ? u.q0 - u.margin : u.q0 + (sg - u.hh) * u.PW - u.hw;
+        int row = lt / nck, cc = lt - row * nck;
+        for (; row < u.rows; ) {
+          const int q = qs + row;
+          bool ok = q >= 0 && q < u.QT;
+          int tt = 0;
+          if (ok) {
+            int rr = __float2int_rd(__int2float_rn(q) * inv);
+            if (rr * u.PW > q) --rr;
+            if ((rr + 1) * u.PW <= q) ++rr;
+            const int wq = q - rr * u.PW;
+            ok = wq >= u.hw && wq < u.hw + u.per;
+            tt = rr * u.per + wq - u.hw;
+          }
+          const int plane = cc / nchunk, c8 = cc - plane * nchunk;
+          const __nv_bfloat16* src = ok ? img + (size_t)tt * p.ld + plane * p.NB + c8 * 8 : img;
+          cp_async16(dst0 + (uint32_t)cc * LBO_A + (uint32_t)row * 16, src, ok ? 16u : 0u);
+          row += d_row;
+          cc += d_cc;
+          if (cc >= nck) { cc -= nck; ++row; }
+        }
+        cp_async_wait_all();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[CS_SEG_FULL + ss]);
+        ++seg_it;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int half = (warp - 6) >> 2;        // every other 16-column group
+    CsUnit u;
+    int it = 0;
+    for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride, ++it) {
+      const int buf = it & 1;
+      mbar_wait_relaxed(&bars[CS_ACC_FULL + buf], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const int q = u.q0 + quad * 32 + lane;
+      bool ok = q < u.QT;
+      int tt = 0;
+      if (ok) {
+        const float inv = 1.0f / (float)u.PW;
+        int rr = __float2int_rd(__int2float_rn(q) * inv);
+        if (rr * u.PW > q) --rr;
+        if ((rr + 1) * u.PW <= q) ++rr;
+        const int w = q - rr * u.PW - u.hw;
+        ok = w >= 0 && w < u.per;
+        tt = rr * u.per + w;
+      }
+      const float* bias = p.bias[u.j];
+      for (int c = half * 16; c < mid; c += 32) {
+        float v[16];
+        tmem_ld16(tmem_base + buf * mid + c + ((uint32_t)(quad * 32) << 16), v);
+        if (ok) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] += __ldg(bias + c + k);
+          __nv_bfloat16* dst = p.out + (u.img_row0 + (size_t)tt) * p.ld + u.j * mid + c;
+          if (NS == 3) {
+            uint32_t h[8], m[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = v[2 * i], b = v[2 * i + 1];
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+              const float ra = a - __bfloat162float(hh.x), rb = b - __bfloat162float(hh.y);
+              const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - __bfloat162float(mm.x), rb - __bfloat162float(mm.y));
+              h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              m[i] = *reinterpret_cast<const uint32_t*>(&mm);
+              l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            uint4* d0 = reinterpret_cast<uint4*>(dst);
+            uint4* d1 = reinterpret_cast<uint4*>(dst + p.NB);
+            uint4* d2 = reinterpret_cast<uint4*>(dst + 2 * p.NB);
+            d0[0] = make_uint4(h[0], h[1], h[2], h[3]); d0[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            d1[0] = make_uint4(m[0], m[1], m[2], m[3]); d1[1] = make_uint4(m[4], m[5], m[6], m[7]);
+            d2[0] = make_uint4(l[0], l[1], l[2], l[3]); d2[1] = make_uint4(l[4], l[5], l[6], l[7]);
+          } else {
+            uint4* d0 = reinterpret_cast<uint4*>(dst);
+            d0[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            d0[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[CS_ACC_EMPTY + buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------
+struct CsLayout { int w_slots, w_slot_bytes, seg_cap; size_t smem; int ut[FTN_MAX_BRANCH]; bool ok; };
+
+static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
+  CsLayout l{};
+  const int mid = w->mid, nck = ns * mid / 8;
+  const long long tap = (long long)ns * mid * mid * 2;
+  long long slot = 0;
+  int hw_max = 0;
+  for (int j = 0; j < w->n_branch; ++j) {
+    l.ut[j] = (long long)w->kw[j] * tap <= 56 * 1024 ? w->kw[j] : 1;
+    slot = slot > l.ut[j] * tap ? slot : l.ut[j] * tap;
+    hw_max = hw_max > w->kw[j] / 2 ? hw_max : w->kw[j] / 2;
+  }
+  slot = (slot + 127) & ~127ll;
+  long long slots = (96 * 1024) / slot;
+  slots = slots < 2 ? 2 : (slots > CS_WSLOTS_MAX ? CS_WSLOTS_MAX : slots);
+  const long long fixed = 128 + slots * slot + (CS_BARS + 4) * 8 + FTN_MAX_K * (long long)sizeof(CsGroup) + 64;
+  long long cap = (227ll * 1024 - fixed) / CS_NSEG / (nck * 16) - 2 - 8;    // -8 rows: 128-byte rounding slack
+  if (cap > 16000) cap = 16000;                                              // LBO field: 14 bits of 16-byte units
+  // beyond ~2 tiles of halo the band of mode A stops paying for itself; a smaller buffer also leaves L1 some room
+  if (cap > 1024) cap = 1024;
+  l.w_slots = (int)slots;
+  l.w_slot_bytes = (int)slot;
+  l.seg_cap = (int)cap;
+  l.ok = cap >= CS_BM + 2 * hw_max;
+  const size_t seg = (((size_t)nck * (size_t)(cap + 2) * 16) + 127) & ~size_t(127);
+  l.smem = (size_t)fixed + CS_NSEG * seg;
+  return l;
+}
+
+bool tc_convs_eligible(const FtnInceptionWeights* w, int ns) {
+  if (w->mid < 16 || w->mid > 128 || w->mid % 16) return false;
+  if (ns != 1 && ns != 3) return false;
+  for (int j = 0; j < w->n_branch; ++j) {
+    if (!(w->kh[j] & 1) || !(w->kw[j] & 1)) return false;
+    if (!(ns == 3 ? w->w_kk_img3[j] : w->w_kk_img[j])) return false;
+  }
+  return convs_layout(w, ns).ok;
+}
+
+int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in, __nv_bfloat16* out,
+                    int ld, const FtnInceptionWeights* w, int ns, cudaStream_t st, bool dependent) {
+  FTN_REQUIRE(tc_convs_eligible(w, ns), "tc_convs: unsupported branch shape (mid=%d, planes=%d)", w->mid, ns);
+  const CsLayout l = convs_layout(w, ns);
+  TcConvsArgs a{};
+  a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.NB = w->n_branch * w->mid;
+  a.mid = w->mid; a.n_branch = w->n_branch; a.ns = ns;
+  a.seg_cap = l.seg_cap; a.w_slots = l.w_slots; a.w_slot_bytes = l.w_slot_bytes;
+  long long units_max = 0;
+  for (int j = 0; j < w->n_branch; ++j) {
+    a.kh[j] = w->kh[j]; a.kw[j] = w->kw[j]; a.ut[j] = l.ut[j];
+    a.w[j] = (const uint8_t*)(ns == 3 ? w->w_kk_img3[j] : w->w_kk_img[j]);
+    a.bias[j] = w->b_kk[j];
+    // worst case: period L - 1 (two cycles), padded width L - 1 + 2 hw
+    units_max += (long long)max_groups * B * ((2ll * (L + 2 * (w->kw[j] / 2)) + CS_BM - 1) / CS_BM);
+  }
+  const int sms = sm_count();
+  const int ctas = (int)(units_max < sms ? (units_max < 1 ? 1 : units_max) : sms);
+  if (ns == 3) {
+    FTN_DYN_SMEM(tc_convs_kernel<3>, l.smem);
+    FTN_CUDA(launch_pdl(dependent, tc_convs_kernel<3>, dim3(ctas), dim3(CS_THREADS), l.smem, st, a));
+  } else {
+    FTN_DYN_SMEM(tc_convs_kernel<1>, l.smem);
+    FTN_CUDA(launch_pdl(dependent, tc_convs_kernel<1>, dim3(ctas), dim3(CS_THREADS), l.smem, st, a));
+  }
+  FTN_LAUNCH_CHECK("tc_convs_kernel");
+  return 0;
+}
+
+}  // namespace ftn

@@ -23,8 +23,20 @@ namespace ftn {
 using namespace tc;
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
-constexpr int TC_STAGE_BYTES = (TC_BM * TC_BK + TC_BN * TC_BK) * 2;  // 32 KB
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;                     // one 128 x 64 bf16 operand tile, 16 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;                    // 32 KB: activation tile + weight tile
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * TC_BN * 4 /*bias*/;
+// SPLIT (fp32 activations on the tensor cores): every fp32 value v travels as three bf16 planes
+//   hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid)        (v = hi + mid + lo to ~2^-25)
+// stored side by side along the channel axis ([rows][3 K]: plane p at columns [p K, (p + 1) K)); the weights are split
+// the same way on the host.  A product a . w is the six bf16 MMAs with plane indices i + j <= 2, accumulated in fp32
+// in TMEM; the dropped terms are below 2^-24 of the result, so the stage keeps fp32 accuracy (SURVEY 9.12 measured
+// 1.7e-6 for the 3 x TF32 equivalent; plain TF32 / bf16 fail the 1e-4 bound).  One stage of the ring then holds the
+// three activation planes and the three weight planes of a K block (96 KB, two stages), so every plane tile is loaded
+// once per K block and used by up to three MMAs.
+constexpr int TC_SPLIT_STAGES = 2;
+constexpr int TC_SPLIT_STAGE_BYTES = 6 * TC_TILE_BYTES;              // 96 KB
+constexpr int TC_SPLIT_SMEM_BYTES = TC_SPLIT_STAGES * TC_SPLIT_STAGE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
 
 struct TcGemmKernelArgs {
   const FtnPeriodPlan* plan;
@@ -32,26 +44,55 @@ struct TcGemmKernelArgs {
   int a1_seq, a2_seq, K1, K2, N, act, epi, res;
   const float* bias1;
   const float* bias2;
-  const __nv_bfloat16* res_ptr;
+  const void* res_ptr;     // bf16 (SPLIT: fp32 x for TC_RES_SEQ, three-plane bf16 for TC_RES_POS)
   int res_ld;
-  __nv_bfloat16* out;
+  void* out;               // bf16 tile-major (SPLIT: three-plane bf16 tile-major; DELTA: fp32 delta)
   int ldo;
-  const __nv_bfloat16* x;
+  const void* x;           // DELTA: grid to subtract (SPLIT: fp32)
   int C;
 };
 
+// exact-erf GELU for the fp32 (SPLIT) epilogues: gelu_fast's A&S 7.1.26 erf is within 1.5e-7 absolute
+__device__ __forceinline__ float act_split(float v, int act) { return act == FTN_ACT_RELU ? fmaxf(v, 0.f) : gelu_fast(v); }
+
+// three bf16 planes of 16 fp32 values -> 3 x 32 bytes at dst, dst + plane_stride, dst + 2 plane_stride (elements)
+__device__ __forceinline__ void store_split16(__nv_bfloat16* dst, int plane_stride, const float* v) {
+  uint32_t h[8], m[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const float ra = a - __bfloat162float(hh.x), rb = b - __bfloat162float(hh.y);
+    const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - __bfloat162float(mm.x), rb - __bfloat162float(mm.y));
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    m[i] = *reinterpret_cast<const uint32_t*>(&mm);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  uint4* d0 = reinterpret_cast<uint4*>(dst);
+  uint4* d1 = reinterpret_cast<uint4*>(dst + plane_stride);
+  uint4* d2 = reinterpret_cast<uint4*>(dst + 2 * plane_stride);
+  d0[0] = make_uint4(h[0], h[1], h[2], h[3]); d0[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  d1[0] = make_uint4(m[0], m[1], m[2], m[3]); d1[1] = make_uint4(m[4], m[5], m[6], m[7]);
+  d2[0] = make_uint4(l[0], l[1], l[2], l[3]); d2[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// STAGES: depth of the operand ring.  SPLIT stages are 96 KB; a stage count of 1 (used when the whole K loop is at most
+// two K blocks, e.g. the etth1-class 1x1 stages) lets two CTAs share an SM so one's epilogue overlaps the other's loads.
+template <bool SPLIT, int STAGES>
 __global__ void __launch_bounds__(256)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                const TcGemmKernelArgs p) {
+  constexpr int STAGE_BYTES = SPLIT ? TC_SPLIT_STAGE_BYTES : TC_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + TC_STAGES;
-  uint64_t* done = bars + 2 * TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-  float* s_bias1 = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + 256);
+  uint64_t* empty = bars + STAGES;
+  uint64_t* done = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* s_bias1 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
   float* s_bias2 = s_bias1 + TC_BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,7 +129,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     s_bias2[threadIdx.x] = p.K2 > 0 ? p.bias2[n0 + threadIdx.x] : 0.f;
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
     fence_barrier_init();
     prefetch_tmap(&tmA1);
@@ -105,18 +146,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (lane == 0) {
       // ===== TMA producer =====
       for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
-        const int s = kb % TC_STAGES;
-        mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
-        uint8_t* sa = smem + s * TC_STAGE_BYTES;
-        uint8_t* sw = sa + TC_BM * TC_BK * 2;
-        mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         const bool ph2 = kb >= nkb1;
         const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
+        const int K = ph2 ? p.K2 : p.K1;
         const CUtensorMap* ma = ph2 ? &tmA2 : &tmA1;
         const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
-        if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(sa, ma, &full[s], k0, t0, b);
-        else tma_load_2d(sa, ma, &full[s], k0, tile_id * TC_BM);
-        tma_load_2d(sw, mw, &full[s], k0, n0);
+        // SPLIT: planes 0..2 of the activation, then planes 0..2 of the weights (plane p = columns [p K, (p + 1) K);
+        // a box that runs past its plane / the tensor reads the next plane / zeros, which no MMA consumes)
+        constexpr int NP = SPLIT ? 3 : 1;
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+          uint8_t* dst = sa + pl * TC_TILE_BYTES;
+          if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(dst, ma, &full[s], pl * K + k0, t0, b);
+          else tma_load_2d(dst, ma, &full[s], pl * K + k0, tile_id * TC_BM);
+          tma_load_2d(sa + (NP + pl) * TC_TILE_BYTES, mw, &full[s], pl * K + k0, n0);
+        }
       }
     }
     __syncwarp();
@@ -125,19 +173,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
       const uint32_t idesc = make_idesc_bf16(TC_BM, n_tile);
       for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
-        const int s = kb % TC_STAGES;
-        mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (kb / STAGES) & 1);
         tc_fence_after();
         const bool ph2 = kb >= nkb1;
         const int kbl = ph2 ? kb - nkb1 : kb;
         const int K = ph2 ? p.K2 : p.K1;
         const int ksteps = min(TC_BK, K - kbl * TC_BK) / 16;
-        const uint32_t sa = desc_sw128_lo(smem_u32(smem + s * TC_STAGE_BYTES));
-        const uint32_t sw = sa + ((TC_BM * TC_BK * 2) >> 4);
+        const uint32_t sa = desc_sw128_lo(smem_u32(smem + s * STAGE_BYTES));
         const uint32_t d = tmem_base + (ph2 ? 128u : 0u);
-        for (int k = 0; k < ksteps; ++k)
-          if (elect_one())
-            mma_bf16_lohi(d, sa + k * 2, kDescSw128Hi, sw + k * 2, kDescSw128Hi, idesc, (kbl | k) != 0 ? 1u : 0u);
+        constexpr uint32_t TILE16 = TC_TILE_BYTES >> 4;
+        if (SPLIT) {
+          // (activation plane, weight plane), smallest products first; planes hi = 0, mid = 1, lo = 2
+          constexpr int PA[6] = {2, 1, 0, 1, 0, 0};
+          constexpr int PW[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
+          for (int pr = 0; pr < 6; ++pr) {
+            const uint32_t da = sa + PA[pr] * TILE16, dw = sa + (3 + PW[pr]) * TILE16;
+            for (int k = 0; k < ksteps; ++k)
+              if (elect_one())
+                mma_bf16_lohi(d, da + k * 2, kDescSw128Hi, dw + k * 2, kDescSw128Hi, idesc, (kbl | k | pr) != 0 ? 1u : 0u);
+          }
+        } else {
+          const uint32_t sw = sa + TILE16;
+          for (int k = 0; k < ksteps; ++k)
+            if (elect_one())
+              mma_bf16_lohi(d, sa + k * 2, kDescSw128Hi, sw + k * 2, kDescSw128Hi, idesc, (kbl | k) != 0 ? 1u : 0u);
+        }
         if (elect_one()) mma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         __syncwarp();
       }
@@ -156,6 +218,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const size_t pos_row = (size_t)tile_id * TC_BM + r;
   const bool row_live = t < Lp;  // rows past the image are never consumed; still written for PLAIN/BLOCK_A
   const bool delta_row = p.epi == TC_EPI_DELTA && t < p.L && row_live;
+  if (SPLIT) {
+    const float* resf = reinterpret_cast<const float*>(p.res_ptr);
+    const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr);
+    const float* xf = reinterpret_cast<const float*>(p.x);
+    for (int c = half * 16; c < n_tile; c += 32) {
+      uint32_t vr[16], wr[16];
+      tmem_ld16_nowait(trow + c, vr);
+      if (p.res == TC_RES_ACC2) tmem_ld16_nowait(trow + 128 + c, wr);
+      const int n = n0 + c;
+      float rs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rs[i] = 0.f;
+      if (p.res == TC_RES_SEQ) {
+        if (t < p.L) {
+          const float4* src = reinterpret_cast<const float4*>(resf + ((size_t)b * p.L + t) * p.res_ld + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float4 q = src[i]; rs[4 * i] = q.x; rs[4 * i + 1] = q.y; rs[4 * i + 2] = q.z; rs[4 * i + 3] = q.w; }
+        }
+      } else if (p.res == TC_RES_POS) {       // three planes of width res_ld / 3
+        const int pw = p.res_ld / 3;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const uint4* src = reinterpret_cast<const uint4*>(resb + pos_row * p.res_ld + pl * pw + n);
+          const uint4 q0 = src[0], q1 = src[1];
+          const __nv_bfloat16* qb0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
+          const __nv_bfloat16* qb1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { rs[i] += __bfloat162float(qb0[i]); rs[8 + i] += __bfloat162float(qb1[i]); }
+        }
+      }
+      float xs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) xs[i] = 0.f;
+      if (delta_row) {
+        const float4* src = reinterpret_cast<const float4*>(xf + ((size_t)b * p.L + t) * p.C + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 q = src[i]; xs[4 * i] = q.x; xs[4 * i + 1] = q.y; xs[4 * i + 2] = q.z; xs[4 * i + 3] = q.w; }
+      }
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(vr[i]) + s_bias1[c + i];
+        if (p.epi != TC_EPI_PLAIN) {
+          a = act_split(a, p.act);
+          a += p.res == TC_RES_ACC2 ? __uint_as_float(wr[i]) + s_bias2[c + i] : rs[i];
+          if (p.epi == TC_EPI_BLOCK_A) a = act_split(a, p.act);
+          else a -= xs[i];
+        }
+        v[i] = a;
+      }
+      if (p.epi == TC_EPI_DELTA) {
+        if (delta_row) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (((size_t)g * p.B + b) * p.L + t) * p.C + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      } else {
+        store_split16(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.ldo + n, p.ldo / 3, v);
+      }
+    }
+  } else
   for (int c = half * 16; c < n_tile; c += 32) {
     uint32_t vr[16], wr[16];
     tmem_ld16_nowait(trow + c, vr);
@@ -164,17 +288,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (p.res == TC_RES_SEQ) {
       if (t < p.L) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.res_ptr + ((size_t)b * p.L + t) * p.res_ld + n);
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + ((size_t)b * p.L + t) * p.res_ld + n);
         rv[0] = src[0]; rv[1] = src[1];
       }
     } else if (p.res == TC_RES_POS) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.res_ptr + pos_row * p.res_ld + n);
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res_ptr) + pos_row * p.res_ld + n);
       rv[0] = src[0]; rv[1] = src[1];
     }
     const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(rv);
     uint4 xv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (delta_row) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.x + ((size_t)b * p.L + t) * p.C + n);
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)b * p.L + t) * p.C + n);
       xv[0] = src[0]; xv[1] = src[1];
     }
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
@@ -198,11 +322,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
     if (p.epi == TC_EPI_DELTA) {
       if (delta_row) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)g * p.B + b) * p.L + t) * p.C + n);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)g * p.B + b) * p.L + t) * p.C + n);
         dst[0] = o0; dst[1] = o1;
       }
     } else {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + pos_row * p.ldo + n);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.ldo + n);
       dst[0] = o0; dst[1] = o1;
     }
   }
@@ -264,20 +388,65 @@ int tc_worst_case_tiles(int B, int L, int max_groups) {
   return max_groups * B * ((2 * L + TC_BM - 1) / TC_BM);
 }
 
+// x fp32 [rows][C] -> xs bf16 [rows][3 C] (hi | mid | lo), 8 values per thread
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, long long rows, int C,
+                                                    __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8 = C >> 3;
+  const long long total = rows * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float4* src = reinterpret_cast<const float4*>(x + r * C + c);
+    const float4 q0 = src[0], q1 = src[1];
+    const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = v[2 * k], b = v[2 * k + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+      const float ra = a - __bfloat162float(hh.x), rb = b - __bfloat162float(hh.y);
+      const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - __bfloat162float(mm.x), rb - __bfloat162float(mm.y));
+      h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      m[k] = *reinterpret_cast<const uint32_t*>(&mm);
+      l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    __nv_bfloat16* dst = out + r * 3 * C + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst + C) = make_uint4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<uint4*>(dst + 2 * C) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call) {
+  FTN_REQUIRE(C % 8 == 0, "split3: C=%d must be a multiple of 8", C);
+  const long long total = rows * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  FTN_CUDA(launch_pdl(!first_in_call, split3_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, rows, C, out));
+  FTN_LAUNCH_CHECK("split3_kernel");
+  return 0;
+}
+
 int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   FTN_REQUIRE(a.K1 > 0 && a.K1 % 16 == 0 && a.K2 % 16 == 0 && a.N % 16 == 0,
               "tc_gemm: K1=%d K2=%d N=%d must be multiples of 16", a.K1, a.K2, a.N);
   FTN_REQUIRE(a.a1_ld % 8 == 0 && (a.K2 == 0 || a.a2_ld % 8 == 0) && a.ldo % 8 == 0,
               "tc_gemm: row pitches must be multiples of 8 elements (16 B)");
   FTN_REQUIRE((a.res == TC_RES_ACC2) == (a.K2 > 0), "tc_gemm: second accumulator and K2 must come together");
+  const int np = a.split ? 3 : 1;                      // planes per operand row
   CUtensorMap mA1, mW1, mA2, mW2;
-  if (a.a1_seq) { if (int rc = make_map_seq(&mA1, a.a1, a.B, a.L, a.K1, a.a1_ld)) return rc; }
-  else if (int rc = make_map_2d(&mA1, a.a1, a.a1_rows, a.K1, a.a1_ld)) return rc;
-  if (int rc = make_map_2d(&mW1, a.w1, a.N, a.K1, a.K1)) return rc;
+  if (a.a1_seq) { if (int rc = make_map_seq(&mA1, a.a1, a.B, a.L, np * a.K1, a.a1_ld)) return rc; }
+  else if (int rc = make_map_2d(&mA1, a.a1, a.a1_rows, np * a.K1, a.a1_ld)) return rc;
+  if (int rc = make_map_2d(&mW1, a.w1, a.N, np * a.K1, np * a.K1)) return rc;
   if (a.K2 > 0) {
-    if (a.a2_seq) { if (int rc = make_map_seq(&mA2, a.a2, a.B, a.L, a.K2, a.a2_ld)) return rc; }
-    else if (int rc = make_map_2d(&mA2, a.a2, a.a2_rows, a.K2, a.a2_ld)) return rc;
-    if (int rc = make_map_2d(&mW2, a.w2, a.N, a.K2, a.K2)) return rc;
+    if (a.a2_seq) { if (int rc = make_map_seq(&mA2, a.a2, a.B, a.L, np * a.K2, a.a2_ld)) return rc; }
+    else if (int rc = make_map_2d(&mA2, a.a2, a.a2_rows, np * a.K2, a.a2_ld)) return rc;
+    if (int rc = make_map_2d(&mW2, a.w2, a.N, np * a.K2, np * a.K2)) return rc;
   } else {
     mA2 = mA1;
     mW2 = mW1;
@@ -287,10 +456,23 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.a1_seq = a.a1_seq; k.a2_seq = a.a2_seq; k.K1 = a.K1; k.K2 = a.K2; k.N = a.N; k.act = a.act; k.epi = a.epi;
   k.res = a.res; k.bias1 = a.bias1; k.bias2 = a.bias2; k.res_ptr = a.res_ptr; k.res_ld = a.res_ld;
   k.out = a.out; k.ldo = a.ldo; k.x = a.x; k.C = a.C;
-  FTN_DYN_SMEM(tc_gemm_kernel, TC_SMEM_BYTES);
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
-  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
+  if (a.split) {
+    FTN_REQUIRE(a.ldo % 3 == 0 || a.epi == TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold three planes", a.ldo);
+    const int nkb = (a.K1 + TC_BK - 1) / TC_BK + (a.K2 + TC_BK - 1) / TC_BK;
+    if (nkb <= 2) {
+      constexpr int smem1 = TC_SPLIT_STAGE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
+      FTN_DYN_SMEM((tc_gemm_kernel<true, 1>), smem1);
+      tc_gemm_kernel<true, 1><<<grid, 256, smem1, st>>>(mA1, mW1, mA2, mW2, k);
+    } else {
+      FTN_DYN_SMEM((tc_gemm_kernel<true, TC_SPLIT_STAGES>), TC_SPLIT_SMEM_BYTES);
+      tc_gemm_kernel<true, TC_SPLIT_STAGES><<<grid, 256, TC_SPLIT_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
+    }
+  } else {
+    FTN_DYN_SMEM((tc_gemm_kernel<false, TC_STAGES>), TC_SMEM_BYTES);
+    tc_gemm_kernel<false, TC_STAGES><<<grid, 256, TC_SMEM_BYTES, st>>>(mA1, mW1, mA2, mW2, k);
+  }
   FTN_LAUNCH_CHECK("tc_gemm_kernel");
   return 0;
 }
@@ -311,4 +493,21 @@ extern "C" FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const f
   g.K2 = 0; g.N = N; g.act = 0; g.epi = TC_EPI_PLAIN; g.res = TC_RES_NONE;
   g.out = (__nv_bfloat16*)out; g.ldo = N;
   return tc_gemm_launch(g, as_stream(stream));
+}
+
+// Unit-test entry for the three-plane (fp32) mode: a[M][K] fp32 is split into a_ws[M][3K], then
+// out_s3[M][3N] (bf16 planes hi | mid | lo of the fp32 result) = a . w^T + bias with w_s3[N][3K] the split weights.
+extern "C" FTN_API int ftn_debug_tc_linear_split(const float* a, const void* w_s3, const float* bias, int M, int K, int N,
+                                                 void* a_ws, void* out_s3, void* stream) {
+  FTN_REQUIRE(a && w_s3 && bias && a_ws && out_s3, "ftn_debug_tc_linear_split: null pointer");
+  FTN_REQUIRE(M > 0 && M % 128 == 0, "ftn_debug_tc_linear_split: M=%d must be a multiple of 128", M);
+  cudaStream_t st = as_stream(stream);
+  if (int rc = split3_launch(a, M, K, (__nv_bfloat16*)a_ws, st, true)) return rc;
+  TcGemmArgs g{};
+  g.plan = nullptr; g.B = 1; g.L = M; g.max_groups = 1; g.n_tiles = M / 128; g.split = 1;
+  g.a1 = (const __nv_bfloat16*)a_ws; g.a1_seq = 0; g.a1_ld = 3 * K; g.a1_rows = M;
+  g.w1 = (const __nv_bfloat16*)w_s3; g.bias1 = bias; g.K1 = K;
+  g.K2 = 0; g.N = N; g.act = 0; g.epi = TC_EPI_PLAIN; g.res = TC_RES_NONE;
+  g.out = out_s3; g.ldo = 3 * N;
+  return tc_gemm_launch(g, st);
 }

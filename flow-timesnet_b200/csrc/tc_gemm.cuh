@@ -30,11 +30,16 @@ struct TcGemmArgs {
   const __nv_bfloat16* w2;  // [N][K2]
   const float* bias2; int K2;
   int N, act, epi, res;
-  const __nv_bfloat16* res_ptr; int res_ld;   // TC_RES_SEQ: x (ld = C); TC_RES_POS: tile-major tensor
-  __nv_bfloat16* out; int ldo;                // PLAIN / BLOCK_A: tile-major; DELTA: delta base
-  const __nv_bfloat16* x; int C;              // DELTA: grid to subtract
+  const void* res_ptr; int res_ld;            // TC_RES_SEQ: x (ld = C); TC_RES_POS: tile-major tensor
+  void* out; int ldo;                         // PLAIN / BLOCK_A: tile-major; DELTA: delta base
+  const void* x; int C;                       // DELTA: grid to subtract
   bool first_in_call;                         // first kernel of an API call: plain launch, no programmatic dependency
+  // split != 0: fp32 activations as three bf16 planes (tc_gemm.cu).  a1 / a2 / w1 / w2 / out then are [rows][3 K] /
+  // [rows][3 N] (a*_ld, ldo count ALL planes), x and a TC_RES_SEQ residual are the fp32 block input, a DELTA out is fp32.
+  int split;
 };
+// fp32 [rows][C] -> three bf16 planes [rows][3 C] (tc_gemm.cu)
+int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call);
 
 int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st);
 // persistent variant for the K <= 128, N <= 128 single-operand stages (tc_gemm2.cu); tc_stage_launch picks
@@ -93,6 +98,12 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
                 int period_lo = 0, int period_hi = 0);
 bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int period_lo, int period_hi);
 bool tc_kk_uses_conv4(const FtnInceptionWeights* w);
+
+// streaming variant (tc_convs.cu): any mid % 16 == 0, bf16 activations (ns = 1) or three-plane fp32 (ns = 3);
+// in / out are tile-major [rows][ld] with plane p of branch j at columns p * n_branch * mid + j * mid
+bool tc_convs_eligible(const FtnInceptionWeights* w, int ns);
+int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in, __nv_bfloat16* out,
+                    int ld, const FtnInceptionWeights* w, int ns, cudaStream_t st, bool dependent = true);
 
 // fused tail (tc_tail.cu): last 1x1 stage + weighted aggregation + residual + LayerNorm
 bool tc_tail_eligible(int K, int C);

@@ -237,7 +237,7 @@ static int g2_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 }
 
 bool tc_gemm2_eligible(const TcGemmArgs& a) {
-  if (a.K2 > 0) return false;
+  if (a.K2 > 0 || a.split) return false;
   if (!a.plan && (a.a1_seq || a.epi != TC_EPI_PLAIN)) return false;
   if (a.K1 % 16 || a.K1 > 128 || a.N % 16 || a.N > 128 || a.N < 16) return false;
   if (a.epi == TC_EPI_PLAIN) return a.res == TC_RES_NONE;
@@ -267,7 +267,8 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   }
   TcGemm2Args k{};
   k.plan = a.plan; k.n_plain = a.n_tiles; k.B = a.B; k.L = a.L; k.a_seq = a.a1_seq; k.K = a.K1; k.N = a.N; k.act = a.act; k.epi = a.epi;
-  k.bias = a.bias1; k.q = a.res_ptr; k.ld_q = a.res_ld; k.x = a.x; k.C = a.C; k.out = a.out; k.ldo = a.ldo;
+  k.bias = a.bias1; k.q = (const __nv_bfloat16*)a.res_ptr; k.ld_q = a.res_ld; k.x = (const __nv_bfloat16*)a.x; k.C = a.C;
+  k.out = (__nv_bfloat16*)a.out; k.ldo = a.ldo;
   const int nkb = (a.K1 + G2_BK - 1) / G2_BK;
   const size_t smem = 1024 + (size_t)nkb * ((a.N * 128 + 1023) & ~1023) + (size_t)G2_STAGES * nkb * G2_A_KB + 128 * 4 + 16 +
                       G2_BARS * 8 + 16;

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -57,6 +57,8 @@ class FtnInceptionWeights(C.Structure):
         ("w_kk_bf16", C.c_void_p * FTN_MAX_BRANCH),
         ("w_mid_first", C.c_void_p), ("w_mid_second", C.c_void_p),
         ("w_kk_phase", C.c_void_p * FTN_MAX_BRANCH),
+        ("w_kk_img", C.c_void_p * FTN_MAX_BRANCH), ("w_kk_img3", C.c_void_p * FTN_MAX_BRANCH),
+        ("w_in_s3", C.c_void_p), ("w_out_s3", C.c_void_p), ("w_res_s3", C.c_void_p),
     ]
 
 
@@ -79,6 +81,7 @@ SIGNATURES = {
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
     "ftn_debug_tc_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ftn_debug_tc_linear_split": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ftn_debug_conv_tiled": (_I, [_P, _P, _I, _P, _I, _I, _I, C.POINTER(FtnInceptionWeights), _I, _P]),
     "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
@@ -379,6 +382,18 @@ def debug_tc_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> tor
     _check(load().ftn_debug_tc_linear(a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, K, N, out.data_ptr(), _stream()),
            "ftn_debug_tc_linear")
     return out
+
+
+def debug_tc_linear_split(a: torch.Tensor, w_s3: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """fp32 a[M, K] x split weights w_s3[N, 3K] (bf16 planes) -> fp32 [M, N] reassembled from the three output planes."""
+    M, K = a.shape
+    N = w_s3.shape[0]
+    a_ws = torch.empty(M, 3 * K, dtype=torch.bfloat16, device=a.device)
+    out = torch.empty(M, 3 * N, dtype=torch.bfloat16, device=a.device)
+    _check(load().ftn_debug_tc_linear_split(a.data_ptr(), w_s3.data_ptr(), bias.data_ptr(), M, K, N, a_ws.data_ptr(),
+                                            out.data_ptr(), _stream()), "ftn_debug_tc_linear_split")
+    o = out.view(M, 3, N).float()
+    return o[:, 0] + o[:, 1] + o[:, 2]
 
 
 def debug_conv_tiled(inp: torch.Tensor, plan_dev: torch.Tensor, B: int, L: int, max_groups: int,

@@ -69,6 +69,12 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         keep.append(d)
         return d.data_ptr()
 
+    def dev_planes(planes: torch.Tensor) -> int:
+        """already-bf16 tensor of split planes -> device"""
+        d = planes.contiguous().to(device)
+        keep.append(d)
+        return d.data_ptr()
+
     st.cin, st.cout, st.n_branch = int(cin), int(cout), n_branch
     macs = 0
     if bottleneck:
@@ -79,6 +85,9 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         b_in = torch.cat([p[0].bias.detach().to("cpu", f64) for p in paths], dim=0)
         st.w_in, st.b_in = dev(w_in.t()), dev(b_in)
         st.w_in_bf16 = dev16(w_in)                                           # [NB][cin]
+        tc_ok = mid % 16 == 0 and cin % 16 == 0 and cout % 16 == 0           # tensor-core tile granularity
+        if tc_ok:
+            st.w_in_s3 = dev_planes(torch.cat(split3(w_in), dim=1))          # [NB][3 cin]
         macs += cin * n_branch * mid
         w_out_rows = []
         b_out = proj_b.clone()
@@ -91,6 +100,10 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             st.b_kk[j] = dev(p[1].bias.detach().to("cpu", f64))
             if mid == 32 and kh % 2 == 1 and kw % 2 == 1:
                 st.w_kk_phase[j] = dev16(_phase_stage_images(wk))
+            if tc_ok and kh % 2 == 1 and kw % 2 == 1:
+                img3 = _tap_images(wk)                                       # [tap][3][mid/8][mid][8] bf16
+                st.w_kk_img3[j] = dev_planes(img3)
+                st.w_kk_img[j] = dev_planes(img3[:, 0])
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
@@ -99,6 +112,8 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         w_out_kn = torch.cat(w_out_rows, dim=0)                              # [NB][cout]
         st.w_out, st.b_out = dev(w_out_kn), dev(b_out)
         st.w_out_bf16 = dev16(w_out_kn.t())                                  # [cout][NB]
+        if tc_ok:
+            st.w_out_s3 = dev_planes(torch.cat(split3(w_out_kn.t()), dim=1))  # [cout][3 NB]
         macs += n_branch * mid * cout
     else:
         st.mid = 0
@@ -125,6 +140,8 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         st.w_res = dev(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0].t())   # [cin, cout]
         st.w_res_bf16 = dev16(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0])  # [cout][cin]
         st.b_res = dev(block.res_proj.bias.detach().to("cpu", f64))
+        if bottleneck and tc_ok:
+            st.w_res_s3 = dev_planes(torch.cat(split3(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0]), dim=1))
         macs += cin * cout
     else:
         st.w_res, st.b_res = None, None
@@ -152,6 +169,27 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             second = both.reshape(NB + cout, cin // 64, 64).permute(1, 0, 2)           # [cin/64][NB+cout][64]
             st.w_mid_second = dev16(second)                                            # == [cin/128][2][NB+cout][64]
     return PackedInception(st, keep, macs)
+
+
+def split3(t: torch.Tensor):
+    """fp32 value of ``t`` as three bf16 planes (hi, mid, lo): hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid).
+    ``t`` is first rounded to fp32 (the reference's parameter dtype); the residuals are exact in fp32."""
+    v = t.to(torch.float32)
+    hi = v.to(torch.bfloat16)
+    r1 = v - hi.to(torch.float32)
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.to(torch.float32)).to(torch.bfloat16)
+    return hi, mid, lo
+
+
+def _tap_images(wk: torch.Tensor) -> torch.Tensor:
+    """Per-tap weight images of the streaming k x k kernel (tc_convs.cu; layout in include/flowtimes.h).
+
+    wk: [mid out, mid in, kh, kw] -> bf16 [kh*kw][3 planes][mid/8 chunks][mid out][8 in]."""
+    n_out, n_in, kh, kw = (int(v) for v in wk.shape)
+    planes = torch.stack(split3(wk), dim=0)                                  # [3][out][in][kh][kw]
+    img = planes.permute(3, 4, 0, 2, 1).reshape(kh * kw, 3, n_in // 8, 8, n_out)   # [tap][plane][chunk][8 in][out]
+    return img.permute(0, 1, 2, 4, 3).contiguous()                           # [tap][plane][chunk][out][8 in]
 
 
 def _phase_stage_images(wk: torch.Tensor) -> torch.Tensor:

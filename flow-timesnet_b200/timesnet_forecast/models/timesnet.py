@@ -1134,9 +1134,14 @@ class TimesNet(nn.Module):
                 self._series_id_reference = ids_ref.to(dev)
             else:
                 if ids_ref is not None:
-                    vocab = int(ids_ref.max().item()) + 1 if ids_ref.numel() > 0 else c_in
-                    if vocab > int(self.series_embedding.num_embeddings):
-                        raise ValueError("series_ids vocabulary expanded between calls")
+                    # the vocabulary check reads the ids back (one host sync): done once per distinct ids tensor, so a
+                    # caller that passes the same tensor every step stays sync-free (and capturable in a CUDA graph)
+                    key = (series_ids.data_ptr(), series_ids._version, tuple(series_ids.shape))
+                    if getattr(self, "_ids_checked", None) != key:
+                        vocab = int(ids_ref.max().item()) + 1 if ids_ref.numel() > 0 else c_in
+                        if vocab > int(self.series_embedding.num_embeddings):
+                            raise ValueError("series_ids vocabulary expanded between calls")
+                        self._ids_checked = key
                     self._series_id_reference = ids_ref.to(dev)
                 elif self._series_id_reference is None:
                     self._series_id_reference = torch.arange(c_in, device=dev, dtype=torch.long)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 9
+#define FTN_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -115,6 +115,18 @@ typedef struct FtnInceptionWeights {
    * row dr holds w_kk[dr][dx][n][c * 8 .. c * 8 + 8) (output channel n, 8 input channels, bf16); all
    * other rows are zero.  NULL = that kernel is not used for this block. */
   const void* w_kk_phase[FTN_MAX_BRANCH];
+  /* Streaming k x k kernel (tc_convs.cu, any mid % 16 == 0): per branch one bf16 image per tap in the un-swizzled
+   * K-major operand layout, [tap][plane][mid / 8 chunks][mid out channels][8 in channels]; w_kk_img has one plane
+   * (bf16 activations), w_kk_img3 three (hi / mid / lo split of the fp32 weights, see below).  NULL = not packed. */
+  const void* w_kk_img[FTN_MAX_BRANCH];
+  const void* w_kk_img3[FTN_MAX_BRANCH];
+  /* fp32 activations on the tensor cores: every fp32 value v is carried as three bf16 planes hi = bf16(v),
+   * mid = bf16(v - hi), lo = bf16(v - hi - mid), side by side along K; a product is the six bf16 MMAs with plane
+   * indices i + j <= 2, fp32 accumulate (tc_gemm.cu).  Split copies of the 1x1 weights, "[N][3 K]" with plane p at
+   * columns [p K, (p + 1) K); NULL = the fp32 chain runs on the SIMT kernels. */
+  const void* w_in_s3;     /* [n_branch*mid][3 cin] */
+  const void* w_out_s3;    /* [cout][3 n_branch*mid] */
+  const void* w_res_s3;    /* [cout][3 cin] or NULL */
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */
@@ -188,9 +200,14 @@ FTN_API size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, const
 /* Unit-test hook for the tcgen05 GEMM: out[M][N] bf16 = a[M][K] . w[N][K]^T + bias (M % 128 == 0) */
 FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias, int M, int K, int N,
                                 void* out, void* stream);
+/* Unit-test hook for the three-plane fp32 mode of the same GEMM: a[M][K] fp32 is split into a_ws[M][3K] (scratch), and
+ * out_s3[M][3N] receives the bf16 planes hi | mid | lo of a . w^T + bias; w_s3[N][3K] = split weights. */
+FTN_API int ftn_debug_tc_linear_split(const float* a, const void* w_s3, const float* bias, int M, int K, int N,
+                                      void* a_ws, void* out_s3, void* stream);
 /* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
  * use_tc = 4 phases-on-M tcgen05 kernel (+ the image-resident kernel for long periods),
- * 2 image-resident tcgen05 kernel, 0 SIMT kernel. */
+ * 2 image-resident tcgen05 kernel, 5 streaming tcgen05 kernel, 6 streaming kernel on three-plane fp32
+ * activations (ld counts all three planes), 0 SIMT kernel. */
 FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                  int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,

@@ -69,3 +69,84 @@ def test_tc_conv_matches_simt_conv(mid, L, periods, variant):
             checked += Lp
             row += rt * 128
     assert checked > 0
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (256, 48, 64), (128, 256, 48), (384, 128, 256), (128, 16, 16), (256, 1024, 192)])
+def test_tc_linear_split_keeps_fp32_accuracy(M, K, N):
+    """Three-plane bf16 GEMM (6 MMAs per product, fp32 accumulate) against a float64 matmul: fp32-level error, four
+    orders of magnitude below a single bf16 product."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast._pack import split3
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    w_s3 = torch.cat(split3(w), dim=1).contiguous()
+    out = nv.debug_tc_linear_split(a.cuda(), w_s3.cuda(), bias.cuda())
+    torch.cuda.synchronize()
+    ref = (a.double() @ w.double().t() + bias.double())
+    err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, f"rel err {err:.3e}"
+
+
+def _tile_major_images(plan_host, B, L, NB, seed, dtype):
+    """Random per-image activations placed in the tile-major layout of the tensor-core chain."""
+    G = plan_host.n_groups
+    tiles = sum(B * ((L + plan_host.grp_pad[g] + 127) // 128) for g in range(G))
+    g_ = torch.Generator().manual_seed(seed)
+    buf = torch.zeros(tiles * 128, NB, dtype=dtype)
+    imgs, row = [], 0
+    for gi in range(G):
+        Lp = L + plan_host.grp_pad[gi]
+        rt = (Lp + 127) // 128
+        for b in range(B):
+            im = torch.randn(Lp, NB, generator=g_).to(dtype)
+            buf[row:row + Lp] = im
+            imgs.append((gi, row, im))
+            row += rt * 128
+    return buf, imgs
+
+
+@pytest.mark.parametrize("mid,L,periods", [(16, 96, [24, 12, 7, 48, 95]), (32, 336, [24, 168, 335, 5]), (64, 720, [6, 24, 359, 719]),
+                                            (64, 96, [1, 2, 48]), (48, 50, [7, 25])])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
+    """Streaming k x k kernel (any mid, bf16 or three-plane fp32 activations) against torch conv2d in float64 on the
+    folded grids: bf16 activations to one output rounding, the three-plane mode to fp32 accuracy."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast._pack import split3
+    from timesnet_forecast.models.timesnet import InceptionBlock
+    B, C = 2, mid * 4
+    torch.manual_seed(0)
+    blk = InceptionBlock(C, C, [(3, 3), (5, 5), (7, 7)], 0.0, "gelu", bottleneck_ratio=4.0).cuda()
+    packed = blk.packed(torch.device("cuda"))
+    assert packed.struct.mid == mid
+    plan_host = nv.plan_build_host(periods, L, None, None)
+    plan = nv.plan_to_device(plan_host, "cuda")
+    NB = 3 * mid
+    dt = torch.bfloat16 if planes == 1 else torch.float32
+    buf, imgs = _tile_major_images(plan_host, B, L, NB, 1, dt)
+    if planes == 1:
+        inp = buf.cuda()
+    else:
+        inp = torch.cat(split3(buf), dim=1).contiguous().cuda()        # [rows][3 NB]
+    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=5 if planes == 1 else 6)
+    torch.cuda.synchronize()
+    got = got.float().cpu()
+    if planes == 3:
+        got = got[:, :NB] + got[:, NB:2 * NB] + got[:, 2 * NB:]
+    worst = 0.0
+    for gi, row, im in imgs:
+        per, cyc = plan_host.grp_period[gi], plan_host.grp_cycles[gi]
+        Lp = per * cyc
+        for j, path in enumerate(blk.paths):
+            conv = path.branch[1]
+            grid = im[:, j * mid:(j + 1) * mid].double().t().reshape(1, mid, cyc, per)
+            ref = torch.nn.functional.conv2d(grid, conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(),
+                                             padding=(conv.kernel_size[0] // 2, conv.kernel_size[1] // 2))
+            ref = ref.reshape(mid, Lp).t()
+            out = got[row:row + Lp, j * mid:(j + 1) * mid].double()
+            err = (out - ref).abs().max().item() / ref.abs().max().item()
+            worst = max(worst, err)
+            assert err < (1e-2 if planes == 1 else 1e-5), f"group {gi} (p={per}) branch {j}: rel err {err:.3e}"
+    assert worst > 0.0
