@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block of the N > 1 line")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the spectrum sums are exchanged (NVLink peer mailbox inside the selection kernel, or NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of CUDA-graph replay")
     ap.add_argument("--activation", default="gelu", choices=["gelu", "relu"],
                     help="diagnostic only: relu removes the GELU cost from the epilogues (the metric is quoted on gelu)")
@@ -299,7 +301,7 @@ def run_native(args):
                      use_checkpoint=False, stack_dtype=sdt, use_zero_mean_context=wl.context_rank > 0,
                      context_rank=wl.context_rank, context_scale=0.05)
     if world > 1:
-        share_period_search(model)                              # the shared search of SURVEY 8e is opt-in
+        share_period_search(model, transport=args.transport)    # the shared search of SURVEY 8e is opt-in
     ids = torch.arange(wl.N, device=dev)
     if recursive:
         x_cpu, st_cpu = recursive_inputs(wl, wl.B, seed=rank)
@@ -619,7 +621,10 @@ def run_native(args):
                                  "resident; value counts window-steps (series x 28)" if recursive else
                                  "TimesBlock stack (n_layers x (TimesBlock + shared LayerNorm)), features resident")
                                 + ("" if args.no_graph else "; step = CUDA-graph replay"),
-                       "l2": l2_note, "selected_periods": group_periods},
+                       "l2": l2_note, "selected_periods": group_periods,
+                       "spectrum_exchange": None if world == 1 else (
+                           "NVLink peer mailbox inside the selection kernel" if model.period_selector.peer_comm is not None
+                           else "NCCL all-reduce")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launch_mode": "eager" if args.no_graph else "cuda_graph",
             "eager_ms_per_step": eager_ms_step, "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -518,11 +518,12 @@ namespace {
 struct SearchCtx {
   const void* x; int dtype, B, L, C, k, pmax, min_period;
   float* amp_median; float* amp_sum; FtnPeriodPlan* plan; void* amps; float* weights; void* ws; size_t ws_bytes;
+  void* peer_comm;
 };
 int run_search(void* c, cudaStream_t st) {
   const SearchCtx* s = static_cast<const SearchCtx*>(c);
   return ftn_period_search(s->x, s->dtype, s->B, s->L, s->C, s->k, s->pmax, s->min_period, s->amp_median, s->amp_sum, s->plan,
-                           s->amps, s->weights, s->ws, s->ws_bytes, st);
+                           s->amps, s->weights, s->ws, s->ws_bytes, s->peer_comm, st);
 }
 }  // namespace
 
@@ -530,7 +531,8 @@ extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, in
                                       float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
                                       void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
                                       const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
-                                      float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+                                      float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* peer_comm,
+                                      void* stream) {
   FTN_REQUIRE(x && plan && out && workspace && weights && amps && amp_median && amp_sum && search_workspace,
               "ftn_timesblock_forward: null pointer");
   FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_timesblock_forward: bad sizes B=%d L=%d C=%d", B, L, C);
@@ -545,7 +547,7 @@ extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, in
   FTN_REQUIRE(workspace_bytes >= ftn_inception_workspace_bytes(B, L, k, a, b), "ftn_timesblock_forward: workspace too small");
   FTN_REQUIRE(search_workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_timesblock_forward: search workspace too small");
   SearchCtx ctx{x, dtype, B, L, C, k, pmax, min_period, amp_median, amp_sum, plan, amps, weights, search_workspace,
-                search_workspace_bytes};
+                search_workspace_bytes, peer_comm};
   // periods the selection kernel can emit: ceil(L / bin) with bin in [1, L/2], clamped to [min_period, pmax], and at
   // least two cycles (period_search.cu); the k x k stages skip their long-period fallback launch when none can need it
   const int hi_raw = pmax > 0 && pmax < L - 1 ? pmax : L - 1;

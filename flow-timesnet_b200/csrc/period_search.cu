@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace ftn {
 
@@ -121,7 +122,7 @@ channel_median_kernel(const float* __restrict__ amp, int rows /*B*F*/, int C, fl
 
 // amp_sum[f] = sum_b med[b][f], fixed order: 32 row-lanes then a serial fold
 __global__ void __launch_bounds__(1024) batch_sum_kernel(const float* __restrict__ med, int B, int F,
-                                                        float* __restrict__ amp_sum) {
+                                                        float* __restrict__ amp_sum, int count) {
   __shared__ float part[32][33];
   const int fl = threadIdx.x, r = threadIdx.y;
   const int f = blockIdx.x * 32 + fl;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(1024) batch_sum_kernel(const float* __restrict
     for (int i = 0; i < 32; ++i) t += part[i][fl];
     amp_sum[f] = t;
   }
-  if (blockIdx.x == 0 && r == 0 && fl == 0) amp_sum[F] = (float)B;   // window count rides along (all-reduced with the sums)
+  if (blockIdx.x == 0 && r == 0 && fl == 0) amp_sum[F] = (float)count;   // window count rides along (all-reduced with the sums)
 }
 
 // rank key: larger is better; NaN ranks above everything like torch.topk
@@ -144,6 +145,50 @@ __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {
   if (na != nb) return na;
   if (!na && sa != sb) return sa > sb;
   return ia < ib;  // tie rule: lower bin first
+}
+
+// per window: amplitudes at the chosen bins (dtype) + softmax group weights.  The fused selection kernel does this in its
+// own tail for ordinary batches; with tens of thousands of windows (BASELINE config 5) one CTA walking them is the
+// bottleneck of the search, so the tail runs as its own grid.
+template <typename T>
+__global__ void __launch_bounds__(128)
+finish_kernel(const float* __restrict__ amp_median, int B, int F, int k, const FtnPeriodPlan* __restrict__ plan,
+              T* __restrict__ amps, float* __restrict__ weights) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nv = plan->n_valid;
+  float a[FTN_MAX_K];
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {
+    float v = 0.f;
+    if (j < nv) v = round_to<T>(amp_median[(size_t)b * F + (int)plan->freq[j]]);
+    a[j] = v;
+    if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
+  }
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j)
+    if (j < nv && plan->mapping[j] >= 0) mx = fmaxf(mx, a[j]);
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j)
+    if (j < nv && plan->mapping[j] >= 0) den += expf(a[j] - mx);
+  float w[FTN_MAX_K];
+#pragma unroll
+  for (int g = 0; g < FTN_MAX_K; ++g) w[g] = 0.f;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {                 // candidates in index order, exactly like scatter_add_
+    const int g = j < nv ? plan->mapping[j] : -1;
+    if (g < 0) continue;
+    const float sm = round_to<T>(expf(a[j] - mx) / den);    // softmax fp32 -> dtype (timesnet.py:1000)
+#pragma unroll
+    for (int q = 0; q < FTN_MAX_K; ++q)
+      if (q == g) w[q] = round_to<T>(w[q] + sm);            // scatter_add_ in dtype (:1009)
+  }
+#pragma unroll
+  for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
 }
 
 // same second half for externally supplied amplitudes (custom selector modules)
@@ -258,9 +303,10 @@ constexpr int kSelFinishThreads = 128;   // 2 x 8 KB of per-thread slots; static
 
 template <typename T>
 __global__ void __launch_bounds__(1024)
-select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ amp_sum, int do_sum, int B,
+select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ amp_sum, int do_sum,
+                    const float* __restrict__ sum_src, int sum_rows, int B, int do_finish,
                     int global_batch, int L, int k, int pmax, int min_period, FtnPeriodPlan* __restrict__ plan,
-                    T* __restrict__ amps, float* __restrict__ weights) {
+                    T* __restrict__ amps, float* __restrict__ weights, const PeerDev peer) {
   extern __shared__ float sf[];
   const int F = L / 2 + 1;
   float* s_sum = sf;              // [F + 1]
@@ -283,23 +329,23 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       int b = warp;
 #pragma unroll 1
-      for (; b + 32 < B; b += 64) {
+      for (; b + 32 < sum_rows; b += 64) {
         float v[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int f = f0 + 32 * q;
-          v[q] = f < F ? amp_median[(size_t)b * F + f] : 0.f;
-          v[4 + q] = f < F ? amp_median[(size_t)(b + 32) * F + f] : 0.f;
+          v[q] = f < F ? sum_src[(size_t)b * F + f] : 0.f;
+          v[4 + q] = f < F ? sum_src[(size_t)(b + 32) * F + f] : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) { acc[q] += v[q]; acc[q] += v[4 + q]; }   // same order as the serial loop
       }
 #pragma unroll 1
-      for (; b < B; b += 32) {
+      for (; b < sum_rows; b += 32) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int f = f0 + 32 * q;
-          if (f < F) acc[q] += amp_median[(size_t)b * F + f];
+          if (f < F) acc[q] += sum_src[(size_t)b * F + f];
         }
       }
 #pragma unroll
@@ -318,6 +364,14 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
       amp_sum[f] = t;
     }
     if (tid == 0) { s_sum[F] = (float)B; amp_sum[F] = (float)B; }
+    if (peer.world > 1) {
+      // sharded batch: exchange the F sums + the window count with the peers over NVLink (peer.cuh) -- every rank ends
+      // up with the same rank-ordered totals, so the selection below is identical everywhere
+      __syncthreads();
+      peer_allreduce_cta(peer, s_sum, F + 1);
+#pragma unroll 1
+      for (int f = tid; f <= F; f += blockDim.x) amp_sum[f] = s_sum[f];
+    }
   } else {
 #pragma unroll 1
     for (int f = tid; f <= F; f += blockDim.x) s_sum[f] = amp_sum[f];
@@ -402,7 +456,7 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
   }
   // per window: amplitudes at the chosen bins (dtype) + softmax group weights  
   const int nv = s_plan.n_valid;
-  if (tid < kSelFinishThreads) {
+  if (do_finish && tid < kSelFinishThreads) {
     #pragma unroll 1
     for (int b = tid; b < B; b += kSelFinishThreads) {
       float mx = -CUDART_INF_F;
@@ -442,6 +496,8 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // spectrum_fft.cu
+int spectrum_small_launch(const void* x, int dtype, int B, int L, int C, float* med, float* part, int part_rows_cap,
+                          cudaStream_t st);
 int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, float* med, bool* fused_median,
                         cudaStream_t st);
 int channel_median_reg_launch(const float* amp, int rows, int C, float* med, cudaStream_t st);
@@ -456,8 +512,12 @@ extern "C" size_t ftn_spectrum_workspace_bytes(int B, int L, int C) {
   return align256((size_t)B * F * C * sizeof(float)) + align256(F * sizeof(float)) + 256;
 }
 
+// sum_src / sum_rows: what the batch sum of the caller's selection kernel has to add up (the B median rows, or the
+// per-CTA partial rows the small-window kernel leaves in the workspace)
 static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum);
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum,
+                         const float** sum_src = nullptr, int* sum_rows = nullptr);
+constexpr int kFinishInKernelMax = 1024;   // windows the one-CTA selection kernel finishes itself
 
 extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
                             float* amp_sum, void* workspace, size_t workspace_bytes, void* stream) {
@@ -468,37 +528,63 @@ extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float
 
 static int launch_select_fused(const float* amp_median, float* amp_sum, int do_sum, int dtype, int B, int global_batch,
                                int L, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
-                               cudaStream_t st, bool after_fft) {
+                               cudaStream_t st, bool after_fft, const float* sum_src = nullptr, int sum_rows = 0,
+                               const void* comm = nullptr) {
   const int F = L / 2 + 1;
   TimedScope ts(FTN_FAM_SELECT, st);
+  PeerDev peer{};
+  peer.world = 1;
+  if (const PeerDev* pv = peer_dev_view(comm)) peer = *pv;
+  FTN_REQUIRE(peer.world == 1 || (do_sum && F + 1 <= FTN_PEER_MAX_FLOATS), "period search: peer exchange needs do_sum and L <= %d",
+              2 * (FTN_PEER_MAX_FLOATS - 2));
+  if (!sum_src) { sum_src = amp_median; sum_rows = B; }
+  const int do_finish = B <= kFinishInKernelMax ? 1 : 0;
   const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : F)) * sizeof(float);
   FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
   if (dtype == FTN_F32) {
     FTN_DYN_SMEM(select_fused_kernel<float>, smem);
-    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B, global_batch, L,
-                        k, pmax, min_period, plan, (float*)amps, weights));
+    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<float>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, sum_src,
+                        sum_rows, B, do_finish, global_batch, L, k, pmax, min_period, plan, (float*)amps, weights, peer));
   } else {
     FTN_DYN_SMEM(select_fused_kernel<__nv_bfloat16>, smem);
-    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum, B,
-                        global_batch, L, k, pmax, min_period, plan, (__nv_bfloat16*)amps, weights));
+    FTN_CUDA(launch_pdl(after_fft, select_fused_kernel<__nv_bfloat16>, dim3(1), dim3(1024), smem, st, amp_median, amp_sum, do_sum,
+                        sum_src, sum_rows, B, do_finish, global_batch, L, k, pmax, min_period, plan, (__nv_bfloat16*)amps, weights,
+                        peer));
   }
   FTN_LAUNCH_CHECK("select_fused_kernel");
+  if (!do_finish) {   // many windows: the per-window tail as its own grid
+    const dim3 grid((B + 127) / 128);
+    if (dtype == FTN_F32)
+      FTN_CUDA(launch_pdl(true, finish_kernel<float>, grid, dim3(128), 0, st, amp_median, B, F, k, (const FtnPeriodPlan*)plan,
+                          (float*)amps, weights));
+    else
+      FTN_CUDA(launch_pdl(true, finish_kernel<__nv_bfloat16>, grid, dim3(128), 0, st, amp_median, B, F, k,
+                          (const FtnPeriodPlan*)plan, (__nv_bfloat16*)amps, weights));
+    FTN_LAUNCH_CHECK("finish_kernel");
+  }
   return 0;
 }
 
 extern "C" int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                                  float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 void* workspace, size_t workspace_bytes, void* peer_comm, void* stream) {
   FTN_REQUIRE(plan && amps && weights, "ftn_period_search: null pointer");
   FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_period_search: k=%d outside [1,%d]", k, FTN_MAX_K);
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_SPECTRUM, st);
-  if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false)) return rc;
-  return launch_select_fused(amp_median, amp_sum, 1, dtype, B, B, L, k, pmax, min_period, plan, amps, weights, st, true);
+  const float* sum_src = nullptr;
+  int sum_rows = 0;
+  if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false, &sum_src, &sum_rows))
+    return rc;
+  // with a peer communicator the count slot is reduced too: divide by the GLOBAL batch (global_batch <= 0 = "take it
+  // from the count slot")
+  return launch_select_fused(amp_median, amp_sum, 1, dtype, B, peer_comm ? 0 : B, L, k, pmax, min_period, plan, amps, weights, st,
+                             true, sum_src, sum_rows, peer_comm);
 }
 
 static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum,
+                         const float** sum_src, int* sum_rows) {
   FTN_REQUIRE(x && amp_median && amp_sum && workspace, "ftn_spectrum: null pointer");
   FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_spectrum: need B>0, L>1, C>0 (got %d,%d,%d)", B, L, C);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_spectrum: unsupported dtype %d", dtype);
@@ -506,6 +592,26 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
   FTN_REQUIRE(workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_spectrum: workspace too small");
   const int F = L / 2 + 1;
   float* amp = reinterpret_cast<float*>(workspace);
+  if (sum_src) { *sum_src = amp_median; *sum_rows = B; }
+  {
+    // short windows, many of them: grid-stride CTAs, medians + per-CTA partial sums in one kernel (spectrum_fft.cu)
+    int rows = 0;
+    if (L <= 64 && B >= 256) {   // (the launcher re-checks; no timing record for a kernel that does not run)
+      TimedScope tf(FTN_FAM_FFT, st);
+      rows = spectrum_small_launch(x, dtype, B, L, C, amp_median, amp, (int)(workspace_bytes / ((size_t)F * 4)), st);
+    }
+    if (rows < 0) return 2;
+    if (rows > 0) {
+      if (with_batch_sum) {
+        batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp, rows, F, amp_sum, B);
+        FTN_LAUNCH_CHECK("batch_sum_kernel");
+      } else if (sum_src) {
+        *sum_src = amp;
+        *sum_rows = rows;
+      }
+      return 0;
+    }
+  }
   int rc;
   bool fused_median = false;   // C <= 256: the FFT kernel's clusters also reduce over channels
   { TimedScope tf(FTN_FAM_FFT, st); rc = spectrum_fft_launch(x, dtype, B, L, C, amp, amp_median, &fused_median, st); }   // mixed-radix FFT (even L); -1 = n/a
@@ -534,7 +640,7 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
     FTN_LAUNCH_CHECK("channel_median_kernel");
   }
   if (with_batch_sum) {
-    batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum);
+    batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum, B);
     FTN_LAUNCH_CHECK("batch_sum_kernel");
   }
   return 0;

@@ -328,6 +328,127 @@ channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float*
   if (lane == 0) med[row] = has_nan ? CUDART_NAN_F : pick;   // torch.median propagates NaN
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short windows (L <= 64; BASELINE config 5 has L = 28 and tens of thousands of windows): one CTA per window with a
+// cluster per window is all overhead there (2.7 ms for 30 000 windows of 28 x 128).  Here a CTA of C threads (one per
+// channel) walks over windows with a grid stride:
+//   * every thread loads its channel's L samples (coalesced across the CTA), folds them into the even / odd parts
+//     s[t] = x[t] + x[L - t], d[t] = x[t] - x[L - t] and evaluates the F = L / 2 + 1 bins directly,
+//       Re X[f] = x[0] + sum_t s[t] cos(2 pi f t / L) (+ (-1)^f x[L / 2]),  Im X[f] = -sum_t d[t] sin(2 pi f t / L),
+//     from one cos / sin table in shared memory (half the multiply-adds of the plain DFT, any L, even or odd);
+//   * the amplitudes of the window go to shared memory and the warps take the lower median over channels per bin
+//     (same register bitonic network as the FFT kernel);
+//   * each bin's medians are also summed over the windows of this CTA (fixed order), so the batch sum of the search is
+//     a second-level sum over gridDim.x partial rows instead of B median rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int KPL>
+__global__ void __launch_bounds__(KPL * 32)
+spectrum_small_kernel(const T* __restrict__ x, int B, int L, int C, float* __restrict__ med /*[B][F]*/,
+                      float* __restrict__ part /*[gridDim.x][F] or null*/) {
+  extern __shared__ float ssm[];
+  const int F = L / 2 + 1, H = (L - 1) / 2;
+  const int nthr = blockDim.x, Cp = nthr + 1;
+  float2* tw = reinterpret_cast<float2*>(ssm);            // [L]: (cos, sin)(2 pi k / L)
+  float* xs = ssm + 2 * L;                                // [L][Cp]   per-thread columns (no cross-thread access)
+  float* amp = xs + (size_t)L * Cp;                       // [F][nthr] amplitudes of the current window
+  float* sums = amp + (size_t)F * nthr;                   // [F]       partial batch sums of this CTA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  pdl_trigger();
+  for (int k = tid; k < L; k += nthr) {
+    float s, c;
+    sincospif(2.0f * (float)k / (float)L, &s, &c);
+    tw[k] = make_float2(c, s);
+  }
+  for (int f = tid; f < F; f += nthr) sums[f] = 0.f;
+  pdl_wait();   // x is a predecessor's output; the table is not
+  __syncthreads();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const T* xb = x + (size_t)b * L * C;
+    if (tid < C) {
+#pragma unroll 4
+      for (int t = 0; t < L; ++t) xs[t * Cp + tid] = to_f32<T>(xb[(size_t)t * C + tid]);
+      for (int t = 1; t <= H; ++t) {                      // fold: rows 1..H hold s, rows L-H..L-1 hold d
+        const float a = xs[t * Cp + tid], z = xs[(L - t) * Cp + tid];
+        xs[t * Cp + tid] = a + z;
+        xs[(L - t) * Cp + tid] = a - z;
+      }
+      const float x0 = xs[tid];
+      const float xh = (L & 1) ? 0.f : xs[(L / 2) * Cp + tid];
+      for (int f = 0; f < F; ++f) {
+        float re = x0 + ((f & 1) ? -xh : xh), im = 0.f;
+        int idx = 0;
+        for (int t = 1; t <= H; ++t) {
+          idx += f;
+          if (idx >= L) idx -= L;
+          const float2 w = tw[idx];
+          re = fmaf(xs[t * Cp + tid], w.x, re);
+          im = fmaf(xs[(L - t) * Cp + tid], w.y, im);
+        }
+        amp[f * nthr + tid] = sqrtf(fmaf(re, re, im * im));
+      }
+    } else {
+      for (int f = 0; f < F; ++f) amp[f * nthr + tid] = CUDART_INF_F;   // padding sorts last
+    }
+    __syncthreads();
+    for (int f = warp; f < F; f += nwarp) {
+      float v[KPL];
+      bool has_nan = false;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const float a = amp[f * nthr + i * 32 + lane];     // any assignment of channels to sort slots works
+        has_nan = has_nan || (a != a);
+        v[i] = a;
+      }
+      has_nan = __any_sync(0xffffffffu, has_nan);
+      const float pick = warp_lower_median<KPL>(v, C, lane);
+      if (lane == 0) {
+        const float m = has_nan ? CUDART_NAN_F : pick;     // torch.median propagates NaN
+        med[(size_t)b * F + f] = m;
+        sums[f] += m;                                      // bin f always belongs to this warp: no race
+      }
+    }
+    __syncthreads();
+  }
+  if (part)
+    for (int f = tid; f < F; f += nthr) part[(size_t)blockIdx.x * F + f] = sums[f];
+}
+
+// returns the number of partial rows written (> 0), 0 when the small-window kernel does not apply, < 0 on error
+int spectrum_small_launch(const void* x, int dtype, int B, int L, int C, float* med, float* part, int part_rows_cap,
+                          cudaStream_t st) {
+  static const bool off = getenv("FLOWTIMES_NO_SMALL_FFT") != nullptr;   // A/B switch for profiling
+  if (off || L > 64 || L < 2 || C > 512 || B < 256) return 0;
+  const int kpl = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 128 ? 4 : (C <= 256 ? 8 : 16)));
+  const int nthr = kpl * 32, F = L / 2 + 1;
+  const size_t smem = (size_t)(2 * L + (size_t)L * (nthr + 1) + (size_t)F * nthr + F) * sizeof(float);
+  if (smem > 200 * 1024) return 0;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  const int by_threads = 2048 / nthr;
+  per_sm = per_sm > by_threads ? by_threads : per_sm;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  int grid = sm_count() * per_sm;
+  grid = grid > B ? B : grid;
+  grid = grid > part_rows_cap ? part_rows_cap : grid;
+  if (grid < 1) return 0;
+#define FTN_SMALL(T, K)                                                                                       \
+  do {                                                                                                        \
+    if (ensure_dyn_smem((const void*)spectrum_small_kernel<T, K>, smem)) return -1;                           \
+    spectrum_small_kernel<T, K><<<grid, nthr, smem, st>>>((const T*)x, B, L, C, med, part);                   \
+  } while (0)
+  if (dtype == FTN_F32) {
+    switch (kpl) { case 1: FTN_SMALL(float, 1); break; case 2: FTN_SMALL(float, 2); break; case 4: FTN_SMALL(float, 4); break;
+                   case 8: FTN_SMALL(float, 8); break; default: FTN_SMALL(float, 16); }
+  } else {
+    switch (kpl) { case 1: FTN_SMALL(__nv_bfloat16, 1); break; case 2: FTN_SMALL(__nv_bfloat16, 2); break;
+                   case 4: FTN_SMALL(__nv_bfloat16, 4); break; case 8: FTN_SMALL(__nv_bfloat16, 8); break;
+                   default: FTN_SMALL(__nv_bfloat16, 16); }
+  }
+#undef FTN_SMALL
+  count_launch();
+  if (check_cuda(cudaGetLastError(), "spectrum_small_kernel")) return -1;
+  return grid;
+}
+
 static bool fft_factor(int N, FftPlan* plan) {
   plan->n_pass = 0;
   auto push = [&](int r) {

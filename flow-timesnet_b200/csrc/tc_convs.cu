@@ -1,8 +1,12 @@
 // K3, k x k stage, general streaming variant: implicit-GEMM convolution on tcgen05 tensor cores for ANY branch width
 // mid (a multiple of 16, up to 128) in both activation formats of the tensor-core chain:
 //   NS = 1  bf16 activations [rows][NB]                     (one MMA per tap and K16 step)
-//   NS = 3  fp32 activations as three bf16 planes [rows][3 NB]   (tc_gemm.cu: six MMAs per tap and K16 step,
-//           fp32 accumulate in TMEM -- the fp32 configurations keep the 1e-4 bound on the tensor cores)
+//   NS = 3  fp32 activations as three bf16 planes [rows][3 NB]   (tc_gemm.cu: the six plane products with i + j <= 2,
+//           fp32 accumulate in TMEM -- the fp32 configurations keep the 1e-4 bound on the tensor cores).  The three
+//           weight planes of a tap sit side by side on N, so the six products are THREE MMAs per tap and K16 step:
+//           a_hi . [w_hi | w_mid | w_lo] (N = 3 mid), a_mid . [w_hi | w_mid] (N = 2 mid), a_lo . w_hi (N = mid), into
+//           three column groups of the accumulator that the epilogue adds up.  A small-N MMA costs what a full one
+//           does (A-fetch bound), so this halves the MMA stream.
 //
 //   out[pos][n] = bias[n] + sum_{dr,dw} sum_c in[pos shifted by (dr,dw)][c] * W[dr][dw][n][c]
 // on the folded [cycles, period] grid with zero "same" padding (timesnet.py:588, :1044-1057).
@@ -16,7 +20,7 @@
 //     band holding the halo of all tap rows (short periods, "mode A") or one 128 + 2 hw row segment per tap row
 //     ("mode B", long periods) -- loader warps, cp.async with zero fill;
 //   * the weights stream through a ring of slots, one tap row (or one tap when a row does not fit) per slot, each a
-//     single cp.async.bulk of a host-packed image [tap][plane][chunk][n][8] -- one producer thread;
+//     single cp.async.bulk of a host-packed image [tap][chunk][plane][n][8] -- one producer thread;
 //   * one warp issues the MMAs (M128, N = mid, K16) into a double-buffered TMEM accumulator, eight warps drain it
 //     (+bias, bf16 or three-plane split, store) while the next unit's MMAs run.
 // With N = mid <= 64 an MMA costs what an N = 128 one does (the 4 KB A fetch bounds it), so the kernel is bound by its
@@ -46,7 +50,7 @@ struct TcConvsArgs {
   int seg_cap;     // rows one segment buffer holds
   int w_slots, w_slot_bytes;
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH], ut[FTN_MAX_BRANCH];   // ut: taps per weight slot (kw or 1)
-  const uint8_t* w[FTN_MAX_BRANCH];    // [tap][plane][chunk][n][8] bf16
+  const uint8_t* w[FTN_MAX_BRANCH];    // [tap][chunk][plane][n][8] bf16
   const float* bias[FTN_MAX_BRANCH];
 };
 
@@ -104,9 +108,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
   const int mid = p.mid, nchunk = mid / 8, nck = NS * nchunk, ksteps = mid / 16;
   const uint32_t LBO_A = (uint32_t)(p.seg_cap + 2) * 16;      // chunk stride; +2 rows de-phases the banks of the chunks
   const uint32_t SEG_BYTES = ((uint32_t)nck * LBO_A + 127) & ~127u;
-  const uint32_t LBO_W = (uint32_t)mid * 16;
-  const uint32_t PLANE_W = (uint32_t)mid * mid * 2;           // one weight plane of one tap
-  const uint32_t TAP_BYTES = NS * PLANE_W;
+  const uint32_t LBO_W = (uint32_t)(NS * mid) * 16;          // chunk stride of the weight image: NS planes x mid rows
+  const uint32_t TAP_BYTES = (uint32_t)NS * mid * mid * 2;
+  const int acc_cols = NS * mid;                              // accumulator columns per buffer
 
   uint8_t* s_w = smem;
   uint8_t* s_seg = smem + (size_t)p.w_slots * p.w_slot_bytes;
@@ -131,7 +135,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
     }
     fence_barrier_init();
   }
-  const uint32_t tmem_cols = 2 * mid <= 32 ? 32u : (2 * mid <= 64 ? 64u : (2 * mid <= 128 ? 128u : 256u));
+  const uint32_t tmem_cols = 2 * acc_cols <= 32 ? 32u : (2 * acc_cols <= 64 ? 64u : (2 * acc_cols <= 128 ? 128u :
+                             (2 * acc_cols <= 256 ? 256u : 512u)));
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
   pdl_wait();   // the plan and the input are a predecessor's output
   if (tid == 0) {
@@ -165,20 +170,22 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
   const int stride = gridDim.x;
 
   if (warp == 0) {
-    // ===================== MMA issuer: ONE lane runs the whole loop =====================
-    // The stream is thousands of small MMAs (N = mid <= 64, ~80 cycles each on the tensor pipe), so the issuing
-    // thread must spend only a handful of instructions per MMA: 32-bit descriptor low words advanced by adds, the
-    // high words and every plane offset hoisted out of the loops (measured on the first version, which rebuilt 64-bit
-    // descriptors under elect.sync for each MMA: 230 cycles per MMA at mid = 16, tensor pipe 4 % active).
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(CS_BM, mid);
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    // The stream is thousands of small MMAs (~80 cycles each on the tensor pipe), so the issuing warp must spend only
+    // a handful of instructions per MMA: everything is warp-uniform (descriptor words live in uniform registers, no
+    // per-lane waterfall), 32-bit descriptor low words advanced by adds, high words and plane offsets hoisted, one
+    // elect per K16 step.  (First version: 64-bit descriptors rebuilt under elect.sync per MMA, 230 cycles per MMA at
+    // mid = 16; a single-lane loop needed R2UR broadcast loops per operand, 175 cycles per MMA at mid = 64.)
+    {
+      const uint32_t idesc = make_idesc_bf16(CS_BM, mid), idesc2 = make_idesc_bf16(CS_BM, 2 * mid),
+                     idesc3 = make_idesc_bf16(CS_BM, NS == 3 ? 3 * mid : mid);
       const uint32_t a_hi = (uint32_t)(make_desc_interleaved(0, LBO_A) >> 32);
       const uint32_t b_hi = (uint32_t)(make_desc_interleaved(0, LBO_W) >> 32);
       const uint32_t a_lbo = (uint32_t)make_desc_interleaved(0, LBO_A);      // LBO field of the low word
       const uint32_t b_lbo = (uint32_t)make_desc_interleaved(0, LBO_W);
       const uint32_t ks_a = 2 * (LBO_A >> 4), ks_w = 2 * (LBO_W >> 4);
       const uint32_t a_pl = (uint32_t)nchunk * (LBO_A >> 4);                 // activation plane stride (16-byte units)
-      const uint32_t w_pl = PLANE_W >> 4, w_tap = TAP_BYTES >> 4;
+      const uint32_t w_tap = TAP_BYTES >> 4;
       uint32_t seg_base[CS_NSEG];
 #pragma unroll
       for (int i = 0; i < CS_NSEG; ++i) seg_base[i] = ((smem_u32(s_seg + (size_t)i * SEG_BYTES) & 0x3FFFFu) >> 4) | a_lbo;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
         const int buf = it & 1;
         mbar_wait(&bars[CS_ACC_EMPTY + buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * mid;
+        const uint32_t acc = tmem_base + buf * acc_cols;
         uint32_t accum = 0;
         const int ut = p.ut[u.j];
         uint32_t seg_lo = 0;
@@ -221,40 +228,40 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
             uint32_t a_tap = row_lo + (uint32_t)dw0;
             for (int dw = dw0; dw < dw1; ++dw, ++a_tap, tap_lo += w_tap) {
               if (NS == 3) {
-                // (activation plane, weight plane) with i + j <= 2, smallest products first; hi = 0, mid = 1, lo = 2
+                // activation planes hi = 0, mid = 1, lo = 2 against the weight planes side by side on N:
+                //   a_hi . [w_hi | w_mid | w_lo], a_mid . [w_hi | w_mid], a_lo . w_hi  -> column groups 0, 1, 2
                 const uint32_t a0 = a_tap, a1 = a_tap + a_pl, a2 = a_tap + 2 * a_pl;
-                const uint32_t w0 = tap_lo, w1 = tap_lo + w_pl, w2 = tap_lo + 2 * w_pl;
-                uint32_t ko_a = 0, ko_w = 0;
-                for (int ks = 0; ks < ksteps; ++ks, ko_a += ks_a, ko_w += ks_w) {
-                  mma_bf16_lohi(acc, a2 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, accum);
-                  mma_bf16_lohi(acc, a1 + ko_a, a_hi, w1 + ko_w, b_hi, idesc, 1u);
-                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w2 + ko_w, b_hi, idesc, 1u);
-                  mma_bf16_lohi(acc, a1 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, 1u);
-                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w1 + ko_w, b_hi, idesc, 1u);
-                  mma_bf16_lohi(acc, a0 + ko_a, a_hi, w0 + ko_w, b_hi, idesc, 1u);
+                uint32_t ko_a = 0, b_k = tap_lo;
+                for (int ks = 0; ks < ksteps; ++ks, ko_a += ks_a, b_k += ks_w) {
+                  if (elect_one()) {
+                    mma_bf16_lohi(acc, a0 + ko_a, a_hi, b_k, b_hi, idesc3, accum);
+                    mma_bf16_lohi(acc, a1 + ko_a, a_hi, b_k, b_hi, idesc2, 1u);
+                    mma_bf16_lohi(acc, a2 + ko_a, a_hi, b_k, b_hi, idesc, 1u);
+                  }
                   accum = 1;
                 }
               } else {
                 uint32_t a_k = a_tap, b_k = tap_lo;
                 for (int ks = 0; ks < ksteps; ++ks, a_k += ks_a, b_k += ks_w) {
-                  mma_bf16_lohi(acc, a_k, a_hi, b_k, b_hi, idesc, accum);
+                  if (elect_one()) mma_bf16_lohi(acc, a_k, a_hi, b_k, b_hi, idesc, accum);
                   accum = 1;
                 }
               }
             }
-            mma_commit(&bars[CS_W_EMPTY + w_slot]);
+            if (elect_one()) mma_commit(&bars[CS_W_EMPTY + w_slot]);
             if (++w_slot == n_wslots) { w_slot = 0; w_par ^= 1u; }
           }
           if (!u.mode_a) {
-            mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
+            if (elect_one()) mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
             ++seg_it;
           }
         }
         if (u.mode_a) {
-          mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
+          if (elect_one()) mma_commit(&bars[CS_SEG_EMPTY + seg_it % CS_NSEG]);
           ++seg_it;
         }
-        mma_commit(&bars[CS_ACC_FULL + buf]);
+        if (elect_one()) mma_commit(&bars[CS_ACC_FULL + buf]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -349,7 +356,18 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
       const float* bias = p.bias[u.j];
       for (int c = half * 16; c < mid; c += 32) {
         float v[16];
-        tmem_ld16(tmem_base + buf * mid + c + ((uint32_t)(quad * 32) << 16), v);
+        const uint32_t tcol = tmem_base + buf * acc_cols + c + ((uint32_t)(quad * 32) << 16);
+        if (NS == 3) {      // the three column groups hold the plane products: add them up
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16_nowait(tcol, r0);
+          tmem_ld16_nowait(tcol + mid, r1);
+          tmem_ld16_nowait(tcol + 2 * mid, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = (__uint_as_float(r2[k]) + __uint_as_float(r1[k])) + __uint_as_float(r0[k]);
+        } else {
+          tmem_ld16(tcol, v);
+        }
         if (ok) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] += __ldg(bias + c + k);
@@ -424,6 +442,7 @@ static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
 bool tc_convs_eligible(const FtnInceptionWeights* w, int ns) {
   if (w->mid < 16 || w->mid > 128 || w->mid % 16) return false;
   if (ns != 1 && ns != 3) return false;
+  if (ns == 3 && w->mid > 80) return false;   // 3 mid <= 256 (one MMA's N) and 6 mid <= 512 TMEM columns
   for (int j = 0; j < w->n_branch; ++j) {
     if (!(w->kh[j] & 1) || !(w->kw[j] & 1)) return false;
     if (!(ns == 3 ? w->w_kk_img3[j] : w->w_kk_img[j])) return false;

@@ -15,6 +15,8 @@
 // zeros (TMA out-of-bounds fill) -- exactly the zero tail F.pad adds in the
 // reference (timesnet.py:1017).  Intermediates live tile-major, 128 rows per
 // tile, so tile id == row block and no store needs masking.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -143,28 +145,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        const bool ph2 = kb >= nkb1;
-        const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
-        const int K = ph2 ? p.K2 : p.K1;
-        const CUtensorMap* ma = ph2 ? &tmA2 : &tmA1;
-        const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
-        // SPLIT: planes 0..2 of the activation, then planes 0..2 of the weights (plane p = columns [p K, (p + 1) K);
-        // a box that runs past its plane / the tensor reads the next plane / zeros, which no MMA consumes)
-        constexpr int NP = SPLIT ? 3 : 1;
-#pragma unroll
-        for (int pl = 0; pl < NP; ++pl) {
-          uint8_t* dst = sa + pl * TC_TILE_BYTES;
-          if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(dst, ma, &full[s], pl * K + k0, t0, b);
-          else tma_load_2d(dst, ma, &full[s], pl * K + k0, tile_id * TC_BM);
-          tma_load_2d(sa + (NP + pl) * TC_TILE_BYTES, mw, &full[s], pl * K + k0, n0);
-        }
+    // ===== TMA producer: lanes 0 .. 2 NP - 1 each issue ONE box per K block =====
+    // (a TMA issue costs ~400 cycles of the issuing thread whatever the box size -- six of them from one thread were
+    // 2.4 k cycles per K block against 1.5 k cycles of MMAs)
+    constexpr int NP = SPLIT ? 3 : 1;
+    for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+      __syncwarp();
+      const bool ph2 = kb >= nkb1;
+      const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
+      const int K = ph2 ? p.K2 : p.K1;
+      const CUtensorMap* ma = ph2 ? &tmA2 : &tmA1;
+      const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
+      // SPLIT: planes 0..2 of the activation, then planes 0..2 of the weights (plane p = columns [p K, (p + 1) K);
+      // a box that runs past its plane / the tensor reads the next plane / zeros, which no MMA consumes)
+      if (lane < NP) {
+        uint8_t* dst = sa + lane * TC_TILE_BYTES;
+        if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(dst, ma, &full[s], lane * K + k0, t0, b);
+        else tma_load_2d(dst, ma, &full[s], lane * K + k0, tile_id * TC_BM);
+      } else if (lane < 2 * NP) {
+        const int pl = lane - NP;
+        tma_load_2d(sa + (NP + pl) * TC_TILE_BYTES, mw, &full[s], pl * K + k0, n0);
       }
     }
     __syncwarp();
@@ -461,7 +465,11 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   if (a.split) {
     FTN_REQUIRE(a.ldo % 3 == 0 || a.epi == TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold three planes", a.ldo);
     const int nkb = (a.K1 + TC_BK - 1) / TC_BK + (a.K2 + TC_BK - 1) / TC_BK;
-    if (nkb <= 2) {
+    static const bool two_stage = getenv("FLOWTIMES_SPLIT_2STAGE") != nullptr;   // A/B switch for profiling
+    (void)nkb;
+    // ONE 96 KB stage per CTA and two CTAs per SM: while one CTA's MMAs run the other loads its K block or drains its
+    // accumulator (a 2-stage CTA owns the SM alone and its prologue and epilogue leave the tensor pipe idle)
+    if (!two_stage) {
       constexpr int smem1 = TC_SPLIT_STAGE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
       FTN_DYN_SMEM((tc_gemm_kernel<true, 1>), smem1);
       tc_gemm_kernel<true, 1><<<grid, 256, smem1, st>>>(mA1, mW1, mA2, mW2, k);

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -76,7 +76,11 @@ SIGNATURES = {
     "ftn_spectrum_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ftn_spectrum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "ftn_peer_create": (_I, [_I, _I, C.POINTER(_P), C.c_char_p]),
+    "ftn_peer_connect": (_I, [_P, C.c_char_p]),
+    "ftn_peer_allreduce": (_I, [_P, _P, _I, _P]),
+    "ftn_peer_destroy": (_I, [_P]),
     "ftn_plan_build_host": (_I, [C.POINTER(_I64), _I, _I, _I, _I, C.POINTER(FtnPeriodPlan)]),
     "ftn_group_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
@@ -89,7 +93,7 @@ SIGNATURES = {
                                   C.POINTER(FtnInceptionWeights), _I, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "ftn_timesblock_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ,
                                     C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights), _I, _P, _P, _F, _P, _P,
-                                    _SZ, _P]),
+                                    _SZ, _P, _P]),
     "ftn_inception_block_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights)]),
     "ftn_inception_block": (_I, [_P, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights), _I, _I, _P, _P, _SZ, _P]),
     "ftn_conv2d_grid": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
@@ -205,8 +209,46 @@ def spectrum(x: torch.Tensor):
     return med, ssum
 
 
-def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int):
-    """Single-rank fused search: x[B,L,C] -> (plan, amps[B,k], weights[B,16], amp_median[B,F], amp_sum[F+1])."""
+PEER_HANDLE_BYTES = 64
+
+
+class PeerComm:
+    """NVLink peer mailbox of one rank (csrc/peer.cuh): the path's one collective -- the sum of L/2 + 2 floats over the
+    ranks -- done inside the selection kernel with plain stores / loads to peer memory instead of an NCCL all-reduce.
+    ``PeerComm(rank, world, gather)``: ``gather(bytes) -> list of every rank's bytes`` exchanges the CUDA IPC handles
+    (torch.distributed, any backend)."""
+
+    def __init__(self, rank: int, world: int, gather):
+        lib = load()
+        self.rank, self.world = int(rank), int(world)
+        self._handle = C.c_void_p()
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _check(lib.ftn_peer_create(self.rank, self.world, C.byref(self._handle), buf), "ftn_peer_create")
+        handles = gather(bytes(buf.raw))
+        if len(handles) != self.world or any(len(h) != PEER_HANDLE_BYTES for h in handles):
+            raise RuntimeError("PeerComm: the handle exchange did not return one 64-byte handle per rank")
+        _check(lib.ftn_peer_connect(self._handle, b"".join(handles)), "ftn_peer_connect")
+
+    @property
+    def ptr(self) -> int:
+        return self._handle.value
+
+    def all_reduce(self, vals: torch.Tensor) -> torch.Tensor:
+        """In place: vals (fp32, <= 1024 elements) <- sum over ranks in rank order.  Every rank must call."""
+        if vals.dtype != torch.float32 or not vals.is_cuda or not vals.is_contiguous():
+            raise TypeError("PeerComm.all_reduce takes a contiguous fp32 CUDA tensor")
+        _check(load().ftn_peer_allreduce(self._handle, vals.data_ptr(), vals.numel(), _stream()), "ftn_peer_allreduce")
+        return vals
+
+    def close(self) -> None:
+        if self._handle:
+            load().ftn_peer_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+
+def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int, comm: Optional["PeerComm"] = None):
+    """Fused search: x[B,L,C] -> (plan, amps[B,k], weights[B,16], amp_median[B,F], amp_sum[F+1]).  With ``comm`` the
+    batch is sharded over the communicator's ranks and the partial sums are exchanged inside the selection kernel."""
     lib = load()
     B, L, Cc = x.shape
     Fq = L // 2 + 1
@@ -219,7 +261,7 @@ def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     _check(lib.ftn_period_search(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
                                  ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), ws.data_ptr(),
-                                 nbytes, _stream()), "ftn_period_search")
+                                 nbytes, None if comm is None else comm.ptr, _stream()), "ftn_period_search")
     return plan, amps, weights, med, ssum
 
 
@@ -306,7 +348,7 @@ def timesblock_fused(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, w
 
 def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: FtnInceptionWeights,
                        wb: FtnInceptionWeights, act: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
-                       eps: float):
+                       eps: float, comm: Optional["PeerComm"] = None):
     """Period search + fused TimesBlock in one call (the first 1x1 stage overlaps the search).
 
     Returns None when the configuration is not eligible (nothing was enqueued), else
@@ -327,7 +369,7 @@ def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: 
     rc = lib.ftn_timesblock_forward(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
                                     ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), sws.data_ptr(),
                                     sbytes, C.byref(wa), C.byref(wb), act, _ptr(ln_w), _ptr(ln_b), float(eps),
-                                    out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+                                    out.data_ptr(), ws.data_ptr(), nbytes, None if comm is None else comm.ptr, _stream())
     if rc == -1:
         return None
     _check(rc, "ftn_timesblock_forward")

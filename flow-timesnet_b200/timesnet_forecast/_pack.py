@@ -101,9 +101,9 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
             if mid == 32 and kh % 2 == 1 and kw % 2 == 1:
                 st.w_kk_phase[j] = dev16(_phase_stage_images(wk))
             if tc_ok and kh % 2 == 1 and kw % 2 == 1:
-                img3 = _tap_images(wk)                                       # [tap][3][mid/8][mid][8] bf16
+                img3 = _tap_images(wk)                                       # [tap][mid/8][3][mid][8] bf16
                 st.w_kk_img3[j] = dev_planes(img3)
-                st.w_kk_img[j] = dev_planes(img3[:, 0])
+                st.w_kk_img[j] = dev_planes(img3[:, :, 0])
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
@@ -185,11 +185,12 @@ def split3(t: torch.Tensor):
 def _tap_images(wk: torch.Tensor) -> torch.Tensor:
     """Per-tap weight images of the streaming k x k kernel (tc_convs.cu; layout in include/flowtimes.h).
 
-    wk: [mid out, mid in, kh, kw] -> bf16 [kh*kw][3 planes][mid/8 chunks][mid out][8 in]."""
+    wk: [mid out, mid in, kh, kw] -> bf16 [kh*kw][mid/8 chunks][3 planes][mid out][8 in]: per 8-channel chunk the
+    three weight planes are consecutive row blocks, i.e. ONE K-major operand with N = 3 mid rows."""
     n_out, n_in, kh, kw = (int(v) for v in wk.shape)
     planes = torch.stack(split3(wk), dim=0)                                  # [3][out][in][kh][kw]
     img = planes.permute(3, 4, 0, 2, 1).reshape(kh * kw, 3, n_in // 8, 8, n_out)   # [tap][plane][chunk][8 in][out]
-    return img.permute(0, 1, 2, 4, 3).contiguous()                           # [tap][plane][chunk][out][8 in]
+    return img.permute(0, 2, 1, 4, 3).contiguous()                           # [tap][chunk][plane][out][8 in]
 
 
 def _phase_stage_images(wk: torch.Tensor) -> torch.Tensor:

@@ -114,6 +114,7 @@ class FFTPeriodSelector(nn.Module):
         self.pmax = int(max(1, pmax))
         self.min_period_threshold = int(min(self.pmax, int(max(1, min_period_threshold))))
         self.process_group = False         # False = rank-local (reference behaviour); None / a group = shared search
+        self.peer_comm = None              # nv.PeerComm: exchange over NVLink peer memory inside the selection kernel
         self._last_plan: Optional[PeriodPlan] = None
         self._empty_device = torch.device("cpu")
 
@@ -153,11 +154,16 @@ class FFTPeriodSelector(nn.Module):
         group, world = self._world()
         if B <= 0:
             if world > 1:                                            # an empty shard still enters the collective
-                reduce_spectrum_sum(torch.zeros(nbins + 1, dtype=torch.float32, device=x.device), self.process_group)
+                zeros = torch.zeros(nbins + 1, dtype=torch.float32, device=x.device)
+                if self.peer_comm is not None:
+                    self.peer_comm.all_reduce(zeros)
+                else:
+                    reduce_spectrum_sum(zeros, self.process_group)
             return None                                              # timesnet.py:89-90
         x = nv.require_cuda(x, "x")
-        if world == 1:                                                 # nothing to reduce: fused 3-launch search
-            plan_dev, amps, weights, _, _ = nv.period_search(x, k, self.pmax, self.min_period_threshold)
+        if world == 1 or self.peer_comm is not None:                   # fused 2-launch search (peer exchange in-kernel)
+            plan_dev, amps, weights, _, _ = nv.period_search(x, k, self.pmax, self.min_period_threshold,
+                                                             self.peer_comm if world > 1 else None)
             self._last_plan = PeriodPlan(plan_dev, amps, weights, k)
             return self._last_plan
         med, ssum = nv.spectrum(x)                                     # ssum = [sum_b median spectrum | B]
@@ -669,14 +675,17 @@ class TimesBlock(nn.Module):
         if sel.k <= 0 or L <= 1 or x.dtype != torch.bfloat16:
             return None
         k = min(sel.k, L // 2)                                       # timesnet.py:122-126 (nbins - 1)
-        if k <= 0 or k > nv.FTN_MAX_K or sel._world()[1] != 1:
+        if k <= 0 or k > nv.FTN_MAX_K:
+            return None
+        world = sel._world()[1]
+        if world != 1 and sel.peer_comm is None:                     # NCCL transport: search and block stay separate calls
             return None
         if self.inception[0].proj.weight.device != x.device:
             self.inception = self.inception.to(x.device)
         pa = self.inception[0].packed(x.device)
         pb = self.inception[2].packed(x.device)
         res = nv.timesblock_forward(x, k, sel.pmax, sel.min_period_threshold, pa.struct, pb.struct,
-                                    _act_code(self._activation_name), ln_w, ln_b, eps)
+                                    _act_code(self._activation_name), ln_w, ln_b, eps, sel.peer_comm if world > 1 else None)
         if res is None:
             return None
         out, plan_dev, amps, weights = res

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 10
+#define FTN_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -116,8 +116,9 @@ typedef struct FtnInceptionWeights {
    * other rows are zero.  NULL = that kernel is not used for this block. */
   const void* w_kk_phase[FTN_MAX_BRANCH];
   /* Streaming k x k kernel (tc_convs.cu, any mid % 16 == 0): per branch one bf16 image per tap in the un-swizzled
-   * K-major operand layout, [tap][plane][mid / 8 chunks][mid out channels][8 in channels]; w_kk_img has one plane
-   * (bf16 activations), w_kk_img3 three (hi / mid / lo split of the fp32 weights, see below).  NULL = not packed. */
+   * K-major operand layout, [tap][mid / 8 chunks][plane][mid out channels][8 in channels]; w_kk_img has one plane
+   * (bf16 activations), w_kk_img3 three (hi / mid / lo split of the fp32 weights, see below: side by side they are
+   * ONE operand with N = 3 mid rows).  NULL = not packed. */
   const void* w_kk_img[FTN_MAX_BRANCH];
   const void* w_kk_img3[FTN_MAX_BRANCH];
   /* fp32 activations on the tensor cores: every fp32 value v is carried as three bf16 planes hi = bf16(v),
@@ -168,12 +169,14 @@ FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, in
                        int global_batch, int L, int k, int pmax, int min_period,
                        FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/, void* stream);
 
-/* Single-rank fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the
- * selection kernel (3 launches instead of 5; nothing to all-reduce).  Same outputs as the pair:
- * amp_median [B][F], amp_sum [F+1], plan, amps [B][k], weights [B][FTN_MAX_K]. */
+/* Fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the selection kernel (2 launches).
+ * Same outputs as the pair: amp_median [B][F], amp_sum [F+1], plan, amps [B][k], weights [B][FTN_MAX_K].
+ * peer_comm = NULL: single rank, nothing to reduce.  peer_comm = a communicator from ftn_peer_create / _connect: the
+ * batch is sharded over its ranks and the selection kernel exchanges the F + 1 partial sums with the peers over NVLink
+ * peer memory (see "NVLink peer mailbox" below) -- every rank must make the call. */
 FTN_API int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                       float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      void* workspace, size_t workspace_bytes, void* peer_comm, void* stream);
 
 /* HOST helper (no CUDA): group an externally supplied candidate list (a custom
  * period_selector module) with the default exact-duplicate rules and fill a
@@ -251,7 +254,8 @@ FTN_API int ftn_timesblock_forward(const void* x, int dtype, int B, int L, int C
                                    float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
                                    void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
                                    const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
-                                   float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* stream);
+                                   float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* peer_comm,
+                                   void* stream);
 /* ---- K4: weighted aggregation + residual (+ shared LayerNorm) ------------
  * out = x + sum_g w[b][g] * delta_g          replaces timesnet.py:1075-1099, :818
  * with ln_weight != NULL additionally        replaces timesnet.py:2059-2061
@@ -308,6 +312,19 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
  * mask: NULL or uint8 [count]; partial: >= 2*1024 floats scratch; out: 1 float. */
 FTN_API int ftn_nb_nll(const float* y, const float* rate, const float* disp, const uint8_t* mask,
                int64_t count, float eps, float* partial, float* out, void* stream);
+
+/* ---- NVLink peer mailbox: the path's one collective without NCCL --------------
+ * replaces the all-reduce of amp_channel_median.mean(dim=0) a sharded batch needs (timesnet.py:112).
+ * One process per GPU.  Every rank: ftn_peer_create (allocates its mailbox with cudaMalloc -- the one allocation the
+ * library makes, at init -- and exports a CUDA IPC handle), the caller all-gathers the FTN_PEER_HANDLE_BYTES-byte
+ * handles (torch.distributed, any backend), ftn_peer_connect maps the peers' mailboxes.  ftn_period_search /
+ * ftn_timesblock_forward then take the communicator; ftn_peer_allreduce is the same one-CTA exchange on its own:
+ * vals[0..n) <- sum over ranks added in RANK ORDER (bit-identical on every rank), n <= 1024.  All ranks must call. */
+#define FTN_PEER_HANDLE_BYTES 64
+FTN_API int ftn_peer_create(int rank, int world, void** comm_out, unsigned char* handle_out);
+FTN_API int ftn_peer_connect(void* comm, const unsigned char* all_handles /*[world][FTN_PEER_HANDLE_BYTES]*/);
+FTN_API int ftn_peer_allreduce(void* comm, float* vals, int n, void* stream);
+FTN_API int ftn_peer_destroy(void* comm);
 
 /* ---- rolling one-step forecast, device resident ----------------------------
  * replaces the tail of the loop body of forecast_recursive_batch (predict.py:333-341):

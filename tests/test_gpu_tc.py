@@ -148,5 +148,5 @@ def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
             out = got[row:row + Lp, j * mid:(j + 1) * mid].double()
             err = (out - ref).abs().max().item() / ref.abs().max().item()
             worst = max(worst, err)
-            assert err < (1e-2 if planes == 1 else 1e-5), f"group {gi} (p={per}) branch {j}: rel err {err:.3e}"
+            assert err < (1e-2 if planes == 1 else 3e-5), f"group {gi} (p={per}) branch {j}: rel err {err:.3e}"
     assert worst > 0.0
