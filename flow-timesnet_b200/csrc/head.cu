@@ -6,6 +6,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace ftn {
 
@@ -450,4 +451,81 @@ extern "C" int ftn_recursive_advance(float* window, const float* rate, const flo
   recursive_bump_kernel<<<1, 1, 0, st>>>(step_counter);
   FTN_LAUNCH_CHECK("recursive_bump_kernel");
   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// The dense layers either side of the stack on the tensor cores (three-plane fp32 GEMM, tc_gemm.cu), with their
+// elementwise tails fused into the GEMM epilogue:
+//   ftn_embed_tc   : K0 = DataEmbedding (timesnet.py:1295-1312): value GEMM + bias + gate * LN(aux) + cast, one kernel
+//                    after the split of x (the fp32 SIMT pair was sgemm + embed_combine, 62 + 9 us at the elec shape)
+//   ftn_nb_head_tc : mu_head and sigma_head as ONE GEMM over [Wmu; Wsg] with the softplus / floor / finite-check
+//                    epilogue (:2079-2097); the time projection stays the fp32 SIMT GEMM (its operand is MN-major)
+// Both return -1 (nothing enqueued) when the shape is not eligible; the caller then uses the SIMT entry points.
+// ---------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" size_t ftn_embed_tc_workspace_bytes(long long rows, int N) {
+  return (size_t)rows * 3 * round_up(N > 0 ? N : 1, 16) * 2 + 256;
+}
+
+extern "C" int ftn_embed_tc(const float* x, long long rows, int L, int N, const void* w_s3, const float* bias,
+                            const float* aux, int aux_batched, const float* gate, int C, int dtype_out, void* out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(x && w_s3 && bias && aux && gate && out && workspace, "ftn_embed_tc: null pointer");
+  FTN_REQUIRE(dtype_out == FTN_F32 || dtype_out == FTN_BF16, "ftn_embed_tc: unsupported dtype %d", dtype_out);
+  FTN_REQUIRE(rows > 0 && L > 0 && N > 0 && C > 0, "ftn_embed_tc: bad sizes");
+  if (C % 16 || N < 16) return -1;                      // tile granularity; a handful of series is cheaper on SIMT
+  const int Kp = round_up(N, 16);
+  FTN_REQUIRE(workspace_bytes >= ftn_embed_tc_workspace_bytes(rows, N), "ftn_embed_tc: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(workspace);
+  if (int rc = split3_pad_launch(x, rows, N, Kp, xs, st)) return rc;
+  TcGemmArgs g{};
+  g.plan = nullptr; g.B = 1; g.L = (int)(rows < 0x7fffffff ? rows : 0x7fffffff); g.max_groups = 1;
+  g.n_tiles = (int)((rows + 127) / 128); g.split = 1;
+  g.a1 = xs; g.a1_seq = 0; g.a1_ld = 3 * Kp; g.a1_rows = rows;
+  g.w1 = (const __nv_bfloat16*)w_s3; g.bias1 = bias; g.K1 = Kp; g.K2 = 0; g.N = C; g.act = 0;
+  g.epi = TC_EPI_EMBED; g.res = TC_RES_NONE; g.out = out; g.ldo = 8;
+  g.rows_valid = rows; g.aux = aux; g.aux_rows = aux_batched ? 0 : L; g.gate = gate; g.out_bf16 = dtype_out == FTN_BF16;
+  return tc_gemm_launch(g, st);
+}
+
+extern "C" size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C) {
+  return (size_t)B * steps * C * 4 + 256 + (size_t)B * steps * 3 * C * 2 + 256;
+}
+
+extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
+                              const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
+                              const float* late, const float* late_gate, const float* floor_n, float* rate, float* disp,
+                              int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
+  FTN_REQUIRE(seq && Wt && bt && w_heads_s3 && b_heads && hist && floor_n && rate && disp && flags && workspace,
+              "ftn_nb_head_tc: null pointer");
+  FTN_REQUIRE((late == nullptr) == (late_gate == nullptr), "ftn_nb_head_tc: late and late_gate must come together");
+  FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_nb_head_tc: unsupported dtype %d", dtype);
+  FTN_REQUIRE(B > 0 && L > 0 && C > 0 && steps > 0 && N > 0, "ftn_nb_head_tc: bad sizes");
+  if (C % 16 || N < 16) return -1;
+  FTN_REQUIRE(Np >= N && Np % 128 == 0, "ftn_nb_head_tc: Np=%d must be a multiple of 128 and >= N=%d", Np, N);
+  FTN_REQUIRE(workspace_bytes >= ftn_nb_head_tc_workspace_bytes(B, steps, C), "ftn_nb_head_tc: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* hidden = reinterpret_cast<float*>(workspace);
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) +
+                                                     (((size_t)B * steps * C * 4 + 255) & ~size_t(255)));
+  // hidden[b] (steps x C) = Wt (steps x L) . seq[b] (L x C) + bt[h]       (forecast_time_proj, :2071)
+  if (dtype == FTN_F32)
+    sgemm_launch<float, false>(Wt, L, 0, (const float*)seq, C, (long long)L * C, hidden, C, (long long)steps * C, steps, C, L, B,
+                               bt, 2, st);
+  else
+    sgemm_launch<__nv_bfloat16, false>(Wt, L, 0, (const __nv_bfloat16*)seq, C, (long long)L * C, hidden, C,
+                                       (long long)steps * C, steps, C, L, B, bt, 2, st);
+  FTN_LAUNCH_CHECK("sgemm_kernel(time_proj)");
+  const long long rows = (long long)B * steps;
+  if (int rc = split3_launch(hidden, rows, C, hs, st, true)) return rc;
+  TcGemmArgs g{};
+  g.plan = nullptr; g.B = 1; g.L = (int)rows; g.max_groups = 1; g.n_tiles = (int)((rows + 127) / 128); g.split = 1;
+  g.a1 = hs; g.a1_seq = 0; g.a1_ld = 3 * C; g.a1_rows = rows;
+  g.w1 = (const __nv_bfloat16*)w_heads_s3; g.bias1 = b_heads; g.K1 = C; g.K2 = 0; g.N = 2 * Np; g.act = 0;
+  g.epi = TC_EPI_NBHEAD; g.res = TC_RES_NONE; g.out = rate; g.ldo = 8;
+  g.rows_valid = rows; g.gate = late_gate; g.head_n = N; g.head_np = Np; g.head_steps = steps;
+  g.hist = hist; g.late = late; g.floor_n = floor_n; g.disp = disp; g.flags = flags;
+  return tc_gemm_launch(g, st);
 }

@@ -52,7 +52,16 @@ struct TcGemmKernelArgs {
   int ldo;
   const void* x;           // DELTA: grid to subtract (SPLIT: fp32)
   int C;
+  long long rows_valid;
+  const float* aux; int aux_rows;
+  const float* gate;
+  int out_bf16;
+  int head_n, head_np, head_steps;
+  const float* hist; const float* late; const float* floor_n; float* disp; int32_t* flags;
 };
+
+// F.softplus(beta = 1, threshold = 20) in fp32 device math (timesnet.py:2081-2091)
+__device__ __forceinline__ float softplus20f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
 
 // exact-erf GELU for the fp32 (SPLIT) epilogues: gelu_fast's A&S 7.1.26 erf is within 1.5e-7 absolute
 __device__ __forceinline__ float act_split(float v, int act) { return act == FTN_ACT_RELU ? fmaxf(v, 0.f) : gelu_fast(v); }
@@ -222,7 +231,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const size_t pos_row = (size_t)tile_id * TC_BM + r;
   const bool row_live = t < Lp;  // rows past the image are never consumed; still written for PLAIN/BLOCK_A
   const bool delta_row = p.epi == TC_EPI_DELTA && t < p.L && row_live;
-  if (SPLIT) {
+  if (SPLIT && p.epi == TC_EPI_EMBED) {
+    // DataEmbedding epilogue (timesnet.py:1295-1312): value + gate * LN(aux), cast to the stack dtype
+    const bool live = (long long)pos_row < p.rows_valid;
+    const size_t arow = p.aux_rows ? pos_row % (size_t)p.aux_rows : pos_row;
+    for (int c = half * 16; c < n_tile; c += 32) {
+      uint32_t vr[16];
+      tmem_ld16_nowait(trow + c, vr);
+      tmem_ld_wait();
+      if (!live) continue;
+      const int n = n0 + c;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        v[i] = __uint_as_float(vr[i]) + s_bias1[c + i] + __ldg(p.gate + n + i) * __ldg(p.aux + arow * p.N + n + i);
+      if (p.out_bf16) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.N + n);
+        dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+      } else {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pos_row * p.N + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  } else if (SPLIT && p.epi == TC_EPI_NBHEAD) {
+    // NB head epilogue (timesnet.py:2079-2097): the N-tiles below head_np hold mu_head, the rest sigma_head
+    const bool live = (long long)pos_row < p.rows_valid;
+    const bool is_rate = n0 < p.head_np;
+    const int h = (int)(pos_row % (size_t)p.head_steps);
+    const size_t bwin = pos_row / (size_t)p.head_steps;
+    int bad = 0;
+    for (int c = half * 16; c < n_tile; c += 32) {
+      uint32_t vr[16];
+      tmem_ld16_nowait(trow + c, vr);
+      tmem_ld_wait();
+      if (!live) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = (is_rate ? n0 : n0 - p.head_np) + c + i;
+        if (n >= p.head_n) continue;
+        const float a = __uint_as_float(vr[i]) + s_bias1[c + i];
+        const size_t o = pos_row * p.head_n + n;
+        if (is_rate) {
+          float pre = a + __ldg(p.hist + o);                                          // mu_head(h) + history_tail (:2079)
+          if (p.late) pre += __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h);   // (:2041-2047)
+          const float rt = softplus20f(pre) + 1e-6f;                                   // :2081-2085
+          reinterpret_cast<float*>(p.out)[o] = rt;
+          if (!isfinite(rt) || rt <= 0.f) bad |= 1;                                    // :2094
+        } else {
+          const float d = softplus20f(a) + __ldg(p.floor_n + n) + 1e-6f;               // :2088-2093
+          p.disp[o] = d;
+          if (!isfinite(d) || d <= 0.f) bad |= 2;                                      // :2096
+        }
+      }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && lane == 0) atomicOr(p.flags, bad);
+  } else if (SPLIT) {
     const float* resf = reinterpret_cast<const float*>(p.res_ptr);
     const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(p.res_ptr);
     const float* xf = reinterpret_cast<const float*>(p.x);
@@ -424,6 +490,36 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
   }
 }
 
+// same for any C: out [rows][3 Kp], columns c >= C of every plane are zero (K padding of the row GEMMs)
+__global__ void __launch_bounds__(256) split3_pad_kernel(const float* __restrict__ x, long long rows, int C, int Kp,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const long long total = rows * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Kp;
+    const int c = (int)(i - r * Kp);
+    const float v = c < C ? x[r * C + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    __nv_bfloat16* dst = out + r * 3 * Kp + c;
+    dst[0] = h;
+    dst[Kp] = m;
+    dst[2 * Kp] = l;
+  }
+}
+
+int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st) {
+  FTN_REQUIRE(Kp >= C && Kp % 16 == 0, "split3_pad: Kp=%d must be a multiple of 16 and >= C=%d", Kp, C);
+  const long long total = rows * Kp;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+  split3_pad_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, C, Kp, out);
+  FTN_LAUNCH_CHECK("split3_pad_kernel");
+  return 0;
+}
+
 int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call) {
   FTN_REQUIRE(C % 8 == 0, "split3: C=%d must be a multiple of 8", C);
   const long long total = rows * (C / 8);
@@ -460,10 +556,14 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.a1_seq = a.a1_seq; k.a2_seq = a.a2_seq; k.K1 = a.K1; k.K2 = a.K2; k.N = a.N; k.act = a.act; k.epi = a.epi;
   k.res = a.res; k.bias1 = a.bias1; k.bias2 = a.bias2; k.res_ptr = a.res_ptr; k.res_ld = a.res_ld;
   k.out = a.out; k.ldo = a.ldo; k.x = a.x; k.C = a.C;
+  k.rows_valid = a.rows_valid; k.aux = a.aux; k.aux_rows = a.aux_rows; k.gate = a.gate; k.out_bf16 = a.out_bf16;
+  k.head_n = a.head_n; k.head_np = a.head_np; k.head_steps = a.head_steps; k.hist = a.hist; k.late = a.late;
+  k.floor_n = a.floor_n; k.disp = a.disp; k.flags = a.flags;
+  FTN_REQUIRE(a.epi < TC_EPI_EMBED || (a.split && !a.plan && a.K2 == 0), "tc_gemm: the row-GEMM epilogues need split mode and no plan");
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
   if (a.split) {
-    FTN_REQUIRE(a.ldo % 3 == 0 || a.epi == TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold three planes", a.ldo);
+    FTN_REQUIRE(a.ldo % 3 == 0 || a.epi >= TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold three planes", a.ldo);
     const int nkb = (a.K1 + TC_BK - 1) / TC_BK + (a.K2 + TC_BK - 1) / TC_BK;
     static const bool two_stage = getenv("FLOWTIMES_SPLIT_2STAGE") != nullptr;   // A/B switch for profiling
     (void)nkb;

@@ -7,7 +7,10 @@
 
 namespace ftn {
 
-enum TcEpi { TC_EPI_PLAIN = 0, TC_EPI_BLOCK_A = 1, TC_EPI_DELTA = 2 };
+enum TcEpi { TC_EPI_PLAIN = 0, TC_EPI_BLOCK_A = 1, TC_EPI_DELTA = 2,
+             // split mode only, plain row GEMMs (plan == nullptr) of the callers either side of the stack:
+             TC_EPI_EMBED = 3,    // out[row][n] = acc + bias1[n] + gate[n] * aux[(row % aux_rows | row)][n]  -> fp32 / bf16 [rows][N]
+             TC_EPI_NBHEAD = 4 }; // columns < head_np: rate = softplus(acc + bias + hist + gate * late) + 1e-6; the rest: dispersion
 enum TcRes { TC_RES_NONE = 0, TC_RES_ACC2 = 1, TC_RES_SEQ = 2, TC_RES_POS = 3 };
 
 // One fused 1x1-conv stage on the tensor cores:
@@ -37,7 +40,16 @@ struct TcGemmArgs {
   // split != 0: fp32 activations as three bf16 planes (tc_gemm.cu).  a1 / a2 / w1 / w2 / out then are [rows][3 K] /
   // [rows][3 N] (a*_ld, ldo count ALL planes), x and a TC_RES_SEQ residual are the fp32 block input, a DELTA out is fp32.
   int split;
+  // TC_EPI_EMBED / TC_EPI_NBHEAD (see tc_gemm.cu): rows_valid = rows of the GEMM that exist (the last tile is ragged)
+  long long rows_valid;
+  const float* aux; int aux_rows;             // EMBED: aux[(aux_rows ? row % aux_rows : row)][N]
+  const float* gate;                          // EMBED: per-column gate; NBHEAD: late-bias gate per step (may be null)
+  int out_bf16;                               // EMBED: output dtype
+  int head_n, head_np, head_steps;            // NBHEAD: series count N, padded column block, steps per window
+  const float* hist; const float* late; const float* floor_n; float* disp; int32_t* flags;
 };
+// fp32 [rows][C] -> three bf16 planes [rows][3 Kp], Kp >= C a multiple of 16 (columns >= C are zero)
+int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st);
 // fp32 [rows][C] -> three bf16 planes [rows][3 C] (tc_gemm.cu)
 int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call);
 

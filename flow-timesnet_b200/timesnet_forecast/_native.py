@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 13
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -105,6 +105,14 @@ SIGNATURES = {
     "ftn_layer_norm": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ftn_embed_combine": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ftn_nb_head": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ftn_nb_nll_backward": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P, _P, _P]),
+    "ftn_nb_head_epilogue_backward": (_I, [_P, _P, _P, _P, _P, _I64, _I, _P, _P, _P]),
+    "ftn_layer_norm_backward": (_I, [_P, _P, _P, _I64, _I, _F, _P, _P, _P, _P]),
+    "ftn_gemm_f32": (_I, [_P, _I, _I64, _I, _P, _I, _I64, _I, _P, _I, _I64, _I, _I, _I, _I, _I, _P]),
+    "ftn_embed_tc_workspace_bytes": (_SZ, [C.c_longlong, _I]),
+    "ftn_embed_tc": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
+    "ftn_nb_head_tc_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ftn_nb_head_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ftn_nb_nll": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P]),
 }
 
@@ -509,6 +517,42 @@ def embed_combine(value, aux, gate, aux_batched: bool, out_dtype: torch.dtype) -
     return out
 
 
+def embed_tc(x: torch.Tensor, w_s3: torch.Tensor, bias: torch.Tensor, aux: torch.Tensor, aux_batched: bool,
+             gate: torch.Tensor, out_dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """DataEmbedding on the tensor cores (value GEMM + combine in one kernel).  None = shape not eligible."""
+    lib = load()
+    B, L, N = x.shape
+    Cc = w_s3.shape[0]
+    rows = B * L
+    out = torch.empty(B, L, Cc, dtype=out_dtype, device=x.device)
+    nbytes = lib.ftn_embed_tc_workspace_bytes(rows, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    rc = lib.ftn_embed_tc(x.data_ptr(), rows, L, N, w_s3.data_ptr(), bias.data_ptr(), aux.data_ptr(), int(aux_batched),
+                          gate.data_ptr(), Cc, dtype_code(out_dtype), out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    if rc == -1:
+        return None
+    _check(rc, "ftn_embed_tc")
+    return out
+
+
+def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_gate, floor_n, flags):
+    """NB head with the mu / sigma heads as one tensor-core GEMM.  None = shape not eligible."""
+    lib = load()
+    B, L, Cc = seq.shape
+    rate = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
+    disp = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
+    nbytes = lib.ftn_nb_head_tc_workspace_bytes(B, steps, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=seq.device)
+    rc = lib.ftn_nb_head_tc(seq.data_ptr(), dtype_code(seq.dtype), B, L, Cc, steps, N, Wt.data_ptr(), bt.data_ptr(),
+                            w_heads_s3.data_ptr(), b_heads.data_ptr(), Np, hist.data_ptr(), _ptr(late), _ptr(late_gate),
+                            floor_n.data_ptr(), rate.data_ptr(), disp.data_ptr(), flags.data_ptr(), ws.data_ptr(), nbytes,
+                            _stream())
+    if rc == -1:
+        return None
+    _check(rc, "ftn_nb_head_tc")
+    return rate, disp
+
+
 def nb_head(seq, steps, N, Wt, bt, Wmu, bmu, Wsg, bsg, hist, late, late_gate, floor_n, flags):
     B, L, Cc = seq.shape
     rate = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
@@ -526,4 +570,57 @@ def nb_nll(y, rate, disp, mask_u8, eps: float) -> torch.Tensor:
     partial = torch.empty(2 * 1024, dtype=torch.float32, device=y.device)
     _check(load().ftn_nb_nll(y.data_ptr(), rate.data_ptr(), disp.data_ptr(), _ptr(mask_u8), y.numel(), float(eps),
                              partial.data_ptr(), out.data_ptr(), _stream()), "ftn_nb_nll")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# backward, first slice
+# --------------------------------------------------------------------------- #
+def nb_nll_backward(y, rate, disp, mask_u8, eps: float, grad_out: torch.Tensor):
+    d_rate = torch.empty_like(rate)
+    d_disp = torch.empty_like(disp)
+    scratch = torch.empty(1, dtype=torch.float32, device=y.device)
+    go = grad_out.detach().to(device=y.device, dtype=torch.float32).reshape(1).contiguous()
+    _check(load().ftn_nb_nll_backward(y.data_ptr(), rate.data_ptr(), disp.data_ptr(), _ptr(mask_u8), y.numel(), float(eps),
+                                      go.data_ptr(), scratch.data_ptr(), d_rate.data_ptr(), d_disp.data_ptr(), _stream()),
+           "ftn_nb_nll_backward")
+    return d_rate, d_disp
+
+
+def nb_head_epilogue_backward(rate, disp, floor_n, d_rate, d_disp):
+    N = rate.shape[-1]
+    rows = rate.numel() // N
+    dpr = torch.empty_like(rate)
+    dpd = torch.empty_like(disp)
+    _check(load().ftn_nb_head_epilogue_backward(rate.data_ptr(), disp.data_ptr(), floor_n.data_ptr(), d_rate.data_ptr(),
+                                                d_disp.data_ptr(), rows, N, dpr.data_ptr(), dpd.data_ptr(), _stream()),
+           "ftn_nb_head_epilogue_backward")
+    return dpr, dpd
+
+
+def layer_norm_backward(x, dy, w, eps: float):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dw = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    _check(load().ftn_layer_norm_backward(x.data_ptr(), dy.data_ptr(), w.data_ptr(), rows, Cc, float(eps), dx.data_ptr(),
+                                          dw.data_ptr(), db.data_ptr(), _stream()), "ftn_layer_norm_backward")
+    return dx, dw, db
+
+
+def gemm_f32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+    """op(a) @ op(b) for contiguous fp32 matrices ``[.., r, c]`` with an optional shared leading batch dim."""
+    batch = a.shape[0] if a.dim() == 3 else (b.shape[0] if b.dim() == 3 else 1)
+    ar, ac = a.shape[-2], a.shape[-1]
+    br, bc = b.shape[-2], b.shape[-1]
+    M, K = (ac, ar) if trans_a else (ar, ac)
+    K2, N = (bc, br) if trans_b else (br, bc)
+    if K != K2:
+        raise ValueError(f"gemm_f32: inner dimensions differ ({K} vs {K2})")
+    shape = (batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    _check(load().ftn_gemm_f32(a.data_ptr(), ac, ar * ac if a.dim() == 3 else 0, int(trans_a), b.data_ptr(), bc,
+                               br * bc if b.dim() == 3 else 0, int(trans_b), out.data_ptr(), N, M * N if len(shape) == 3 else 0,
+                               M, N, K, batch, 0, _stream()), "ftn_gemm_f32")
     return out

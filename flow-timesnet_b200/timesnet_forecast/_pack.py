@@ -211,3 +211,15 @@ def _phase_stage_images(wk: torch.Tensor) -> torch.Tensor:
 
 def params_fingerprint(module: nn.Module) -> Tuple:
     return tuple((p.data_ptr(), p._version, p.device.type) for p in module.parameters())
+
+
+def split_linear_weight(w: torch.Tensor, k_pad: int, rows_pad: int = 0, row_offset: int = 0) -> torch.Tensor:
+    """``nn.Linear`` weight ``[N, K]`` as the three-plane bf16 operand of the tensor-core row GEMMs: ``[rows][3 k_pad]``
+    (plane p at columns ``[p k_pad, (p + 1) k_pad)``, K zero-padded to ``k_pad``); with ``rows_pad`` the N rows are
+    placed at ``row_offset`` of a zero matrix with ``rows_pad`` rows."""
+    N, K = w.shape
+    rows = rows_pad if rows_pad > 0 else N
+    out = torch.zeros(rows, 3, k_pad, dtype=torch.bfloat16, device=w.device)
+    for p, plane in enumerate(split3(w.detach())):
+        out[row_offset:row_offset + N, p, :K] = plane
+    return out.reshape(rows, 3 * k_pad).contiguous()

@@ -2,7 +2,9 @@
 
 ``negative_binomial_nll`` runs as one fused elementwise + reduction pass in
 libflowtimes (lgamma / log1p in fp32 device math, deterministic two-level
-reduction).  Forward only.
+reduction).  When ``rate`` or ``dispersion`` require grad the call goes through
+``timesnet_forecast.autograd.nb_nll`` and is differentiable w.r.t. both
+(``ftn_nb_nll_backward``).
 """
 from __future__ import annotations
 
@@ -36,11 +38,15 @@ def negative_binomial_nll(y: torch.Tensor, rate: torch.Tensor, dispersion: torch
     nv.require_cuda(rate, "rate")
     if not (y.shape == rate.shape == dispersion.shape):
         y, rate, dispersion = torch.broadcast_tensors(y, rate, dispersion)
+    needs_grad = torch.is_grad_enabled() and (rate.requires_grad or dispersion.requires_grad)
     with torch.no_grad():
         yf = nv.require_cuda(y.to(device=rate.device), "y").to(torch.float32).contiguous()
-        rf = rate.detach().to(torch.float32).contiguous()
-        df = nv.require_cuda(dispersion, "dispersion").detach().to(torch.float32).contiguous()
         m8 = None
         if mask is not None:
             m8 = _expand_mask(mask.to(rate.device), yf).to(torch.uint8).contiguous()
-        return nv.nb_nll(yf, rf, df, m8, eps)
+        if not needs_grad:
+            rf = rate.detach().to(torch.float32).contiguous()
+            df = nv.require_cuda(dispersion, "dispersion").detach().to(torch.float32).contiguous()
+            return nv.nb_nll(yf, rf, df, m8, eps)
+    from .autograd import nb_nll as _nb_nll_grad
+    return _nb_nll_grad(yf, rate, nv.require_cuda(dispersion, "dispersion"), m8, eps)

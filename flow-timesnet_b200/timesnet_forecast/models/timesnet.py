@@ -41,7 +41,7 @@ import torch
 from torch import nn
 
 from .. import _native as nv
-from .._pack import PackedInception, pack_inception_block, params_fingerprint
+from .._pack import PackedInception, pack_inception_block, params_fingerprint, split_linear_weight
 from ..parallel import reduce_spectrum_sum, resolve_group
 
 __all__ = [
@@ -843,6 +843,16 @@ class DataEmbedding(nn.Module):
             self.register_parameter("gate", None)
         self.dropout = nn.Dropout(float(dropout))
         self._aux_cache = None
+        self._ve_cache = None
+
+    def _value_weight_split(self, device) -> torch.Tensor:
+        """value_embedding.weight as the three-plane bf16 operand of ``ftn_embed_tc`` (re-packed when it changes)."""
+        w = self.value_embedding.weight
+        key = (w.data_ptr(), w._version, str(device))
+        if self._ve_cache is None or self._ve_cache[0] != key:
+            kp = (w.shape[1] + 15) // 16 * 16
+            self._ve_cache = (key, split_linear_weight(w.detach().to(device=device, dtype=torch.float32), kp))
+        return self._ve_cache[1]
 
     def _aux_static(self, L: int, device: torch.device) -> torch.Tensor:
         norm_key = (None if self.aux_norm is None
@@ -882,8 +892,7 @@ class DataEmbedding(nn.Module):
         out_dtype = out_dtype or x.dtype
         with torch.no_grad():
             ve = self.value_embedding
-            value = nv.linear(x, ve.weight.detach().float().contiguous(), ve.bias.detach().float().contiguous())
-            d_model = value.shape[-1]
+            d_model = ve.out_features
             batched = self.temporal_embedding is not None and x_mark is not None
             if batched:
                 te = self.temporal_embedding
@@ -900,6 +909,19 @@ class DataEmbedding(nn.Module):
                 gate = self.gate.detach().float().reshape(-1).contiguous()
             else:
                 gate = torch.ones(d_model, dtype=torch.float32, device=dev)
+            fused_dtype = torch.float32 if self.embed_norm_mode in ("layer", "rms") else out_dtype
+            # K0: value GEMM on the tensor cores with the combine fused into its epilogue (None = shape not eligible)
+            out = nv.embed_tc(x.contiguous(), self._value_weight_split(dev), ve.bias.detach().float().contiguous(), aux,
+                              batched, gate, fused_dtype)
+            if out is not None:
+                if self.embed_norm_mode in ("layer", "rms"):
+                    norm_fn = nv.layer_norm if self.embed_norm_mode == "layer" else nv.rms_norm
+                    out = norm_fn(out, self.norm.weight.detach().float().contiguous(),
+                                  self.norm.bias.detach().float().contiguous(), self.norm.eps).to(out_dtype)
+                if shape4 is not None:
+                    return out.view(shape4[0], shape4[1], shape4[2], out.size(-1))
+                return out
+            value = nv.linear(x, ve.weight.detach().float().contiguous(), ve.bias.detach().float().contiguous())
             if self.embed_norm_mode in ("layer", "rms"):                       # timesnet.py:1313-1316
                 out = nv.embed_combine(value, aux, gate, batched, torch.float32)
                 norm_fn = nv.layer_norm if self.embed_norm_mode == "layer" else nv.rms_norm
@@ -1236,6 +1258,24 @@ class TimesNet(nn.Module):
     def _f32(t: torch.Tensor) -> torch.Tensor:
         return t.detach().to(torch.float32).contiguous()
 
+    def _heads_split(self, dev):
+        """[mu_head; sigma_head] as ONE three-plane bf16 operand of ``ftn_nb_head_tc`` (re-packed when a head changes):
+        rows [0, N) = mu_head.weight, rows [Np, Np + N) = sigma_head.weight, Np = N rounded up to 128."""
+        ps = (self.mu_head.weight, self.mu_head.bias, self.sigma_head.weight, self.sigma_head.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (str(dev),)
+        cache = getattr(self, "_heads_cache", None)
+        if cache is None or cache[0] != key:
+            N, Cc = self.mu_head.weight.shape
+            n_pad = (N + 127) // 128 * 128
+            f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
+            w = split_linear_weight(f32(self.mu_head.weight), Cc, 2 * n_pad, 0)
+            w += split_linear_weight(f32(self.sigma_head.weight), Cc, 2 * n_pad, n_pad)
+            b = torch.zeros(2 * n_pad, dtype=torch.float32, device=dev)
+            b[:N] = f32(self.mu_head.bias)
+            b[n_pad:n_pad + N] = f32(self.sigma_head.bias)
+            self._heads_cache = (key, w.contiguous(), b, n_pad)
+        return self._heads_cache[1], self._heads_cache[2], self._heads_cache[3]
+
     def _context(self, B: int, N: int, dev, series_static, series_ids) -> Optional[torch.Tensor]:
         """Static projection + id embedding + context LayerNorm (timesnet.py:1886-1957)."""
         comps = []
@@ -1373,9 +1413,15 @@ class TimesNet(nn.Module):
             else:
                 floor = torch.full((N,), self.min_sigma, dtype=torch.float32, device=dev)
             flags = torch.zeros(1, dtype=torch.int32, device=dev)
-            rate, disp = nv.nb_head(seq, steps, N, Wt, bt, self._f32(self.mu_head.weight),
-                                    self._f32(self.mu_head.bias), self._f32(self.sigma_head.weight),
-                                    self._f32(self.sigma_head.bias), hist, late, gate, floor, flags)
+            res = None
+            if self.d_model % 16 == 0 and N >= 16:
+                w_heads, b_heads, n_pad = self._heads_split(dev)
+                res = nv.nb_head_tc(seq, steps, N, Wt, bt, w_heads, b_heads, n_pad, hist, late, gate, floor, flags)
+            if res is None:
+                res = nv.nb_head(seq, steps, N, Wt, bt, self._f32(self.mu_head.weight),
+                                 self._f32(self.mu_head.bias), self._f32(self.sigma_head.weight),
+                                 self._f32(self.sigma_head.bias), hist, late, gate, floor, flags)
+            rate, disp = res
             if self.check_finite:
                 bad = int(flags.item())                                      # the reference syncs here too
                 if bad & 1:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 11
+#define FTN_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -293,6 +293,16 @@ FTN_API int ftn_rms_norm(const void* x, int dtype, int rows, int C, const float*
 FTN_API int ftn_embed_combine(const float* value, const float* aux, const float* gate, int aux_batched,
                       int B, int L, int C, int dtype_out, void* out, void* stream);
 
+/* K0 on the tensor cores: value GEMM (three-plane fp32 split, include note on FtnInceptionWeights.w_in_s3) with the
+ * combine above fused into its epilogue.  x: fp32 [rows = B*L][N]; w_s3: split value_embedding.weight, bf16
+ * [C][3 Kp] with Kp = N rounded up to 16 and zero padding; aux: [L][C] (aux_batched = 0) or [rows][C]; out: dtype_out
+ * [rows][C].  replaces timesnet.py:1295 + :1306-1312.  Returns -1 (nothing enqueued) when C % 16 != 0 or N < 16:
+ * the caller then uses ftn_linear + ftn_embed_combine. */
+FTN_API size_t ftn_embed_tc_workspace_bytes(long long rows, int N);
+FTN_API int ftn_embed_tc(const float* x, long long rows, int L, int N, const void* w_s3, const float* bias, const float* aux,
+                         int aux_batched, const float* gate, int C, int dtype_out, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- K6: Negative-Binomial head -------------------------------------------
  * hidden[b,h,c] = sum_t Wt[h][t] seq[b,t,c] + bt[h]              (forecast_time_proj, :2071)
  * rate  = softplus(hidden . Wmu^T + bmu + hist[b,h,n] + gate[h] late[b,n,h]) + 1e-6   (:2079-2085)
@@ -308,10 +318,40 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
                 const float* late_gate, const float* floor_n, float* rate, float* disp,
                 int32_t* flags, float* workspace, void* stream);
 
+/* Same head with mu_head and sigma_head as ONE tensor-core GEMM (three-plane fp32 split) whose epilogue does the
+ * softplus / floor / finite checks.  w_heads_s3: bf16 [2 Np][3 C], rows [0, N) = split mu_head.weight, rows
+ * [Np, Np + N) = split sigma_head.weight, other rows zero; b_heads: [2 Np] fp32 likewise; Np a multiple of 128.
+ * Returns -1 (nothing enqueued) when C % 16 != 0 or N < 16. */
+FTN_API size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C);
+FTN_API int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
+                           const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
+                           const float* late, const float* late_gate, const float* floor_n, float* rate, float* disp,
+                           int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* NB negative log-likelihood, masked mean.  replaces losses.py:27-58.
  * mask: NULL or uint8 [count]; partial: >= 2*1024 floats scratch; out: 1 float. */
 FTN_API int ftn_nb_nll(const float* y, const float* rate, const float* disp, const uint8_t* mask,
                int64_t count, float eps, float* partial, float* out, void* stream);
+
+/* ---- backward, first slice -------------------------------------
+ * The stages where a backward is cheapest; the Inception chain and the selector have none yet, so the modules stay
+ * forward-only and these are reached through timesnet_forecast/autograd.py.
+ *   ftn_nb_nll_backward           d loss / d rate, d loss / d dispersion of ftn_nb_nll (losses.py:27-58); grad_out: 1 float
+ *                                 (device); wsum_scratch: 1 float scratch
+ *   ftn_nb_head_epilogue_backward gradients w.r.t. the mu / sigma head pre-activations (softplus', timesnet.py:2079-2093)
+ *   ftn_layer_norm_backward       dx, dw, db of LayerNorm over the last dim (fp32)
+ *   ftn_gemm_f32                  C[b] = op(A[b]) . op(B[b]) (+ C[b]); row-major fp32, transposes, batch strides in
+ *                                 elements: dX = dY . W and dW = dY^T . X of the nn.Linear layers */
+FTN_API int ftn_nb_nll_backward(const float* y, const float* rate, const float* disp, const uint8_t* mask, int64_t count,
+                                float eps, const float* grad_out, float* wsum_scratch, float* d_rate, float* d_disp, void* stream);
+FTN_API int ftn_nb_head_epilogue_backward(const float* rate, const float* disp, const float* floor_n, const float* d_rate,
+                                          const float* d_disp, int64_t rows, int N, float* d_pre_rate, float* d_pre_disp,
+                                          void* stream);
+FTN_API int ftn_layer_norm_backward(const float* x, const float* dy, const float* w, int64_t rows, int C, float eps, float* dx,
+                                    float* dw, float* db, void* stream);
+FTN_API int ftn_gemm_f32(const float* A, int lda, int64_t stride_a, int trans_a, const float* B, int ldb, int64_t stride_b,
+                         int trans_b, float* C, int ldc, int64_t stride_c, int M, int N, int K, int batch, int accumulate,
+                         void* stream);
 
 /* ---- NVLink peer mailbox: the path's one collective without NCCL --------------
  * replaces the all-reduce of amp_channel_median.mean(dim=0) a sharded batch needs (timesnet.py:112).

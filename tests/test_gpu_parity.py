@@ -9,6 +9,7 @@ Bars (BASELINE.json north_star):
     a few bf16 ulps of the output scale: REL_BF16 = 2e-2
 """
 import math
+import os
 
 import pytest
 import torch
@@ -23,10 +24,19 @@ REL_BF16 = 2e-2
 
 
 def _rel(got, want):
+    """max |got - want| / max |want|: a tensor-level bound (looser than element-wise relative error).
+    With FLOWTIMES_LOG_ERR=<file> every measured value is appended with the calling test's name (profiles/ keeps the
+    margins of a round)."""
     got = got.detach().float().cpu()
     want = want.detach().float().cpu()
     scale = max(1e-6, want.abs().max().item())
-    return (got - want).abs().max().item() / scale
+    err = (got - want).abs().max().item() / scale
+    log = os.environ.get("FLOWTIMES_LOG_ERR")
+    if log:
+        name = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+        with open(log, "a") as f:
+            f.write(f"{err:.3e} {name}\n")
+    return err
 
 
 def _sub(t, n=4096):

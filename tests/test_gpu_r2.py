@@ -398,3 +398,49 @@ def test_shared_period_search_is_opt_in():
     assert sel.process_group is None
     local_period_search(sel)
     assert sel.process_group is False
+
+
+@pytest.mark.parametrize("stack_dtype", [None, torch.bfloat16])
+def test_timesnet_forward_tensor_core_embedding_and_heads(stack_dtype):
+    """N >= 16 series and d_model % 16 == 0: the value embedding (K0) and the mu / sigma heads run as three-plane
+    tensor-core GEMMs with fused epilogues (ftn_embed_tc, ftn_nb_head_tc); same bounds against the oracle as the fp32
+    SIMT layers they replace."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.losses import negative_binomial_nll
+    from timesnet_forecast.models.timesnet import TimesNet
+    wl = syn.Workload("tc_head", B=5, T=48, N=37, H=12, d_model=32, n_layers=1, k_periods=3, dtype="f32", d_ff=64)
+    m = TimesNet(input_len=wl.T, pred_len=wl.H, d_model=wl.d_model, n_layers=wl.n_layers, k_periods=wl.k_periods,
+                 kernel_set=[list(k) for k in wl.kernel_set], dropout=0.0, activation="gelu", mode="direct", d_ff=wl.ff,
+                 bottleneck_ratio=wl.bottleneck_ratio, use_checkpoint=False, stack_dtype=stack_dtype).eval()
+    x = syn.planted_series(wl.B, wl.T, wl.N, seed=3)
+    m(x[:1].cuda())
+    sd = syn.reseed_module_state(m, seed=9)
+    m.load_state_dict(sd, strict=True)
+    calls = {"embed": 0, "head": 0}
+    orig_e, orig_h = nv.embed_tc, nv.nb_head_tc
+
+    def spy_e(*a, **k):
+        out = orig_e(*a, **k)
+        calls["embed"] += out is not None
+        return out
+
+    def spy_h(*a, **k):
+        out = orig_h(*a, **k)
+        calls["head"] += out is not None
+        return out
+    nv.embed_tc, nv.nb_head_tc = spy_e, spy_h
+    try:
+        rate, disp = m(x.cuda())
+    finally:
+        nv.embed_tc, nv.nb_head_tc = orig_e, orig_h
+    assert calls == {"embed": 1, "head": 1}, f"tensor-core layers were not used: {calls}"
+    cfg = orc.ModelCfg(wl.T, wl.H, wl.d_model, wl.n_layers, wl.k_periods)
+    tr = {}
+    r_ref, d_ref = orc.timesnet_forward(x, {k: v.cpu() for k, v in sd.items()}, cfg, trace=tr)
+    tol = REL_F32 if stack_dtype is None else REL_BF16
+    assert _rel(rate, r_ref) < tol and _rel(disp, d_ref) < tol
+    y = syn.poisson_targets(wl.B, wl.H, wl.N, 5.0, seed=2)
+    assert _rel(negative_binomial_nll(y.cuda(), rate, disp), orc.nb_nll(y, r_ref, d_ref)) < tol
+    # the embedding on its own, fp32 out
+    feat = m.embedding(x.cuda())
+    assert _rel(feat, tr["features"]) < 1e-5
