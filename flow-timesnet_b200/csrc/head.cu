@@ -221,7 +221,7 @@ __global__ void embed_combine_kernel(const float* __restrict__ value, const floa
 __global__ void nb_epilogue_kernel(float* __restrict__ rate, float* __restrict__ disp,
                                    const float* __restrict__ hist, const float* __restrict__ late,
                                    const float* __restrict__ late_gate, const float* __restrict__ floor_n,
-                                   int B, int steps, int N, int32_t* __restrict__ flags) {
+                                   int B, int steps, int N, long long hist_stride, int32_t* __restrict__ flags) {
   // one (window, step) row per block, threads stride over the series axis: no per-element 64-bit division, and
   // N = 321 fills 128-thread blocks to 84 % (the flat-index form spent its time in two long-long divides per element)
   int bad = 0;
@@ -230,7 +230,7 @@ __global__ void nb_epilogue_kernel(float* __restrict__ rate, float* __restrict__
     const long long b = bh / steps;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       const long long i = bh * N + n;
-      float pre = rate[i] + hist[i];                                      // mu_head(h) + history_tail (:2079)
+      float pre = rate[i] + hist[b * hist_stride + (long long)h * N + n];   // mu_head(h) + history_tail (:2079)
       if (late) pre += late_gate[h] * late[((size_t)b * N + n) * steps + h];   // gate * bias^T (:2041-2047)
       float r = softplus20(pre) + 1e-6f;                                  // :2081-2085
       float d = softplus20(disp[i]) + floor_n[n] + 1e-6f;                 // :2088-2093
@@ -396,8 +396,8 @@ extern "C" int ftn_embed_combine(const float* value, const float* aux, const flo
 
 extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
                            const float* bt, const float* Wmu, const float* bmu, const float* Wsg, const float* bsg,
-                           const float* hist, const float* late, const float* late_gate, const float* floor_n,
-                           float* rate, float* disp, int32_t* flags, float* workspace, void* stream) {
+                           const float* hist, int64_t hist_batch_stride, const float* late, const float* late_gate,
+                           const float* floor_n, float* rate, float* disp, int32_t* flags, float* workspace, void* stream) {
   FTN_REQUIRE(seq && Wt && bt && Wmu && bmu && Wsg && bsg && hist && floor_n && rate && disp && flags && workspace,
               "ftn_nb_head: null pointer");
   FTN_REQUIRE((late == nullptr) == (late_gate == nullptr), "ftn_nb_head: late and late_gate must come together");
@@ -416,8 +416,9 @@ extern "C" int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int 
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wmu, C, 0, rate, N, 0, M, N, C, 1, true, bmu, 1, st)) return rc;
   if (int rc = launch_sgemm_f32(workspace, C, 0, Wsg, C, 0, disp, N, 0, M, N, C, 1, true, bsg, 1, st)) return rc;
   const long long rows = (long long)M;
+  const long long hstride = hist_batch_stride > 0 ? hist_batch_stride : (long long)steps * N;
   nb_epilogue_kernel<<<(unsigned)(rows < (1 << 20) ? rows : (1 << 20)), 128, 0, st>>>(rate, disp, hist, late, late_gate, floor_n, B,
-                                                                                    steps, N, flags);
+                                                                                    steps, N, hstride, flags);
   FTN_LAUNCH_CHECK("nb_epilogue_kernel");
   return 0;
 }
@@ -496,8 +497,8 @@ extern "C" size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C) {
 
 extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
                               const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
-                              const float* late, const float* late_gate, const float* floor_n, float* rate, float* disp,
-                              int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
+                              int64_t hist_batch_stride, const float* late, const float* late_gate, const float* floor_n,
+                              float* rate, float* disp, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
   FTN_REQUIRE(seq && Wt && bt && w_heads_s3 && b_heads && hist && floor_n && rate && disp && flags && workspace,
               "ftn_nb_head_tc: null pointer");
   FTN_REQUIRE((late == nullptr) == (late_gate == nullptr), "ftn_nb_head_tc: late and late_gate must come together");
@@ -526,6 +527,7 @@ extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, i
   g.w1 = (const __nv_bfloat16*)w_heads_s3; g.bias1 = b_heads; g.K1 = C; g.K2 = 0; g.N = 2 * Np; g.act = 0;
   g.epi = TC_EPI_NBHEAD; g.res = TC_RES_NONE; g.out = rate; g.ldo = 8;
   g.rows_valid = rows; g.gate = late_gate; g.head_n = N; g.head_np = Np; g.head_steps = steps;
-  g.hist = hist; g.late = late; g.floor_n = floor_n; g.disp = disp; g.flags = flags;
+  g.hist = hist; g.hist_stride = hist_batch_stride > 0 ? hist_batch_stride : (long long)steps * N;
+  g.late = late; g.floor_n = floor_n; g.disp = disp; g.flags = flags;
   return tc_gemm_launch(g, st);
 }

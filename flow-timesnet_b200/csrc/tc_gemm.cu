@@ -57,7 +57,7 @@ struct TcGemmKernelArgs {
   const float* gate;
   int out_bf16;
   int head_n, head_np, head_steps;
-  const float* hist; const float* late; const float* floor_n; float* disp; int32_t* flags;
+  const float* hist; long long hist_stride; const float* late; const float* floor_n; float* disp; int32_t* flags;
 };
 
 // F.softplus(beta = 1, threshold = 20) in fp32 device math (timesnet.py:2081-2091)
@@ -274,7 +274,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const float a = __uint_as_float(vr[i]) + s_bias1[c + i];
         const size_t o = pos_row * p.head_n + n;
         if (is_rate) {
-          float pre = a + __ldg(p.hist + o);                                          // mu_head(h) + history_tail (:2079)
+          float pre = a + __ldg(p.hist + bwin * p.hist_stride + (size_t)h * p.head_n + n);   // mu_head(h) + history_tail (:2079)
           if (p.late) pre += __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h);   // (:2041-2047)
           const float rt = softplus20f(pre) + 1e-6f;                                   // :2081-2085
           reinterpret_cast<float*>(p.out)[o] = rt;
@@ -557,7 +557,7 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.res = a.res; k.bias1 = a.bias1; k.bias2 = a.bias2; k.res_ptr = a.res_ptr; k.res_ld = a.res_ld;
   k.out = a.out; k.ldo = a.ldo; k.x = a.x; k.C = a.C;
   k.rows_valid = a.rows_valid; k.aux = a.aux; k.aux_rows = a.aux_rows; k.gate = a.gate; k.out_bf16 = a.out_bf16;
-  k.head_n = a.head_n; k.head_np = a.head_np; k.head_steps = a.head_steps; k.hist = a.hist; k.late = a.late;
+  k.head_n = a.head_n; k.head_np = a.head_np; k.head_steps = a.head_steps; k.hist = a.hist; k.hist_stride = a.hist_stride; k.late = a.late;
   k.floor_n = a.floor_n; k.disp = a.disp; k.flags = a.flags;
   FTN_REQUIRE(a.epi < TC_EPI_EMBED || (a.split && !a.plan && a.K2 == 0), "tc_gemm: the row-GEMM epilogues need split mode and no plan");
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;

@@ -46,7 +46,7 @@ struct TcGemmArgs {
   const float* gate;                          // EMBED: per-column gate; NBHEAD: late-bias gate per step (may be null)
   int out_bf16;                               // EMBED: output dtype
   int head_n, head_np, head_steps;            // NBHEAD: series count N, padded column block, steps per window
-  const float* hist; const float* late; const float* floor_n; float* disp; int32_t* flags;
+  const float* hist; long long hist_stride; const float* late; const float* floor_n; float* disp; int32_t* flags;
 };
 // fp32 [rows][C] -> three bf16 planes [rows][3 Kp], Kp >= C a multiple of 16 (columns >= C are zero)
 int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st);

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -104,7 +104,7 @@ SIGNATURES = {
     "ftn_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ftn_layer_norm": (_I, [_P, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ftn_embed_combine": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "ftn_nb_head": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ftn_nb_head": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ftn_nb_nll_backward": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P, _P, _P]),
     "ftn_nb_head_epilogue_backward": (_I, [_P, _P, _P, _P, _P, _I64, _I, _P, _P, _P]),
     "ftn_layer_norm_backward": (_I, [_P, _P, _P, _I64, _I, _F, _P, _P, _P, _P]),
@@ -112,7 +112,7 @@ SIGNATURES = {
     "ftn_embed_tc_workspace_bytes": (_SZ, [C.c_longlong, _I]),
     "ftn_embed_tc": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
     "ftn_nb_head_tc_workspace_bytes": (_SZ, [_I, _I, _I]),
-    "ftn_nb_head_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ftn_nb_head_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ftn_nb_nll": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P]),
 }
 
@@ -535,6 +535,13 @@ def embed_tc(x: torch.Tensor, w_s3: torch.Tensor, bias: torch.Tensor, aux: torch
     return out
 
 
+def _hist_view(hist: torch.Tensor, steps: int, N: int):
+    """(pointer, batch stride in elements) of a history tail ``[B, steps, N]`` that may be a VIEW into x (rows dense)."""
+    if hist.stride(2) != 1 or hist.stride(1) != N:
+        hist = hist.contiguous()
+    return hist, hist.data_ptr(), int(hist.stride(0)) if hist.shape[0] > 1 else steps * N
+
+
 def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_gate, floor_n, flags):
     """NB head with the mu / sigma heads as one tensor-core GEMM.  None = shape not eligible."""
     lib = load()
@@ -543,8 +550,9 @@ def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_
     disp = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
     nbytes = lib.ftn_nb_head_tc_workspace_bytes(B, steps, Cc)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=seq.device)
+    hist, hist_ptr, hist_stride = _hist_view(hist, steps, N)
     rc = lib.ftn_nb_head_tc(seq.data_ptr(), dtype_code(seq.dtype), B, L, Cc, steps, N, Wt.data_ptr(), bt.data_ptr(),
-                            w_heads_s3.data_ptr(), b_heads.data_ptr(), Np, hist.data_ptr(), _ptr(late), _ptr(late_gate),
+                            w_heads_s3.data_ptr(), b_heads.data_ptr(), Np, hist_ptr, hist_stride, _ptr(late), _ptr(late_gate),
                             floor_n.data_ptr(), rate.data_ptr(), disp.data_ptr(), flags.data_ptr(), ws.data_ptr(), nbytes,
                             _stream())
     if rc == -1:
@@ -558,8 +566,9 @@ def nb_head(seq, steps, N, Wt, bt, Wmu, bmu, Wsg, bsg, hist, late, late_gate, fl
     rate = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
     disp = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
     ws = torch.empty(B * steps * Cc, dtype=torch.float32, device=seq.device)
+    hist, hist_ptr, hist_stride = _hist_view(hist, steps, N)
     _check(load().ftn_nb_head(seq.data_ptr(), dtype_code(seq.dtype), B, L, Cc, steps, N, Wt.data_ptr(), bt.data_ptr(),
-                              Wmu.data_ptr(), bmu.data_ptr(), Wsg.data_ptr(), bsg.data_ptr(), hist.data_ptr(),
+                              Wmu.data_ptr(), bmu.data_ptr(), Wsg.data_ptr(), bsg.data_ptr(), hist_ptr, hist_stride,
                               _ptr(late), _ptr(late_gate), floor_n.data_ptr(), rate.data_ptr(), disp.data_ptr(),
                               flags.data_ptr(), ws.data_ptr(), _stream()), "ftn_nb_head")
     return rate, disp

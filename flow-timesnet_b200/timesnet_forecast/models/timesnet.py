@@ -1393,10 +1393,9 @@ class TimesNet(nn.Module):
             seq = self.stack_forward(seq)                                    # timesnet.py:2050-2061
             # ---- head (timesnet.py:2008-2014, 2063-2093) ----
             hist_steps = min(steps, L)
-            hist = xv[:, -hist_steps:, :]
-            if hist_steps < steps:
-                hist = torch.cat([hist, hist[:, -1:, :].expand(-1, steps - hist_steps, -1)], dim=1)
-            hist = hist.contiguous()
+            hist = xv[:, -hist_steps:, :]                                    # a VIEW of x: the head reads it in place
+            if hist_steps < steps:                                           # pred_len > input_len: repeat the last step
+                hist = torch.cat([hist, hist[:, -1:, :].expand(-1, steps - hist_steps, -1)], dim=1).contiguous()
             Wt = self._f32(self.forecast_time_proj.weight[-steps:, :] if steps != self.pred_len
                            else self.forecast_time_proj.weight)
             bt = self._f32(self.forecast_time_proj.bias[-steps:] if steps != self.pred_len
@@ -1411,7 +1410,10 @@ class TimesNet(nn.Module):
             if isinstance(self.min_sigma_vector, torch.Tensor) and self.min_sigma_vector.numel() > 0:
                 floor = self.min_sigma_vector.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
             else:
-                floor = torch.full((N,), self.min_sigma, dtype=torch.float32, device=dev)
+                fkey = (N, self.min_sigma, str(dev))
+                if getattr(self, "_floor_cache", (None,))[0] != fkey:
+                    self._floor_cache = (fkey, torch.full((N,), self.min_sigma, dtype=torch.float32, device=dev))
+                floor = self._floor_cache[1]
             flags = torch.zeros(1, dtype=torch.int32, device=dev)
             res = None
             if self.d_model % 16 == 0 and N >= 16:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 13
+#define FTN_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -310,11 +310,13 @@ FTN_API int ftn_embed_tc(const float* x, long long rows, int L, int N, const voi
  * Wt rows are the LAST `steps` rows of forecast_time_proj (caller slices for recursive mode).
  * late: NULL or late_bias_head output [B][N][steps] with late_gate[steps] (:2028-2048);
  * floor is [N] (min_sigma broadcast by the caller).
+ * hist: history tail, element (b, h, n) at hist[b * hist_batch_stride + h * N + n]; hist_batch_stride <= 0 = dense
+ *   [B][steps][N].  With steps <= L the caller passes a VIEW of x (x + (L - steps) * N, stride L * N): no copy.
  * flags[0] |= 1 if any rate is non-finite or <= 0, |= 2 for dispersion      (:2094-2097)
  * workspace: B*steps*C floats. */
 FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int steps, int N,
                 const float* Wt, const float* bt, const float* Wmu, const float* bmu,
-                const float* Wsg, const float* bsg, const float* hist, const float* late,
+                const float* Wsg, const float* bsg, const float* hist, int64_t hist_batch_stride, const float* late,
                 const float* late_gate, const float* floor_n, float* rate, float* disp,
                 int32_t* flags, float* workspace, void* stream);
 
@@ -325,8 +327,8 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
 FTN_API size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C);
 FTN_API int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
                            const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
-                           const float* late, const float* late_gate, const float* floor_n, float* rate, float* disp,
-                           int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
+                           int64_t hist_batch_stride, const float* late, const float* late_gate, const float* floor_n,
+                           float* rate, float* disp, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* NB negative log-likelihood, masked mean.  replaces losses.py:27-58.
  * mask: NULL or uint8 [count]; partial: >= 2*1024 floats scratch; out: 1 float. */
