@@ -390,7 +390,9 @@ bool tc_block_search_overlap_eligible(int dtype, int B, int L, int C, int max_gr
 int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
                                 const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                                 const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
-                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi);
+                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi,
+                                bool search_is_one_kernel);
+bool tc_dft_one_kernel(int dtype, int B, int L, int C);   // tc_dft.cu: the search with this basis is a single launch
 int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                     const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                     const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st);
@@ -518,21 +520,21 @@ namespace {
 struct SearchCtx {
   const void* x; int dtype, B, L, C, k, pmax, min_period;
   float* amp_median; float* amp_sum; FtnPeriodPlan* plan; void* amps; float* weights; void* ws; size_t ws_bytes;
-  void* peer_comm;
+  const void* dft_basis; void* peer_comm;
 };
 int run_search(void* c, cudaStream_t st) {
   const SearchCtx* s = static_cast<const SearchCtx*>(c);
   return ftn_period_search(s->x, s->dtype, s->B, s->L, s->C, s->k, s->pmax, s->min_period, s->amp_median, s->amp_sum, s->plan,
-                           s->amps, s->weights, s->ws, s->ws_bytes, s->peer_comm, st);
+                           s->amps, s->weights, s->ws, s->ws_bytes, s->dft_basis, s->peer_comm, st);
 }
 }  // namespace
 
 extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                                       float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                                      void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
-                                      const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
-                                      float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* peer_comm,
-                                      void* stream) {
+                                      void* search_workspace, size_t search_workspace_bytes, const void* dft_basis,
+                                      const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
+                                      const float* ln_weight, const float* ln_bias, float ln_eps, void* out, void* workspace,
+                                      size_t workspace_bytes, void* peer_comm, void* stream) {
   FTN_REQUIRE(x && plan && out && workspace && weights && amps && amp_median && amp_sum && search_workspace,
               "ftn_timesblock_forward: null pointer");
   FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_timesblock_forward: bad sizes B=%d L=%d C=%d", B, L, C);
@@ -547,12 +549,13 @@ extern "C" int ftn_timesblock_forward(const void* x, int dtype, int B, int L, in
   FTN_REQUIRE(workspace_bytes >= ftn_inception_workspace_bytes(B, L, k, a, b), "ftn_timesblock_forward: workspace too small");
   FTN_REQUIRE(search_workspace_bytes >= ftn_spectrum_workspace_bytes(B, L, C), "ftn_timesblock_forward: search workspace too small");
   SearchCtx ctx{x, dtype, B, L, C, k, pmax, min_period, amp_median, amp_sum, plan, amps, weights, search_workspace,
-                search_workspace_bytes, peer_comm};
+                search_workspace_bytes, dft_basis, peer_comm};
   // periods the selection kernel can emit: ceil(L / bin) with bin in [1, L/2], clamped to [min_period, pmax], and at
   // least two cycles (period_search.cu); the k x k stages skip their long-period fallback launch when none can need it
   const int hi_raw = pmax > 0 && pmax < L - 1 ? pmax : L - 1;
   const int lo = hi_raw >= 2 ? (min_period > 2 ? min_period : 2) : 1;
   const int hi = hi_raw > lo ? hi_raw : lo;
+  const bool one_kernel = dft_basis && tc_dft_one_kernel(dtype, B, L, C);
   return period_block_tc_with_search(x, B, L, C, plan, k, a, b, act, weights, ln_weight, ln_bias, ln_eps, out, workspace,
-                                     as_stream(stream), run_search, &ctx, lo, hi);
+                                     as_stream(stream), run_search, &ctx, lo, hi, one_kernel);
 }

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "peer.cuh"
+#include "select_tail.cuh"
 
 namespace ftn {
 
@@ -139,14 +140,6 @@ __global__ void __launch_bounds__(1024) batch_sum_kernel(const float* __restrict
   if (blockIdx.x == 0 && r == 0 && fl == 0) amp_sum[F] = (float)count;   // window count rides along (all-reduced with the sums)
 }
 
-// rank key: larger is better; NaN ranks above everything like torch.topk
-__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {
-  bool na = sa != sa, nb = sb != sb;
-  if (na != nb) return na;
-  if (!na && sa != sb) return sa > sb;
-  return ia < ib;  // tie rule: lower bin first
-}
-
 // per window: amplitudes at the chosen bins (dtype) + softmax group weights.  The fused selection kernel does this in its
 // own tail for ordinary batches; with tens of thousands of windows (BASELINE config 5) one CTA walking them is the
 // bottleneck of the search, so the tail runs as its own grid.
@@ -216,91 +209,8 @@ __global__ void group_weights_kernel(const T* __restrict__ amps, int B, int k, i
   for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = w[g];
 }
 
-// ---- fused tail: batch sum (optional) + scores + top-k + plan + per-window amplitudes / weights ----
-// One CTA of 1024 threads (three separate launches cost ~32 us at the elec shape, all latency); with
-// a sharded batch the caller runs batch_sum_kernel, all-reduces, and calls this with do_sum = 0.
-// Summation order, score rounding, tie rule and grouping are the ones of the separate kernels.
-__device__ __forceinline__ void argbest_warp(float& s, int& i) {
-  #pragma unroll 1
-  for (int o = 16; o > 0; o >>= 1) {
-    const float so = __shfl_xor_sync(0xffffffffu, s, o);
-    const int io = __shfl_xor_sync(0xffffffffu, i, o);
-    if (io != 0x7fffffff && (i == 0x7fffffff || better(so, io, s, i))) { s = so; i = io; }
-  }
-}
-
-// Warp-cooperative equivalent of plan_group_default (common.cuh): lane i owns candidate i.  Same semantics
-// (default exact-duplicate grouping, groups ascending by period, canonical member = largest mean amplitude,
-// lowest index on ties), ~200 instructions per lane instead of ~2000 dependent ones in a single thread.
-__device__ __noinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
-                                                float my_amp, int nv, int L, int min_p, int max_p) {
-  bool v = lane < nv && my_p > 0;
-  if (min_p > 0 && my_p < min_p) v = false;
-  if (max_p > 0 && my_p > max_p) v = false;
-  int pad = 0, cyc = 0;
-  if (v) {
-    pad = (my_p - (L % my_p)) % my_p;
-    cyc = (L + pad) / my_p;
-    if (cyc < 2) v = false;
-  }
-  const int p = v ? my_p : 0;
-  // first = lowest valid lane holding this period
-  bool first = v;
-  int rank = 0, off = 0, canon = lane;
-  float best = my_amp;
-  #pragma unroll 1
-  for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int pj = __shfl_sync(0xffffffffu, p, j);
-    const float aj = __shfl_sync(0xffffffffu, my_amp, j);
-    if (pj > 0 && pj == p && j < lane) first = false;
-  }
-  const int padv = pad;
-  #pragma unroll 1
-  for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int pj = __shfl_sync(0xffffffffu, p, j);
-    const int firstj = __shfl_sync(0xffffffffu, (int)first, j);
-    const int padj = __shfl_sync(0xffffffffu, padv, j);
-    const float aj = __shfl_sync(0xffffffffu, my_amp, j);
-    if (firstj && pj > 0 && pj < p) { ++rank; off += L + padj; }           // groups ascend by period
-    if (pj > 0 && pj == p && j != lane) {
-      // canonical member: strictly larger amplitude wins, scanning candidates in index order
-      if (j < canon ? !(best > aj) : aj > best) { canon = j; best = aj; }
-    }
-  }
-  const unsigned firsts = __ballot_sync(0xffffffffu, first && v);
-  const int G = __popc(firsts);
-  int total = 0;
-  #pragma unroll 1
-  for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int firstj = __shfl_sync(0xffffffffu, (int)(first && v), j);
-    const int padj = __shfl_sync(0xffffffffu, padv, j);
-    if (firstj) total += L + padj;
-  }
-  if (lane < FTN_MAX_K) {
-    pl->mapping[lane] = v ? rank : -1;
-    // unused group slots
-    if (lane >= G) {
-      pl->grp_period[lane] = 0; pl->grp_pad[lane] = 0; pl->grp_cycles[lane] = 0; pl->grp_canon[lane] = -1;
-      pl->grp_row_off[lane] = total;
-    }
-  }
-  if (first && v) {
-    pl->grp_period[rank] = p;
-    pl->grp_pad[rank] = pad;
-    pl->grp_cycles[rank] = cyc;
-    pl->grp_row_off[rank] = off;
-    pl->grp_canon[rank] = canon;
-  }
-  if (lane == 0) {
-    pl->seq_len = L;
-    pl->n_groups = G;
-    pl->total_rows_per_window = total;
-    pl->grp_row_off[FTN_MAX_K] = total;
-  }
-}
-
-constexpr int kSelFinishThreads = 128;   // 2 x 8 KB of per-thread slots; static + dynamic shared memory must stay < 48 KB by default
-
+// ---- fused tail as its own kernel: one CTA running select_tail (select_tail.cuh) after the SIMT spectrum kernels, or
+// after an all-reduce of the sums (do_sum = 0).  The tensor-core spectrum (tc_dft.cu) runs the same function in its last CTA.
 template <typename T>
 __global__ void __launch_bounds__(1024)
 select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ amp_sum, int do_sum,
@@ -308,189 +218,11 @@ select_fused_kernel(const float* __restrict__ amp_median, float* __restrict__ am
                     int global_batch, int L, int k, int pmax, int min_period, FtnPeriodPlan* __restrict__ plan,
                     T* __restrict__ amps, float* __restrict__ weights, const PeerDev peer) {
   extern __shared__ float sf[];
-  const int F = L / 2 + 1;
-  float* s_sum = sf;              // [F + 1]
-  float* s_score = sf + F + 1;    // [F]
-  float* s_part = s_score + F;    // [32][F]   (do_sum only)
-  __shared__ int s_top[FTN_MAX_K];
-  __shared__ FtnPeriodPlan s_plan;
-  __shared__ float s_e[FTN_MAX_K][kSelFinishThreads];
-  __shared__ float s_w[FTN_MAX_K][kSelFinishThreads];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ SelShared sh;
   pdl_trigger();
   pdl_wait();   // reads the medians and rewrites the plan / weights earlier kernels of the stream were reading
-
-  if (do_sum) {
-    // same order as batch_sum_kernel: row-lane r sums b = r, r+32, ... serially, then a serial fold over r.
-    // Loads are issued four at a time before they are consumed: this kernel is one CTA, so dependent L2 round
-    // trips (~700 cycles each on B200), not instructions, are what it spends its time on.
-#pragma unroll 1
-    for (int f0 = lane; f0 < F; f0 += 128) {       // 4 bins x 2 rows = 8 independent loads in flight per thread
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      int b = warp;
-#pragma unroll 1
-      for (; b + 32 < sum_rows; b += 64) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int f = f0 + 32 * q;
-          v[q] = f < F ? sum_src[(size_t)b * F + f] : 0.f;
-          v[4 + q] = f < F ? sum_src[(size_t)(b + 32) * F + f] : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[q] += v[q]; acc[q] += v[4 + q]; }   // same order as the serial loop
-      }
-#pragma unroll 1
-      for (; b < sum_rows; b += 32) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int f = f0 + 32 * q;
-          if (f < F) acc[q] += sum_src[(size_t)b * F + f];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int f = f0 + 32 * q;
-        if (f < F) s_part[warp * F + f] = acc[q];
-      }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int f = tid; f < F; f += blockDim.x) {
-      float t = 0.f;
-#pragma unroll 8
-      for (int i = 0; i < 32; ++i) t += s_part[i * F + f];
-      s_sum[f] = t;
-      amp_sum[f] = t;
-    }
-    if (tid == 0) { s_sum[F] = (float)B; amp_sum[F] = (float)B; }
-    if (peer.world > 1) {
-      // sharded batch: exchange the F sums + the window count with the peers over NVLink (peer.cuh) -- every rank ends
-      // up with the same rank-ordered totals, so the selection below is identical everywhere
-      __syncthreads();
-      peer_allreduce_cta(peer, s_sum, F + 1);
-#pragma unroll 1
-      for (int f = tid; f <= F; f += blockDim.x) amp_sum[f] = s_sum[f];
-    }
-  } else {
-#pragma unroll 1
-    for (int f = tid; f <= F; f += blockDim.x) s_sum[f] = amp_sum[f];
-  }
-  __syncthreads();
-
-  // scores in the activation dtype, exactly as timesnet.py:119-130
-  const float gb = global_batch > 0 ? (float)global_batch : s_sum[F];
-  #pragma unroll 1
-  for (int f = tid; f < F; f += blockDim.x) {
-    const float m = round_to<T>(s_sum[f] / gb);
-    const float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
-    float sc = round_to<T>(m - pen);
-    if (f == 0) sc = -CUDART_INF_F;
-    s_score[f] = sc;
-  }
-  __syncthreads();
-  const int kk = min(k, F - 1);
-  // top-k by rank counting: candidate f's rank = number of candidates that beat it (the ordering `better` is
-  // total: score, then lower bin), so all kk winners are found in one parallel pass instead of kk dependent
-  // arg-max rounds
-  // (s_part is free again after the batch sum and doubles as the integer rank counters)
-  int* s_rank = reinterpret_cast<int*>(s_sum + 2 * F + 1);
-  const int nseg = max(1, (int)blockDim.x / F);            // threads per candidate
-  const int seg_len = (F + nseg - 1) / nseg;
-#pragma unroll 1
-  for (int f = tid; f < F; f += blockDim.x) s_rank[f] = 0;
-  __syncthreads();
-#pragma unroll 1
-  for (int item = tid; item < nseg * F; item += blockDim.x) {
-    const int f = item % F, sg = item / F;
-    const float sc = s_score[f];
-    const int o_end = min(F, (sg + 1) * seg_len);
-    int part = 0;
-#pragma unroll 4
-    for (int o = sg * seg_len; o < o_end; ++o) part += (o != f && better(s_score[o], o, sc, f)) ? 1 : 0;
-    if (part) atomicAdd(&s_rank[f], part);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int f = tid; f < F; f += blockDim.x)
-    if (s_rank[f] < kk) s_top[s_rank[f]] = f;
-  __syncthreads();
-  if (warp == 0) {
-    // period math for candidate `lane` (timesnet.py:137-154), then the cooperative grouping
-    const int upper = min(pmax, max(1, L - 1));
-    const int lower = min_period;
-    int safe = 0, per = 0;
-    bool keep = false;
-    if (lane < kk) {
-      safe = max(s_top[lane], 1);
-      if (upper >= lower) {
-        int p = (L + safe - 1) / safe;
-        p = p < lower ? lower : (p > upper ? upper : p);
-        if ((L + p - 1) / p >= 2) { keep = true; per = p; }
-      }
-    }
-    // compact the kept candidates in rank order: position = number of kept lanes below
-    const unsigned kept = __ballot_sync(0xffffffffu, keep);
-    const int nv = __popc(kept);
-    const int pos = __popc(kept & ((1u << lane) - 1u));
-    if (lane < FTN_MAX_K) {
-      s_plan.raw_freq[lane] = lane < kk ? safe : 0;
-      s_plan.freq[lane] = 0;
-      s_plan.period[lane] = 0;
-    }
-    if (lane < 3) s_plan.reserved[lane] = 0;
-    __syncwarp();
-    if (keep) { s_plan.freq[pos] = safe; s_plan.period[pos] = per; }
-    if (lane == 0) { s_plan.n_raw = kk; s_plan.n_valid = nv; }
-    __syncwarp();
-    const int my_p = lane < nv ? (int)s_plan.period[lane] : 0;
-    const float my_amp = lane < nv ? s_sum[(int)s_plan.freq[lane]] : 0.f;
-    plan_group_warp(&s_plan, lane, my_p, my_amp, nv, L, min_period, pmax);
-  }
-  __syncthreads();
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_plan);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
-    #pragma unroll 1
-    for (int i = tid; i < (int)(sizeof(FtnPeriodPlan) / 4); i += blockDim.x) dst[i] = src[i];
-  }
-  // per window: amplitudes at the chosen bins (dtype) + softmax group weights  
-  const int nv = s_plan.n_valid;
-  if (do_finish && tid < kSelFinishThreads) {
-    #pragma unroll 1
-    for (int b = tid; b < B; b += kSelFinishThreads) {
-      float mx = -CUDART_INF_F;
-      float raw[FTN_MAX_K];
-#pragma unroll
-      for (int j = 0; j < FTN_MAX_K; ++j)                    // all loads in flight together (one L2 round trip)
-        raw[j] = j < nv ? amp_median[(size_t)b * F + (int)s_plan.freq[j]] : 0.f;
-#pragma unroll
-      for (int j = 0; j < FTN_MAX_K; ++j) {
-        const float v = j < nv ? round_to<T>(raw[j]) : 0.f;
-        if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
-        if (j < nv) {
-          s_e[j][tid] = v;
-          if (s_plan.mapping[j] >= 0) mx = fmaxf(mx, v);
-        }
-      }
-      float den = 0.f;
-      #pragma unroll 1
-      for (int j = 0; j < nv; ++j)
-        if (s_plan.mapping[j] >= 0) den += expf(s_e[j][tid] - mx);
-      #pragma unroll 1
-      for (int j = 0; j < nv; ++j)
-        s_e[j][tid] = round_to<T>(expf(s_e[j][tid] - mx) / den);     // softmax fp32 -> dtype (timesnet.py:1000)
-      #pragma unroll
-      for (int g = 0; g < FTN_MAX_K; ++g) s_w[g][tid] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < nv; ++j) {                        // candidates in index order, exactly like scatter_add_
-        const int g = s_plan.mapping[j];
-        if (g >= 0) s_w[g][tid] = round_to<T>(s_w[g][tid] + s_e[j][tid]);   // scatter_add_ in dtype (:1009)
-      }
-#pragma unroll
-      for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = s_w[g][tid];
-    }
-  }
+  select_tail<T>(amp_median, amp_sum, do_sum, sum_src, sum_rows, B, do_finish, global_batch, L, k, pmax, min_period, plan, amps,
+                 weights, peer, sf, &sh);
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -501,6 +233,13 @@ int spectrum_small_launch(const void* x, int dtype, int B, int L, int C, float* 
 int spectrum_fft_launch(const void* x, int dtype, int B, int L, int C, float* amp, float* med, bool* fused_median,
                         cudaStream_t st);
 int channel_median_reg_launch(const float* amp, int rows, int C, float* med, cudaStream_t st);
+// tc_dft.cu
+bool tc_dft_eligible(int dtype, int B, int L, int C);
+int tc_dft_launch(const void* x, int B, int L, int C, const void* basis, float* med, cudaStream_t st);
+bool tc_dft_tail_eligible(int L);
+int tc_dft_search_launch(const void* x, int B, int L, int C, const void* basis, float* med, float* amp_sum, int do_finish,
+                         int global_batch, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
+                         const void* comm, cudaStream_t st);
 
 }  // namespace ftn
 
@@ -516,7 +255,7 @@ extern "C" size_t ftn_spectrum_workspace_bytes(int B, int L, int C) {
 // per-CTA partial rows the small-window kernel leaves in the workspace)
 static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
                          void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum,
-                         const float** sum_src = nullptr, int* sum_rows = nullptr);
+                         const float** sum_src = nullptr, int* sum_rows = nullptr, const void* dft_basis = nullptr);
 constexpr int kFinishInKernelMax = 1024;   // windows the one-CTA selection kernel finishes itself
 
 extern "C" int ftn_spectrum(const void* x, int dtype, int B, int L, int C, float* amp_median,
@@ -539,7 +278,7 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
               2 * (FTN_PEER_MAX_FLOATS - 2));
   if (!sum_src) { sum_src = amp_median; sum_rows = B; }
   const int do_finish = B <= kFinishInKernelMax ? 1 : 0;
-  const size_t smem = (size_t)(2 * F + 1 + (do_sum ? 32 * F : F)) * sizeof(float);
+  const size_t smem = select_tail_floats(F, do_sum) * sizeof(float);
   FTN_REQUIRE(smem <= 160 * 1024, "period search: L=%d too long for the fused selection tail", L);
   if (dtype == FTN_F32) {
     FTN_DYN_SMEM(select_fused_kernel<float>, smem);
@@ -567,14 +306,36 @@ static int launch_select_fused(const float* amp_median, float* amp_sum, int do_s
 
 extern "C" int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                                  float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                                 void* workspace, size_t workspace_bytes, void* peer_comm, void* stream) {
+                                 void* workspace, size_t workspace_bytes, const void* dft_basis, void* peer_comm,
+                                 void* stream) {
   FTN_REQUIRE(plan && amps && weights, "ftn_period_search: null pointer");
   FTN_REQUIRE(k >= 1 && k <= FTN_MAX_K, "ftn_period_search: k=%d outside [1,%d]", k, FTN_MAX_K);
   cudaStream_t st = as_stream(stream);
   TimedScope timed(FTN_FAM_SPECTRUM, st);
+  if (dft_basis && tc_dft_eligible(dtype, B, L, C) && tc_dft_tail_eligible(L)) {
+    // ONE launch: tensor-core spectrum + medians, and the last CTA to finish runs the selection tail (tc_dft.cu).
+    // plan->reserved[2] is the ticket: zero on entry (a plan buffer starts zeroed; every search leaves it zero).
+    FTN_REQUIRE(x && amp_median && amp_sum, "ftn_period_search: null pointer");
+    FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_period_search: need B>0, L>1, C>0 (got %d,%d,%d)", B, L, C);
+    const int do_finish = B <= kFinishInKernelMax ? 1 : 0;
+    {
+      TimedScope tf(FTN_FAM_FFT, st);
+      if (int rc = tc_dft_search_launch(x, B, L, C, dft_basis, amp_median, amp_sum, do_finish, peer_comm ? 0 : B, k, pmax, min_period,
+                                        plan, amps, weights, peer_comm, st))
+        return rc;
+    }
+    if (!do_finish) {   // many windows: the per-window tail as its own grid
+      const int F = L / 2 + 1;
+      FTN_CUDA(launch_pdl(true, finish_kernel<__nv_bfloat16>, dim3((B + 127) / 128), dim3(128), 0, st, (const float*)amp_median, B, F, k,
+                          (const FtnPeriodPlan*)plan, (__nv_bfloat16*)amps, weights));
+      FTN_LAUNCH_CHECK("finish_kernel");
+    }
+    return 0;
+  }
   const float* sum_src = nullptr;
   int sum_rows = 0;
-  if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false, &sum_src, &sum_rows))
+  if (int rc = spectrum_impl(x, dtype, B, L, C, amp_median, amp_sum, workspace, workspace_bytes, st, false, &sum_src, &sum_rows,
+                             dft_basis))
     return rc;
   // with a peer communicator the count slot is reduced too: divide by the GLOBAL batch (global_batch <= 0 = "take it
   // from the count slot")
@@ -584,7 +345,7 @@ extern "C" int ftn_period_search(const void* x, int dtype, int B, int L, int C, 
 
 static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* amp_median, float* amp_sum,
                          void* workspace, size_t workspace_bytes, cudaStream_t st, bool with_batch_sum,
-                         const float** sum_src, int* sum_rows) {
+                         const float** sum_src, int* sum_rows, const void* dft_basis) {
   FTN_REQUIRE(x && amp_median && amp_sum && workspace, "ftn_spectrum: null pointer");
   FTN_REQUIRE(B > 0 && L > 1 && C > 0, "ftn_spectrum: need B>0, L>1, C>0 (got %d,%d,%d)", B, L, C);
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_spectrum: unsupported dtype %d", dtype);
@@ -593,6 +354,15 @@ static int spectrum_impl(const void* x, int dtype, int B, int L, int C, float* a
   const int F = L / 2 + 1;
   float* amp = reinterpret_cast<float*>(workspace);
   if (sum_src) { *sum_src = amp_median; *sum_rows = B; }
+  if (dft_basis && tc_dft_eligible(dtype, B, L, C)) {
+    // tensor-core route (tc_dft.cu): spectrum as a GEMM against the caller's DFT basis, channel median in its epilogue
+    { TimedScope tf(FTN_FAM_FFT, st); if (int rc = tc_dft_launch(x, B, L, C, dft_basis, amp_median, st)) return rc; }
+    if (with_batch_sum) {
+      batch_sum_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(amp_median, B, F, amp_sum, B);
+      FTN_LAUNCH_CHECK("batch_sum_kernel");
+    }
+    return 0;
+  }
   {
     // short windows, many of them: grid-stride CTAs, medians + per-CTA partial sums in one kernel (spectrum_fft.cu)
     int rows = 0;

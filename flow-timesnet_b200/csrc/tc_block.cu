@@ -163,7 +163,8 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
                                const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta,
                                void* workspace, const TcTailSpec* tail, cudaStream_t st, const TcS1Done* s1 = nullptr);
 static int launch_block_s1(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
-                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row);
+                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row,
+                           bool after_search = false);
 
 int period_conv_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                    const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
@@ -200,7 +201,21 @@ int period_block_tc(const void* x, int B, int L, int C, const FtnPeriodPlan* pla
 int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPlan* plan, int max_groups,
                                 const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, const float* weights,
                                 const float* ln_w, const float* ln_b, float eps, void* out, void* workspace, cudaStream_t st,
-                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi) {
+                                int (*search)(void*, cudaStream_t), void* search_ctx, int period_lo, int period_hi,
+                                bool search_is_one_kernel) {
+  if (search_is_one_kernel) {
+    // The tensor-core search (tc_dft.cu) is ONE kernel whose CTAs own whole SMs, followed by a one-CTA tail.  No side
+    // stream: the first stage is launched programmatically right behind it in the same stream, starts when the
+    // search's CTAs have finished their spectra (that kernel triggers its dependents there), fills the SMs they free
+    // while the last CTA selects the periods, and waits for the search only before exiting (late_wait) -- so the k x k
+    // stage, which waits for this stage, has waited for the plan too.
+    TcS1Done s1{-1, period_lo, period_hi};
+    if (int rc = search(search_ctx, st)) return rc;
+    if (int rc = launch_block_s1(x, B, L, C, nullptr, max_groups, a, act, workspace, st, &s1.shared_bias_row, true)) return rc;
+    TcTailSpec tail{weights, ln_w, ln_b, eps, out};
+    TimedScope timed(FTN_FAM_CONV, st);
+    return period_conv_tc_impl(x, B, L, C, plan, max_groups, a, b, act, nullptr, workspace, &tail, st, &s1);
+  }
   // per-device side stream, per-call event pair (lib.cu): re-entrant across devices and host threads
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -227,14 +242,16 @@ int period_block_tc_with_search(const void* x, int B, int L, int C, FtnPeriodPla
 // (plus one tile of out-of-bounds = zero rows, whose output is the row every padded step t >= L stands for) instead
 // of once per group over the tile-major grid; the k x k loaders then index h1 by (window, t).
 static int launch_block_s1(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
-                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row) {
+                           const FtnInceptionWeights* a, int act, void* workspace, cudaStream_t st, long long* shared_bias_row,
+                           bool after_search) {
   const int tiles = tc_worst_case_tiles(B, L, max_groups);
   const int NBa = a->n_branch * a->mid;
   TcGemmArgs s{};
   s.plan = plan; s.B = B; s.L = L; s.max_groups = max_groups; s.n_tiles = tiles; s.act = act;
   s.a1 = reinterpret_cast<const __nv_bfloat16*>(x); s.a1_ld = C; s.w1 = (const __nv_bfloat16*)a->w_in_bf16; s.bias1 = a->b_in;
   s.K1 = C; s.N = NBa; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = reinterpret_cast<__nv_bfloat16*>(workspace); s.ldo = NBa;
-  s.first_in_call = true;
+  s.first_in_call = !after_search;
+  s.late_wait = after_search;
   *shared_bias_row = -1;
   const long long seq_tiles = ((long long)B * L + 127) / 128 + 1;
   if (tc_kk_uses_conv4(a) && seq_tiles <= tiles) {

@@ -37,6 +37,9 @@ struct TcGemmArgs {
   void* out; int ldo;                         // PLAIN / BLOCK_A: tile-major; DELTA: delta base
   const void* x; int C;                       // DELTA: grid to subtract
   bool first_in_call;                         // first kernel of an API call: plain launch, no programmatic dependency
+  int max_ctas;                               // > 0: cap on the persistent grid (a kernel running beside it owns the other SMs)
+  bool late_wait;                             // tc_gemm2 only: the stage reads nothing its stream predecessor writes -- it runs
+                                              // beside that kernel's tail and waits for it just before exiting (see tc_block.cu)
   // split != 0: fp32 activations as three bf16 planes (tc_gemm.cu).  a1 / a2 / w1 / w2 / out then are [rows][3 K] /
   // [rows][3 N] (a*_ld, ldo count ALL planes), x and a TC_RES_SEQ residual are the fp32 block input, a DELTA out is fp32.
   int split;

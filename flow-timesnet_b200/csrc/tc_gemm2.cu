@@ -35,6 +35,7 @@ struct TcGemm2Args {
   const __nv_bfloat16* q; int ld_q;       // DELTA: residual, tile-major
   const __nv_bfloat16* x; int C;          // DELTA: grid to subtract, x[B][L][C]
   __nv_bfloat16* out; int ldo;            // PLAIN: tile-major [tiles*128][ldo]; DELTA: delta[g][B][L][C]
+  int late_wait;                          // 1: griddepcontrol.wait at the END of the kernel instead of before the first load
 };
 
 enum { G2_W_FULL = 0, G2_A_FULL = 1, G2_A_EMPTY = 3, G2_ACC_FULL = 5, G2_ACC_EMPTY = 7, G2_BARS = 9 };
@@ -93,7 +94,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();   // the activations (and the plan) are predecessors' outputs
+  // late_wait: nothing this stage reads or writes is touched by its stream predecessor (the period search: the
+  // activations were complete before that kernel started), so it runs beside the predecessor's tail; the wait moves to
+  // the end, which makes this grid complete only after the predecessor -- dependents that wait for this grid have then
+  // waited for both
+  if (!p.late_wait) pdl_wait();   // the activations (and the plan) are predecessors' outputs
   const FtnPeriodPlan* pl = p.plan;
 
   if (warp == 0) {
@@ -205,6 +210,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (p.late_wait) pdl_wait();
 }
 
 // ---------------------------------------------------------------------------------
@@ -269,6 +275,8 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.plan = a.plan; k.n_plain = a.n_tiles; k.B = a.B; k.L = a.L; k.a_seq = a.a1_seq; k.K = a.K1; k.N = a.N; k.act = a.act; k.epi = a.epi;
   k.bias = a.bias1; k.q = (const __nv_bfloat16*)a.res_ptr; k.ld_q = a.res_ld; k.x = (const __nv_bfloat16*)a.x; k.C = a.C;
   k.out = (__nv_bfloat16*)a.out; k.ldo = a.ldo;
+  k.late_wait = a.late_wait ? 1 : 0;
+  FTN_REQUIRE(!a.late_wait || (!a.first_in_call && !a.plan), "tc_gemm2: late_wait needs a programmatic launch and no plan");
   const int nkb = (a.K1 + G2_BK - 1) / G2_BK;
   const size_t smem = 1024 + (size_t)nkb * ((a.N * 128 + 1023) & ~1023) + (size_t)G2_STAGES * nkb * G2_A_KB + 128 * 4 + 16 +
                       G2_BARS * 8 + 16;
@@ -276,7 +284,8 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st) {
   if (ai) FTN_DYN_SMEM(tc_gemm2_kernel<1>, smem);
   else FTN_DYN_SMEM(tc_gemm2_kernel<0>, smem);
   const int worst = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
-  const int grid = worst < sm_count() ? worst : sm_count();
+  int grid = worst < sm_count() ? worst : sm_count();
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   if (ai) FTN_CUDA(launch_pdl(!a.first_in_call, tc_gemm2_kernel<1>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
   else FTN_CUDA(launch_pdl(!a.first_in_call, tc_gemm2_kernel<0>, dim3(grid), dim3(G2_THREADS), smem, st, mA, mW, k));
   FTN_LAUNCH_CHECK("tc_gemm2_kernel");

@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 14
+ABI_VERSION = 15
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -76,7 +76,9 @@ SIGNATURES = {
     "ftn_spectrum_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ftn_spectrum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    "ftn_dft_basis_bytes": (_SZ, [_I]),
+    "ftn_dft_basis_build": (_I, [_I, _P, _SZ, _P]),
     "ftn_peer_create": (_I, [_I, _I, C.POINTER(_P), C.c_char_p]),
     "ftn_peer_connect": (_I, [_P, C.c_char_p]),
     "ftn_peer_allreduce": (_I, [_P, _P, _I, _P]),
@@ -91,7 +93,7 @@ SIGNATURES = {
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
     "ftn_timesblock_fused": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                                   C.POINTER(FtnInceptionWeights), _I, _P, _P, _P, _F, _P, _P, _SZ, _P]),
-    "ftn_timesblock_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ,
+    "ftn_timesblock_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P,
                                     C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights), _I, _P, _P, _F, _P, _P,
                                     _SZ, _P, _P]),
     "ftn_inception_block_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights)]),
@@ -254,10 +256,37 @@ class PeerComm:
             self._handle = C.c_void_p()
 
 
-def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int, comm: Optional["PeerComm"] = None):
+_DFT_BASIS = {}   # (device index, L) -> uint8 tensor holding the three-plane DFT basis of the tensor-core spectrum
+
+
+def dft_basis(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """DFT basis for the tensor-core spectrum of ``x[B, L, C]`` (csrc/tc_dft.cu), built once per (device, L) and cached;
+    ``None`` when that route does not apply (fp32 activations, C other than 64 / 128, short windows) or while a CUDA
+    graph is being captured before the basis exists (the SIMT FFT is captured instead)."""
+    B, L, Cc = x.shape
+    if x.dtype != torch.bfloat16 or Cc not in (64, 128) or L <= 64 or os.environ.get("FLOWTIMES_NO_TC_DFT"):
+        return None
+    key = (x.device.index, L)
+    t = _DFT_BASIS.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        lib = load()
+        nbytes = lib.ftn_dft_basis_bytes(L)
+        t = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _check(lib.ftn_dft_basis_build(L, t.data_ptr(), nbytes, _stream()), "ftn_dft_basis_build")
+        torch.cuda.current_stream(x.device).synchronize()   # one-time: later calls may come from any stream
+        _DFT_BASIS[key] = t
+    return t
+
+
+def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int, comm: Optional["PeerComm"] = None,
+                  tensor_dft: bool = True):
     """Fused search: x[B,L,C] -> (plan, amps[B,k], weights[B,16], amp_median[B,F], amp_sum[F+1]).  With ``comm`` the
-    batch is sharded over the communicator's ranks and the partial sums are exchanged inside the selection kernel."""
+    batch is sharded over the communicator's ranks and the partial sums are exchanged inside the selection kernel.
+    ``tensor_dft=False`` keeps the spectrum on the SIMT FFT (A/B tests)."""
     lib = load()
+    basis = dft_basis(x) if tensor_dft else None
     B, L, Cc = x.shape
     Fq = L // 2 + 1
     med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
@@ -269,7 +298,7 @@ def period_search(x: torch.Tensor, k: int, pmax: int, min_period: int, comm: Opt
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     _check(lib.ftn_period_search(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
                                  ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), ws.data_ptr(),
-                                 nbytes, None if comm is None else comm.ptr, _stream()), "ftn_period_search")
+                                 nbytes, _ptr(basis), None if comm is None else comm.ptr, _stream()), "ftn_period_search")
     return plan, amps, weights, med, ssum
 
 
@@ -371,12 +400,13 @@ def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: 
     weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=x.device)
     sbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)
     sws = torch.empty(sbytes, dtype=torch.uint8, device=x.device)
+    basis = dft_basis(x)
     nbytes = lib.ftn_inception_workspace_bytes(B, L, k, C.byref(wa), C.byref(wb))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     out = torch.empty_like(x)
     rc = lib.ftn_timesblock_forward(x.data_ptr(), dtype_code(x.dtype), B, L, Cc, k, pmax, min_period, med.data_ptr(),
                                     ssum.data_ptr(), plan.data_ptr(), amps.data_ptr(), weights.data_ptr(), sws.data_ptr(),
-                                    sbytes, C.byref(wa), C.byref(wb), act, _ptr(ln_w), _ptr(ln_b), float(eps),
+                                    sbytes, _ptr(basis), C.byref(wa), C.byref(wb), act, _ptr(ln_w), _ptr(ln_b), float(eps),
                                     out.data_ptr(), ws.data_ptr(), nbytes, None if comm is None else comm.ptr, _stream())
     if rc == -1:
         return None

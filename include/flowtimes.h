@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 14
+#define FTN_ABI_VERSION 15
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -173,10 +173,20 @@ FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, in
  * Same outputs as the pair: amp_median [B][F], amp_sum [F+1], plan, amps [B][k], weights [B][FTN_MAX_K].
  * peer_comm = NULL: single rank, nothing to reduce.  peer_comm = a communicator from ftn_peer_create / _connect: the
  * batch is sharded over its ranks and the selection kernel exchanges the F + 1 partial sums with the peers over NVLink
- * peer memory (see "NVLink peer mailbox" below) -- every rank must make the call. */
+ * peer memory (see "NVLink peer mailbox" below) -- every rank must make the call.
+ * dft_basis = NULL: mixed-radix FFT on the SIMT pipes.  dft_basis = a buffer filled by ftn_dft_basis_build(L): for bf16
+ * x with C = 64 or 128 and L > 64 the spectrum is ONE tcgen05 GEMM against the DFT basis with the channel median in its
+ * epilogue (csrc/tc_dft.cu); other shapes ignore the basis. */
 FTN_API int ftn_period_search(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                       float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                      void* workspace, size_t workspace_bytes, void* peer_comm, void* stream);
+                      void* workspace, size_t workspace_bytes, const void* dft_basis, void* peer_comm, void* stream);
+
+/* DFT basis of the tensor-core spectrum: (cos, sin)(2 pi f t / L) for f < L/2 + 1, t < L as three bf16 planes
+ * (hi / mid / lo parts of the double-precision value -> fp32-accurate products), rows ordered for the kernel's epilogue.
+ * The caller owns the buffer (128-byte aligned, ftn_dft_basis_bytes(L) bytes), builds it once per L and device and passes it
+ * to ftn_period_search / ftn_timesblock_forward; it is read-only afterwards and may be shared by any number of streams. */
+FTN_API size_t ftn_dft_basis_bytes(int L);
+FTN_API int ftn_dft_basis_build(int L, void* basis, size_t basis_bytes, void* stream);
 
 /* HOST helper (no CUDA): group an externally supplied candidate list (a custom
  * period_selector module) with the default exact-duplicate rules and fill a
@@ -252,10 +262,10 @@ FTN_API int ftn_timesblock_fused(const void* x, int dtype, int B, int L, int C, 
  * issues the two calls itself), 0 on success. */
 FTN_API int ftn_timesblock_forward(const void* x, int dtype, int B, int L, int C, int k, int pmax, int min_period,
                                    float* amp_median, float* amp_sum, FtnPeriodPlan* plan, void* amps, float* weights,
-                                   void* search_workspace, size_t search_workspace_bytes, const FtnInceptionWeights* a,
-                                   const FtnInceptionWeights* b, int act, const float* ln_weight, const float* ln_bias,
-                                   float ln_eps, void* out, void* workspace, size_t workspace_bytes, void* peer_comm,
-                                   void* stream);
+                                   void* search_workspace, size_t search_workspace_bytes, const void* dft_basis,
+                                   const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
+                                   const float* ln_weight, const float* ln_bias, float ln_eps, void* out, void* workspace,
+                                   size_t workspace_bytes, void* peer_comm, void* stream);
 /* ---- K4: weighted aggregation + residual (+ shared LayerNorm) ------------
  * out = x + sum_g w[b][g] * delta_g          replaces timesnet.py:1075-1099, :818
  * with ln_weight != NULL additionally        replaces timesnet.py:2059-2061
