@@ -33,8 +33,10 @@ __device__ __forceinline__ unsigned long long rank_key(float score, int f) {
 
 // Warp-cooperative equivalent of plan_group_default (common.cuh): lane i owns candidate i.  Same semantics
 // (default exact-duplicate grouping, groups ascending by period, canonical member = largest mean amplitude,
-// lowest index on ties), ~200 instructions per lane instead of ~2000 dependent ones in a single thread.
-static __device__ __noinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
+// lowest index on ties).  No dependent loops: duplicates are found with match.any, the canonical member with a
+// masked max-reduction, and the group order with sixteen independent shuffles -- this runs in ONE warp on the
+// critical path of every block (the rolled shuffle loops it replaces took 5 us of latency).
+__device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
                                                 float my_amp, int nv, int L, int min_p, int max_p) {
   bool v = lane < nv && my_p > 0;
   if (min_p > 0 && my_p < min_p) v = false;
@@ -45,38 +47,28 @@ static __device__ __noinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane,
     cyc = (L + pad) / my_p;
     if (cyc < 2) v = false;
   }
-  const int p = v ? my_p : 0;
-  // first = lowest valid lane holding this period
-  bool first = v;
-  int rank = 0, off = 0, canon = lane;
-  float best = my_amp;
-  #pragma unroll 1
+  // lanes that are not valid candidates get distinct negative keys: each is alone in its match group
+  const int key = v ? my_p : -1 - lane;
+  const unsigned same = __match_any_sync(0xffffffffu, key);
+  const bool first = v && (lane == __ffs(same) - 1);            // lowest lane holding this period
+  // canonical member of the group: largest mean amplitude (NaN counts as largest), lowest index on ties
+  const uint32_t au = __float_as_uint(my_amp + 0.0f);
+  uint32_t akey = (au & 0x80000000u) ? ~au : (au | 0x80000000u);
+  if (my_amp != my_amp) akey = 0xffffffffu;
+  const uint32_t amax = __reduce_max_sync(same, akey);
+  const int canon = __ffs(__ballot_sync(same, akey == amax)) - 1;
+  // group order: ascending period; row offset = lengths of the groups in front
+  const int pf = first ? my_p : 0x7fffffff;
+  const int len = first ? L + pad : 0;
+  int rank = 0, off = 0, total = 0;
+#pragma unroll
   for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int pj = __shfl_sync(0xffffffffu, p, j);
-    if (pj > 0 && pj == p && j < lane) first = false;
+    const int pj = __shfl_sync(0xffffffffu, pf, j);
+    const int lj = __shfl_sync(0xffffffffu, len, j);
+    if (pj < my_p) { ++rank; off += lj; }
+    total += lj;
   }
-  const int padv = pad;
-  #pragma unroll 1
-  for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int pj = __shfl_sync(0xffffffffu, p, j);
-    const int firstj = __shfl_sync(0xffffffffu, (int)first, j);
-    const int padj = __shfl_sync(0xffffffffu, padv, j);
-    const float aj = __shfl_sync(0xffffffffu, my_amp, j);
-    if (firstj && pj > 0 && pj < p) { ++rank; off += L + padj; }           // groups ascend by period
-    if (pj > 0 && pj == p && j != lane) {
-      // canonical member: strictly larger amplitude wins, scanning candidates in index order
-      if (j < canon ? !(best > aj) : aj > best) { canon = j; best = aj; }
-    }
-  }
-  const unsigned firsts = __ballot_sync(0xffffffffu, first && v);
-  const int G = __popc(firsts);
-  int total = 0;
-  #pragma unroll 1
-  for (int j = 0; j < FTN_MAX_K; ++j) {
-    const int firstj = __shfl_sync(0xffffffffu, (int)(first && v), j);
-    const int padj = __shfl_sync(0xffffffffu, padv, j);
-    if (firstj) total += L + padj;
-  }
+  const int G = __popc(__ballot_sync(0xffffffffu, first));
   if (lane < FTN_MAX_K) {
     pl->mapping[lane] = v ? rank : -1;
     // unused group slots
@@ -85,8 +77,8 @@ static __device__ __noinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane,
       pl->grp_row_off[lane] = total;
     }
   }
-  if (first && v) {
-    pl->grp_period[rank] = p;
+  if (first) {
+    pl->grp_period[rank] = my_p;
     pl->grp_pad[rank] = pad;
     pl->grp_cycles[rank] = cyc;
     pl->grp_row_off[rank] = off;
@@ -124,8 +116,18 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
                                             const float* __restrict__ sum_src, int sum_rows, int B, int do_finish,
                                             int global_batch, int L, int k, int pmax, int min_period,
                                             FtnPeriodPlan* __restrict__ plan, T* __restrict__ amps, float* __restrict__ weights,
-                                            const PeerDev& peer, float* sf, SelShared* sh) {
+                                            const PeerDev& peer, float* sf, SelShared* sh,
+                                            unsigned long long* trace = nullptr) {
   const int F = L / 2 + 1;
+#define FTN_TAIL_MARK(i)                                                                           \
+  do {                                                                                             \
+    if (trace && threadIdx.x == 0) {                                                               \
+      unsigned long long t_;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                       \
+      trace[i] = t_;                                                                               \
+    }                                                                                              \
+  } while (0)
+  FTN_TAIL_MARK(2);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   float* s_sum = sf;                                                          // [F + 1]
   unsigned long long* s_key = reinterpret_cast<unsigned long long*>(sf + ((F + 2) & ~1));   // [F]
@@ -136,7 +138,7 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
     // the 32 row-lanes are folded serially.  One item = (r, f); a thread's items are independent, so their loads are
     // all in flight together -- this CTA is alone on the critical path and L2 round trips are what it waits for.
     const int items = 32 * F;
-    constexpr int Q = 8;                       // items per thread and pass: 2 Q loads in flight
+    constexpr int Q = 8;                       // items per thread and pass: 2 Q loads in flight (more only grows the code: no gain measured)
 #pragma unroll 1
     for (int it0 = tid; it0 < items; it0 += Q * nthr) {
       float acc[Q];
@@ -191,6 +193,7 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
     for (int f = tid; f <= F; f += nthr) s_sum[f] = amp_sum[f];
   }
   __syncthreads();
+  FTN_TAIL_MARK(3);
 
   // scores in the activation dtype, exactly as timesnet.py:119-130
   const float gb = global_batch > 0 ? (float)global_batch : s_sum[F];
@@ -229,6 +232,7 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
   for (int f = tid; f < F; f += nthr)
     if (s_rank[f] < kk) sh->top[s_rank[f]] = f;
   __syncthreads();
+  FTN_TAIL_MARK(4);
   if (warp == 0) {
     // period math for candidate `lane` (timesnet.py:137-154), then the cooperative grouping
     const int upper = min(pmax, max(1, L - 1));
@@ -262,6 +266,7 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
     plan_group_warp(&sh->plan, lane, my_p, my_amp, nv, L, min_period, pmax);
   }
   __syncthreads();
+  FTN_TAIL_MARK(5);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&sh->plan);
     uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
@@ -305,6 +310,8 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
       for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = sh->w[g][tid];
     }
   }
+  FTN_TAIL_MARK(6);
+#undef FTN_TAIL_MARK
 }
 
 }  // namespace ftn

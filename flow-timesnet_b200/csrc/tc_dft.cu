@@ -73,8 +73,13 @@ __device__ __forceinline__ void sort_regs(float (&v)[N]) {
 // The selection tail (select_tail.cuh) folded into this kernel: the last CTA to finish its medians (ticket in
 // plan->reserved[2], zero on entry, zero again on exit) sums them over the batch, ranks the bins, builds the plan and
 // writes the per-window amplitudes / weights -- the whole period search is ONE launch.
+// FLOWTIMES_DFT_TRACE: globaltimer marks of the last launch (0 kernel start of CTA 0, 1 ticket taken by the last CTA,
+// 2..6 the tail's phases), read back with ftn_debug_dft_trace
+__device__ unsigned long long g_dft_trace[8];
+
 struct DftTail {
   int enabled;
+  int trace;
   float* amp_sum;
   int do_finish, global_batch, k, pmax, min_period;
   FtnPeriodPlan* plan;
@@ -118,6 +123,11 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x, b0 = blockIdx.y * WPC;
   const int nkb = (L + DFT_BK - 1) / DFT_BK;
+  if (tail.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_dft_trace[0] = t_;
+  }
   // dependents are released AFTER the spectra (below), not here: a CTA of this kernel needs a whole SM (shared memory)
   // and the L2 bandwidth of the basis stream; what follows it in the stream runs beside the one-CTA tail instead
   if (warp == 0 && lane == 0) {
@@ -244,12 +254,14 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
   }
   tc_fence_before();
-  if (tail.enabled) __threadfence();                       // this thread's medians are visible device-wide before the ticket
   __syncthreads();
   pdl_trigger();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   if (!tail.enabled) return;
   if (threadIdx.x == 0) {
+    // the barrier above ordered every thread's medians before this thread; its fence (cumulative) publishes them
+    // device-wide before the ticket
+    __threadfence();
     const int total = (int)(gridDim.x * gridDim.y);
     const int prev = atomicAdd(reinterpret_cast<int*>(&tail.plan->reserved[2]), 1);
     *s_last = prev == total - 1 ? 1 : 0;
@@ -257,11 +269,17 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   if (!*s_last) return;
   __threadfence();
+  if (tail.trace && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_dft_trace[1] = t_;
+  }
   // the stage ring is idle now (every MMA has completed and every TMA box has landed): the tail's scratch lives there
   float* sf = reinterpret_cast<float*>(smem);
   SelShared* sh = reinterpret_cast<SelShared*>(smem + ((select_tail_floats(F, 1) * 4 + 15) & ~(size_t)15));
   select_tail<__nv_bfloat16>(med, tail.amp_sum, 1, med, B, B, tail.do_finish, tail.global_batch, L, tail.k, tail.pmax,
-                             tail.min_period, tail.plan, tail.amps, tail.weights, tail.peer, sf, sh);
+                             tail.min_period, tail.plan, tail.amps, tail.weights, tail.peer, sf, sh,
+                             tail.trace ? g_dft_trace : nullptr);
 }
 
 // basis[plane][row][t], row = m * 128 + q * 32 + l:  bin f = 64 m + 32 (q / 2) + l, q even = cos, q odd = sin;
@@ -397,8 +415,10 @@ int tc_dft_launch(const void* x, int B, int L, int C, const void* basis, float* 
 int tc_dft_search_launch(const void* x, int B, int L, int C, const void* basis, float* med, float* amp_sum, int do_finish,
                          int global_batch, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
                          const void* comm, cudaStream_t st) {
+  static const bool trace = getenv("FLOWTIMES_DFT_TRACE") != nullptr;
   DftTail tail{};
   tail.enabled = 1;
+  tail.trace = trace ? 1 : 0;
   tail.amp_sum = amp_sum; tail.do_finish = do_finish; tail.global_batch = global_batch;
   tail.k = k; tail.pmax = pmax; tail.min_period = min_period;
   tail.plan = plan; tail.amps = reinterpret_cast<__nv_bfloat16*>(amps); tail.weights = weights;
@@ -412,6 +432,12 @@ int tc_dft_search_launch(const void* x, int B, int L, int C, const void* basis, 
 }  // namespace ftn
 
 using namespace ftn;
+
+extern "C" int ftn_debug_dft_trace(unsigned long long* out8) {
+  FTN_REQUIRE(out8, "ftn_debug_dft_trace: null pointer");
+  FTN_CUDA(cudaMemcpyFromSymbol(out8, g_dft_trace, sizeof(unsigned long long) * 8));
+  return 0;
+}
 
 extern "C" size_t ftn_dft_basis_bytes(int L) {
   if (L < 2) return 0;

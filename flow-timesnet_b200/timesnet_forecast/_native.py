@@ -78,6 +78,7 @@ SIGNATURES = {
     "ftn_select_periods": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ftn_period_search": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     "ftn_dft_basis_bytes": (_SZ, [_I]),
+    "ftn_debug_dft_trace": (_I, [C.POINTER(C.c_ulonglong)]),
     "ftn_dft_basis_build": (_I, [_I, _P, _SZ, _P]),
     "ftn_peer_create": (_I, [_I, _I, C.POINTER(_P), C.c_char_p]),
     "ftn_peer_connect": (_I, [_P, C.c_char_p]),

@@ -185,6 +185,9 @@ FTN_API int ftn_period_search(const void* x, int dtype, int B, int L, int C, int
  * (hi / mid / lo parts of the double-precision value -> fp32-accurate products), rows ordered for the kernel's epilogue.
  * The caller owns the buffer (128-byte aligned, ftn_dft_basis_bytes(L) bytes), builds it once per L and device and passes it
  * to ftn_period_search / ftn_timesblock_forward; it is read-only afterwards and may be shared by any number of streams. */
+/* diagnostic (FLOWTIMES_DFT_TRACE=1): %globaltimer marks of the last one-launch search on the current device:
+ * [0] kernel start, [1] last CTA took the ticket, [2..6] tail phases (start, sums, ranks, plan, per-window finish) */
+FTN_API int ftn_debug_dft_trace(unsigned long long* out8);
 FTN_API size_t ftn_dft_basis_bytes(int L);
 FTN_API int ftn_dft_basis_build(int L, void* basis, size_t basis_bytes, void* stream);
 

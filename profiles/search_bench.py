@@ -34,3 +34,15 @@ for route in (True, False):
     torch.cuda.synchronize()
     print(f"{name} search route={'tensor' if route else 'simt'}: {e0.elapsed_time(e1) * 1e3 / (iters * len(xs)):.2f} us per search "
           f"(graph of {len(xs)} searches)")
+
+if __import__("os").environ.get("FLOWTIMES_DFT_TRACE"):
+    import ctypes
+    lib = nv.load()
+    for rep in range(3):
+        nv.period_search(xs[rep], k, L, 1)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_ulonglong * 8)()
+        lib.ftn_debug_dft_trace(buf)
+        t = list(buf)
+        names = ["start", "ticket", "tail0", "sums", "ranks", "plan", "finish"]
+        print("trace (us from kernel start): " + "  ".join(f"{n}={(t[i] - t[0]) / 1e3:.2f}" for i, n in enumerate(names)))
