@@ -496,7 +496,7 @@ extern "C" size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C) {
 }
 
 extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
-                              const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
+                              const float* bt, const void* wt_s3, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
                               int64_t hist_batch_stride, const float* late, const float* late_gate, const float* floor_n,
                               float* rate, float* disp, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
   FTN_REQUIRE(seq && Wt && bt && w_heads_s3 && b_heads && hist && floor_n && rate && disp && flags && workspace,
@@ -512,15 +512,23 @@ extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, i
   __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) +
                                                      (((size_t)B * steps * C * 4 + 255) & ~size_t(255)));
   // hidden[b] (steps x C) = Wt (steps x L) . seq[b] (L x C) + bt[h]       (forecast_time_proj, :2071)
-  if (dtype == FTN_F32)
+  const long long rows = (long long)B * steps;
+  bool hs_done = false;
+  if (wt_s3 && tc_time_proj_eligible(dtype, B, L, C, steps)) {
+    // bf16 stack output: seq[b] is an MN-major tcgen05 operand -- the projection is the DFT kernel's GEMM with Wt as the
+    // basis, and its epilogue writes the three bf16 planes of hidden directly (tc_dft.cu, MODE 1)
+    if (int rc = tc_time_proj_launch(seq, B, L, C, steps, wt_s3, bt, hs, st)) return rc;
+    hs_done = true;
+  } else if (dtype == FTN_F32)
     sgemm_launch<float, false>(Wt, L, 0, (const float*)seq, C, (long long)L * C, hidden, C, (long long)steps * C, steps, C, L, B,
                                bt, 2, st);
   else
     sgemm_launch<__nv_bfloat16, false>(Wt, L, 0, (const __nv_bfloat16*)seq, C, (long long)L * C, hidden, C,
                                        (long long)steps * C, steps, C, L, B, bt, 2, st);
-  FTN_LAUNCH_CHECK("sgemm_kernel(time_proj)");
-  const long long rows = (long long)B * steps;
-  if (int rc = split3_launch(hidden, rows, C, hs, st, true)) return rc;
+  if (!hs_done) {
+    FTN_LAUNCH_CHECK("sgemm_kernel(time_proj)");
+    if (int rc = split3_launch(hidden, rows, C, hs, st, true)) return rc;
+  }
   TcGemmArgs g{};
   g.plan = nullptr; g.B = 1; g.L = (int)rows; g.max_groups = 1; g.n_tiles = (int)((rows + 127) / 128); g.split = 1;
   g.a1 = hs; g.a1_seq = 0; g.a1_ld = 3 * C; g.a1_rows = rows;

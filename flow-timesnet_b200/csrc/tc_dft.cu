@@ -88,6 +88,17 @@ struct DftTail {
   PeerDev peer;
 };
 
+// MODE 1 of the same kernel: the head's time projection (forecast_time_proj, timesnet.py:2071)
+//     hidden_b[steps, C] = Wt[steps, L] . seq_b[L, C] + bt[h]
+// is the same "left-multiply every window along time" GEMM with Wt (three bf16 planes) in place of the DFT basis.  The
+// epilogue adds the bias and writes hidden as the hi | mid | lo bf16 planes the head GEMM (tc_gemm SPLIT) consumes, so
+// neither the fp32 hidden tensor nor the split kernel exist on this route.
+struct DftProj {
+  const float* bias;        // [steps]
+  __nv_bfloat16* out;       // [B * steps][3 C]
+  int steps;
+};
+
 template <int C, int WPC>
 struct DftCfg {
   static constexpr int N = C * WPC;                       // MMA N: WPC windows side by side
@@ -103,10 +114,10 @@ struct DftCfg {
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)SETS * (XCH_FLOATS + 64) * 4 + 16 * 8 + 32;
 };
 
-template <int C, int WPC>
+template <int C, int WPC, int MODE>
 __global__ void __launch_bounds__(DFT_THREADS, 1)
 tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, float* __restrict__ med,
-              int B, int L, int F, int m_rows, const DftTail tail) {
+              int B, int L, int F, int m_rows, const DftTail tail, const DftProj proj) {
   using Cfg = DftCfg<C, WPC>;
   constexpr int HALF = Cfg::HALF, NX = Cfg::NX, NBOX = Cfg::NBOX, X_BYTES = Cfg::X_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int STAGES = Cfg::STAGES, SETS = Cfg::SETS;
@@ -128,8 +139,9 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
     g_dft_trace[0] = t_;
   }
-  // dependents are released AFTER the spectra (below), not here: a CTA of this kernel needs a whole SM (shared memory)
-  // and the L2 bandwidth of the basis stream; what follows it in the stream runs beside the one-CTA tail instead
+  // MODE 0: dependents are released AFTER the spectra (below), not here: a CTA of this kernel needs a whole SM (shared
+  // memory) and the L2 bandwidth of the basis stream; what follows it in the stream runs beside the one-CTA tail instead
+  if (MODE == 1) pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -190,7 +202,41 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
     if (elect_one()) mma_commit(acc_bar);
     __syncwarp();
-  } else if (warp >= 4 && ((warp - 4) >> 2) < SETS) {
+  } else if (MODE == 1 && warp >= 4) {
+    // ===== epilogue of the time projection: + bias, three-plane bf16 split, row-per-lane 256-bit stores =====
+    const int set = (warp - 4) >> 2, quad = warp & 3;
+    const int h = m * 128 + quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool row_ok = h < proj.steps;
+    const float bias = row_ok ? proj.bias[h] : 0.f;
+    mbar_wait_relaxed(acc_bar, 0);
+    tc_fence_after();
+    constexpr int NH = Cfg::N / 2;                          // columns per warp set
+#pragma unroll 1
+    for (int n0 = set * NH; n0 < (set + 1) * NH; n0 += 16) {
+      float v[16];
+      tmem_ld16(lane_base + n0, v);
+      const int w = n0 / C, c = n0 - w * C, b = b0 + w;
+      if (row_ok && b < B) {
+        uint32_t hi[8], mi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = v[2 * i] + bias, a1 = v[2 * i + 1] + bias;
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+          const float r0 = a0 - __bfloat162float(hh.x), r1 = a1 - __bfloat162float(hh.y);
+          const __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __bfloat162float(mm.x), r1 - __bfloat162float(mm.y));
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          mi[i] = *reinterpret_cast<const uint32_t*>(&mm);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        __nv_bfloat16* dst = proj.out + ((size_t)b * proj.steps + h) * (3 * C) + c;
+        st_global_256(dst, hi);
+        st_global_256(dst + C, mi);
+        st_global_256(dst + 2 * C, lo);
+      }
+    }
+  } else if (MODE == 0 && warp >= 4 && ((warp - 4) >> 2) < SETS) {
     // ===== epilogue: squared amplitudes, register sort, half-cleaner median =====
     const int set = (warp - 4) >> 2, quad = warp & 3, pair = quad >> 1, odd = quad & 1;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -255,9 +301,9 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  pdl_trigger();
+  if (MODE == 0) pdl_trigger();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  if (!tail.enabled) return;
+  if (MODE == 1 || !tail.enabled) return;
   if (threadIdx.x == 0) {
     // the barrier above ordered every thread's medians before this thread; its fence (cumulative) publishes them
     // device-wide before the ticket
@@ -375,11 +421,21 @@ static int dft_launch_cw(const CUtensorMap& mX, const CUtensorMap& mW, float* me
                          cudaStream_t st) {
   using Cfg = DftCfg<C, WPC>;
   const int F = L / 2 + 1, mt = dft_m_tiles(L);
-  FTN_DYN_SMEM((tc_dft_kernel<C, WPC>), Cfg::SMEM);
+  FTN_DYN_SMEM((tc_dft_kernel<C, WPC, 0>), Cfg::SMEM);
   // first kernel of a search: no programmatic attribute (what precedes it in the stream is the caller's)
-  FTN_CUDA(launch_pdl(false, tc_dft_kernel<C, WPC>, dim3(mt, (B + WPC - 1) / WPC), dim3(DFT_THREADS), Cfg::SMEM, st, mX, mW, med, B,
-                      L, F, mt * 128, tail));
+  FTN_CUDA(launch_pdl(false, tc_dft_kernel<C, WPC, 0>, dim3(mt, (B + WPC - 1) / WPC), dim3(DFT_THREADS), Cfg::SMEM, st, mX, mW, med,
+                      B, L, F, mt * 128, tail, DftProj{}));
   FTN_LAUNCH_CHECK("tc_dft_kernel");
+  return 0;
+}
+
+template <int C, int WPC>
+static int proj_launch_cw(const CUtensorMap& mX, const CUtensorMap& mW, int B, int L, int mt, const DftProj& proj, cudaStream_t st) {
+  using Cfg = DftCfg<C, WPC>;
+  FTN_DYN_SMEM((tc_dft_kernel<C, WPC, 1>), Cfg::SMEM);
+  FTN_CUDA(launch_pdl(false, tc_dft_kernel<C, WPC, 1>, dim3(mt, (B + WPC - 1) / WPC), dim3(DFT_THREADS), Cfg::SMEM, st, mX, mW,
+                      (float*)nullptr, B, L, 0, mt * 128, DftTail{}, proj));
+  FTN_LAUNCH_CHECK("tc_dft_kernel(time_proj)");
   return 0;
 }
 
@@ -404,6 +460,60 @@ static int dft_launch(const void* x, int B, int L, int C, const void* basis, flo
   if (wpc == 1) return dft_launch_cw<64, 1>(mX, mW, med, B, L, tail, st);
   if (wpc == 2) return dft_launch_cw<64, 2>(mX, mW, med, B, L, tail, st);
   return dft_launch_cw<64, 4>(mX, mW, med, B, L, tail, st);
+}
+
+// ---- time projection (MODE 1) ----
+static inline int proj_m_tiles(int steps) { return (steps + 127) / 128; }
+
+bool tc_time_proj_eligible(int dtype, int B, int L, int C, int steps) {
+  static const bool off = getenv("FLOWTIMES_NO_TC_TIMEPROJ") != nullptr;   // A/B switch for profiling
+  return !off && dtype == FTN_BF16 && (C == 64 || C == 128 || C == 256) && L >= 16 && L <= 8192 && B >= 1 && B <= 65535 &&
+         steps >= 1 && steps <= 4096;
+}
+
+// hs[B * steps][3 C] = split3(Wt . seq_b + bt) with wt_s3 from ftn_time_proj_pack
+int tc_time_proj_launch(const void* seq, int B, int L, int C, int steps, const void* wt_s3, const float* bt, void* hs,
+                        cudaStream_t st) {
+  const int mt = proj_m_tiles(steps), kpad = dft_kpad(L);
+  CUtensorMap mX, mW;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
+    cuuint32_t box[3] = {64, DFT_BK, 1};
+    if (int rc = dft_map(&mX, seq, 3, dims, strides, box)) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)DFT_PLANES * mt * 128};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {DFT_BK, 128};
+    if (int rc = dft_map(&mW, wt_s3, 2, dims, strides, box)) return rc;
+  }
+  DftProj proj{bt, reinterpret_cast<__nv_bfloat16*>(hs), steps};
+  const int max_wpc = 256 / C > 4 ? 4 : 256 / C;
+  int wpc = 1;
+  while (wpc < max_wpc && ((B + wpc - 1) / wpc) * mt > sm_count()) wpc *= 2;
+  if (C == 256) return proj_launch_cw<256, 1>(mX, mW, B, L, mt, proj, st);
+  if (C == 128) return wpc == 1 ? proj_launch_cw<128, 1>(mX, mW, B, L, mt, proj, st) : proj_launch_cw<128, 2>(mX, mW, B, L, mt, proj, st);
+  if (wpc == 1) return proj_launch_cw<64, 1>(mX, mW, B, L, mt, proj, st);
+  if (wpc == 2) return proj_launch_cw<64, 2>(mX, mW, B, L, mt, proj, st);
+  return proj_launch_cw<64, 4>(mX, mW, B, L, mt, proj, st);
+}
+
+// Wt fp32 [steps][L] -> [3 planes][m_tiles * 128][kpad] bf16 (hi | mid | lo), zero rows / columns beyond
+__global__ void time_proj_pack_kernel(const float* __restrict__ Wt, int steps, int L, int m_rows, int kpad,
+                                      __nv_bfloat16* __restrict__ out) {
+  const long long n = (long long)m_rows * kpad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / kpad), t = (int)(idx - (long long)r * kpad);
+    const float w = r < steps && t < L ? Wt[(size_t)r * L + t] : 0.f;
+    const __nv_bfloat16 w1 = __float2bfloat16_rn(w);
+    const float r1 = w - __bfloat162float(w1);
+    const __nv_bfloat16 w2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 w3 = __float2bfloat16_rn(r1 - __bfloat162float(w2));
+    out[idx] = w1;
+    out[n + idx] = w2;
+    out[2 * n + idx] = w3;
+  }
 }
 
 int tc_dft_launch(const void* x, int B, int L, int C, const void* basis, float* med, cudaStream_t st) {
@@ -436,6 +546,24 @@ using namespace ftn;
 extern "C" int ftn_debug_dft_trace(unsigned long long* out8) {
   FTN_REQUIRE(out8, "ftn_debug_dft_trace: null pointer");
   FTN_CUDA(cudaMemcpyFromSymbol(out8, g_dft_trace, sizeof(unsigned long long) * 8));
+  return 0;
+}
+
+extern "C" size_t ftn_time_proj_pack_bytes(int steps, int L) {
+  if (steps < 1 || L < 1) return 0;
+  return (size_t)DFT_PLANES * proj_m_tiles(steps) * 128 * dft_kpad(L) * sizeof(__nv_bfloat16);
+}
+
+extern "C" int ftn_time_proj_pack(const float* Wt, int steps, int L, void* out, size_t out_bytes, void* stream) {
+  FTN_REQUIRE(Wt && out, "ftn_time_proj_pack: null pointer");
+  FTN_REQUIRE(steps >= 1 && steps <= 4096 && L >= 1 && L <= 8192, "ftn_time_proj_pack: bad sizes steps=%d L=%d", steps, L);
+  FTN_REQUIRE(out_bytes >= ftn_time_proj_pack_bytes(steps, L), "ftn_time_proj_pack: buffer too small");
+  FTN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 127) == 0, "ftn_time_proj_pack: out must be 128-byte aligned");
+  const int m_rows = proj_m_tiles(steps) * 128, kpad = dft_kpad(L);
+  const long long n = (long long)m_rows * kpad;
+  const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  time_proj_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(Wt, steps, L, m_rows, kpad, reinterpret_cast<__nv_bfloat16*>(out));
+  FTN_LAUNCH_CHECK("time_proj_pack_kernel");
   return 0;
 }
 

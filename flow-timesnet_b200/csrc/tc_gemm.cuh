@@ -55,6 +55,10 @@ struct TcGemmArgs {
 int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st);
 // fp32 [rows][C] -> three bf16 planes [rows][3 C] (tc_gemm.cu)
 int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call);
+// tc_dft.cu, MODE 1: hs[B * steps][3 C] = three bf16 planes of (Wt . seq_b + bt), seq bf16 [B][L][C], wt_s3 from ftn_time_proj_pack
+bool tc_time_proj_eligible(int dtype, int B, int L, int C, int steps);
+int tc_time_proj_launch(const void* seq, int B, int L, int C, int steps, const void* wt_s3, const float* bt, void* hs,
+                        cudaStream_t st);
 
 int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st);
 // persistent variant for the K <= 128, N <= 128 single-operand stages (tc_gemm2.cu); tc_stage_launch picks

@@ -115,7 +115,9 @@ SIGNATURES = {
     "ftn_embed_tc_workspace_bytes": (_SZ, [C.c_longlong, _I]),
     "ftn_embed_tc": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
     "ftn_nb_head_tc_workspace_bytes": (_SZ, [_I, _I, _I]),
-    "ftn_nb_head_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ftn_nb_head_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ftn_time_proj_pack_bytes": (_SZ, [_I, _I]),
+    "ftn_time_proj_pack": (_I, [_P, _I, _I, _P, _SZ, _P]),
     "ftn_nb_nll": (_I, [_P, _P, _P, _P, _I64, _F, _P, _P, _P]),
 }
 
@@ -573,8 +575,19 @@ def _hist_view(hist: torch.Tensor, steps: int, N: int):
     return hist, hist.data_ptr(), int(hist.stride(0)) if hist.shape[0] > 1 else steps * N
 
 
-def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_gate, floor_n, flags):
-    """NB head with the mu / sigma heads as one tensor-core GEMM.  None = shape not eligible."""
+def time_proj_pack(Wt: torch.Tensor) -> torch.Tensor:
+    """forecast_time_proj rows ``[steps, L]`` fp32 -> the three-plane bf16 operand of the tensor-core time projection."""
+    lib = load()
+    steps, L = Wt.shape
+    nbytes = lib.ftn_time_proj_pack_bytes(steps, L)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=Wt.device)
+    _check(lib.ftn_time_proj_pack(Wt.data_ptr(), steps, L, out.data_ptr(), nbytes, _stream()), "ftn_time_proj_pack")
+    return out
+
+
+def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_gate, floor_n, flags, wt_s3=None):
+    """NB head with the mu / sigma heads as one tensor-core GEMM (and, given ``wt_s3`` from ``time_proj_pack`` and a bf16
+    ``seq``, the time projection too).  None = shape not eligible."""
     lib = load()
     B, L, Cc = seq.shape
     rate = torch.empty(B, steps, N, dtype=torch.float32, device=seq.device)
@@ -583,7 +596,7 @@ def nb_head_tc(seq, steps, N, Wt, bt, w_heads_s3, b_heads, Np, hist, late, late_
     ws = torch.empty(nbytes, dtype=torch.uint8, device=seq.device)
     hist, hist_ptr, hist_stride = _hist_view(hist, steps, N)
     rc = lib.ftn_nb_head_tc(seq.data_ptr(), dtype_code(seq.dtype), B, L, Cc, steps, N, Wt.data_ptr(), bt.data_ptr(),
-                            w_heads_s3.data_ptr(), b_heads.data_ptr(), Np, hist_ptr, hist_stride, _ptr(late), _ptr(late_gate),
+                            _ptr(wt_s3), w_heads_s3.data_ptr(), b_heads.data_ptr(), Np, hist_ptr, hist_stride, _ptr(late), _ptr(late_gate),
                             floor_n.data_ptr(), rate.data_ptr(), disp.data_ptr(), flags.data_ptr(), ws.data_ptr(), nbytes,
                             _stream())
     if rc == -1:

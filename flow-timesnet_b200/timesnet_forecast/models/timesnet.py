@@ -1276,6 +1276,23 @@ class TimesNet(nn.Module):
             self._heads_cache = (key, w.contiguous(), b, n_pad)
         return self._heads_cache[1], self._heads_cache[2], self._heads_cache[3]
 
+    def _time_proj_split(self, Wt: torch.Tensor, steps: int, dev) -> Optional[torch.Tensor]:
+        """The last ``steps`` rows of forecast_time_proj.weight as the three-plane bf16 operand of the tensor-core time
+        projection (re-packed when the weight changes).  None while a CUDA graph is being captured before the first pack
+        (the SIMT projection is captured instead) or when the stack is fp32."""
+        if self.stack_dtype != torch.bfloat16:
+            return None
+        p = self.forecast_time_proj.weight
+        key = (p.data_ptr(), p._version, steps, str(dev))
+        cache = getattr(self, "_time_proj_cache", None)
+        if cache is None or cache[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            packed = nv.time_proj_pack(Wt)
+            torch.cuda.current_stream(dev).synchronize()
+            self._time_proj_cache = (key, packed)
+        return self._time_proj_cache[1]
+
     def _context(self, B: int, N: int, dev, series_static, series_ids) -> Optional[torch.Tensor]:
         """Static projection + id embedding + context LayerNorm (timesnet.py:1886-1957)."""
         comps = []
@@ -1418,7 +1435,8 @@ class TimesNet(nn.Module):
             res = None
             if self.d_model % 16 == 0 and N >= 16:
                 w_heads, b_heads, n_pad = self._heads_split(dev)
-                res = nv.nb_head_tc(seq, steps, N, Wt, bt, w_heads, b_heads, n_pad, hist, late, gate, floor, flags)
+                res = nv.nb_head_tc(seq, steps, N, Wt, bt, w_heads, b_heads, n_pad, hist, late, gate, floor, flags,
+                                    wt_s3=self._time_proj_split(Wt, steps, dev))
             if res is None:
                 res = nv.nb_head(seq, steps, N, Wt, bt, self._f32(self.mu_head.weight),
                                  self._f32(self.mu_head.bias), self._f32(self.sigma_head.weight),

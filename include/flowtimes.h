@@ -185,6 +185,12 @@ FTN_API int ftn_period_search(const void* x, int dtype, int B, int L, int C, int
  * (hi / mid / lo parts of the double-precision value -> fp32-accurate products), rows ordered for the kernel's epilogue.
  * The caller owns the buffer (128-byte aligned, ftn_dft_basis_bytes(L) bytes), builds it once per L and device and passes it
  * to ftn_period_search / ftn_timesblock_forward; it is read-only afterwards and may be shared by any number of streams. */
+/* forecast_time_proj.weight rows [steps][L] fp32 -> three bf16 planes (hi | mid | lo), rows padded to 128 and columns
+ * to 64: the A operand of the tensor-core time projection.  out: 128-byte aligned, ftn_time_proj_pack_bytes() bytes;
+ * re-pack when the weight changes. */
+FTN_API size_t ftn_time_proj_pack_bytes(int steps, int L);
+FTN_API int ftn_time_proj_pack(const float* Wt, int steps, int L, void* out, size_t out_bytes, void* stream);
+
 /* diagnostic (FLOWTIMES_DFT_TRACE=1): %globaltimer marks of the last one-launch search on the current device:
  * [0] kernel start, [1] last CTA took the ticket, [2..6] tail phases (start, sums, ranks, plan, per-window finish) */
 FTN_API int ftn_debug_dft_trace(unsigned long long* out8);
@@ -336,10 +342,13 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
 /* Same head with mu_head and sigma_head as ONE tensor-core GEMM (three-plane fp32 split) whose epilogue does the
  * softplus / floor / finite checks.  w_heads_s3: bf16 [2 Np][3 C], rows [0, N) = split mu_head.weight, rows
  * [Np, Np + N) = split sigma_head.weight, other rows zero; b_heads: [2 Np] fp32 likewise; Np a multiple of 128.
+ * wt_s3: NULL, or Wt packed by ftn_time_proj_pack: with a bf16 seq and C in {64, 128, 256} the time projection then runs
+ * on tcgen05 too (seq[b] is an MN-major operand; csrc/tc_dft.cu MODE 1) and writes the split hidden directly.
  * Returns -1 (nothing enqueued) when C % 16 != 0 or N < 16. */
 FTN_API size_t ftn_nb_head_tc_workspace_bytes(int B, int steps, int C);
 FTN_API int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, int steps, int N, const float* Wt,
-                           const float* bt, const void* w_heads_s3, const float* b_heads, int Np, const float* hist,
+                           const float* bt, const void* wt_s3, const void* w_heads_s3, const float* b_heads, int Np,
+                           const float* hist,
                            int64_t hist_batch_stride, const float* late, const float* late_gate, const float* floor_n,
                            float* rate, float* disp, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
 
