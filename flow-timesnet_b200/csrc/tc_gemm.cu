@@ -58,6 +58,7 @@ struct TcGemmKernelArgs {
   int out_bf16;
   int head_n, head_np, head_steps;
   const float* hist; long long hist_stride; const float* late; const float* floor_n; float* disp; int32_t* flags;
+  int planes;              // SPLIT: bf16 planes of each operand that are loaded and multiplied (3, or 2 = hi and mid)
 };
 
 // F.softplus(beta = 1, threshold = 20) in fp32 device math (timesnet.py:2081-2091)
@@ -162,7 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int s = kb % STAGES;
       mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
       uint8_t* sa = smem + s * STAGE_BYTES;
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], SPLIT ? (uint32_t)(2 * p.planes) * TC_TILE_BYTES : (uint32_t)STAGE_BYTES);
       __syncwarp();
       const bool ph2 = kb >= nkb1;
       const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
@@ -171,7 +172,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
       // SPLIT: planes 0..2 of the activation, then planes 0..2 of the weights (plane p = columns [p K, (p + 1) K);
       // a box that runs past its plane / the tensor reads the next plane / zeros, which no MMA consumes)
-      if (lane < NP) {
+      if (SPLIT && lane % NP >= p.planes) {
+        // the lo plane is neither loaded nor multiplied in two-plane mode
+      } else if (lane < NP) {
         uint8_t* dst = sa + lane * TC_TILE_BYTES;
         if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(dst, ma, &full[s], lane * K + k0, t0, b);
         else tma_load_2d(dst, ma, &full[s], lane * K + k0, tile_id * TC_BM);
@@ -200,12 +203,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           // (activation plane, weight plane), smallest products first; planes hi = 0, mid = 1, lo = 2
           constexpr int PA[6] = {2, 1, 0, 1, 0, 0};
           constexpr int PW[6] = {0, 1, 2, 0, 1, 0};
+          uint32_t accum = kbl != 0 ? 1u : 0u;
 #pragma unroll
           for (int pr = 0; pr < 6; ++pr) {
+            if (p.planes == 2 && PA[pr] + PW[pr] != 1 && pr != 5) continue;   // two planes: hi.mid, mid.hi, hi.hi
             const uint32_t da = sa + PA[pr] * TILE16, dw = sa + (3 + PW[pr]) * TILE16;
-            for (int k = 0; k < ksteps; ++k)
-              if (elect_one())
-                mma_bf16_lohi(d, da + k * 2, kDescSw128Hi, dw + k * 2, kDescSw128Hi, idesc, (kbl | k | pr) != 0 ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) {
+              if (elect_one()) mma_bf16_lohi(d, da + k * 2, kDescSw128Hi, dw + k * 2, kDescSw128Hi, idesc, accum);
+              accum = 1u;
+            }
           }
         } else {
           const uint32_t sw = sa + TILE16;
@@ -256,34 +262,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (SPLIT && p.epi == TC_EPI_NBHEAD) {
-    // NB head epilogue (timesnet.py:2079-2097): the N-tiles below head_np hold mu_head, the rest sigma_head
-    const bool live = (long long)pos_row < p.rows_valid;
+    // NB head epilogue (timesnet.py:2079-2097): the N-tiles below head_np hold mu_head, the rest sigma_head.
+    // rate / dispersion rows are head_n floats long (321 at the elec shape: not even 16-byte aligned), so a lane that
+    // owns an accumulator ROW can only store single floats, 32 lines per instruction -- the epilogue was 60 us of LSU
+    // time for 16 MB of output.  Each warp transposes its 32 x 32 chunks through shared memory (the stage ring is idle
+    // once `done` has fired) so that lanes run along n: history loads and rate / dispersion stores are coalesced.
     const bool is_rate = n0 < p.head_np;
-    const int h = (int)(pos_row % (size_t)p.head_steps);
-    const size_t bwin = pos_row / (size_t)p.head_steps;
+    const int nb = is_rate ? n0 : n0 - p.head_np;
+    float* T = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const size_t pr0 = (size_t)tile_id * TC_BM + quad * 32;
     int bad = 0;
-    for (int c = half * 16; c < n_tile; c += 32) {
-      uint32_t vr[16];
+    for (int c = half * 32; c < n_tile; c += 64) {
+      uint32_t vr[32];
       tmem_ld16_nowait(trow + c, vr);
+      tmem_ld16_nowait(trow + c + 16, vr + 16);
       tmem_ld_wait();
-      if (!live) continue;
+      __syncwarp();                                   // the previous chunk has been read out of T
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = (is_rate ? n0 : n0 - p.head_np) + c + i;
-        if (n >= p.head_n) continue;
-        const float a = __uint_as_float(vr[i]) + s_bias1[c + i];
-        const size_t o = pos_row * p.head_n + n;
-        if (is_rate) {
-          float pre = a + __ldg(p.hist + bwin * p.hist_stride + (size_t)h * p.head_n + n);   // mu_head(h) + history_tail (:2079)
-          if (p.late) pre += __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h);   // (:2041-2047)
-          const float rt = softplus20f(pre) + 1e-6f;                                   // :2081-2085
-          reinterpret_cast<float*>(p.out)[o] = rt;
-          if (!isfinite(rt) || rt <= 0.f) bad |= 1;                                    // :2094
-        } else {
-          const float d = softplus20f(a) + __ldg(p.floor_n + n) + 1e-6f;               // :2088-2093
-          p.disp[o] = d;
-          if (!isfinite(d) || d <= 0.f) bad |= 2;                                      // :2096
+      for (int i = 0; i < 32; ++i) T[lane * 33 + i] = __uint_as_float(vr[i]);
+      __syncwarp();
+      const int n = nb + c + lane;
+      const bool col_ok = c + lane < n_tile && n < p.head_n;
+      const float bias = c + lane < n_tile ? s_bias1[c + lane] : 0.f;
+      const float fl = (!is_rate && col_ok) ? __ldg(p.floor_n + n) : 0.f;
+      int h = (int)(pr0 % (size_t)p.head_steps);
+      size_t bwin = pr0 / (size_t)p.head_steps;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const size_t prow = pr0 + rr;
+        if (col_ok && (long long)prow < p.rows_valid) {
+          const float a = T[rr * 33 + lane] + bias;
+          const size_t o = prow * p.head_n + n;
+          if (is_rate) {
+            float pre = a + __ldg(p.hist + bwin * p.hist_stride + (size_t)h * p.head_n + n);   // mu_head(h) + history_tail (:2079)
+            if (p.late) pre += __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h);   // (:2041-2047)
+            const float rt = softplus20f(pre) + 1e-6f;                                   // :2081-2085
+            reinterpret_cast<float*>(p.out)[o] = rt;
+            if (!isfinite(rt) || rt <= 0.f) bad |= 1;                                    // :2094
+          } else {
+            const float d = softplus20f(a) + fl + 1e-6f;                                 // :2088-2093
+            p.disp[o] = d;
+            if (!isfinite(d) || d <= 0.f) bad |= 2;                                      // :2096
+          }
         }
+        if (++h == p.head_steps) { h = 0; ++bwin; }
       }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
@@ -490,32 +512,52 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
   }
 }
 
-// same for any C: out [rows][3 Kp], columns c >= C of every plane are zero (K padding of the row GEMMs)
+// same for any C: out [rows][3 Kp], columns c >= C of every plane are zero (K padding of the row GEMMs).  A thread owns
+// eight consecutive columns of one row: eight coalesced 4-byte loads (rows of C floats are only 4-byte aligned), one
+// 16-byte store per plane.  PLANES = 2 leaves the lo plane unwritten (two-plane GEMMs never read it).
+template <int PLANES>
 __global__ void __launch_bounds__(256) split3_pad_kernel(const float* __restrict__ x, long long rows, int C, int Kp,
                                                         __nv_bfloat16* __restrict__ out) {
-  const long long total = rows * Kp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / Kp;
-    const int c = (int)(i - r * Kp);
-    const float v = c < C ? x[r * C + c] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-    __nv_bfloat16* dst = out + r * 3 * Kp + c;
-    dst[0] = h;
-    dst[Kp] = m;
-    dst[2 * Kp] = l;
+  const unsigned k8 = (unsigned)Kp >> 3;
+  const unsigned long long total = (unsigned long long)rows * k8;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long r;
+    unsigned j;
+    if (total <= 0xffffffffull) { const unsigned i32 = (unsigned)i; const unsigned r32 = i32 / k8; r = r32; j = i32 - r32 * k8; }
+    else { r = i / k8; j = (unsigned)(i - r * k8); }
+    const int c0 = (int)j * 8;
+    const float* src = x + r * C + c0;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = c0 + q < C ? src[q] : 0.f;
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = v[2 * q], b = v[2 * q + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+      const float ra = a - __bfloat162float(hh.x), rb = b - __bfloat162float(hh.y);
+      const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - __bfloat162float(mm.x), rb - __bfloat162float(mm.y));
+      h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+      m[q] = *reinterpret_cast<const uint32_t*>(&mm);
+      l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    __nv_bfloat16* dst = out + r * 3 * Kp + c0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst + Kp) = make_uint4(m[0], m[1], m[2], m[3]);
+    if (PLANES == 3) *reinterpret_cast<uint4*>(dst + 2 * Kp) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
-int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st) {
+int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st, int planes) {
   FTN_REQUIRE(Kp >= C && Kp % 16 == 0, "split3_pad: Kp=%d must be a multiple of 16 and >= C=%d", Kp, C);
-  const long long total = rows * Kp;
+  const long long total = rows * (Kp / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
-  split3_pad_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, C, Kp, out);
+  if (planes == 2) split3_pad_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, rows, C, Kp, out);
+  else split3_pad_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, rows, C, Kp, out);
   FTN_LAUNCH_CHECK("split3_pad_kernel");
   return 0;
 }
@@ -559,6 +601,7 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.rows_valid = a.rows_valid; k.aux = a.aux; k.aux_rows = a.aux_rows; k.gate = a.gate; k.out_bf16 = a.out_bf16;
   k.head_n = a.head_n; k.head_np = a.head_np; k.head_steps = a.head_steps; k.hist = a.hist; k.hist_stride = a.hist_stride; k.late = a.late;
   k.floor_n = a.floor_n; k.disp = a.disp; k.flags = a.flags;
+  k.planes = a.split_planes == 2 ? 2 : 3;
   FTN_REQUIRE(a.epi < TC_EPI_EMBED || (a.split && !a.plan && a.K2 == 0), "tc_gemm: the row-GEMM epilogues need split mode and no plan");
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);

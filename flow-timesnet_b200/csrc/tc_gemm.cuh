@@ -43,6 +43,8 @@ struct TcGemmArgs {
   // split != 0: fp32 activations as three bf16 planes (tc_gemm.cu).  a1 / a2 / w1 / w2 / out then are [rows][3 K] /
   // [rows][3 N] (a*_ld, ldo count ALL planes), x and a TC_RES_SEQ residual are the fp32 block input, a DELTA out is fp32.
   int split;
+  int split_planes;                           // 0 / 3: all three planes (6 products, fp32-accurate); 2: hi and mid only (3 products,
+                                              // 2^-16 relative) for results that are rounded to bf16 anyway
   // TC_EPI_EMBED / TC_EPI_NBHEAD (see tc_gemm.cu): rows_valid = rows of the GEMM that exist (the last tile is ragged)
   long long rows_valid;
   const float* aux; int aux_rows;             // EMBED: aux[(aux_rows ? row % aux_rows : row)][N]
@@ -52,7 +54,7 @@ struct TcGemmArgs {
   const float* hist; long long hist_stride; const float* late; const float* floor_n; float* disp; int32_t* flags;
 };
 // fp32 [rows][C] -> three bf16 planes [rows][3 Kp], Kp >= C a multiple of 16 (columns >= C are zero)
-int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st);
+int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st, int planes = 3);
 // fp32 [rows][C] -> three bf16 planes [rows][3 C] (tc_gemm.cu)
 int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call);
 // tc_dft.cu, MODE 1: hs[B * steps][3 C] = three bf16 planes of (Wt . seq_b + bt), seq bf16 [B][L][C], wt_s3 from ftn_time_proj_pack

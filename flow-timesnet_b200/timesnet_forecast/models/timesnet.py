@@ -1293,8 +1293,49 @@ class TimesNet(nn.Module):
             self._time_proj_cache = (key, packed)
         return self._time_proj_cache[1]
 
+    def _context_key(self, B: int, N: int, dev, series_static, series_ids):
+        """Identity of everything the per-series context and the late bias depend on (they do NOT depend on x): parameter
+        versions and the id tensor.  None = not cacheable (static features are per call)."""
+        if series_static is not None:
+            return None
+        mods = (self.series_embedding, self.context_norm, self.late_bias_norm, self.late_bias_head)
+        ps = [p for m in mods if isinstance(m, nn.Module) for p in m.parameters()]
+        # the id tensor is matched by OBJECT identity + version (the cache keeps it alive, so its address cannot be
+        # recycled for a different tensor); a fresh tensor per call simply misses
+        ids = None if series_ids is None else (id(series_ids), series_ids._version)
+        ref = self._series_id_reference
+        ref_key = None if ref is None else (ref.data_ptr(), ref._version)
+        return (B, N, str(dev), ids, ref_key if series_ids is None else None,
+                tuple((p.data_ptr(), p._version) for p in ps))
+
     def _context(self, B: int, N: int, dev, series_static, series_ids) -> Optional[torch.Tensor]:
         """Static projection + id embedding + context LayerNorm (timesnet.py:1886-1957)."""
+        key = self._context_key(B, N, dev, series_static, series_ids)
+        cache = getattr(self, "_ctx_cache", None)
+        if key is not None and cache is not None and cache[0] == key:
+            return cache[1]
+        ctx = self._context_compute(B, N, dev, series_static, series_ids)
+        # re-key after the call (it may have stored the id reference); never cache tensors born inside a graph capture
+        if key is not None and ctx is not None and not torch.cuda.is_current_stream_capturing():
+            self._ctx_cache = (self._context_key(B, N, dev, series_static, series_ids), ctx, series_ids)
+            self._late_cache = None
+        return ctx
+
+    def _late_bias(self, ctx: torch.Tensor) -> torch.Tensor:
+        """late_bias_head(late_bias_norm(ctx)) (timesnet.py:2028-2040); cached with the context it was computed from."""
+        cache = getattr(self, "_late_cache", None)
+        ctx_cache = getattr(self, "_ctx_cache", None)
+        cached_ctx = ctx_cache is not None and ctx_cache[1] is ctx
+        if cached_ctx and cache is not None and cache[0] is ctx:
+            return cache[1]
+        c = nv.layer_norm(ctx, self._f32(self.late_bias_norm.weight), self._f32(self.late_bias_norm.bias),
+                          self.late_bias_norm.eps)
+        late = nv.linear(c, self._f32(self.late_bias_head.weight), self._f32(self.late_bias_head.bias))
+        if cached_ctx and not torch.cuda.is_current_stream_capturing():
+            self._late_cache = (ctx, late)
+        return late
+
+    def _context_compute(self, B: int, N: int, dev, series_static, series_ids) -> Optional[torch.Tensor]:
         comps = []
         if self.static_proj is not None and series_static is not None:
             if series_static.ndim == 2:
@@ -1420,9 +1461,7 @@ class TimesNet(nn.Module):
             late = gate = None
             if (ctx is not None and self.late_bias_head is not None and self.late_bias_norm is not None
                     and isinstance(self.late_bias_gate, nn.Parameter)):
-                c = nv.layer_norm(ctx, self._f32(self.late_bias_norm.weight), self._f32(self.late_bias_norm.bias),
-                                  self.late_bias_norm.eps)
-                late = nv.linear(c, self._f32(self.late_bias_head.weight), self._f32(self.late_bias_head.bias))
+                late = self._late_bias(ctx)
                 gate = self._f32(self.late_bias_gate).reshape(-1)
             if isinstance(self.min_sigma_vector, torch.Tensor) and self.min_sigma_vector.numel() > 0:
                 floor = self.min_sigma_vector.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
