@@ -585,8 +585,10 @@ def run_native(args):
         roofline["chain_kernels"] = kernels
         hbm = []
         Fq = wl.T // 2 + 1
+        one_launch = (not recursive) and nv.dft_basis(feats[0]) is not None      # tensor-core search (csrc/tc_dft.cu)
         for name, ms_f, calls, per_call in (
-                ("spectrum_fft" if search["fft"][1] else "period_search (all kernels)",
+                ("period_search = tc_dft_kernel (spectrum GEMM + channel median + selection tail, ONE launch)" if one_launch
+                 else "spectrum_fft" if search["fft"][1] else "period_search (all kernels)",
                  *(search["fft"] if search["fft"][1] else (spec_ms, spec_calls)),
                  wl.B * wl.T * wl.d_model * e_bytes + 4 * wl.B * Fq),        # read x once + medians out
                 ("aggregate", agg_ms, agg_calls,
@@ -595,6 +597,15 @@ def run_native(args):
                 gbs = per_call / (ms_f / calls * 1e-3) / 1e9
                 hbm.append({"kernel": name, "achieved_GBs": gbs, "frac": gbs / float(peaks["hbm_gbs"]),
                             "avg_ms": ms_f / calls, "algorithmic_bytes": per_call})
+        if one_launch and hbm:
+            # SURVEY 8d classes K1 as HBM-bound (read x once); the one-launch search is not: its spectra take ~12 us
+            # (a tcgen05 GEMM against the three-plane DFT basis, L2-resident, plus a register-sort median) and the
+            # one-CTA selection tail another ~13 us of pure latency.  The GEMM's executed FLOPs are reported beside it.
+            mt = (Fq + 63) // 64
+            dft_flops = 2.0 * 3 * (mt * 128) * wl.T * wl.d_model * wl.B
+            hbm[0]["executed_TFLOPs"] = dft_flops / (hbm[0]["avg_ms"] * 1e-3) / 1e12
+            hbm[0]["note"] = ("latency-bound, not HBM-bound: eager CUDA-event time of the whole search (spectra + tail); "
+                              "profiles/ holds the in-graph timeline and the tail's phase trace")
         roofline["hbm_kernels"] = hbm
         roofline["search_kernels"] = [{"kernel": n, "avg_ms": ms_f / calls} for n, (ms_f, calls) in search.items() if calls]
         cpu_baseline = None
