@@ -169,7 +169,9 @@ FTN_API int ftn_select_periods(const float* amp_median, const float* amp_sum, in
                        int global_batch, int L, int k, int pmax, int min_period,
                        FtnPeriodPlan* plan, void* amps, float* weights /*[B][FTN_MAX_K]*/, void* stream);
 
-/* Fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the selection kernel (2 launches).
+/* Fast path: ftn_spectrum + ftn_select_periods with the batch sum folded into the selection kernel (2 launches; ONE
+ * with a DFT basis, see below -- that route keeps an atomic ticket in plan->reserved[2]: the plan buffer must be zero
+ * before its first use, and every search leaves the ticket zero again).
  * Same outputs as the pair: amp_median [B][F], amp_sum [F+1], plan, amps [B][k], weights [B][FTN_MAX_K].
  * peer_comm = NULL: single rank, nothing to reduce.  peer_comm = a communicator from ftn_peer_create / _connect: the
  * batch is sharded over its ranks and the selection kernel exchanges the F + 1 partial sums with the peers over NVLink
