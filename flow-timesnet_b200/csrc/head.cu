@@ -521,7 +521,7 @@ extern "C" int ftn_nb_head_tc(const void* seq, int dtype, int B, int L, int C, i
                               float* rate, float* disp, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
   FTN_REQUIRE(seq && Wt && bt && w_heads_s3 && b_heads && hist && floor_n && rate && disp && flags && workspace,
               "ftn_nb_head_tc: null pointer");
-  FTN_REQUIRE((late == nullptr) == (late_gate == nullptr), "ftn_nb_head_tc: late and late_gate must come together");
+  FTN_REQUIRE(late || !late_gate, "ftn_nb_head_tc: late_gate without late");
   FTN_REQUIRE(dtype == FTN_F32 || dtype == FTN_BF16, "ftn_nb_head_tc: unsupported dtype %d", dtype);
   FTN_REQUIRE(B > 0 && L > 0 && C > 0 && steps > 0 && N > 0, "ftn_nb_head_tc: bad sizes");
   if (C % 16 || N < 16) return -1;

@@ -63,6 +63,19 @@ struct TcGemmKernelArgs {
 
 // F.softplus(beta = 1, threshold = 20) in fp32 device math (timesnet.py:2081-2091)
 __device__ __forceinline__ float softplus20f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
+// The same for the NB-head epilogue, where log1pf(expf(v)) was ~50 of the ~90 instructions per element:
+//   softplus(v) = max(v, 0) + log1p(exp(-|v|)),  exp(-|v|) in (0, 1], 1 + e in (1, 2]
+// on MUFU.EX2 / MUFU.LG2 (absolute error ~2^-22 on the log term).  For v >= -3 the result is >= 0.0486, so that is
+// <= 5e-6 relative; smaller results (rare: rate pre-activations carry the non-negative history tail) keep the accurate
+// form so that tiny rates and dispersions stay relatively exact.
+__device__ __forceinline__ float softplus20_fast(float v) {
+  if (v > 20.0f) return v;
+  if (v < -3.0f) return log1pf(expf(v));
+  const float e = ex2_approx(-fabsf(v) * 1.4426950408889634f);
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+  return fmaf(l, 0.6931471805599453f, fmaxf(v, 0.0f));
+}
 
 // exact-erf GELU for the fp32 (SPLIT) epilogues: gelu_fast's A&S 7.1.26 erf is within 1.5e-7 absolute
 __device__ __forceinline__ float act_split(float v, int act) { return act == FTN_ACT_RELU ? fmaxf(v, 0.f) : gelu_fast(v); }
@@ -91,12 +104,14 @@ __device__ __forceinline__ void store_split16(__nv_bfloat16* dst, int plane_stri
 
 // STAGES: depth of the operand ring.  SPLIT stages are 96 KB; a stage count of 1 (used when the whole K loop is at most
 // two K blocks, e.g. the etth1-class 1x1 stages) lets two CTAs share an SM so one's epilogue overlaps the other's loads.
-template <bool SPLIT, int STAGES>
+// NPL: planes of each operand a stage holds (SPLIT).  3 = all (6 products).  2 = hi and mid only (3 products): a stage is
+// 64 KB, so THREE of them fit and the K loop is pipelined -- used where the result is rounded to bf16 anyway.
+template <bool SPLIT, int STAGES, int NPL = 3>
 __global__ void __launch_bounds__(256)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2,
                const TcGemmKernelArgs p) {
-  constexpr int STAGE_BYTES = SPLIT ? TC_SPLIT_STAGE_BYTES : TC_STAGE_BYTES;
+  constexpr int STAGE_BYTES = SPLIT ? 2 * NPL * TC_TILE_BYTES : TC_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -158,12 +173,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // ===== TMA producer: lanes 0 .. 2 NP - 1 each issue ONE box per K block =====
     // (a TMA issue costs ~400 cycles of the issuing thread whatever the box size -- six of them from one thread were
     // 2.4 k cycles per K block against 1.5 k cycles of MMAs)
-    constexpr int NP = SPLIT ? 3 : 1;
+    constexpr int NP = SPLIT ? NPL : 1;
     for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
       uint8_t* sa = smem + s * STAGE_BYTES;
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], SPLIT ? (uint32_t)(2 * p.planes) * TC_TILE_BYTES : (uint32_t)STAGE_BYTES);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
       __syncwarp();
       const bool ph2 = kb >= nkb1;
       const int k0 = (ph2 ? kb - nkb1 : kb) * TC_BK;
@@ -172,9 +187,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const CUtensorMap* mw = ph2 ? &tmW2 : &tmW1;
       // SPLIT: planes 0..2 of the activation, then planes 0..2 of the weights (plane p = columns [p K, (p + 1) K);
       // a box that runs past its plane / the tensor reads the next plane / zeros, which no MMA consumes)
-      if (SPLIT && lane % NP >= p.planes) {
-        // the lo plane is neither loaded nor multiplied in two-plane mode
-      } else if (lane < NP) {
+      if (lane < NP) {
         uint8_t* dst = sa + lane * TC_TILE_BYTES;
         if (ph2 ? p.a2_seq : p.a1_seq) tma_load_3d(dst, ma, &full[s], lane * K + k0, t0, b);
         else tma_load_2d(dst, ma, &full[s], lane * K + k0, tile_id * TC_BM);
@@ -206,8 +219,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint32_t accum = kbl != 0 ? 1u : 0u;
 #pragma unroll
           for (int pr = 0; pr < 6; ++pr) {
-            if (p.planes == 2 && PA[pr] + PW[pr] != 1 && pr != 5) continue;   // two planes: hi.mid, mid.hi, hi.hi
-            const uint32_t da = sa + PA[pr] * TILE16, dw = sa + (3 + PW[pr]) * TILE16;
+            if (NPL == 2 && PA[pr] + PW[pr] != 1 && pr != 5) continue;        // two planes: hi.mid, mid.hi, hi.hi
+            const uint32_t da = sa + PA[pr] * TILE16, dw = sa + (NPL + PW[pr]) * TILE16;
             for (int k = 0; k < ksteps; ++k) {
               if (elect_one()) mma_bf16_lohi(d, da + k * 2, kDescSw128Hi, dw + k * 2, kDescSw128Hi, idesc, accum);
               accum = 1u;
@@ -247,10 +260,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       tmem_ld_wait();
       if (!live) continue;
       const int n = n0 + c;
+      // a lane owns a ROW: its 16 aux values are 64 contiguous bytes -- four 16-byte loads (scalar loads were 16 requests
+      // of 32 sectors each per warp and made this epilogue the kernel's run time)
       float v[16];
+      const float4* gq = reinterpret_cast<const float4*>(p.gate + n);
+      const float4* aq = reinterpret_cast<const float4*>(p.aux + arow * p.N + n);
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        v[i] = __uint_as_float(vr[i]) + s_bias1[c + i] + __ldg(p.gate + n + i) * __ldg(p.aux + arow * p.N + n + i);
+      for (int i = 0; i < 4; ++i) {
+        const float4 g4 = __ldg(gq + i), a4 = __ldg(aq + i);
+        v[4 * i + 0] = __uint_as_float(vr[4 * i + 0]) + s_bias1[c + 4 * i + 0] + g4.x * a4.x;
+        v[4 * i + 1] = __uint_as_float(vr[4 * i + 1]) + s_bias1[c + 4 * i + 1] + g4.y * a4.y;
+        v[4 * i + 2] = __uint_as_float(vr[4 * i + 2]) + s_bias1[c + 4 * i + 2] + g4.z * a4.z;
+        v[4 * i + 3] = __uint_as_float(vr[4 * i + 3]) + s_bias1[c + 4 * i + 3] + g4.w * a4.w;
+      }
       if (p.out_bf16) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.N + n);
         dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -287,25 +309,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const float fl = (!is_rate && col_ok) ? __ldg(p.floor_n + n) : 0.f;
       int h = (int)(pr0 % (size_t)p.head_steps);
       size_t bwin = pr0 / (size_t)p.head_steps;
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const size_t prow = pr0 + rr;
-        if (col_ok && (long long)prow < p.rows_valid) {
-          const float a = T[rr * 33 + lane] + bias;
-          const size_t o = prow * p.head_n + n;
-          if (is_rate) {
-            float pre = a + __ldg(p.hist + bwin * p.hist_stride + (size_t)h * p.head_n + n);   // mu_head(h) + history_tail (:2079)
-            if (p.late) pre += __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h);   // (:2041-2047)
-            const float rt = softplus20f(pre) + 1e-6f;                                   // :2081-2085
-            reinterpret_cast<float*>(p.out)[o] = rt;
-            if (!isfinite(rt) || rt <= 0.f) bad |= 1;                                    // :2094
-          } else {
-            const float d = softplus20f(a) + fl + 1e-6f;                                 // :2088-2093
-            p.disp[o] = d;
-            if (!isfinite(d) || d <= 0.f) bad |= 2;                                      // :2096
+      // running element pointers (one 64-bit add per row instead of two multiplies)
+      float* dst = (is_rate ? reinterpret_cast<float*>(p.out) : p.disp) + pr0 * p.head_n + n;
+      const float* hp = p.hist + bwin * p.hist_stride + (size_t)h * p.head_n + n;
+      const float* lp = (p.late && !p.gate) ? p.late + pr0 * p.head_n + n : nullptr;
+      const int rows_here = (long long)pr0 + 32 <= p.rows_valid ? 32 : (int)max(0ll, p.rows_valid - (long long)pr0);
+      // eight rows at a time: their history / late-bias loads are issued together BEFORE the math (every load is an L2
+      // or HBM round trip with nothing to reuse; one row per iteration left 16 warps per SM waiting on them: 80 us)
+#pragma unroll 1
+      for (int r0 = 0; r0 < rows_here; r0 += 8) {
+        float hv[8], lv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = is_rate && col_ok && r0 + j < rows_here;
+          hv[j] = ok ? __ldg(hp) : 0.f;                                                 // history_tail (:2079)
+          // late bias (:2041-2047): gate[h] * late[b][n][h], or -- gate == NULL -- the caller's pre-gated step-major
+          // copy late_t[b][h][n] = gate[h] * late[b][n][h], indexed like the output (coalesced)
+          lv[j] = !(ok && p.late) ? 0.f
+                  : (p.gate ? __ldg(p.gate + h) * __ldg(p.late + (bwin * p.head_n + n) * p.head_steps + h) : __ldg(lp));
+          hp += p.head_n;
+          if (lp) lp += p.head_n;
+          if (++h == p.head_steps) { h = 0; ++bwin; hp = p.hist + bwin * p.hist_stride + n; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (col_ok && r0 + j < rows_here) {
+            const float a = T[(r0 + j) * 33 + lane] + bias;
+            if (is_rate) {
+              const float rt = softplus20_fast(a + hv[j] + lv[j]) + 1e-6f;               // :2079-2085
+              dst[(size_t)j * p.head_n] = rt;
+              if (!(rt > 0.f && rt <= 3.4028235e38f)) bad |= 1;                          // :2094 (NaN, inf, <= 0)
+            } else {
+              const float d = softplus20_fast(a) + fl + 1e-6f;                           // :2088-2093
+              dst[(size_t)j * p.head_n] = d;
+              if (!(d > 0.f && d <= 3.4028235e38f)) bad |= 2;                            // :2096
+            }
           }
         }
-        if (++h == p.head_steps) { h = 0; ++bwin; }
+        dst += (size_t)8 * p.head_n;
       }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
@@ -612,7 +653,13 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
     (void)nkb;
     // ONE 96 KB stage per CTA and two CTAs per SM: while one CTA's MMAs run the other loads its K block or drains its
     // accumulator (a 2-stage CTA owns the SM alone and its prologue and epilogue leave the tensor pipe idle)
-    if (!two_stage) {
+    if (k.planes == 2) {
+      // two-plane stages are 64 KB: a 3-deep ring pipelines the K loop (the embedding has six K blocks; with one stage
+      // every block paid a full TMA round trip: 36 us for a 12 us kernel)
+      constexpr int smem3 = 3 * 4 * TC_TILE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
+      FTN_DYN_SMEM((tc_gemm_kernel<true, 3, 2>), smem3);
+      tc_gemm_kernel<true, 3, 2><<<grid, 256, smem3, st>>>(mA1, mW1, mA2, mW2, k);
+    } else if (!two_stage) {
       constexpr int smem1 = TC_SPLIT_STAGE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
       FTN_DYN_SMEM((tc_gemm_kernel<true, 1>), smem1);
       tc_gemm_kernel<true, 1><<<grid, 256, smem1, st>>>(mA1, mW1, mA2, mW2, k);

@@ -1335,6 +1335,19 @@ class TimesNet(nn.Module):
             self._late_cache = (ctx, late)
         return late
 
+    def _late_bias_gated_t(self, late: torch.Tensor, gate: torch.Tensor) -> Optional[torch.Tensor]:
+        """``gate[h] * late[b, n, h]`` as a step-major ``[B, steps, N]`` tensor (the layout of the head's output, so the
+        tensor-core head reads it coalesced) -- a cached repack of the cached late bias, like the weight packs.  None
+        when the late bias is not the cached one (per-call static features)."""
+        cache = getattr(self, "_late_cache", None)
+        if cache is None or cache[1] is not late or torch.cuda.is_current_stream_capturing() and len(cache) < 4:
+            return None
+        gkey = (self.late_bias_gate.data_ptr(), self.late_bias_gate._version)
+        if len(cache) < 4 or cache[2] != gkey:
+            packed = (late * gate.view(1, 1, -1)).transpose(1, 2).contiguous()
+            self._late_cache = (cache[0], late, gkey, packed)
+        return self._late_cache[3]
+
     def _context_compute(self, B: int, N: int, dev, series_static, series_ids) -> Optional[torch.Tensor]:
         comps = []
         if self.static_proj is not None and series_static is not None:
@@ -1474,7 +1487,9 @@ class TimesNet(nn.Module):
             res = None
             if self.d_model % 16 == 0 and N >= 16:
                 w_heads, b_heads, n_pad = self._heads_split(dev)
-                res = nv.nb_head_tc(seq, steps, N, Wt, bt, w_heads, b_heads, n_pad, hist, late, gate, floor, flags,
+                late_t = self._late_bias_gated_t(late, gate) if late is not None else None
+                res = nv.nb_head_tc(seq, steps, N, Wt, bt, w_heads, b_heads, n_pad, hist,
+                                    late if late_t is None else late_t, gate if late_t is None else None, floor, flags,
                                     wt_s3=self._time_proj_split(Wt, steps, dev))
             if res is None:
                 res = nv.nb_head(seq, steps, N, Wt, bt, self._f32(self.mu_head.weight),

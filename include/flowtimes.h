@@ -344,6 +344,8 @@ FTN_API int ftn_nb_head(const void* seq, int dtype, int B, int L, int C, int ste
 /* Same head with mu_head and sigma_head as ONE tensor-core GEMM (three-plane fp32 split) whose epilogue does the
  * softplus / floor / finite checks.  w_heads_s3: bf16 [2 Np][3 C], rows [0, N) = split mu_head.weight, rows
  * [Np, Np + N) = split sigma_head.weight, other rows zero; b_heads: [2 Np] fp32 likewise; Np a multiple of 128.
+ * late_gate == NULL with late != NULL: late is the caller's PRE-GATED, step-major copy late_t[B][steps][N] =
+ * gate[h] * late[b][n][h] (it depends on parameters and ids only, so callers cache it; it loads coalesced).
  * wt_s3: NULL, or Wt packed by ftn_time_proj_pack: with a bf16 seq and C in {64, 128, 256} the time projection then runs
  * on tcgen05 too (seq[b] is an MN-major operand; csrc/tc_dft.cu MODE 1) and writes the split hidden directly.
  * Returns -1 (nothing enqueued) when C % 16 != 0 or N < 16. */
