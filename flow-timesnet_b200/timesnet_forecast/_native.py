@@ -388,9 +388,11 @@ def timesblock_fused(x: torch.Tensor, plan_dev: torch.Tensor, max_groups: int, w
 
 def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: FtnInceptionWeights,
                        wb: FtnInceptionWeights, act: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
-                       eps: float, comm: Optional["PeerComm"] = None):
+                       eps: float, comm: Optional["PeerComm"] = None, plan: Optional[torch.Tensor] = None):
     """Period search + fused TimesBlock in one call (the first 1x1 stage overlaps the search).
 
+    ``plan``: a plan buffer to reuse (zero before its FIRST use -- every search leaves its ticket zero and rewrites the
+    rest), which saves the fill kernel of a fresh ``new_plan`` per call.
     Returns None when the configuration is not eligible (nothing was enqueued), else
     (out, plan, amps[B,k], weights[B,16])."""
     lib = load()
@@ -398,7 +400,8 @@ def timesblock_forward(x: torch.Tensor, k: int, pmax: int, min_period: int, wa: 
     Fq = L // 2 + 1
     med = torch.empty(B, Fq, dtype=torch.float32, device=x.device)
     ssum = torch.empty(Fq + 1, dtype=torch.float32, device=x.device)
-    plan = new_plan(x.device)
+    if plan is None:
+        plan = new_plan(x.device)
     amps = torch.empty(B, k, dtype=x.dtype, device=x.device)
     weights = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=x.device)
     sbytes = lib.ftn_spectrum_workspace_bytes(B, L, Cc)

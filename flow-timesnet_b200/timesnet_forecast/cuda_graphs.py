@@ -56,7 +56,9 @@ class GraphedCallable:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        # capture on the warm-up stream: per-(device, stream) state the modules created while warming up (the zeroed
+        # plan buffers of the TimesBlocks) is found again during the capture instead of being re-created inside it
+        with torch.cuda.graph(self._graph, stream=side):
             self._static_out = fn(*self._static_in)
         self._captured_fp = self._fingerprint()
         self.captures += 1

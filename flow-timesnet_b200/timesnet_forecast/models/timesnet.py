@@ -684,8 +684,16 @@ class TimesBlock(nn.Module):
             self.inception = self.inception.to(x.device)
         pa = self.inception[0].packed(x.device)
         pb = self.inception[2].packed(x.device)
+        # one plan buffer per (block, device, stream), zeroed once: the search rewrites it completely and leaves its
+        # ticket zero, so no fill kernel per call (never a buffer born inside a graph capture)
+        bufs = self.__dict__.setdefault("_plan_bufs", {})
+        pkey = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+        plan_buf = bufs.get(pkey)
+        if plan_buf is None and not torch.cuda.is_current_stream_capturing():
+            plan_buf = bufs[pkey] = nv.new_plan(x.device)
         res = nv.timesblock_forward(x, k, sel.pmax, sel.min_period_threshold, pa.struct, pb.struct,
-                                    _act_code(self._activation_name), ln_w, ln_b, eps, sel.peer_comm if world > 1 else None)
+                                    _act_code(self._activation_name), ln_w, ln_b, eps, sel.peer_comm if world > 1 else None,
+                                    plan=plan_buf)
         if res is None:
             return None
         out, plan_dev, amps, weights = res
