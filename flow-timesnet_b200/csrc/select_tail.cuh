@@ -36,27 +36,33 @@ __device__ __forceinline__ unsigned long long rank_key(float score, int f) {
 // lowest index on ties).  No dependent loops: duplicates are found with match.any, the canonical member with a
 // masked max-reduction, and the group order with sixteen independent shuffles -- this runs in ONE warp on the
 // critical path of every block (the rolled shuffle loops it replaces took 5 us of latency).
+// `pad` / `cyc` (cyc = 0: the grouper drops the candidate) come from the per-bin table the scores pass fills in parallel:
+// the five integer divisions per candidate were ~2 k cycles of dependent latency in this one warp.
 __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int my_p /*period of candidate lane, 0 = none*/,
-                                                float my_amp, int nv, int L, int min_p, int max_p) {
-  bool v = lane < nv && my_p > 0;
-  if (min_p > 0 && my_p < min_p) v = false;
-  if (max_p > 0 && my_p > max_p) v = false;
-  int pad = 0, cyc = 0;
-  if (v) {
-    pad = (my_p - (L % my_p)) % my_p;
-    cyc = (L + pad) / my_p;
-    if (cyc < 2) v = false;
-  }
-  // lanes that are not valid candidates get distinct negative keys: each is alone in its match group
-  const int key = v ? my_p : -1 - lane;
-  const unsigned same = __match_any_sync(0xffffffffu, key);
-  const bool first = v && (lane == __ffs(same) - 1);            // lowest lane holding this period
-  // canonical member of the group: largest mean amplitude (NaN counts as largest), lowest index on ties
+                                                float my_amp, int nv, int L, int pad, int cyc) {
+  const bool v = lane < nv && my_p > 0 && cyc >= 2;
+  // Duplicates and the canonical member (largest mean amplitude -- NaN counts as largest --, lowest index on ties) in
+  // ONE unrolled pass of full-mask shuffles.  (match.any + redux / ballot on the per-group masks looked shorter, but a
+  // collective on a partial mask runs once per distinct mask -- up to 32 serialised WARPSYNC.EXCLUSIVE rounds: 3 us.)
+  const int key = v ? my_p : -1 - lane;                          // invalid lanes: distinct keys, alone in their group
   const uint32_t au = __float_as_uint(my_amp + 0.0f);
   uint32_t akey = (au & 0x80000000u) ? ~au : (au | 0x80000000u);
   if (my_amp != my_amp) akey = 0xffffffffu;
-  const uint32_t amax = __reduce_max_sync(same, akey);
-  const int canon = __ffs(__ballot_sync(same, akey == amax)) - 1;
+  unsigned same = 0;
+  int canon = -1;
+  uint32_t best = 0;
+#pragma unroll
+  for (int j = 0; j < FTN_MAX_K; ++j) {
+    const int kj = __shfl_sync(0xffffffffu, key, j);
+    const uint32_t aj = __shfl_sync(0xffffffffu, akey, j);
+    // selects, not branches: a data-dependent branch between two shuffles costs a divergence + reconvergence round
+    const bool eq = kj == key;
+    const bool take = eq && (canon < 0 || aj > best);
+    same |= eq ? (1u << j) : 0u;
+    canon = take ? j : canon;
+    best = take ? aj : best;
+  }
+  const bool first = v && (lane == __ffs(same) - 1);            // lowest lane holding this period
   // group order: ascending period; row offset = lengths of the groups in front
   const int pf = first ? my_p : 0x7fffffff;
   const int len = first ? L + pad : 0;
@@ -65,7 +71,9 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   for (int j = 0; j < FTN_MAX_K; ++j) {
     const int pj = __shfl_sync(0xffffffffu, pf, j);
     const int lj = __shfl_sync(0xffffffffu, len, j);
-    if (pj < my_p) { ++rank; off += lj; }
+    const bool before = pj < my_p;
+    rank += before ? 1 : 0;
+    off += before ? lj : 0;
     total += lj;
   }
   const int G = __popc(__ballot_sync(0xffffffffu, first));
@@ -104,8 +112,9 @@ struct SelShared {
 
 // floats of dynamic shared memory select_tail needs at `sf`
 __host__ __device__ inline size_t select_tail_floats(int F, int do_sum) {
-  //  s_sum [F + 1] (+1 pad)  |  keys [F] u64 = 2 F floats  |  s_part [32][F] (do_sum) or rank counters [F]
-  return (size_t)(F + 2) + 2 * (size_t)F + (size_t)(do_sum ? 32 * F : F);
+  //  s_sum [F + 1] (+1 pad)  |  keys [F] u64 = 2 F floats  |  s_part [32][F] (do_sum), later rank counters [F] + the
+  //  per-bin period / pad / cycles table [3][F]
+  return (size_t)(F + 2) + 2 * (size_t)F + (size_t)(do_sum ? 32 * F : 4 * F);
 }
 
 // All threads of one CTA call this (blockDim.x a multiple of 32, >= kSelFinishThreads).  amp_median / sum_src are read
@@ -195,15 +204,36 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
   __syncthreads();
   FTN_TAIL_MARK(3);
 
-  // scores in the activation dtype, exactly as timesnet.py:119-130
+  // scores in the activation dtype, exactly as timesnet.py:119-130 -- and, in the same parallel pass, the period math of
+  // EVERY bin (timesnet.py:137-154 and the grouper's pad / cycles, :286-325): the top-k candidates then only look theirs up
   const float gb = global_batch > 0 ? (float)global_batch : s_sum[F];
+  int* s_bper = reinterpret_cast<int*>(s_part) + F;      // period the selector assigns to bin f (0 = dropped)
+  int* s_bpad = s_bper + F;                               // grouper: (-L) mod p
+  int* s_bcyc = s_bpad + F;                               // grouper: (L + pad) / p, 0 = dropped by the grouper
+  __syncthreads();                                        // the fold above has finished reading s_part
+  {
+    const int upper = min(pmax, max(1, L - 1)), lower = min_period;
 #pragma unroll 1
-  for (int f = tid; f < F; f += nthr) {
-    const float m = round_to<T>(s_sum[f] / gb);
-    const float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
-    float sc = round_to<T>(m - pen);
-    if (f == 0) sc = -CUDART_INF_F;
-    s_key[f] = rank_key(sc, f);
+    for (int f = tid; f < F; f += nthr) {
+      const float m = round_to<T>(s_sum[f] / gb);
+      const float pen = round_to<T>(1e-8f * round_to<T>(log1pf((float)f)));
+      float sc = round_to<T>(m - pen);
+      if (f == 0) sc = -CUDART_INF_F;
+      s_key[f] = rank_key(sc, f);
+      const int safe = max(f, 1);
+      int per = 0, pad = 0, cyc = 0;
+      if (upper >= lower) {
+        int p = (L + safe - 1) / safe;
+        p = p < lower ? lower : (p > upper ? upper : p);
+        if ((L + p - 1) / p >= 2) per = p;
+      }
+      if (per > 0 && !(min_period > 0 && per < min_period) && !(pmax > 0 && per > pmax)) {
+        pad = (per - (L % per)) % per;
+        cyc = (L + pad) / per;
+        if (cyc < 2) cyc = 0;
+      }
+      s_bper[f] = per; s_bpad[f] = pad; s_bcyc[f] = cyc;
+    }
   }
   __syncthreads();
   const int kk = min(k, F - 1);
@@ -234,18 +264,13 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
   __syncthreads();
   FTN_TAIL_MARK(4);
   if (warp == 0) {
-    // period math for candidate `lane` (timesnet.py:137-154), then the cooperative grouping
-    const int upper = min(pmax, max(1, L - 1));
-    const int lower = min_period;
+    // candidate `lane` looks its period up (table above), then the cooperative grouping
     int safe = 0, per = 0;
     bool keep = false;
     if (lane < kk) {
       safe = max(sh->top[lane], 1);
-      if (upper >= lower) {
-        int p = (L + safe - 1) / safe;
-        p = p < lower ? lower : (p > upper ? upper : p);
-        if ((L + p - 1) / p >= 2) { keep = true; per = p; }
-      }
+      per = s_bper[safe];
+      keep = per > 0;
     }
     // compact the kept candidates in rank order: position = number of kept lanes below
     const unsigned kept = __ballot_sync(0xffffffffu, keep);
@@ -261,9 +286,10 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
     if (keep) { sh->plan.freq[pos] = safe; sh->plan.period[pos] = per; }
     if (lane == 0) { sh->plan.n_raw = kk; sh->plan.n_valid = nv; }
     __syncwarp();
+    const int my_f = lane < nv ? (int)sh->plan.freq[lane] : 0;
     const int my_p = lane < nv ? (int)sh->plan.period[lane] : 0;
-    const float my_amp = lane < nv ? s_sum[(int)sh->plan.freq[lane]] : 0.f;
-    plan_group_warp(&sh->plan, lane, my_p, my_amp, nv, L, min_period, pmax);
+    const float my_amp = lane < nv ? s_sum[my_f] : 0.f;
+    plan_group_warp(&sh->plan, lane, my_p, my_amp, nv, L, s_bpad[my_f], s_bcyc[my_f]);
   }
   __syncthreads();
   FTN_TAIL_MARK(5);
@@ -294,11 +320,14 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
       }
       float den = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < nv; ++j)
-        if (sh->plan.mapping[j] >= 0) den += expf(sh->e[j][tid] - mx);
+      for (int j = 0; j < nv; ++j) {                        // one expf per candidate (w is free until the scatter below)
+        const float ex = expf(sh->e[j][tid] - mx);
+        sh->w[j][tid] = ex;
+        if (sh->plan.mapping[j] >= 0) den += ex;
+      }
 #pragma unroll 1
       for (int j = 0; j < nv; ++j)
-        sh->e[j][tid] = round_to<T>(expf(sh->e[j][tid] - mx) / den);     // softmax fp32 -> dtype (timesnet.py:1000)
+        sh->e[j][tid] = round_to<T>(sh->w[j][tid] / den);                // softmax fp32 -> dtype (timesnet.py:1000)
 #pragma unroll
       for (int g = 0; g < FTN_MAX_K; ++g) sh->w[g][tid] = 0.f;
 #pragma unroll 1

@@ -75,7 +75,7 @@ __device__ __forceinline__ void sort_regs(float (&v)[N]) {
 // writes the per-window amplitudes / weights -- the whole period search is ONE launch.
 // FLOWTIMES_DFT_TRACE: globaltimer marks of the last launch (0 kernel start of CTA 0, 1 ticket taken by the last CTA,
 // 2..6 the tail's phases), read back with ftn_debug_dft_trace
-__device__ unsigned long long g_dft_trace[8];
+__device__ unsigned long long g_dft_trace[16];
 
 struct DftTail {
   int enabled;
@@ -326,6 +326,13 @@ tc_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   select_tail<__nv_bfloat16>(med, tail.amp_sum, 1, med, B, B, tail.do_finish, tail.global_batch, L, tail.k, tail.pmax,
                              tail.min_period, tail.plan, tail.amps, tail.weights, tail.peer, sf, sh,
                              tail.trace ? g_dft_trace : nullptr);
+  if (tail.trace & 2) {   // experiment (FLOWTIMES_DFT_TRACE=2): the same tail once more, warm -- how much of it is cold code?
+    __syncthreads();
+    if (threadIdx.x == 0) g_dft_trace[7] = g_dft_trace[6];
+    __syncthreads();
+    select_tail<__nv_bfloat16>(med, tail.amp_sum, 1, med, B, B, tail.do_finish, tail.global_batch, L, tail.k, tail.pmax,
+                               tail.min_period, tail.plan, tail.amps, tail.weights, tail.peer, sf, sh, g_dft_trace);
+  }
 }
 
 // basis[plane][row][t], row = m * 128 + q * 32 + l:  bin f = 64 m + 32 (q / 2) + l, q even = cos, q odd = sin;
@@ -525,10 +532,10 @@ int tc_dft_launch(const void* x, int B, int L, int C, const void* basis, float* 
 int tc_dft_search_launch(const void* x, int B, int L, int C, const void* basis, float* med, float* amp_sum, int do_finish,
                          int global_batch, int k, int pmax, int min_period, FtnPeriodPlan* plan, void* amps, float* weights,
                          const void* comm, cudaStream_t st) {
-  static const bool trace = getenv("FLOWTIMES_DFT_TRACE") != nullptr;
+  static const int trace = getenv("FLOWTIMES_DFT_TRACE") ? (atoi(getenv("FLOWTIMES_DFT_TRACE")) == 2 ? 3 : 1) : 0;
   DftTail tail{};
   tail.enabled = 1;
-  tail.trace = trace ? 1 : 0;
+  tail.trace = trace;
   tail.amp_sum = amp_sum; tail.do_finish = do_finish; tail.global_batch = global_batch;
   tail.k = k; tail.pmax = pmax; tail.min_period = min_period;
   tail.plan = plan; tail.amps = reinterpret_cast<__nv_bfloat16*>(amps); tail.weights = weights;
@@ -543,9 +550,9 @@ int tc_dft_search_launch(const void* x, int B, int L, int C, const void* basis, 
 
 using namespace ftn;
 
-extern "C" int ftn_debug_dft_trace(unsigned long long* out8) {
-  FTN_REQUIRE(out8, "ftn_debug_dft_trace: null pointer");
-  FTN_CUDA(cudaMemcpyFromSymbol(out8, g_dft_trace, sizeof(unsigned long long) * 8));
+extern "C" int ftn_debug_dft_trace(unsigned long long* out16) {
+  FTN_REQUIRE(out16, "ftn_debug_dft_trace: null pointer");
+  FTN_CUDA(cudaMemcpyFromSymbol(out16, g_dft_trace, sizeof(unsigned long long) * 16));
   return 0;
 }
 

@@ -195,7 +195,7 @@ FTN_API int ftn_time_proj_pack(const float* Wt, int steps, int L, void* out, siz
 
 /* diagnostic (FLOWTIMES_DFT_TRACE=1): %globaltimer marks of the last one-launch search on the current device:
  * [0] kernel start, [1] last CTA took the ticket, [2..6] tail phases (start, sums, ranks, plan, per-window finish) */
-FTN_API int ftn_debug_dft_trace(unsigned long long* out8);
+FTN_API int ftn_debug_dft_trace(unsigned long long* out16);
 FTN_API size_t ftn_dft_basis_bytes(int L);
 FTN_API int ftn_dft_basis_build(int L, void* basis, size_t basis_bytes, void* stream);
 

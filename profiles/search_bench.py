@@ -41,8 +41,12 @@ if __import__("os").environ.get("FLOWTIMES_DFT_TRACE"):
     for rep in range(3):
         nv.period_search(xs[rep], k, L, 1)
         torch.cuda.synchronize()
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 16)()
         lib.ftn_debug_dft_trace(buf)
         t = list(buf)
         names = ["start", "ticket", "tail0", "sums", "ranks", "plan", "finish"]
-        print("trace (us from kernel start): " + "  ".join(f"{n}={(t[i] - t[0]) / 1e3:.2f}" for i, n in enumerate(names)))
+        if __import__("os").environ["FLOWTIMES_DFT_TRACE"] == "2":      # marks 2..6 belong to the second (warm) run
+            print(f"first tail ends {(t[7] - t[0]) / 1e3:.2f} us; warm re-run: " +
+                  "  ".join(f"{n}={(t[i] - t[7]) / 1e3:.2f}" for i, n in enumerate(names) if i >= 2))
+        else:
+            print("trace (us from kernel start): " + "  ".join(f"{n}={(t[i] - t[0]) / 1e3:.2f}" for i, n in enumerate(names)))
