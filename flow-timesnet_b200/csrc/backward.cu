@@ -172,6 +172,94 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, long long sA, const float* 
   }
 }
 
+
+// ---- second slice: the pieces of the Inception chain and of the aggregation ----------------------------------------
+// activation forward / backward, elementwise (exact erf GELU -- nn.GELU() default, timesnet.py:643 -- or ReLU)
+__global__ void act_forward_kernel(const float* __restrict__ x, long long n, int act, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = apply_act(x[i], act);
+}
+__global__ void act_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long n, int act,
+                                    float* __restrict__ dx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    float d;
+    if (act == FTN_ACT_RELU) d = v > 0.f ? 1.f : 0.f;
+    else d = 0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);   // Phi + x phi
+    dx[i] = dy[i] * d;
+  }
+}
+
+// Weight gradient of one Conv2d on a folded grid (the backward of ftn_conv2d_grid, ONE period group of period W and
+// H = L / W cycles, zero "same" padding):
+//   dW[tap][c][n] = sum_{b, r, w} x[b][(r + dr - ph) W + (w + dw - pw)][c] * dy[b][r W + w][n]     (taps outside the grid: 0)
+//   db[n]         = sum_{b, t} dy[b][t][n]
+// One CTA per (tap, 16 x 16 tile of (c, n)): a tiled GEMM x_shifted^T . dy over the B * L positions.
+__global__ void __launch_bounds__(256)
+conv2d_grid_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int L, int W, int cin, int cout,
+                         int kh, int kw, float* __restrict__ dw) {
+  __shared__ float Xs[16][17], Ys[16][17];
+  const int tap = blockIdx.z, dr = tap / kw - kh / 2, dc = tap % kw - kw / 2;
+  const int H = L / W;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+  const long long P = (long long)B * L;
+  float acc = 0.f;
+  for (long long p0 = 0; p0 < P; p0 += 16) {
+    {   // row ty of this chunk: position p0 + ty; Xs[ty][tx] = shifted x at channel c0 + tx, Ys[ty][tx] = dy at n0 + tx
+      const long long pp = p0 + ty;
+      float xv = 0.f, yv = 0.f;
+      if (pp < P) {
+        const int b = (int)(pp / L), t = (int)(pp - (long long)b * L);
+        const int r = t / W + dr, w = t % W + dc;
+        if (r >= 0 && r < H && w >= 0 && w < W && c0 + tx < cin) xv = x[((size_t)b * L + (size_t)r * W + w) * cin + c0 + tx];
+        if (n0 + tx < cout) yv = dy[(size_t)pp * cout + n0 + tx];
+      }
+      Xs[ty][tx] = xv;
+      Ys[ty][tx] = yv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(Xs[k][ty], Ys[k][tx], acc);
+    __syncthreads();
+  }
+  if (c0 + ty < cin && n0 + tx < cout) dw[((size_t)tap * cin + c0 + ty) * cout + n0 + tx] = acc;
+}
+
+// Backward of out = x + sum_g w[b][g] * delta_g (ftn_aggregate without LayerNorm; timesnet.py:1075-1099, :818), fp32:
+//   d_x = d_out,  d_delta_g[b][t][c] = w[b][g] d_out[b][t][c],  d_w[b][g] = sum_{t, c} d_out[b][t][c] delta_g[b][t][c]
+// One CTA per (window, group); d_w slots of unused groups are zeroed.
+__global__ void __launch_bounds__(256)
+aggregate_backward_kernel(const float* __restrict__ d_out, const float* __restrict__ delta, const float* __restrict__ weights,
+                          const FtnPeriodPlan* __restrict__ plan, int B, int L, int C, float* __restrict__ d_delta,
+                          float* __restrict__ d_weights) {
+  const int b = blockIdx.x, g = blockIdx.y;
+  const int G = plan->n_groups;
+  if (g >= G) {
+    if (threadIdx.x == 0) d_weights[(size_t)b * FTN_MAX_K + g] = 0.f;
+    return;
+  }
+  const float w = weights[(size_t)b * FTN_MAX_K + g];
+  const size_t n = (size_t)L * C;
+  const float* go = d_out + (size_t)b * n;
+  const float* dl = delta + ((size_t)g * B + b) * n;
+  float* dd = d_delta + ((size_t)g * B + b) * n;
+  float s = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gv = go[i];
+    dd[i] = w * gv;
+    s = fmaf(gv, dl[i], s);
+  }
+  __shared__ float ss[256];
+  ss[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) ss[threadIdx.x] += ss[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) d_weights[(size_t)b * FTN_MAX_K + g] = ss[0];
+}
+
 }  // namespace ftn
 
 using namespace ftn;
@@ -235,5 +323,47 @@ extern "C" int ftn_gemm_f32(const float* A, int lda, int64_t stride_a, int trans
   else if (trans_b) gemm_tn_kernel<false, true><<<grid, 256, 0, st>>>(A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c, M, N, K, accumulate);
   else gemm_tn_kernel<false, false><<<grid, 256, 0, st>>>(A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c, M, N, K, accumulate);
   FTN_LAUNCH_CHECK("gemm_tn_kernel");
+  return 0;
+}
+
+extern "C" int ftn_act_forward(const float* x, int64_t n, int act, float* y, void* stream) {
+  FTN_REQUIRE(x && y, "ftn_act_forward: null pointer");
+  FTN_REQUIRE(n > 0 && (act == FTN_ACT_GELU || act == FTN_ACT_RELU), "ftn_act_forward: bad arguments");
+  long long blocks = (n + 255) / 256;
+  blocks = blocks > 4096 ? 4096 : blocks;
+  act_forward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n, act, y);
+  FTN_LAUNCH_CHECK("act_forward_kernel");
+  return 0;
+}
+
+extern "C" int ftn_act_backward(const float* x, const float* dy, int64_t n, int act, float* dx, void* stream) {
+  FTN_REQUIRE(x && dy && dx, "ftn_act_backward: null pointer");
+  FTN_REQUIRE(n > 0 && (act == FTN_ACT_GELU || act == FTN_ACT_RELU), "ftn_act_backward: bad arguments");
+  long long blocks = (n + 255) / 256;
+  blocks = blocks > 4096 ? 4096 : blocks;
+  act_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, dy, n, act, dx);
+  FTN_LAUNCH_CHECK("act_backward_kernel");
+  return 0;
+}
+
+extern "C" int ftn_conv2d_grid_backward_weight(const float* x, const float* dy, int B, int L, int period, int cin, int cout,
+                                               int kh, int kw, float* dw, void* stream) {
+  FTN_REQUIRE(x && dy && dw, "ftn_conv2d_grid_backward_weight: null pointer");
+  FTN_REQUIRE(B > 0 && L > 0 && period > 0 && L % period == 0 && cin > 0 && cout > 0,
+              "ftn_conv2d_grid_backward_weight: bad sizes B=%d L=%d period=%d", B, L, period);
+  FTN_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1) && kh * kw <= 65535, "ftn_conv2d_grid_backward_weight: kernel %dx%d must be odd", kh, kw);
+  dim3 grid((cout + 15) / 16, (cin + 15) / 16, kh * kw);
+  conv2d_grid_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dy, B, L, period, cin, cout, kh, kw, dw);
+  FTN_LAUNCH_CHECK("conv2d_grid_wgrad_kernel");
+  return 0;
+}
+
+extern "C" int ftn_aggregate_backward(const float* d_out, const float* delta, const float* weights, const FtnPeriodPlan* plan,
+                                      int B, int L, int C, float* d_delta, float* d_weights, void* stream) {
+  FTN_REQUIRE(d_out && delta && weights && plan && d_delta && d_weights, "ftn_aggregate_backward: null pointer");
+  FTN_REQUIRE(B > 0 && B <= 65535 * 32 && L > 0 && C > 0, "ftn_aggregate_backward: bad sizes");
+  aggregate_backward_kernel<<<dim3(B, FTN_MAX_K), 256, 0, as_stream(stream)>>>(d_out, delta, weights, plan, B, L, C, d_delta,
+                                                                              d_weights);
+  FTN_LAUNCH_CHECK("aggregate_backward_kernel");
   return 0;
 }

@@ -112,6 +112,10 @@ SIGNATURES = {
     "ftn_nb_head_epilogue_backward": (_I, [_P, _P, _P, _P, _P, _I64, _I, _P, _P, _P]),
     "ftn_layer_norm_backward": (_I, [_P, _P, _P, _I64, _I, _F, _P, _P, _P, _P]),
     "ftn_gemm_f32": (_I, [_P, _I, _I64, _I, _P, _I, _I64, _I, _P, _I, _I64, _I, _I, _I, _I, _I, _P]),
+    "ftn_act_forward": (_I, [_P, _I64, _I, _P, _P]),
+    "ftn_act_backward": (_I, [_P, _P, _I64, _I, _P, _P]),
+    "ftn_conv2d_grid_backward_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ftn_aggregate_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ftn_embed_tc_workspace_bytes": (_SZ, [C.c_longlong, _I]),
     "ftn_embed_tc": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
     "ftn_nb_head_tc_workspace_bytes": (_SZ, [_I, _I, _I]),
@@ -680,3 +684,38 @@ def gemm_f32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: b
                                br * bc if b.dim() == 3 else 0, int(trans_b), out.data_ptr(), N, M * N if len(shape) == 3 else 0,
                                M, N, K, batch, 0, _stream()), "ftn_gemm_f32")
     return out
+
+
+# --------------------------------------------------------------------------- #
+# backward, second slice (csrc/backward.cu)
+# --------------------------------------------------------------------------- #
+def act_forward(x: torch.Tensor, act: int) -> torch.Tensor:
+    out = torch.empty_like(x)
+    _check(load().ftn_act_forward(x.data_ptr(), x.numel(), act, out.data_ptr(), _stream()), "ftn_act_forward")
+    return out
+
+
+def act_backward(x: torch.Tensor, dy: torch.Tensor, act: int) -> torch.Tensor:
+    dx = torch.empty_like(x)
+    _check(load().ftn_act_backward(x.data_ptr(), dy.data_ptr(), x.numel(), act, dx.data_ptr(), _stream()), "ftn_act_backward")
+    return dx
+
+
+def conv2d_grid_backward_weight(x: torch.Tensor, dy: torch.Tensor, period: int, kh: int, kw: int) -> torch.Tensor:
+    """dW ``[kh*kw, cin, cout]`` of ``conv2d_grid`` for x ``[B, L, cin]``, dy ``[B, L, cout]`` (fp32, one period group)."""
+    B, L, cin = x.shape
+    cout = dy.shape[-1]
+    dw = torch.empty(kh * kw, cin, cout, dtype=torch.float32, device=x.device)
+    _check(load().ftn_conv2d_grid_backward_weight(x.data_ptr(), dy.data_ptr(), B, L, int(period), cin, cout, kh, kw,
+                                                  dw.data_ptr(), _stream()), "ftn_conv2d_grid_backward_weight")
+    return dw
+
+
+def aggregate_backward(d_out: torch.Tensor, delta: torch.Tensor, weights: torch.Tensor, plan_dev: torch.Tensor):
+    """-> (d_delta ``[G_slots, B, L, C]``, d_weights ``[B, FTN_MAX_K]``); d_x of the aggregation is d_out itself."""
+    B, L, Cc = d_out.shape
+    d_delta = torch.zeros_like(delta)
+    d_w = torch.empty(B, FTN_MAX_K, dtype=torch.float32, device=d_out.device)
+    _check(load().ftn_aggregate_backward(d_out.data_ptr(), delta.data_ptr(), weights.data_ptr(), plan_dev.data_ptr(), B, L, Cc,
+                                         d_delta.data_ptr(), d_w.data_ptr(), _stream()), "ftn_aggregate_backward")
+    return d_delta, d_w

@@ -118,3 +118,113 @@ def nb_head(seq, Wt, bt, Wmu, bmu, Wsg, bsg, hist, late=None, late_gate=None, fl
     """Differentiable NB head.  ``seq`` fp32 ``[B, L, C]``; ``Wt`` ``[steps, L]``; heads ``[N, C]``; ``hist`` ``[B, steps, N]``;
     ``late`` ``[B, N, steps]`` with ``late_gate`` ``[steps]`` or both ``None``; ``floor_n`` ``[N]``."""
     return _NBHead.apply(seq, Wt, bt, Wmu, bmu, Wsg, bsg, hist, late, late_gate, floor_n)
+
+
+# --------------------------------------------------------------------------- #
+# second slice: the pieces of the Inception chain and of the aggregation
+# --------------------------------------------------------------------------- #
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act_code):
+        xf = _f32c(x)
+        ctx.save_for_backward(xf)
+        ctx.act = int(act_code)
+        return nv.act_forward(xf, ctx.act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xf,) = ctx.saved_tensors
+        return nv.act_backward(xf, _f32c(dy), ctx.act), None
+
+
+def activation(x: torch.Tensor, name: str = "gelu") -> torch.Tensor:
+    """Exact-erf GELU (``nn.GELU()`` default, timesnet.py:643) or ReLU, forward and backward in libflowtimes."""
+    return _Act.apply(x, nv.FTN_ACT_RELU if name.lower() == "relu" else nv.FTN_ACT_GELU)
+
+
+class _Conv2dGrid(torch.autograd.Function):
+    """``F.conv2d(x, w, b, padding="same")`` (odd kernel) on an NCHW grid, computed on the zero-copy fold
+    ``[B, H*W, C]`` by ``ftn_conv2d_grid``.  Backward: the data gradient is the same kernel with the taps flipped and
+    cin / cout swapped, the weight gradient ``ftn_conv2d_grid_backward_weight``, the bias gradient a column sum."""
+
+    @staticmethod
+    def forward(ctx, x_nchw, weight, bias):
+        B, Cin, H, W = x_nchw.shape
+        Cout, _, kh, kw = weight.shape
+        xs = _f32c(x_nchw).permute(0, 2, 3, 1).reshape(B, H * W, Cin).contiguous()        # fold: memory plumbing only
+        w_taps = _f32c(weight).permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous()
+        b = _f32c(bias) if bias is not None else torch.zeros(Cout, dtype=torch.float32, device=xs.device)
+        plan = nv.single_group_plan(W, H, xs.device)
+        out = nv.conv2d_grid(xs, plan, w_taps, b, kh, kw)
+        ctx.save_for_backward(xs, w_taps)
+        ctx.geom = (B, Cin, Cout, H, W, kh, kw, bias is not None)
+        ctx.plan = plan
+        return out.view(B, H, W, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy_nchw):
+        xs, w_taps = ctx.saved_tensors
+        B, Cin, Cout, H, W, kh, kw, has_bias = ctx.geom
+        dy = _f32c(dy_nchw).permute(0, 2, 3, 1).reshape(B, H * W, Cout).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w_back = w_taps.flip(0).transpose(1, 2).contiguous()                         # tap (dr, dw) -> (kh-1-dr, kw-1-dw)
+            zero = torch.zeros(Cin, dtype=torch.float32, device=dy.device)
+            dxs = nv.conv2d_grid(dy, ctx.plan, w_back, zero, kh, kw)
+            dx = dxs.view(B, H, W, Cin).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dwt = nv.conv2d_grid_backward_weight(xs, dy, W, kh, kw)                       # [taps, cin, cout]
+            dw = dwt.view(kh, kw, Cin, Cout).permute(3, 2, 0, 1)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(dy.view(B * H * W, Cout))
+        return dx, dw, db
+
+
+def conv2d_same(x_nchw: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Differentiable ``conv2d`` with zero "same" padding and an odd kernel on an NCHW grid (InceptionBranch's convs,
+    timesnet.py:575-593)."""
+    return _Conv2dGrid.apply(x_nchw, weight, bias)
+
+
+def inception_branch(x_nchw: torch.Tensor, branch: torch.nn.Sequential) -> torch.Tensor:
+    """Differentiable ``InceptionBranch.forward`` (timesnet.py:592-593): the branch's convs in order."""
+    out = x_nchw
+    for conv in branch:
+        out = conv2d_same(out, conv.weight, conv.bias)
+    return out
+
+
+def inception_block(x_nchw: torch.Tensor, block) -> torch.Tensor:
+    """Differentiable ``InceptionBlock.forward`` (timesnet.py:645-654): ``act(proj(cat_j branch_j(x))) + res_proj(x)``
+    (dropout is the identity: the build has no RNG on the path; ``dropout > 0`` in train mode raises upstream)."""
+    feats = [inception_branch(x_nchw, p.branch) for p in block.paths]
+    cat = torch.cat(feats, dim=1)                                                        # memory plumbing
+    out = conv2d_same(cat, block.proj.weight, block.proj.bias)
+    out = activation(out, "relu" if isinstance(block.act, torch.nn.ReLU) else "gelu")
+    res = x_nchw if isinstance(block.res_proj, torch.nn.Identity) else conv2d_same(x_nchw, block.res_proj.weight,
+                                                                                    block.res_proj.bias)
+    return out + res
+
+
+class _Aggregate(torch.autograd.Function):
+    """``x + sum_g w[b, g] * delta_g`` (timesnet.py:1075-1099, :818) for fp32 tensors and a device plan."""
+
+    @staticmethod
+    def forward(ctx, x, delta, weights, plan_dev):
+        xf, df, wf = _f32c(x), _f32c(delta), _f32c(weights)
+        out = torch.empty_like(xf)
+        nv.aggregate(xf, df, wf, plan_dev, None, None, 0.0, out)
+        ctx.save_for_backward(df, wf, plan_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        df, wf, plan_dev = ctx.saved_tensors
+        g = _f32c(d_out)
+        d_delta, d_w = nv.aggregate_backward(g, df, wf, plan_dev)
+        return g, d_delta, d_w, None
+
+
+def aggregate(x: torch.Tensor, delta: torch.Tensor, weights: torch.Tensor, plan_dev: torch.Tensor) -> torch.Tensor:
+    """Differentiable softmax-weighted aggregation + residual given the group weights ``[B, 16]`` and the device plan."""
+    return _Aggregate.apply(x, delta, weights, plan_dev)

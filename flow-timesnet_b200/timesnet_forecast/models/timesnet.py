@@ -57,6 +57,12 @@ def _act_code(name: str) -> int:
 _warned_train = set()
 
 
+def _wants_grad(module: nn.Module, x: torch.Tensor) -> bool:
+    """The differentiable route of a module is taken when autograd is recording and either the input carries a graph or
+    the module was opted in (``module.differentiable = True``: weight gradients for a grad-less input)."""
+    return torch.is_grad_enabled() and (bool(getattr(x, "requires_grad", False)) or bool(getattr(module, "differentiable", False)))
+
+
 def _forward_only_guard(module: nn.Module, x: torch.Tensor, dropout: float) -> None:
     """The build is forward-only: say so instead of silently returning grad-less, dropout-free outputs."""
     if torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.requires_grad:
@@ -446,6 +452,9 @@ class InceptionBranch(nn.Module):
         if x.ndim != 4:
             raise ValueError("InceptionBranch expects an NCHW grid [B, C, H, W]")
         x = nv.require_cuda(x, "x")
+        if _wants_grad(self, x):                                   # differentiable route: native forward AND backward
+            from ..autograd import inception_branch
+            return inception_branch(x, self.branch).to(x.dtype)
         B, _, H, W = x.shape
         dt = x.dtype
         with torch.no_grad():
@@ -514,6 +523,15 @@ class InceptionBlock(nn.Module):
         if x.ndim != 4:
             raise ValueError("InceptionBlock expects an NCHW grid [B, C, H, W]")
         x = nv.require_cuda(x, "x")
+        if _wants_grad(self, x):
+            # differentiable route (second backward slice): every conv / activation is a libflowtimes kernel forward
+            # and backward (timesnet_forecast/autograd.py); as written, fp32, not the packed tensor-core chain
+            if self.training and float(self.dropout.p) > 0.0:
+                raise RuntimeError("InceptionBlock: the differentiable route has no dropout (set dropout=0 or call .eval())")
+            from ..autograd import inception_block
+            if self.proj.weight.device != x.device:
+                self.to(x.device)
+            return inception_block(x, self).to(x.dtype)
         _forward_only_guard(self, x, float(self.dropout.p))
         B, _, H, W = x.shape
         dt = x.dtype
@@ -713,6 +731,8 @@ class TimesBlock(nn.Module):
             raise RuntimeError("TimesBlock.period_selector has not been set")
         x = nv.require_cuda(x, "x")
         nv.dtype_code(x.dtype)
+        if _wants_grad(self, x) and self.inception is not None and self._is_native_bank():
+            return self._run_differentiable(x, ln_w, ln_b, eps)
         _forward_only_guard(self, x, self._dropout)
         self._period_calls = getattr(self, "_period_calls", 0) + 1
         if self.inception is None:
@@ -753,12 +773,58 @@ class TimesBlock(nn.Module):
             nv.aggregate(x, delta, plan.weights, plan.plan_dev, ln_w, ln_b, eps, out)
             return out
 
+    def _run_differentiable(self, x: torch.Tensor, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
+                            eps: float) -> torch.Tensor:
+        """Differentiable route (backward slice 2; fp32): the period search runs as usual (no gradient -- top-k has
+        none), then, per period group, the fold is a padded VIEW of x (memory plumbing, torch autograd), the two
+        InceptionBlocks and the activations are libflowtimes kernels forward and backward
+        (``autograd.inception_block`` / ``activation``), and the weighted sum + residual is ``autograd.aggregate``.
+        The group weights are treated as constants: the reference also back-propagates through the amplitudes that
+        feed the softmax (a second-order path into x, timesnet.py:992-1009), which this slice does not yet do."""
+        from ..autograd import activation, aggregate, inception_block, layer_norm
+        if x.dtype != torch.float32:
+            raise RuntimeError("TimesBlock: the differentiable route is fp32 (cast the input; bf16 stacks are forward-only)")
+        if self.training and self._dropout > 0.0:
+            raise RuntimeError("TimesBlock: the differentiable route has no dropout (set dropout=0 or call .eval())")
+        self._period_calls = getattr(self, "_period_calls", 0) + 1
+        B, L, C = x.shape
+        with torch.no_grad():
+            plan = self._plan_for(x.detach())
+        if plan is None:
+            return x if ln_w is None else layer_norm(x, ln_w, ln_b, eps)
+        self._vec_calls += 1
+        if self.inception[0].proj.weight.device != x.device:
+            self.inception = self.inception.to(x.device)
+        h = plan.host()                                          # one sync: the group geometry shapes the views below
+        blk_a, blk_b = self.inception[0], self.inception[2]
+        slots = max(1, min(plan.k, nv.FTN_MAX_K))
+        deltas = []
+        for g in range(h.n_groups):
+            p, pad, cyc = int(h.grp_period[g]), int(h.grp_pad[g]), int(h.grp_cycles[g])
+            grid = torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x          # [B, L + pad, C]
+            grid = grid.reshape(B, cyc, p, C).permute(0, 3, 1, 2)                     # the reference's NCHW grid
+            y = inception_block(grid, blk_a)
+            y = activation(y, self._activation_name)
+            y = inception_block(y, blk_b)
+            deltas.append((y - grid).permute(0, 2, 3, 1).reshape(B, cyc * p, C)[:, :L])
+        zero = x.new_zeros(B, L, C)
+        delta = torch.stack(deltas + [zero] * (slots - len(deltas)), dim=0).contiguous()
+        out = aggregate(x, delta, plan.weights.detach(), plan.plan_dev)
+        return out if ln_w is None else layer_norm(out, ln_w, ln_b, eps)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x + sum_g w_g * (inception(fold_g(x)) - fold_g(x))``  (timesnet.py:767-818)."""
         return self._run(x, None, None, 0.0)
 
+    def forward_norm_differentiable(self, x: torch.Tensor, norm: nn.LayerNorm) -> torch.Tensor:
+        """``forward_norm`` on the differentiable route with gradients into the LayerNorm parameters as well (the fused
+        forward-only route takes detached copies of them)."""
+        return self._run_differentiable(x, norm.weight, norm.bias, float(norm.eps))
+
     def forward_norm(self, x: torch.Tensor, norm: nn.LayerNorm) -> torch.Tensor:
         """Block + inter-block residual + shared LayerNorm in one pass (timesnet.py:2058-2061)."""
+        if _wants_grad(self, x) and self.inception is not None and self._is_native_bank():
+            return self.forward_norm_differentiable(x, norm)
         w = norm.weight.detach().to(device=x.device, dtype=torch.float32)
         b = norm.bias.detach().to(device=x.device, dtype=torch.float32)
         return self._run(x, w.contiguous(), b.contiguous(), float(norm.eps))

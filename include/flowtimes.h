@@ -381,6 +381,23 @@ FTN_API int ftn_gemm_f32(const float* A, int lda, int64_t stride_a, int trans_a,
                          int trans_b, float* C, int ldc, int64_t stride_c, int M, int N, int K, int batch, int accumulate,
                          void* stream);
 
+/* ---- backward, second slice: the pieces of the Inception chain and of the aggregation (fp32) -----------------
+ *   ftn_act_forward / _backward        y = act(x), dx = dy * act'(x): exact erf GELU (nn.GELU() default, timesnet.py:643) or ReLU
+ *   ftn_conv2d_grid_backward_weight    dW[kh*kw][cin][cout] of ftn_conv2d_grid on ONE period group (period = W, L / W cycles,
+ *                                      zero "same" padding): sum over positions of x shifted by the tap times dy.  The data
+ *                                      gradient is ftn_conv2d_grid itself with the taps flipped and cin / cout swapped; the
+ *                                      bias gradient a column sum (ftn_gemm_f32 with a row of ones)
+ *   ftn_aggregate_backward             out = x + sum_g w[b][g] delta_g (timesnet.py:1075-1099, :818):
+ *                                      d_delta[g][B][L][C] = w d_out, d_weights[B][FTN_MAX_K] = <d_out, delta_g>; d_x = d_out
+ * Together with the first slice these make InceptionBranch / InceptionBlock (on NCHW grids) and the aggregation
+ * differentiable through timesnet_forecast/autograd.py, checked against float64 autograd and reference-generated goldens. */
+FTN_API int ftn_act_forward(const float* x, int64_t n, int act, float* y, void* stream);
+FTN_API int ftn_act_backward(const float* x, const float* dy, int64_t n, int act, float* dx, void* stream);
+FTN_API int ftn_conv2d_grid_backward_weight(const float* x, const float* dy, int B, int L, int period, int cin, int cout,
+                                            int kh, int kw, float* dw, void* stream);
+FTN_API int ftn_aggregate_backward(const float* d_out, const float* delta, const float* weights, const FtnPeriodPlan* plan,
+                                   int B, int L, int C, float* d_delta, float* d_weights, void* stream);
+
 /* ---- NVLink peer mailbox: the path's one collective without NCCL --------------
  * replaces the all-reduce of amp_channel_median.mean(dim=0) a sharded batch needs (timesnet.py:112).
  * One process per GPU.  Every rank: ftn_peer_create (allocates its mailbox with cudaMalloc -- the one allocation the

@@ -102,9 +102,9 @@ def test_nb_head_backward_matches_float64_autograd(with_late):
         assert _rel(pc[k].grad, p64[k].grad) < 1e-4, k
 
 
-def test_blocks_stay_forward_only():
-    """The Inception chain has no backward yet: a block refuses inputs that require grad instead of returning
-    grad-less tensors silently."""
+def test_bf16_blocks_stay_forward_only():
+    """The differentiable route is fp32: a bf16 block refuses inputs that require grad instead of returning grad-less
+    tensors silently."""
     from timesnet_forecast.models.timesnet import TimesBlock
     blk = TimesBlock(16, [(3, 3)], 0.0, "gelu").cuda().eval()
 
@@ -113,4 +113,152 @@ def test_blocks_stay_forward_only():
             return torch.tensor([4, 6]), torch.ones(x.size(0), 2, device=x.device, dtype=x.dtype)
     object.__setattr__(blk, "period_selector", Sel())
     with pytest.raises(RuntimeError):
-        blk(torch.randn(2, 24, 16, device="cuda", requires_grad=True))
+        blk(torch.randn(2, 24, 16, device="cuda", dtype=torch.bfloat16, requires_grad=True))
+
+
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_timesblock_backward_matches_float64_autograd(with_ln):
+    """TimesBlock.forward on an fp32 input that requires grad: fold views + differentiable Inception chain + aggregation
+    (all compute in libflowtimes, forward and backward) against a float64 torch evaluation of timesnet.py:767-818 with
+    the same periods and the same (constant) group weights.  Periods 4, 6, 5: pads 0, 0 and 1 at L = 24."""
+    import copy
+    from timesnet_forecast.models.timesnet import TimesBlock
+    torch.manual_seed(5)
+    C, L, B = 16, 24, 2
+    blk = TimesBlock(C, [(3, 3), (5, 5)], 0.0, "gelu", d_ff=32, bottleneck_ratio=4.0)
+    for p in blk.parameters():
+        p.data.normal_(0, 0.25)
+    ref = copy.deepcopy(blk.inception).double()
+    amps = torch.tensor([[1.0, 0.5, 0.2], [0.3, 0.9, 0.1]])
+
+    class Sel(torch.nn.Module):
+        def forward(self, x):
+            return torch.tensor([4, 6, 5]), amps.to(device=x.device, dtype=x.dtype)
+    blk = blk.cuda().eval()
+    object.__setattr__(blk, "period_selector", Sel())
+    norm = torch.nn.LayerNorm(C)
+    norm.weight.data.normal_(1, 0.1)
+    norm.bias.data.normal_(0, 0.1)
+    x = torch.randn(B, L, C)
+    u = torch.randn(B, L, C)
+
+    def inc(m, g):
+        out = m.act(m.proj(torch.cat([p.branch(g) for p in m.paths], dim=1)))
+        return out + m.res_proj(g)
+    xr = x.double().requires_grad_()
+    w = torch.softmax(amps.double(), dim=1)
+    acc = xr
+    for gi, p in enumerate([4, 5, 6]):                                # groups ascend by period
+        col = {4: 0, 5: 2, 6: 1}[p]
+        pad = (-L) % p
+        grid = torch.nn.functional.pad(xr, (0, 0, 0, pad)).reshape(B, (L + pad) // p, p, C).permute(0, 3, 1, 2)
+        y = inc(ref[2], ref[1](inc(ref[0], grid)))
+        d = (y - grid).permute(0, 2, 3, 1).reshape(B, L + pad, C)[:, :L]
+        acc = acc + w[:, col].view(B, 1, 1) * d
+    n64 = copy.deepcopy(norm).double()
+    want = n64(acc) if with_ln else acc
+    (want * u.double()).sum().backward()
+    xc = x.cuda().requires_grad_()
+    normc = norm.cuda()
+    got = blk.forward_norm_differentiable(xc, normc) if with_ln else blk(xc)
+    assert got.requires_grad and _rel(got, want) < 2e-5
+    (got * u.cuda()).sum().backward()
+    assert _rel(xc.grad, xr.grad) < 5e-5
+    for (n, p), (_, q) in zip(blk.inception.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and _rel(p.grad, q.grad) < 5e-5, n
+    if with_ln:
+        assert _rel(normc.weight.grad, n64.weight.grad) < 5e-5 and _rel(normc.bias.grad, n64.bias.grad) < 5e-5
+
+
+# ---- second slice: Inception chain pieces and the aggregation -------------------------------------------------------
+@pytest.mark.parametrize("kh,kw", [(1, 1), (3, 3), (5, 7)])
+def test_conv2d_same_backward_matches_float64_autograd(kh, kw):
+    """conv2d with zero "same" padding on an NCHW grid: native forward (ftn_conv2d_grid on the fold), native data /
+    weight / bias gradients, against float64 F.conv2d autograd (InceptionBranch's convs, timesnet.py:575-593)."""
+    from timesnet_forecast.autograd import conv2d_same
+    g = torch.Generator().manual_seed(kh * 10 + kw)
+    B, Cin, Cout, H, W = 2, 5, 7, 4, 6
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    u = torch.randn(B, Cout, H, W, generator=g)
+    ref = [t.double().requires_grad_() for t in (x, w, b)]
+    (torch.nn.functional.conv2d(ref[0], ref[1], ref[2], padding=(kh // 2, kw // 2)) * u.double()).sum().backward()
+    got = [t.cuda().requires_grad_() for t in (x, w, b)]
+    out = conv2d_same(got[0], got[1], got[2])
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
+    assert _rel(out, want) < 1e-5
+    (out * u.cuda()).sum().backward()
+    for name, a, r in zip(("dx", "dw", "db"), got, ref):
+        assert _rel(a.grad, r.grad) < 1e-5, name
+
+
+@pytest.mark.parametrize("name", ["gelu", "relu"])
+def test_activation_backward_matches_float64_autograd(name):
+    from timesnet_forecast.autograd import activation
+    x = torch.linspace(-6, 6, 4001)
+    r = x.double().requires_grad_()
+    (torch.nn.functional.gelu(r) if name == "gelu" else torch.relu(r)).sum().backward()
+    c = x.cuda().requires_grad_()
+    activation(c, name).sum().backward()
+    assert (c.grad.cpu().double() - r.grad).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("ratio,cin,cout", [(4.0, 8, 16), (1.0, 6, 6), (2.0, 12, 8)])
+def test_inception_block_backward_matches_float64_autograd(ratio, cin, cout):
+    """InceptionBlock.forward on an NCHW grid that requires grad takes the differentiable route: outputs and every
+    gradient (input, all branch convs, proj, res_proj) against the same module evaluated in float64 with torch ops
+    (the reference's formula, timesnet.py:645-654)."""
+    import copy
+    from timesnet_forecast.models.timesnet import InceptionBlock
+    torch.manual_seed(int(ratio * 10) + cin)
+    blk = InceptionBlock(cin, cout, [(3, 3), (5, 5)], 0.0, "gelu", bottleneck_ratio=ratio)
+    for p in blk.parameters():
+        p.data.normal_(0, 0.3)
+    ref = copy.deepcopy(blk).double()
+    x = torch.randn(2, cin, 3, 8)
+    u = torch.randn(2, cout, 3, 8)
+
+    def ref_forward(m, xx):
+        feats = [p.branch(xx) for p in m.paths]
+        out = m.act(m.proj(torch.cat(feats, dim=1)))
+        return out + m.res_proj(xx)
+    xr = x.double().requires_grad_()
+    want = ref_forward(ref, xr)
+    (want * u.double()).sum().backward()
+    blk = blk.cuda()
+    xc = x.cuda().requires_grad_()
+    got = blk(xc)
+    assert got.requires_grad and _rel(got, want) < 1e-5
+    (got * u.cuda()).sum().backward()
+    assert _rel(xc.grad, xr.grad) < 1e-5
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and _rel(p.grad, q.grad) < 1e-5, n
+    # a grad-less input keeps the fast forward-only route (packed chain), bit-for-bit deterministic
+    with torch.no_grad():
+        assert not blk(x.cuda()).requires_grad
+
+
+def test_aggregate_backward_matches_float64_autograd():
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast.autograd import aggregate
+    g = torch.Generator().manual_seed(3)
+    B, L, C = 3, 24, 16
+    plan_host = nv.plan_build_host([4, 6, 12, 6], L, None, None)       # 3 groups (6 twice)
+    plan = nv.plan_to_device(plan_host, "cuda")
+    G = plan_host.n_groups
+    x = torch.randn(B, L, C, generator=g)
+    delta = torch.randn(nv.FTN_MAX_K, B, L, C, generator=g)
+    w = torch.zeros(B, nv.FTN_MAX_K)
+    w[:, :G] = torch.softmax(torch.randn(B, G, generator=g), dim=1)
+    u = torch.randn(B, L, C, generator=g)
+    xr, dr, wr = x.double().requires_grad_(), delta.double().requires_grad_(), w.double().requires_grad_()
+    want = xr + sum(wr[:, gi].view(B, 1, 1) * dr[gi] for gi in range(G))
+    (want * u.double()).sum().backward()
+    xc, dc, wc = x.cuda().requires_grad_(), delta.cuda().requires_grad_(), w.cuda().requires_grad_()
+    got = aggregate(xc, dc, wc, plan)
+    assert _rel(got, want) < 1e-6
+    (got * u.cuda()).sum().backward()
+    assert _rel(xc.grad, xr.grad) < 1e-6
+    assert _rel(dc.grad[:G], dr.grad[:G]) < 1e-6 and float(dc.grad[G:].abs().max()) == 0.0
+    assert _rel(wc.grad[:, :G], wr.grad[:, :G]) < 1e-5
