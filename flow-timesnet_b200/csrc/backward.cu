@@ -260,6 +260,86 @@ aggregate_backward_kernel(const float* __restrict__ d_out, const float* __restri
   if (threadIdx.x == 0) d_weights[(size_t)b * FTN_MAX_K + g] = ss[0];
 }
 
+
+// ---- gradient through the period weights (timesnet.py:992-1009 <- :109-111, :134) -----------------------------------
+// weights[b][g] = sum_{j -> g} softmax_j(amps[b][valid]);  d_amps[b][j] = s_j (d_w[g(j)] - sum_i s_i d_w[g(i)])
+__global__ void group_weights_backward_kernel(const float* __restrict__ amps, int B, int k, const FtnPeriodPlan* __restrict__ plan,
+                                              const float* __restrict__ d_weights, float* __restrict__ d_amps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nv = plan->n_valid;
+  float mx = -CUDART_INF_F;
+  for (int j = 0; j < k && j < nv; ++j)
+    if (plan->mapping[j] >= 0) mx = fmaxf(mx, amps[(size_t)b * k + j]);
+  float den = 0.f;
+  for (int j = 0; j < k && j < nv; ++j)
+    if (plan->mapping[j] >= 0) den += expf(amps[(size_t)b * k + j] - mx);
+  float dot = 0.f;
+  for (int j = 0; j < k && j < nv; ++j) {
+    const int g = plan->mapping[j];
+    if (g >= 0) dot += expf(amps[(size_t)b * k + j] - mx) / den * d_weights[(size_t)b * FTN_MAX_K + g];
+  }
+  for (int j = 0; j < k; ++j) {
+    const int g = j < nv ? plan->mapping[j] : -1;
+    float d = 0.f;
+    if (g >= 0) d = expf(amps[(size_t)b * k + j] - mx) / den * (d_weights[(size_t)b * FTN_MAX_K + g] - dot);
+    d_amps[(size_t)b * k + j] = d;
+  }
+}
+
+// amps[b][j] = lower median over channels of |rfft_t x[b, :, c]|[f_j]: the gradient goes to the median channel c*,
+//   d|X| / d x[t] = (Re X cos(th_t) - Im X sin(th_t)) / |X|,  X = sum_t x[t] (cos th_t - i sin th_t),  th_t = 2 pi f t / L
+// One CTA per (candidate j, window b); d_x accumulates with atomics (several candidates can share a median channel).
+__global__ void __launch_bounds__(256)
+spectrum_amp_backward_kernel(const float* __restrict__ x, int B, int L, int C, int k, const FtnPeriodPlan* __restrict__ plan,
+                             const float* __restrict__ d_amps, float* __restrict__ d_x) {
+  extern __shared__ float sm_[];
+  float* s_cos = sm_;            // [L]
+  float* s_sin = sm_ + L;        // [L]
+  float* s_re = s_sin + L;       // [C]
+  float* s_im = s_re + C;        // [C]
+  float* s_amp = s_im + C;       // [C]
+  __shared__ int s_star;
+  const int j = blockIdx.x, b = blockIdx.y;
+  if (j >= plan->n_valid || j >= k) return;
+  const float g = d_amps[(size_t)b * k + j];
+  if (g == 0.f) return;
+  const int f = (int)plan->freq[j];
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    const long long ft = ((long long)f * t) % L;
+    float sn, cs;
+    sincospif(2.0f * (float)ft / (float)L, &sn, &cs);
+    s_cos[t] = cs;
+    s_sin[t] = sn;
+  }
+  __syncthreads();
+  const float* xb = x + (size_t)b * L * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    for (int t = 0; t < L; ++t) {
+      const float v = xb[(size_t)t * C + c];
+      re = fmaf(v, s_cos[t], re);
+      im = fmaf(-v, s_sin[t], im);
+    }
+    s_re[c] = re; s_im[c] = im; s_amp[c] = sqrtf(fmaf(re, re, im * im));
+  }
+  __syncthreads();
+  const int want = (C - 1) >> 1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = s_amp[c];
+    int rank = 0;
+    for (int o = 0; o < C; ++o) rank += (s_amp[o] < a || (s_amp[o] == a && o < c)) ? 1 : 0;
+    if (rank == want) s_star = c;
+  }
+  __syncthreads();
+  const int cs_ = s_star;
+  const float re = s_re[cs_], im = s_im[cs_], amp = s_amp[cs_];
+  if (!(amp > 0.f)) return;                                     // |X| = 0: subgradient 0 (torch gives NaN/0 here too)
+  const float sc = g / amp;
+  for (int t = threadIdx.x; t < L; t += blockDim.x)
+    atomicAdd(&d_x[((size_t)b * L + t) * C + cs_], sc * (re * s_cos[t] - im * s_sin[t]));   // Im X = -sum x sin
+}
+
 }  // namespace ftn
 
 using namespace ftn;
@@ -365,5 +445,26 @@ extern "C" int ftn_aggregate_backward(const float* d_out, const float* delta, co
   aggregate_backward_kernel<<<dim3(B, FTN_MAX_K), 256, 0, as_stream(stream)>>>(d_out, delta, weights, plan, B, L, C, d_delta,
                                                                               d_weights);
   FTN_LAUNCH_CHECK("aggregate_backward_kernel");
+  return 0;
+}
+
+extern "C" int ftn_group_weights_backward(const float* amps, int B, int k, const FtnPeriodPlan* plan, const float* d_weights,
+                                          float* d_amps, void* stream) {
+  FTN_REQUIRE(amps && plan && d_weights && d_amps, "ftn_group_weights_backward: null pointer");
+  FTN_REQUIRE(B > 0 && k >= 1 && k <= FTN_MAX_K, "ftn_group_weights_backward: bad sizes");
+  group_weights_backward_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(amps, B, k, plan, d_weights, d_amps);
+  FTN_LAUNCH_CHECK("group_weights_backward_kernel");
+  return 0;
+}
+
+extern "C" int ftn_spectrum_amp_backward(const float* x, int B, int L, int C, int k, const FtnPeriodPlan* plan,
+                                         const float* d_amps, float* d_x, void* stream) {
+  FTN_REQUIRE(x && plan && d_amps && d_x, "ftn_spectrum_amp_backward: null pointer");
+  FTN_REQUIRE(B > 0 && B <= 65535 && L > 1 && C > 0 && k >= 1 && k <= FTN_MAX_K, "ftn_spectrum_amp_backward: bad sizes");
+  const size_t smem = (size_t)(2 * L + 3 * C) * sizeof(float);
+  FTN_REQUIRE(smem <= 200 * 1024, "ftn_spectrum_amp_backward: L=%d, C=%d too large", L, C);
+  FTN_DYN_SMEM(spectrum_amp_backward_kernel, smem);
+  spectrum_amp_backward_kernel<<<dim3(k, B), 256, smem, as_stream(stream)>>>(x, B, L, C, k, plan, d_amps, d_x);
+  FTN_LAUNCH_CHECK("spectrum_amp_backward_kernel");
   return 0;
 }

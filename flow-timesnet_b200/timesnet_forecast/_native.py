@@ -116,6 +116,8 @@ SIGNATURES = {
     "ftn_act_backward": (_I, [_P, _P, _I64, _I, _P, _P]),
     "ftn_conv2d_grid_backward_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ftn_aggregate_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ftn_group_weights_backward": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "ftn_spectrum_amp_backward": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ftn_embed_tc_workspace_bytes": (_SZ, [C.c_longlong, _I]),
     "ftn_embed_tc": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
     "ftn_nb_head_tc_workspace_bytes": (_SZ, [_I, _I, _I]),
@@ -719,3 +721,20 @@ def aggregate_backward(d_out: torch.Tensor, delta: torch.Tensor, weights: torch.
     _check(load().ftn_aggregate_backward(d_out.data_ptr(), delta.data_ptr(), weights.data_ptr(), plan_dev.data_ptr(), B, L, Cc,
                                          d_delta.data_ptr(), d_w.data_ptr(), _stream()), "ftn_aggregate_backward")
     return d_delta, d_w
+
+
+def group_weights_backward(amps: torch.Tensor, plan_dev: torch.Tensor, d_weights: torch.Tensor) -> torch.Tensor:
+    B, k = amps.shape
+    d_amps = torch.empty_like(amps)
+    _check(load().ftn_group_weights_backward(amps.data_ptr(), B, k, plan_dev.data_ptr(), d_weights.data_ptr(),
+                                             d_amps.data_ptr(), _stream()), "ftn_group_weights_backward")
+    return d_amps
+
+
+def spectrum_amp_backward(x: torch.Tensor, plan_dev: torch.Tensor, d_amps: torch.Tensor) -> torch.Tensor:
+    """d_x ``[B, L, C]`` of the per-window amplitudes at the plan's bins (gradient to the lower-median channel)."""
+    B, L, Cc = x.shape
+    d_x = torch.zeros_like(x)
+    _check(load().ftn_spectrum_amp_backward(x.data_ptr(), B, L, Cc, d_amps.shape[1], plan_dev.data_ptr(), d_amps.data_ptr(),
+                                            d_x.data_ptr(), _stream()), "ftn_spectrum_amp_backward")
+    return d_x

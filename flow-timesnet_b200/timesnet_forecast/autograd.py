@@ -228,3 +228,45 @@ class _Aggregate(torch.autograd.Function):
 def aggregate(x: torch.Tensor, delta: torch.Tensor, weights: torch.Tensor, plan_dev: torch.Tensor) -> torch.Tensor:
     """Differentiable softmax-weighted aggregation + residual given the group weights ``[B, 16]`` and the device plan."""
     return _Aggregate.apply(x, delta, weights, plan_dev)
+
+
+class _GroupWeights(torch.autograd.Function):
+    """Group weights ``[B, 16]`` of a plan from per-window amplitudes ``[B, k]`` (softmax over the valid candidates,
+    scatter-added per group; timesnet.py:992-1009).  The forward value is the one the search already produced."""
+
+    @staticmethod
+    def forward(ctx, amps, weights_value, plan_dev):
+        ctx.save_for_backward(_f32c(amps), plan_dev)
+        return weights_value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, d_w):
+        amps, plan_dev = ctx.saved_tensors
+        return nv.group_weights_backward(amps, plan_dev, _f32c(d_w)), None, None
+
+
+class _SpectrumAmps(torch.autograd.Function):
+    """Per-window amplitudes at the selected bins, ``median_c |rfft_t x|[f_j]`` (timesnet.py:109-111, :134), as a function
+    of x: the value is the search's, the backward sends each amplitude's gradient to its lower-median channel."""
+
+    @staticmethod
+    def forward(ctx, x, amps_value, plan_dev):
+        ctx.save_for_backward(_f32c(x), plan_dev)
+        return amps_value.detach().float().clone()
+
+    @staticmethod
+    def backward(ctx, d_amps):
+        xf, plan_dev = ctx.saved_tensors
+        return nv.spectrum_amp_backward(xf, plan_dev, _f32c(d_amps)), None, None
+
+
+def period_weights(x: torch.Tensor, plan) -> torch.Tensor:
+    """The plan's group weights as a differentiable function of x (FFT selector) -- the second path from the
+    aggregation back into the input that the reference's autograd follows."""
+    amps = _SpectrumAmps.apply(x, plan.amps, plan.plan_dev)
+    return _GroupWeights.apply(amps, plan.weights, plan.plan_dev)
+
+
+def group_weights(amps: torch.Tensor, plan) -> torch.Tensor:
+    """Same for amplitudes a custom selector module returned (they may carry their own graph)."""
+    return _GroupWeights.apply(amps, plan.weights, plan.plan_dev)

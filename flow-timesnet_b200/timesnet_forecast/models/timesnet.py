@@ -779,9 +779,10 @@ class TimesBlock(nn.Module):
         none), then, per period group, the fold is a padded VIEW of x (memory plumbing, torch autograd), the two
         InceptionBlocks and the activations are libflowtimes kernels forward and backward
         (``autograd.inception_block`` / ``activation``), and the weighted sum + residual is ``autograd.aggregate``.
-        The group weights are treated as constants: the reference also back-propagates through the amplitudes that
-        feed the softmax (a second-order path into x, timesnet.py:992-1009), which this slice does not yet do."""
-        from ..autograd import activation, aggregate, inception_block, layer_norm
+        With the FFT selector the group weights are differentiable too (``autograd.period_weights``: softmax <- amplitude
+        <- the median channel's DFT bin), the second path into x that the reference's autograd follows
+        (timesnet.py:992-1009); amplitudes of a custom selector module are taken as constants."""
+        from ..autograd import activation, aggregate, inception_block, layer_norm, period_weights
         if x.dtype != torch.float32:
             raise RuntimeError("TimesBlock: the differentiable route is fp32 (cast the input; bf16 stacks are forward-only)")
         if self.training and self._dropout > 0.0:
@@ -809,7 +810,11 @@ class TimesBlock(nn.Module):
             deltas.append((y - grid).permute(0, 2, 3, 1).reshape(B, cyc * p, C)[:, :L])
         zero = x.new_zeros(B, L, C)
         delta = torch.stack(deltas + [zero] * (slots - len(deltas)), dim=0).contiguous()
-        out = aggregate(x, delta, plan.weights.detach(), plan.plan_dev)
+        if isinstance(self.period_selector, FFTPeriodSelector) and plan.amps is not None:
+            weights = period_weights(x, plan)
+        else:
+            weights = plan.weights.detach()
+        out = aggregate(x, delta, weights, plan.plan_dev)
         return out if ln_w is None else layer_norm(out, ln_w, ln_b, eps)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

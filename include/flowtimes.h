@@ -397,6 +397,16 @@ FTN_API int ftn_conv2d_grid_backward_weight(const float* x, const float* dy, int
                                             int kh, int kw, float* dw, void* stream);
 FTN_API int ftn_aggregate_backward(const float* d_out, const float* delta, const float* weights, const FtnPeriodPlan* plan,
                                    int B, int L, int C, float* d_delta, float* d_weights, void* stream);
+/* gradient through the period weights, the path the reference's autograd takes from the aggregation back into x
+ * (timesnet.py:992-1009 <- :134 <- :109-111; pinned by tests/test_fft_period_selector.py:73-102):
+ *   ftn_group_weights_backward   d_amps[B][k] from d_weights[B][FTN_MAX_K] (softmax over the valid candidates + scatter-add)
+ *   ftn_spectrum_amp_backward    d_x[B][L][C] += d_amps[b][j] * d|rfft x[b,:,c*]|[f_j] / dx, c* = the lower-median channel
+ *                                (recomputed: one DFT bin per channel); d_x must hold the gradient accumulated so far
+ * top-k itself has no gradient (the plan is a constant of the backward pass). */
+FTN_API int ftn_group_weights_backward(const float* amps, int B, int k, const FtnPeriodPlan* plan, const float* d_weights,
+                                       float* d_amps, void* stream);
+FTN_API int ftn_spectrum_amp_backward(const float* x, int B, int L, int C, int k, const FtnPeriodPlan* plan,
+                                      const float* d_amps, float* d_x, void* stream);
 
 /* ---- NVLink peer mailbox: the path's one collective without NCCL --------------
  * replaces the all-reduce of amp_channel_median.mean(dim=0) a sharded batch needs (timesnet.py:112).

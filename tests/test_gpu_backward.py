@@ -262,3 +262,60 @@ def test_aggregate_backward_matches_float64_autograd():
     assert _rel(xc.grad, xr.grad) < 1e-6
     assert _rel(dc.grad[:G], dr.grad[:G]) < 1e-6 and float(dc.grad[G:].abs().max()) == 0.0
     assert _rel(wc.grad[:, :G], wr.grad[:, :G]) < 1e-5
+
+
+def test_timesblock_backward_through_fft_selector():
+    """With the FFT selector the gradient also flows through the group weights (softmax <- amplitudes <- |rfft| of the
+    median channel), like the reference's autograd (timesnet.py:992-1009; tests/test_fft_period_selector.py:73-102
+    pins that amplitudes carry grad).  Float64 torch evaluation with the SAME bins (top-k has no gradient)."""
+    import copy
+    from timesnet_forecast.models.timesnet import FFTPeriodSelector, TimesBlock
+    torch.manual_seed(11)
+    C, L, B, k = 8, 36, 3, 3
+    blk = TimesBlock(C, [(3, 3)], 0.0, "gelu", d_ff=16, bottleneck_ratio=2.0)
+    for p in blk.parameters():
+        p.data.normal_(0, 0.3)
+    ref = copy.deepcopy(blk.inception).double()
+    blk = blk.cuda().eval()
+    object.__setattr__(blk, "period_selector", FFTPeriodSelector(k, L, 1))
+    t = torch.arange(L, dtype=torch.float32).view(1, L, 1)
+    x = (torch.sin(2 * torch.pi * t / 6 + torch.rand(B, 1, C) * 6) + 0.7 * torch.sin(2 * torch.pi * t / 9 + torch.rand(B, 1, C))
+         + 0.5 * torch.sin(2 * torch.pi * t / 4) + 0.3 * torch.randn(B, L, C))
+    u = torch.randn(B, L, C)
+    xc = x.cuda().requires_grad_()
+    got = blk(xc)
+    h = blk._last_plan.host()
+    nvld, G = h.n_valid, h.n_groups
+    bins = [int(h.freq[j]) for j in range(nvld)]
+    mapping = [int(h.mapping[j]) for j in range(nvld)]
+    assert G >= 2
+
+    def inc(m, g):
+        out = m.act(m.proj(torch.cat([p.branch(g) for p in m.paths], dim=1)))
+        return out + m.res_proj(g)
+    xr = x.double().requires_grad_()
+    amp = torch.fft.rfft(xr, dim=1).abs().median(dim=2).values                      # [B, F]
+    a = amp[:, bins]
+    valid = [j for j in range(nvld) if mapping[j] >= 0]
+    sm = torch.softmax(a[:, valid], dim=1)
+    w = [sum(sm[:, i] for i, j in enumerate(valid) if mapping[j] == g) for g in range(G)]
+    acc = xr
+    for g in range(G):
+        p, pad, cyc = int(h.grp_period[g]), int(h.grp_pad[g]), int(h.grp_cycles[g])
+        grid = torch.nn.functional.pad(xr, (0, 0, 0, pad)).reshape(B, cyc, p, C).permute(0, 3, 1, 2)
+        y = inc(ref[2], ref[1](inc(ref[0], grid)))
+        acc = acc + w[g].view(B, 1, 1) * (y - grid).permute(0, 2, 3, 1).reshape(B, cyc * p, C)[:, :L]
+    (acc * u.double()).sum().backward()
+    assert _rel(got, acc) < 2e-5
+    (got * u.cuda()).sum().backward()
+    assert _rel(xc.grad, xr.grad) < 1e-4
+    # the weight path is really there: with constant weights the input gradient differs measurably
+    blk2_in = x.cuda().requires_grad_()
+    from timesnet_forecast import autograd as ag
+    keep = ag.period_weights
+    try:
+        ag.period_weights = lambda xx, plan: plan.weights.detach()
+        (blk(blk2_in) * u.cuda()).sum().backward()
+    finally:
+        ag.period_weights = keep
+    assert _rel(blk2_in.grad, xr.grad) > 1e-3

@@ -377,11 +377,15 @@ def test_graph_recaptures_after_parameter_update():
 
 
 def test_forward_only_guard():
+    """bf16 stacks are forward-only and say so; an fp32 input that requires grad takes the differentiable route
+    (tests/test_gpu_backward.py) and agrees with the forward-only fp32 route."""
     blk, x = _elec_block_and_input(B=1)
     with pytest.raises(RuntimeError):
-        blk(x.float().requires_grad_(True))
+        blk(x.detach().clone().requires_grad_(True))             # bf16 + requires_grad
     with torch.no_grad():
-        blk(x)                                                   # explicit no_grad is fine
+        fast = blk(x.float())                                    # explicit no_grad is fine
+    slow = blk(x.float().requires_grad_(True))
+    assert slow.requires_grad and _rel(slow.detach(), fast) < 1e-4
     from timesnet_forecast.models.timesnet import TimesBlock
     tb = TimesBlock(16, [(3, 3)], 0.2, "gelu").cuda()
     object.__setattr__(tb, "period_selector", FixedSelector([4, 6], [1.0, 0.5]))
