@@ -270,3 +270,32 @@ def period_weights(x: torch.Tensor, plan) -> torch.Tensor:
 def group_weights(amps: torch.Tensor, plan) -> torch.Tensor:
     """Same for amplitudes a custom selector module returned (they may carry their own graph)."""
     return _GroupWeights.apply(amps, plan.weights, plan.plan_dev)
+
+
+class _Linear(torch.autograd.Function):
+    """``F.linear`` on the last dim (fp32): forward ``ftn_linear``, backward the two GEMMs dX = dY . W, dW = dY^T . X
+    (``ftn_gemm_f32``) and a column sum for the bias."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xf, wf = _f32c(x), _f32c(weight)
+        bf = None if bias is None else _f32c(bias)
+        ctx.save_for_backward(xf, wf)
+        ctx.has_bias = bias is not None
+        return nv.linear(xf, wf, bf)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, wf = ctx.saved_tensors
+        K, N = xf.shape[-1], wf.shape[0]
+        dy2 = _f32c(dy).reshape(-1, N)
+        x2 = xf.reshape(-1, K)
+        dx = nv.gemm_f32(dy2, wf).reshape(xf.shape) if ctx.needs_input_grad[0] else None
+        dw = nv.gemm_f32(dy2, x2, trans_a=True) if ctx.needs_input_grad[1] else None
+        db = _colsum(dy2) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable fp32 ``nn.Linear`` (value / temporal embeddings, static and context projections, late-bias head)."""
+    return _Linear.apply(x, weight, bias)

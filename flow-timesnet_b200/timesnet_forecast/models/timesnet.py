@@ -1475,6 +1475,96 @@ class TimesNet(nn.Module):
                                 self.context_norm.eps)
         return ctx
 
+    def _forward_differentiable(self, x, x_mark, series_static, series_ids):
+        """Training route (``model.differentiable = True`` or an input that requires grad; fp32 stack, dropout 0): the
+        same forward assembled from the differentiable building blocks of ``timesnet_forecast.autograd`` -- every dense
+        layer, LayerNorm, convolution, activation, the aggregation, the period weights and the NB head run in
+        libflowtimes kernels forward AND backward; torch autograd only chains them (views, ``cat``, the id gather and a
+        few broadcast adds / multiplies are its own ops).  The period search itself has no gradient (top-k)."""
+        from .. import autograd as ag
+        if (self.stack_dtype or torch.float32) != torch.float32:
+            raise RuntimeError("TimesNet: the differentiable route needs an fp32 stack (stack_dtype=None)")
+        if self.training and float(self.dropout) > 0.0:
+            raise RuntimeError("TimesNet: the differentiable route has no dropout (build the model with dropout=0)")
+        B, T, N = x.shape
+        L, dev = self.input_len, x.device
+        xv = x[:, -L:, :].contiguous()
+        mark = x_mark[:, -L:, :].contiguous() if x_mark is not None else None
+        self._ensure_embedding(xv, mark, series_static, series_ids)
+        steps = self.pred_len if self.mode == "direct" else self._out_steps
+        # ---- per-series context (timesnet.py:1886-1957) ----
+        comps = []
+        if self.static_proj is not None and series_static is not None:
+            st = series_static.unsqueeze(0).expand(B, -1, -1) if series_static.ndim == 2 else series_static
+            sp = ag.linear(st.to(device=dev, dtype=torch.float32).contiguous(), self.static_proj.weight, self.static_proj.bias)
+            if isinstance(self.static_norm, nn.LayerNorm):
+                sp = ag.layer_norm(sp, self.static_norm.weight, self.static_norm.bias, self.static_norm.eps)
+            comps.append(sp)
+        if self.series_embedding is not None and self.id_embed_dim > 0:
+            if series_ids is None:
+                ids = (torch.arange(N, device=dev) if self._series_id_reference is None
+                       else self._series_id_reference.to(dev)).view(1, -1)
+            else:
+                ids = series_ids.to(device=dev, dtype=torch.long)
+                ids = ids.unsqueeze(0) if ids.ndim == 1 else ids
+            ids = ids.expand(B, -1) if ids.size(0) == 1 and B > 1 else ids
+            comps.append(self.series_embedding.weight[ids])                  # row gather: torch indexing (and its index_add)
+        ctx = None
+        if comps:
+            ctx = torch.cat(comps, dim=-1).contiguous()
+            if self.context_norm is not None:
+                ctx = ag.layer_norm(ctx, self.context_norm.weight, self.context_norm.bias, self.context_norm.eps)
+        feat_in = xv
+        if (ctx is not None and self.use_zero_mean_context and self.context_coeff is not None
+                and self.temporal_context is not None):                      # timesnet.py:1966-1983
+            coeff = ag.linear(ctx, self.context_coeff.weight, self.context_coeff.bias)            # [B, N, R]
+            basis = self.temporal_context._basis(L, xv)                                            # [L, R] constant
+            tc = ag.linear(coeff, basis, None).permute(0, 2, 1)                                    # einsum('lr,bnr->bln')
+            tc = tc - tc.mean(dim=1, keepdim=True)
+            feat_in = feat_in + tc * self.temporal_context.scale.to(torch.float32)
+        if ctx is not None and self.use_constant_context_bias and self.context_proj is not None:
+            cb = ag.linear(ctx, self.context_proj.weight, self.context_proj.bias)
+            feat_in = feat_in + cb.squeeze(-1).unsqueeze(1)
+        # ---- K0: DataEmbedding (timesnet.py:1295-1320) ----
+        emb = self.embedding
+        value = ag.linear(feat_in.contiguous(), emb.value_embedding.weight, emb.value_embedding.bias)
+        aux = emb.position_embedding.table(L, dev).unsqueeze(0)
+        if emb.temporal_embedding is not None and mark is not None:
+            aux = aux + ag.linear(mark.to(torch.float32), emb.temporal_embedding.weight, emb.temporal_embedding.bias)
+        if emb.embed_norm_mode == "decoupled":
+            auxn = ag.layer_norm(aux.expand(B, -1, -1).contiguous() if aux.size(0) == 1 else aux, emb.aux_norm.weight,
+                                 emb.aux_norm.bias, emb.aux_norm.eps)
+            seq = value + emb.gate.to(torch.float32) * auxn
+        elif emb.embed_norm_mode == "layer":
+            seq = ag.layer_norm(value + aux, emb.norm.weight, emb.norm.bias, emb.norm.eps)
+        elif emb.embed_norm_mode == "none":
+            seq = value + aux
+        else:
+            raise NotImplementedError(f"differentiable route: embed_norm_mode={emb.embed_norm_mode!r}")
+        # ---- TimesBlock stack + shared LayerNorm (timesnet.py:2050-2061) ----
+        for block in self.blocks:
+            object.__setattr__(block, "period_selector", self.period_selector)
+            seq = block.forward_norm_differentiable(seq.contiguous(), self.layer_norm)
+        # ---- head (timesnet.py:2008-2014, 2063-2093) ----
+        hist_steps = min(steps, L)
+        hist = xv[:, -hist_steps:, :]
+        if hist_steps < steps:
+            hist = torch.cat([hist, hist[:, -1:, :].expand(-1, steps - hist_steps, -1)], dim=1)
+        Wt = self.forecast_time_proj.weight[-steps:, :] if steps != self.pred_len else self.forecast_time_proj.weight
+        bt = self.forecast_time_proj.bias[-steps:] if steps != self.pred_len else self.forecast_time_proj.bias
+        late = gate = None
+        if (ctx is not None and self.late_bias_head is not None and self.late_bias_norm is not None
+                and isinstance(self.late_bias_gate, nn.Parameter)):
+            c = ag.layer_norm(ctx, self.late_bias_norm.weight, self.late_bias_norm.bias, self.late_bias_norm.eps)
+            late = ag.linear(c, self.late_bias_head.weight, self.late_bias_head.bias)             # [B, N, steps]
+            gate = self.late_bias_gate.reshape(-1)
+        if isinstance(self.min_sigma_vector, torch.Tensor) and self.min_sigma_vector.numel() > 0:
+            floor = self.min_sigma_vector.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        else:
+            floor = torch.full((N,), self.min_sigma, dtype=torch.float32, device=dev)
+        return ag.nb_head(seq, Wt, bt, self.mu_head.weight, self.mu_head.bias, self.sigma_head.weight, self.sigma_head.bias,
+                          hist.contiguous(), late, gate, floor)
+
     def stack_forward(self, seq: torch.Tensor) -> torch.Tensor:
         """TimesBlock stack on pre-embedded features ``[B, L, d_model]``: ``n_layers x (TimesBlock + residual +
         shared LayerNorm)`` (timesnet.py:2050-2061).  Sync-free, so it can be captured in a CUDA graph."""
@@ -1519,6 +1609,8 @@ class TimesNet(nn.Module):
         if x.dtype != torch.float32:
             raise TypeError("TimesNet.forward takes float32 input (the reference rejects half inputs too); "
                             "use stack_dtype=torch.bfloat16 for the bf16 TimesBlock stack")
+        if _wants_grad(self, x):
+            return self._forward_differentiable(x, x_mark, series_static, series_ids)
         _forward_only_guard(self, x, self.dropout)
         L = self.input_len
         dev = x.device

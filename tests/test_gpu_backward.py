@@ -319,3 +319,54 @@ def test_timesblock_backward_through_fft_selector():
     finally:
         ag.period_weights = keep
     assert _rel(blk2_in.grad, xr.grad) > 1e-3
+
+
+@pytest.mark.parametrize("name", ["toy_direct", "toy_recursive"])
+def test_timesnet_training_step_gradients_match_oracle_autograd(golden_dir, name):
+    """One training step's gradients through the WHOLE model (embedding, context, TimesBlock stack with the period-weight
+    path, NB head, NB-NLL) on the differentiable route, against torch autograd of the oracle (= the reference's forward,
+    pinned by the goldens) on the CPU with the same weights.  fp32 on both sides: 2e-3 of the largest gradient."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import flowtimes_oracle as orc
+    import flowtimes_synth as syn
+    from test_gpu_parity import _build_model, _wl
+    from timesnet_forecast.autograd import nb_nll
+    c = torch.load(golden_dir / "model_toy.pt")[name]
+    wl = _wl(c["workload"])
+    m, x, static, ids = _build_model(c, wl)
+    m.dropout = 0.0
+    for b in m.blocks:
+        b._dropout = 0.0
+    m.differentiable = True
+    for b in m.blocks:
+        b.differentiable = True
+    y, mask = c["y"].cuda(), c["mask"].cuda()
+    rate, disp = m(x, series_static=static, series_ids=ids)
+    assert rate.requires_grad
+    steps = wl.H if wl.mode == "direct" else 1
+    loss = nb_nll(y[:, :steps], rate, disp, mask[:, :steps].to(torch.uint8).contiguous() if mask is not None else None)
+    loss.backward()
+    # oracle autograd
+    w = {k: v.clone().float().requires_grad_(v.is_floating_point()) for k, v in c["state"].items()}
+    cfg = orc.ModelCfg(wl.T, wl.H, wl.d_model, wl.n_layers, wl.k_periods, wl.mode, "gelu", wl.min_period_threshold, 1e-3,
+                       wl.context_rank > 0, wl.context_rank)
+    xr = syn.planted_series(wl.B, c["T_in"], wl.N, seed=c["x_seed"])
+    r, d = orc.timesnet_forward(xr, w, cfg, series_static=c["static"], series_ids=c["ids"],
+                                min_sigma_vector=c["min_sigma_vector"])
+    lo = orc.nb_nll(c["y"][:, :steps], r, d, c["mask"][:, :steps] if c["mask"] is not None else None)
+    lo.backward()
+    assert _rel(loss, lo) < 1e-4
+    checked = 0
+    for k, p in m.named_parameters():
+        if w[k].grad is None:
+            continue
+        assert p.grad is not None, f"{k}: no gradient on the differentiable route"
+        gr = w[k].grad
+        if float(gr.abs().max()) < 1e-10:
+            assert float(p.grad.abs().max()) < 1e-6, k
+            continue
+        assert _rel(p.grad, gr) < 2e-3, f"{k}: {_rel(p.grad, gr):.2e}"
+        checked += 1
+    assert checked >= 20
