@@ -34,8 +34,10 @@ int check_cuda(cudaError_t e, const char* what);
   do {                                                             \
     ::ftn::count_launch();                                         \
     if (::ftn::check_cuda(cudaGetLastError(), name)) return 3;     \
+    if (::ftn::launch_sync_debug(name)) return 3;                  \
   } while (0)
 
+int launch_sync_debug(const char* name);   // FLOWTIMES_SYNC_LAUNCH: synchronise after every launch, name the kernel that faulted
 void count_launch();   // every kernel this library enqueues is counted (bench.py "gpu_launches")
 
 // Optional per-call CUDA-event timing of one kernel family (bench.py roofline leg):

@@ -28,6 +28,18 @@ int check_cuda(cudaError_t e, const char* what) {
   return 1;
 }
 
+// diagnostic switch (never set in production: it serialises host and device)
+int launch_sync_debug(const char* name) {
+  static const bool on = getenv("FLOWTIMES_SYNC_LAUNCH") != nullptr;
+  if (!on) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(cudaStreamPerThread, &cs) != cudaSuccess) (void)cudaGetLastError();
+  const cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaErrorStreamCaptureUnsupported) { (void)cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) fprintf(stderr, "[flowtimes] device fault in or before %s: %s\n", name, cudaGetErrorName(e));
+  return check_cuda(e, name);
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -277,10 +277,14 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
       const int buf = i & 1;
       const float inv = 1.0f / (float)u.PW;
       for (int m = 0; m < u.tiles; ++m) {
-        if (mid == 16 && (m & 1) != slot) continue;
         const int bi = buf * C2_MAX_TILES + m;
-        mbar_wait_relaxed(&bars[C2_TILE_FULL + bi], (phase_bits >> bi) & 1u);
-        phase_bits ^= 1u << bi;
+        const bool mine = mid == 32 || (m & 1) == slot;
+        // mid 16, single-tile unit: the odd-tile warps own nothing here, but they must not run ahead of the unit --
+        // their ACC_EMPTY arrivals of unit i + 2 would otherwise complete the phase of unit i before the even-tile
+        // warps have drained it (many units per CTA: 256 windows of L = 96).  They wait for tile 0 and read nothing.
+        if (mine || u.tiles == 1) mbar_wait_relaxed(&bars[C2_TILE_FULL + bi], (phase_bits >> bi) & 1u);
+        phase_bits ^= 1u << bi;   // every tile barrier of the unit completes once, whether or not this warp waits on it
+        if (!mine) continue;
         tc_fence_after();
         float v[16];
         tmem_ld16(tmem_base + buf * 256 + m * 32 + col0 + ((uint32_t)(quad * 32) << 16), v);

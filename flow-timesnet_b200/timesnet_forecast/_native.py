@@ -155,10 +155,18 @@ class FlowTimesError(RuntimeError):
     pass
 
 
+_SYNC_CHECK = bool(os.environ.get("FLOWTIMES_SYNC_CHECK"))   # diagnostic: synchronise after every call and name the one that faulted
+
+
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().ftn_last_error().decode("utf-8", "replace")
         raise FlowTimesError(f"{what} failed (rc={rc}): {msg}")
+    if _SYNC_CHECK and not torch.cuda.is_current_stream_capturing():
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError as e:
+            raise FlowTimesError(f"{what}: device fault after the call: {e}") from e
 
 
 def dtype_code(dt: torch.dtype) -> int:

@@ -254,6 +254,28 @@ def test_full_size_elec_windows_match_oracle():
     assert _rel(out[-1:], tr.out) < REL_BF16
 
 
+@pytest.mark.parametrize("dname", ["f32", "bf16"])
+def test_full_size_etth1_windows_match_oracle(dname):
+    """BASELINE etth1 launch geometry (B=256, L=96, C=64, F=256, mid=16): 1280 small images, tens of units per
+    persistent CTA in every stage.  bf16 takes tc_gemm2 / tc_conv2 (image-resident, mid 16) / tc_gemm, fp32 the
+    three-plane route; first, middle and last windows of the full batch must equal the oracle run on them alone."""
+    wl = syn.WORKLOADS["etth1"]
+    dt = torch.float32 if dname == "f32" else torch.bfloat16
+    w = syn.stack_weights(wl, seed=0)
+    x = syn.white_features(wl.B, wl.T, wl.d_model, seed=1).to(dt)
+    periods = [24, 12, 7, 48, 6]
+    g = torch.Generator().manual_seed(3)
+    amps = torch.randn(wl.B, 5, generator=g)
+    blk = _make_block(wl, w)
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    torch.cuda.synchronize()
+    tol = REL_F32 if dname == "f32" else REL_BF16
+    for sl in (slice(0, 2), slice(127, 129), slice(wl.B - 1, wl.B)):
+        tr = orc.timesblock_from_periods(x[sl], periods, amps[sl].to(dt), w, "blocks.0.inception.")
+        assert _rel(out[sl], tr.out) < tol
+
+
 def test_elec_block_with_long_periods_matches_oracle():
     """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
     inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""

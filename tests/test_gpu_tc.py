@@ -36,10 +36,22 @@ def test_tc_conv_matches_simt_conv(mid, L, periods, variant):
         pytest.skip("tc_conv4 is written for mid = 32")
     """k x k stage alone: tcgen05 implicit-GEMM kernel vs the fp32-math SIMT kernel on the same
     tile-major bf16 activations (identical inputs, fp32 accumulation in both -> <= 1 bf16 ulp)."""
-    import flowtimes_synth as syn
+    _conv_vs_simt(mid, L, periods, variant, B=3)
+
+
+@pytest.mark.parametrize("mid,L,periods,B", [(16, 96, [24, 12, 7, 48, 6], 256), (32, 96, [24, 12, 7, 48, 6], 128),
+                                              (16, 336, [24, 12, 7, 48, 335], 40)])
+def test_tc_conv2_many_units_per_cta(mid, L, periods, B):
+    """Image-resident kernel with tens of units per persistent CTA (the etth1 batch: 256 windows x 5 groups over 148
+    CTAs).  mid = 16 splits the epilogue warps by tile parity; on single-tile images the odd-tile warps own nothing
+    and used to run ahead of the unit, breaking the accumulator hand-over (trap after a bounded spin)."""
+    _conv_vs_simt(mid, L, periods, 2, B=B)
+
+
+def _conv_vs_simt(mid, L, periods, variant, B):
+    import flowtimes_synth as syn  # noqa: F401
     from timesnet_forecast import _native as nv
     from timesnet_forecast.models.timesnet import InceptionBlock
-    B = 3
     C = mid * 4
     torch.manual_seed(0)
     blk = InceptionBlock(C, C, [(3, 3), (5, 5), (7, 7)], 0.0, "gelu", bottleneck_ratio=4.0).cuda()
