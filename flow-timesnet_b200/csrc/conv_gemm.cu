@@ -403,7 +403,7 @@ extern "C" size_t ftn_inception_workspace_bytes(int B, int L, int max_groups, co
   if (!a || !b || B <= 0 || L <= 0 || max_groups <= 0) return 256;
   size_t simt = stack_layout(B, L, max_groups, a, b).total;
   size_t tcb = (a->mid > 0 && b->mid > 0) ? tc_workspace_bytes(B, L, max_groups, a, b) : 0;
-  if (a->mid > 0 && b->mid > 0 && a->w_in_s3 && b->w_in_s3) {
+  if (a->mid > 0 && b->mid > 0 && ((a->w_in_s3 && b->w_in_s3) || (a->w_in_h2 && b->w_in_h2))) {
     const size_t sp = tc_split_workspace_bytes(B, L, max_groups, a, b);
     tcb = sp > tcb ? sp : tcb;
   }
@@ -428,7 +428,7 @@ extern "C" int ftn_period_conv(const void* x, int dtype, int B, int L, int C, co
   TimedScope timed(FTN_FAM_CONV, st);
   if (tc_path_eligible(dtype, C, a, b))   // bf16 + channel counts the tensor-core tiles accept
     return period_conv_tc(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
-  if (tc_split_eligible(dtype, C, a, b))  // fp32 activations as three bf16 planes on the tensor cores
+  if (tc_split_eligible(dtype, C, a, b))  // fp32 activations as two fp16 / three bf16 planes on the tensor cores
     return period_conv_tc_split(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);
   if (dtype == FTN_F32)
     return period_conv_impl<float>(x, B, L, C, plan, max_groups, a, b, act, delta, workspace, st);

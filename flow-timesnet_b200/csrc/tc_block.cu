@@ -31,21 +31,42 @@ size_t tc_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeight
   return 2 * al256(rows * nbA * 2) + al256(rows * (size_t)(a->cout > a->cin ? a->cout : a->cin) * 2) + 2 * al256(rows * nbB * 2) + 256;
 }
 
-// ---- fp32 activations on the tensor cores: the same six stages with three-plane bf16 operands (tc_gemm.cu) ----
-bool tc_split_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
-  static const bool off = getenv("FLOWTIMES_NO_SPLIT") != nullptr;   // A/B switch: fp32 chain on the SIMT kernels
-  if (off || dtype != FTN_F32 || C % 16) return false;
+// ---- fp32 activations on the tensor cores: the same six stages with split operands (tc_gemm.cu) ----
+// Two forms: two fp16 planes (three products per MAC; the default when the packer supplied the *_h2 weights) and three
+// bf16 planes (six products; FLOWTIMES_SPLIT_BF16 forces it, and it is what remains when a weight tensor does not fit the
+// fp16 range).
+static bool split_ok_for(const FtnInceptionWeights* a, const FtnInceptionWeights* b, bool h2) {
   const FtnInceptionWeights* ws[2] = {a, b};
   for (const FtnInceptionWeights* w : ws) {
     if (w->mid <= 0 || w->mid % 16 || w->cin % 16 || w->cout % 16) return false;
-    if (!w->w_in_s3 || !w->w_out_s3) return false;
-    if (w->w_res && !w->w_res_s3) return false;
-    if (!tc_convs_eligible(w, 3)) return false;
+    if (h2) {
+      if (!w->w_in_h2 || !w->w_out_h2) return false;
+      if (w->w_res && !w->w_res_h2) return false;
+      if (!tc_convs_eligible(w, 2)) return false;
+    } else {
+      if (!w->w_in_s3 || !w->w_out_s3) return false;
+      if (w->w_res && !w->w_res_s3) return false;
+      if (!tc_convs_eligible(w, 3)) return false;
+    }
   }
   return true;
 }
 
+// 0 = no split route, 2 = two fp16 planes, 3 = three bf16 planes
+static int tc_split_planes(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  static const bool off = getenv("FLOWTIMES_NO_SPLIT") != nullptr;        // A/B switch: fp32 chain on the SIMT kernels
+  static const bool bf16_planes = getenv("FLOWTIMES_SPLIT_BF16") != nullptr;   // A/B switch: three bf16 planes
+  if (off || dtype != FTN_F32 || C % 16) return 0;
+  if (!bf16_planes && split_ok_for(a, b, true)) return 2;
+  return split_ok_for(a, b, false) ? 3 : 0;
+}
+
+bool tc_split_eligible(int dtype, int C, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  return tc_split_planes(dtype, C, a, b) != 0;
+}
+
 size_t tc_split_workspace_bytes(int B, int L, int max_groups, const FtnInceptionWeights* a, const FtnInceptionWeights* b) {
+  // sized for three planes whichever form runs (the choice may differ between calls through the A/B switch)
   const size_t rows = (size_t)tc_worst_case_tiles(B, L, max_groups) * 128;
   const size_t nbA = (size_t)a->n_branch * a->mid, nbB = (size_t)b->n_branch * b->mid;
   return al256((size_t)B * L * 3 * a->cin * 2 + 3 * 128 * a->cin * 2) + 2 * al256(rows * 3 * nbA * 2) +
@@ -55,36 +76,44 @@ size_t tc_split_workspace_bytes(int B, int L, int max_groups, const FtnInception
 int period_conv_tc_split(const void* x, int B, int L, int C, const FtnPeriodPlan* plan, int max_groups,
                          const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act, void* delta, void* workspace,
                          cudaStream_t st) {
+  const int np = tc_split_planes(FTN_F32, C, a, b);
+  FTN_REQUIRE(np != 0, "period_conv_tc_split: no split form applies to this block");
+  const bool h2 = np == 2;
   const int tiles = tc_worst_case_tiles(B, L, max_groups);
   const long long rows = (long long)tiles * 128;
   const int NBa = a->n_branch * a->mid, NBb = b->n_branch * b->mid, F = a->cout;
   char* ws = reinterpret_cast<char*>(workspace);
   size_t o = 0;
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)B * L * 3 * C * 2 + 3 * 128 * C * 2);
-  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * 3 * NBa * 2);
-  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * 3 * NBa * 2);
-  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * 3 * F * 2);
-  __nv_bfloat16* g1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * 3 * NBb * 2);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)B * L * np * C * 2 + np * 128 * C * 2);
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * np * NBa * 2);
+  __nv_bfloat16* h2b = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * np * NBa * 2);
+  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * np * F * 2);
+  __nv_bfloat16* g1 = reinterpret_cast<__nv_bfloat16*>(ws + o); o += al256((size_t)rows * np * NBb * 2);
   __nv_bfloat16* g2 = reinterpret_cast<__nv_bfloat16*>(ws + o);
   const float* xf = reinterpret_cast<const float*>(x);
-  if (int rc = split3_launch(xf, (long long)B * L, C, xs, st, true)) return rc;
+  if (int rc = split3_launch(xf, (long long)B * L, C, xs, st, true, h2 ? 1 : 0)) return rc;
+  auto W = [&](const void* s3, const void* w2) { return (const __nv_bfloat16*)(h2 ? w2 : s3); };
   TcGemmArgs base{};
   base.plan = plan; base.B = B; base.L = L; base.max_groups = max_groups; base.n_tiles = tiles; base.act = act; base.split = 1;
+  base.split_fmt = h2 ? 1 : 0;
   // S1
   TcGemmArgs s = base;
-  s.a1 = xs; s.a1_seq = 1; s.a1_ld = 3 * C; s.w1 = (const __nv_bfloat16*)a->w_in_s3; s.bias1 = a->b_in; s.K1 = C; s.N = NBa;
-  s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = 3 * NBa;
+  s.a1 = xs; s.a1_seq = 1; s.a1_ld = np * C; s.w1 = W(a->w_in_s3, a->w_in_h2); s.bias1 = a->b_in; s.K1 = C; s.N = NBa;
+  s.scale1 = h2 ? a->sc_in : 0.f;
+  s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = h1; s.ldo = np * NBa;
   { TimedScope t(FTN_FAM_S1, st); if (int rc = tc_gemm_launch(s, st)) return rc; }
   // S2
-  { TimedScope t(FTN_FAM_KK_A, st); if (int rc = tc_convs_launch(plan, B, L, max_groups, h1, h2, 3 * NBa, a, 3, st, false)) return rc; }
+  { TimedScope t(FTN_FAM_KK_A, st); if (int rc = tc_convs_launch(plan, B, L, max_groups, h1, h2b, np * NBa, a, np, st, false)) return rc; }
   {
     TimedScope t(FTN_FAM_MID, st);
     // S3
     s = base;
-    s.a1 = h2; s.a1_seq = 0; s.a1_ld = 3 * NBa; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)a->w_out_s3; s.bias1 = a->b_out;
-    s.K1 = NBa; s.N = F; s.epi = TC_EPI_BLOCK_A; s.out = a2; s.ldo = 3 * F;
+    s.a1 = h2b; s.a1_seq = 0; s.a1_ld = np * NBa; s.a1_rows = rows; s.w1 = W(a->w_out_s3, a->w_out_h2); s.bias1 = a->b_out;
+    s.scale1 = h2 ? a->sc_out : 0.f;
+    s.K1 = NBa; s.N = F; s.epi = TC_EPI_BLOCK_A; s.out = a2; s.ldo = np * F;
     if (a->w_res) {
-      s.a2 = xs; s.a2_seq = 1; s.a2_ld = 3 * C; s.w2 = (const __nv_bfloat16*)a->w_res_s3; s.bias2 = a->b_res; s.K2 = C;
+      s.a2 = xs; s.a2_seq = 1; s.a2_ld = np * C; s.w2 = W(a->w_res_s3, a->w_res_h2); s.bias2 = a->b_res; s.K2 = C;
+      s.scale2 = h2 ? a->sc_res : 0.f;
       s.res = TC_RES_ACC2;
     } else {
       s.res = TC_RES_SEQ; s.res_ptr = xf; s.res_ld = C;
@@ -92,21 +121,24 @@ int period_conv_tc_split(const void* x, int B, int L, int C, const FtnPeriodPlan
     if (int rc = tc_gemm_launch(s, st)) return rc;
     // S4
     s = base;
-    s.a1 = a2; s.a1_seq = 0; s.a1_ld = 3 * F; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_in_s3; s.bias1 = b->b_in;
-    s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = 3 * NBb;
+    s.a1 = a2; s.a1_seq = 0; s.a1_ld = np * F; s.a1_rows = rows; s.w1 = W(b->w_in_s3, b->w_in_h2); s.bias1 = b->b_in;
+    s.scale1 = h2 ? b->sc_in : 0.f;
+    s.K1 = F; s.N = NBb; s.epi = TC_EPI_PLAIN; s.res = TC_RES_NONE; s.out = g1; s.ldo = np * NBb;
     if (int rc = tc_gemm_launch(s, st)) return rc;
   }
   // S5
-  { TimedScope t(FTN_FAM_KK_B, st); if (int rc = tc_convs_launch(plan, B, L, max_groups, g1, g2, 3 * NBb, b, 3, st, false)) return rc; }
+  { TimedScope t(FTN_FAM_KK_B, st); if (int rc = tc_convs_launch(plan, B, L, max_groups, g1, g2, np * NBb, b, np, st, false)) return rc; }
   // S6
   s = base;
-  s.a1 = g2; s.a1_seq = 0; s.a1_ld = 3 * NBb; s.a1_rows = rows; s.w1 = (const __nv_bfloat16*)b->w_out_s3; s.bias1 = b->b_out;
+  s.a1 = g2; s.a1_seq = 0; s.a1_ld = np * NBb; s.a1_rows = rows; s.w1 = W(b->w_out_s3, b->w_out_h2); s.bias1 = b->b_out;
+  s.scale1 = h2 ? b->sc_out : 0.f;
   s.K1 = NBb; s.N = C; s.epi = TC_EPI_DELTA; s.out = delta; s.ldo = C; s.x = xf; s.C = C;
   if (b->w_res) {
-    s.a2 = a2; s.a2_seq = 0; s.a2_ld = 3 * F; s.a2_rows = rows; s.w2 = (const __nv_bfloat16*)b->w_res_s3; s.bias2 = b->b_res;
+    s.a2 = a2; s.a2_seq = 0; s.a2_ld = np * F; s.a2_rows = rows; s.w2 = W(b->w_res_s3, b->w_res_h2); s.bias2 = b->b_res;
+    s.scale2 = h2 ? b->sc_res : 0.f;
     s.K2 = F; s.res = TC_RES_ACC2;
   } else {
-    s.res = TC_RES_POS; s.res_ptr = a2; s.res_ld = 3 * F;
+    s.res = TC_RES_POS; s.res_ptr = a2; s.res_ld = np * F;
   }
   TimedScope t(FTN_FAM_S6, st);
   return tc_gemm_launch(s, st);
@@ -369,8 +401,8 @@ extern "C" FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, c
     return tc_conv2_launch_filtered(plan, B, L, max_groups, src, dst, ld, w, caps, st);
   }
   if (use_tc == 2) return tc_conv2_launch_filtered(plan, B, L, max_groups, src, dst, ld, w, nullptr, st, -1, false);
-  if (use_tc == 5 || use_tc == 6) {   // streaming kernel: 5 = bf16 activations, 6 = three-plane fp32 (ld counts all planes)
-    const int ns = use_tc == 5 ? 1 : 3;
+  if (use_tc >= 5 && use_tc <= 7) {   // streaming kernel: 5 = bf16 activations, 6 = three-plane fp32, 7 = two-plane fp16 (ld counts all planes)
+    const int ns = use_tc == 5 ? 1 : (use_tc == 6 ? 3 : 2);
     FTN_REQUIRE(tc_convs_eligible(w, ns), "ftn_debug_conv_tiled: tc_convs not eligible for this block");
     return tc_convs_launch(plan, B, L, max_groups, src, dst, ld, w, ns, st, false);
   }

@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace ftn {
@@ -207,6 +208,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// the same with fp16 operands (format code 0 for A and B): the two-plane form of the fp32 chain (split_h2 below)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) /*D=f32*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // K-major operand tile stored by TMA with SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) /*LBO (unused)*/ |
@@ -383,6 +388,29 @@ __device__ __forceinline__ float act_fast(float v, int act) { return act == 1 ? 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- fp32 as TWO fp16 planes ("h2"): v = hi + lo, hi = fp16(v), lo = fp16(v - hi) -------------------------------
+// 11 + 11 significand bits: a product a . w = a_hi w_hi + a_hi w_lo + a_lo w_hi drops only lo . lo (2^-22 of the
+// result), i.e. fp32-class accuracy from THREE tensor-core MMAs instead of the six of the three-plane bf16 form.
+// fp16 has 5 exponent bits: finite magnitudes above 65504 saturate (activations of this chain are O(1..100); NaN still
+// propagates), values below 2^-14 * 2^11 = 0.125 keep an ABSOLUTE precision of 2^-25 (subnormal lo) -- weights are
+// therefore pre-scaled by an exact power of two on the host (FtnInceptionWeights::sc_*), activations are not.
+__device__ __forceinline__ float h2_sat(float v) {
+  return v != v ? v : fminf(fmaxf(v, -65504.0f), 65504.0f);
+}
+// planes of the pair (a, b): a in the low half-word, b in the high one (memory order)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = h2_sat(a);
+  b = h2_sat(b);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 h2_to_float2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
 }
 
 }  // namespace tc

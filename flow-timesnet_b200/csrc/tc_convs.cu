@@ -8,6 +8,10 @@
 //           three column groups of the accumulator that the epilogue adds up.  A small-N MMA costs what a full one
 //           does (A-fetch bound), so this halves the MMA stream.
 //
+//   NS = 2  fp32 activations as two fp16 planes [rows][2 NB] (tc_common.cuh: split_h2; three products per MAC): TWO MMAs
+//           per tap and K16 step, a_hi . [w_hi | w_lo] (N = 2 mid) and a_lo . w_hi (N = mid); the weights were scaled by
+//           a power of two on the host, `scale` undoes it on the accumulator.
+//
 //   out[pos][n] = bias[n] + sum_{dr,dw} sum_c in[pos shifted by (dr,dw)][c] * W[dr][dw][n][c]
 // on the folded [cycles, period] grid with zero "same" padding (timesnet.py:588, :1044-1057).
 //
@@ -52,6 +56,7 @@ struct TcConvsArgs {
   int kh[FTN_MAX_BRANCH], kw[FTN_MAX_BRANCH], ut[FTN_MAX_BRANCH];   // ut: taps per weight slot (kw or 1)
   const uint8_t* w[FTN_MAX_BRANCH];    // [tap][chunk][plane][n][8] bf16
   const float* bias[FTN_MAX_BRANCH];
+  float scale[FTN_MAX_BRANCH];         // NS = 2: power of two that undoes the host-side weight scaling (1 otherwise)
 };
 
 struct CsGroup {
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
     // elect per K16 step.  (First version: 64-bit descriptors rebuilt under elect.sync per MMA, 230 cycles per MMA at
     // mid = 16; a single-lane loop needed R2UR broadcast loops per operand, 175 cycles per MMA at mid = 64.)
     {
-      const uint32_t idesc = make_idesc_bf16(CS_BM, mid), idesc2 = make_idesc_bf16(CS_BM, 2 * mid),
+      const uint32_t idesc = NS == 2 ? make_idesc_f16(CS_BM, mid) : make_idesc_bf16(CS_BM, mid),
+                     idesc2 = NS == 2 ? make_idesc_f16(CS_BM, 2 * mid) : make_idesc_bf16(CS_BM, 2 * mid),
                      idesc3 = make_idesc_bf16(CS_BM, NS == 3 ? 3 * mid : mid);
       const uint32_t a_hi = (uint32_t)(make_desc_interleaved(0, LBO_A) >> 32);
       const uint32_t b_hi = (uint32_t)(make_desc_interleaved(0, LBO_W) >> 32);
@@ -237,6 +243,17 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
                     mma_bf16_lohi(acc, a0 + ko_a, a_hi, b_k, b_hi, idesc3, accum);
                     mma_bf16_lohi(acc, a1 + ko_a, a_hi, b_k, b_hi, idesc2, 1u);
                     mma_bf16_lohi(acc, a2 + ko_a, a_hi, b_k, b_hi, idesc, 1u);
+                  }
+                  accum = 1;
+                }
+              } else if (NS == 2) {
+                // fp16 planes hi = 0, lo = 1: a_hi . [w_hi | w_lo], a_lo . w_hi -> column groups 0, 1
+                const uint32_t a0 = a_tap, a1 = a_tap + a_pl;
+                uint32_t ko_a = 0, b_k = tap_lo;
+                for (int ks = 0; ks < ksteps; ++ks, ko_a += ks_a, b_k += ks_w) {
+                  if (elect_one()) {
+                    mma_bf16_lohi(acc, a0 + ko_a, a_hi, b_k, b_hi, idesc2, accum);
+                    mma_bf16_lohi(acc, a1 + ko_a, a_hi, b_k, b_hi, idesc, 1u);
                   }
                   accum = 1;
                 }
@@ -365,6 +382,14 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = (__uint_as_float(r2[k]) + __uint_as_float(r1[k])) + __uint_as_float(r0[k]);
+        } else if (NS == 2) {   // two column groups; the weights carried a power-of-two scale
+          uint32_t r0[16], r1[16];
+          tmem_ld16_nowait(tcol, r0);
+          tmem_ld16_nowait(tcol + mid, r1);
+          tmem_ld_wait();
+          const float sc = p.scale[u.j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = (__uint_as_float(r1[k]) + __uint_as_float(r0[k])) * sc;
         } else {
           tmem_ld16(tcol, v);
         }
@@ -372,7 +397,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] += __ldg(bias + c + k);
           __nv_bfloat16* dst = p.out + (u.img_row0 + (size_t)tt) * p.ld + u.j * mid + c;
-          if (NS == 3) {
+          if (NS == 2) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_h2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+            uint4* d0 = reinterpret_cast<uint4*>(dst);
+            uint4* d1 = reinterpret_cast<uint4*>(dst + p.NB);
+            d0[0] = make_uint4(h[0], h[1], h[2], h[3]); d0[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            d1[0] = make_uint4(l[0], l[1], l[2], l[3]); d1[1] = make_uint4(l[4], l[5], l[6], l[7]);
+          } else if (NS == 3) {
             uint32_t h[8], m[8], l[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -441,11 +474,11 @@ static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
 
 bool tc_convs_eligible(const FtnInceptionWeights* w, int ns) {
   if (w->mid < 16 || w->mid > 128 || w->mid % 16) return false;
-  if (ns != 1 && ns != 3) return false;
+  if (ns != 1 && ns != 2 && ns != 3) return false;
   if (ns == 3 && w->mid > 80) return false;   // 3 mid <= 256 (one MMA's N) and 6 mid <= 512 TMEM columns
   for (int j = 0; j < w->n_branch; ++j) {
     if (!(w->kh[j] & 1) || !(w->kw[j] & 1)) return false;
-    if (!(ns == 3 ? w->w_kk_img3[j] : w->w_kk_img[j])) return false;
+    if (!(ns == 3 ? w->w_kk_img3[j] : (ns == 2 ? w->w_kk_img2[j] : w->w_kk_img[j]))) return false;
   }
   return convs_layout(w, ns).ok;
 }
@@ -461,8 +494,9 @@ int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   long long units_max = 0;
   for (int j = 0; j < w->n_branch; ++j) {
     a.kh[j] = w->kh[j]; a.kw[j] = w->kw[j]; a.ut[j] = l.ut[j];
-    a.w[j] = (const uint8_t*)(ns == 3 ? w->w_kk_img3[j] : w->w_kk_img[j]);
+    a.w[j] = (const uint8_t*)(ns == 3 ? w->w_kk_img3[j] : (ns == 2 ? w->w_kk_img2[j] : w->w_kk_img[j]));
     a.bias[j] = w->b_kk[j];
+    a.scale[j] = (ns == 2 && w->sc_kk[j] != 0.f) ? w->sc_kk[j] : 1.f;
     // worst case: period L - 1 (two cycles), padded width L - 1 + 2 hw
     units_max += (long long)max_groups * B * ((2ll * (L + 2 * (w->kw[j] / 2)) + CS_BM - 1) / CS_BM);
   }
@@ -471,6 +505,9 @@ int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   if (ns == 3) {
     FTN_DYN_SMEM(tc_convs_kernel<3>, l.smem);
     FTN_CUDA(launch_pdl(dependent, tc_convs_kernel<3>, dim3(ctas), dim3(CS_THREADS), l.smem, st, a));
+  } else if (ns == 2) {
+    FTN_DYN_SMEM(tc_convs_kernel<2>, l.smem);
+    FTN_CUDA(launch_pdl(dependent, tc_convs_kernel<2>, dim3(ctas), dim3(CS_THREADS), l.smem, st, a));
   } else {
     FTN_DYN_SMEM(tc_convs_kernel<1>, l.smem);
     FTN_CUDA(launch_pdl(dependent, tc_convs_kernel<1>, dim3(ctas), dim3(CS_THREADS), l.smem, st, a));

@@ -59,6 +59,8 @@ struct TcGemmKernelArgs {
   int head_n, head_np, head_steps;
   const float* hist; long long hist_stride; const float* late; const float* floor_n; float* disp; int32_t* flags;
   int planes;              // SPLIT: bf16 planes of each operand that are loaded and multiplied (3, or 2 = hi and mid)
+  int fmt;                 // SPLIT: 0 = bf16 planes, 1 = two fp16 planes (planes == 2; the operands hold exactly two)
+  float sc1, sc2;          // fmt 1: power-of-two factors that undo the host-side weight scaling (accumulator 1 / 2)
 };
 
 // F.softplus(beta = 1, threshold = 20) in fp32 device math (timesnet.py:2081-2091)
@@ -100,6 +102,17 @@ __device__ __forceinline__ void store_split16(__nv_bfloat16* dst, int plane_stri
   d0[0] = make_uint4(h[0], h[1], h[2], h[3]); d0[1] = make_uint4(h[4], h[5], h[6], h[7]);
   d1[0] = make_uint4(m[0], m[1], m[2], m[3]); d1[1] = make_uint4(m[4], m[5], m[6], m[7]);
   d2[0] = make_uint4(l[0], l[1], l[2], l[3]); d2[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// two fp16 planes of 16 fp32 values -> 2 x 32 bytes at dst, dst + plane_stride (elements)
+__device__ __forceinline__ void store_split16_h2(__nv_bfloat16* dst, int plane_stride, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_h2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  uint4* d0 = reinterpret_cast<uint4*>(dst);
+  uint4* d1 = reinterpret_cast<uint4*>(dst + plane_stride);
+  d0[0] = make_uint4(h[0], h[1], h[2], h[3]); d0[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  d1[0] = make_uint4(l[0], l[1], l[2], l[3]); d1[1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
 // STAGES: depth of the operand ring.  SPLIT stages are 96 KB; a stage count of 1 (used when the whole K loop is at most
@@ -200,7 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp == 1) {
     {
       // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
-      const uint32_t idesc = make_idesc_bf16(TC_BM, n_tile);
+      const uint32_t idesc = (SPLIT && p.fmt == 1) ? make_idesc_f16(TC_BM, n_tile) : make_idesc_bf16(TC_BM, n_tile);
       for (int kb = 0; kb < nkb1 + nkb2; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&full[s], (kb / STAGES) & 1);
@@ -369,6 +382,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 4; ++i) { const float4 q = src[i]; rs[4 * i] = q.x; rs[4 * i + 1] = q.y; rs[4 * i + 2] = q.z; rs[4 * i + 3] = q.w; }
         }
+      } else if (p.res == TC_RES_POS && p.fmt == 1) {   // two fp16 planes of width res_ld / 2
+        const int pw = p.res_ld / 2;
+#pragma unroll
+        for (int pl = 1; pl >= 0; --pl) {
+          const uint4* src = reinterpret_cast<const uint4*>(resb + pos_row * p.res_ld + pl * pw + n);
+          const uint4 q0 = src[0], q1 = src[1];
+          const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float2 f = h2_to_float2(qw[i]); rs[2 * i] += f.x; rs[2 * i + 1] += f.y; }
+        }
       } else if (p.res == TC_RES_POS) {       // three planes of width res_ld / 3
         const int pw = p.res_ld / 3;
 #pragma unroll
@@ -393,10 +416,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(vr[i]) + s_bias1[c + i];
+        float a = fmaf(__uint_as_float(vr[i]), p.sc1, s_bias1[c + i]);    // sc1 = sc2 = 1 unless the weights were scaled
         if (p.epi != TC_EPI_PLAIN) {
           a = act_split(a, p.act);
-          a += p.res == TC_RES_ACC2 ? __uint_as_float(wr[i]) + s_bias2[c + i] : rs[i];
+          a += p.res == TC_RES_ACC2 ? fmaf(__uint_as_float(wr[i]), p.sc2, s_bias2[c + i]) : rs[i];
           if (p.epi == TC_EPI_BLOCK_A) a = act_split(a, p.act);
           else a -= xs[i];
         }
@@ -409,7 +432,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       } else {
-        store_split16(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.ldo + n, p.ldo / 3, v);
+        if (p.fmt == 1) store_split16_h2(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.ldo + n, p.ldo / 2, v);
+        else store_split16(reinterpret_cast<__nv_bfloat16*>(p.out) + pos_row * p.ldo + n, p.ldo / 3, v);
       }
     }
   } else
@@ -521,6 +545,29 @@ int tc_worst_case_tiles(int B, int L, int max_groups) {
   return max_groups * B * ((2 * L + TC_BM - 1) / TC_BM);
 }
 
+// x fp32 [rows][C] -> xs fp16 [rows][2 C] (hi | lo), 8 values per thread
+__global__ void __launch_bounds__(256) split_h2_kernel(const float* __restrict__ x, long long rows, int C,
+                                                      __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8 = C >> 3;
+  const long long total = rows * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float4* src = reinterpret_cast<const float4*>(x + r * C + c);
+    const float4 q0 = src[0], q1 = src[1];
+    uint32_t h[4], l[4];
+    split_h2(q0.x, q0.y, h[0], l[0]);
+    split_h2(q0.z, q0.w, h[1], l[1]);
+    split_h2(q1.x, q1.y, h[2], l[2]);
+    split_h2(q1.z, q1.w, h[3], l[3]);
+    __nv_bfloat16* dst = out + r * 2 * C + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst + C) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // x fp32 [rows][C] -> xs bf16 [rows][3 C] (hi | mid | lo), 8 values per thread
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, long long rows, int C,
                                                     __nv_bfloat16* __restrict__ out) {
@@ -603,14 +650,15 @@ int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat
   return 0;
 }
 
-int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call) {
+int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call, int fmt) {
   FTN_REQUIRE(C % 8 == 0, "split3: C=%d must be a multiple of 8", C);
   const long long total = rows * (C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  FTN_CUDA(launch_pdl(!first_in_call, split3_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, rows, C, out));
+  if (fmt == 1) FTN_CUDA(launch_pdl(!first_in_call, split_h2_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, rows, C, out));
+  else FTN_CUDA(launch_pdl(!first_in_call, split3_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, rows, C, out));
   FTN_LAUNCH_CHECK("split3_kernel");
   return 0;
 }
@@ -621,7 +669,8 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   FTN_REQUIRE(a.a1_ld % 8 == 0 && (a.K2 == 0 || a.a2_ld % 8 == 0) && a.ldo % 8 == 0,
               "tc_gemm: row pitches must be multiples of 8 elements (16 B)");
   FTN_REQUIRE((a.res == TC_RES_ACC2) == (a.K2 > 0), "tc_gemm: second accumulator and K2 must come together");
-  const int np = a.split ? 3 : 1;                      // planes per operand row
+  FTN_REQUIRE(a.split_fmt == 0 || (a.split && a.epi < TC_EPI_EMBED), "tc_gemm: the fp16 two-plane format is a split-mode chain format");
+  const int np = a.split ? (a.split_fmt == 1 ? 2 : 3) : 1;   // planes per operand row
   CUtensorMap mA1, mW1, mA2, mW2;
   if (a.a1_seq) { if (int rc = make_map_seq(&mA1, a.a1, a.B, a.L, np * a.K1, a.a1_ld)) return rc; }
   else if (int rc = make_map_2d(&mA1, a.a1, a.a1_rows, np * a.K1, a.a1_ld)) return rc;
@@ -642,18 +691,28 @@ int tc_gemm_launch(const TcGemmArgs& a, cudaStream_t st) {
   k.rows_valid = a.rows_valid; k.aux = a.aux; k.aux_rows = a.aux_rows; k.gate = a.gate; k.out_bf16 = a.out_bf16;
   k.head_n = a.head_n; k.head_np = a.head_np; k.head_steps = a.head_steps; k.hist = a.hist; k.hist_stride = a.hist_stride; k.late = a.late;
   k.floor_n = a.floor_n; k.disp = a.disp; k.flags = a.flags;
-  k.planes = a.split_planes == 2 ? 2 : 3;
+  k.planes = (a.split_planes == 2 || a.split_fmt == 1) ? 2 : 3;
+  k.fmt = a.split_fmt;
+  k.sc1 = a.scale1 != 0.f ? a.scale1 : 1.f;
+  k.sc2 = a.scale2 != 0.f ? a.scale2 : 1.f;
   FTN_REQUIRE(a.epi < TC_EPI_EMBED || (a.split && !a.plan && a.K2 == 0), "tc_gemm: the row-GEMM epilogues need split mode and no plan");
   const int tiles = a.plan ? tc_worst_case_tiles(a.B, a.L, a.max_groups) : a.n_tiles;
   dim3 grid(tiles, (a.N + TC_BN - 1) / TC_BN);
   if (a.split) {
-    FTN_REQUIRE(a.ldo % 3 == 0 || a.epi >= TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold three planes", a.ldo);
+    FTN_REQUIRE(a.ldo % np == 0 || a.epi >= TC_EPI_DELTA, "tc_gemm(split): ldo=%d must hold %d planes", a.ldo, np);
     const int nkb = (a.K1 + TC_BK - 1) / TC_BK + (a.K2 + TC_BK - 1) / TC_BK;
     static const bool two_stage = getenv("FLOWTIMES_SPLIT_2STAGE") != nullptr;   // A/B switch for profiling
     (void)nkb;
     // ONE 96 KB stage per CTA and two CTAs per SM: while one CTA's MMAs run the other loads its K block or drains its
     // accumulator (a 2-stage CTA owns the SM alone and its prologue and epilogue leave the tensor pipe idle)
-    if (k.planes == 2) {
+    static const bool h2_ring = getenv("FLOWTIMES_H2_RING") != nullptr;   // A/B switch: 3-deep ring, one CTA per SM
+    if (k.fmt == 1 && !h2_ring) {
+      // fp16 pair: ONE 64 KB stage per CTA, up to three CTAs per SM (one loads while another multiplies and the third
+      // drains; the same reasoning as the single 96 KB stage of the three-plane form below)
+      constexpr int smem1 = 4 * TC_TILE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
+      FTN_DYN_SMEM((tc_gemm_kernel<true, 1, 2>), smem1);
+      tc_gemm_kernel<true, 1, 2><<<grid, 256, smem1, st>>>(mA1, mW1, mA2, mW2, k);
+    } else if (k.planes == 2) {
       // two-plane stages are 64 KB: a 3-deep ring pipelines the K loop (the embedding has six K blocks; with one stage
       // every block paid a full TMA round trip: 36 us for a 12 us kernel)
       constexpr int smem3 = 3 * 4 * TC_TILE_BYTES + 1024 + 256 + 2 * TC_BN * 4;
@@ -707,5 +766,22 @@ extern "C" FTN_API int ftn_debug_tc_linear_split(const float* a, const void* w_s
   g.w1 = (const __nv_bfloat16*)w_s3; g.bias1 = bias; g.K1 = K;
   g.K2 = 0; g.N = N; g.act = 0; g.epi = TC_EPI_PLAIN; g.res = TC_RES_NONE;
   g.out = out_s3; g.ldo = 3 * N;
+  return tc_gemm_launch(g, st);
+}
+
+// Unit-test entry for the two-plane fp16 mode: a[M][K] fp32 is split into a_ws[M][2K], then out_h2[M][2N] (fp16 planes
+// hi | lo of the fp32 result) = (a . w_h2^T) * scale + bias with w_h2[N][2K] the split (power-of-two scaled) weights.
+extern "C" FTN_API int ftn_debug_tc_linear_h2(const float* a, const void* w_h2, float scale, const float* bias, int M, int K,
+                                              int N, void* a_ws, void* out_h2, void* stream) {
+  FTN_REQUIRE(a && w_h2 && bias && a_ws && out_h2, "ftn_debug_tc_linear_h2: null pointer");
+  FTN_REQUIRE(M > 0 && M % 128 == 0, "ftn_debug_tc_linear_h2: M=%d must be a multiple of 128", M);
+  cudaStream_t st = as_stream(stream);
+  if (int rc = split3_launch(a, M, K, (__nv_bfloat16*)a_ws, st, true, 1)) return rc;
+  TcGemmArgs g{};
+  g.plan = nullptr; g.B = 1; g.L = M; g.max_groups = 1; g.n_tiles = M / 128; g.split = 1; g.split_fmt = 1; g.scale1 = scale;
+  g.a1 = (const __nv_bfloat16*)a_ws; g.a1_seq = 0; g.a1_ld = 2 * K; g.a1_rows = M;
+  g.w1 = (const __nv_bfloat16*)w_h2; g.bias1 = bias; g.K1 = K;
+  g.K2 = 0; g.N = N; g.act = 0; g.epi = TC_EPI_PLAIN; g.res = TC_RES_NONE;
+  g.out = out_h2; g.ldo = 2 * N;
   return tc_gemm_launch(g, st);
 }

@@ -45,6 +45,11 @@ struct TcGemmArgs {
   int split;
   int split_planes;                           // 0 / 3: all three planes (6 products, fp32-accurate); 2: hi and mid only (3 products,
                                               // 2^-16 relative) for results that are rounded to bf16 anyway
+  // split_fmt = 1: fp32 activations as TWO fp16 planes (tc_common.cuh: split_h2) -- operands are [rows][2 K] / [rows][2 N],
+  // three products per MAC; the weights were scaled by a power of two on the host, scale1 / scale2 (0 = 1) undo it on
+  // the accumulators before the bias.  split_fmt = 0: the bf16 planes described above.
+  int split_fmt;
+  float scale1, scale2;
   // TC_EPI_EMBED / TC_EPI_NBHEAD (see tc_gemm.cu): rows_valid = rows of the GEMM that exist (the last tile is ragged)
   long long rows_valid;
   const float* aux; int aux_rows;             // EMBED: aux[(aux_rows ? row % aux_rows : row)][N]
@@ -55,8 +60,8 @@ struct TcGemmArgs {
 };
 // fp32 [rows][C] -> three bf16 planes [rows][3 Kp], Kp >= C a multiple of 16 (columns >= C are zero)
 int split3_pad_launch(const float* x, long long rows, int C, int Kp, __nv_bfloat16* out, cudaStream_t st, int planes = 3);
-// fp32 [rows][C] -> three bf16 planes [rows][3 C] (tc_gemm.cu)
-int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call);
+// fp32 [rows][C] -> three bf16 planes [rows][3 C], or (fmt = 1) two fp16 planes [rows][2 C] (tc_gemm.cu)
+int split3_launch(const float* x, long long rows, int C, __nv_bfloat16* out, cudaStream_t st, bool first_in_call, int fmt = 0);
 // tc_dft.cu, MODE 1: hs[B * steps][3 C] = three bf16 planes of (Wt . seq_b + bt), seq bf16 [B][L][C], wt_s3 from ftn_time_proj_pack
 bool tc_time_proj_eligible(int dtype, int B, int L, int C, int steps);
 int tc_time_proj_launch(const void* seq, int B, int L, int C, int steps, const void* wt_s3, const float* bt, void* hs,

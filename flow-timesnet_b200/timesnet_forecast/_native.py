@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 15
+ABI_VERSION = 16
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -59,6 +59,10 @@ class FtnInceptionWeights(C.Structure):
         ("w_kk_phase", C.c_void_p * FTN_MAX_BRANCH),
         ("w_kk_img", C.c_void_p * FTN_MAX_BRANCH), ("w_kk_img3", C.c_void_p * FTN_MAX_BRANCH),
         ("w_in_s3", C.c_void_p), ("w_out_s3", C.c_void_p), ("w_res_s3", C.c_void_p),
+        ("w_in_h2", C.c_void_p), ("w_out_h2", C.c_void_p), ("w_res_h2", C.c_void_p),
+        ("w_kk_img2", C.c_void_p * FTN_MAX_BRANCH),
+        ("sc_in", C.c_float), ("sc_out", C.c_float), ("sc_res", C.c_float),
+        ("sc_kk", C.c_float * FTN_MAX_BRANCH),
     ]
 
 
@@ -89,6 +93,7 @@ SIGNATURES = {
     "ftn_inception_workspace_bytes": (_SZ, [_I, _I, _I, C.POINTER(FtnInceptionWeights), C.POINTER(FtnInceptionWeights)]),
     "ftn_debug_tc_linear": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ftn_debug_tc_linear_split": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ftn_debug_tc_linear_h2": (_I, [_P, _P, _F, _P, _I, _I, _I, _P, _P, _P]),
     "ftn_debug_conv_tiled": (_I, [_P, _P, _I, _P, _I, _I, _I, C.POINTER(FtnInceptionWeights), _I, _P]),
     "ftn_period_conv": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(FtnInceptionWeights),
                              C.POINTER(FtnInceptionWeights), _I, _P, _P, _SZ, _P]),
@@ -494,6 +499,18 @@ def debug_tc_linear_split(a: torch.Tensor, w_s3: torch.Tensor, bias: torch.Tenso
                                             out.data_ptr(), _stream()), "ftn_debug_tc_linear_split")
     o = out.view(M, 3, N).float()
     return o[:, 0] + o[:, 1] + o[:, 2]
+
+
+def debug_tc_linear_h2(a: torch.Tensor, w_h2: torch.Tensor, scale: float, bias: torch.Tensor) -> torch.Tensor:
+    """fp32 a[M, K] x two-plane fp16 weights w_h2[N, 2K] (scaled by 1 / scale) -> fp32 [M, N] from the two output planes."""
+    M, K = a.shape
+    N = w_h2.shape[0]
+    a_ws = torch.empty(M, 2 * K, dtype=torch.float16, device=a.device)
+    out = torch.empty(M, 2 * N, dtype=torch.float16, device=a.device)
+    _check(load().ftn_debug_tc_linear_h2(a.data_ptr(), w_h2.data_ptr(), float(scale), bias.data_ptr(), M, K, N,
+                                         a_ws.data_ptr(), out.data_ptr(), _stream()), "ftn_debug_tc_linear_h2")
+    o = out.view(M, 2, N).float()
+    return o[:, 1] + o[:, 0]
 
 
 def debug_conv_tiled(inp: torch.Tensor, plan_dev: torch.Tensor, B: int, L: int, max_groups: int,

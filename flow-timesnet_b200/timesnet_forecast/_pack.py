@@ -17,6 +17,7 @@ include/flowtimes.h describes.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import List, Tuple
 
 import torch
@@ -75,6 +76,15 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         keep.append(d)
         return d.data_ptr()
 
+    def dev_h2(t: torch.Tensor) -> Tuple[int, float]:
+        """[N][K] weight -> two fp16 planes [N][2 K] of (t * 2^s) on the device, and 2^-s (split_h2 below)"""
+        planes, inv = split_h2(t)
+        if planes is None:
+            return None, 0.0
+        d = torch.cat(planes, dim=1).contiguous().to(device)
+        keep.append(d)
+        return d.data_ptr(), inv
+
     st.cin, st.cout, st.n_branch = int(cin), int(cout), n_branch
     macs = 0
     if bottleneck:
@@ -88,6 +98,7 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         tc_ok = mid % 16 == 0 and cin % 16 == 0 and cout % 16 == 0           # tensor-core tile granularity
         if tc_ok:
             st.w_in_s3 = dev_planes(torch.cat(split3(w_in), dim=1))          # [NB][3 cin]
+            st.w_in_h2, st.sc_in = dev_h2(w_in)                              # [NB][2 cin] fp16
         macs += cin * n_branch * mid
         w_out_rows = []
         b_out = proj_b.clone()
@@ -104,6 +115,10 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
                 img3 = _tap_images(wk)                                       # [tap][mid/8][3][mid][8] bf16
                 st.w_kk_img3[j] = dev_planes(img3)
                 st.w_kk_img[j] = dev_planes(img3[:, :, 0])
+                img2, inv = _tap_images_h2(wk)                               # [tap][mid/8][2][mid][8] fp16
+                if img2 is not None:
+                    st.w_kk_img2[j] = dev_planes(img2)
+                    st.sc_kk[j] = inv
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
@@ -114,6 +129,7 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         st.w_out_bf16 = dev16(w_out_kn.t())                                  # [cout][NB]
         if tc_ok:
             st.w_out_s3 = dev_planes(torch.cat(split3(w_out_kn.t()), dim=1))  # [cout][3 NB]
+            st.w_out_h2, st.sc_out = dev_h2(w_out_kn.t())                     # [cout][2 NB] fp16
         macs += n_branch * mid * cout
     else:
         st.mid = 0
@@ -142,6 +158,7 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
         st.b_res = dev(block.res_proj.bias.detach().to("cpu", f64))
         if bottleneck and tc_ok:
             st.w_res_s3 = dev_planes(torch.cat(split3(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0]), dim=1))
+            st.w_res_h2, st.sc_res = dev_h2(block.res_proj.weight.detach().to("cpu", f64)[:, :, 0, 0])
         macs += cin * cout
     else:
         st.w_res, st.b_res = None, None
@@ -180,6 +197,34 @@ def split3(t: torch.Tensor):
     mid = r1.to(torch.bfloat16)
     lo = (r1 - mid.to(torch.float32)).to(torch.bfloat16)
     return hi, mid, lo
+
+
+def split_h2(t: torch.Tensor):
+    """fp32 value of ``t`` as TWO fp16 planes of ``t * 2^s``: hi = fp16(v), lo = fp16(v - hi), 22 significand bits.
+    ``s`` brings the largest magnitude into [2^13, 2^14) so that the lo plane of typical weights stays out of the fp16
+    subnormals; the kernels multiply their accumulators by the returned ``2^-s`` (exact).  Returns ``(None, 0.0)`` when
+    the tensor has non-finite entries (the three-plane bf16 form then runs, it has fp32's range)."""
+    v = t.to(torch.float32)
+    if not bool(torch.isfinite(v).all()):
+        return None, 0.0
+    amax = float(v.abs().max())
+    s = 0 if amax == 0.0 else int(math.floor(math.log2(16383.0 / amax)))
+    s = max(-100, min(100, s))
+    scaled = v * (2.0 ** s)                                                  # exact: a power of two
+    hi = scaled.to(torch.float16)
+    lo = (scaled - hi.to(torch.float32)).to(torch.float16)
+    return (hi, lo), 2.0 ** (-s)
+
+
+def _tap_images_h2(wk: torch.Tensor):
+    """fp16 two-plane form of ``_tap_images``: [kh*kw][mid/8 chunks][2 planes][mid out][8 in] and the inverse scale."""
+    n_out, n_in, kh, kw = (int(v) for v in wk.shape)
+    planes, inv = split_h2(wk)
+    if planes is None:
+        return None, 0.0
+    st = torch.stack(planes, dim=0)                                          # [2][out][in][kh][kw]
+    img = st.permute(3, 4, 0, 2, 1).reshape(kh * kw, 2, n_in // 8, 8, n_out)  # [tap][plane][chunk][8 in][out]
+    return img.permute(0, 2, 1, 4, 3).contiguous(), inv                       # [tap][chunk][plane][out][8 in]
 
 
 def _tap_images(wk: torch.Tensor) -> torch.Tensor:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 15
+#define FTN_ABI_VERSION 16
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -128,6 +128,17 @@ typedef struct FtnInceptionWeights {
   const void* w_in_s3;     /* [n_branch*mid][3 cin] */
   const void* w_out_s3;    /* [cout][3 n_branch*mid] */
   const void* w_res_s3;    /* [cout][3 cin] or NULL */
+  /* The same chain with every fp32 value as TWO fp16 planes (hi = fp16(v), lo = fp16(v - hi): 22 significand bits), a
+   * product being three fp16 MMAs (hi.hi, hi.lo, lo.hi) -- half the tensor-core work of the three-plane form at the same
+   * 1e-4 bound.  fp16 has a narrow exponent: the packer multiplies each weight tensor by an exact power of two 2^s that
+   * brings its largest magnitude into [2^13, 2^14) and the kernels multiply the accumulator by sc_* = 2^-s.  Layouts as
+   * above with two planes: "[N][2 K]", and w_kk_img2 = [tap][mid / 8][2][mid][8].  NULL = the three-plane form is used. */
+  const void* w_in_h2;     /* [n_branch*mid][2 cin] */
+  const void* w_out_h2;    /* [cout][2 n_branch*mid] */
+  const void* w_res_h2;    /* [cout][2 cin] or NULL */
+  const void* w_kk_img2[FTN_MAX_BRANCH];
+  float sc_in, sc_out, sc_res;
+  float sc_kk[FTN_MAX_BRANCH];
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */
@@ -228,10 +239,14 @@ FTN_API int ftn_debug_tc_linear(const void* a, const void* w, const float* bias,
  * out_s3[M][3N] receives the bf16 planes hi | mid | lo of a . w^T + bias; w_s3[N][3K] = split weights. */
 FTN_API int ftn_debug_tc_linear_split(const float* a, const void* w_s3, const float* bias, int M, int K, int N,
                                       void* a_ws, void* out_s3, void* stream);
+/* The same for the two-plane fp16 mode: a_ws[M][2K] scratch, out_h2[M][2N] = fp16 planes hi | lo of
+ * (a . w^T) * scale + bias; w_h2[N][2K] = fp16 planes of w / scale (scale an exact power of two). */
+FTN_API int ftn_debug_tc_linear_h2(const float* a, const void* w_h2, float scale, const float* bias, int M, int K, int N,
+                                   void* a_ws, void* out_h2, void* stream);
 /* Unit-test hook: only the k x k stage on tile-major bf16 activations [n_tiles*128][ld];
  * use_tc = 4 phases-on-M tcgen05 kernel (+ the image-resident kernel for long periods),
  * 2 image-resident tcgen05 kernel, 5 streaming tcgen05 kernel, 6 streaming kernel on three-plane fp32
- * activations (ld counts all three planes), 0 SIMT kernel. */
+ * activations (ld counts all three planes), 7 streaming kernel on two-plane fp16 activations, 0 SIMT kernel. */
 FTN_API int ftn_debug_conv_tiled(const void* in, void* out, int ld, const FtnPeriodPlan* plan, int B, int L,
                                  int max_groups, const FtnInceptionWeights* w, int use_tc, void* stream);
 FTN_API int ftn_period_conv(const void* x, int dtype, int B, int L, int C, const FtnPeriodPlan* plan,

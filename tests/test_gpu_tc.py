@@ -1,5 +1,7 @@
 """GPU: unit tests of the tcgen05 / TMEM / TMA GEMM kernel in isolation (bf16 in, fp32 accumulate,
 bf16 out) against a plain PyTorch fp32 reference of the same op."""
+import math
+
 import pytest
 import torch
 
@@ -101,6 +103,42 @@ def test_tc_linear_split_keeps_fp32_accuracy(M, K, N):
     assert err < 1e-5, f"rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (256, 48, 64), (128, 256, 48), (384, 128, 256), (128, 16, 16), (256, 1024, 192)])
+@pytest.mark.parametrize("wscale", [1.0, 1e-3, 300.0])
+def test_tc_linear_h2_keeps_fp32_accuracy(M, K, N, wscale):
+    """Two-plane fp16 GEMM (3 MMAs per product, fp32 accumulate, power-of-two weight scaling) against a float64 matmul:
+    fp32-level error whatever the magnitude of the weights."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast._pack import split_h2
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g) * 3.0
+    a[0, 0] = 1e-4                                     # deep in the range where the lo plane is an fp16 subnormal
+    w = torch.randn(N, K, generator=g) / K ** 0.5 * wscale
+    bias = torch.randn(N, generator=g) * wscale
+    planes, inv = split_h2(w)
+    w_h2 = torch.cat(planes, dim=1).contiguous()
+    out = nv.debug_tc_linear_h2(a.cuda(), w_h2.cuda(), inv, bias.cuda())
+    torch.cuda.synchronize()
+    ref = (a.double() @ w.double().t() + bias.double())
+    err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, f"rel err {err:.3e}"
+
+
+def test_split_h2_saturates_and_keeps_nan():
+    """fp16 planes cannot hold |v| > 65504: finite values saturate, NaN propagates (documented limit of the h2 form)."""
+    from timesnet_forecast import _native as nv
+    from timesnet_forecast._pack import split_h2
+    a = torch.zeros(128, 16)
+    a[0, 0] = 1e6
+    a[1, 0] = float("nan")
+    w = torch.eye(16)
+    planes, inv = split_h2(w)
+    out = nv.debug_tc_linear_h2(a.cuda(), torch.cat(planes, dim=1).contiguous().cuda(), inv, torch.zeros(16).cuda()).cpu()
+    assert out[0, 0].item() == 65504.0
+    assert math.isnan(out[1, 0].item())
+    assert torch.equal(out[2:], torch.zeros(126, 16))
+
+
 def _tile_major_images(plan_host, B, L, NB, seed, dtype):
     """Random per-image activations placed in the tile-major layout of the tensor-core chain."""
     G = plan_host.n_groups
@@ -121,12 +159,12 @@ def _tile_major_images(plan_host, B, L, NB, seed, dtype):
 
 @pytest.mark.parametrize("mid,L,periods", [(16, 96, [24, 12, 7, 48, 95]), (32, 336, [24, 168, 335, 5]), (64, 720, [6, 24, 359, 719]),
                                             (64, 96, [1, 2, 48]), (48, 50, [7, 25])])
-@pytest.mark.parametrize("planes", [1, 3])
+@pytest.mark.parametrize("planes", [1, 2, 3])
 def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
     """Streaming k x k kernel (any mid, bf16 or three-plane fp32 activations) against torch conv2d in float64 on the
     folded grids: bf16 activations to one output rounding, the three-plane mode to fp32 accuracy."""
     from timesnet_forecast import _native as nv
-    from timesnet_forecast._pack import split3
+    from timesnet_forecast._pack import split3, split_h2
     from timesnet_forecast.models.timesnet import InceptionBlock
     B, C = 2, mid * 4
     torch.manual_seed(0)
@@ -140,13 +178,19 @@ def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
     buf, imgs = _tile_major_images(plan_host, B, L, NB, 1, dt)
     if planes == 1:
         inp = buf.cuda()
+    elif planes == 2:
+        hi = buf.to(torch.float16)
+        lo = (buf - hi.float()).to(torch.float16)
+        inp = torch.cat([hi, lo], dim=1).contiguous().cuda()           # [rows][2 NB] fp16 (activations are not scaled)
     else:
         inp = torch.cat(split3(buf), dim=1).contiguous().cuda()        # [rows][3 NB]
-    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc=5 if planes == 1 else 6)
+    got = nv.debug_conv_tiled(inp, plan, B, L, len(periods), packed.struct, use_tc={1: 5, 2: 7, 3: 6}[planes])
     torch.cuda.synchronize()
     got = got.float().cpu()
     if planes == 3:
         got = got[:, :NB] + got[:, NB:2 * NB] + got[:, 2 * NB:]
+    elif planes == 2:
+        got = got[:, NB:] + got[:, :NB]
     worst = 0.0
     for gi, row, im in imgs:
         per, cyc = plan_host.grp_period[gi], plan_host.grp_cycles[gi]
