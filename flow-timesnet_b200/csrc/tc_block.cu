@@ -161,7 +161,7 @@ bool tc_kk_uses_conv4(const FtnInceptionWeights* w) {
 
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
-                int period_lo, int period_hi) {
+                int period_lo, int period_hi, int gran) {
   const bool force_v2 = kk_force(0);   // SIMT only
   FTN_REQUIRE(shared_bias_row < 0 || tc_kk_uses_conv4(w), "tc_kk_stage: the shared input layout needs the tc_conv4 route");
   if (tc_kk_uses_conv4(w)) {
@@ -171,10 +171,11 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
     int caps[FTN_MAX_BRANCH];
     tc_conv4_caps(w, caps);
     if (period_lo > 0 && tc_conv4_covers(w, L, period_lo, period_hi))   // nothing can be left for the fallback
-      return tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row);
-    if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row)) return rc;
-    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row);
+      return tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, true, gran);
+    if (int rc = tc_conv4_launch(plan, B, L, max_groups, in, out, ld, w, st, shared_bias_row, true, gran)) return rc;
+    return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row, true, gran);
   }
+  FTN_REQUIRE(gran == 128, "tc_kk_stage: the 32-row granule layout needs the tc_conv4 route");
   static const bool force_stream = getenv("FLOWTIMES_CONV_STREAM") != nullptr;   // A/B: streaming kernel for every mid
   if (!force_v2 && !force_stream && tc_conv2_eligible(w)) return tc_conv2_launch(plan, B, L, max_groups, in, out, ld, w, st);
   if (!force_v2 && tc_convs_eligible(w, 1)) return tc_convs_launch(plan, B, L, max_groups, in, out, ld, w, 1, st);
@@ -320,20 +321,25 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
   long long shared_bias_row = -1;
   if (s1) shared_bias_row = s1->shared_bias_row;
   else if (int rc = launch_block_s1(x, B, L, C, plan, max_groups, a, act, workspace, st, &shared_bias_row)) return rc;
+  static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
+  const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
+  // Row layout of h2 / g1 / q / g2 (tc_gemm.cuh: img_pitch): when every kernel between the once-per-window first stage
+  // and the block output is one of tc_conv4 (+ tc_conv2 for the groups it leaves) / tc_mid / tc_tail, images are packed on
+  // 32-row granules; the plan-decoding GEMMs of the other routes need whole 128-row tiles per image.
+  static const bool no_gran = getenv("FLOWTIMES_TILE_MAJOR") != nullptr;         // A/B switch for profiling
+  const int gran = (!no_gran && tail && fused_mid && shared_bias_row >= 0 && tc_kk_uses_conv4(a) && tc_kk_uses_conv4(b)) ? 32 : 128;
   // S2
   {
     TimedScope t2(FTN_FAM_KK_A, st);
     if (int rc = tc_kk_stage(plan, B, L, max_groups, h1, h2, NBa, a, st, shared_bias_row, s1 ? s1->period_lo : 0,
-                             s1 ? s1->period_hi : 0))
+                             s1 ? s1->period_hi : 0, gran))
       return rc;
   }
-  static const bool no_fused_mid = getenv("FLOWTIMES_NO_FUSED_MID") != nullptr;   // A/B switch for profiling
-  const bool fused_mid = !no_fused_mid && tc_mid_eligible(a, b);
   __nv_bfloat16* q = a2;   // the fused middle never materialises a2: its slot holds q = a2 . V_res + b (C columns)
   if (fused_mid) {
     // S3 + S4 + block B's res_proj in one persistent kernel (tc_mid.cu)
     TimedScope t3(FTN_FAM_MID, st);
-    if (int rc = tc_mid_launch(plan, B, L, max_groups, h2, rows, xb, a, b, act, g1, q, st)) return rc;
+    if (int rc = tc_mid_launch(plan, B, L, max_groups, h2, rows, xb, a, b, act, g1, q, st, gran)) return rc;
   } else {
     // S3
     s = base;
@@ -355,14 +361,14 @@ static int period_conv_tc_impl(const void* x, int B, int L, int C, const FtnPeri
   // S5
   {
     TimedScope t4(FTN_FAM_KK_B, st);
-    if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st, -1, s1 ? s1->period_lo : 0, s1 ? s1->period_hi : 0))
+    if (int rc = tc_kk_stage(plan, B, L, max_groups, g1, g2, NBb, b, st, -1, s1 ? s1->period_lo : 0, s1 ? s1->period_hi : 0, gran))
       return rc;
   }
   if (tail) {
     // S6 + aggregation + residual + LayerNorm in one kernel: the deltas never reach HBM
     TimedScope t5(FTN_FAM_S6, st);
     return tc_tail_launch(plan, B, L, max_groups, g2, rows, NBb, (const __nv_bfloat16*)b->w_out_bf16, b->b_out, q, C, xb,
-                          tail->weights, tail->ln_w, tail->ln_b, tail->eps, act, (__nv_bfloat16*)tail->out, st);
+                          tail->weights, tail->ln_w, tail->ln_b, tail->eps, act, (__nv_bfloat16*)tail->out, st, gran);
   }
   // S6
   s = base;

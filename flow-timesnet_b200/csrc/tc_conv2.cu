@@ -41,6 +41,7 @@ struct TcConv2Args {
   __nv_bfloat16* out;
   int ld;        // row pitch of in / out (elements)
   long long shared_bias_row;   // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L (tc_gemm.cuh)
+  int gran;      // row granule of the image layout (tc_gemm.cuh: img_pitch)
   int mid;       // channels per branch (K and N of the MMAs): 16 or 32
   int n_branch;
   int cap_rows;  // rows one image buffer can hold
@@ -63,10 +64,10 @@ struct C2Unit {
 
 // unit index (within one branch's enumeration) -> image, band and buffer geometry
 __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L, int kh, int hw, int cap, int v3cap,
-                                          int unit, C2Unit& u) {
+                                          int gran, int unit, C2Unit& u) {
   const int G = pl->n_groups;
   const int hh = kh / 2;
-  int row_tiles_before = 0;
+  size_t rows_before = 0;
   for (int g = 0; g < G; ++g) {
     const int per = pl->grp_period[g], cyc = pl->grp_cycles[g];
     const int Lp = L + pl->grp_pad[g];
@@ -91,13 +92,13 @@ __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L,
     }
     const bool taken = v3cap < 0 && c4_group_fits(per, cyc, kh, 2 * hw + 1, -v3cap);
     const int n = taken ? 0 : bands * B;   // tc_conv4 owns this group
-    const int rt = (Lp + 127) / 128;
+    const int pitch = img_pitch(Lp, gran);
     if (unit < n) {
       u.g = g;
       u.b = unit / bands;
       const int band = unit - u.b * bands;
       u.per = per; u.cyc = cyc; u.PW = PW; u.QT = QT;
-      u.img_row0 = (size_t)(row_tiles_before + u.b * rt) * 128;
+      u.img_row0 = rows_before + (size_t)u.b * pitch;
       u.q0 = band * T * C2_BM;
       u.tiles = min(T, tiles_img - band * T);
       u.mode_b = mode_b;
@@ -106,7 +107,7 @@ __device__ __forceinline__ bool c2_decode(const FtnPeriodPlan* pl, int B, int L,
       return true;
     }
     unit -= n;
-    row_tiles_before += rt * B;
+    rows_before += (size_t)pitch * B;
   }
   return false;
 }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
   {
     // nothing to do for this CTA (e.g. tc_conv4 owns every group): leave before touching TMEM / weights
     C2Unit probe;
-    if (!c2_decode(p.plan, p.B, p.L, kh, hw, cap, p.v3_cap[j], cta_in_branch, probe)) return;
+    if (!c2_decode(p.plan, p.B, p.L, kh, hw, cap, p.v3_cap[j], p.gran, cta_in_branch, probe)) return;
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
       const uint32_t wbase = smem_u32(s_w);
       C2Unit u;
       int i = 0;
-      for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
+      for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], p.gran, unit, u); unit += ctas_of_branch, ++i) {
         const int buf = i & 1;
         const uint32_t par = (uint32_t)(i >> 1) & 1u;
         mbar_wait(&bars[C2_ACC_EMPTY + buf], par ^ 1u);   // epilogue drained the unit that used these columns
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
     const int r_step = C2_LOADERS / nchunk;
     C2Unit u;
     int i = 0;
-    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], p.gran, unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       const uint32_t par = (uint32_t)(i >> 1) & 1u;
       mbar_wait_relaxed(&bars[C2_IMG_EMPTY + buf], par ^ 1u);
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) tc_conv2_kernel(const TcConv2Ar
     uint32_t phase_bits = 0;                 // one parity bit per (buffer, tile) barrier
     C2Unit u;
     int i = 0;
-    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c2_decode(pl, p.B, p.L, kh, hw, cap, p.v3_cap[j], p.gran, unit, u); unit += ctas_of_branch, ++i) {
       const int buf = i & 1;
       const float inv = 1.0f / (float)u.PW;
       for (int m = 0; m < u.tiles; ++m) {
@@ -355,13 +356,15 @@ int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
 
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                              __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
-                             long long shared_bias_row, bool dependent) {
+                             long long shared_bias_row, bool dependent, int gran) {
   FTN_REQUIRE(tc_conv2_eligible(w), "tc_conv2: unsupported branch shape (mid=%d)", w->mid);
+  FTN_REQUIRE(gran == 32 || gran == 128, "tc_conv2: row granule %d", gran);
   (void)max_groups;
   TcConv2Args a{};
   for (int j = 0; j < w->n_branch; ++j) a.v3_cap[j] = v3_caps ? v3_caps[j] : 0;
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.mid = w->mid; a.n_branch = w->n_branch;
   a.shared_bias_row = shared_bias_row;
+  a.gran = gran;
   a.cap_rows = conv2_cap_rows(w);
   int cost_total = 0;
   for (int j = 0; j < w->n_branch; ++j) {

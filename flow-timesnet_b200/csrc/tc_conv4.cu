@@ -57,6 +57,7 @@ struct TcConv4Args {
   __nv_bfloat16* out;
   int ld;
   long long shared_bias_row;      // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L
+  int gran;                       // row granule of the image layout (tc_gemm.cuh: img_pitch)
   int n_branch;
   int cap_rows[FTN_MAX_BRANCH];   // rows one phase plane of an image buffer can hold
   int cap_rows1[FTN_MAX_BRANCH];  // the same for the single-buffer CTAs (second half of the grid)
@@ -84,7 +85,7 @@ struct C4Unit {
 
 // per-group geometry, computed once per CTA: the device plan lives in global memory and a decode that re-reads
 // it per image costs ~700 cycles per group visited (L2 latency) in every role of the pipeline
-struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, tile0, rt, hh_eff; };
+struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, pitch, hh_eff; long long row0; };
 
 __host__ __device__ inline int c4_stage_bytes(int kw) { return 2048 * (kw + 3) + 1536; }
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int unit, C
     const C4Group q = grp[g];
     if (unit < q.n_units) {
       u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
-      u.img_row0 = (size_t)(q.tile0 + unit * q.rt) * 128;
+      u.img_row0 = (size_t)q.row0 + (size_t)unit * q.pitch;
       u.b = unit;
       u.hh_eff = q.hh_eff;
       return true;
@@ -181,10 +182,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     const C4Geom gm = c4_geometry(q.per, q.cyc, kh, kw);
     q.PW = gm.PW; q.NB = gm.NB; q.blocks = gm.blocks; q.O4 = gm.O4; q.rows = gm.rows; q.hh_eff = gm.hh_eff;
     q.n_units = (gm.rows <= cap && gm.rows > cap_min) ? p.B : 0;     // the rest is another pass's or tc_conv2's
-    q.rt = (p.L + pl->grp_pad[g] + 127) / 128;
-    int tiles = 0;
-    for (int h = 0; h < g; ++h) tiles += (p.L + pl->grp_pad[h] + 127) / 128;
-    q.tile0 = tiles * p.B;
+    q.pitch = img_pitch(p.L + pl->grp_pad[g], p.gran);
+    long long before = 0;
+    for (int h = 0; h < g; ++h) before += img_pitch(p.L + pl->grp_pad[h], p.gran);
+    q.row0 = before * p.B;
     s_grp[g] = q;
   }
   tc_fence_before();
@@ -466,9 +467,11 @@ void tc_conv4_caps(const FtnInceptionWeights* w, int* caps) {
 
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row,
-                    bool dependent) {
+                    bool dependent, int gran) {
   FTN_REQUIRE(tc_conv4_eligible(w), "tc_conv4: unsupported branch shape (mid=%d)", w->mid);
+  FTN_REQUIRE(gran == 32 || gran == 128, "tc_conv4: row granule %d", gran);
   TcConv4Args a{};
+  a.gran = gran;
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.n_branch = w->n_branch;
   a.shared_bias_row = shared_bias_row;
   // cycles per image: MMAs at ~94 cycles (N ~ 170 columns, barrier hops included) plus the fixed cost of the unit

@@ -74,6 +74,15 @@ int tc_gemm2_launch(const TcGemmArgs& a, cudaStream_t st);
 int tc_stage_launch(const TcGemmArgs& a, cudaStream_t st);
 int tc_worst_case_tiles(int B, int L, int max_groups);
 
+// Row layout of the inter-stage activations of the bf16 chain: image (group g, window b) starts at row
+//   sum_{h < g} pitch_h * B + b * pitch_g,      pitch_g = ceil((L + pad_g) / gran) * gran.
+// gran = 128 is the "tile-major" layout (an image owns whole 128-row tiles: a tile id is a row-block index AND names one
+// window, which the plan-decoding GEMMs rely on).  The fully fused route (tc_gemm2 S1 once per window -> tc_conv4 ->
+// tc_mid -> tc_conv4 -> tc_tail) packs images on 32-row granules instead: its 1x1 kernels work on any 128 consecutive
+// rows (a TMEM lane quadrant = one granule = one image), so 3 tiles = 384 rows per elec image become 11 granules = 352
+// and the 28-row images of the 30 000-series configuration fill 7/8 of a tile instead of 7/32.
+__host__ __device__ inline int img_pitch(int Lp, int gran) { return (Lp + gran - 1) / gran * gran; }
+
 // k x k stage on tile-major bf16 activations (SIMT for now; see conv_gemm.cu)
 int simt_conv_tiled_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                            __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
@@ -84,7 +93,7 @@ int tc_conv2_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st);
 int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                              __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, const int* v3_caps, cudaStream_t st,
-                             long long shared_bias_row = -1, bool dependent = true);
+                             long long shared_bias_row = -1, bool dependent = true, int gran = 128);
 // "output phases on M" variant (tc_conv4.cu): 4 phases x 32 channels on M, no cross-quadrant reduction in the
 // drain; whole images only, groups whose padded image does not fit go to tc_conv2
 struct C4Geom { int PW, QT, blocks, NB, O4, rows, hh_eff; };
@@ -111,7 +120,8 @@ bool tc_conv4_eligible(const FtnInceptionWeights* w);
 void tc_conv4_caps(const FtnInceptionWeights* w, int* caps);   // negated capacities for tc_conv2_launch_filtered
 int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                     __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1,
-                    bool dependent = true);   // dependent: the previous kernel in the stream is one of this library's
+                    bool dependent = true,    // dependent: the previous kernel in the stream is one of this library's
+                    int gran = 128);          // row granule of the image layout of in (tile-major form) and out
 
 // picks tc_conv4 (+ tc_conv2 for the groups it leaves) / tc_conv2 / SIMT for one k x k stage
 // shared_bias_row >= 0: `in` is NOT tile-major but one copy per window, row b * L + t for t < L, and row
@@ -121,7 +131,7 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
 // tc_conv4 takes every one of them the tc_conv2 fallback is not launched at all
 int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in,
                 __nv_bfloat16* out, int ld, const FtnInceptionWeights* w, cudaStream_t st, long long shared_bias_row = -1,
-                int period_lo = 0, int period_hi = 0);
+                int period_lo = 0, int period_hi = 0, int gran = 128);
 bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int period_lo, int period_hi);
 bool tc_kk_uses_conv4(const FtnInceptionWeights* w);
 
@@ -136,12 +146,12 @@ bool tc_tail_eligible(int K, int C);
 int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* g2, long long rows, int K,
                    const __nv_bfloat16* w_out, const float* bias, const __nv_bfloat16* q, int C, const __nv_bfloat16* x,
                    const float* weights, const float* ln_w, const float* ln_b, float eps, int act, __nv_bfloat16* out,
-                   cudaStream_t st);
+                   cudaStream_t st, int gran = 128);
 
 // fused middle of the chain (tc_mid.cu): h2, x -> g1 (block B k x k input) and q (block B residual)
 bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b);
 int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,
                   const __nv_bfloat16* x, const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
-                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st);
+                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st, int gran = 128);
 
 }  // namespace ftn

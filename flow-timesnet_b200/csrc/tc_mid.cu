@@ -58,6 +58,7 @@ struct TcMidKernelArgs {
   const float* b_res2;  // [N4]
   __nv_bfloat16* g1; int ld_g1;
   __nv_bfloat16* q;  int ld_q;
+  int gran;             // row granule of the image layout of h2 / g1 / q (tc_gemm.cuh: img_pitch)
   long long* trace;     // debug (FLOWTIMES_MID_TRACE): CTA 0 records clock64() per (event, chunk)
 };
 
@@ -73,20 +74,24 @@ enum {
     if (p.trace && blockIdx.x == 0 && (n) < 256) p.trace[(ev) * 256 + (n)] = clock64();       \
   } while (0)
 
-__device__ __forceinline__ bool mid_decode_tile(const FtnPeriodPlan* pl, int B, int L, int tile, int& b, int& t0) {
-  const int G = pl->n_groups;
-  for (int g = 0; g < G; ++g) {
-    const int Lp = L + pl->grp_pad[g];
-    const int tiles_g = (Lp + MD_BM - 1) / MD_BM;
-    const int n = tiles_g * B;
-    if (tile < n) {
-      b = tile / tiles_g;
-      t0 = (tile - b * tiles_g) * MD_BM;
-      return true;
-    }
-    tile -= n;
-  }
-  return false;
+// Row layout of h2 / g1 / q (tc_gemm.cuh: img_pitch): group g starts at row goff[g], its images are pitch[g] rows apart.
+// A 128-row tile is four 32-row sub-blocks; with both granules (32, 128) a sub-block lies inside ONE image.
+struct MidLayout {
+  long long goff[FTN_MAX_K + 1];
+  int pitch[FTN_MAX_K];
+  int G, n_tiles;
+};
+
+// sub-block starting at row r0 -> (window b, first time step t0); rows past the last image map to window B (the TMA
+// box is then out of bounds and arrives as zeros)
+__device__ __forceinline__ void mid_decode_rows(const MidLayout& lay, int B, long long r0, int& b, int& t0) {
+  b = B; t0 = 0;
+  if (r0 >= lay.goff[lay.G]) return;
+  int g = 0;
+  while (g + 1 < lay.G && r0 >= lay.goff[g + 1]) ++g;
+  const long long rel = r0 - lay.goff[g];
+  b = (int)(rel / lay.pitch[g]);
+  t0 = (int)(rel - (long long)b * lay.pitch[g]);
 }
 
 __host__ __device__ inline uint32_t md_align1024(uint32_t v) { return (v + 1023u) & ~1023u; }
@@ -117,6 +122,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   float* sb_res2 = sb_in2 + p.N3;
   uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(sb_res2 + p.N4), 16));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + MB_COUNT);
+  MidLayout* lay_s = reinterpret_cast<MidLayout*>(tmem_slot + 4);   // 8-byte aligned like the barriers
 
   for (int i = threadIdx.x; i < p.F; i += MD_THREADS) { sb_out[i] = p.b_out[i]; sb_res[i] = p.b_res[i]; }
   for (int i = threadIdx.x; i < p.N3; i += MD_THREADS) sb_in2[i] = p.b_in2[i];
@@ -136,31 +142,51 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // the plan, h2 and x are predecessors' outputs
-  const FtnPeriodPlan* pl = p.plan;
-
+  if (threadIdx.x == 0) {
+    const FtnPeriodPlan* pl = p.plan;
+    MidLayout l;
+    l.G = pl->n_groups < FTN_MAX_K ? pl->n_groups : FTN_MAX_K;
+    long long off = 0;
+    for (int g = 0; g < l.G; ++g) {
+      l.goff[g] = off;
+      l.pitch[g] = img_pitch(p.L + pl->grp_pad[g], p.gran);
+      off += (long long)l.pitch[g] * p.B;
+    }
+    for (int g = l.G; g <= FTN_MAX_K; ++g) l.goff[g] = off;
+    for (int g = l.G; g < FTN_MAX_K; ++g) l.pitch[g] = 1;
+    l.n_tiles = (int)((off + MD_BM - 1) / MD_BM);
+    *lay_s = l;
+  }
+  __syncthreads();
+  const MidLayout& lay = *lay_s;
+  const int n_tiles = lay.n_tiles;
   // tiles this CTA owns (static round-robin); the chunk stream n = tile_iteration * nch + c runs
   // across tile boundaries
-  int my_tiles = 0;
-  {
-    int b_, t_;
-    for (int tile = blockIdx.x; mid_decode_tile(pl, p.B, p.L, tile, b_, t_); tile += gridDim.x) ++my_tiles;
-  }
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t n_total = (uint32_t)my_tiles * (uint32_t)nch;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer 1: activation tiles + stage-1 weights =====================
-      uint32_t n = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; it < my_tiles; tile += gridDim.x, ++it) {
-        int b, t0;
-        mid_decode_tile(pl, p.B, p.L, tile, b, t0);
+    // ===================== TMA producer 1: activation tiles + stage-1 weights =====================
+    // lane 0 runs the protocol (waits, expect_tx, the h2 tile, the weight stages); lanes 1-4 each issue the x boxes of one
+    // 32-row sub-block of the tile (a TMA issue costs ~400 cycles of the issuing thread: in parallel, not in a row)
+    uint32_t n = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; it < my_tiles; tile += gridDim.x, ++it) {
+      if (lane == 0) {
         mbar_wait(&bars[MB_A_EMPTY], (it & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[MB_A_FULL], (uint32_t)(kb1 + kb2) * MD_A_KB_BYTES);
         for (int kb = 0; kb < kb1; ++kb)
           tma_load_2d(sH2 + kb * MD_A_KB_BYTES, &tmH2, &bars[MB_A_FULL], kb * MD_BK, tile * MD_BM);
+      }
+      __syncwarp();
+      if (lane >= 1 && lane <= 4) {
+        const int sb = lane - 1;
+        int b, t0;
+        mid_decode_rows(lay, p.B, (long long)tile * MD_BM + sb * 32, b, t0);
         for (int kb = 0; kb < kb2; ++kb)
-          tma_load_3d(sX + kb * MD_A_KB_BYTES, &tmX, &bars[MB_A_FULL], kb * MD_BK, t0, b);
+          tma_load_3d(sX + kb * MD_A_KB_BYTES + sb * (32 * 128), &tmX, &bars[MB_A_FULL], kb * MD_BK, t0, b);
+      }
+      if (lane == 0) {
         for (int c = 0; c < nch; ++c, ++n) {
           // the stage image of chunk c is (kb1+kb2) x 128 rows of 128 B, streamed as 256-row boxes.  Its U and R
           // halves have their own barriers: the buffer is single (64 KB do not fit twice), so each half is refilled
@@ -178,8 +204,8 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
             tma_load_2d(sR1 + kb * MD_W_KB_BYTES, &tmW1, &bars[MB_R1B_FULL], 0, (c * (kb1 + kb2) + kb) * MD_NC);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 3) {
     if (lane == 0) {
       // ===================== TMA producer 2: stage-2 weights =====================
@@ -383,9 +409,7 @@ tc_mid_kernel(const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ 
     // the last stage-2 MMAs of a tile (and their barrier hops) hide under useful epilogue work instead of idling 16 warps.
     uint32_t n = 0;
     int it = 0, prev_tile = -1;
-    for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
-      int b, t0;
-      if (!mid_decode_tile(pl, p.B, p.L, tile, b, t0)) break;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       for (int c = 0; c < nch; ++c, ++n) {
         do_chunk(n, c);
         if (c == 0 && prev_tile >= 0) do_drain(prev_tile, it - 1);
@@ -439,7 +463,7 @@ static int md_map_seq(CUtensorMap* m, const void* base, int B, int L, int C) {
   FTN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)MD_BK, (cuuint32_t)MD_BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)MD_BK, 32u, 1};   // one 32-row sub-block of a tile (a sub-block is inside ONE window)
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -452,7 +476,7 @@ static size_t mid_smem_bytes(int K1, int K2, int F, int N3, int N4) {
   const int kb1 = (K1 + MD_BK - 1) / MD_BK, kb2 = (K2 + MD_BK - 1) / MD_BK;
   size_t s = (size_t)(kb1 + kb2) * MD_A_KB_BYTES + (size_t)(kb1 + kb2) * MD_W_KB_BYTES +
              2 * (size_t)md_align1024((N3 + N4) * 128) + MD_A2_BYTES;
-  s += (size_t)(2 * F + N3 + N4) * 4 + 16 + MB_COUNT * 8 + 16;
+  s += (size_t)(2 * F + N3 + N4) * 4 + 16 + MB_COUNT * 8 + 16 + sizeof(MidLayout) + 16;
   return s + 1024;  // alignment slack
 }
 
@@ -469,8 +493,9 @@ bool tc_mid_eligible(const FtnInceptionWeights* a, const FtnInceptionWeights* b)
 
 int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* h2, long long rows,
                   const __nv_bfloat16* x, const FtnInceptionWeights* a, const FtnInceptionWeights* b, int act,
-                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st) {
+                  __nv_bfloat16* g1, __nv_bfloat16* q, cudaStream_t st, int gran) {
   FTN_REQUIRE(tc_mid_eligible(a, b), "tc_mid: unsupported channel configuration");
+  FTN_REQUIRE(gran == 32 || gran == 128, "tc_mid: row granule %d", gran);
   const int K1 = a->n_branch * a->mid, K2 = a->cin, F = a->cout, N3 = b->n_branch * b->mid, N4 = b->cout;
   CUtensorMap mH2, mX, mW1, mW2;
   const int kbs = (K1 + 63) / 64 + (K2 + 63) / 64;
@@ -482,7 +507,7 @@ int tc_mid_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const
   TcMidKernelArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K1 = K1; k.K2 = K2; k.F = F; k.N3 = N3; k.N4 = N4;
   k.b_out = a->b_out; k.b_res = a->b_res; k.b_in2 = b->b_in; k.b_res2 = b->b_res;
-  k.g1 = g1; k.ld_g1 = N3; k.q = q; k.ld_q = N4;
+  k.g1 = g1; k.ld_g1 = N3; k.q = q; k.ld_q = N4; k.gran = gran;
   static const char* trace_path = getenv("FLOWTIMES_MID_TRACE");
   static long long* trace_dev = nullptr;
   if (trace_path && !trace_dev) cudaMalloc(&trace_dev, (64 * 256) * sizeof(long long));

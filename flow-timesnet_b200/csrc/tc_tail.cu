@@ -34,6 +34,7 @@ constexpr int TL_STAGES = 2;
 struct TcTailArgs {
   const FtnPeriodPlan* plan;
   int B, L, K, C, act;
+  int gran;                       // row granule of the g2 / q image layout
   const float* bias;              // [C]
   const __nv_bfloat16* q; int ld_q;     // tile-major residual of block B
   const __nv_bfloat16* x;         // [B][L][C]
@@ -47,11 +48,12 @@ struct TcTailArgs {
 enum { TL_W_FULL = 0, TL_A_FULL = 1, TL_A_EMPTY = 3, TL_ACC_FULL = 5, TL_ACC_EMPTY = 7, TL_Q_FULL = 9, TL_Q_EMPTY = 11,
        TL_X_FULL = 13, TL_X_EMPTY = 14, TL_BARS = 15 };
 
-// tile-major index of (group g, window b, time tile tt): tiles are enumerated group-major, then window, then tile
-__device__ __forceinline__ int tl_tile_index(const FtnPeriodPlan* pl, int B, int L, int g, int b, int tt) {
-  int base = 0;
-  for (int h = 0; h < g; ++h) base += ((L + pl->grp_pad[h] + TL_BM - 1) / TL_BM) * B;
-  return base + b * ((L + pl->grp_pad[g] + TL_BM - 1) / TL_BM) + tt;
+// first row of time tile tt of image (group g, window b) in the g2 / q layout (tc_gemm.cuh: img_pitch).  With 32-row
+// granules the 128-row box of an image's last tile may run into the next image: those rows are steps t >= L, never live.
+__device__ __forceinline__ int tl_tile_row(const FtnPeriodPlan* pl, int B, int L, int gran, int g, int b, int tt) {
+  long long base = 0;
+  for (int h = 0; h < g; ++h) base += (long long)img_pitch(L + pl->grp_pad[h], gran) * B;
+  return (int)(base + (long long)b * img_pitch(L + pl->grp_pad[g], gran) + tt * TL_BM);
 }
 
 // Round a PAIR to bf16 and widen it again.  A scalar __float2bfloat16_rn is F2F.BF16.F32 on the XU pipe (8 cycles per
@@ -133,15 +135,15 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nq; ++kb) tma_load_3d(sX + kb * TL_A_KB, &tmX, &bars[TL_X_FULL], kb * TL_BK, tt * TL_BM, b);
         for (int g = 0; g < G; ++g, ++n) {
           const uint32_t s = n & 1, ph = (n >> 1) & 1;
-          const int tile = tl_tile_index(pl, p.B, p.L, g, b, tt);
+          const int row0 = tl_tile_row(pl, p.B, p.L, p.gran, g, b, tt);
           mbar_wait(&bars[TL_A_EMPTY + s], ph ^ 1);
           mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
           for (int kb = 0; kb < nkb; ++kb)
-            tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, tile * TL_BM);
+            tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, row0);
           mbar_wait(&bars[TL_Q_EMPTY + s], ph ^ 1);
           mbar_arrive_expect_tx(&bars[TL_Q_FULL + s], (uint32_t)nq * TL_A_KB);
           for (int kb = 0; kb < nq; ++kb)
-            tma_load_2d(sQ + (s * nq + kb) * TL_A_KB, &tmQ, &bars[TL_Q_FULL + s], kb * TL_BK, tile * TL_BM);
+            tma_load_2d(sQ + (s * nq + kb) * TL_A_KB, &tmQ, &bars[TL_Q_FULL + s], kb * TL_BK, row0);
         }
       }
     }
@@ -340,8 +342,10 @@ bool tc_tail_eligible(int K, int C) { return K % 16 == 0 && K <= 128 && C % 64 =
 int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* g2, long long rows, int K,
                    const __nv_bfloat16* w_out, const float* bias, const __nv_bfloat16* q, int C, const __nv_bfloat16* x,
                    const float* weights, const float* ln_w, const float* ln_b, float eps, int act, __nv_bfloat16* out,
-                   cudaStream_t st) {
+                   cudaStream_t st, int gran) {
   FTN_REQUIRE(tc_tail_eligible(K, C), "tc_tail: unsupported K=%d C=%d", K, C);
+  FTN_REQUIRE(gran == 32 || gran == 128, "tc_tail: row granule %d", gran);
+  FTN_REQUIRE(rows < (1ll << 31), "tc_tail: %lld rows exceed a 32-bit TMA coordinate", rows);
   (void)max_groups;
   CUtensorMap mA, mW;
   if (int rc = tl_map_2d(&mA, g2, rows, K, K, TL_BM)) return rc;
@@ -361,7 +365,7 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   }
   TcTailArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K = K; k.C = C; k.act = act; k.bias = bias; k.q = q; k.ld_q = C; k.x = x;
-  k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out;
+  k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out; k.gran = gran;
   const int nkb = (K + TL_BK - 1) / TL_BK;
   const int nq = (C + TL_BK - 1) / TL_BK;
   const size_t smem = 1024 + (size_t)nkb * ((C * 128 + 1023) & ~1023) + (size_t)TL_STAGES * nkb * TL_A_KB +
