@@ -58,6 +58,7 @@ struct TcConv4Args {
   int ld;
   long long shared_bias_row;      // >= 0: `in` holds one copy per window (row b * L + t) + this row for t >= L
   int gran;                       // row granule of the image layout (tc_gemm.cuh: img_pitch)
+  int no_stack;                   // A/B switch (FLOWTIMES_CONV_NO_STACK): one image per unit whatever its size
   int n_branch;
   int cap_rows[FTN_MAX_BRANCH];   // rows one phase plane of an image buffer can hold
   int cap_rows1[FTN_MAX_BRANCH];  // the same for the single-buffer CTAs (second half of the grid)
@@ -81,27 +82,52 @@ struct TcConv4Args {
 struct C4Unit {
   int per, cyc, PW, NB, blocks, O4, rows, b, hh_eff;
   size_t img_row0;
+  // stacked unit (tc_gemm.cuh: c4_stack): nimg images of windows b .. b + nimg - 1, cs = cyc + hh_eff grid rows apart,
+  // cyc_v rows in all; image i lives `pitch` rows after image i - 1 in the tile-major tensors
+  int nimg, cs, cyc_v, pitch;
+  float inv_cs;
 };
 
 // per-group geometry, computed once per CTA: the device plan lives in global memory and a decode that re-reads
 // it per image costs ~700 cycles per group visited (L2 latency) in every role of the pipeline
-struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, pitch, hh_eff; long long row0; };
+struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, pitch, hh_eff, nstack, cs, cyc_v; float inv_cs; long long row0; };
 
 __host__ __device__ inline int c4_stage_bytes(int kw) { return 2048 * (kw + 3) + 1536; }
 
-__device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int unit, C4Unit& u) {
+__device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int B, int kw, int unit, C4Unit& u) {
   for (int g = 0; g < G; ++g) {
     const C4Group q = grp[g];
     if (unit < q.n_units) {
       u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
-      u.img_row0 = (size_t)q.row0 + (size_t)unit * q.pitch;
-      u.b = unit;
+      u.b = unit * q.nstack;
+      u.img_row0 = (size_t)q.row0 + (size_t)u.b * q.pitch;
       u.hh_eff = q.hh_eff;
+      u.pitch = q.pitch;
+      u.nimg = q.nstack;
+      u.cs = q.cs;
+      u.inv_cs = q.inv_cs;
+      u.cyc_v = q.cyc_v;
+      if (q.nstack > 1 && u.b + q.nstack > B) {   // the ragged last unit of a group: a shorter stack
+        u.nimg = B - u.b;
+        u.cyc_v = c4_stack_rows(q.cyc, u.nimg, q.hh_eff);
+        const C4Geom gm = c4_geometry_v(q.per, u.cyc_v, q.hh_eff, kw);
+        u.NB = gm.NB; u.blocks = gm.blocks; u.O4 = gm.O4; u.rows = gm.rows;
+      }
       return true;
     }
     unit -= q.n_units;
   }
   return false;
+}
+// grid row rr of a (stacked) unit -> image i and its row r; false: a separator row or outside the grid
+__device__ __forceinline__ bool c4_row(const C4Unit& u, int rr, int& i, int& r) {
+  i = 0; r = rr;
+  if (rr < 0 || rr >= u.cyc_v) return false;
+  if (u.nimg > 1) {
+    i = __float2int_rd((__int2float_rn(rr) + 0.5f) * u.inv_cs);   // rr < 2^12: exact
+    r = rr - i * u.cs;
+  }
+  return r < u.cyc;
 }
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -179,9 +205,15 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     const int g = tid - 32;
     C4Group q;
     q.per = pl->grp_period[g]; q.cyc = pl->grp_cycles[g];
-    const C4Geom gm = c4_geometry(q.per, q.cyc, kh, kw);
+    C4Geom gm = c4_geometry(q.per, q.cyc, kh, kw);
+    const bool mine = gm.rows <= cap && gm.rows > cap_min;            // the rest is another pass's or tc_conv2's
+    q.nstack = (mine && !pass && !p.no_stack) ? c4_stack(q.per, q.cyc, kh, kw, cap, p.B) : 1;
+    if (q.nstack > 1) gm = c4_geometry_v(q.per, c4_stack_rows(q.cyc, q.nstack, gm.hh_eff), gm.hh_eff, kw);
     q.PW = gm.PW; q.NB = gm.NB; q.blocks = gm.blocks; q.O4 = gm.O4; q.rows = gm.rows; q.hh_eff = gm.hh_eff;
-    q.n_units = (gm.rows <= cap && gm.rows > cap_min) ? p.B : 0;     // the rest is another pass's or tc_conv2's
+    q.n_units = mine ? (p.B + q.nstack - 1) / q.nstack : 0;
+    q.cs = q.cyc + q.hh_eff;
+    q.inv_cs = 1.0f / (float)q.cs;
+    q.cyc_v = c4_stack_rows(q.cyc, q.nstack, q.hh_eff);
     q.pitch = img_pitch(p.L + pl->grp_pad[g], p.gran);
     long long before = 0;
     for (int h = 0; h < g; ++h) before += img_pitch(p.L + pl->grp_pad[h], p.gran);
@@ -210,7 +242,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     C4Unit u;
     int i = 0;
     uint32_t blk_count = 0, wc = 0;
-    for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c4_decode(s_grp, G, p.B, kw, unit, u); unit += ctas_of_branch, ++i) {
       if (two_issuers ? (i & 1) != mw : mw != 0) {   // the other issuer's image
         blk_count += (uint32_t)u.blocks;
         continue;
@@ -276,8 +308,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
         C4Unit ua, ub;
         uint32_t wl[2] = {0, 0};
         const bool two_issuers = NBUF > 1;       // one image buffer: one issuer, every image on ring 0
-        for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, ua); unit += (two_issuers ? 2 : 1) * ctas_of_branch) {
-          const bool vb = two_issuers && c4_decode(s_grp, G, unit + ctas_of_branch, ub);
+        for (int unit = cta_in_branch; c4_decode(s_grp, G, p.B, kw, unit, ua); unit += (two_issuers ? 2 : 1) * ctas_of_branch) {
+          const bool vb = two_issuers && c4_decode(s_grp, G, p.B, kw, unit + ctas_of_branch, ub);
           const int na = ua.blocks * kh, nb = vb ? ub.blocks * kh : 0;
           for (int k = 0; k < (na > nb ? na : nb); ++k) {
 #pragma unroll
@@ -306,7 +338,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     uint4 padv = make_uint4(0, 0, 0, 0);     // this thread's 16 bytes of the row that stands for every padded step
     if (p.shared_bias_row >= 0)
       padv = *reinterpret_cast<const uint4*>(p.in + (size_t)p.shared_bias_row * p.ld + j * C4_MID + c * 8);
-    for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c4_decode(s_grp, G, p.B, kw, unit, u); unit += ctas_of_branch, ++i) {
       const uint32_t buf = (uint32_t)i % NBUF;
       mbar_wait_relaxed(&bars[C4_IMG_EMPTY + buf], (((uint32_t)i / NBUF) & 1u) ^ 1u);
       if (lt == 0) C4_TRACE(5, i);
@@ -323,21 +355,41 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
       const int n_beta = 4 * u.rows;
       // (an LDG-to-registers + STS variant with 12 loads in flight per thread was slower: the loop is bound by the
       // LSU walking ~12 partially used lines per warp instruction -- 64 B of every 192 B row -- not by latency)
-      for (int beta = r_first; beta < n_beta; beta += C4_LSTEP) {
-        const bool ok = rr >= 0 && rr < u.cyc && wq >= hw && wq < hw + u.per;
-        const int tt = rr * u.per + wq - hw;
-        if (ok && tt >= t_lim) {
-          // padded step of the once-per-window input: every such position holds the same row.  Reading it from
-          // global memory makes all SMs hammer one L2 line (a p = L - 1 group is half padding: 86 us instead of 26)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(padv.x), "r"(padv.y), "r"(padv.z), "r"(padv.w)
-                       : "memory");
-        } else {
-          cp_async16(dst, ok ? img + (size_t)tt * p.ld : img, ok ? 16u : 0u);
+      if (u.nimg == 1) {
+        for (int beta = r_first; beta < n_beta; beta += C4_LSTEP) {
+          const bool ok = rr >= 0 && rr < u.cyc && wq >= hw && wq < hw + u.per;
+          const int tt = rr * u.per + wq - hw;
+          if (ok && tt >= t_lim) {
+            // padded step of the once-per-window input: every such position holds the same row.  Reading it from
+            // global memory makes all SMs hammer one L2 line (a p = L - 1 group is half padding: 86 us instead of 26)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(padv.x), "r"(padv.y), "r"(padv.z), "r"(padv.w)
+                         : "memory");
+          } else {
+            cp_async16(dst, ok ? img + (size_t)tt * p.ld : img, ok ? 16u : 0u);
+          }
+          dst += C4_LSTEP * 4;
+          rr += step_r;
+          wq += step_w;
+          if (wq >= u.PW) { wq -= u.PW; ++rr; }
         }
-        dst += C4_LSTEP * 4;
-        rr += step_r;
-        wq += step_w;
-        if (wq >= u.PW) { wq -= u.PW; ++rr; }
+      } else {
+        // stacked unit: grid row -> (image, row of that image); separator rows are zero like the halo
+        const size_t img_step = (size_t)(shared ? p.L : u.pitch) * p.ld;
+        for (int beta = r_first; beta < n_beta; beta += C4_LSTEP) {
+          int si, sr;
+          const bool ok = c4_row(u, rr, si, sr) && wq >= hw && wq < hw + u.per;
+          const int tt = sr * u.per + wq - hw;
+          if (ok && tt >= t_lim) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(padv.x), "r"(padv.y), "r"(padv.z), "r"(padv.w)
+                         : "memory");
+          } else {
+            cp_async16(dst, ok ? img + (size_t)si * img_step + (size_t)tt * p.ld : img, ok ? 16u : 0u);
+          }
+          dst += C4_LSTEP * 4;
+          rr += step_r;
+          wq += step_w;
+          if (wq >= u.PW) { wq -= u.PW; ++rr; }
+        }
       }
       if (lt == 0) C4_TRACE(10, i);
       cp_async_wait_all();
@@ -359,7 +411,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
     C4Unit u;
     int i = 0;
     uint32_t blk_count = 0, step_count = 0;
-    for (int unit = cta_in_branch; c4_decode(s_grp, G, unit, u); unit += ctas_of_branch, ++i) {
+    for (int unit = cta_in_branch; c4_decode(s_grp, G, p.B, kw, unit, u); unit += ctas_of_branch, ++i) {
       const float inv = 1.0f / (float)u.PW;
       __nv_bfloat16* out_img = p.out + u.img_row0 * p.ld + j * C4_MID;
       for (int t = 0; t < u.blocks; ++t, ++blk_count) {
@@ -390,9 +442,16 @@ __global__ void __launch_bounds__(C4_THREADS, 1) tc_conv4_kernel(const TcConv4Ar
             if (rr * u.PW > P) --rr;
             if ((rr + 1) * u.PW <= P) ++rr;
             const int wq = P - rr * u.PW;
-            if (rr < u.cyc && wq >= hw && wq < hw + u.per)
-              *reinterpret_cast<uint4*>(out_img + (size_t)(rr * u.per + wq - hw) * p.ld + (item & 3) * 8) =
-                  *reinterpret_cast<const uint4*>(stage + item * 16);
+            if (u.nimg == 1) {
+              if (rr < u.cyc && wq >= hw && wq < hw + u.per)
+                *reinterpret_cast<uint4*>(out_img + (size_t)(rr * u.per + wq - hw) * p.ld + (item & 3) * 8) =
+                    *reinterpret_cast<const uint4*>(stage + item * 16);
+            } else {
+              int si, sr;
+              if (c4_row(u, rr, si, sr) && wq >= hw && wq < hw + u.per)
+                *reinterpret_cast<uint4*>(out_img + ((size_t)si * u.pitch + (size_t)(sr * u.per + wq - hw)) * p.ld + (item & 3) * 8) =
+                    *reinterpret_cast<const uint4*>(stage + item * 16);
+            }
           }
         }
         tc_fence_before();
@@ -472,6 +531,8 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   FTN_REQUIRE(gran == 32 || gran == 128, "tc_conv4: row granule %d", gran);
   TcConv4Args a{};
   a.gran = gran;
+  static const bool no_stack = getenv("FLOWTIMES_CONV_NO_STACK") != nullptr;   // A/B switch for profiling
+  a.no_stack = no_stack ? 1 : 0;
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.n_branch = w->n_branch;
   a.shared_bias_row = shared_bias_row;
   // cycles per image: MMAs at ~94 cycles (N ~ 170 columns, barrier hops included) plus the fixed cost of the unit

@@ -97,21 +97,47 @@ int tc_conv2_launch_filtered(const FtnPeriodPlan* plan, int B, int L, int max_gr
 // "output phases on M" variant (tc_conv4.cu): 4 phases x 32 channels on M, no cross-quadrant reduction in the
 // drain; whole images only, groups whose padded image does not fit go to tc_conv2
 struct C4Geom { int PW, QT, blocks, NB, O4, rows, hh_eff; };
-__host__ __device__ inline C4Geom c4_geometry(int per, int cyc, int kh, int kw) {
+// tap rows further than cycles - 1 from the centre only ever see zero padding: they are skipped, and the halo
+// the image buffer has to hold shrinks with them (long periods have few cycles: p = 168 at L = 336 has 2)
+__host__ __device__ inline int c4_hh_eff(int cyc, int kh) {
+  const int hh = kh / 2;
+  return hh < cyc - 1 ? hh : (cyc > 1 ? cyc - 1 : 0);
+}
+// geometry of a grid of `cyc` rows whose taps reach hh_eff rows up and down
+__host__ __device__ inline C4Geom c4_geometry_v(int per, int cyc, int hh_eff, int kw) {
   C4Geom g;
-  const int hw = kw / 2, hh = kh / 2;
+  const int hw = kw / 2;
   g.PW = per + 2 * hw;
   g.QT = cyc * g.PW;
   const int nc = (g.QT + 3) / 4;                       // accumulator columns: 4 positions each
   g.blocks = (nc + 255) / 256;
   g.NB = (((nc + g.blocks - 1) / g.blocks) + 15) & ~15;
-  // tap rows further than cycles - 1 from the centre only ever see zero padding: they are skipped, and the halo
-  // the image buffer has to hold shrinks with them (long periods have few cycles: p = 168 at L = 336 has 2)
-  g.hh_eff = hh < cyc - 1 ? hh : (cyc > 1 ? cyc - 1 : 0);
+  g.hh_eff = hh_eff;
   g.O4 = (g.hh_eff * g.PW + hw + 3) / 4;               // plane rows in front of the image origin
   const int max_beta = 4 * (g.blocks * g.NB - 1) + (kw + 2) + g.hh_eff * g.PW - hw + 4 * g.O4;
   g.rows = (max_beta >> 2) + 1;                        // rows per phase plane the MMAs may touch
   return g;
+}
+__host__ __device__ inline C4Geom c4_geometry(int per, int cyc, int kh, int kw) {
+  return c4_geometry_v(per, cyc, c4_hh_eff(cyc, kh), kw);
+}
+// Small images are STACKED: n images of the same group on top of each other with hh_eff zero rows between them are one
+// taller grid to the convolution (the zero rows are the "same" padding of both neighbours), so one unit of the kernel
+// -- one image load, one MMA block, one drain -- serves n windows.  Only grids of at most 256 padded positions (64
+// accumulator columns) are stacked: the 28-step windows of the 30 000-series configuration, whose single images filled
+// 16 of an MMA's 256 columns and paid the per-unit hand-over ~5 k cycles each.  Returns the images per unit.
+__host__ __device__ inline int c4_stack_rows(int cyc, int n, int hh_eff) { return n * cyc + (n - 1) * hh_eff; }
+__host__ __device__ inline int c4_stack(int per, int cyc, int kh, int kw, int cap, int B) {
+  const int PW = per + 2 * (kw / 2);
+  if (cyc * PW > 256) return 1;
+  const int he = c4_hh_eff(cyc, kh);
+  int n = 1;
+  for (int m = 2; m <= 64 && m <= B; ++m) {
+    const C4Geom g = c4_geometry_v(per, c4_stack_rows(cyc, m, he), he, kw);
+    if (g.blocks > 1 || g.rows > cap) break;
+    n = m;
+  }
+  return n;
 }
 __host__ __device__ inline bool c4_group_fits(int per, int cyc, int kh, int kw, int cap) {
   return c4_geometry(per, cyc, kh, kw).rows <= cap;
