@@ -11,13 +11,17 @@
 // those of the unfused kernels (delta, the weighted product, the sums and the residual are rounded to
 // the activation dtype exactly where aggregate.cu rounds them), so both routes give the same bits.
 //
-// Persistent, one CTA per SM; work item = (window, time tile), inner loop over the G groups:
+// Persistent, one CTA per SM; work item = (window, 128-step time tile) -- or, for windows of at most 96 steps, (four
+// windows, 32-step granule): a TMEM lane quadrant then is one window, so the 28-step windows of the 30 000-series
+// configuration fill 7/8 of an item's rows instead of 7/32 -- inner loop over the G groups:
 //   warp 0 lane 0 : TMA producer   -- g2 and q tiles of (group, window, tile) into 2-deep rings, the item's x tile,
 //                   weights once: the epilogue never issues a global load
 //   warp 1        : MMA issuer     -- 6 MMAs per sub-tile, accumulators double-buffered in TMEM
 //   warp 2        : TMEM allocator
 //   warps 4..19   : epilogue       -- four warps per lane quadrant (32 columns each); the four quarters of a
 //                   row meet through shared memory for the LayerNorm statistics
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -35,6 +39,8 @@ struct TcTailArgs {
   const FtnPeriodPlan* plan;
   int B, L, K, C, act;
   int gran;                       // row granule of the g2 / q image layout
+  int wq;                         // windows per item: 1 = (window, 128-step tile); 4 = (four windows, 32-step granule), the
+                                  // form for short windows (L <= 96), with 32-row TMA boxes
   const float* bias;              // [C]
   const __nv_bfloat16* q; int ld_q;     // tile-major residual of block B
   const __nv_bfloat16* x;         // [B][L][C]
@@ -48,14 +54,8 @@ struct TcTailArgs {
 enum { TL_W_FULL = 0, TL_A_FULL = 1, TL_A_EMPTY = 3, TL_ACC_FULL = 5, TL_ACC_EMPTY = 7, TL_Q_FULL = 9, TL_Q_EMPTY = 11,
        TL_X_FULL = 13, TL_X_EMPTY = 14, TL_BARS = 15 };
 
-// first row of time tile tt of image (group g, window b) in the g2 / q layout (tc_gemm.cuh: img_pitch).  With 32-row
-// granules the 128-row box of an image's last tile may run into the next image: those rows are steps t >= L, never live.
-__device__ __forceinline__ int tl_tile_row(const FtnPeriodPlan* pl, int B, int L, int gran, int g, int b, int tt) {
-  long long base = 0;
-  for (int h = 0; h < g; ++h) base += (long long)img_pitch(L + pl->grp_pad[h], gran) * B;
-  return (int)(base + (long long)b * img_pitch(L + pl->grp_pad[g], gran) + tt * TL_BM);
-}
-
+// g2 / q are stored image by image (tc_gemm.cuh: img_pitch); with 32-row granules the 128-row box of an image's last
+// tile may run into the next image: those rows are steps t >= L, never live.
 // Round a PAIR to bf16 and widen it again.  A scalar __float2bfloat16_rn is F2F.BF16.F32 on the XU pipe (8 cycles per
 // warp instruction, like MUFU): with two roundings per value and group this kernel was XU-bound (ncu: 54 % XU).
 // The packed F2FP.BF16.F32.PACK_AB runs on the ALU side at ~2 cycles for two values; the results are identical.
@@ -65,7 +65,7 @@ __device__ __forceinline__ void bf16_round2(float a, float b, float& ra, float& 
   rb = __uint_as_float(pk & 0xffff0000u);
 }
 
-template <int ACT>
+template <int ACT, bool QUAD>
 __global__ void __launch_bounds__(TL_THREADS, 1)
 tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const TcTailArgs p) {
@@ -86,6 +86,8 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_red = s_lnb + 128;                         // [4 quarters][128 rows][2] LayerNorm partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(align_smem(reinterpret_cast<uint8_t*>(s_red + 1024), 16));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TL_BARS);
+  int* s_goff = reinterpret_cast<int*>(tmem_slot + 2);    // [FTN_MAX_K] first row of group g in g2 / q (tc_gemm.cuh: img_pitch)
+  int* s_pitch = s_goff + FTN_MAX_K;                      // [FTN_MAX_K] rows between its images
 
   if ((int)threadIdx.x < p.C) {
     s_bias[threadIdx.x] = p.bias[threadIdx.x];
@@ -118,36 +120,98 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();   // the plan, g2, q, x and the group weights are predecessors' outputs
   const FtnPeriodPlan* pl = p.plan;
   const int G = pl->n_groups;
-  const int tiles_x = (p.L + TL_BM - 1) / TL_BM;
-  const int n_items = p.B * tiles_x;
+  constexpr bool quad_items = QUAD;     // a template parameter: the one-window form must not pay registers for the other
+  // items: (window, 128-step tile) or (window quad, 32-step granule); `tiles_x` = time pieces per window (quad)
+  const int tiles_x = quad_items ? (p.L + 31) / 32 : (p.L + TL_BM - 1) / TL_BM;
+  const int n_items = (quad_items ? (p.B + 3) / 4 : p.B) * tiles_x;
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
+    // lane 0 runs the protocol (waits, expect_tx); the boxes of a stage are issued by as many lanes as there are boxes (a
+    // TMA issue costs ~400 cycles of the issuing thread).  Item of four windows: one 32-row box per window and K block,
+    // placed at row 32 q of the 128-row operand tile.
     if (lane == 0) {
-      // ===================== TMA producer =====================
       mbar_arrive_expect_tx(&bars[TL_W_FULL], (uint32_t)nkb * (uint32_t)p.C * 128u);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sW + kb * w_kb, &tmW, &bars[TL_W_FULL], kb * TL_BK, 0);
-      uint32_t n = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int b = item / tiles_x, tt = item - b * tiles_x;
+    }
+    {
+      // image layout of g2 / q, private to this warp: lane g reads group g's pad (ONE L2 round trip for all groups, under
+      // the weight load), an exclusive scan over the lanes gives the first row of every group
+      const int pitch = lane < G ? img_pitch(p.L + pl->grp_pad[lane], p.gran) : 0;
+      int incl = pitch * p.B;
+#pragma unroll
+      for (int d = 1; d < FTN_MAX_K; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane < G && lane < FTN_MAX_K) { s_goff[lane] = incl - pitch * p.B; s_pitch[lane] = pitch; }
+      __syncwarp();
+    }
+    if (!quad_items) {
+      // one window per item: few boxes per stage, all from lane 0 (spreading them over lanes and the __syncwarp that
+      // needs was 2 us slower at the elec shape)
+      if (lane == 0) {
+        uint32_t n = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+          const int b = item / tiles_x, tt = item - b * tiles_x;
+          mbar_wait(&bars[TL_X_EMPTY], (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[TL_X_FULL], (uint32_t)nq * TL_A_KB);
+          for (int kb = 0; kb < nq; ++kb) tma_load_3d(sX + kb * TL_A_KB, &tmX, &bars[TL_X_FULL], kb * TL_BK, tt * TL_BM, b);
+          for (int g = 0; g < G; ++g, ++n) {
+            const uint32_t s = n & 1, ph = (n >> 1) & 1;
+            const int row0 = s_goff[g] + b * s_pitch[g] + tt * TL_BM;
+            mbar_wait(&bars[TL_A_EMPTY + s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
+            for (int kb = 0; kb < nkb; ++kb)
+              tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, row0);
+            mbar_wait(&bars[TL_Q_EMPTY + s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars[TL_Q_FULL + s], (uint32_t)nq * TL_A_KB);
+            for (int kb = 0; kb < nq; ++kb)
+              tma_load_2d(sQ + (s * nq + kb) * TL_A_KB, &tmQ, &bars[TL_Q_FULL + s], kb * TL_BK, row0);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+    const int nwin = 4;
+    const int sub = lane & 3;                                // window of the quad this lane loads
+    const int boxl = lane >> 2;                              // which box of the stage: A blocks first, then Q blocks
+    uint32_t n = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int bq = item / tiles_x, tt = item - bq * tiles_x;
+      const int b = 4 * bq + sub;                            // windows past the batch: boxes out of bounds = zeros
+      const int t0 = 32 * tt;
+      if (lane == 0) {
         mbar_wait(&bars[TL_X_EMPTY], (it & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[TL_X_FULL], (uint32_t)nq * TL_A_KB);
-        for (int kb = 0; kb < nq; ++kb) tma_load_3d(sX + kb * TL_A_KB, &tmX, &bars[TL_X_FULL], kb * TL_BK, tt * TL_BM, b);
-        for (int g = 0; g < G; ++g, ++n) {
-          const uint32_t s = n & 1, ph = (n >> 1) & 1;
-          const int row0 = tl_tile_row(pl, p.B, p.L, p.gran, g, b, tt);
+      }
+      __syncwarp();
+      if (boxl < nq && lane < nwin * nq)
+        tma_load_3d(sX + boxl * TL_A_KB + sub * (32 * 128), &tmX, &bars[TL_X_FULL], boxl * TL_BK, t0, b);
+      for (int g = 0; g < G; ++g, ++n) {
+        const uint32_t s = n & 1, ph = (n >> 1) & 1;
+        // rows past the last image (a window beyond the batch) are out of bounds of the tensor map: zero fill
+        const int row0 = b < p.B ? s_goff[g] + b * s_pitch[g] + t0 : 0x7fffff00;
+        if (lane == 0) {
           mbar_wait(&bars[TL_A_EMPTY + s], ph ^ 1);
           mbar_arrive_expect_tx(&bars[TL_A_FULL + s], (uint32_t)nkb * TL_A_KB);
-          for (int kb = 0; kb < nkb; ++kb)
-            tma_load_2d(sA + (s * nkb + kb) * TL_A_KB, &tmA, &bars[TL_A_FULL + s], kb * TL_BK, row0);
           mbar_wait(&bars[TL_Q_EMPTY + s], ph ^ 1);
           mbar_arrive_expect_tx(&bars[TL_Q_FULL + s], (uint32_t)nq * TL_A_KB);
-          for (int kb = 0; kb < nq; ++kb)
-            tma_load_2d(sQ + (s * nq + kb) * TL_A_KB, &tmQ, &bars[TL_Q_FULL + s], kb * TL_BK, row0);
+        }
+        __syncwarp();
+        if (lane < nwin * (nkb + nq)) {
+          if (boxl < nkb)
+            tma_load_2d(sA + (s * nkb + boxl) * TL_A_KB + sub * (32 * 128), &tmA, &bars[TL_A_FULL + s], boxl * TL_BK, row0);
+          else
+            tma_load_2d(sQ + (s * nq + (boxl - nkb)) * TL_A_KB + sub * (32 * 128), &tmQ, &bars[TL_Q_FULL + s],
+                        (boxl - nkb) * TL_BK, row0);
         }
       }
     }
     __syncwarp();
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_bf16(TL_BM, p.C);
@@ -192,16 +256,17 @@ tc_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       return reinterpret_cast<const uint4*>(base + kb * TL_A_KB + r * 128 + ((ch ^ (r & 7)) << 4));
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int b = item / tiles_x, tt = item - b * tiles_x;
-      const int t = tt * TL_BM + r;
-      const bool live = t < p.L;
+      const int bq = item / tiles_x, tt = item - bq * tiles_x;
+      const int b = quad_items ? 4 * bq + quad : bq;         // quad items: this warp's lane quadrant is one window
+      const int t = quad_items ? 32 * tt + lane : tt * TL_BM + r;
+      const bool live = t < p.L && b < p.B;
       float comb[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) comb[i] = 0.f;
       mbar_wait_relaxed(&bars[TL_X_FULL], it & 1);
       for (int g = 0; g < G; ++g, ++n) {
         const uint32_t s = n & 1;
-        const float wg = p.weights[(size_t)b * FTN_MAX_K + g];
+        const float wg = b < p.B ? p.weights[(size_t)b * FTN_MAX_K + g] : 0.f;
         mbar_wait_relaxed(&bars[TL_ACC_FULL + s], (n >> 1) & 1);
         mbar_wait_relaxed(&bars[TL_Q_FULL + s], (n >> 1) & 1);
         tc_fence_after();
@@ -347,16 +412,19 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   FTN_REQUIRE(gran == 32 || gran == 128, "tc_tail: row granule %d", gran);
   FTN_REQUIRE(rows < (1ll << 31), "tc_tail: %lld rows exceed a 32-bit TMA coordinate", rows);
   (void)max_groups;
+  static const bool force_tall = getenv("FLOWTIMES_TAIL_TALL") != nullptr;   // A/B switch for profiling
+  const int wq = (!force_tall && L <= 96) ? 4 : 1;
+  const int box_rows = wq == 4 ? 32 : TL_BM;
   CUtensorMap mA, mW;
-  if (int rc = tl_map_2d(&mA, g2, rows, K, K, TL_BM)) return rc;
+  if (int rc = tl_map_2d(&mA, g2, rows, K, K, box_rows)) return rc;
   if (int rc = tl_map_2d(&mW, w_out, C, K, K, C)) return rc;
   CUtensorMap mQ, mX;
-  if (int rc = tl_map_2d(&mQ, q, rows, C, C, TL_BM)) return rc;
+  if (int rc = tl_map_2d(&mQ, q, rows, C, C, box_rows)) return rc;
   {
     EncodeTiledFn fn = tl_encode_fn();
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
-    cuuint32_t box[3] = {TL_BK, TL_BM, 1};
+    cuuint32_t box[3] = {TL_BK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = fn(&mX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -365,18 +433,23 @@ int tc_tail_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, cons
   }
   TcTailArgs k{};
   k.plan = plan; k.B = B; k.L = L; k.K = K; k.C = C; k.act = act; k.bias = bias; k.q = q; k.ld_q = C; k.x = x;
-  k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out; k.gran = gran;
+  k.weights = weights; k.ln_w = ln_w; k.ln_b = ln_b; k.eps = eps; k.out = out; k.gran = gran; k.wq = wq;
   const int nkb = (K + TL_BK - 1) / TL_BK;
   const int nq = (C + TL_BK - 1) / TL_BK;
   const size_t smem = 1024 + (size_t)nkb * ((C * 128 + 1023) & ~1023) + (size_t)TL_STAGES * nkb * TL_A_KB +
-                      (size_t)(TL_STAGES + 1) * nq * TL_A_KB + (3 * 128 + 1024) * 4 + 16 + TL_BARS * 8 + 16;
+                      (size_t)(TL_STAGES + 1) * nq * TL_A_KB + (3 * 128 + 1024) * 4 + 16 + TL_BARS * 8 + 16 +
+                      2 * FTN_MAX_K * sizeof(int);
   const int ai = act == FTN_ACT_RELU ? 1 : 0;
-  if (ai) FTN_DYN_SMEM(tc_tail_kernel<1>, smem);
-  else FTN_DYN_SMEM(tc_tail_kernel<0>, smem);
-  const int items = B * ((L + TL_BM - 1) / TL_BM);
+  const int items = wq == 4 ? ((B + 3) / 4) * ((L + 31) / 32) : B * ((L + TL_BM - 1) / TL_BM);
   const int grid = items < sm_count() ? items : sm_count();
-  if (ai) FTN_CUDA(launch_pdl(true, tc_tail_kernel<1>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
-  else FTN_CUDA(launch_pdl(true, tc_tail_kernel<0>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));
+#define TL_LAUNCH(A, Q)                                                                                              \
+  do {                                                                                                              \
+    FTN_DYN_SMEM((tc_tail_kernel<A, Q>), smem);                                                                     \
+    FTN_CUDA(launch_pdl(true, tc_tail_kernel<A, Q>, dim3(grid), dim3(TL_THREADS), smem, st, mA, mW, mQ, mX, k));    \
+  } while (0)
+  if (wq == 4) { if (ai) TL_LAUNCH(1, true); else TL_LAUNCH(0, true); }
+  else { if (ai) TL_LAUNCH(1, false); else TL_LAUNCH(0, false); }
+#undef TL_LAUNCH
   FTN_LAUNCH_CHECK("tc_tail_kernel");
   return 0;
 }
