@@ -95,29 +95,37 @@ struct C4Group { int per, cyc, PW, NB, blocks, O4, rows, n_units, pitch, hh_eff,
 __host__ __device__ inline int c4_stage_bytes(int kw) { return 2048 * (kw + 3) + 1536; }
 
 __device__ __forceinline__ bool c4_decode(const C4Group* grp, int G, int B, int kw, int unit, C4Unit& u) {
-  for (int g = 0; g < G; ++g) {
-    const C4Group q = grp[g];
-    if (unit < q.n_units) {
-      u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
-      u.b = unit * q.nstack;
-      u.img_row0 = (size_t)q.row0 + (size_t)u.b * q.pitch;
-      u.hh_eff = q.hh_eff;
-      u.pitch = q.pitch;
-      u.nimg = q.nstack;
-      u.cs = q.cs;
-      u.inv_cs = q.inv_cs;
-      u.cyc_v = q.cyc_v;
-      if (q.nstack > 1 && u.b + q.nstack > B) {   // the ragged last unit of a group: a shorter stack
-        u.nimg = B - u.b;
-        u.cyc_v = c4_stack_rows(q.cyc, u.nimg, q.hh_eff);
-        const C4Geom gm = c4_geometry_v(q.per, u.cyc_v, q.hh_eff, kw);
-        u.NB = gm.NB; u.blocks = gm.blocks; u.O4 = gm.O4; u.rows = gm.rows;
-      }
-      return true;
-    }
-    unit -= q.n_units;
+  // find the group first (one word per group visited), then read that group's geometry: this runs in every role for
+  // every unit, and in the MMA issuers it sits in the hand-over between two images
+  int g = 0;
+  for (; g < G; ++g) {
+    const int n = grp[g].n_units;
+    if (unit < n) break;
+    unit -= n;
   }
-  return false;
+  if (g >= G) return false;
+  const C4Group& q = grp[g];
+  u.per = q.per; u.cyc = q.cyc; u.PW = q.PW; u.NB = q.NB; u.blocks = q.blocks; u.O4 = q.O4; u.rows = q.rows;
+  u.hh_eff = q.hh_eff;
+  u.nimg = q.nstack;
+  if (q.nstack == 1) {
+    u.b = unit;
+    u.img_row0 = (size_t)q.row0 + (size_t)unit * q.pitch;
+    return true;
+  }
+  u.b = unit * q.nstack;
+  u.img_row0 = (size_t)q.row0 + (size_t)u.b * q.pitch;
+  u.pitch = q.pitch;
+  u.cs = q.cs;
+  u.inv_cs = q.inv_cs;
+  u.cyc_v = q.cyc_v;
+  if (u.b + q.nstack > B) {   // the ragged last unit of a group: a shorter stack
+    u.nimg = B - u.b;
+    u.cyc_v = c4_stack_rows(q.cyc, u.nimg, q.hh_eff);
+    const C4Geom gm = c4_geometry_v(q.per, u.cyc_v, q.hh_eff, kw);
+    u.NB = gm.NB; u.blocks = gm.blocks; u.O4 = gm.O4; u.rows = gm.rows;
+  }
+  return true;
 }
 // grid row rr of a (stacked) unit -> image i and its row r; false: a separator row or outside the grid
 __device__ __forceinline__ bool c4_row(const C4Unit& u, int rr, int& i, int& r) {
