@@ -176,6 +176,7 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
     return tc_conv2_launch_filtered(plan, B, L, max_groups, in, out, ld, w, caps, st, shared_bias_row, true, gran);
   }
   FTN_REQUIRE(gran == 128, "tc_kk_stage: the 32-row granule layout needs the tc_conv4 route");
+  if (!force_v2 && tc_convs_row_preferred(w)) return tc_convs_launch(plan, B, L, max_groups, in, out, ld, w, 1, st);
   static const bool force_stream = getenv("FLOWTIMES_CONV_STREAM") != nullptr;   // A/B: streaming kernel for every mid
   if (!force_v2 && !force_stream && tc_conv2_eligible(w)) return tc_conv2_launch(plan, B, L, max_groups, in, out, ld, w, st);
   if (!force_v2 && tc_convs_eligible(w, 1)) return tc_convs_launch(plan, B, L, max_groups, in, out, ld, w, 1, st);

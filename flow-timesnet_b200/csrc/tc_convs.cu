@@ -12,6 +12,13 @@
 //           per tap and K16 step, a_hi . [w_hi | w_lo] (N = 2 mid) and a_lo . w_hi (N = mid); the weights were scaled by
 //           a power of two on the host, `scale` undoes it on the accumulator.
 //
+//   ROW MODE (narrow branches: kw * planes * mid <= 256, i.e. mid = 16 -- the etth1 class): an M128 x N16 MMA costs what
+//           an N = 128 one does, so a tap-by-tap stream runs at 1/8 of the tensor rate.  Here the kw taps of a tap ROW sit
+//           side by side on N (one weight image per tap row, N = planes * kw * mid): kh MMAs per unit instead of kh * kw,
+//               D[m][(dw, n)] = sum_{dr, c} in[q0 - hw + m + (dr - hh) PW][c] * W[dr][dw][n][c]
+//           and the epilogue adds the kw shifted partial sums, out[q0 + j][n] = sum_dw D[j + dw][(dw, n)], through a
+//           shared-memory stage (rows j + dw live in other lanes / warps).  A unit then yields 128 - 2 hw outputs.
+//
 //   out[pos][n] = bias[n] + sum_{dr,dw} sum_c in[pos shifted by (dr,dw)][c] * W[dr][dw][n][c]
 // on the folded [cycles, period] grid with zero "same" padding (timesnet.py:588, :1044-1057).
 //
@@ -30,6 +37,8 @@
 // With N = mid <= 64 an MMA costs what an N = 128 one does (the 4 KB A fetch bounds it), so the kernel is bound by its
 // MMA issue rate; at mid = 64 that is half of the tensor peak, which tc_conv4's phases-on-M trick would double for
 // mid = 32 only.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -57,6 +66,11 @@ struct TcConvsArgs {
   const uint8_t* w[FTN_MAX_BRANCH];    // [tap][chunk][plane][n][8] bf16
   const float* bias[FTN_MAX_BRANCH];
   float scale[FTN_MAX_BRANCH];         // NS = 2: power of two that undoes the host-side weight scaling (1 otherwise)
+  int row_mode;    // taps of a tap row side by side on N (see the header); w[] then holds one image per tap ROW,
+                   // [kh][chunk][plane][dw][n][8], and a weight slot is a whole row (ut = kw)
+  int acc_cols;    // accumulator columns per TMEM buffer
+  int stage_off;   // row mode: byte offset of the fp32 partial-sum stage [128][stage_pitch] in shared memory
+  int stage_pitch; // floats per stage row
 };
 
 struct CsGroup {
@@ -83,7 +97,7 @@ __device__ __forceinline__ bool cs_decode(const CsGroup* grp, int G, int n_branc
   u.kh = p.kh[j]; u.kw = p.kw[j]; u.hw = u.kw / 2; u.hh = u.kh / 2;
   u.PW = gr.per + 2 * u.hw;
   u.QT = gr.cyc * u.PW;
-  u.q0 = r * CS_BM;
+  u.q0 = r * (p.row_mode ? CS_BM - 2 * u.hw : CS_BM);   // row mode: a unit yields 128 - 2 hw outputs
   u.margin = u.hh * u.PW + u.hw;
   u.mode_a = (CS_BM + 2 * u.margin <= p.seg_cap) ? 1 : 0;
   u.rows = u.mode_a ? CS_BM + 2 * u.margin : CS_BM + 2 * u.hw;
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
   const uint32_t SEG_BYTES = ((uint32_t)nck * LBO_A + 127) & ~127u;
   const uint32_t LBO_W = (uint32_t)(NS * mid) * 16;          // chunk stride of the weight image: NS planes x mid rows
   const uint32_t TAP_BYTES = (uint32_t)NS * mid * mid * 2;
-  const int acc_cols = NS * mid;                              // accumulator columns per buffer
+  const int acc_cols = p.acc_cols;                            // accumulator columns per buffer
 
   uint8_t* s_w = smem;
   uint8_t* s_seg = smem + (size_t)p.w_slots * p.w_slot_bytes;
@@ -157,7 +171,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
       gr.S = 0;
       for (int j = 0; j < p.n_branch; ++j) {
         const int QT = gr.cyc * (gr.per + 2 * (p.kw[j] / 2));
-        gr.tiles[j] = (QT + CS_BM - 1) / CS_BM;
+        const int T = p.row_mode ? CS_BM - 2 * (p.kw[j] / 2) : CS_BM;
+        gr.tiles[j] = (QT + T - 1) / T;
         gr.S += gr.tiles[j];
       }
       gr.unit0 = unit0;
@@ -226,6 +241,29 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
             tc_fence_after();
             row_lo = seg_base[ss];
           }
+          if (p.row_mode) {
+            // one weight image per tap row: N = planes * kw * mid columns in one MMA per K16 step (two for fp16 pairs)
+            mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
+            tc_fence_after();
+            const uint32_t nrow = (uint32_t)(u.kw * mid);                     // columns of one weight plane
+            const uint32_t lbo_w = (uint32_t)NS * nrow * 16;                  // chunk stride of the row image
+            const uint32_t b_row = ((smem_u32(s_w) & 0x3FFFFu) >> 4) + w_slot * w_slot16;
+            const uint32_t b_hi_r = (uint32_t)(make_desc_interleaved(0, lbo_w) >> 32);
+            const uint32_t b_lbo_r = (uint32_t)make_desc_interleaved(0, lbo_w);
+            const uint32_t ks_wr = 2 * (lbo_w >> 4);
+            const uint32_t id_all = NS == 2 ? make_idesc_f16(CS_BM, (int)(2 * nrow)) : make_idesc_bf16(CS_BM, (int)nrow);
+            const uint32_t id_one = NS == 2 ? make_idesc_f16(CS_BM, (int)nrow) : id_all;
+            uint32_t ko_a = 0, b_k = b_row | b_lbo_r;
+            for (int ks = 0; ks < ksteps; ++ks, ko_a += ks_a, b_k += ks_wr) {
+              if (elect_one()) {
+                mma_bf16_lohi(acc, row_lo + ko_a, a_hi, b_k, b_hi_r, id_all, accum);
+                if (NS == 2) mma_bf16_lohi(acc, row_lo + a_pl + ko_a, a_hi, b_k, b_hi_r, id_one, 1u);
+              }
+              accum = 1;
+            }
+            if (elect_one()) mma_commit(&bars[CS_W_EMPTY + w_slot]);
+            if (++w_slot == n_wslots) { w_slot = 0; w_par ^= 1u; }
+          } else
           for (int dw0 = 0; dw0 < u.kw; dw0 += ut) {
             mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
             tc_fence_after();
@@ -358,6 +396,79 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
       const int buf = it & 1;
       mbar_wait_relaxed(&bars[CS_ACC_FULL + buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      if (p.row_mode) {
+        // accumulator row m = position q0 - hw + m, columns (plane, dw, n).  (1) plane sums of this warp's taps go to
+        // the shared-memory stage, (2) every output row adds its kw shifted partial sums: out[q0 + m] = sum_dw D[m + dw][dw]
+        float* stage = reinterpret_cast<float*>(smem + p.stage_off);
+        const int SP = p.stage_pitch;
+        const int nrow = u.kw * mid;
+        const int m = quad * 32 + lane;
+        const float sc = p.scale[u.j];
+        for (int dw = half; dw < u.kw; dw += 2) {
+          for (int c = 0; c < mid; c += 16) {
+            float v[16];
+            const uint32_t tcol = tmem_base + buf * acc_cols + dw * mid + c + ((uint32_t)(quad * 32) << 16);
+            if (NS == 2) {
+              uint32_t r0[16], r1[16];
+              tmem_ld16_nowait(tcol, r0);
+              tmem_ld16_nowait(tcol + nrow, r1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] = (__uint_as_float(r1[k]) + __uint_as_float(r0[k])) * sc;
+            } else {
+              tmem_ld16(tcol, v);
+            }
+            float4* d = reinterpret_cast<float4*>(stage + (size_t)m * SP + dw * mid + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[CS_ACC_EMPTY + buf]);   // the next unit's MMAs may reuse the accumulator
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // all partial sums of the unit are staged
+        const int T = CS_BM - 2 * u.hw;
+        const int q = u.q0 + m;
+        bool ok = m < T && q < u.QT;
+        int tt = 0;
+        if (ok) {
+          const float inv = 1.0f / (float)u.PW;
+          int rr = __float2int_rd(__int2float_rn(q) * inv);
+          if (rr * u.PW > q) --rr;
+          if ((rr + 1) * u.PW <= q) ++rr;
+          const int w = q - rr * u.PW - u.hw;
+          ok = w >= 0 && w < u.per;
+          tt = rr * u.per + w;
+        }
+        if (ok) {
+          const float* bias = p.bias[u.j];
+          const int c0 = half * (mid / 2);
+          __nv_bfloat16* dst = p.out + (u.img_row0 + (size_t)tt) * p.ld + u.j * mid;
+          for (int c = c0; c < c0 + mid / 2; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(bias + c + k);
+            const float* sp = stage + (size_t)m * SP + c;
+            for (int dw = 0; dw < u.kw; ++dw, sp += SP + mid) {
+              const float4 a = reinterpret_cast<const float4*>(sp)[0], b = reinterpret_cast<const float4*>(sp)[1];
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+              v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            }
+            if (NS == 2) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) split_h2(v[2 * k], v[2 * k + 1], h[k], l[k]);
+              *reinterpret_cast<uint4*>(dst + c) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(dst + p.NB + c) = make_uint4(l[0], l[1], l[2], l[3]);
+            } else {
+              *reinterpret_cast<uint4*>(dst + c) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // the stage may be overwritten by the next unit
+        continue;
+      }
       const int q = u.q0 + quad * 32 + lane;
       bool ok = q < u.QT;
       int tt = 0;
@@ -442,23 +553,40 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
 }
 
 // ---------------------------------------------------------------------------------
-struct CsLayout { int w_slots, w_slot_bytes, seg_cap; size_t smem; int ut[FTN_MAX_BRANCH]; bool ok; };
+struct CsLayout { int w_slots, w_slot_bytes, seg_cap; size_t smem; int ut[FTN_MAX_BRANCH]; bool ok; int stage_off, stage_pitch, acc_cols; };
+
+// row mode (taps of a tap row on N): bf16 or fp16-pair activations, every branch's planes * kw * mid <= 256 columns (one
+// MMA's N; two accumulator buffers then fit the 512 TMEM columns), and the row images packed
+static bool convs_row_mode(const FtnInceptionWeights* w, int ns) {
+  static const bool off = getenv("FLOWTIMES_CONVS_NO_ROW") != nullptr;   // A/B switch for profiling
+  if (off || (ns != 1 && ns != 2)) return false;
+  for (int j = 0; j < w->n_branch; ++j) {
+    if (ns * w->kw[j] * w->mid > 256) return false;
+    if (!(ns == 2 ? w->w_kk_row2[j] : w->w_kk_row[j])) return false;
+  }
+  return true;
+}
 
 static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
   CsLayout l{};
   const int mid = w->mid, nck = ns * mid / 8;
   const long long tap = (long long)ns * mid * mid * 2;
+  const bool row = convs_row_mode(w, ns);
   long long slot = 0;
-  int hw_max = 0;
+  int hw_max = 0, kw_max = 0;
+  for (int j = 0; j < w->n_branch; ++j) kw_max = kw_max > w->kw[j] ? kw_max : w->kw[j];
+  l.acc_cols = row ? ns * kw_max * mid : ns * mid;
+  l.stage_pitch = kw_max * mid + 4;                     // floats; (pitch / 4) odd: conflict-free 16-byte row accesses
+  const long long stage_bytes = row ? (long long)CS_BM * l.stage_pitch * 4 : 0;
   for (int j = 0; j < w->n_branch; ++j) {
-    l.ut[j] = (long long)w->kw[j] * tap <= 56 * 1024 ? w->kw[j] : 1;
+    l.ut[j] = (row || (long long)w->kw[j] * tap <= 56 * 1024) ? w->kw[j] : 1;
     slot = slot > l.ut[j] * tap ? slot : l.ut[j] * tap;
     hw_max = hw_max > w->kw[j] / 2 ? hw_max : w->kw[j] / 2;
   }
   slot = (slot + 127) & ~127ll;
   long long slots = (96 * 1024) / slot;
   slots = slots < 2 ? 2 : (slots > CS_WSLOTS_MAX ? CS_WSLOTS_MAX : slots);
-  const long long fixed = 128 + slots * slot + (CS_BARS + 4) * 8 + FTN_MAX_K * (long long)sizeof(CsGroup) + 64;
+  const long long fixed = 128 + slots * slot + (CS_BARS + 4) * 8 + FTN_MAX_K * (long long)sizeof(CsGroup) + 64 + stage_bytes + 16;
   long long cap = (227ll * 1024 - fixed) / CS_NSEG / (nck * 16) - 2 - 8;    // -8 rows: 128-byte rounding slack
   if (cap > 16000) cap = 16000;                                              // LBO field: 14 bits of 16-byte units
   // beyond ~2 tiles of halo the band of mode A stops paying for itself; a smaller buffer also leaves L1 some room
@@ -469,6 +597,8 @@ static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
   l.ok = cap >= CS_BM + 2 * hw_max;
   const size_t seg = (((size_t)nck * (size_t)(cap + 2) * 16) + 127) & ~size_t(127);
   l.smem = (size_t)fixed + CS_NSEG * seg;
+  // the stage sits behind everything the kernel carves up itself (weights, segments, barriers, group table)
+  l.stage_off = (int)((slots * slot + CS_NSEG * seg + (CS_BARS + 4) * 8 + FTN_MAX_K * sizeof(CsGroup) + 64 + 15) & ~size_t(15));
   return l;
 }
 
@@ -483,6 +613,11 @@ bool tc_convs_eligible(const FtnInceptionWeights* w, int ns) {
   return convs_layout(w, ns).ok;
 }
 
+// narrow branches (mid = 16): the row mode beats the image-resident tc_conv2 for bf16 activations too
+bool tc_convs_row_preferred(const FtnInceptionWeights* w) {
+  return w->mid == 16 && tc_convs_eligible(w, 1) && convs_row_mode(w, 1);
+}
+
 int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in, __nv_bfloat16* out,
                     int ld, const FtnInceptionWeights* w, int ns, cudaStream_t st, bool dependent) {
   FTN_REQUIRE(tc_convs_eligible(w, ns), "tc_convs: unsupported branch shape (mid=%d, planes=%d)", w->mid, ns);
@@ -491,14 +626,18 @@ int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   a.plan = plan; a.B = B; a.L = L; a.in = in; a.out = out; a.ld = ld; a.NB = w->n_branch * w->mid;
   a.mid = w->mid; a.n_branch = w->n_branch; a.ns = ns;
   a.seg_cap = l.seg_cap; a.w_slots = l.w_slots; a.w_slot_bytes = l.w_slot_bytes;
+  a.row_mode = convs_row_mode(w, ns) ? 1 : 0;
+  a.acc_cols = l.acc_cols; a.stage_off = l.stage_off; a.stage_pitch = l.stage_pitch;
   long long units_max = 0;
   for (int j = 0; j < w->n_branch; ++j) {
     a.kh[j] = w->kh[j]; a.kw[j] = w->kw[j]; a.ut[j] = l.ut[j];
-    a.w[j] = (const uint8_t*)(ns == 3 ? w->w_kk_img3[j] : (ns == 2 ? w->w_kk_img2[j] : w->w_kk_img[j]));
+    a.w[j] = a.row_mode ? (const uint8_t*)(ns == 2 ? w->w_kk_row2[j] : w->w_kk_row[j])
+                        : (const uint8_t*)(ns == 3 ? w->w_kk_img3[j] : (ns == 2 ? w->w_kk_img2[j] : w->w_kk_img[j]));
     a.bias[j] = w->b_kk[j];
     a.scale[j] = (ns == 2 && w->sc_kk[j] != 0.f) ? w->sc_kk[j] : 1.f;
     // worst case: period L - 1 (two cycles), padded width L - 1 + 2 hw
-    units_max += (long long)max_groups * B * ((2ll * (L + 2 * (w->kw[j] / 2)) + CS_BM - 1) / CS_BM);
+    const int T = a.row_mode ? CS_BM - 2 * (w->kw[j] / 2) : CS_BM;
+    units_max += (long long)max_groups * B * ((2ll * (L + 2 * (w->kw[j] / 2)) + T - 1) / T);
   }
   const int sms = sm_count();
   const int ctas = (int)(units_max < sms ? (units_max < 1 ? 1 : units_max) : sms);

@@ -161,9 +161,11 @@ int tc_kk_stage(const FtnPeriodPlan* plan, int B, int L, int max_groups, const _
 bool tc_conv4_covers(const FtnInceptionWeights* w, int L, int period_lo, int period_hi);
 bool tc_kk_uses_conv4(const FtnInceptionWeights* w);
 
-// streaming variant (tc_convs.cu): any mid % 16 == 0, bf16 activations (ns = 1) or three-plane fp32 (ns = 3);
+// streaming variant (tc_convs.cu): any mid % 16 == 0, bf16 activations (ns = 1), two-plane fp16 (ns = 2) or three-plane
+// bf16 (ns = 3) fp32 activations; narrow branches (planes * kw * mid <= 256) run its row mode (taps of a tap row on N);
 // in / out are tile-major [rows][ld] with plane p of branch j at columns p * n_branch * mid + j * mid
 bool tc_convs_eligible(const FtnInceptionWeights* w, int ns);
+bool tc_convs_row_preferred(const FtnInceptionWeights* w);   // mid = 16, bf16: the row mode of tc_convs beats tc_conv2
 int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, const __nv_bfloat16* in, __nv_bfloat16* out,
                     int ld, const FtnInceptionWeights* w, int ns, cudaStream_t st, bool dependent = true);
 

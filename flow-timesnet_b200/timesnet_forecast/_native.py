@@ -16,7 +16,7 @@ import torch
 
 FTN_F32, FTN_BF16 = 0, 1
 FTN_ACT_GELU, FTN_ACT_RELU = 0, 1
-ABI_VERSION = 16
+ABI_VERSION = 17
 FTN_MAX_K = 16
 FTN_MAX_BRANCH = 8
 
@@ -63,6 +63,7 @@ class FtnInceptionWeights(C.Structure):
         ("w_kk_img2", C.c_void_p * FTN_MAX_BRANCH),
         ("sc_in", C.c_float), ("sc_out", C.c_float), ("sc_res", C.c_float),
         ("sc_kk", C.c_float * FTN_MAX_BRANCH),
+        ("w_kk_row", C.c_void_p * FTN_MAX_BRANCH), ("w_kk_row2", C.c_void_p * FTN_MAX_BRANCH),
     ]
 
 

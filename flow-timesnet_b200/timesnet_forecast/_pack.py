@@ -119,6 +119,10 @@ def pack_inception_block(block: nn.Module, device: torch.device) -> PackedIncept
                 if img2 is not None:
                     st.w_kk_img2[j] = dev_planes(img2)
                     st.sc_kk[j] = inv
+                if kw * mid <= 256:                                          # row mode of tc_convs (narrow branches)
+                    st.w_kk_row[j] = dev_planes(_row_images(img3[:, :, :1], kh, kw))
+                    if img2 is not None and 2 * kw * mid <= 256:
+                        st.w_kk_row2[j] = dev_planes(_row_images(img2, kh, kw))
             macs += kh * kw * mid * mid
             P = proj_w[:, j * cout:(j + 1) * cout]                           # [cout, cout]
             W3 = p[2].weight.detach().to("cpu", f64)[:, :, 0, 0]             # [cout, mid]
@@ -225,6 +229,15 @@ def _tap_images_h2(wk: torch.Tensor):
     st = torch.stack(planes, dim=0)                                          # [2][out][in][kh][kw]
     img = st.permute(3, 4, 0, 2, 1).reshape(kh * kw, 2, n_in // 8, 8, n_out)  # [tap][plane][chunk][8 in][out]
     return img.permute(0, 2, 1, 4, 3).contiguous(), inv                       # [tap][chunk][plane][out][8 in]
+
+
+def _row_images(img: torch.Tensor, kh: int, kw: int) -> torch.Tensor:
+    """Per-tap images ``[kh*kw][chunk][plane][out][8]`` -> per-tap-ROW images ``[kh][chunk][plane][kw][out][8]``: the kw
+    taps of a row side by side on N (tc_convs.cu, row mode)."""
+    taps, chunks, planes, n_out, eight = (int(v) for v in img.shape)
+    assert taps == kh * kw
+    r = img.reshape(kh, kw, chunks, planes, n_out, eight).permute(0, 2, 3, 1, 4, 5)
+    return r.contiguous()
 
 
 def _tap_images(wk: torch.Tensor) -> torch.Tensor:

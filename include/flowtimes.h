@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FTN_ABI_VERSION 16
+#define FTN_ABI_VERSION 17
 
 #if defined(__GNUC__)
 #define FTN_API __attribute__((visibility("default")))
@@ -139,6 +139,11 @@ typedef struct FtnInceptionWeights {
   const void* w_kk_img2[FTN_MAX_BRANCH];
   float sc_in, sc_out, sc_res;
   float sc_kk[FTN_MAX_BRANCH];
+  /* Row images of the streaming k x k kernel for narrow branches (planes * kw * mid <= 256): the kw taps of a tap row
+   * side by side on N, [kh][mid / 8 chunks][plane][kw][mid out channels][8 in channels]; w_kk_row is bf16 (one plane),
+   * w_kk_row2 the two fp16 planes of the scaled weights (same scale sc_kk as w_kk_img2).  NULL = tap-by-tap stream. */
+  const void* w_kk_row[FTN_MAX_BRANCH];
+  const void* w_kk_row2[FTN_MAX_BRANCH];
 } FtnInceptionWeights;
 
 /* ---- library ---------------------------------------------------------- */

@@ -158,7 +158,10 @@ def _tile_major_images(plan_host, B, L, NB, seed, dtype):
 
 
 @pytest.mark.parametrize("mid,L,periods", [(16, 96, [24, 12, 7, 48, 95]), (32, 336, [24, 168, 335, 5]), (64, 720, [6, 24, 359, 719]),
-                                            (64, 96, [1, 2, 48]), (48, 50, [7, 25])])
+                                            (64, 96, [1, 2, 48]), (48, 50, [7, 25]),
+                                            # mid = 16 runs the row mode (taps of a tap row on N): long periods (one segment
+                                            # per tap row), single-row grids, periods shorter than the kernel
+                                            (16, 336, [24, 12, 7, 168, 335]), (16, 720, [6, 359, 719]), (16, 50, [1, 2, 3, 49])])
 @pytest.mark.parametrize("planes", [1, 2, 3])
 def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
     """Streaming k x k kernel (any mid, bf16 or three-plane fp32 activations) against torch conv2d in float64 on the
