@@ -286,7 +286,13 @@ def run_native(args):
         raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
+        # the contract is ONE JSON line on stdout: NCCL prints its version banner there (NCCL_DEBUG=VERSION on the pool's
+        # multi-GPU boxes), so stdout points at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     nv.load()
@@ -648,6 +654,9 @@ def run_native(args):
             line["strong_scaling"] = strong
         if same_periods is not None:
             line["periods_identical_on_all_ranks"] = same_periods
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: communicator destruction with captured graphs that still hold
