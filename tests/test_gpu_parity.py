@@ -276,6 +276,30 @@ def test_full_size_etth1_windows_match_oracle(dname):
         assert _rel(out[sl], tr.out) < tol
 
 
+@pytest.mark.parametrize("periods", [[7, 14], [27, 9], [28, 2]])
+@pytest.mark.parametrize("B", [6, 70])
+def test_short_window_fused_block_matches_oracle(periods, B):
+    """Config-5 block geometry (L = 28, C = 128, F = 512, bf16) through the fused route with every short-window form
+    at once: 32-row granules, stacked tc_conv4 units (several windows per unit, a ragged last unit at B = 70) and
+    tc_tail items of four windows (a ragged last quad at B = 6 and 70); images of one and two granules."""
+    wl = syn.WORKLOADS["recursive"]
+    w = syn.stack_weights(wl, seed=0)
+    x = syn.white_features(B, wl.T, wl.d_model, seed=11).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    amps = torch.randn(B, len(periods), generator=g)
+    blk = _make_block(wl, w)
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    torch.cuda.synchronize()
+    tr = orc.timesblock_from_periods(x, periods, amps.to(torch.bfloat16), w, "blocks.0.inception.")
+    assert _rel(out, tr.out) < REL_BF16
+    # every window on its own: a window must not see its neighbours in a stacked unit or a quad item
+    for b in (0, B // 2, B - 1):
+        object.__setattr__(blk, "period_selector", FixedSelector(periods, amps[b:b + 1]))
+        one = blk(x[b:b + 1].cuda())
+        assert torch.equal(one[0], out[b]), f"window {b} depends on its batch neighbours"
+
+
 def test_elec_block_with_long_periods_matches_oracle():
     """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
     inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""
