@@ -66,6 +66,10 @@ struct TcConvsArgs {
   const uint8_t* w[FTN_MAX_BRANCH];    // [tap][chunk][plane][n][8] bf16
   const float* bias[FTN_MAX_BRANCH];
   float scale[FTN_MAX_BRANCH];         // NS = 2: power of two that undoes the host-side weight scaling (1 otherwise)
+  int w_resident;  // row mode, small branches: the row images of ALL branches stay in shared memory (one slot of
+                   // w_slot_bytes, branch j at w_off[j]), loaded once per CTA -- no per-unit weight stream (one bulk copy and
+                   // two barrier hops per tap row and unit made the producer thread the bottleneck of the etth1 shapes)
+  int w_off[FTN_MAX_BRANCH];
   int row_mode;    // taps of a tap row side by side on N (see the header); w[] then holds one image per tap ROW,
                    // [kh][chunk][plane][dw][n][8], and a weight slot is a whole row (ut = kw)
   int acc_cols;    // accumulator columns per TMEM buffer
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
       const uint32_t n_wslots = (uint32_t)p.w_slots;
       CsUnit u;
       uint32_t seg_it = 0, w_slot = 0, w_par = 0;
+      bool w_ready = false;
       int it = 0;
       for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride, ++it) {
         const int buf = it & 1;
@@ -243,11 +248,19 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
           }
           if (p.row_mode) {
             // one weight image per tap row: N = planes * kw * mid columns in one MMA per K16 step (two for fp16 pairs)
-            mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
-            tc_fence_after();
+            if (!p.w_resident) {
+              mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
+              tc_fence_after();
+            } else if (!w_ready) {
+              mbar_wait(&bars[CS_W_FULL], 0);   // all branches' images, loaded once
+              tc_fence_after();
+              w_ready = true;
+            }
             const uint32_t nrow = (uint32_t)(u.kw * mid);                     // columns of one weight plane
             const uint32_t lbo_w = (uint32_t)NS * nrow * 16;                  // chunk stride of the row image
-            const uint32_t b_row = ((smem_u32(s_w) & 0x3FFFFu) >> 4) + w_slot * w_slot16;
+            const uint32_t b_row = ((smem_u32(s_w) & 0x3FFFFu) >> 4) +
+                                   (p.w_resident ? ((uint32_t)p.w_off[u.j] + (uint32_t)dr * (uint32_t)u.kw * TAP_BYTES) >> 4
+                                                 : w_slot * w_slot16);
             const uint32_t b_hi_r = (uint32_t)(make_desc_interleaved(0, lbo_w) >> 32);
             const uint32_t b_lbo_r = (uint32_t)make_desc_interleaved(0, lbo_w);
             const uint32_t ks_wr = 2 * (lbo_w >> 4);
@@ -261,8 +274,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
               }
               accum = 1;
             }
-            if (elect_one()) mma_commit(&bars[CS_W_EMPTY + w_slot]);
-            if (++w_slot == n_wslots) { w_slot = 0; w_par ^= 1u; }
+            if (!p.w_resident) {
+              if (elect_one()) mma_commit(&bars[CS_W_EMPTY + w_slot]);
+              if (++w_slot == n_wslots) { w_slot = 0; w_par ^= 1u; }
+            }
           } else
           for (int dw0 = 0; dw0 < u.kw; dw0 += ut) {
             mbar_wait(&bars[CS_W_FULL + w_slot], w_par);
@@ -322,7 +337,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
     __syncwarp();
   } else if (warp == 1) {
     // ===================== weight producer: one bulk copy per ring slot =====================
-    if (lane == 0) {
+    if (lane == 0 && p.w_resident) {
+      uint32_t total = 0;
+      for (int j = 0; j < p.n_branch; ++j) total += (uint32_t)(p.kh[j] * p.kw[j]) * TAP_BYTES;
+      mbar_arrive_expect_tx(&bars[CS_W_FULL], total);
+      for (int j = 0; j < p.n_branch; ++j)
+        cs_bulk_load(s_w + p.w_off[j], p.w[j], (uint32_t)(p.kh[j] * p.kw[j]) * TAP_BYTES, &bars[CS_W_FULL]);
+    } else if (lane == 0) {
       CsUnit u;
       uint32_t w_it = 0;
       for (int unit = blockIdx.x; cs_decode(s_grp, G, p.n_branch, p, unit, u); unit += stride) {
@@ -404,21 +425,34 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
         const int nrow = u.kw * mid;
         const int m = quad * 32 + lane;
         const float sc = p.scale[u.j];
-        for (int dw = half; dw < u.kw; dw += 2) {
-          for (int c = 0; c < mid; c += 16) {
-            float v[16];
-            const uint32_t tcol = tmem_base + buf * acc_cols + dw * mid + c + ((uint32_t)(quad * 32) << 16);
-            if (NS == 2) {
-              uint32_t r0[16], r1[16];
-              tmem_ld16_nowait(tcol, r0);
-              tmem_ld16_nowait(tcol + nrow, r1);
-              tmem_ld_wait();
+        // this warp's taps are dw = half, half + 2, ...: two (tap, 16-column group) items per TMEM round trip (a load ->
+        // wait -> store chain per tap left the eight warps waiting on TMEM latency four times per unit)
+        const int n16 = mid / 16;
+        const int n_items = ((u.kw - half + 1) / 2) * n16;
+        for (int it0 = 0; it0 < n_items; it0 += 2) {
+          uint32_t ra[2][16], rb[2][16];
+          int col[2];
 #pragma unroll
-              for (int k = 0; k < 16; ++k) v[k] = (__uint_as_float(r1[k]) + __uint_as_float(r0[k])) * sc;
-            } else {
-              tmem_ld16(tcol, v);
+          for (int e = 0; e < 2; ++e) {
+            const int item = it0 + e;
+            col[e] = -1;
+            if (item < n_items) {
+              const int dw = half + 2 * (item / n16), c = (item % n16) * 16;
+              col[e] = dw * mid + c;
+              const uint32_t tcol = tmem_base + buf * acc_cols + col[e] + ((uint32_t)(quad * 32) << 16);
+              tmem_ld16_nowait(tcol, ra[e]);
+              if (NS == 2) tmem_ld16_nowait(tcol + nrow, rb[e]);
             }
-            float4* d = reinterpret_cast<float4*>(stage + (size_t)m * SP + dw * mid + c);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (col[e] < 0) continue;
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              v[k] = NS == 2 ? (__uint_as_float(rb[e][k]) + __uint_as_float(ra[e][k])) * sc : __uint_as_float(ra[e][k]);
+            float4* d = reinterpret_cast<float4*>(stage + (size_t)m * SP + col[e]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) d[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           }
@@ -553,7 +587,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) tc_convs_kernel(const TcConvsAr
 }
 
 // ---------------------------------------------------------------------------------
-struct CsLayout { int w_slots, w_slot_bytes, seg_cap; size_t smem; int ut[FTN_MAX_BRANCH]; bool ok; int stage_off, stage_pitch, acc_cols; };
+struct CsLayout { int w_slots, w_slot_bytes, seg_cap; size_t smem; int ut[FTN_MAX_BRANCH]; bool ok; int stage_off, stage_pitch, acc_cols;
+                  bool w_resident; int w_off[FTN_MAX_BRANCH]; };
 
 // row mode (taps of a tap row on N): bf16 or fp16-pair activations, every branch's planes * kw * mid <= 256 columns (one
 // MMA's N; two accumulator buffers then fit the 512 TMEM columns), and the row images packed
@@ -586,6 +621,15 @@ static CsLayout convs_layout(const FtnInceptionWeights* w, int ns) {
   slot = (slot + 127) & ~127ll;
   long long slots = (96 * 1024) / slot;
   slots = slots < 2 ? 2 : (slots > CS_WSLOTS_MAX ? CS_WSLOTS_MAX : slots);
+  // row mode with small branches: every branch's row images resident (one "slot" holding all of them)
+  long long resident = 0;
+  for (int j = 0; j < w->n_branch; ++j) {
+    l.w_off[j] = (int)resident;
+    resident += ((long long)w->kh[j] * w->kw[j] * tap + 127) & ~127ll;
+  }
+  static const bool no_resident = getenv("FLOWTIMES_CONVS_STREAM_W") != nullptr;   // A/B switch for profiling
+  l.w_resident = row && !no_resident && resident <= 100 * 1024;
+  if (l.w_resident) { slots = 1; slot = resident; }
   const long long fixed = 128 + slots * slot + (CS_BARS + 4) * 8 + FTN_MAX_K * (long long)sizeof(CsGroup) + 64 + stage_bytes + 16;
   long long cap = (227ll * 1024 - fixed) / CS_NSEG / (nck * 16) - 2 - 8;    // -8 rows: 128-byte rounding slack
   if (cap > 16000) cap = 16000;                                              // LBO field: 14 bits of 16-byte units
@@ -627,6 +671,8 @@ int tc_convs_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
   a.mid = w->mid; a.n_branch = w->n_branch; a.ns = ns;
   a.seg_cap = l.seg_cap; a.w_slots = l.w_slots; a.w_slot_bytes = l.w_slot_bytes;
   a.row_mode = convs_row_mode(w, ns) ? 1 : 0;
+  a.w_resident = l.w_resident ? 1 : 0;
+  for (int j = 0; j < w->n_branch; ++j) a.w_off[j] = l.w_off[j];
   a.acc_cols = l.acc_cols; a.stage_off = l.stage_off; a.stage_pitch = l.stage_pitch;
   long long units_max = 0;
   for (int j = 0; j < w->n_branch; ++j) {
