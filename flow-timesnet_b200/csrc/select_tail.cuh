@@ -51,8 +51,11 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   unsigned same = 0;
   int canon = -1;
   uint32_t best = 0;
-#pragma unroll
-  for (int j = 0; j < FTN_MAX_K; ++j) {
+  // rolled, and over the nv live candidates only (warp-uniform): this code runs ONCE per launch, from a cold instruction
+  // cache -- sixteen unrolled copies of the body were ~40 cache lines fetched from L2 one after the other (the grouping
+  // was 9 us of the tail's 17), five trips through two lines are not
+#pragma unroll 1
+  for (int j = 0; j < nv; ++j) {
     const int kj = __shfl_sync(0xffffffffu, key, j);
     const uint32_t aj = __shfl_sync(0xffffffffu, akey, j);
     // selects, not branches: a data-dependent branch between two shuffles costs a divergence + reconvergence round
@@ -67,8 +70,8 @@ __device__ __forceinline__ void plan_group_warp(FtnPeriodPlan* pl, int lane, int
   const int pf = first ? my_p : 0x7fffffff;
   const int len = first ? L + pad : 0;
   int rank = 0, off = 0, total = 0;
-#pragma unroll
-  for (int j = 0; j < FTN_MAX_K; ++j) {
+#pragma unroll 1
+  for (int j = 0; j < nv; ++j) {
     const int pj = __shfl_sync(0xffffffffu, pf, j);
     const int lj = __shfl_sync(0xffffffffu, len, j);
     const bool before = pj < my_p;
@@ -305,17 +308,24 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
 #pragma unroll 1
     for (int b = tid; b < B; b += kSelFinishThreads) {
       float mx = -CUDART_INF_F;
-      float raw[FTN_MAX_K];
+      // four candidates per trip: their loads are in flight together (one L2 round trip per trip), and the loop body is
+      // fetched once -- sixteen unrolled copies were ~300 instructions of cold straight-line code for k = 5
+#pragma unroll 1
+      for (int j0 = 0; j0 < FTN_MAX_K; j0 += 4) {
+        if (j0 >= nv && j0 >= k) break;
+        float raw[4];
 #pragma unroll
-      for (int j = 0; j < FTN_MAX_K; ++j)                    // all loads in flight together (one L2 round trip)
-        raw[j] = j < nv ? __ldcg(amp_median + (size_t)b * F + (int)sh->plan.freq[j]) : 0.f;
+        for (int i = 0; i < 4; ++i)
+          raw[i] = j0 + i < nv ? __ldcg(amp_median + (size_t)b * F + (int)sh->plan.freq[j0 + i]) : 0.f;
 #pragma unroll
-      for (int j = 0; j < FTN_MAX_K; ++j) {
-        const float v = j < nv ? round_to<T>(raw[j]) : 0.f;
-        if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
-        if (j < nv) {
-          sh->e[j][tid] = v;
-          if (sh->plan.mapping[j] >= 0) mx = fmaxf(mx, v);
+        for (int i = 0; i < 4; ++i) {
+          const int j = j0 + i;
+          const float v = j < nv ? round_to<T>(raw[i]) : 0.f;
+          if (j < k) amps[(size_t)b * k + j] = from_f32<T>(v);
+          if (j < nv) {
+            sh->e[j][tid] = v;
+            if (sh->plan.mapping[j] >= 0) mx = fmaxf(mx, v);
+          }
         }
       }
       float den = 0.f;
@@ -328,14 +338,14 @@ __device__ __forceinline__ void select_tail(const float* __restrict__ amp_median
 #pragma unroll 1
       for (int j = 0; j < nv; ++j)
         sh->e[j][tid] = round_to<T>(sh->w[j][tid] / den);                // softmax fp32 -> dtype (timesnet.py:1000)
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < FTN_MAX_K; ++g) sh->w[g][tid] = 0.f;
 #pragma unroll 1
       for (int j = 0; j < nv; ++j) {                        // candidates in index order, exactly like scatter_add_
         const int g = sh->plan.mapping[j];
         if (g >= 0) sh->w[g][tid] = round_to<T>(sh->w[g][tid] + sh->e[j][tid]);   // scatter_add_ in dtype (:1009)
       }
-#pragma unroll
+#pragma unroll 4
       for (int g = 0; g < FTN_MAX_K; ++g) weights[(size_t)b * FTN_MAX_K + g] = sh->w[g][tid];
     }
   }
