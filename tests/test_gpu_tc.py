@@ -166,12 +166,24 @@ def _tile_major_images(plan_host, B, L, NB, seed, dtype):
 def test_tc_convs_streaming_kernel_matches_conv2d(mid, L, periods, planes):
     """Streaming k x k kernel (any mid, bf16 or three-plane fp32 activations) against torch conv2d in float64 on the
     folded grids: bf16 activations to one output rounding, the three-plane mode to fp32 accuracy."""
+    _convs_vs_conv2d(mid, L, periods, planes, [(3, 3), (5, 5), (7, 7)])
+
+
+@pytest.mark.parametrize("mid", [16, 64])
+@pytest.mark.parametrize("planes", [1, 2])
+def test_tc_convs_rectangular_kernels(mid, planes):
+    """Non-square kernels (kh != kw, a 1 x 7 row kernel, a 7 x 1 column kernel) through the streaming kernel: mid = 16
+    takes the row mode (kw taps on N, kh MMAs), mid = 64 the tap-by-tap stream."""
+    _convs_vs_conv2d(mid, 96, [24, 7, 48, 95], planes, [(3, 5), (1, 7), (7, 1)])
+
+
+def _convs_vs_conv2d(mid, L, periods, planes, kernel_set):
     from timesnet_forecast import _native as nv
     from timesnet_forecast._pack import split3, split_h2
     from timesnet_forecast.models.timesnet import InceptionBlock
     B, C = 2, mid * 4
     torch.manual_seed(0)
-    blk = InceptionBlock(C, C, [(3, 3), (5, 5), (7, 7)], 0.0, "gelu", bottleneck_ratio=4.0).cuda()
+    blk = InceptionBlock(C, C, kernel_set, 0.0, "gelu", bottleneck_ratio=4.0).cuda()
     packed = blk.packed(torch.device("cuda"))
     assert packed.struct.mid == mid
     plan_host = nv.plan_build_host(periods, L, None, None)
