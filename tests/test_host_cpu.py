@@ -237,3 +237,55 @@ def test_phase_stage_images_are_toeplitz_windows():
                         dx = s - phi
                         want = wk[:, c * 8:(c + 1) * 8, dr, dx] if 0 <= dx < kw else torch.zeros(32, 8, dtype=torch.float64)
                         assert torch.equal(blk, want), (kh, dr, c, s, phi)
+
+
+def test_split_h2_is_a_22_bit_pair_with_an_exact_scale():
+    """_pack.split_h2: hi + lo reproduces w * 2^s to 2^-22 relative of the largest entry, the scale is an exact power of two
+    that puts the largest magnitude in [2^13, 2^14), zeros and tiny / huge tensors survive, non-finite tensors are refused."""
+    import math
+    import torch
+    from timesnet_forecast._pack import split_h2
+    g = torch.Generator().manual_seed(0)
+    for mag in (1e-6, 3e-3, 0.05, 1.0, 700.0, 1e6):
+        w = torch.randn(64, 48, generator=g) * mag
+        w[0, 0] = 0.0
+        (hi, lo), inv = split_h2(w)
+        assert hi.dtype == torch.float16 and lo.dtype == torch.float16
+        s = -math.log2(inv)
+        assert s == int(s)                                                   # exact power of two
+        amax = float(w.abs().max()) / inv
+        assert 2 ** 13 <= amax < 2 ** 14
+        assert bool(torch.isfinite(hi).all()) and bool(torch.isfinite(lo).all())
+        back = (hi.double() + lo.double()) * inv
+        err = float((back - w.double()).abs().max()) / float(w.abs().max())
+        assert err < 2.0 ** -22, (mag, err)
+    (hi, lo), inv = split_h2(torch.zeros(4, 4))
+    assert inv == 1.0 and float(hi.abs().max()) == 0.0
+    bad = torch.ones(4, 4)
+    bad[1, 1] = float("inf")
+    assert split_h2(bad) == (None, 0.0)
+
+
+def test_row_images_put_the_taps_of_a_row_side_by_side():
+    """_pack._row_images (tc_convs.cu, row mode): [kh][chunk][plane][kw][out][8 in] -- for a tap row and an 8-channel
+    chunk, rows (plane, dw, n) are the N axis of ONE operand, so the kw taps of the row multiply in one MMA."""
+    import torch
+    from timesnet_forecast._pack import _row_images, _tap_images, _tap_images_h2
+    g = torch.Generator().manual_seed(1)
+    for kh, kw in ((3, 3), (3, 5), (7, 7), (1, 7)):
+        wk = torch.randn(16, 16, kh, kw, generator=g, dtype=torch.float64)
+        img3 = _tap_images(wk)                                               # [tap][chunk][3][out][8]
+        row = _row_images(img3[:, :, :1], kh, kw)
+        assert tuple(row.shape) == (kh, 2, 1, kw, 16, 8)
+        for dr in range(kh):
+            for dw in range(kw):
+                assert torch.equal(row[dr, :, 0, dw], img3[dr * kw + dw, :, 0])
+                want = wk[:, :, dr, dw].to(torch.float32).to(torch.bfloat16)       # [out][in]
+                got = row[dr, :, 0, dw].permute(1, 0, 2).reshape(16, 16)             # [out][chunk * 8 + in]
+                assert torch.equal(got, want)
+        img2, inv = _tap_images_h2(wk)
+        row2 = _row_images(img2, kh, kw)
+        assert tuple(row2.shape) == (kh, 2, 2, kw, 16, 8) and row2.dtype == torch.float16
+        back = (row2[:, :, 0].double() + row2[:, :, 1].double()) * inv       # [kh][chunk][kw][out][8]
+        want = wk.permute(2, 3, 0, 1).reshape(kh, kw, 16, 2, 8).permute(0, 3, 1, 2, 4)   # [kh][chunk][kw][out][8]
+        assert float((back - want).abs().max()) < 2.0 ** -20 * float(wk.abs().max())
