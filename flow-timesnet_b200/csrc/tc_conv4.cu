@@ -572,6 +572,21 @@ int tc_conv4_launch(const FtnPeriodPlan* plan, int B, int L, int max_groups, con
     }
     ++n_cta[worst];
   }
+  // experiment switch: FLOWTIMES_CONV_SPLIT="a,b,c" overrides the CTAs per branch (the sum must not exceed the SM count)
+  if (const char* ov = getenv("FLOWTIMES_CONV_SPLIT")) {
+    int v[FTN_MAX_BRANCH] = {0}, n = 0, tot = 0;
+    for (const char* q = ov; *q && n < FTN_MAX_BRANCH; ++n) {
+      v[n] = atoi(q);
+      tot += v[n];
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (n == w->n_branch && tot <= sms) {
+      bool ok = true;
+      for (int j = 0; j < n; ++j) ok = ok && v[j] >= 1;
+      if (ok) for (int j = 0; j < n; ++j) n_cta[j] = v[j];
+    }
+  }
   a.cta_begin[0] = 0;
   for (int j = 0; j < w->n_branch; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + n_cta[j];
   a.n_ctas0 = a.cta_begin[w->n_branch];
