@@ -374,6 +374,44 @@ spectrum_small_kernel(const T* __restrict__ x, int B, int L, int C, float* __res
       }
       const float x0 = xs[tid];
       const float xh = (L & 1) ? 0.f : xs[(L / 2) * Cp + tid];
+      if ((L & 1) == 0) {
+        // even L: bins f and g = L / 2 - f share their products, cos(2 pi g t / L) = (-1)^t cos(2 pi f t / L) and
+        // sin(2 pi g t / L) = -(-1)^t sin(2 pi f t / L): with the even-t and odd-t partial sums E, O of bin f,
+        //   X[f] = (x0 +- xh + Ec + Oc, -(Es + Os)),   X[g] = (x0 +- xh + Ec - Oc, Es - Os)
+        // -- two bins for the multiply-adds of one (this loop is 60 % of the kernel's instructions)
+        const int half = L / 2;
+        for (int f = 0; 2 * f <= half; ++f) {
+          const int g = half - f;
+          float ec = 0.f, oc = 0.f, es = 0.f, os = 0.f;
+          int idx = 0;
+          int t = 1;
+          for (; t + 1 <= H; t += 2) {
+            idx += f;
+            if (idx >= L) idx -= L;
+            const float2 w1 = tw[idx];
+            oc = fmaf(xs[t * Cp + tid], w1.x, oc);
+            os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
+            idx += f;
+            if (idx >= L) idx -= L;
+            const float2 w2 = tw[idx];
+            ec = fmaf(xs[(t + 1) * Cp + tid], w2.x, ec);
+            es = fmaf(xs[(L - t - 1) * Cp + tid], w2.y, es);
+          }
+          if (t <= H) {                                     // H odd: one more odd step
+            idx += f;
+            if (idx >= L) idx -= L;
+            const float2 w1 = tw[idx];
+            oc = fmaf(xs[t * Cp + tid], w1.x, oc);
+            os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
+          }
+          const float re_f = (x0 + ((f & 1) ? -xh : xh)) + (ec + oc), im_f = es + os;
+          amp[f * nthr + tid] = sqrtf(fmaf(re_f, re_f, im_f * im_f));
+          if (g != f) {
+            const float re_g = (x0 + ((g & 1) ? -xh : xh)) + (ec - oc), im_g = es - os;
+            amp[g * nthr + tid] = sqrtf(fmaf(re_g, re_g, im_g * im_g));
+          }
+        }
+      } else
       for (int f = 0; f < F; ++f) {
         float re = x0 + ((f & 1) ? -xh : xh), im = 0.f;
         int idx = 0;
