@@ -95,6 +95,36 @@ int ctx_event_pair(cudaEvent_t* a, cudaEvent_t* b);       // a fresh fork / join
     if (int rc_ = ::ftn::ensure_dyn_smem((const void*)(kernel), (size_t)(bytes))) return rc_; \
   } while (0)
 
+// ascending sort of N registers: bitonic network whose merges start with the mirrored compare (i, i ^ (size - 1)),
+// so every compare-exchange orders (low index, high index) and the whole thing is FMNMX pairs on fixed registers
+template <int N>
+__device__ __forceinline__ void sort_regs(float (&v)[N]) {
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int j = i ^ (size - 1);
+      if (j > i) {
+        const float lo = fminf(v[i], v[j]), hi = fmaxf(v[i], v[j]);
+        v[i] = lo;
+        v[j] = hi;
+      }
+    }
+#pragma unroll
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const float lo = fminf(v[i], v[j]), hi = fmaxf(v[i], v[j]);
+          v[i] = lo;
+          v[j] = hi;
+        }
+      }
+    }
+  }
+}
+
 // ---- dtype access -------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);

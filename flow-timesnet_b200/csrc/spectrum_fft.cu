@@ -341,6 +341,73 @@ channel_median_reg_kernel(const float* __restrict__ amp, int rows, int C, float*
 //   * each bin's medians are also summed over the windows of this CTA (fixed order), so the batch sum of the search is
 //     a second-level sum over gridDim.x partial rows instead of B median rows.
 // ---------------------------------------------------------------------------------------------------------------
+// amplitudes of one window for channel `tid` (one thread per channel): amp[f * amp_pitch + slot], f = 0 .. F - 1
+template <typename T>
+__device__ __forceinline__ void small_window_amps(const T* __restrict__ xb, int L, int C, int F, int H, int Cp, int tid,
+                                                  const float2* __restrict__ tw, float* __restrict__ xs,
+                                                  float* __restrict__ amp, int amp_pitch, int slot) {
+#pragma unroll 4
+  for (int t = 0; t < L; ++t) xs[t * Cp + tid] = to_f32<T>(xb[(size_t)t * C + tid]);
+  for (int t = 1; t <= H; ++t) {                      // fold: rows 1..H hold s, rows L-H..L-1 hold d
+    const float a = xs[t * Cp + tid], z = xs[(L - t) * Cp + tid];
+    xs[t * Cp + tid] = a + z;
+    xs[(L - t) * Cp + tid] = a - z;
+  }
+  const float x0 = xs[tid];
+  const float xh = (L & 1) ? 0.f : xs[(L / 2) * Cp + tid];
+  if ((L & 1) == 0) {
+    // even L: bins f and g = L / 2 - f share their products, cos(2 pi g t / L) = (-1)^t cos(2 pi f t / L) and
+    // sin(2 pi g t / L) = -(-1)^t sin(2 pi f t / L): with the even-t and odd-t partial sums E, O of bin f,
+    //   X[f] = (x0 +- xh + Ec + Oc, -(Es + Os)),   X[g] = (x0 +- xh + Ec - Oc, Es - Os)
+    // -- two bins for the multiply-adds of one (this loop is 60 % of the kernel's instructions)
+    const int half = L / 2;
+    for (int f = 0; 2 * f <= half; ++f) {
+      const int g = half - f;
+      float ec = 0.f, oc = 0.f, es = 0.f, os = 0.f;
+      int idx = 0;
+      int t = 1;
+      for (; t + 1 <= H; t += 2) {
+        idx += f;
+        if (idx >= L) idx -= L;
+        const float2 w1 = tw[idx];
+        oc = fmaf(xs[t * Cp + tid], w1.x, oc);
+        os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
+        idx += f;
+        if (idx >= L) idx -= L;
+        const float2 w2 = tw[idx];
+        ec = fmaf(xs[(t + 1) * Cp + tid], w2.x, ec);
+        es = fmaf(xs[(L - t - 1) * Cp + tid], w2.y, es);
+      }
+      if (t <= H) {                                     // H odd: one more odd step
+        idx += f;
+        if (idx >= L) idx -= L;
+        const float2 w1 = tw[idx];
+        oc = fmaf(xs[t * Cp + tid], w1.x, oc);
+        os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
+      }
+      const float re_f = (x0 + ((f & 1) ? -xh : xh)) + (ec + oc), im_f = es + os;
+      amp[f * amp_pitch + slot] = sqrtf(fmaf(re_f, re_f, im_f * im_f));
+      if (g != f) {
+        const float re_g = (x0 + ((g & 1) ? -xh : xh)) + (ec - oc), im_g = es - os;
+        amp[g * amp_pitch + slot] = sqrtf(fmaf(re_g, re_g, im_g * im_g));
+      }
+    }
+  } else {
+    for (int f = 0; f < F; ++f) {
+      float re = x0 + ((f & 1) ? -xh : xh), im = 0.f;
+      int idx = 0;
+      for (int t = 1; t <= H; ++t) {
+        idx += f;
+        if (idx >= L) idx -= L;
+        const float2 w = tw[idx];
+        re = fmaf(xs[t * Cp + tid], w.x, re);
+        im = fmaf(xs[(L - t) * Cp + tid], w.y, im);
+      }
+      amp[f * amp_pitch + slot] = sqrtf(fmaf(re, re, im * im));
+    }
+  }
+}
+
 template <typename T, int KPL>
 __global__ void __launch_bounds__(KPL * 32)
 spectrum_small_kernel(const T* __restrict__ x, int B, int L, int C, float* __restrict__ med /*[B][F]*/,
@@ -363,67 +430,8 @@ spectrum_small_kernel(const T* __restrict__ x, int B, int L, int C, float* __res
   pdl_wait();   // x is a predecessor's output; the table is not
   __syncthreads();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    const T* xb = x + (size_t)b * L * C;
     if (tid < C) {
-#pragma unroll 4
-      for (int t = 0; t < L; ++t) xs[t * Cp + tid] = to_f32<T>(xb[(size_t)t * C + tid]);
-      for (int t = 1; t <= H; ++t) {                      // fold: rows 1..H hold s, rows L-H..L-1 hold d
-        const float a = xs[t * Cp + tid], z = xs[(L - t) * Cp + tid];
-        xs[t * Cp + tid] = a + z;
-        xs[(L - t) * Cp + tid] = a - z;
-      }
-      const float x0 = xs[tid];
-      const float xh = (L & 1) ? 0.f : xs[(L / 2) * Cp + tid];
-      if ((L & 1) == 0) {
-        // even L: bins f and g = L / 2 - f share their products, cos(2 pi g t / L) = (-1)^t cos(2 pi f t / L) and
-        // sin(2 pi g t / L) = -(-1)^t sin(2 pi f t / L): with the even-t and odd-t partial sums E, O of bin f,
-        //   X[f] = (x0 +- xh + Ec + Oc, -(Es + Os)),   X[g] = (x0 +- xh + Ec - Oc, Es - Os)
-        // -- two bins for the multiply-adds of one (this loop is 60 % of the kernel's instructions)
-        const int half = L / 2;
-        for (int f = 0; 2 * f <= half; ++f) {
-          const int g = half - f;
-          float ec = 0.f, oc = 0.f, es = 0.f, os = 0.f;
-          int idx = 0;
-          int t = 1;
-          for (; t + 1 <= H; t += 2) {
-            idx += f;
-            if (idx >= L) idx -= L;
-            const float2 w1 = tw[idx];
-            oc = fmaf(xs[t * Cp + tid], w1.x, oc);
-            os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
-            idx += f;
-            if (idx >= L) idx -= L;
-            const float2 w2 = tw[idx];
-            ec = fmaf(xs[(t + 1) * Cp + tid], w2.x, ec);
-            es = fmaf(xs[(L - t - 1) * Cp + tid], w2.y, es);
-          }
-          if (t <= H) {                                     // H odd: one more odd step
-            idx += f;
-            if (idx >= L) idx -= L;
-            const float2 w1 = tw[idx];
-            oc = fmaf(xs[t * Cp + tid], w1.x, oc);
-            os = fmaf(xs[(L - t) * Cp + tid], w1.y, os);
-          }
-          const float re_f = (x0 + ((f & 1) ? -xh : xh)) + (ec + oc), im_f = es + os;
-          amp[f * nthr + tid] = sqrtf(fmaf(re_f, re_f, im_f * im_f));
-          if (g != f) {
-            const float re_g = (x0 + ((g & 1) ? -xh : xh)) + (ec - oc), im_g = es - os;
-            amp[g * nthr + tid] = sqrtf(fmaf(re_g, re_g, im_g * im_g));
-          }
-        }
-      } else
-      for (int f = 0; f < F; ++f) {
-        float re = x0 + ((f & 1) ? -xh : xh), im = 0.f;
-        int idx = 0;
-        for (int t = 1; t <= H; ++t) {
-          idx += f;
-          if (idx >= L) idx -= L;
-          const float2 w = tw[idx];
-          re = fmaf(xs[t * Cp + tid], w.x, re);
-          im = fmaf(xs[(L - t) * Cp + tid], w.y, im);
-        }
-        amp[f * nthr + tid] = sqrtf(fmaf(re, re, im * im));
-      }
+      small_window_amps<T>(x + (size_t)b * L * C, L, C, F, H, Cp, tid, tw, xs, amp, nthr, tid);
     } else {
       for (int f = 0; f < F; ++f) amp[f * nthr + tid] = CUDART_INF_F;   // padding sorts last
     }
@@ -451,6 +459,96 @@ spectrum_small_kernel(const T* __restrict__ x, int B, int L, int C, float* __res
     for (int f = tid; f < F; f += nthr) part[(size_t)blockIdx.x * F + f] = sums[f];
 }
 
+// The same for exactly 128 channels, FOUR windows per pass: the warp-cooperative median above is ~250 warp instructions
+// per (window, bin) -- more than half of the kernel once the DFT uses the bin symmetry.  Here a THREAD takes one
+// (window, bin, channel half): it sorts its 64 amplitudes in registers (the bitonic network of the tensor-core spectrum,
+// no shuffles) and the lower median of the 128 is the half-cleaner max_i min(A[i], B[63 - i]) against its partner's
+// sorted half -- ~1/4 of the instructions.  Four windows per pass give 4 F 2 items for the 128 threads (120 at L = 28).
+// The medians are identical to the one-window kernel's; the per-CTA partial sums group the windows differently (another
+// grid), which the second-level sum of the search adds up in a fixed order as before.
+constexpr int kSm4W = 4;
+constexpr int kSm4Pitch = 128 + 16 + 1;   // amplitudes of one (window, bin): channel c at c (c < 64) or c + 16: the two
+                                          // halves and neighbouring bins land on different banks for the strided reads
+template <typename T>
+__global__ void __launch_bounds__(128)
+spectrum_small4_kernel(const T* __restrict__ x, int B, int L, float* __restrict__ med, float* __restrict__ part) {
+  extern __shared__ float ssm[];
+  constexpr int C = 128, nthr = 128, Cp = nthr + 1;
+  const int F = L / 2 + 1, H = (L - 1) / 2;
+  float2* tw = reinterpret_cast<float2*>(ssm);                      // [L]
+  float* xs = ssm + 2 * L;                                          // [L][Cp]
+  float* xch = xs;                                                  // [nthr / 2][65]: the odd halves' sorted lists (+ NaN carrier);
+                                                                    // shares the sample buffer (the phases are barrier-separated)
+  const size_t r0 = (size_t)L * Cp > (size_t)(nthr / 2) * 65 ? (size_t)L * Cp : (size_t)(nthr / 2) * 65;
+  float* amp = xs + r0;                                             // [kSm4W][F][kSm4Pitch]
+  float* medbuf = amp + (size_t)kSm4W * F * kSm4Pitch;              // [kSm4W][F]
+  float* sums = medbuf + kSm4W * F;                                 // [F]
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  for (int k = tid; k < L; k += nthr) {
+    float s, c;
+    sincospif(2.0f * (float)k / (float)L, &s, &c);
+    tw[k] = make_float2(c, s);
+  }
+  for (int f = tid; f < F; f += nthr) sums[f] = 0.f;
+  pdl_wait();
+  __syncthreads();
+  const int n_items = kSm4W * F * 2;
+  for (int b0 = blockIdx.x; b0 < B; b0 += kSm4W * gridDim.x) {
+    // this CTA's next four windows, in the order of the one-window kernel: b0, b0 + grid, b0 + 2 grid, b0 + 3 grid
+    const int slot = tid < 64 ? tid : tid + 16;
+#pragma unroll 1
+    for (int j = 0; j < kSm4W; ++j) {
+      const int b = b0 + j * gridDim.x;
+      if (b < B) small_window_amps<T>(x + (size_t)b * L * C, L, C, F, H, Cp, tid, tw, xs, amp + (size_t)j * F * kSm4Pitch, kSm4Pitch, slot);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int item0 = 0; item0 < n_items; item0 += nthr) {
+      const int item = item0 + tid;
+      const int j = item / (2 * F), rem = item - j * 2 * F, f = rem >> 1, hf = rem & 1;
+      const bool live = item < n_items && b0 + j * (int)gridDim.x < B;
+      float v[64];
+      float carry = 0.f;
+      if (live) {
+        const float* src = amp + (size_t)(j * F + f) * kSm4Pitch + hf * 80;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { v[i] = src[i]; carry += v[i]; }     // amplitudes are >= 0: only a NaN makes the sum NaN
+        sort_regs<64>(v);
+        if (hf) {
+          float* dst = xch + (size_t)(tid >> 1) * 65;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) dst[i] = v[i];
+          dst[64] = carry;
+        }
+      }
+      __syncthreads();
+      if (live && !hf) {
+        const float* other = xch + (size_t)(tid >> 1) * 65;     // partner = tid + 1 (same pair index)
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, fminf(v[i], other[63 - i]));
+        const float oc = other[64];
+        medbuf[j * F + f] = (carry != carry || oc != oc) ? CUDART_NAN_F : mx;     // torch.median propagates NaN
+      }
+      __syncthreads();
+    }
+    for (int f = tid; f < F; f += nthr) {
+      for (int j = 0; j < kSm4W; ++j) {
+        const int b = b0 + j * gridDim.x;
+        if (b < B) {
+          const float m = medbuf[j * F + f];
+          med[(size_t)b * F + f] = m;
+          sums[f] += m;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (part)
+    for (int f = tid; f < F; f += nthr) part[(size_t)blockIdx.x * F + f] = sums[f];
+}
+
 // returns the number of partial rows written (> 0), 0 when the small-window kernel does not apply, < 0 on error
 int spectrum_small_launch(const void* x, int dtype, int B, int L, int C, float* med, float* part, int part_rows_cap,
                           cudaStream_t st) {
@@ -458,6 +556,31 @@ int spectrum_small_launch(const void* x, int dtype, int B, int L, int C, float* 
   if (off || L > 64 || L < 2 || C > 512 || B < 256) return 0;
   const int kpl = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 128 ? 4 : (C <= 256 ? 8 : 16)));
   const int nthr = kpl * 32, F = L / 2 + 1;
+  static const bool no_batch4 = getenv("FLOWTIMES_SMALL_FFT_WARP_MEDIAN") != nullptr;   // A/B switch for profiling
+  if (C == 128 && !no_batch4) {
+    const size_t r0 = (size_t)L * 129 > (size_t)64 * 65 ? (size_t)L * 129 : (size_t)64 * 65;
+    const size_t smem4 = (size_t)(2 * L + r0 + (size_t)kSm4W * F * kSm4Pitch + kSm4W * F + F) * sizeof(float);
+    if (smem4 <= 100 * 1024) {
+      int per_sm = (int)((220 * 1024) / (smem4 + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+      int grid = sm_count() * per_sm;
+      const int quads = (B + kSm4W - 1) / kSm4W;
+      grid = grid > quads ? quads : grid;
+      grid = grid > part_rows_cap ? part_rows_cap : grid;
+      if (grid >= 1) {
+        if (dtype == FTN_F32) {
+          if (ensure_dyn_smem((const void*)spectrum_small4_kernel<float>, smem4)) return -1;
+          spectrum_small4_kernel<float><<<grid, 128, smem4, st>>>((const float*)x, B, L, med, part);
+        } else {
+          if (ensure_dyn_smem((const void*)spectrum_small4_kernel<__nv_bfloat16>, smem4)) return -1;
+          spectrum_small4_kernel<__nv_bfloat16><<<grid, 128, smem4, st>>>((const __nv_bfloat16*)x, B, L, med, part);
+        }
+        count_launch();
+        if (check_cuda(cudaGetLastError(), "spectrum_small4_kernel")) return -1;
+        return grid;
+      }
+    }
+  }
   const size_t smem = (size_t)(2 * L + (size_t)L * (nthr + 1) + (size_t)F * nthr + F) * sizeof(float);
   if (smem > 200 * 1024) return 0;
   int per_sm = (int)((220 * 1024) / (smem + 1024));

@@ -40,36 +40,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ascending sort of N registers: bitonic network whose merges start with the mirrored compare (i, i ^ (size - 1)),
-// so every compare-exchange orders (low index, high index) and the whole thing is FMNMX pairs on fixed registers
-template <int N>
-__device__ __forceinline__ void sort_regs(float (&v)[N]) {
-#pragma unroll
-  for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int j = i ^ (size - 1);
-      if (j > i) {
-        const float lo = fminf(v[i], v[j]), hi = fmaxf(v[i], v[j]);
-        v[i] = lo;
-        v[j] = hi;
-      }
-    }
-#pragma unroll
-    for (int stride = size >> 2; stride > 0; stride >>= 1) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int j = i ^ stride;
-        if (j > i) {
-          const float lo = fminf(v[i], v[j]), hi = fmaxf(v[i], v[j]);
-          v[i] = lo;
-          v[j] = hi;
-        }
-      }
-    }
-  }
-}
-
 // The selection tail (select_tail.cuh) folded into this kernel: the last CTA to finish its medians (ticket in
 // plan->reserved[2], zero on entry, zero again on exit) sums them over the batch, ranks the bins, builds the plan and
 // writes the per-window amplitudes / weights -- the whole period search is ONE launch.
