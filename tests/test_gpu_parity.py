@@ -300,6 +300,27 @@ def test_short_window_fused_block_matches_oracle(periods, B):
         assert torch.equal(one[0], out[b]), f"window {b} depends on its batch neighbours"
 
 
+@pytest.mark.parametrize("L", [30, 47, 64, 65, 96, 97, 129, 200])
+def test_fused_block_window_length_sweep(L):
+    """Elec-class block (C = 128, F = 512, mid = 32, bf16) over window lengths that straddle every geometry switch of the
+    fused route: tc_tail's four-window items (L <= 96) vs one window per item, one / several granules per image, stacked
+    vs single tc_conv4 units (grids of at most 256 padded positions), ragged last tiles.  Periods are drawn at random
+    (seeded) from [1, L - 1] plus the extremes; B = 5 leaves ragged quads and stacks."""
+    wl0 = syn.WORKLOADS["elec"]
+    wl = syn.Workload(**{**wl0.__dict__, "T": L, "B": 5})
+    w = syn.stack_weights(wl, seed=0)
+    g = torch.Generator().manual_seed(L)
+    periods = sorted({1, 2, L - 1, L // 2, *torch.randint(3, L - 1, (3,), generator=g).tolist()})[:6]
+    x = syn.white_features(wl.B, L, wl.d_model, seed=L).to(torch.bfloat16)
+    amps = torch.randn(wl.B, len(periods), generator=g)
+    blk = _make_block(wl, w)
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    torch.cuda.synchronize()
+    tr = orc.timesblock_from_periods(x, periods, amps.to(torch.bfloat16), w, "blocks.0.inception.")
+    assert _rel(out, tr.out) < REL_BF16, f"L={L} periods={periods}"
+
+
 def test_elec_block_with_long_periods_matches_oracle():
     """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
     inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""
