@@ -321,6 +321,27 @@ def test_fused_block_window_length_sweep(L):
     assert _rel(out, tr.out) < REL_BF16, f"L={L} periods={periods}"
 
 
+@pytest.mark.parametrize("L", [40, 96, 130])
+@pytest.mark.parametrize("dname", ["f32", "bf16"])
+def test_narrow_block_window_length_sweep(L, dname):
+    """etth1-class block (C = 64, F = 256, mid = 16) over window lengths with random periods: fp32 on the fp16-pair GEMMs
+    and the row mode of tc_convs (1e-4 bound), bf16 on tc_gemm2 / the row mode / tc_gemm (2e-2)."""
+    wl0 = syn.WORKLOADS["etth1"]
+    wl = syn.Workload(**{**wl0.__dict__, "T": L, "B": 3})
+    dt = torch.float32 if dname == "f32" else torch.bfloat16
+    w = syn.stack_weights(wl, seed=0)
+    g = torch.Generator().manual_seed(100 + L)
+    periods = sorted({1, 2, L - 1, L // 2, *torch.randint(3, L - 1, (3,), generator=g).tolist()})[:6]
+    x = syn.white_features(wl.B, L, wl.d_model, seed=L).to(dt)
+    amps = torch.randn(wl.B, len(periods), generator=g)
+    blk = _make_block(wl, w)
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    torch.cuda.synchronize()
+    tr = orc.timesblock_from_periods(x, periods, amps.to(dt), w, "blocks.0.inception.")
+    assert _rel(out, tr.out) < (REL_F32 if dname == "f32" else REL_BF16), f"L={L} periods={periods}"
+
+
 def test_elec_block_with_long_periods_matches_oracle():
     """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
     inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""
