@@ -342,6 +342,26 @@ def test_narrow_block_window_length_sweep(L, dname):
     assert _rel(out, tr.out) < (REL_F32 if dname == "f32" else REL_BF16), f"L={L} periods={periods}"
 
 
+@pytest.mark.parametrize("wname,dname", [("etth1", "f32"), ("etth1", "bf16"), ("elec", "bf16"), ("elec", "f32")])
+def test_relu_blocks_on_the_tensor_core_routes(wname, dname):
+    """activation = "relu" (timesnet.py:736-747) through the tensor-core routes: the fused bf16 chain (ACT = 1 template
+    instances of tc_mid / tc_tail / tc_gemm2), the fp16-pair fp32 chain and the narrow-branch row mode."""
+    wl0 = syn.WORKLOADS[wname]
+    wl = syn.Workload(**{**wl0.__dict__, "B": 3})
+    dt = torch.float32 if dname == "f32" else torch.bfloat16
+    w = syn.stack_weights(wl, seed=0)
+    periods = [24, 12, 7, wl.T // 2, wl.T - 1]
+    x = syn.white_features(wl.B, wl.T, wl.d_model, seed=3).to(dt)
+    g = torch.Generator().manual_seed(8)
+    amps = torch.randn(wl.B, len(periods), generator=g)
+    blk = _make_block(wl, w, 0, "relu")
+    object.__setattr__(blk, "period_selector", FixedSelector(periods, amps))
+    out = blk(x.cuda())
+    torch.cuda.synchronize()
+    tr = orc.timesblock_from_periods(x, periods, amps.to(dt), w, "blocks.0.inception.", "relu")
+    assert _rel(out, tr.out) < (REL_F32 if dname == "f32" else REL_BF16)
+
+
 def test_elec_block_with_long_periods_matches_oracle():
     """Periods whose padded grid does not fit tc_conv4's shared-memory image (100, 168) take the tc_conv2 fallback
     inside the same launch sequence, both reading the once-per-window first 1x1 stage; short ones stay on tc_conv4."""
